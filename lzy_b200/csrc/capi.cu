@@ -1,0 +1,1393 @@
+// capi.cu — implementation of the C ABI declared in include/lzy_b200.h: slot registry, HBM frame
+// pool, kernel launch policy, CUDA-IPC peers, pinned host ring, fault injection.
+//
+// Reference seams implemented here (see the header for per-function citations):
+//   OutputSlotBackend / InputSlotBackend   lzy/slots/src/main/java/ai/lzy/slots/backends/*.java
+//   InputTransfer.transferChunkTo          lzy/slots/src/main/java/ai/lzy/slots/transfers/InputTransfer.java:8-11
+//   SlotsService slot map                  lzy/slots/src/main/java/ai/lzy/slots/SlotsService.java:21-30
+//
+// There is no CPU data path in this file: without a CUDA device lzyb_init returns LZYB_E_NOGPU and
+// every data call returns LZYB_E_STATE.
+#include <cuda_runtime.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+#include "tma_kernels.cuh"
+
+using namespace lzyb;
+
+namespace {
+
+constexpr uint64_t HEADER_BYTES = 128;
+static_assert(sizeof(lzyb_frame_header_t) == 128, "frame header must be 128 bytes");
+static_assert(sizeof(lzyb_ipc_desc_t) == 256, "ipc descriptor must be 256 bytes");
+constexpr int CTL_SLAB = 8192;        // slots that can be live per device
+constexpr int MBOX_SLAB = 65536;      // mailboxes (pinned, all devices)
+constexpr int TMA_STAGES = 6;
+constexpr int TMA_STAGE_BYTES = 16384;
+constexpr size_t TMA_SMEM = static_cast<size_t>(TMA_STAGES) * TMA_STAGE_BYTES + 2 * TMA_STAGES * sizeof(uint64_t);
+
+thread_local char tl_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_err, sizeof(tl_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(expr)                                                                                  \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(LZYB_E_LOCAL, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+struct DeviceCtx {
+    int ordinal = 0;  // CUDA device ordinal
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;       // library stream (blocking calls, broadcasts)
+    std::mutex mu;
+    std::multimap<size_t, void*> pool;   // free frames by capacity
+    size_t pooled_bytes = 0;
+    SlotCtl* ctl_slab = nullptr;
+    std::vector<int> ctl_free;
+    bool tma_attr_set = false;
+};
+
+struct Slot {
+    lzyb_handle_t handle = 0;
+    std::string id;
+    int dev = 0;                 // index into g.devs
+    uint64_t nbytes = 0;
+    uint64_t cap = 0;            // bytes of the HBM frame (header + padded payload)
+    uint8_t* buf = nullptr;      // header at buf, payload at buf + HEADER_BYTES
+    SlotCtl* ctl = nullptr;
+    int ctl_idx = -1;
+    Mailbox* mbox = nullptr;
+    int mbox_idx = -1;
+    int state = LZYB_ST_EMPTY;
+    bool is_input = false;
+    bool remote = false;         // imported over CUDA IPC: we do not own buf
+    void* ipc_base = nullptr;
+    bool digest_pending = false; // a finalizing launch is in flight (or done) for the payload
+    bool ctl_dirty = false;      // partial sums sit in ctl (mid-transfer)
+    uint64_t delivered = 0;
+    uint64_t digest[2] = {0, 0};
+    uint64_t sum = 0, xr = 0;
+    uint32_t dtype = LZYB_DT_BYTES, ndim = 0;
+    uint64_t shape[LZYB_MAX_DIMS] = {0};
+    unsigned seq = 0;
+    cudaEvent_t last_ev = nullptr;
+    cudaStream_t last_stream = nullptr;
+    int fault_kind = LZYB_FAULT_NONE;
+    uint64_t fault_arg = 0;
+    std::mutex mu;
+    uint8_t* payload() const { return buf + HEADER_BYTES; }
+};
+using SlotPtr = std::shared_ptr<Slot>;
+
+struct RingFrame {
+    uint64_t off, bytes;
+    bool live;
+};
+
+struct Global {
+    bool inited = false;
+    int first = 0;
+    std::vector<std::unique_ptr<DeviceCtx>> devs;
+    std::shared_mutex reg_mu;
+    std::unordered_map<lzyb_handle_t, SlotPtr> slots;
+    std::unordered_map<std::string, lzyb_handle_t> by_id;
+    std::atomic<uint64_t> next_handle{1};
+    Mailbox* mbox_slab = nullptr;
+    std::mutex mbox_mu;
+    std::vector<int> mbox_free;
+    // host ring
+    uint8_t* ring = nullptr;
+    uint64_t ring_bytes = 0, ring_head = 0, ring_used = 0;
+    std::deque<RingFrame> ring_frames;
+    std::mutex ring_mu;
+    // CUDA-IPC mappings are expensive to open and the producer's pool recycles the same frames:
+    // keep every mapping open until shutdown, keyed by (device, 64-byte handle)
+    std::mutex ipc_mu;
+    std::map<std::pair<int, std::string>, void*> ipc_cache;
+    // policy
+    std::atomic<int> engine{0};
+    std::atomic<int> ctas_per_sm{4};
+    std::atomic<int> global_fault{LZYB_FAULT_NONE};
+    // stats
+    std::atomic<uint64_t> st_launch{0}, st_pack{0}, st_pull{0}, st_scan{0}, st_frame{0}, st_bpack{0},
+        st_bpull_l{0}, st_bpull_p{0}, st_bframe{0}, st_h2d{0}, st_d2h{0}, st_live{0}, st_hbm_live{0};
+};
+Global g;
+
+uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+uint64_t frame_capacity(uint64_t nbytes) {
+    uint64_t need = HEADER_BYTES + round_up(nbytes ? nbytes : 16, 256);
+    if (need <= (1ull << 20)) {  // small: power-of-two classes from 4 KiB
+        uint64_t c = 4096;
+        while (c < need) c <<= 1;
+        return c;
+    }
+    return round_up(need, 2ull << 20);  // large: 2 MiB granules (one TLB page each)
+}
+
+SlotPtr find(lzyb_handle_t h) {
+    std::shared_lock<std::shared_mutex> lk(g.reg_mu);
+    auto it = g.slots.find(h);
+    return it == g.slots.end() ? nullptr : it->second;
+}
+
+int alloc_frame(DeviceCtx& d, uint64_t cap, uint8_t** out) {
+    {
+        std::lock_guard<std::mutex> lk(d.mu);
+        auto it = d.pool.find(cap);
+        if (it != d.pool.end()) {
+            *out = static_cast<uint8_t*>(it->second);
+            d.pooled_bytes -= cap;
+            d.pool.erase(it);
+            return LZYB_OK;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e == cudaErrorMemoryAllocation) {  // give pooled frames back to the driver and retry once
+        cudaGetLastError();
+        std::lock_guard<std::mutex> lk(d.mu);
+        for (auto& kv : d.pool) cudaFree(kv.second);
+        d.pool.clear();
+        d.pooled_bytes = 0;
+        e = cudaMalloc(&p, cap);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(LZYB_E_LOCAL, "cudaMalloc(%llu) failed on GPU %d: %s", (unsigned long long)cap, d.ordinal,
+                    cudaGetErrorString(e));
+    }
+    *out = static_cast<uint8_t*>(p);
+    return LZYB_OK;
+}
+
+void free_frame(DeviceCtx& d, uint8_t* p, uint64_t cap) {
+    std::lock_guard<std::mutex> lk(d.mu);
+    d.pool.emplace(cap, p);
+    d.pooled_bytes += cap;
+}
+
+cudaStream_t pick_stream(DeviceCtx& d, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : d.stream; }
+
+void note(Slot& s, cudaStream_t st) {
+    if (!s.last_ev) cudaEventCreateWithFlags(&s.last_ev, cudaEventDisableTiming);
+    cudaEventRecord(s.last_ev, st);
+    s.last_stream = st;
+}
+
+void fill_template(const Slot& s, lzyb_frame_header_t* h) {
+    memset(h, 0, sizeof(*h));
+    memcpy(h->magic, "LZYB200", 8);
+    h->version = LZYB_ABI_VERSION;
+    h->dtype = s.dtype;
+    h->nbytes = s.nbytes;
+    h->ndim = s.ndim;
+    memcpy(h->shape, s.shape, sizeof(h->shape));
+}
+
+int src_alignment(const void* p, uint64_t pitch) {
+    uintptr_t v = reinterpret_cast<uintptr_t>(p) | static_cast<uintptr_t>(pitch);
+    if ((v & 15) == 0) return 16;
+    if ((v & 7) == 0) return 8;
+    if ((v & 3) == 0) return 4;
+    return 1;
+}
+
+template <int ALIGN>
+void launch_flat(const CopyParams& p, bool store, int grid, cudaStream_t st) {
+    if (store)
+        stream_digest_kernel<ALIGN, 8, true><<<grid, 256, 0, st>>>(p);
+    else
+        stream_digest_kernel<ALIGN, 8, false><<<grid, 256, 0, st>>>(p);
+}
+
+// One launch of the streaming family.  Chooses the engine (LDG/STG vectors or TMA bulk) and a
+// grid that is a multiple of the SM count for large chunks (persistent-style walk) and shrinks
+// to the work for small ones.
+int launch_stream(DeviceCtx& d, const CopyParams& p, bool store, cudaStream_t st) {
+    const int align = src_alignment(p.src, 0);
+    const uint64_t nvec = p.nbytes >> 4;
+    int engine = g.engine.load();
+    const bool tma_ok = align == 16 && p.nbytes >= (1ull << 20) && (!store || (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0);
+    if (engine == 0) engine = 1;  // auto: LDG/STG (measured faster end to end)
+    if (engine == 2 && !tma_ok) engine = 1;
+    if (engine == 2) {
+        if (!d.tma_attr_set) {
+            cudaFuncSetAttribute(tma_stream_digest_kernel<TMA_STAGES, TMA_STAGE_BYTES, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
+            cudaFuncSetAttribute(tma_stream_digest_kernel<TMA_STAGES, TMA_STAGE_BYTES, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
+            d.tma_attr_set = true;
+        }
+        uint64_t tiles = p.nbytes / TMA_STAGE_BYTES;
+        int grid = d.sm_count * 2;
+        if ((uint64_t)grid > tiles) grid = (int)(tiles ? tiles : 1);
+        if (store)
+            tma_stream_digest_kernel<TMA_STAGES, TMA_STAGE_BYTES, true><<<grid, TMA_THREADS, TMA_SMEM, st>>>(p);
+        else
+            tma_stream_digest_kernel<TMA_STAGES, TMA_STAGE_BYTES, false><<<grid, TMA_THREADS, TMA_SMEM, st>>>(p);
+    } else {
+        const uint64_t tile = 256ull * 8;
+        uint64_t want = (nvec + tile - 1) / tile;
+        int grid = d.sm_count * g.ctas_per_sm.load();
+        if ((uint64_t)grid > want) grid = (int)(want ? want : 1);
+        switch (align) {
+            case 16: launch_flat<16>(p, store, grid, st); break;
+            case 8: launch_flat<8>(p, store, grid, st); break;
+            case 4: launch_flat<4>(p, store, grid, st); break;
+            default: launch_flat<1>(p, store, grid, st); break;
+        }
+    }
+    g.st_launch++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "kernel launch failed: %s", cudaGetErrorString(e));
+    return LZYB_OK;
+}
+
+void arm_mailbox(Slot& s, CopyParams& p) {
+    s.seq++;
+    s.mbox->status = 0;
+    s.mbox->seq = 0;
+    p.mbox = s.mbox;
+    p.seq = s.seq;
+}
+
+// wait for the finalizing launch of `s` and fold its verdict into the slot; returns the status word
+int harvest(Slot& s) {
+    if (s.last_ev) {
+        cudaError_t e = cudaEventSynchronize(s.last_ev);
+        if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "wait on slot %s failed: %s", s.id.c_str(), cudaGetErrorString(e));
+    }
+    if (s.mbox->seq != s.seq || s.mbox->status == 0)
+        return fail(LZYB_E_LOCAL, "slot %s: finalize did not report (seq %u/%u status %u)", s.id.c_str(), s.mbox->seq,
+                    s.seq, s.mbox->status);
+    s.digest[0] = s.mbox->digest[0];
+    s.digest[1] = s.mbox->digest[1];
+    s.sum = s.mbox->sum;
+    s.xr = s.mbox->xr;
+    s.ctl_dirty = false;
+    return static_cast<int>(s.mbox->status);
+}
+
+int new_slot(const char* slot_id, int gpu, uint64_t nbytes, bool is_input, lzyb_handle_t* out) {
+    if (!g.inited) return fail(LZYB_E_STATE, "lzyb_init has not been called (or found no GPU)");
+    if (!slot_id || !out) return fail(LZYB_E_ARG, "null argument");
+    int di = gpu - g.first;
+    if (di < 0 || di >= (int)g.devs.size()) return fail(LZYB_E_ARG, "GPU %d is not managed by this process", gpu);
+    DeviceCtx& d = *g.devs[di];
+    if (is_input && g.global_fault.load() == LZYB_FAULT_LOCAL_OPEN) {
+        g.global_fault = LZYB_FAULT_NONE;
+        return fail(LZYB_E_LOCAL, "injected fault: cannot open input slot %s", slot_id);
+    }
+    DeviceGuard dg(d.ordinal);
+    auto s = std::make_shared<Slot>();
+    s->id = slot_id;
+    s->dev = di;
+    s->nbytes = nbytes;
+    s->cap = frame_capacity(nbytes);
+    s->is_input = is_input;
+    int rc = alloc_frame(d, s->cap, &s->buf);
+    if (rc != LZYB_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lk(d.mu);
+        if (d.ctl_free.empty()) {
+            free_frame(d, s->buf, s->cap);
+            return fail(LZYB_E_LOCAL, "too many live slots on GPU %d", gpu);
+        }
+        s->ctl_idx = d.ctl_free.back();
+        d.ctl_free.pop_back();
+        s->ctl = d.ctl_slab + s->ctl_idx;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g.mbox_mu);
+        if (g.mbox_free.empty()) return fail(LZYB_E_LOCAL, "out of mailboxes");
+        s->mbox_idx = g.mbox_free.back();
+        g.mbox_free.pop_back();
+        s->mbox = g.mbox_slab + s->mbox_idx;
+        memset((void*)s->mbox, 0, sizeof(Mailbox));
+    }
+    s->handle = g.next_handle++;
+    {
+        std::unique_lock<std::shared_mutex> lk(g.reg_mu);
+        g.slots[s->handle] = s;
+        g.by_id[s->id] = s->handle;
+    }
+    g.st_live++;
+    g.st_hbm_live += s->cap;
+    *out = s->handle;
+    return LZYB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lzyb_abi_version(void) { return LZYB_ABI_VERSION; }
+const char* lzyb_last_error(void) { return tl_err; }
+int lzyb_is_initialized(void) { return g.inited ? 1 : 0; }
+int lzyb_device_count(void) { return g.inited ? (int)g.devs.size() : 0; }
+
+const char* lzyb_strerror(int code) {
+    switch (code) {
+        case LZYB_OK: return "ok";
+        case LZYB_EOF: return "end of stream";
+        case LZYB_E_PEER: return "peer fault (ReadException)";
+        case LZYB_E_LOCAL: return "local fault (IOException)";
+        case LZYB_E_ARG: return "bad argument";
+        case LZYB_E_STATE: return "wrong state";
+        case LZYB_E_NOGPU: return "no CUDA device";
+        case LZYB_E_NOT_FOUND: return "NOT_FOUND";
+        case LZYB_E_PRECONDITION: return "FAILED_PRECONDITION";
+        case LZYB_E_UNAVAILABLE: return "UNAVAILABLE";
+        case LZYB_E_INTERNAL: return "INTERNAL";
+        case LZYB_E_UNIMPLEMENTED: return "UNIMPLEMENTED";
+        case LZYB_E_INVALID: return "INVALID_ARGUMENT";
+        case LZYB_E_EXISTS: return "ALREADY_EXISTS";
+        default: return "unknown";
+    }
+}
+
+int lzyb_init(int first_gpu, int n_gpus, uint64_t host_ring_bytes) {
+    if (g.inited) return LZYB_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(LZYB_E_NOGPU, "no CUDA device visible (%s); liblzy_b200 has no CPU fallback",
+                    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    }
+    if (first_gpu < 0 || first_gpu >= count) return fail(LZYB_E_ARG, "first_gpu %d out of range (%d devices)", first_gpu, count);
+    if (n_gpus <= 0 || first_gpu + n_gpus > count) n_gpus = count - first_gpu;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    g.first = first_gpu;
+    for (int i = 0; i < n_gpus; ++i) {
+        auto d = std::make_unique<DeviceCtx>();
+        d->ordinal = first_gpu + i;
+        CU(cudaSetDevice(d->ordinal));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, d->ordinal));
+        if (prop.major < 10) {
+            return fail(LZYB_E_NOGPU, "GPU %d is sm_%d%d; this library carries sm_100a code only", d->ordinal, prop.major,
+                        prop.minor);
+        }
+        d->sm_count = prop.multiProcessorCount;
+        CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&d->ctl_slab, sizeof(SlotCtl) * CTL_SLAB));
+        CU(cudaMemset(d->ctl_slab, 0, sizeof(SlotCtl) * CTL_SLAB));
+        for (int k = CTL_SLAB - 1; k >= 0; --k) d->ctl_free.push_back(k);
+        g.devs.push_back(std::move(d));
+    }
+    // all-to-all peer access between the managed devices (NVSwitch: every pair is one hop)
+    for (int i = 0; i < n_gpus; ++i) {
+        cudaSetDevice(first_gpu + i);
+        for (int j = 0; j < n_gpus; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, first_gpu + i, first_gpu + j);
+            if (can) {
+                cudaError_t pe = cudaDeviceEnablePeerAccess(first_gpu + j, 0);
+                if (pe != cudaSuccess) cudaGetLastError();  // already enabled (e.g. by torch) is fine
+            }
+        }
+    }
+    cudaSetDevice(first_gpu);
+    CU(cudaHostAlloc((void**)&g.mbox_slab, sizeof(Mailbox) * MBOX_SLAB, cudaHostAllocPortable | cudaHostAllocMapped));
+    memset((void*)g.mbox_slab, 0, sizeof(Mailbox) * MBOX_SLAB);
+    for (int k = MBOX_SLAB - 1; k >= 0; --k) g.mbox_free.push_back(k);
+    g.ring_bytes = host_ring_bytes ? round_up(host_ring_bytes, 4096) : (64ull << 20);
+    CU(cudaHostAlloc((void**)&g.ring, g.ring_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    cudaSetDevice(prev);
+    g.inited = true;
+    return LZYB_OK;
+}
+
+int lzyb_shutdown(void) {
+    if (!g.inited) return LZYB_OK;
+    std::vector<lzyb_handle_t> hs;
+    {
+        std::shared_lock<std::shared_mutex> lk(g.reg_mu);
+        for (auto& kv : g.slots) hs.push_back(kv.first);
+    }
+    for (auto h : hs) lzyb_slot_close(h);
+    {
+        std::lock_guard<std::mutex> lk(g.ipc_mu);
+        for (auto& kv : g.ipc_cache) {
+            cudaSetDevice(kv.first.first);
+            cudaIpcCloseMemHandle(kv.second);
+        }
+        g.ipc_cache.clear();
+    }
+    for (auto& d : g.devs) {
+        cudaSetDevice(d->ordinal);
+        cudaDeviceSynchronize();
+        for (auto& kv : d->pool) cudaFree(kv.second);
+        d->pool.clear();
+        cudaFree(d->ctl_slab);
+        cudaStreamDestroy(d->stream);
+    }
+    g.devs.clear();
+    cudaFreeHost((void*)g.mbox_slab);
+    cudaFreeHost(g.ring);
+    g.mbox_slab = nullptr;
+    g.ring = nullptr;
+    g.mbox_free.clear();
+    g.ring_frames.clear();
+    g.ring_head = g.ring_used = 0;
+    g.inited = false;
+    return LZYB_OK;
+}
+
+int lzyb_slot_create(const char* slot_id, int gpu, uint64_t nbytes, lzyb_handle_t* out) {
+    return new_slot(slot_id, gpu, nbytes, false, out);
+}
+int lzyb_input_open(const char* slot_id, int gpu, uint64_t nbytes, lzyb_handle_t* out) {
+    return new_slot(slot_id, gpu, nbytes, true, out);
+}
+
+int lzyb_slot_find(const char* slot_id, lzyb_handle_t* out) {
+    if (!slot_id || !out) return fail(LZYB_E_ARG, "null argument");
+    std::shared_lock<std::shared_mutex> lk(g.reg_mu);
+    auto it = g.by_id.find(slot_id);
+    if (it == g.by_id.end()) return fail(LZYB_E_NOT_FOUND, "Slot not found: %s", slot_id);
+    *out = it->second;
+    return LZYB_OK;
+}
+
+int lzyb_slot_device_ptr(lzyb_handle_t h, void** dptr) {
+    auto s = find(h);
+    if (!s || !dptr) return fail(LZYB_E_ARG, "unknown slot handle %llu", (unsigned long long)h);
+    if (s->state == LZYB_ST_CLOSED) return fail(LZYB_E_STATE, "slot %s is closed", s->id.c_str());
+    *dptr = s->payload();
+    return LZYB_OK;
+}
+
+int lzyb_slot_set_meta(lzyb_handle_t h, uint32_t dtype, uint32_t ndim, const uint64_t* shape) {
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    if (ndim > LZYB_MAX_DIMS) return fail(LZYB_E_ARG, "ndim %u > %d", ndim, LZYB_MAX_DIMS);
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state != LZYB_ST_EMPTY || s->digest_pending) return fail(LZYB_E_STATE, "slot %s: meta must be set before data", s->id.c_str());
+    s->dtype = dtype;
+    s->ndim = ndim;
+    memset(s->shape, 0, sizeof(s->shape));
+    for (uint32_t i = 0; i < ndim; ++i) s->shape[i] = shape[i];
+    return LZYB_OK;
+}
+
+static int pack_common(lzyb_handle_t h, const void* src, uint64_t rows, uint64_t row_bytes, uint64_t pitch, void* stream) {
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->is_input || s->remote) return fail(LZYB_E_STATE, "slot %s is not a local output slot", s->id.c_str());
+    if (s->state != LZYB_ST_EMPTY || s->digest_pending) return fail(LZYB_E_STATE, "slot %s already holds data", s->id.c_str());
+    const uint64_t nbytes = rows ? rows * row_bytes : row_bytes;
+    if (nbytes != s->nbytes) return fail(LZYB_E_ARG, "slot %s holds %llu bytes, pack of %llu", s->id.c_str(),
+                                         (unsigned long long)s->nbytes, (unsigned long long)nbytes);
+    if (nbytes && !src) return fail(LZYB_E_ARG, "null source");
+    DeviceCtx& d = *g.devs[s->dev];
+    DeviceGuard dg(d.ordinal);
+    cudaStream_t st = pick_stream(d, stream);
+    CopyParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = static_cast<const uint8_t*>(src);
+    p.dst = s->payload();
+    p.nbytes = nbytes;
+    p.ctl = s->ctl;
+    p.dst_hdr = reinterpret_cast<lzyb_frame_header_t*>(s->buf);
+    p.total_nbytes = s->nbytes;
+    p.fin = FIN_PUBLISH;
+    fill_template(*s, &p.hdr_template);
+    arm_mailbox(*s, p);
+    int rc;
+    if (rows && pitch != row_bytes) {
+        if (row_bytes & 15) return fail(LZYB_E_ARG, "2-D pack needs row_bytes %% 16 == 0 (got %llu)", (unsigned long long)row_bytes);
+        p.rows = rows;
+        p.row_bytes = row_bytes;
+        p.src_pitch = pitch;
+        const int align = src_alignment(src, pitch);
+        const uint64_t tile = 256ull * 4;
+        uint64_t items = rows * ((row_bytes / 16 + tile - 1) / tile);
+        int grid = d.sm_count * g.ctas_per_sm.load();
+        if ((uint64_t)grid > items) grid = (int)(items ? items : 1);
+        switch (align) {
+            case 16: gather2d_digest_kernel<16, 4><<<grid, 256, 0, st>>>(p); break;
+            case 8: gather2d_digest_kernel<8, 4><<<grid, 256, 0, st>>>(p); break;
+            case 4: gather2d_digest_kernel<4, 4><<<grid, 256, 0, st>>>(p); break;
+            default: gather2d_digest_kernel<1, 4><<<grid, 256, 0, st>>>(p); break;
+        }
+        g.st_launch++;
+        cudaError_t e = cudaGetLastError();
+        rc = e == cudaSuccess ? LZYB_OK : fail(LZYB_E_LOCAL, "gather launch failed: %s", cudaGetErrorString(e));
+    } else {
+        rc = launch_stream(d, p, true, st);
+    }
+    if (rc != LZYB_OK) return rc;
+    g.st_pack++;
+    g.st_bpack += nbytes;
+    s->digest_pending = true;
+    note(*s, st);
+    return LZYB_OK;
+}
+
+int lzyb_slot_pack(lzyb_handle_t h, const void* src_dptr, uint64_t nbytes, void* stream) {
+    return pack_common(h, src_dptr, 0, nbytes, nbytes, stream);
+}
+int lzyb_slot_pack_2d(lzyb_handle_t h, const void* src_dptr, uint64_t rows, uint64_t row_bytes, uint64_t src_pitch, void* stream) {
+    if (rows == 0) return pack_common(h, src_dptr, 0, 0, 0, stream);
+    return pack_common(h, src_dptr, rows, row_bytes, src_pitch, stream);
+}
+
+static int scan_publish(Slot& s, DeviceCtx& d, cudaStream_t st) {
+    CopyParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = s.payload();
+    p.dst = nullptr;
+    p.nbytes = s.nbytes;
+    p.ctl = s.ctl;
+    p.dst_hdr = reinterpret_cast<lzyb_frame_header_t*>(s.buf);
+    p.total_nbytes = s.nbytes;
+    p.fin = FIN_PUBLISH;
+    fill_template(s, &p.hdr_template);
+    arm_mailbox(s, p);
+    int rc = launch_stream(d, p, false, st);
+    if (rc != LZYB_OK) return rc;
+    g.st_scan++;
+    s.digest_pending = true;
+    note(s, st);
+    return LZYB_OK;
+}
+
+int lzyb_slot_pack_host(lzyb_handle_t h, const void* src_host, uint64_t nbytes, void* stream) {
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->is_input || s->remote) return fail(LZYB_E_STATE, "slot %s is not a local output slot", s->id.c_str());
+    if (s->state != LZYB_ST_EMPTY || s->digest_pending) return fail(LZYB_E_STATE, "slot %s already holds data", s->id.c_str());
+    if (nbytes != s->nbytes) return fail(LZYB_E_ARG, "slot %s holds %llu bytes, pack of %llu", s->id.c_str(),
+                                         (unsigned long long)s->nbytes, (unsigned long long)nbytes);
+    DeviceCtx& d = *g.devs[s->dev];
+    DeviceGuard dg(d.ordinal);
+    cudaStream_t st = pick_stream(d, stream);
+    if (nbytes) CU(cudaMemcpyAsync(s->payload(), src_host, nbytes, cudaMemcpyHostToDevice, st));
+    g.st_h2d += nbytes;
+    return scan_publish(*s, d, st);
+}
+
+int lzyb_slot_commit(lzyb_handle_t h, uint64_t digest_out[2], void* stream) {
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state == LZYB_ST_CLOSED || s->state == LZYB_ST_FAILED) return fail(LZYB_E_STATE, "slot %s is closed/failed", s->id.c_str());
+    if (s->state != LZYB_ST_READY) {
+        if (s->is_input) return fail(LZYB_E_STATE, "slot %s is an input slot; finish the transfer instead", s->id.c_str());
+        DeviceCtx& d = *g.devs[s->dev];
+        DeviceGuard dg(d.ordinal);
+        if (!s->digest_pending) {  // payload was written in place through lzyb_slot_device_ptr
+            int rc = scan_publish(*s, d, pick_stream(d, stream));
+            if (rc != LZYB_OK) return rc;
+        }
+        int st = harvest(*s);
+        if (st < 0) return st;
+        if (st != 1) return fail(LZYB_E_LOCAL, "slot %s: unexpected finalize status %d", s->id.c_str(), st);
+        s->state = LZYB_ST_READY;
+        s->delivered = s->nbytes;
+    }
+    if (digest_out) {
+        digest_out[0] = s->digest[0];
+        digest_out[1] = s->digest[1];
+    }
+    return LZYB_OK;
+}
+
+int64_t lzyb_slot_read(lzyb_handle_t h, uint64_t offset, void* dst_host, uint64_t len) {
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state != LZYB_ST_READY) return fail(LZYB_E_STATE, "slot %s is not ready", s->id.c_str());
+    if (s->is_input) return fail(LZYB_E_UNIMPLEMENTED, "unexpected `read` call on input slot %s", s->id.c_str());
+    if (offset >= s->nbytes) return LZYB_EOF;
+    uint64_t n = s->nbytes - offset;
+    if (n > len) n = len;
+    DeviceCtx& d = *g.devs[s->dev];
+    DeviceGuard dg(d.ordinal);
+    CU(cudaMemcpyAsync(dst_host, s->payload() + offset, n, cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    g.st_d2h += n;
+    return (int64_t)n;
+}
+
+int lzyb_copy_to_host(lzyb_handle_t h, uint64_t offset, void* dst_host, uint64_t len, void* stream) {
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state == LZYB_ST_CLOSED) return fail(LZYB_E_STATE, "slot %s is closed", s->id.c_str());
+    if (offset + len > s->nbytes) return fail(LZYB_E_ARG, "range beyond payload");
+    DeviceCtx& d = *g.devs[s->dev];
+    DeviceGuard dg(d.ordinal);
+    cudaStream_t st = pick_stream(d, stream);
+    if (len) CU(cudaMemcpyAsync(dst_host, s->payload() + offset, len, cudaMemcpyDeviceToHost, st));
+    if (!stream) CU(cudaStreamSynchronize(st));
+    g.st_d2h += len;
+    return LZYB_OK;
+}
+
+int lzyb_slot_info(lzyb_handle_t h, lzyb_slot_info_t* out) {
+    auto s = find(h);
+    if (!s || !out) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    memset(out, 0, sizeof(*out));
+    out->nbytes = s->nbytes;
+    out->gpu = g.devs[s->dev]->ordinal;
+    out->state = s->state;
+    out->is_input = s->is_input;
+    out->is_remote = s->remote;
+    out->delivered = s->delivered;
+    out->digest[0] = s->digest[0];
+    out->digest[1] = s->digest[1];
+    out->dtype = s->dtype;
+    out->ndim = s->ndim;
+    memcpy(out->shape, s->shape, sizeof(out->shape));
+    return LZYB_OK;
+}
+
+int lzyb_slot_header(lzyb_handle_t h, lzyb_frame_header_t* out) {
+    auto s = find(h);
+    if (!s || !out) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state == LZYB_ST_CLOSED) return fail(LZYB_E_STATE, "slot %s is closed", s->id.c_str());
+    DeviceCtx& d = *g.devs[s->dev];
+    DeviceGuard dg(d.ordinal);
+    if (s->last_ev) CU(cudaEventSynchronize(s->last_ev));
+    CU(cudaMemcpy(out, s->buf, sizeof(*out), cudaMemcpyDeviceToHost));
+    return LZYB_OK;
+}
+
+int lzyb_slot_close(lzyb_handle_t h) {
+    SlotPtr s;
+    {
+        std::unique_lock<std::shared_mutex> lk(g.reg_mu);
+        auto it = g.slots.find(h);
+        if (it == g.slots.end()) return LZYB_OK;  // idempotent (InputSlot.close, InputSlot.java:110-113)
+        s = it->second;
+        g.slots.erase(it);
+        auto bi = g.by_id.find(s->id);
+        if (bi != g.by_id.end() && bi->second == h) g.by_id.erase(bi);
+    }
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceCtx& d = *g.devs[s->dev];
+    DeviceGuard dg(d.ordinal);
+    if (s->last_ev) {
+        cudaEventSynchronize(s->last_ev);  // cancel = let in-flight work drain before the frame is reused
+        cudaEventDestroy(s->last_ev);
+        s->last_ev = nullptr;
+    }
+    if (s->remote) {
+        // the mapping stays in g.ipc_cache (closed at shutdown)
+    } else if (s->buf) {
+        free_frame(d, s->buf, s->cap);
+        g.st_hbm_live -= s->cap;
+    }
+    if (s->ctl_idx >= 0) {
+        if (s->ctl_dirty) cudaMemset(s->ctl, 0, sizeof(SlotCtl));
+        std::lock_guard<std::mutex> dl(d.mu);
+        d.ctl_free.push_back(s->ctl_idx);
+    }
+    if (s->mbox_idx >= 0) {
+        std::lock_guard<std::mutex> ml(g.mbox_mu);
+        g.mbox_free.push_back(s->mbox_idx);
+    }
+    s->buf = nullptr;
+    s->state = LZYB_ST_CLOSED;
+    g.st_live--;
+    return LZYB_OK;
+}
+
+// ---- transfers -------------------------------------------------------------------------------
+
+int64_t lzyb_transfer_chunk(lzyb_handle_t dst_h, lzyb_handle_t src_h, uint64_t offset, uint64_t max_len, void* stream) {
+    auto dst = find(dst_h);
+    auto src = find(src_h);
+    if (!dst || !src) return fail(LZYB_E_ARG, "unknown slot handle");
+    if (dst == src) return fail(LZYB_E_ARG, "source and sink are the same slot");
+    std::scoped_lock lk(dst->mu, src->mu);
+    if (!dst->is_input) return fail(LZYB_E_STATE, "slot %s is not an input slot", dst->id.c_str());
+    if (dst->state == LZYB_ST_CLOSED || dst->state == LZYB_ST_FAILED) return fail(LZYB_E_LOCAL, "sink %s already closed", dst->id.c_str());
+    if (dst->state == LZYB_ST_READY) return LZYB_EOF;
+    if (src->state != LZYB_ST_READY) return fail(LZYB_E_PEER, "peer %s has no complete data", src->id.c_str());
+    if (src->nbytes != dst->nbytes) return fail(LZYB_E_PEER, "peer %s holds %llu bytes, sink expects %llu", src->id.c_str(),
+                                                (unsigned long long)src->nbytes, (unsigned long long)dst->nbytes);
+    if (offset != dst->delivered) return fail(LZYB_E_ARG, "offset %llu != delivered %llu (transferChunkTo repositions the sink)",
+                                             (unsigned long long)offset, (unsigned long long)dst->delivered);
+    if (dst->digest_pending) return LZYB_EOF;  // final chunk already queued
+    if (offset == dst->nbytes && dst->nbytes != 0) return LZYB_EOF;
+    uint64_t len = dst->nbytes - offset;
+    if (max_len < len) {
+        len = max_len & ~15ull;
+        if (len == 0) return fail(LZYB_E_ARG, "max_len %llu is below the 16-byte transfer granule", (unsigned long long)max_len);
+    }
+    // fault injection at the backend seam (FailingInputStream, SlotsTest.java:914-943)
+    if (src->fault_kind == LZYB_FAULT_PEER_AFTER) {
+        if (offset >= src->fault_arg) return fail(LZYB_E_PEER, "injected fault: Cannot read from slot peer %s", src->id.c_str());
+        if (offset + len > src->fault_arg) len = (src->fault_arg - offset) & ~15ull;
+        if (len == 0) return fail(LZYB_E_PEER, "injected fault: Cannot read from slot peer %s", src->id.c_str());
+    }
+    DeviceCtx& d = *g.devs[dst->dev];
+    DeviceGuard dg(d.ordinal);
+    cudaStream_t st = pick_stream(d, stream);
+    const bool last = offset + len == dst->nbytes;
+    CopyParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = src->payload() + offset;
+    p.dst = dst->payload() + offset;
+    p.nbytes = len;
+    p.word_base = offset >> 3;
+    p.ctl = dst->ctl;
+    p.total_nbytes = dst->nbytes;
+    p.fin = FIN_NONE;
+    if (last) {
+        p.fin = FIN_VERIFY;
+        p.expect[0] = src->digest[0];
+        p.expect[1] = src->digest[1];
+        p.dst_hdr = reinterpret_cast<lzyb_frame_header_t*>(dst->buf);
+        dst->dtype = src->dtype;
+        dst->ndim = src->ndim;
+        memcpy(dst->shape, src->shape, sizeof(dst->shape));
+        fill_template(*dst, &p.hdr_template);
+        arm_mailbox(*dst, p);
+    }
+    // the producer's payload must be final on this stream's timeline
+    if (src->last_ev && src->last_stream != st) cudaStreamWaitEvent(st, src->last_ev, 0);
+    int rc = launch_stream(d, p, true, st);
+    if (rc != LZYB_OK) return rc;
+    g.st_pull++;
+    if (src->dev == dst->dev && !src->remote)
+        g.st_bpull_l += len;
+    else
+        g.st_bpull_p += len;
+    dst->delivered += len;
+    dst->state = LZYB_ST_FILLING;
+    dst->ctl_dirty = !last;
+    if (last) dst->digest_pending = true;
+    note(*dst, st);
+    if (!stream) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "transfer failed: %s", cudaGetErrorString(e));
+    }
+    return (int64_t)len;
+}
+
+static int input_reset_locked(Slot& s) {
+    DeviceCtx& d = *g.devs[s.dev];
+    DeviceGuard dg(d.ordinal);
+    if (s.last_ev) cudaEventSynchronize(s.last_ev);
+    if (s.ctl_dirty) {
+        CU(cudaMemset(s.ctl, 0, sizeof(SlotCtl)));
+        s.ctl_dirty = false;
+    }
+    s.delivered = 0;
+    s.digest_pending = false;
+    s.state = LZYB_ST_EMPTY;
+    return LZYB_OK;
+}
+
+static int finish_common(Slot& dst, const uint64_t expect[2], const Slot* src, void* stream) {
+    if (!dst.is_input) return fail(LZYB_E_STATE, "slot %s is not an input slot", dst.id.c_str());
+    if (dst.state == LZYB_ST_READY) return LZYB_OK;
+    if (dst.state == LZYB_ST_CLOSED || dst.state == LZYB_ST_FAILED) return fail(LZYB_E_LOCAL, "sink %s already closed", dst.id.c_str());
+    if (dst.delivered != dst.nbytes) return fail(LZYB_E_STATE, "slot %s: %llu of %llu bytes delivered", dst.id.c_str(),
+                                                 (unsigned long long)dst.delivered, (unsigned long long)dst.nbytes);
+    DeviceCtx& d = *g.devs[dst.dev];
+    DeviceGuard dg(d.ordinal);
+    if (!dst.digest_pending) {  // zero-byte payload or host-fed chunks: finalize on its own
+        cudaStream_t st = pick_stream(d, stream);
+        CopyParams p;
+        memset(&p, 0, sizeof(p));
+        p.ctl = dst.ctl;
+        p.total_nbytes = dst.nbytes;
+        p.fin = FIN_VERIFY;
+        p.expect[0] = expect[0];
+        p.expect[1] = expect[1];
+        p.dst_hdr = reinterpret_cast<lzyb_frame_header_t*>(dst.buf);
+        if (src) {
+            dst.dtype = src->dtype;
+            dst.ndim = src->ndim;
+            memcpy(dst.shape, src->shape, sizeof(dst.shape));
+        }
+        fill_template(dst, &p.hdr_template);
+        arm_mailbox(dst, p);
+        finalize_kernel<<<1, 32, 0, st>>>(p);
+        g.st_launch++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "finalize launch failed: %s", cudaGetErrorString(e));
+        dst.digest_pending = true;
+        note(dst, st);
+    }
+    int st = harvest(dst);
+    if (st < 0) return st;
+    if (st == 2) {
+        input_reset_locked(dst);
+        return fail(LZYB_E_PEER, "digest mismatch on slot %s: delivered bytes differ from what the producer committed",
+                    dst.id.c_str());
+    }
+    dst.state = LZYB_ST_READY;
+    return LZYB_OK;
+}
+
+int lzyb_input_finish(lzyb_handle_t dst_h, lzyb_handle_t src_h, void* stream) {
+    auto dst = find(dst_h);
+    auto src = find(src_h);
+    if (!dst || !src) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::scoped_lock lk(dst->mu, src->mu);
+    return finish_common(*dst, src->digest, src.get(), stream);
+}
+
+int lzyb_input_finish_expect(lzyb_handle_t dst_h, const uint64_t digest[2], void* stream) {
+    auto dst = find(dst_h);
+    if (!dst || !digest) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(dst->mu);
+    return finish_common(*dst, digest, nullptr, stream);
+}
+
+int64_t lzyb_input_write_host(lzyb_handle_t dst_h, uint64_t offset, const void* src_host, uint64_t len, void* stream) {
+    auto dst = find(dst_h);
+    if (!dst) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(dst->mu);
+    if (!dst->is_input) return fail(LZYB_E_STATE, "slot %s is not an input slot", dst->id.c_str());
+    if (dst->state == LZYB_ST_CLOSED || dst->state == LZYB_ST_FAILED) return fail(LZYB_E_LOCAL, "sink %s already closed", dst->id.c_str());
+    if (offset != dst->delivered) return fail(LZYB_E_ARG, "offset %llu != delivered %llu", (unsigned long long)offset,
+                                             (unsigned long long)dst->delivered);
+    if (offset == dst->nbytes) return LZYB_EOF;
+    if (offset + len > dst->nbytes) len = dst->nbytes - offset;
+    if (offset + len != dst->nbytes && (len & 15)) return fail(LZYB_E_ARG, "intermediate chunks must be multiples of 16 bytes");
+    DeviceCtx& d = *g.devs[dst->dev];
+    DeviceGuard dg(d.ordinal);
+    cudaStream_t st = pick_stream(d, stream);
+    CU(cudaMemcpyAsync(dst->payload() + offset, src_host, len, cudaMemcpyHostToDevice, st));
+    g.st_h2d += len;
+    // digest the landed bytes in place (scan), accumulating into the slot's partials
+    CopyParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = dst->payload() + offset;
+    p.nbytes = len;
+    p.word_base = offset >> 3;
+    p.ctl = dst->ctl;
+    p.total_nbytes = dst->nbytes;
+    p.fin = FIN_NONE;
+    int rc = launch_stream(d, p, false, st);
+    if (rc != LZYB_OK) return rc;
+    g.st_scan++;
+    dst->delivered += len;
+    dst->state = LZYB_ST_FILLING;
+    dst->ctl_dirty = true;
+    note(*dst, st);
+    if (!stream) CU(cudaStreamSynchronize(st));
+    return (int64_t)len;
+}
+
+int lzyb_input_to_output(lzyb_handle_t h) {
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state == LZYB_ST_CLOSED) return fail(LZYB_E_STATE, "Already closed");
+    if (!s->is_input) return LZYB_OK;
+    if (s->state != LZYB_ST_READY) return fail(LZYB_E_STATE, "slot %s is not ready", s->id.c_str());
+    s->is_input = false;
+    return LZYB_OK;
+}
+
+int lzyb_input_reset(lzyb_handle_t h) {
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (!s->is_input) return fail(LZYB_E_STATE, "slot %s is not an input slot", s->id.c_str());
+    return input_reset_locked(*s);
+}
+
+// ---- CUDA IPC peers --------------------------------------------------------------------------
+
+int lzyb_slot_export(lzyb_handle_t h, lzyb_ipc_desc_t* out) {
+    auto s = find(h);
+    if (!s || !out) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->state != LZYB_ST_READY) return fail(LZYB_E_STATE, "slot %s is not committed", s->id.c_str());
+    if (s->remote) return fail(LZYB_E_STATE, "slot %s is itself an import", s->id.c_str());
+    DeviceCtx& d = *g.devs[s->dev];
+    DeviceGuard dg(d.ordinal);
+    memset(out, 0, sizeof(*out));
+    cudaIpcMemHandle_t mh;
+    CU(cudaIpcGetMemHandle(&mh, s->buf));
+    static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out->ipc_handle, &mh, 64);
+    out->buffer_bytes = s->cap;
+    out->nbytes = s->nbytes;
+    out->gpu = d.ordinal;
+    out->pid = (int32_t)getpid();
+    out->digest[0] = s->digest[0];
+    out->digest[1] = s->digest[1];
+    out->sum = s->sum;
+    out->xr = s->xr;
+    out->dtype = s->dtype;
+    out->ndim = s->ndim;
+    memcpy(out->shape, s->shape, sizeof(out->shape));
+    return LZYB_OK;
+}
+
+int lzyb_peer_import(const lzyb_ipc_desc_t* desc, int onto_gpu, lzyb_handle_t* out) {
+    if (!g.inited) return fail(LZYB_E_STATE, "lzyb_init has not been called");
+    if (!desc || !out) return fail(LZYB_E_ARG, "null argument");
+    int di = onto_gpu - g.first;
+    if (di < 0 || di >= (int)g.devs.size()) return fail(LZYB_E_ARG, "GPU %d is not managed by this process", onto_gpu);
+    if (desc->pid == (int32_t)getpid()) return fail(LZYB_E_ARG, "descriptor comes from this process; use the slot handle");
+    DeviceCtx& d = *g.devs[di];
+    DeviceGuard dg(d.ordinal);
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, desc->ipc_handle, 64);
+    void* base = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g.ipc_mu);
+        auto key = std::make_pair(d.ordinal, std::string(reinterpret_cast<const char*>(desc->ipc_handle), 64));
+        auto it = g.ipc_cache.find(key);
+        if (it != g.ipc_cache.end()) {
+            base = it->second;
+        } else {
+            cudaError_t e = cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(LZYB_E_PEER, "cannot map peer frame (pid %d gpu %d): %s", desc->pid, desc->gpu, cudaGetErrorString(e));
+            }
+            g.ipc_cache.emplace(key, base);
+        }
+    }
+    auto s = std::make_shared<Slot>();
+    char name[64];
+    snprintf(name, sizeof(name), "ipc:%d:%d:%p", desc->pid, desc->gpu, base);
+    s->id = name;
+    s->dev = di;
+    s->nbytes = desc->nbytes;
+    s->cap = desc->buffer_bytes;
+    s->buf = static_cast<uint8_t*>(base);
+    s->ipc_base = base;
+    s->remote = true;
+    s->state = LZYB_ST_READY;
+    s->delivered = desc->nbytes;
+    s->digest[0] = desc->digest[0];
+    s->digest[1] = desc->digest[1];
+    s->sum = desc->sum;
+    s->xr = desc->xr;
+    s->dtype = desc->dtype;
+    s->ndim = desc->ndim;
+    memcpy(s->shape, desc->shape, sizeof(s->shape));
+    s->handle = g.next_handle++;
+    {
+        std::unique_lock<std::shared_mutex> lk(g.reg_mu);
+        g.slots[s->handle] = s;
+    }
+    g.st_live++;
+    *out = s->handle;
+    return LZYB_OK;
+}
+
+// ---- fan-out: chunk-pipelined pull chain -------------------------------------------------------
+
+int lzyb_broadcast(lzyb_handle_t src_h, const lzyb_handle_t* dsts, int n, uint64_t chunk_bytes) {
+    if (n <= 0 || !dsts) return fail(LZYB_E_ARG, "no consumers");
+    if (chunk_bytes == 0) chunk_bytes = 32ull << 20;
+    chunk_bytes = round_up(chunk_bytes, 4096);
+    auto src = find(src_h);
+    if (!src) return fail(LZYB_E_ARG, "unknown source handle");
+    const uint64_t total = src->nbytes;
+    std::vector<SlotPtr> chain;
+    for (int k = 0; k < n; ++k) {
+        auto s = find(dsts[k]);
+        if (!s) return fail(LZYB_E_ARG, "unknown consumer handle #%d", k);
+        chain.push_back(s);
+    }
+    // stage k pulls chunk c from stage k-1 as soon as that chunk has landed there: every launch
+    // goes to its own GPU's library stream and waits on the event of the upstream launch.
+    const uint64_t nchunks = total ? (total + chunk_bytes - 1) / chunk_bytes : 0;
+    std::vector<std::vector<cudaEvent_t>> ev(n, std::vector<cudaEvent_t>(nchunks, nullptr));
+    int rc = LZYB_OK;
+    for (uint64_t c = 0; c < nchunks && rc == LZYB_OK; ++c) {
+        const uint64_t off = c * chunk_bytes;
+        const uint64_t len = (off + chunk_bytes > total) ? total - off : chunk_bytes;
+        for (int k = 0; k < n; ++k) {
+            DeviceCtx& d = *g.devs[chain[k]->dev];
+            DeviceGuard dg(d.ordinal);
+            if (k > 0) cudaStreamWaitEvent(d.stream, ev[k - 1][c], 0);
+            lzyb_handle_t from = k == 0 ? src_h : dsts[k - 1];
+            // upstream stage is mid-download: pull from its frame directly (same bytes, same offsets)
+            int64_t moved;
+            if (k == 0) {
+                moved = lzyb_transfer_chunk(dsts[k], from, off, len, d.stream);
+            } else {
+                // temporarily present the upstream input slot as a readable peer
+                std::scoped_lock lk(chain[k]->mu, chain[k - 1]->mu);
+                Slot& dd = *chain[k];
+                Slot& up = *chain[k - 1];
+                CopyParams p;
+                memset(&p, 0, sizeof(p));
+                p.src = up.payload() + off;
+                p.dst = dd.payload() + off;
+                p.nbytes = len;
+                p.word_base = off >> 3;
+                p.ctl = dd.ctl;
+                p.total_nbytes = total;
+                p.fin = FIN_NONE;
+                const bool last = off + len == total;
+                if (last) {
+                    p.fin = FIN_VERIFY;
+                    p.expect[0] = src->digest[0];
+                    p.expect[1] = src->digest[1];
+                    p.dst_hdr = reinterpret_cast<lzyb_frame_header_t*>(dd.buf);
+                    dd.dtype = src->dtype;
+                    dd.ndim = src->ndim;
+                    memcpy(dd.shape, src->shape, sizeof(dd.shape));
+                    fill_template(dd, &p.hdr_template);
+                    arm_mailbox(dd, p);
+                }
+                int lr = launch_stream(d, p, true, d.stream);
+                if (lr != LZYB_OK) {
+                    rc = lr;
+                    break;
+                }
+                g.st_pull++;
+                g.st_bpull_p += len;
+                dd.delivered += len;
+                dd.state = LZYB_ST_FILLING;
+                dd.ctl_dirty = !last;
+                if (last) dd.digest_pending = true;
+                note(dd, d.stream);
+                moved = (int64_t)len;
+            }
+            if (moved < 0) {
+                rc = (int)moved;
+                break;
+            }
+            cudaEventCreateWithFlags(&ev[k][c], cudaEventDisableTiming);
+            cudaEventRecord(ev[k][c], d.stream);
+        }
+    }
+    if (rc == LZYB_OK) {
+        for (int k = 0; k < n && rc == LZYB_OK; ++k) rc = lzyb_input_finish(dsts[k], src_h, nullptr);
+    }
+    for (auto& row : ev)
+        for (auto e : row)
+            if (e) cudaEventDestroy(e);
+    return rc;
+}
+
+// ---- pinned host ring --------------------------------------------------------------------------
+
+static int ring_alloc(uint64_t bytes, uint64_t* off) {
+    std::lock_guard<std::mutex> lk(g.ring_mu);
+    while (!g.ring_frames.empty() && !g.ring_frames.front().live) {
+        g.ring_used -= g.ring_frames.front().bytes;
+        g.ring_frames.pop_front();
+    }
+    if (g.ring_frames.empty()) g.ring_head = 0;
+    if (bytes > g.ring_bytes) return fail(LZYB_E_LOCAL, "object of %llu bytes exceeds the host ring (%llu)", (unsigned long long)bytes,
+                                          (unsigned long long)g.ring_bytes);
+    uint64_t tail = g.ring_frames.empty() ? 0 : g.ring_frames.front().off;
+    uint64_t head = g.ring_head;
+    if (!g.ring_frames.empty() && head <= tail && g.ring_used > 0) {
+        // wrapped: free space is [head, tail)
+        if (head + bytes > tail) return fail(LZYB_E_LOCAL, "host ring full");
+    } else {
+        if (head + bytes > g.ring_bytes) {  // wrap: pad the end
+            uint64_t pad = g.ring_bytes - head;
+            if (bytes > tail) return fail(LZYB_E_LOCAL, "host ring full");
+            if (pad) {
+                g.ring_frames.push_back({head, pad, false});
+                g.ring_used += pad;
+            }
+            head = 0;
+        }
+    }
+    *off = head;
+    g.ring_frames.push_back({head, bytes, true});
+    g.ring_used += bytes;
+    g.ring_head = head + bytes;
+    return LZYB_OK;
+}
+
+static SlotCtl* borrow_ctl(DeviceCtx& d, int* idx) {
+    std::lock_guard<std::mutex> lk(d.mu);
+    if (d.ctl_free.empty()) return nullptr;
+    *idx = d.ctl_free.back();
+    d.ctl_free.pop_back();
+    return d.ctl_slab + *idx;
+}
+static void return_ctl(DeviceCtx& d, int idx) {
+    std::lock_guard<std::mutex> lk(d.mu);
+    d.ctl_free.push_back(idx);
+}
+
+// run one blocking scan (+ publish or verify) over host-mapped or device memory
+static int scan_blocking(DeviceCtx& d, const uint8_t* src, uint64_t nbytes, int fin, const uint64_t expect[2],
+                         lzyb_frame_header_t* dst_hdr, const lzyb_frame_header_t* tmpl, uint64_t out_digest[2],
+                         cudaStream_t st) {
+    int cidx = -1, midx = -1;
+    SlotCtl* ctl = borrow_ctl(d, &cidx);
+    if (!ctl) return fail(LZYB_E_LOCAL, "no free accumulator block");
+    Mailbox* mb;
+    {
+        std::lock_guard<std::mutex> lk(g.mbox_mu);
+        if (g.mbox_free.empty()) {
+            return_ctl(d, cidx);
+            return fail(LZYB_E_LOCAL, "out of mailboxes");
+        }
+        midx = g.mbox_free.back();
+        g.mbox_free.pop_back();
+        mb = g.mbox_slab + midx;
+        memset((void*)mb, 0, sizeof(Mailbox));
+    }
+    CopyParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = src;
+    p.nbytes = nbytes;
+    p.ctl = ctl;
+    p.mbox = mb;
+    p.seq = 1;
+    p.total_nbytes = nbytes;
+    p.fin = fin;
+    if (expect) {
+        p.expect[0] = expect[0];
+        p.expect[1] = expect[1];
+    }
+    p.dst_hdr = dst_hdr;
+    if (tmpl) p.hdr_template = *tmpl;
+    int rc = launch_stream(d, p, false, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    int status = (int)mb->status;
+    if (out_digest) {
+        out_digest[0] = mb->digest[0];
+        out_digest[1] = mb->digest[1];
+    }
+    {
+        std::lock_guard<std::mutex> lk(g.mbox_mu);
+        g.mbox_free.push_back(midx);
+    }
+    return_ctl(d, cidx);
+    if (rc != LZYB_OK) return rc;
+    if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "scan failed: %s", cudaGetErrorString(e));
+    if (status == 0) return fail(LZYB_E_LOCAL, "scan did not report");
+    return status;
+}
+
+int lzyb_frame_host_object(const void* bytes, uint64_t len, uint64_t* ring_off) {
+    if (!g.inited) return fail(LZYB_E_STATE, "lzyb_init has not been called (or found no GPU)");
+    if (!ring_off || (len && !bytes)) return fail(LZYB_E_ARG, "null argument");
+    uint64_t frame = HEADER_BYTES + round_up(len ? len : 16, 128);
+    uint64_t off = 0;
+    int rc = ring_alloc(frame, &off);
+    if (rc != LZYB_OK) return rc;
+    uint8_t* base = g.ring + off;
+    memset(base, 0, HEADER_BYTES);
+    if (len) memcpy(base + HEADER_BYTES, bytes, len);
+    DeviceCtx& d = *g.devs[0];
+    DeviceGuard dg(d.ordinal);
+    lzyb_frame_header_t tmpl;
+    memset(&tmpl, 0, sizeof(tmpl));
+    memcpy(tmpl.magic, "LZYB200", 8);
+    tmpl.version = LZYB_ABI_VERSION;
+    tmpl.dtype = LZYB_DT_PICKLE;
+    tmpl.nbytes = len;
+    tmpl.ndim = 1;
+    tmpl.shape[0] = len;
+    // the frame kernel reads the payload through the device mapping of the pinned ring and writes
+    // the header (digest included) back into the ring
+    int st = scan_blocking(d, base + HEADER_BYTES, len, FIN_PUBLISH, nullptr, reinterpret_cast<lzyb_frame_header_t*>(base),
+                           &tmpl, nullptr, d.stream);
+    if (st < 0) {
+        lzyb_ring_release(off);
+        return st;
+    }
+    g.st_frame++;
+    g.st_bframe += len;
+    *ring_off = off;
+    return LZYB_OK;
+}
+
+static int ring_check(uint64_t off, lzyb_frame_header_t** hdr) {
+    if (!g.inited) return fail(LZYB_E_STATE, "lzyb_init has not been called");
+    std::lock_guard<std::mutex> lk(g.ring_mu);
+    for (auto& f : g.ring_frames) {
+        if (f.off == off && f.live) {
+            *hdr = reinterpret_cast<lzyb_frame_header_t*>(g.ring + off);
+            return LZYB_OK;
+        }
+    }
+    return fail(LZYB_E_NOT_FOUND, "no live frame at ring offset %llu", (unsigned long long)off);
+}
+
+int lzyb_ring_frame_info(uint64_t ring_off, lzyb_frame_header_t* out) {
+    lzyb_frame_header_t* h = nullptr;
+    int rc = ring_check(ring_off, &h);
+    if (rc != LZYB_OK) return rc;
+    if (!out) return fail(LZYB_E_ARG, "null argument");
+    *out = *h;
+    return LZYB_OK;
+}
+
+int64_t lzyb_ring_read(uint64_t ring_off, void* dst, uint64_t cap) {
+    lzyb_frame_header_t* h = nullptr;
+    int rc = ring_check(ring_off, &h);
+    if (rc != LZYB_OK) return rc;
+    if (memcmp(h->magic, "LZYB200", 8) != 0 || !(h->flags & 1u)) return fail(LZYB_E_PEER, "ring frame %llu has no valid header", (unsigned long long)ring_off);
+    if (h->nbytes > cap) return fail(LZYB_E_ARG, "frame holds %llu bytes, buffer %llu", (unsigned long long)h->nbytes, (unsigned long long)cap);
+    DeviceCtx& d = *g.devs[0];
+    DeviceGuard dg(d.ordinal);
+    uint64_t expect[2] = {h->digest[0], h->digest[1]};
+    int st = scan_blocking(d, g.ring + ring_off + HEADER_BYTES, h->nbytes, FIN_VERIFY, expect, nullptr, nullptr, nullptr, d.stream);
+    if (st < 0) return st;
+    g.st_frame++;
+    if (st == 2) return fail(LZYB_E_PEER, "digest mismatch on ring frame %llu", (unsigned long long)ring_off);
+    if (h->nbytes) memcpy(dst, g.ring + ring_off + HEADER_BYTES, h->nbytes);
+    return (int64_t)h->nbytes;
+}
+
+int lzyb_ring_release(uint64_t ring_off) {
+    std::lock_guard<std::mutex> lk(g.ring_mu);
+    for (auto& f : g.ring_frames) {
+        if (f.off == ring_off && f.live) {
+            f.live = false;
+            return LZYB_OK;
+        }
+    }
+    return LZYB_OK;
+}
+
+// ---- utilities ---------------------------------------------------------------------------------
+
+int lzyb_digest_device(int gpu, const void* dptr, uint64_t nbytes, uint64_t digest_out[2], void* stream) {
+    if (!g.inited) return fail(LZYB_E_STATE, "lzyb_init has not been called (or found no GPU)");
+    int di = gpu - g.first;
+    if (di < 0 || di >= (int)g.devs.size()) return fail(LZYB_E_ARG, "GPU %d is not managed by this process", gpu);
+    if (!digest_out || (nbytes && !dptr)) return fail(LZYB_E_ARG, "null argument");
+    DeviceCtx& d = *g.devs[di];
+    DeviceGuard dg(d.ordinal);
+    int st = scan_blocking(d, static_cast<const uint8_t*>(dptr), nbytes, FIN_PUBLISH, nullptr, nullptr, nullptr, digest_out,
+                           pick_stream(d, stream));
+    if (st < 0) return st;
+    g.st_scan++;
+    return LZYB_OK;
+}
+
+int lzyb_fill_pattern(int gpu, void* dptr, uint64_t nbytes, uint64_t seed, void* stream) {
+    if (!g.inited) return fail(LZYB_E_STATE, "lzyb_init has not been called (or found no GPU)");
+    int di = gpu - g.first;
+    if (di < 0 || di >= (int)g.devs.size()) return fail(LZYB_E_ARG, "GPU %d is not managed by this process", gpu);
+    if (reinterpret_cast<uintptr_t>(dptr) & 15) return fail(LZYB_E_ARG, "fill target must be 16-byte aligned");
+    DeviceCtx& d = *g.devs[di];
+    DeviceGuard dg(d.ordinal);
+    uint64_t nvec = nbytes >> 4;
+    uint64_t want = (nvec + 255) / 256;
+    int grid = d.sm_count * 8;
+    if ((uint64_t)grid > want) grid = (int)(want ? want : 1);
+    fill_pattern_kernel<<<grid, 256, 0, pick_stream(d, stream)>>>(static_cast<uint8_t*>(dptr), nbytes, seed);
+    g.st_launch++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "fill launch failed: %s", cudaGetErrorString(e));
+    return LZYB_OK;
+}
+
+int lzyb_stats(lzyb_stats_t* out) {
+    if (!out) return fail(LZYB_E_ARG, "null argument");
+    memset(out, 0, sizeof(*out));
+    out->kernel_launches = g.st_launch;
+    out->pack_launches = g.st_pack;
+    out->pull_launches = g.st_pull;
+    out->scan_launches = g.st_scan;
+    out->frame_launches = g.st_frame;
+    out->bytes_packed = g.st_bpack;
+    out->bytes_pulled_local = g.st_bpull_l;
+    out->bytes_pulled_peer = g.st_bpull_p;
+    out->bytes_framed_host = g.st_bframe;
+    out->h2d_bytes = g.st_h2d;
+    out->d2h_bytes = g.st_d2h;
+    out->slots_live = g.st_live;
+    out->hbm_bytes_live = g.st_hbm_live;
+    uint64_t pooled = 0;
+    for (auto& d : g.devs) pooled += d->pooled_bytes;
+    out->hbm_bytes_pooled = pooled;
+    return LZYB_OK;
+}
+
+int lzyb_stats_reset(void) {
+    g.st_launch = g.st_pack = g.st_pull = g.st_scan = g.st_frame = 0;
+    g.st_bpack = g.st_bpull_l = g.st_bpull_p = g.st_bframe = g.st_h2d = g.st_d2h = 0;
+    return LZYB_OK;
+}
+
+int lzyb_set_copy_engine(int engine) {
+    if (engine < 0 || engine > 2) return fail(LZYB_E_ARG, "engine must be 0 (auto), 1 (LDG/STG) or 2 (TMA bulk)");
+    g.engine = engine;
+    return LZYB_OK;
+}
+
+int lzyb_set_grid(int ctas_per_sm) {
+    if (ctas_per_sm < 1 || ctas_per_sm > 16) return fail(LZYB_E_ARG, "ctas_per_sm must be in [1, 16]");
+    g.ctas_per_sm = ctas_per_sm;
+    return LZYB_OK;
+}
+
+int lzyb_fault_inject(lzyb_handle_t h, int kind, uint64_t arg) {
+    if (h == 0) {
+        g.global_fault = kind;
+        return LZYB_OK;
+    }
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (kind == LZYB_FAULT_CORRUPT_ONCE) {
+        if (arg >= s->nbytes) return fail(LZYB_E_ARG, "corrupt offset beyond payload");
+        DeviceCtx& d = *g.devs[s->dev];
+        DeviceGuard dg(d.ordinal);
+        if (s->last_ev) cudaEventSynchronize(s->last_ev);
+        corrupt_byte_kernel<<<1, 1, 0, d.stream>>>(s->payload() + arg);
+        CU(cudaStreamSynchronize(d.stream));
+        return LZYB_OK;
+    }
+    s->fault_kind = kind;
+    s->fault_arg = arg;
+    return LZYB_OK;
+}
+
+}  // extern "C"
