@@ -183,8 +183,10 @@ def run_ours(args):
     n_elem = payload // 4
     side = int(round(n_elem ** 0.5))
     shape = (side, side) if side * side == n_elem else (n_elem,)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)  # a real (non-legacy) stream: every launch and every event goes here
+    torch.cuda.set_stream(stream)
     sp = int(stream.cuda_stream)
+    assert sp != 0
 
     gen = torch.Generator(device=f"cuda:{dev}")
     gen.manual_seed(1234 + rank)

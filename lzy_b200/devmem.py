@@ -58,4 +58,6 @@ def view_tensor(ptr: int, dtype: torch.dtype, shape: Sequence[int], gpu: int, ow
 
 
 def current_stream_ptr(gpu: int) -> int:
-    return int(torch.cuda.current_stream(gpu).cuda_stream)
+    """cudaStream_t of torch's current stream.  The C ABI reserves NULL for "the library's own
+    stream", so the legacy default stream (handle 0) is passed as cudaStreamLegacy (0x1)."""
+    return int(torch.cuda.current_stream(gpu).cuda_stream) or 1
