@@ -1,0 +1,149 @@
+/*
+ * lzy_b200_host.h — C ABI of the host-side control logic that sits either side of the data plane:
+ * the channel manager's peer/transfer matcher and the graph dispatcher.  Same library
+ * (liblzy_b200.so), same conventions as lzy_b200.h (plain structs, negative LZYB_E_* codes that are
+ * the images of the reference's gRPC status codes).  Nothing here touches CUDA.
+ */
+#ifndef LZY_B200_HOST_H
+#define LZY_B200_HOST_H
+
+#include "lzy_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- LC.PeerDescription (model/src/main/proto/ai/lzy/v1/common/channel.proto:20-40) ---------- */
+#define LZYB_PEER_NONE 0
+#define LZYB_PEER_SLOT 1     /* oneof slot_peer { peer_url }                                       */
+#define LZYB_PEER_STORAGE 2  /* oneof storage_peer { storage_uri, credentials }                    */
+
+typedef struct lzyb_peer_desc {
+    char peer_id[128];
+    int32_t kind;            /* LZYB_PEER_SLOT | LZYB_PEER_STORAGE                                */
+    int32_t reserved;
+    char url[512];           /* SlotPeer.peer_url  or  StoragePeer.storage_uri                    */
+} lzyb_peer_desc_t;
+
+/* LCMS.BindRequest.Role (lzy/channel-manager-api/.../channel-manager.proto) */
+#define LZYB_ROLE_UNSPECIFIED 0
+#define LZYB_ROLE_PRODUCER 1
+#define LZYB_ROLE_CONSUMER 2
+
+/* BindResponse / TransferFailedResponse: optional peer + transfer id */
+typedef struct lzyb_bind_result {
+    int32_t has_peer;
+    int32_t reserved;
+    lzyb_peer_desc_t peer;
+    char transfer_id[64];
+} lzyb_bind_result_t;
+
+/* transfer states (channel-manager/.../db/TransferDao.java:47-52) */
+enum lzyb_transfer_state { LZYB_TR_PENDING = 0, LZYB_TR_ACTIVE = 1, LZYB_TR_COMPLETED = 2, LZYB_TR_FAILED = 3 };
+
+/* peer priorities (channel-manager/.../db/PeerDao.java:44-53) */
+#define LZYB_PRIO_PRIMARY 7
+#define LZYB_PRIO_BACKUP 5
+#define LZYB_PRIO_DONT_USE (-1)
+
+/* What the channel manager asks the outside world to do after a reply has been sent:
+ *  START_TRANSFER = ActionScheduler.startTransfer → LzySlotsApi.StartTransfer(slot_id = consumer,
+ *  peer = producer) (channel-manager/.../ActionScheduler.java:61-91);
+ *  ABORT_WORKFLOW = LzyServiceClient.destroyChannelAndWorkflow (LzyServiceClient.java:37-55). */
+#define LZYB_ACT_NONE 0
+#define LZYB_ACT_START_TRANSFER 1
+#define LZYB_ACT_ABORT_WORKFLOW 2
+
+typedef struct lzyb_cm_action {
+    int32_t kind;
+    int32_t reserved;
+    char channel_id[64];
+    char transfer_id[64];
+    char consumer_id[128];        /* StartTransferRequest.slot_id                                  */
+    char consumer_url[512];
+    lzyb_peer_desc_t producer;    /* StartTransferRequest.peer                                     */
+    char dial_url[512];           /* the URL the reference dials: the PRODUCER's (ActionScheduler.java:64) */
+    char execution_id[128];
+    char workflow_name[128];
+    char reason[256];
+    char idempotency_key[128];
+} lzyb_cm_action_t;
+
+/* ---- channel manager ------------------------------------------------------------------------ */
+int lzyb_cm_create(lzyb_handle_t* cm);
+int lzyb_cm_free(lzyb_handle_t cm);
+/* deterministic tie-break for tests: FIND_PRODUCER orders by priority DESC, RANDOM() (PeerDaoImpl.java:61-65) */
+int lzyb_cm_seed(lzyb_handle_t cm, uint64_t seed);
+
+/* LzyChannelManagerPrivate.GetOrCreate (channel-manager/.../services/ChannelService.java:39-116).
+ * storage_role: LZYB_ROLE_PRODUCER (pre-existing data) or LZYB_ROLE_CONSUMER (op output). */
+int lzyb_cm_get_or_create(lzyb_handle_t cm, const char* user_id, const char* workflow_name, const char* execution_id,
+                          const char* data_format, const char* scheme_format, const char* scheme_content,
+                          int storage_role, const char* storage_uri, char channel_id_out[64]);
+/* Destroy / DestroyAll (ChannelService.java:119-155) */
+int lzyb_cm_destroy(lzyb_handle_t cm, const char* channel_id, const char* reason);
+int lzyb_cm_destroy_all(lzyb_handle_t cm, const char* execution_id, const char* reason);
+
+/* LzyChannelManager.Bind (channel-manager/.../services/SlotsService.java:67-145) */
+int lzyb_cm_bind(lzyb_handle_t cm, const char* idempotency_key, const char* channel_id, const char* peer_id,
+                 const char* execution_id, const char* peer_url, int role, lzyb_bind_result_t* out);
+/* Unbind (:148-188): LZYB_E_UNAVAILABLE while the peer has PENDING/ACTIVE transfers */
+int lzyb_cm_unbind(lzyb_handle_t cm, const char* channel_id, const char* peer_id);
+/* TransferCompleted (:294-358) */
+int lzyb_cm_transfer_completed(lzyb_handle_t cm, const char* idempotency_key, const char* channel_id,
+                               const char* transfer_id);
+/* TransferFailed (:191-291): on success `out` carries the new peer and transfer id */
+int lzyb_cm_transfer_failed(lzyb_handle_t cm, const char* idempotency_key, const char* channel_id,
+                            const char* transfer_id, const char* description, lzyb_bind_result_t* out);
+/* GetChannelsStatus (:361-407): writes a JSON document
+ *   {"channels":[{"channel_id":..,"execution_id":..,"scheme":{..},"producers":[{"peer_id":..,"kind":..,"url":..}],"consumers":[..]}]}
+ * channel_ids may be NULL/0 = every channel of the execution.  Returns bytes needed (may exceed cap). */
+int64_t lzyb_cm_channels_status(lzyb_handle_t cm, const char* execution_id, const char* const* channel_ids,
+                                int n_channel_ids, char* json_out, uint64_t cap);
+
+/* deferred actions: returns 1 and fills `out` when one is available within timeout_ms, else 0 */
+int lzyb_cm_poll_action(lzyb_handle_t cm, lzyb_cm_action_t* out, int timeout_ms);
+/* outcome of a START_TRANSFER action: ok → PENDING→ACTIVE (ActionScheduler.java:79-91);
+ * !ok → channel dropped + ABORT_WORKFLOW queued (:92-104) */
+int lzyb_cm_action_result(lzyb_handle_t cm, const char* channel_id, const char* transfer_id, int ok, const char* reason);
+/* ActionScheduler.restoreActions (:47-59): re-queue START_TRANSFER for every PENDING transfer */
+int lzyb_cm_restore_actions(lzyb_handle_t cm);
+
+/* introspection used by the conformance tests (DbTest.java) */
+int lzyb_cm_transfer_state(lzyb_handle_t cm, const char* channel_id, const char* transfer_id, int* state_out);
+int lzyb_cm_peer_priority(lzyb_handle_t cm, const char* channel_id, const char* peer_id, int* priority_out);
+int lzyb_cm_is_aborted(lzyb_handle_t cm, const char* execution_id, char* reason_out, uint64_t cap);
+
+/* ---- graph dispatch -------------------------------------------------------------------------- */
+/* Replaces BfsGraphProcessor + Algorithms (lzy/graph-executor/.../exec/BfsGraphProcessor.java:44-258,
+ * algo/Algorithms.java:7-148) and the dependency build of graph-executor-2
+ * (lzy/graph-executor-2/.../algo/Algorithms.java:10-73).  Tasks are 0..n-1; an edge (a, b) says
+ * "a channel produced by task a is consumed by task b" (DirectChannelChecker.java:24-32). */
+enum lzyb_graph_status { LZYB_G_WAITING = 0, LZYB_G_EXECUTING = 1, LZYB_G_COMPLETED = 2, LZYB_G_FAILED = 3 };
+enum lzyb_task_status { LZYB_T_WAITING = 0, LZYB_T_EXECUTING = 1, LZYB_T_SUCCESS = 2, LZYB_T_ERROR = 3 };
+
+int lzyb_graph_create(int n_tasks, const int32_t* edges_from, const int32_t* edges_to, int n_edges, int allow_cycles,
+                      lzyb_handle_t* out);
+int lzyb_graph_free(lzyb_handle_t g);
+/* One dispatch step (BfsGraphProcessor.exec): returns how many tasks became runnable and writes
+ * their ids; they are marked EXECUTING.  A task is runnable when every producer of each of its
+ * input channels has finished successfully; members of one strongly connected component start
+ * together.  No sleep between steps (the reference sleeps 1 s, BfsGraphProcessor.java:148). */
+int lzyb_graph_next(lzyb_handle_t g, int32_t* runnable_out, int cap);
+int lzyb_graph_task_done(lzyb_handle_t g, int32_t task, int ok, const char* error_description);
+/* tasks EXECUTING now (GraphExecutionState.currentExecutionGroup) */
+int lzyb_graph_executing(lzyb_handle_t g, int32_t* out, int cap);
+int lzyb_graph_status(lzyb_handle_t g);
+int lzyb_graph_task_status(lzyb_handle_t g, int32_t task);
+/* stop(graph, description): FAILED; returns the tasks that must be killed (were EXECUTING) */
+int lzyb_graph_stop(lzyb_handle_t g, const char* description, int32_t* kill_out, int cap);
+int lzyb_graph_error(lzyb_handle_t g, char* description_out, uint64_t cap, int32_t* failed_task_out);
+/* LocalRuntime.exec order (pylzy/lzy/api/v1/local/runtime.py:48-85) is available for comparison */
+int lzyb_graph_topo_order(lzyb_handle_t g, int32_t* order_out, int cap);
+/* graph-executor-2 Algorithms.buildTaskDependents cycle check: 1 if the task graph has a cycle */
+int lzyb_graph_has_cycle(lzyb_handle_t g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LZY_B200_HOST_H */

@@ -1,0 +1,264 @@
+"""ctypes binding of the host-side control logic in liblzy_b200.so (include/lzy_b200_host.h):
+the channel manager's matcher and the graph dispatcher.  No CUDA involved."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Dict, List, Optional, Sequence, Tuple
+
+from . import _native as N
+
+lib = N.lib
+_H = C.c_uint64
+
+PEER_SLOT, PEER_STORAGE = 1, 2
+ROLE_PRODUCER, ROLE_CONSUMER = 1, 2
+TR_PENDING, TR_ACTIVE, TR_COMPLETED, TR_FAILED = 0, 1, 2, 3
+PRIO_PRIMARY, PRIO_BACKUP = 7, 5
+ACT_START_TRANSFER, ACT_ABORT_WORKFLOW = 1, 2
+G_WAITING, G_EXECUTING, G_COMPLETED, G_FAILED = 0, 1, 2, 3
+T_WAITING, T_EXECUTING, T_SUCCESS, T_ERROR = 0, 1, 2, 3
+
+
+class PeerDesc(C.Structure):
+    _fields_ = [("peer_id", C.c_char * 128), ("kind", C.c_int32), ("reserved", C.c_int32), ("url", C.c_char * 512)]
+
+    def as_tuple(self):
+        return self.peer_id.decode(), int(self.kind), self.url.decode()
+
+
+class BindResult(C.Structure):
+    _fields_ = [("has_peer", C.c_int32), ("reserved", C.c_int32), ("peer", PeerDesc), ("transfer_id", C.c_char * 64)]
+
+
+class CmAction(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("channel_id", C.c_char * 64),
+                ("transfer_id", C.c_char * 64), ("consumer_id", C.c_char * 128), ("consumer_url", C.c_char * 512),
+                ("producer", PeerDesc), ("dial_url", C.c_char * 512), ("execution_id", C.c_char * 128),
+                ("workflow_name", C.c_char * 128), ("reason", C.c_char * 256), ("idempotency_key", C.c_char * 128)]
+
+
+_s, _i = C.c_char_p, C.c_int
+_SIGS = {
+    "lzyb_cm_create": (_i, [C.POINTER(_H)]),
+    "lzyb_cm_free": (_i, [_H]),
+    "lzyb_cm_seed": (_i, [_H, C.c_uint64]),
+    "lzyb_cm_get_or_create": (_i, [_H, _s, _s, _s, _s, _s, _s, _i, _s, C.c_char * 64]),
+    "lzyb_cm_destroy": (_i, [_H, _s, _s]),
+    "lzyb_cm_destroy_all": (_i, [_H, _s, _s]),
+    "lzyb_cm_bind": (_i, [_H, _s, _s, _s, _s, _s, _i, C.POINTER(BindResult)]),
+    "lzyb_cm_unbind": (_i, [_H, _s, _s]),
+    "lzyb_cm_transfer_completed": (_i, [_H, _s, _s, _s]),
+    "lzyb_cm_transfer_failed": (_i, [_H, _s, _s, _s, _s, C.POINTER(BindResult)]),
+    "lzyb_cm_channels_status": (C.c_int64, [_H, _s, C.POINTER(_s), _i, C.c_char_p, C.c_uint64]),
+    "lzyb_cm_poll_action": (_i, [_H, C.POINTER(CmAction), _i]),
+    "lzyb_cm_action_result": (_i, [_H, _s, _s, _i, _s]),
+    "lzyb_cm_restore_actions": (_i, [_H]),
+    "lzyb_cm_transfer_state": (_i, [_H, _s, _s, C.POINTER(_i)]),
+    "lzyb_cm_peer_priority": (_i, [_H, _s, _s, C.POINTER(_i)]),
+    "lzyb_cm_is_aborted": (_i, [_H, _s, C.c_char_p, C.c_uint64]),
+    "lzyb_graph_create": (_i, [_i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i, _i, C.POINTER(_H)]),
+    "lzyb_graph_free": (_i, [_H]),
+    "lzyb_graph_next": (_i, [_H, C.POINTER(C.c_int32), _i]),
+    "lzyb_graph_task_done": (_i, [_H, C.c_int32, _i, _s]),
+    "lzyb_graph_executing": (_i, [_H, C.POINTER(C.c_int32), _i]),
+    "lzyb_graph_status": (_i, [_H]),
+    "lzyb_graph_task_status": (_i, [_H, C.c_int32]),
+    "lzyb_graph_stop": (_i, [_H, _s, C.POINTER(C.c_int32), _i]),
+    "lzyb_graph_error": (_i, [_H, C.c_char_p, C.c_uint64, C.POINTER(C.c_int32)]),
+    "lzyb_graph_topo_order": (_i, [_H, C.POINTER(C.c_int32), _i]),
+    "lzyb_graph_has_cycle": (_i, [_H]),
+}
+for _n, (_r, _a) in _SIGS.items():
+    _f = getattr(lib, _n)
+    _f.restype, _f.argtypes = _r, _a
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def _b(s: Optional[str]) -> Optional[bytes]:
+    return None if s is None else s.encode()
+
+
+class GrpcStatusError(N.LzybError):
+    """Control-plane failure; ``status`` is the gRPC status name the reference would return."""
+    NAMES = {N.E_NOT_FOUND: "NOT_FOUND", N.E_PRECONDITION: "FAILED_PRECONDITION", N.E_UNAVAILABLE: "UNAVAILABLE",
+             N.E_INTERNAL: "INTERNAL", N.E_UNIMPLEMENTED: "UNIMPLEMENTED", N.E_INVALID: "INVALID_ARGUMENT",
+             N.E_EXISTS: "ALREADY_EXISTS"}
+
+    def __init__(self, code, message):
+        super().__init__(code, message)
+        self.status = self.NAMES.get(code, "UNKNOWN")
+
+
+def _check(rc: int) -> int:
+    if rc >= 0:
+        return rc
+    msg = N.last_error()
+    if rc in GrpcStatusError.NAMES:
+        raise GrpcStatusError(rc, msg)
+    raise N.LzybError(rc, msg)
+
+
+class Peer:
+    __slots__ = ("peer_id", "kind", "url")
+
+    def __init__(self, peer_id: str, kind: int, url: str):
+        self.peer_id, self.kind, self.url = peer_id, kind, url
+
+    @property
+    def is_storage(self) -> bool:
+        return self.kind == PEER_STORAGE
+
+    def __repr__(self):
+        return f"Peer({self.peer_id!r}, {'storage' if self.is_storage else 'slot'}, {self.url!r})"
+
+
+class ChannelManager:
+    """In-process LzyChannelManager + LzyChannelManagerPrivate
+    (lzy/channel-manager-api/src/main/proto/ai/lzy/v1/channel/channel-manager*.proto)."""
+
+    def __init__(self, seed: Optional[int] = None):
+        h = _H()
+        _check(lib.lzyb_cm_create(C.byref(h)))
+        self.h = h.value
+        if seed is not None:
+            _check(lib.lzyb_cm_seed(self.h, seed))
+
+    def close(self):
+        if self.h:
+            lib.lzyb_cm_free(self.h)
+            self.h = 0
+
+    # -- private API ---------------------------------------------------------------------------
+    def get_or_create(self, user_id: str, workflow_name: str, execution_id: str, *, producer_uri: Optional[str] = None,
+                      consumer_uri: Optional[str] = None, data_format: str = "", scheme_format: str = "",
+                      scheme_content: str = "") -> str:
+        role = ROLE_PRODUCER if producer_uri is not None else (ROLE_CONSUMER if consumer_uri is not None else 0)
+        uri = producer_uri if producer_uri is not None else consumer_uri
+        out = (C.c_char * 64)()
+        _check(lib.lzyb_cm_get_or_create(self.h, _b(user_id), _b(workflow_name), _b(execution_id), _b(data_format),
+                                         _b(scheme_format), _b(scheme_content), role, _b(uri), out))
+        return out.value.decode()
+
+    def destroy(self, channel_id: str, reason: str = "") -> None:
+        _check(lib.lzyb_cm_destroy(self.h, _b(channel_id), _b(reason)))
+
+    def destroy_all(self, execution_id: str, reason: str = "") -> None:
+        _check(lib.lzyb_cm_destroy_all(self.h, _b(execution_id), _b(reason)))
+
+    # -- public API ----------------------------------------------------------------------------
+    def bind(self, channel_id: str, role: int, peer_id: str, peer_url: str = "", execution_id: str = "",
+             idempotency_key: Optional[str] = None) -> Tuple[Optional[Peer], Optional[str]]:
+        r = BindResult()
+        _check(lib.lzyb_cm_bind(self.h, _b(idempotency_key), _b(channel_id), _b(peer_id), _b(execution_id),
+                                _b(peer_url), role, C.byref(r)))
+        if not r.has_peer:
+            return None, None
+        return Peer(*r.peer.as_tuple()), r.transfer_id.decode()
+
+    def unbind(self, channel_id: str, peer_id: str) -> None:
+        _check(lib.lzyb_cm_unbind(self.h, _b(channel_id), _b(peer_id)))
+
+    def transfer_completed(self, channel_id: str, transfer_id: str, idempotency_key: Optional[str] = None) -> None:
+        _check(lib.lzyb_cm_transfer_completed(self.h, _b(idempotency_key), _b(channel_id), _b(transfer_id)))
+
+    def transfer_failed(self, channel_id: str, transfer_id: str, description: str = "",
+                        idempotency_key: Optional[str] = None) -> Tuple[Peer, str]:
+        r = BindResult()
+        _check(lib.lzyb_cm_transfer_failed(self.h, _b(idempotency_key), _b(channel_id), _b(transfer_id),
+                                           _b(description), C.byref(r)))
+        return Peer(*r.peer.as_tuple()), r.transfer_id.decode()
+
+    def channels_status(self, execution_id: str = "", channel_ids: Sequence[str] = ()) -> List[dict]:
+        arr = (C.c_char_p * max(1, len(channel_ids)))(*[c.encode() for c in channel_ids])
+        need = _check(lib.lzyb_cm_channels_status(self.h, _b(execution_id), arr, len(channel_ids), None, 0))
+        buf = C.create_string_buffer(int(need))
+        _check(lib.lzyb_cm_channels_status(self.h, _b(execution_id), arr, len(channel_ids), buf, need))
+        return json.loads(buf.value.decode())["channels"]
+
+    # -- deferred actions ------------------------------------------------------------------------
+    def poll_action(self, timeout_ms: int = 0) -> Optional[dict]:
+        a = CmAction()
+        if not _check(lib.lzyb_cm_poll_action(self.h, C.byref(a), timeout_ms)):
+            return None
+        return {"kind": int(a.kind), "channel_id": a.channel_id.decode(), "transfer_id": a.transfer_id.decode(),
+                "consumer_id": a.consumer_id.decode(), "consumer_url": a.consumer_url.decode(),
+                "producer": Peer(*a.producer.as_tuple()), "dial_url": a.dial_url.decode(),
+                "execution_id": a.execution_id.decode(), "workflow_name": a.workflow_name.decode(),
+                "reason": a.reason.decode(), "idempotency_key": a.idempotency_key.decode()}
+
+    def action_result(self, channel_id: str, transfer_id: str, ok: bool, reason: str = "") -> None:
+        _check(lib.lzyb_cm_action_result(self.h, _b(channel_id), _b(transfer_id), int(ok), _b(reason)))
+
+    def restore_actions(self) -> int:
+        return _check(lib.lzyb_cm_restore_actions(self.h))
+
+    # -- introspection ---------------------------------------------------------------------------
+    def transfer_state(self, channel_id: str, transfer_id: str) -> int:
+        st = C.c_int()
+        _check(lib.lzyb_cm_transfer_state(self.h, _b(channel_id), _b(transfer_id), C.byref(st)))
+        return st.value
+
+    def peer_priority(self, channel_id: str, peer_id: str) -> int:
+        p = C.c_int()
+        _check(lib.lzyb_cm_peer_priority(self.h, _b(channel_id), _b(peer_id), C.byref(p)))
+        return p.value
+
+    def aborted(self, execution_id: str) -> Optional[str]:
+        buf = C.create_string_buffer(256)
+        if _check(lib.lzyb_cm_is_aborted(self.h, _b(execution_id), buf, 256)):
+            return buf.value.decode()
+        return None
+
+
+class GraphDispatcher:
+    """Dependency-count dispatcher with the BFS processor's observable behaviour."""
+
+    def __init__(self, n_tasks: int, edges: Sequence[Tuple[int, int]], allow_cycles: bool = True):
+        fr = (C.c_int32 * max(1, len(edges)))(*[e[0] for e in edges])
+        to = (C.c_int32 * max(1, len(edges)))(*[e[1] for e in edges])
+        h = _H()
+        _check(lib.lzyb_graph_create(n_tasks, fr, to, len(edges), int(allow_cycles), C.byref(h)))
+        self.h, self.n = h.value, n_tasks
+        self._buf = (C.c_int32 * max(1, n_tasks))()
+
+    def close(self):
+        if self.h:
+            lib.lzyb_graph_free(self.h)
+            self.h = 0
+
+    def next(self) -> List[int]:
+        k = _check(lib.lzyb_graph_next(self.h, self._buf, self.n))
+        return [int(self._buf[i]) for i in range(k)]
+
+    def task_done(self, task: int, ok: bool = True, error: str = "") -> None:
+        _check(lib.lzyb_graph_task_done(self.h, task, int(ok), _b(error)))
+
+    def executing(self) -> List[int]:
+        k = _check(lib.lzyb_graph_executing(self.h, self._buf, self.n))
+        return [int(self._buf[i]) for i in range(k)]
+
+    @property
+    def status(self) -> int:
+        return _check(lib.lzyb_graph_status(self.h))
+
+    def task_status(self, task: int) -> int:
+        return _check(lib.lzyb_graph_task_status(self.h, task))
+
+    def stop(self, description: str = "") -> List[int]:
+        k = _check(lib.lzyb_graph_stop(self.h, _b(description), self._buf, self.n))
+        return [int(self._buf[i]) for i in range(k)]
+
+    def error(self) -> Tuple[bool, str, int]:
+        buf = C.create_string_buffer(512)
+        t = C.c_int32(-1)
+        failed = _check(lib.lzyb_graph_error(self.h, buf, 512, C.byref(t)))
+        return bool(failed), buf.value.decode(), int(t.value)
+
+    def topo_order(self) -> List[int]:
+        k = _check(lib.lzyb_graph_topo_order(self.h, self._buf, self.n))
+        return [int(self._buf[i]) for i in range(k)]
+
+    @property
+    def has_cycle(self) -> bool:
+        return bool(_check(lib.lzyb_graph_has_cycle(self.h)))

@@ -24,6 +24,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "host/host_common.h"
 #include "kernels.cuh"
 #include "tma_kernels.cuh"
 
@@ -40,12 +41,10 @@ constexpr int TMA_STAGES = 6;
 constexpr int TMA_STAGE_BYTES = 16384;
 constexpr size_t TMA_SMEM = static_cast<size_t>(TMA_STAGES) * TMA_STAGE_BYTES + 2 * TMA_STAGES * sizeof(uint64_t);
 
-thread_local char tl_err[512] = "";
-
 int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
-    vsnprintf(tl_err, sizeof(tl_err), fmt, ap);
+    lzyb_host::vfail(code, fmt, ap);
     va_end(ap);
     return code;
 }
@@ -359,7 +358,7 @@ int new_slot(const char* slot_id, int gpu, uint64_t nbytes, bool is_input, lzyb_
 extern "C" {
 
 int lzyb_abi_version(void) { return LZYB_ABI_VERSION; }
-const char* lzyb_last_error(void) { return tl_err; }
+const char* lzyb_last_error(void) { return lzyb_host::err_buf(); }
 int lzyb_is_initialized(void) { return g.inited ? 1 : 0; }
 int lzyb_device_count(void) { return g.inited ? (int)g.devs.size() : 0; }
 

@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.json.  Run ONLY in the authoring container, where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+* reference_leaf_vectors.json — produced by executing the reference's own pure-Python leaf modules
+  (they import without the missing third parties): pylzy/lzy/api/v1/utils/hashing.py (HashingIO,
+  md5_of_str) and pylzy/lzy/storage/async_/fs.py (FsStorageClient read/write 8096-byte loops,
+  path_from_uri).  `lzy.api.v1` itself cannot be imported (serialzy, envzy, generated protobuf
+  stubs are absent), so the modules are loaded by file path.
+* digest_vectors.json — known answers of the data plane's digest from the oracle's C restatement
+  cross-checked with the pure-Python definition in tests/test_abi_and_oracle.py.
+"""
+import asyncio
+import hashlib
+import importlib.util
+import io
+import json
+import os
+import sys
+import tempfile
+import types
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent.parent
+sys.path.insert(0, str(ROOT))
+REF = Path("/root/reference/pylzy")
+
+
+def load(path: Path, name: str):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    import oracle
+    out = {}
+    hashing = load(REF / "lzy/api/v1/utils/hashing.py", "ref_hashing")
+    out["md5_of_str"] = [{"in": s, "out": hashing.md5_of_str(s)} for s in
+                         ["", "file:///tmp/lzy_storage/lzy_runs/wf/ops/foo/1234/return_0", "ʎzy"]]
+    hio = []
+    for writes in ([b""], [b"Hello"], [b"a" * 8096, b"b" * 8096, b"tail"], [bytes(range(256)) * 33]):
+        sink = io.BytesIO()
+        h = hashing.HashingIO(sink)
+        for w in writes:
+            h.write(w)
+        assert sink.getvalue() == b"".join(writes)
+        hio.append({"writes_hex": [w.hex() for w in writes], "md5": h.md5})
+    out["hashing_io"] = hio
+
+    # fs.py imports lzy.storage.api (pure) — make the package importable without lzy/__init__ side effects
+    sys.path.insert(0, str(REF))
+    fs = load(REF / "lzy/storage/async_/fs.py", "ref_fs")
+    client = fs.FsStorageClient()
+    fsv = []
+    for nbytes, seed in ((0, 1), (1, 2), (8095, 3), (8096, 4), (8097, 5), (1 << 20, 42), (3 * 8096 + 17, 6)):
+        data = oracle.pattern(nbytes, seed).tobytes()
+        with tempfile.TemporaryDirectory() as d:
+            uri = "file://" + os.path.join(d, "x", "blob")
+            calls = []
+            asyncio.run(client.write(uri, io.BytesIO(data), progress=lambda n, r: calls.append(n)))
+            dst = io.BytesIO()
+            asyncio.run(client.read(uri, dst))
+            assert asyncio.run(client.size_in_bytes(uri)) == nbytes
+            assert asyncio.run(client.blob_exists(uri))
+        fsv.append({"nbytes": nbytes, "seed": seed, "src_md5": hashlib.md5(data).hexdigest(),
+                    "dst_md5": hashlib.md5(dst.getvalue()).hexdigest(), "loop_iterations": len(calls)})
+    out["fs_copy"] = fsv
+    p = fs.FsStorageClient._FsStorageClient__path_from_uri
+    out["path_from_uri"] = [{"in": u, "out": p(u)} for u in
+                            ["file:///tmp/lzy_storage/a", "file:///tmp/lzy_storage/lzy_runs/wf/inputs/abc"]]
+    (ROOT / "tests/golden/reference_leaf_vectors.json").write_text(json.dumps(out, indent=1))
+
+    vecs = [{"name": "empty", "hex": ""}, {"name": "Hello", "hex": b"Hello".hex()},
+            {"name": "one-word", "hex": bytes(range(8)).hex()}, {"name": "17-bytes", "hex": bytes(range(17)).hex()},
+            {"name": "zeros-4096", "hex": (b"\0" * 4096).hex()}]
+    for v in vecs:
+        v["digest"] = oracle.digest_hex(bytes.fromhex(v["hex"]))
+    for nbytes, seed in ((1 << 20, 7), ((2 << 20) + 5, 1234), (64 << 20, 7)):
+        vecs.append({"name": f"pattern-{nbytes}-{seed}", "pattern_nbytes": nbytes, "pattern_seed": seed,
+                     "digest": oracle.digest_hex(oracle.pattern(nbytes, seed))})
+    (ROOT / "tests/golden/digest_vectors.json").write_text(json.dumps({"vectors": vecs}, indent=1))
+    print("golden vectors written")
+
+
+if __name__ == "__main__":
+    main()
