@@ -144,6 +144,8 @@ int lzyb_abi_version(void);
 int lzyb_device_count(void);                 /* devices managed by this process                   */
 const char* lzyb_last_error(void);           /* thread-local, valid until the next call           */
 const char* lzyb_strerror(int code);
+/* lets a pluggable backend (lzy_b200_host.h: lzyb_backend_ops_t) report through the same channel */
+int lzyb_set_last_error(const char* message);
 
 /* ---- output slots: OutputSlotBackend (lzy/slots/.../backends/OutputSlotBackend.java:6-16) ----- */
 
@@ -203,7 +205,8 @@ int lzyb_input_finish(lzyb_handle_t dst, lzyb_handle_t src_peer, void* stream);
 int64_t lzyb_input_write_host(lzyb_handle_t dst, uint64_t offset, const void* src_host, uint64_t len,
                               void* stream);
 /* expected digest supplied by the control plane (DataScheme.metadata "lzy.checksum") for
- * sources that have no frame header (host/storage peers) */
+ * sources that have no frame header (host/storage peers); NULL = no expectation, the digest
+ * computed while the bytes landed is published */
 int lzyb_input_finish_expect(lzyb_handle_t dst, const uint64_t digest[2], void* stream);
 /* = InputSlotBackend.toOutput() (FileInputBackend.java:38-45): the delivered bytes become an
  * output slot ("<slotId>-out" re-publication, InputSlot.java:160-168) with no copy. */

@@ -114,6 +114,86 @@ int lzyb_cm_transfer_state(lzyb_handle_t cm, const char* channel_id, const char*
 int lzyb_cm_peer_priority(lzyb_handle_t cm, const char* channel_id, const char* peer_id, int* priority_out);
 int lzyb_cm_is_aborted(lzyb_handle_t cm, const char* execution_id, char* reason_out, uint64_t cap);
 
+/* ---- slots runtime: the worker-side state machines of lzy/slots -------------------------------- */
+/* Replaces, behind the same seams (paths relative to lzy/slots/src/main/java/ai/lzy/slots/):
+ *   Slots.java:44-106                     one per worker: slots server + execution contexts
+ *   SlotsService.java:21-69               slot registry, Read / StartTransfer routing
+ *   SlotsExecutionContext.java:45-107     beforeExecution / afterExecution / close / add
+ *   InputSlot.java:127-295                BINDING → WAITING_FOR_PEER → DOWNLOADING → READY (+ "-out")
+ *   OutputSlot.java:135-273               waitCompleted → register → Bind(PRODUCER) → storage upload
+ *   transfers/TransferFactory.java:19-33  peer-kind dispatch (slot peer → NVLink pull, storage → host blob)
+ * and the worker staging order of lzy/worker/.../WorkerApiImpl.java:191-225. */
+
+/* The backend seam (InputSlotBackend / OutputSlotBackend / InputTransfer).  The default table is the
+ * HBM data plane of lzy_b200.h; the reference's tests swap in an in-memory backend with failure
+ * knobs at exactly this seam (SlotsTest.InMemBackend, SlotsTest.java:866-912) and so do ours. */
+typedef struct lzyb_backend_ops {
+    int (*slot_create)(const char* slot_id, int gpu, uint64_t nbytes, lzyb_handle_t* out);
+    int (*input_open)(const char* slot_id, int gpu, uint64_t nbytes, lzyb_handle_t* out);
+    int (*slot_commit)(lzyb_handle_t h, uint64_t digest_out[2], void* stream);
+    int64_t (*slot_read)(lzyb_handle_t h, uint64_t offset, void* dst_host, uint64_t len);
+    int (*slot_info)(lzyb_handle_t h, lzyb_slot_info_t* out);
+    int (*slot_find)(const char* slot_id, lzyb_handle_t* out);
+    int (*slot_close)(lzyb_handle_t h);
+    int64_t (*transfer_chunk)(lzyb_handle_t dst, lzyb_handle_t src_peer, uint64_t offset, uint64_t max_len, void* stream);
+    int (*input_finish)(lzyb_handle_t dst, lzyb_handle_t src_peer, void* stream);
+    int64_t (*input_write_host)(lzyb_handle_t dst, uint64_t offset, const void* src_host, uint64_t len, void* stream);
+    int (*input_finish_expect)(lzyb_handle_t dst, const uint64_t digest[2], void* stream);
+    int (*input_to_output)(lzyb_handle_t h);
+    int (*input_reset)(lzyb_handle_t h);
+} lzyb_backend_ops_t;
+int lzyb_slots_set_backend(const lzyb_backend_ops_t* ops); /* NULL = the HBM backend */
+
+#define LZYB_DIR_INPUT 1
+#define LZYB_DIR_OUTPUT 2
+
+/* Slots(...): one per worker.  `api_url` is what the worker puts in BindRequest.peer_url. */
+int lzyb_slots_create(lzyb_handle_t cm, int gpu, const char* api_url, lzyb_handle_t* out);
+int lzyb_slots_free(lzyb_handle_t slots);
+/* bytes per transferChunkTo call (0 = the whole remaining payload in one launch; the reference's
+ * gRPC chunk is 2 MiB, OutputSlot.java:241) */
+int lzyb_slots_set_chunk_bytes(lzyb_handle_t slots, uint64_t chunk_bytes);
+/* Slots.context(requestId, executionId, taskId, slots, slotToChannelMapping) */
+int lzyb_ctx_create(lzyb_handle_t slots, const char* execution_id, const char* task_id, lzyb_handle_t* out);
+/* one LMS.Slot + its channel assignment (model/.../slot.proto:10-30, operation.proto:31-37) */
+int lzyb_ctx_add_slot(lzyb_handle_t ctx, const char* slot_name, const char* channel_id, int direction);
+/* beforeExecution(): build the slots; block until every input is READY (or a slot failed) */
+int lzyb_ctx_before_execution(lzyb_handle_t ctx, int timeout_ms);
+/* non-blocking half of beforeExecution(): create the slots and let the inputs bind/download in the
+ * background (downstream prefetch); a later before_execution() only waits */
+int lzyb_ctx_prefetch(lzyb_handle_t ctx);
+/* the delivered frame of an input slot (after before_execution) */
+int lzyb_ctx_input_handle(lzyb_handle_t ctx, const char* slot_name, lzyb_handle_t* slot_out);
+/* the op opens its output: allocate the frame to pack / write into (the fifo of OutputPipeBackend) */
+int lzyb_ctx_output_open(lzyb_handle_t ctx, const char* slot_name, uint64_t nbytes, lzyb_handle_t* slot_out);
+/* the op closed its output: data is complete (waitCompleted returns) → register → Bind(PRODUCER) */
+int lzyb_ctx_output_done(lzyb_handle_t ctx, const char* slot_name);
+/* afterExecution(): block until every output is bound (and uploaded when the channel has a storage consumer) */
+int lzyb_ctx_after_execution(lzyb_handle_t ctx, int timeout_ms);
+int lzyb_ctx_close(lzyb_handle_t ctx);
+/* input slot state for tests/metrics: enum below */
+enum lzyb_input_state { LZYB_IS_BINDING = 0, LZYB_IS_WAITING_FOR_PEER = 1, LZYB_IS_DOWNLOADING = 2, LZYB_IS_READY = 3, LZYB_IS_CLOSED = 4 };
+int lzyb_ctx_input_state(lzyb_handle_t ctx, const char* slot_name);
+
+/* LzySlotsApi server side (lzy/slots-api/src/main/proto/ai/lzy/v1/slots/slots-api.proto:13-47) */
+int lzyb_slots_start_transfer(lzyb_handle_t slots, const char* slot_id, const lzyb_peer_desc_t* peer, const char* transfer_id);
+/* Read(peer_id, offset): one chunk per call (≤ len bytes); LZYB_EOF = the EOS control message;
+ * LZYB_E_NOT_FOUND unknown slot; LZYB_E_UNIMPLEMENTED input slot */
+int64_t lzyb_slots_read(lzyb_handle_t slots, const char* peer_id, uint64_t offset, void* dst_host, uint64_t len);
+
+/* the channel manager's deferred actions need somebody to execute them (ActionScheduler's executor):
+ * start a thread that polls `cm` and delivers StartTransfer to the registered Slots instances */
+int lzyb_cm_pump_start(lzyb_handle_t cm);
+int lzyb_cm_pump_stop(lzyb_handle_t cm);
+
+/* storage peers: on one box the reference's S3 rendezvous/backup store becomes a host-memory blob
+ * store keyed by the storage URI (StorageOutputTransfer / StorageInputTransfer,
+ * lzy/slots/.../transfers/StorageOutputTransfer.java:30-40, StorageInputTransfer.java:32-41) */
+int lzyb_blob_put(const char* uri, const void* data, uint64_t len);
+int64_t lzyb_blob_size(const char* uri);                       /* LZYB_E_NOT_FOUND if absent */
+int64_t lzyb_blob_get(const char* uri, void* dst, uint64_t cap);
+int lzyb_blob_delete(const char* uri);
+
 /* ---- graph dispatch -------------------------------------------------------------------------- */
 /* Replaces BfsGraphProcessor + Algorithms (lzy/graph-executor/.../exec/BfsGraphProcessor.java:44-258,
  * algo/Algorithms.java:7-148) and the dependency build of graph-executor-2

@@ -57,6 +57,28 @@ _SIGS = {
     "lzyb_cm_transfer_state": (_i, [_H, _s, _s, C.POINTER(_i)]),
     "lzyb_cm_peer_priority": (_i, [_H, _s, _s, C.POINTER(_i)]),
     "lzyb_cm_is_aborted": (_i, [_H, _s, C.c_char_p, C.c_uint64]),
+    "lzyb_slots_set_backend": (_i, [C.c_void_p]),
+    "lzyb_slots_create": (_i, [_H, _i, _s, C.POINTER(_H)]),
+    "lzyb_slots_free": (_i, [_H]),
+    "lzyb_slots_set_chunk_bytes": (_i, [_H, C.c_uint64]),
+    "lzyb_ctx_create": (_i, [_H, _s, _s, C.POINTER(_H)]),
+    "lzyb_ctx_add_slot": (_i, [_H, _s, _s, _i]),
+    "lzyb_ctx_before_execution": (_i, [_H, _i]),
+    "lzyb_ctx_prefetch": (_i, [_H]),
+    "lzyb_ctx_input_handle": (_i, [_H, _s, C.POINTER(_H)]),
+    "lzyb_ctx_output_open": (_i, [_H, _s, C.c_uint64, C.POINTER(_H)]),
+    "lzyb_ctx_output_done": (_i, [_H, _s]),
+    "lzyb_ctx_after_execution": (_i, [_H, _i]),
+    "lzyb_ctx_close": (_i, [_H]),
+    "lzyb_ctx_input_state": (_i, [_H, _s]),
+    "lzyb_slots_start_transfer": (_i, [_H, _s, C.POINTER(PeerDesc), _s]),
+    "lzyb_slots_read": (C.c_int64, [_H, _s, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "lzyb_cm_pump_start": (_i, [_H]),
+    "lzyb_cm_pump_stop": (_i, [_H]),
+    "lzyb_blob_put": (_i, [_s, C.c_void_p, C.c_uint64]),
+    "lzyb_blob_size": (C.c_int64, [_s]),
+    "lzyb_blob_get": (C.c_int64, [_s, C.c_void_p, C.c_uint64]),
+    "lzyb_blob_delete": (_i, [_s]),
     "lzyb_graph_create": (_i, [_i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i, _i, C.POINTER(_H)]),
     "lzyb_graph_free": (_i, [_H]),
     "lzyb_graph_next": (_i, [_H, C.POINTER(C.c_int32), _i]),
@@ -262,3 +284,111 @@ class GraphDispatcher:
     @property
     def has_cycle(self) -> bool:
         return bool(_check(lib.lzyb_graph_has_cycle(self.h)))
+
+
+DIR_INPUT, DIR_OUTPUT = 1, 2
+IS_BINDING, IS_WAITING_FOR_PEER, IS_DOWNLOADING, IS_READY, IS_CLOSED = 0, 1, 2, 3, 4
+
+
+def blob_put(uri: str, data: bytes) -> None:
+    _check(lib.lzyb_blob_put(_b(uri), data, len(data)))
+
+
+def blob_get(uri: str) -> bytes:
+    n = _check(lib.lzyb_blob_size(_b(uri)))
+    buf = C.create_string_buffer(max(1, n))
+    _check(lib.lzyb_blob_get(_b(uri), buf, n))
+    return buf.raw[:n]
+
+
+def blob_exists(uri: str) -> bool:
+    return lib.lzyb_blob_size(_b(uri)) >= 0
+
+
+def blob_delete(uri: str) -> None:
+    _check(lib.lzyb_blob_delete(_b(uri)))
+
+
+class ExecutionContext:
+    """SlotsExecutionContext (lzy/slots/src/main/java/ai/lzy/slots/SlotsExecutionContext.java:45-107)."""
+
+    def __init__(self, slots: "Slots", execution_id: str, task_id: str):
+        h = _H()
+        _check(lib.lzyb_ctx_create(slots.h, _b(execution_id), _b(task_id), C.byref(h)))
+        self.h, self.slots = h.value, slots
+
+    def add_slot(self, name: str, channel_id: str, direction: int) -> None:
+        _check(lib.lzyb_ctx_add_slot(self.h, _b(name), _b(channel_id), direction))
+
+    def prefetch(self) -> None:
+        _check(lib.lzyb_ctx_prefetch(self.h))
+
+    def before_execution(self, timeout_ms: int = -1) -> None:
+        _check(lib.lzyb_ctx_before_execution(self.h, timeout_ms))
+
+    def input_handle(self, name: str) -> int:
+        h = _H()
+        _check(lib.lzyb_ctx_input_handle(self.h, _b(name), C.byref(h)))
+        return h.value
+
+    def input_state(self, name: str) -> int:
+        return _check(lib.lzyb_ctx_input_state(self.h, _b(name)))
+
+    def output_open(self, name: str, nbytes: int) -> int:
+        h = _H()
+        _check(lib.lzyb_ctx_output_open(self.h, _b(name), nbytes, C.byref(h)))
+        return h.value
+
+    def output_done(self, name: str) -> None:
+        _check(lib.lzyb_ctx_output_done(self.h, _b(name)))
+
+    def after_execution(self, timeout_ms: int = -1) -> None:
+        _check(lib.lzyb_ctx_after_execution(self.h, timeout_ms))
+
+    def close(self) -> None:
+        if self.h:
+            lib.lzyb_ctx_close(self.h)
+            self.h = 0
+
+
+class Slots:
+    """One per worker: Slots (lzy/slots/src/main/java/ai/lzy/slots/Slots.java:44-106) with the
+    LzySlotsApi entry points (StartTransfer / Read) as methods."""
+
+    def __init__(self, cm: ChannelManager, gpu: int, api_url: str):
+        h = _H()
+        _check(lib.lzyb_slots_create(cm.h, gpu, _b(api_url), C.byref(h)))
+        self.h, self.cm, self.gpu, self.api_url = h.value, cm, gpu, api_url
+
+    def set_chunk_bytes(self, n: int) -> None:
+        _check(lib.lzyb_slots_set_chunk_bytes(self.h, n))
+
+    def context(self, execution_id: str, task_id: str) -> ExecutionContext:
+        return ExecutionContext(self, execution_id, task_id)
+
+    def start_transfer(self, slot_id: str, peer: Peer, transfer_id: str) -> None:
+        d = PeerDesc()
+        d.peer_id, d.kind, d.url = peer.peer_id.encode(), peer.kind, peer.url.encode()
+        _check(lib.lzyb_slots_start_transfer(self.h, _b(slot_id), C.byref(d), _b(transfer_id)))
+
+    def read(self, peer_id: str, offset: int, max_len: int = 2 << 20) -> Optional[bytes]:
+        """one ReadDataChunk; None = the EOS control message"""
+        buf = C.create_string_buffer(max_len)
+        n = lib.lzyb_slots_read(self.h, _b(peer_id), offset, buf, max_len)
+        if n == N.EOF:
+            return None
+        _check(n)
+        return buf.raw[:n]
+
+    def close(self) -> None:
+        if self.h:
+            lib.lzyb_slots_free(self.h)
+            self.h = 0
+
+
+def pump_start(cm: ChannelManager) -> None:
+    _check(lib.lzyb_cm_pump_start(cm.h))
+
+
+def pump_stop(cm: ChannelManager) -> None:
+    _check(lib.lzyb_cm_pump_stop(cm.h))

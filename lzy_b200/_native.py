@@ -130,6 +130,7 @@ _SIGNATURES = {
     "lzyb_device_count": (C.c_int, []),
     "lzyb_last_error": (C.c_char_p, []),
     "lzyb_strerror": (C.c_char_p, [C.c_int]),
+    "lzyb_set_last_error": (C.c_int, [C.c_char_p]),
     "lzyb_slot_create": (C.c_int, [C.c_char_p, C.c_int, C.c_uint64, C.POINTER(_H)]),
     "lzyb_slot_device_ptr": (C.c_int, [_H, C.POINTER(_P)]),
     "lzyb_slot_set_meta": (C.c_int, [_H, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),

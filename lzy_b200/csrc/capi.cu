@@ -360,6 +360,10 @@ extern "C" {
 int lzyb_abi_version(void) { return LZYB_ABI_VERSION; }
 const char* lzyb_last_error(void) { return lzyb_host::err_buf(); }
 int lzyb_is_initialized(void) { return g.inited ? 1 : 0; }
+int lzyb_set_last_error(const char* message) {
+    fail(0, "%s", message ? message : "");
+    return LZYB_OK;
+}
 int lzyb_device_count(void) { return g.inited ? (int)g.devs.size() : 0; }
 
 const char* lzyb_strerror(int code) {
@@ -840,9 +844,11 @@ static int finish_common(Slot& dst, const uint64_t expect[2], const Slot* src, v
         memset(&p, 0, sizeof(p));
         p.ctl = dst.ctl;
         p.total_nbytes = dst.nbytes;
-        p.fin = FIN_VERIFY;
-        p.expect[0] = expect[0];
-        p.expect[1] = expect[1];
+        p.fin = expect ? FIN_VERIFY : FIN_PUBLISH;
+        if (expect) {
+            p.expect[0] = expect[0];
+            p.expect[1] = expect[1];
+        }
         p.dst_hdr = reinterpret_cast<lzyb_frame_header_t*>(dst.buf);
         if (src) {
             dst.dtype = src->dtype;
@@ -879,9 +885,9 @@ int lzyb_input_finish(lzyb_handle_t dst_h, lzyb_handle_t src_h, void* stream) {
 
 int lzyb_input_finish_expect(lzyb_handle_t dst_h, const uint64_t digest[2], void* stream) {
     auto dst = find(dst_h);
-    if (!dst || !digest) return fail(LZYB_E_ARG, "unknown slot handle");
+    if (!dst) return fail(LZYB_E_ARG, "unknown slot handle");
     std::lock_guard<std::mutex> lk(dst->mu);
-    return finish_common(*dst, digest, nullptr, stream);
+    return finish_common(*dst, digest, nullptr, stream);  // digest == NULL: publish what was computed
 }
 
 int64_t lzyb_input_write_host(lzyb_handle_t dst_h, uint64_t offset, const void* src_host, uint64_t len, void* stream) {

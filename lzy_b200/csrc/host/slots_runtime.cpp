@@ -1,0 +1,980 @@
+// slots_runtime.cpp — the worker-side slot state machines, re-built over HBM frames.
+//
+// What each piece replaces (paths relative to lzy/slots/src/main/java/ai/lzy/slots/):
+//   SlotsInstance     Slots.java:44-106              (the gRPC server becomes an in-process registry; the RPC
+//                                                      entry points lzyb_slots_start_transfer / lzyb_slots_read stay)
+//   SlotsServiceImpl  SlotsService.java:21-69        register / unregister / read / startTransfer routing + error codes
+//   ExecCtx           SlotsExecutionContext.java:45-107
+//   InputSlotImpl     InputSlot.java:127-295         one thread per input slot, same state machine, same failover loop
+//   OutputSlotImpl    OutputSlot.java:135-273        prepare thread: waitCompleted → register → bind → storage upload
+//   make_input_transfer / storage upload              transfers/TransferFactory.java:19-33, SlotInputTransfer.java:43-99,
+//                                                      StorageInputTransfer.java:32-41, StorageOutputTransfer.java:30-40
+// The byte movers are gone: a "transfer" is a CUDA pull kernel over NVLink/HBM issued through the
+// backend table (default: the lzyb_* data plane), verified against the producer's digest.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../../include/lzy_b200_host.h"
+#include "host_common.h"
+
+namespace {
+
+using lzyb_host::fail;
+using lzyb_host::scopy;
+
+// ---- backend seam ------------------------------------------------------------------------------
+const lzyb_backend_ops_t kHbmBackend = {
+    lzyb_slot_create, lzyb_input_open,      lzyb_slot_commit,         lzyb_slot_read,       lzyb_slot_info,
+    lzyb_slot_find,   lzyb_slot_close,      lzyb_transfer_chunk,      lzyb_input_finish,    lzyb_input_write_host,
+    lzyb_input_finish_expect, lzyb_input_to_output, lzyb_input_reset,
+};
+std::atomic<const lzyb_backend_ops_t*> g_ops{&kHbmBackend};
+lzyb_backend_ops_t g_custom_ops;
+const lzyb_backend_ops_t& ops() { return *g_ops.load(); }
+
+// ---- host blob store (storage peers) -----------------------------------------------------------------
+struct Blob {
+    std::vector<uint8_t> data;
+    bool has_digest = false;   // known when the object was uploaded from a committed slot
+    uint64_t digest[2] = {0, 0};
+};
+std::mutex g_blob_mu;
+std::map<std::string, std::shared_ptr<Blob>> g_blobs;
+
+std::shared_ptr<Blob> blob_find(const std::string& uri) {
+    std::lock_guard<std::mutex> lk(g_blob_mu);
+    auto it = g_blobs.find(uri);
+    return it == g_blobs.end() ? nullptr : it->second;
+}
+
+// ---- a tiny future -------------------------------------------------------------------------------------
+struct Completion {
+    std::mutex mu;
+    std::condition_variable cv;
+    int state = 0;  // 0 pending, 1 ok, 2 failed
+    std::string error;
+    void complete() {
+        std::lock_guard<std::mutex> lk(mu);
+        if (state == 0) state = 1;
+        cv.notify_all();
+    }
+    void fail_with(const std::string& e) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (state == 0) {
+            state = 2;
+            error = e;
+        }
+        cv.notify_all();
+    }
+    bool done() {
+        std::lock_guard<std::mutex> lk(mu);
+        return state != 0;
+    }
+    // 1 ok, 2 failed, 0 timeout
+    int wait(int timeout_ms) {
+        std::unique_lock<std::mutex> lk(mu);
+        if (timeout_ms < 0)
+            cv.wait(lk, [&] { return state != 0; });
+        else
+            cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return state != 0; });
+        return state;
+    }
+};
+
+struct SlotsInstance;
+struct ExecCtx;
+
+// ---- Slot / SlotInternal ---------------------------------------------------------------------------
+struct SlotBase {
+    std::string id, channel_id;
+    ExecCtx* ctx = nullptr;
+    virtual ~SlotBase() = default;
+    virtual bool is_input() const = 0;
+    virtual int start_transfer(const lzyb_peer_desc_t& peer, const std::string& transfer_id) = 0;
+    virtual int64_t read(uint64_t offset, void* dst, uint64_t len) = 0;
+    virtual Completion& before() = 0;
+    virtual Completion& after() = 0;
+    virtual void close() = 0;
+    virtual void join() = 0;
+};
+
+// ---- SlotsService --------------------------------------------------------------------------------------
+struct SlotsServiceImpl {
+    std::shared_mutex mu;
+    std::unordered_map<std::string, std::shared_ptr<SlotBase>> slots;
+    void reg(const std::shared_ptr<SlotBase>& s) {
+        std::unique_lock<std::shared_mutex> lk(mu);
+        slots[s->id] = s;
+    }
+    void unreg(const std::string& id) {
+        std::unique_lock<std::shared_mutex> lk(mu);
+        slots.erase(id);
+    }
+    std::shared_ptr<SlotBase> find(const std::string& id) {
+        std::shared_lock<std::shared_mutex> lk(mu);
+        auto it = slots.find(id);
+        return it == slots.end() ? nullptr : it->second;
+    }
+};
+
+struct SlotsInstance {
+    lzyb_handle_t handle = 0;
+    lzyb_handle_t cm = 0;
+    int gpu = 0;
+    std::string api_url;
+    std::atomic<uint64_t> chunk_bytes{0};
+    SlotsServiceImpl service;
+    std::mutex mu;
+    std::vector<std::shared_ptr<ExecCtx>> contexts;
+    std::atomic<uint64_t> idk{0};
+    std::string next_idk(const std::string& what) { return api_url + "/" + what + "/" + std::to_string(++idk); }
+};
+
+struct OutputSlotImpl;
+struct InputSlotImpl;
+
+struct ExecCtx : std::enable_shared_from_this<ExecCtx> {
+    lzyb_handle_t handle = 0;
+    SlotsInstance* inst = nullptr;
+    std::string execution_id, task_id;
+    struct Desc {
+        std::string name, channel;
+        int direction;
+    };
+    std::vector<Desc> descs;
+    std::mutex mu;
+    std::vector<std::shared_ptr<SlotBase>> slots;
+    std::map<std::string, std::shared_ptr<InputSlotImpl>> inputs;
+    std::map<std::string, std::shared_ptr<OutputSlotImpl>> outputs;
+    bool built = false, closed = false;
+    void add(const std::shared_ptr<SlotBase>& s) {
+        std::lock_guard<std::mutex> lk(mu);
+        slots.push_back(s);
+    }
+};
+
+// ---- OutputSlot ------------------------------------------------------------------------------------------
+struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
+    SlotsInstance* inst;
+    lzyb_handle_t backend = 0;  // HBM frame (OutputSlotBackend)
+    bool own_backend = true;
+    Completion before_, complete_;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool data_done = false, closed = false;
+    std::thread prepare;
+
+    ~OutputSlotImpl() override {
+        if (prepare.joinable()) prepare.detach();
+    }
+    bool is_input() const override { return false; }
+    Completion& before() override { return before_; }
+    Completion& after() override { return complete_; }
+
+    int start_transfer(const lzyb_peer_desc_t&, const std::string&) override {
+        return fail(LZYB_E_INTERNAL, "Cannot start transfer in output slot");  // NotImplementedException → INTERNAL
+    }
+
+    int64_t read(uint64_t offset, void* dst, uint64_t len) override {
+        // OutputSlot.ReadThread: bytes [offset, end) in ≤ len chunks, then EOS (OutputSlot.java:238-265)
+        int64_t n = ops().slot_read(backend, offset, dst, len);
+        if (n < LZYB_EOF) return fail(LZYB_E_INTERNAL, "Error while reading from backend: %s", lzyb_last_error());
+        return n;
+    }
+
+    void start() {
+        before_.complete();
+        auto self = shared_from_this();
+        prepare = std::thread([self] { self->run(); });
+    }
+
+    void signal_data_done() {
+        std::lock_guard<std::mutex> lk(mu);
+        data_done = true;
+        cv.notify_all();
+    }
+
+    void run() {
+        // PrepareThread.runImpl (OutputSlot.java:158-192)
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return data_done || closed; });  // backend.waitCompleted(): the op closed its output
+            if (closed) {
+                complete_.fail_with("Slot closed before ready");
+                return;
+            }
+        }
+        uint64_t dg[2];
+        if (ops().slot_commit(backend, dg, nullptr) != LZYB_OK) {
+            complete_.fail_with(std::string("Error while binding output slot: ") + lzyb_last_error());
+            return;
+        }
+        inst->service.reg(shared_from_this());  // enable requests from outside
+        lzyb_bind_result_t res;
+        int rc = lzyb_cm_bind(inst->cm, inst->next_idk("bind").c_str(), channel_id.c_str(), id.c_str(),
+                              ctx ? ctx->execution_id.c_str() : "", inst->api_url.c_str(), LZYB_ROLE_PRODUCER, &res);
+        if (rc != LZYB_OK) {
+            complete_.fail_with(std::string("Error while binding output slot: ") + lzyb_last_error());
+            return;
+        }
+        if (res.has_peer) {
+            // bind answered with the channel's storage consumer: upload, then report
+            bool ok = res.peer.kind == LZYB_PEER_STORAGE && upload_to_storage(res.peer.url);
+            if (!ok) {
+                std::string why = res.peer.kind == LZYB_PEER_STORAGE ? lzyb_last_error() : "Cannot create transfer for peer";
+                lzyb_bind_result_t dummy;
+                lzyb_cm_transfer_failed(inst->cm, inst->next_idk("fail").c_str(), channel_id.c_str(), res.transfer_id,
+                                        why.c_str(), &dummy);
+                complete_.fail_with("Error while transferring data to peer " + std::string(res.peer.peer_id) + ": " + why);
+                return;
+            }
+            if (lzyb_cm_transfer_completed(inst->cm, inst->next_idk("done").c_str(), channel_id.c_str(), res.transfer_id) != LZYB_OK) {
+                complete_.fail_with(std::string("Error while binding output slot: ") + lzyb_last_error());
+                return;
+            }
+        }
+        complete_.complete();  // "Slot is ready"
+    }
+
+    // StorageOutputTransfer.readFrom(backend.readFromOffset(0))
+    bool upload_to_storage(const char* uri) {
+        lzyb_slot_info_t info;
+        if (ops().slot_info(backend, &info) != LZYB_OK) return false;
+        auto blob = std::make_shared<Blob>();
+        blob->data.resize(info.nbytes);
+        uint64_t off = 0;
+        while (off < info.nbytes) {
+            uint64_t want = std::min<uint64_t>(info.nbytes - off, 64ull << 20);
+            int64_t n = ops().slot_read(backend, off, blob->data.data() + off, want);
+            if (n < 0) return false;
+            off += (uint64_t)n;
+        }
+        blob->has_digest = true;
+        blob->digest[0] = info.digest[0];
+        blob->digest[1] = info.digest[1];
+        std::lock_guard<std::mutex> lk(g_blob_mu);
+        g_blobs[uri] = blob;
+        return true;
+    }
+
+    void close() override {
+        // OutputSlot.close (OutputSlot.java:90-133): unregister, fail the future, unbind (errors ignored), close backend
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (closed) return;
+            closed = true;
+            cv.notify_all();
+        }
+        inst->service.unreg(id);
+        complete_.fail_with("Slot closed before ready");
+        lzyb_cm_unbind(inst->cm, channel_id.c_str(), id.c_str());
+        if (backend && own_backend) ops().slot_close(backend);
+    }
+
+    void join() override {
+        if (prepare.joinable()) prepare.join();
+    }
+};
+
+// ---- InputTransfer variants ------------------------------------------------------------------------------
+struct InputTransfer {
+    virtual ~InputTransfer() = default;
+    // bytes moved, LZYB_EOF, LZYB_E_PEER (ReadException) or another negative code (IOException)
+    virtual int64_t transfer_chunk_to(lzyb_handle_t sink, uint64_t offset, uint64_t max_len) = 0;
+    virtual int finish(lzyb_handle_t sink) = 0;
+    virtual uint64_t nbytes() const = 0;
+};
+
+// SlotInputTransfer: consumer-pull from the peer's frame (same GPU: HBM; other GPU: NVLink)
+struct SlotPullTransfer : InputTransfer {
+    lzyb_handle_t peer = 0;
+    uint64_t size = 0;
+    int64_t transfer_chunk_to(lzyb_handle_t sink, uint64_t offset, uint64_t max_len) override {
+        return ops().transfer_chunk(sink, peer, offset, max_len, nullptr);
+    }
+    int finish(lzyb_handle_t sink) override { return ops().input_finish(sink, peer, nullptr); }
+    uint64_t nbytes() const override { return size; }
+};
+
+// StorageInputTransfer: the whole object in one go, then EOF (StorageInputTransfer.java:32-41)
+struct BlobTransfer : InputTransfer {
+    std::shared_ptr<Blob> blob;
+    bool sent = false;
+    int64_t transfer_chunk_to(lzyb_handle_t sink, uint64_t offset, uint64_t) override {
+        if (sent || offset >= blob->data.size()) return LZYB_EOF;
+        // a storage object cannot resume mid-way with a digest of its own: restart the sink at 0
+        if (offset != 0) {
+            if (ops().input_reset(sink) != LZYB_OK) return LZYB_E_LOCAL;
+        }
+        uint64_t off = 0;
+        const uint64_t total = blob->data.size();
+        while (off < total) {
+            uint64_t step = std::min<uint64_t>(total - off, 64ull << 20);
+            int64_t n = ops().input_write_host(sink, off, blob->data.data() + off, step, nullptr);
+            if (n < 0) return n == LZYB_E_PEER ? LZYB_E_PEER : n;
+            off += (uint64_t)n;
+        }
+        sent = true;
+        return (int64_t)total;
+    }
+    int finish(lzyb_handle_t sink) override {
+        // an object uploaded from a slot carries that slot's digest; a pre-existing object has none
+        // and the digest computed while it landed becomes the published one
+        return ops().input_finish_expect(sink, blob->has_digest ? blob->digest : nullptr, nullptr);
+    }
+    uint64_t nbytes() const override { return blob->data.size(); }
+};
+
+// ---- InputSlot ---------------------------------------------------------------------------------------------
+struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
+    SlotsInstance* inst;
+    lzyb_handle_t backend = 0;  // HBM frame (InputSlotBackend), opened once the peer (hence the size) is known
+    std::atomic<int> state{LZYB_IS_BINDING};
+    Completion ready_, after_;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool have_peer = false, closed = false, handed_over = false;
+    lzyb_peer_desc_t peer{};
+    std::string transfer_id;
+    std::thread thr;
+
+    ~InputSlotImpl() override {
+        if (thr.joinable()) thr.detach();
+    }
+    bool is_input() const override { return true; }
+    Completion& before() override { return ready_; }
+    Completion& after() override { return after_; }
+
+    int64_t read(uint64_t, void*, uint64_t) override {
+        return fail(LZYB_E_UNIMPLEMENTED, "unexpected `read` call on input slot %s", id.c_str());
+    }
+
+    int start_transfer(const lzyb_peer_desc_t& p, const std::string& tid) override {
+        std::lock_guard<std::mutex> lk(mu);
+        if (have_peer) return fail(LZYB_E_INTERNAL, "Transfer is already started in this slot");  // IllegalStateException → INTERNAL
+        peer = p;
+        transfer_id = tid;
+        have_peer = true;
+        cv.notify_all();
+        return LZYB_OK;
+    }
+
+    void start() {
+        after_.complete();
+        auto self = shared_from_this();
+        thr = std::thread([self] {
+            std::string err;
+            if (!self->run(err)) self->ready_.fail_with(err.empty() ? "Closed before ready" : err);
+            self->clear();
+        });
+    }
+
+    std::unique_ptr<InputTransfer> make_transfer(const lzyb_peer_desc_t& p, std::string& err) {
+        // TransferFactory.input(peer, offset)
+        if (p.kind == LZYB_PEER_STORAGE) {
+            auto blob = blob_find(p.url);
+            if (!blob) {
+                err = std::string("Error while reading from storage: no object at ") + p.url;
+                return nullptr;
+            }
+            auto t = std::make_unique<BlobTransfer>();
+            t->blob = blob;
+            return t;
+        }
+        lzyb_handle_t h = 0;
+        if (ops().slot_find(p.peer_id, &h) != LZYB_OK) {
+            err = std::string("Cannot read from slot peer ") + p.peer_id + ": " + lzyb_last_error();
+            return nullptr;
+        }
+        lzyb_slot_info_t info;
+        if (ops().slot_info(h, &info) != LZYB_OK) {
+            err = std::string("Cannot read from slot peer ") + p.peer_id + ": " + lzyb_last_error();
+            return nullptr;
+        }
+        auto t = std::make_unique<SlotPullTransfer>();
+        t->peer = h;
+        t->size = info.nbytes;
+        return t;
+    }
+
+    bool run(std::string& err) {
+        // InputSlot.runImpl (InputSlot.java:127-169)
+        inst->service.reg(shared_from_this());  // registering before bind
+        lzyb_bind_result_t resp;
+        if (is_closed()) return false;
+        int rc = lzyb_cm_bind(inst->cm, inst->next_idk("bind").c_str(), channel_id.c_str(), id.c_str(),
+                              ctx ? ctx->execution_id.c_str() : "", inst->api_url.c_str(), LZYB_ROLE_CONSUMER, &resp);
+        if (rc != LZYB_OK) {
+            err = std::string("Bind failed: ") + lzyb_last_error();
+            return false;
+        }
+        lzyb_peer_desc_t cur;
+        std::string tid;
+        if (!resp.has_peer) {
+            state = LZYB_IS_WAITING_FOR_PEER;
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return have_peer || closed; });
+            if (closed) return false;
+            cur = peer;
+            tid = transfer_id;
+        } else {
+            std::lock_guard<std::mutex> lk(mu);
+            if (closed) return false;
+            have_peer = true;  // a late StartTransfer must now fail
+            cur = resp.peer;
+            tid = resp.transfer_id;
+        }
+        state = LZYB_IS_DOWNLOADING;
+        inst->service.unreg(id);  // got peer, unregistering
+        if (!download(cur, tid, err)) return false;
+        state = LZYB_IS_READY;
+        // re-publish the delivered bytes as producer "<slotId>-out" on the same channel
+        // (InputSlot.java:160-168).  The companion joins the context before `ready` completes so that
+        // an afterExecution() issued right after beforeExecution() already sees it.
+        if (ops().input_to_output(backend) == LZYB_OK) {
+            auto out = std::make_shared<OutputSlotImpl>();
+            out->inst = inst;
+            out->id = id + "-out";
+            out->channel_id = channel_id;
+            out->ctx = ctx;
+            out->backend = backend;
+            out->own_backend = false;  // the frame stays owned by this slot's context entry
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                handed_over = true;
+            }
+            if (ctx) ctx->add(out);
+            out->start();
+            out->signal_data_done();
+        }
+        ready_.complete();
+        return true;
+    }
+
+    bool is_closed() {
+        std::lock_guard<std::mutex> lk(mu);
+        return closed;
+    }
+
+    bool download(lzyb_peer_desc_t cur, std::string tid, std::string& err) {
+        // InputSlot.download (InputSlot.java:223-295)
+        uint64_t offset = 0;
+        std::string terr;
+        auto transfer = make_transfer(cur, terr);
+        std::string peer_fail_reason = transfer ? "" : terr;
+        bool need_new_peer = !transfer;
+        while (true) {
+            if (is_closed()) {
+                err = "Closed before ready";
+                return false;
+            }
+            if (need_new_peer) {
+                lzyb_bind_result_t np;
+                int rc = lzyb_cm_transfer_failed(inst->cm, inst->next_idk("failed").c_str(), channel_id.c_str(), tid.c_str(),
+                                                 peer_fail_reason.c_str(), &np);
+                if (rc != LZYB_OK || !np.has_peer) {
+                    err = std::string("Cannot get data from any peer: ") + lzyb_last_error();
+                    return false;
+                }
+                cur = np.peer;
+                tid = np.transfer_id;
+                need_new_peer = false;
+                peer_fail_reason.clear();
+                transfer = make_transfer(cur, terr);
+                if (!transfer) {
+                    peer_fail_reason = terr;
+                    need_new_peer = true;
+                    continue;
+                }
+            }
+            if (!backend) {  // FileInputBackend ctor: the sink exists once the size is known
+                if (ops().input_open(id.c_str(), inst->gpu, transfer->nbytes(), &backend) != LZYB_OK) {
+                    err = std::string("Error while reading into backend: ") + lzyb_last_error();
+                    return false;
+                }
+            }
+            lzyb_slot_info_t info;
+            if (ops().slot_info(backend, &info) == LZYB_OK) offset = info.delivered;  // reopening the channel: resume here
+            const uint64_t chunk = inst->chunk_bytes.load();
+            int64_t moved = transfer->transfer_chunk_to(backend, offset, chunk ? chunk : ~0ull);
+            if (moved == LZYB_E_PEER) {  // ReadException: mark the peer bad, ask for another one
+                peer_fail_reason = lzyb_last_error();
+                need_new_peer = true;
+                continue;
+            }
+            if (moved < LZYB_EOF) {  // error on the backend side: this slot fails
+                err = std::string("Error while reading into backend: ") + lzyb_last_error();
+                return false;
+            }
+            if (moved == LZYB_EOF) {
+                int frc = transfer->finish(backend);
+                if (frc == LZYB_E_PEER) {  // delivered bytes are not what the producer committed
+                    peer_fail_reason = lzyb_last_error();
+                    need_new_peer = true;
+                    continue;
+                }
+                if (frc != LZYB_OK) {
+                    err = std::string("Error while reading into backend: ") + lzyb_last_error();
+                    return false;
+                }
+                if (lzyb_cm_transfer_completed(inst->cm, inst->next_idk("completed").c_str(), channel_id.c_str(), tid.c_str()) != LZYB_OK) {
+                    err = std::string("TransferCompleted failed: ") + lzyb_last_error();
+                    return false;
+                }
+                return true;
+            }
+            offset += (uint64_t)moved;
+        }
+    }
+
+    void clear() {
+        // InputSlot.clear (InputSlot.java:195-221): runs after success as well as after failure
+        bool keep;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            keep = handed_over;
+            closed = true;
+        }
+        if (!keep && backend) {
+            ops().slot_close(backend);
+            backend = 0;
+        }
+        state = LZYB_IS_CLOSED;
+        inst->service.unreg(id);
+        ready_.fail_with("Closed before ready");
+        lzyb_cm_unbind(inst->cm, channel_id.c_str(), id.c_str());  // error ignored
+    }
+
+    void close() override {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (closed && !handed_over) return;
+            closed = true;
+            cv.notify_all();
+        }
+    }
+
+    void join() override {
+        if (thr.joinable()) thr.join();
+    }
+
+    void release_frame() {
+        if (backend) {
+            ops().slot_close(backend);
+            backend = 0;
+        }
+    }
+};
+
+// ---- registries ------------------------------------------------------------------------------------------
+std::shared_mutex g_mu;
+std::unordered_map<lzyb_handle_t, std::shared_ptr<SlotsInstance>> g_instances;
+std::unordered_map<lzyb_handle_t, std::shared_ptr<ExecCtx>> g_ctxs;
+lzyb_handle_t g_next = 0x6000000000000001ull;
+
+std::shared_ptr<SlotsInstance> get_inst(lzyb_handle_t h) {
+    std::shared_lock<std::shared_mutex> lk(g_mu);
+    auto it = g_instances.find(h);
+    return it == g_instances.end() ? nullptr : it->second;
+}
+std::shared_ptr<ExecCtx> get_ctx(lzyb_handle_t h) {
+    std::shared_lock<std::shared_mutex> lk(g_mu);
+    auto it = g_ctxs.find(h);
+    return it == g_ctxs.end() ? nullptr : it->second;
+}
+
+int build_slots(ExecCtx& c) {
+    // SlotsExecutionContext.beforeExecution, first half (SlotsExecutionContext.java:45-63)
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.closed) return fail(LZYB_E_STATE, "context is closed");
+    if (c.built) return LZYB_OK;
+    c.built = true;
+    for (auto& d : c.descs) {
+        if (d.direction == LZYB_DIR_INPUT) {
+            auto s = std::make_shared<InputSlotImpl>();
+            s->inst = c.inst;
+            s->id = d.name;
+            s->channel_id = d.channel;
+            s->ctx = &c;
+            c.slots.push_back(s);
+            c.inputs[d.name] = s;
+            s->start();
+        } else {
+            auto s = std::make_shared<OutputSlotImpl>();
+            s->inst = c.inst;
+            s->id = d.name;
+            s->channel_id = d.channel;
+            s->ctx = &c;
+            c.slots.push_back(s);
+            c.outputs[d.name] = s;
+            s->start();
+        }
+    }
+    return LZYB_OK;
+}
+
+int wait_all(ExecCtx& c, bool before, int timeout_ms) {
+    auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms < 0 ? 0 : timeout_ms);
+    size_t i = 0;
+    while (true) {
+        std::shared_ptr<SlotBase> s;
+        {
+            std::lock_guard<std::mutex> lk(c.mu);
+            if (i >= c.slots.size()) break;  // slots added meanwhile ("-out" companions) are picked up too
+            s = c.slots[i++];
+        }
+        Completion& f = before ? s->before() : s->after();
+        int left = -1;
+        if (timeout_ms >= 0) {
+            auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(deadline - std::chrono::steady_clock::now()).count();
+            left = ms < 0 ? 0 : (int)ms;
+        }
+        int st = f.wait(left);
+        if (st == 0) return fail(LZYB_E_UNAVAILABLE, "timed out waiting for slot %s", s->id.c_str());
+        if (st == 2) return fail(LZYB_E_LOCAL, "slot %s failed: %s", s->id.c_str(), f.error.c_str());
+    }
+    return LZYB_OK;
+}
+
+void close_ctx(ExecCtx& c) {
+    std::vector<std::shared_ptr<SlotBase>> slots;
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (c.closed) return;
+        c.closed = true;
+        slots = c.slots;
+    }
+    for (auto& s : slots) s->close();
+    for (auto& s : slots) s->join();
+    // companions created while closing
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        slots = c.slots;
+    }
+    for (auto& s : slots) {
+        s->close();
+        s->join();
+    }
+    for (auto& kv : c.inputs) kv.second->release_frame();
+}
+
+// ---- channel-manager action pump -----------------------------------------------------------------------
+struct Pump {
+    std::thread thr;
+    std::atomic<bool> stop{false};
+};
+std::mutex g_pump_mu;
+std::map<lzyb_handle_t, std::shared_ptr<Pump>> g_pumps;
+
+void pump_loop(lzyb_handle_t cm, std::shared_ptr<Pump> p) {
+    while (!p->stop.load()) {
+        lzyb_cm_action_t a;
+        int got = lzyb_cm_poll_action(cm, &a, 20);
+        if (got <= 0) continue;
+        if (a.kind == LZYB_ACT_START_TRANSFER) {
+            // ActionScheduler.startTransfer: deliver StartTransfer(slot_id = consumer, peer = producer).
+            // The consumer is looked up by slot id across the workers of this process.
+            std::vector<std::shared_ptr<SlotsInstance>> insts;
+            {
+                std::shared_lock<std::shared_mutex> lk(g_mu);
+                for (auto& kv : g_instances)
+                    if (kv.second->cm == cm) insts.push_back(kv.second);
+            }
+            int rc = LZYB_E_NOT_FOUND;
+            for (auto& inst : insts) {
+                auto s = inst->service.find(a.consumer_id);
+                if (!s) continue;
+                rc = s->start_transfer(a.producer, a.transfer_id);
+                break;
+            }
+            lzyb_cm_action_result(cm, a.channel_id, a.transfer_id, rc == LZYB_OK, rc == LZYB_OK ? "" : "Cannot connect.");
+        } else if (a.kind == LZYB_ACT_ABORT_WORKFLOW) {
+            // lzy-service aborts the workflow: every context of that execution is closed
+            std::vector<std::shared_ptr<ExecCtx>> ctxs;
+            {
+                std::shared_lock<std::shared_mutex> lk(g_mu);
+                for (auto& kv : g_ctxs)
+                    if (kv.second->inst->cm == cm && kv.second->execution_id == a.execution_id) ctxs.push_back(kv.second);
+            }
+            for (auto& c : ctxs) {
+                std::vector<std::shared_ptr<SlotBase>> slots;
+                {
+                    std::lock_guard<std::mutex> lk(c->mu);
+                    slots = c->slots;
+                }
+                for (auto& s : slots) s->close();
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int lzyb_slots_set_backend(const lzyb_backend_ops_t* o) {
+    if (!o) {
+        g_ops = &kHbmBackend;
+        return LZYB_OK;
+    }
+    g_custom_ops = *o;
+    g_ops = &g_custom_ops;
+    return LZYB_OK;
+}
+
+int lzyb_slots_create(lzyb_handle_t cm, int gpu, const char* api_url, lzyb_handle_t* out) {
+    if (!out || !api_url) return fail(LZYB_E_ARG, "null argument");
+    auto s = std::make_shared<SlotsInstance>();
+    s->cm = cm;
+    s->gpu = gpu;
+    s->api_url = api_url;
+    std::unique_lock<std::shared_mutex> lk(g_mu);
+    s->handle = g_next++;
+    g_instances[s->handle] = s;
+    *out = s->handle;
+    return LZYB_OK;
+}
+
+int lzyb_slots_free(lzyb_handle_t h) {
+    std::shared_ptr<SlotsInstance> s;
+    std::vector<std::shared_ptr<ExecCtx>> ctxs;
+    {
+        std::unique_lock<std::shared_mutex> lk(g_mu);
+        auto it = g_instances.find(h);
+        if (it == g_instances.end()) return LZYB_OK;
+        s = it->second;
+        g_instances.erase(it);
+        for (auto it2 = g_ctxs.begin(); it2 != g_ctxs.end();) {
+            if (it2->second->inst == s.get()) {
+                ctxs.push_back(it2->second);
+                it2 = g_ctxs.erase(it2);
+            } else
+                ++it2;
+        }
+    }
+    for (auto& c : ctxs) close_ctx(*c);  // Slots.close(): every context is closed
+    return LZYB_OK;
+}
+
+int lzyb_slots_set_chunk_bytes(lzyb_handle_t h, uint64_t chunk) {
+    auto s = get_inst(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slots handle");
+    if (chunk & 15) return fail(LZYB_E_ARG, "chunk size must be a multiple of 16");
+    s->chunk_bytes = chunk;
+    return LZYB_OK;
+}
+
+int lzyb_ctx_create(lzyb_handle_t slots, const char* execution_id, const char* task_id, lzyb_handle_t* out) {
+    auto inst = get_inst(slots);
+    if (!inst) return fail(LZYB_E_ARG, "unknown slots handle");
+    if (!out) return fail(LZYB_E_ARG, "null argument");
+    auto c = std::make_shared<ExecCtx>();
+    c->inst = inst.get();
+    c->execution_id = execution_id ? execution_id : "";
+    c->task_id = task_id ? task_id : "";
+    std::unique_lock<std::shared_mutex> lk(g_mu);
+    c->handle = g_next++;
+    g_ctxs[c->handle] = c;
+    *out = c->handle;
+    return LZYB_OK;
+}
+
+int lzyb_ctx_add_slot(lzyb_handle_t h, const char* slot_name, const char* channel_id, int direction) {
+    auto c = get_ctx(h);
+    if (!c) return fail(LZYB_E_ARG, "unknown context handle");
+    if (!slot_name || !channel_id) return fail(LZYB_E_ARG, "null argument");
+    if (direction != LZYB_DIR_INPUT && direction != LZYB_DIR_OUTPUT) return fail(LZYB_E_INVALID, "slot direction must be INPUT or OUTPUT");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->built) return fail(LZYB_E_STATE, "slots are already built");
+    c->descs.push_back({slot_name, channel_id, direction});
+    return LZYB_OK;
+}
+
+int lzyb_ctx_prefetch(lzyb_handle_t h) {
+    auto c = get_ctx(h);
+    if (!c) return fail(LZYB_E_ARG, "unknown context handle");
+    return build_slots(*c);
+}
+
+int lzyb_ctx_before_execution(lzyb_handle_t h, int timeout_ms) {
+    auto c = get_ctx(h);
+    if (!c) return fail(LZYB_E_ARG, "unknown context handle");
+    int rc = build_slots(*c);
+    if (rc != LZYB_OK) return rc;
+    rc = wait_all(*c, true, timeout_ms);
+    if (rc != LZYB_OK && rc != LZYB_E_UNAVAILABLE) {
+        std::string keep = lzyb_last_error();
+        close_ctx(*c);  // "Failed to initialize slots" → close()
+        return fail(rc, "%s", keep.c_str());
+    }
+    return rc;
+}
+
+int lzyb_ctx_input_handle(lzyb_handle_t h, const char* slot_name, lzyb_handle_t* out) {
+    auto c = get_ctx(h);
+    if (!c || !slot_name || !out) return fail(LZYB_E_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->inputs.find(slot_name);
+    if (it == c->inputs.end()) return fail(LZYB_E_NOT_FOUND, "Slot not found: %s", slot_name);
+    if (it->second->state.load() != LZYB_IS_READY && !it->second->ready_.done()) return fail(LZYB_E_STATE, "slot %s is not ready", slot_name);
+    if (!it->second->backend) return fail(LZYB_E_STATE, "slot %s has no data", slot_name);
+    *out = it->second->backend;
+    return LZYB_OK;
+}
+
+int lzyb_ctx_input_state(lzyb_handle_t h, const char* slot_name) {
+    auto c = get_ctx(h);
+    if (!c || !slot_name) return fail(LZYB_E_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->inputs.find(slot_name);
+    if (it == c->inputs.end()) return fail(LZYB_E_NOT_FOUND, "Slot not found: %s", slot_name);
+    if (it->second->ready_.done() && it->second->ready_.state == 1) return LZYB_IS_READY;
+    return it->second->state.load();
+}
+
+int lzyb_ctx_output_open(lzyb_handle_t h, const char* slot_name, uint64_t nbytes, lzyb_handle_t* out) {
+    auto c = get_ctx(h);
+    if (!c || !slot_name || !out) return fail(LZYB_E_ARG, "bad argument");
+    int rc = build_slots(*c);
+    if (rc != LZYB_OK) return rc;
+    std::shared_ptr<OutputSlotImpl> s;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        auto it = c->outputs.find(slot_name);
+        if (it == c->outputs.end()) return fail(LZYB_E_NOT_FOUND, "Slot not found: %s", slot_name);
+        s = it->second;
+    }
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->closed) return fail(LZYB_E_STATE, "slot %s is closed", slot_name);
+    if (s->backend) return fail(LZYB_E_STATE, "output %s is already open", slot_name);
+    rc = ops().slot_create(slot_name, c->inst->gpu, nbytes, &s->backend);
+    if (rc != LZYB_OK) return rc;
+    *out = s->backend;
+    return LZYB_OK;
+}
+
+int lzyb_ctx_output_done(lzyb_handle_t h, const char* slot_name) {
+    auto c = get_ctx(h);
+    if (!c || !slot_name) return fail(LZYB_E_ARG, "bad argument");
+    std::shared_ptr<OutputSlotImpl> s;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        auto it = c->outputs.find(slot_name);
+        if (it == c->outputs.end()) return fail(LZYB_E_NOT_FOUND, "Slot not found: %s", slot_name);
+        s = it->second;
+    }
+    if (!s->backend) return fail(LZYB_E_STATE, "output %s was never opened", slot_name);
+    s->signal_data_done();
+    return LZYB_OK;
+}
+
+int lzyb_ctx_after_execution(lzyb_handle_t h, int timeout_ms) {
+    auto c = get_ctx(h);
+    if (!c) return fail(LZYB_E_ARG, "unknown context handle");
+    int rc = wait_all(*c, false, timeout_ms);
+    if (rc != LZYB_OK && rc != LZYB_E_UNAVAILABLE) {
+        std::string keep = lzyb_last_error();
+        close_ctx(*c);  // "Failed to finalize slots" → close()
+        return fail(rc, "%s", keep.c_str());
+    }
+    return rc;
+}
+
+int lzyb_ctx_close(lzyb_handle_t h) {
+    std::shared_ptr<ExecCtx> c;
+    {
+        std::unique_lock<std::shared_mutex> lk(g_mu);
+        auto it = g_ctxs.find(h);
+        if (it == g_ctxs.end()) return LZYB_OK;
+        c = it->second;
+        g_ctxs.erase(it);
+    }
+    close_ctx(*c);
+    return LZYB_OK;
+}
+
+int lzyb_slots_start_transfer(lzyb_handle_t h, const char* slot_id, const lzyb_peer_desc_t* peer, const char* transfer_id) {
+    auto inst = get_inst(h);
+    if (!inst) return fail(LZYB_E_ARG, "unknown slots handle");
+    if (!slot_id || !peer) return fail(LZYB_E_ARG, "null argument");
+    auto s = inst->service.find(slot_id);
+    if (!s) return fail(LZYB_E_NOT_FOUND, "Slot not found: %s", slot_id);
+    return s->start_transfer(*peer, transfer_id ? transfer_id : "");
+}
+
+int64_t lzyb_slots_read(lzyb_handle_t h, const char* peer_id, uint64_t offset, void* dst, uint64_t len) {
+    auto inst = get_inst(h);
+    if (!inst) return fail(LZYB_E_ARG, "unknown slots handle");
+    if (!peer_id) return fail(LZYB_E_ARG, "null argument");
+    auto s = inst->service.find(peer_id);
+    if (!s) return fail(LZYB_E_NOT_FOUND, "Slot not found: %s", peer_id);
+    return s->read(offset, dst, len);
+}
+
+int lzyb_cm_pump_start(lzyb_handle_t cm) {
+    std::lock_guard<std::mutex> lk(g_pump_mu);
+    if (g_pumps.count(cm)) return LZYB_OK;
+    auto p = std::make_shared<Pump>();
+    p->thr = std::thread(pump_loop, cm, p);
+    g_pumps[cm] = p;
+    return LZYB_OK;
+}
+
+int lzyb_cm_pump_stop(lzyb_handle_t cm) {
+    std::shared_ptr<Pump> p;
+    {
+        std::lock_guard<std::mutex> lk(g_pump_mu);
+        auto it = g_pumps.find(cm);
+        if (it == g_pumps.end()) return LZYB_OK;
+        p = it->second;
+        g_pumps.erase(it);
+    }
+    p->stop = true;
+    if (p->thr.joinable()) p->thr.join();
+    return LZYB_OK;
+}
+
+int lzyb_blob_put(const char* uri, const void* data, uint64_t len) {
+    if (!uri || (len && !data)) return fail(LZYB_E_ARG, "null argument");
+    auto b = std::make_shared<Blob>();
+    b->data.assign(static_cast<const uint8_t*>(data), static_cast<const uint8_t*>(data) + len);
+    std::lock_guard<std::mutex> lk(g_blob_mu);
+    g_blobs[uri] = b;
+    return LZYB_OK;
+}
+
+int64_t lzyb_blob_size(const char* uri) {
+    if (!uri) return fail(LZYB_E_ARG, "null argument");
+    auto b = blob_find(uri);
+    if (!b) return fail(LZYB_E_NOT_FOUND, "no object at %s", uri);
+    return (int64_t)b->data.size();
+}
+
+int64_t lzyb_blob_get(const char* uri, void* dst, uint64_t cap) {
+    if (!uri) return fail(LZYB_E_ARG, "null argument");
+    auto b = blob_find(uri);
+    if (!b) return fail(LZYB_E_NOT_FOUND, "no object at %s", uri);
+    if (b->data.size() > cap) return fail(LZYB_E_ARG, "object holds %zu bytes, buffer %llu", b->data.size(), (unsigned long long)cap);
+    if (!b->data.empty()) memcpy(dst, b->data.data(), b->data.size());
+    return (int64_t)b->data.size();
+}
+
+int lzyb_blob_delete(const char* uri) {
+    if (!uri) return fail(LZYB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(g_blob_mu);
+    g_blobs.erase(uri);
+    return LZYB_OK;
+}
+
+}  // extern "C"

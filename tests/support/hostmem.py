@@ -1,0 +1,55 @@
+"""Test-only: builds and installs the in-memory slot backend (tests/support/hostmem_backend.c) at the
+backend seam of the C++ slots runtime — the analogue of SlotsTest.InMemBackend."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent.parent
+_SO = Path(__file__).resolve().parent / "_build" / "libhostmem_backend.so"
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    src = Path(__file__).resolve().parent / "hostmem_backend.c"
+    libdir = ROOT / "lzy_b200" / "lib"
+    if not _SO.exists() or _SO.stat().st_mtime < src.stat().st_mtime:
+        _SO.parent.mkdir(exist_ok=True)
+        subprocess.run(["gcc", "-O1", "-fPIC", "-shared", "-Wall", "-o", str(_SO), str(src), f"-L{libdir}",
+                        "-llzy_b200", f"-Wl,-rpath,{libdir}", "-lpthread"], check=True)
+    from lzy_b200 import _native  # noqa: F401  (liblzy_b200.so must be loaded first)
+    lib = C.CDLL(str(_SO))
+    lib.hostmem_write.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.hostmem_peek.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.hostmem_peek.restype = C.c_int64
+    lib.hostmem_set_fail_after.argtypes = [C.c_uint64, C.c_longlong]
+    lib.hostmem_set_fail_read.argtypes = [C.c_uint64, C.c_int]
+    lib.hostmem_corrupt.argtypes = [C.c_uint64, C.c_uint64]
+    _lib = lib
+    return lib
+
+
+def install():
+    from lzy_b200 import _host
+    lib = load()
+    ops = C.c_void_p.in_dll(lib, "hostmem_backend_ops")
+    _host.lib.lzyb_slots_set_backend(C.addressof(ops))
+    return lib
+
+
+def uninstall():
+    from lzy_b200 import _host
+    _host.lib.lzyb_slots_set_backend(None)
+
+
+def write(h, data: bytes, offset=0):
+    assert load().hostmem_write(h, offset, data, len(data)) == 0
+
+
+def peek(h, n, offset=0) -> bytes:
+    buf = C.create_string_buffer(max(1, n))
+    got = load().hostmem_peek(h, offset, buf, n)
+    assert got >= 0
+    return buf.raw[:got]

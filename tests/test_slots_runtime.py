@@ -1,0 +1,296 @@
+"""The C++ slot state machines (InputSlot / OutputSlot / SlotsExecutionContext / SlotsService) against
+the reference's own slot tests, run over the test-only in-memory backend installed at the backend
+seam — the role SlotsTest.InMemBackend plays in
+lzy/slots/src/test/java/ai/lzy/slots/SlotsTest.java (testSimple :130-187, testConnect :216-256,
+testInputRestart :339-393, testReadFromStorage / testWriteToStorage :395-462, testExecutionContext
+:524-626, testLargeData :628-693, testRestoreReadFromOffset :803-864) and
+lzy/channel-manager/src/test/java/ai/lzy/channelmanager/SlotsIntegrationTest.java (testStorageToConsumer
+:119-163, testProducerToStorage :165-210, testMultiConsumer :212-297).  The channel manager is the
+real in-memory one (the reference scripts a mock; a real matcher is a stronger test)."""
+import os
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from lzy_b200 import _host as H
+from lzy_b200 import _native as N
+from lzy_b200._host import (DIR_INPUT, DIR_OUTPUT, ROLE_CONSUMER, ROLE_PRODUCER, ChannelManager, GrpcStatusError, Peer,
+                            Slots)
+from tests.support import hostmem
+
+
+@pytest.fixture
+def env():
+    lib = hostmem.install()
+    cm = ChannelManager(seed=3)
+    H.pump_start(cm)
+    slots = Slots(cm, 0, "lzyb://worker-0")
+    yield cm, slots, lib
+    slots.close()
+    H.pump_stop(cm)
+    cm.close()
+    hostmem.uninstall()
+    assert lib.hostmem_live_slots() == 0, "a slot frame leaked"
+
+
+def produce(ctx, name, data: bytes):
+    h = ctx.output_open(name, len(data))
+    hostmem.write(h, data)
+    ctx.output_done(name)
+    return h
+
+
+def test_simple_producer_then_consumer(env):
+    """testSimple: 'Hello' travels output slot → input slot; the input re-publishes as '<id>-out'."""
+    cm, slots, _ = env
+    chan = cm.get_or_create("u", "wf", "exec", consumer_uri="mem://simple")
+    out = slots.context("exec", "task-a")
+    out.add_slot("2", chan, DIR_OUTPUT)
+    out.before_execution()
+    produce(out, "2", b"Hello")
+    out.after_execution(5000)
+    assert H.blob_get("mem://simple") == b"Hello"  # bound with a storage consumer → uploaded
+
+    inp = slots.context("exec", "task-b")
+    inp.add_slot("1", chan, DIR_INPUT)
+    inp.before_execution(5000)
+    assert hostmem.peek(inp.input_handle("1"), 5) == b"Hello"
+    inp.after_execution(5000)  # waits for the "1-out" companion to be bound
+    st = cm.channels_status("exec", [chan])[0]
+    producers = sorted(p["peer_id"] for p in st["producers"] if p["kind"] == "slot")
+    assert producers == ["1-out", "2"] and st["consumers"] == []
+    # legacy Read on the companion and on the original producer, NOT_FOUND / UNIMPLEMENTED mapping
+    assert slots.read("1-out", 0) == b"Hello" and slots.read("1-out", 5) is None
+    assert slots.read("2", 1, 3) == b"ell"
+    with pytest.raises(GrpcStatusError) as e:
+        slots.read("nope", 0)
+    assert e.value.status == "NOT_FOUND"
+    inp.close()
+    out.close()
+    H.blob_delete("mem://simple")
+
+
+def test_connect_early_consumer_gets_start_transfer(env):
+    """testConnect / ApiTest.testEarlyConsumer: consumer binds first, waits for its peer, the producer's
+    bind pushes StartTransfer."""
+    cm, slots, _ = env
+    chan = cm.get_or_create("u", "wf", "exec", consumer_uri="mem://early")
+    inp = slots.context("exec", "task-b")
+    inp.add_slot("in", chan, DIR_INPUT)
+    inp.prefetch()
+    deadline = time.time() + 5
+    while inp.input_state("in") != H.IS_WAITING_FOR_PEER and time.time() < deadline:
+        time.sleep(0.005)
+    assert inp.input_state("in") == H.IS_WAITING_FOR_PEER
+    # Read on an input slot is UNIMPLEMENTED; StartTransfer on an output slot is INTERNAL
+    with pytest.raises(GrpcStatusError) as e:
+        slots.read("in", 0)
+    assert e.value.status == "UNIMPLEMENTED"
+    out = slots.context("exec", "task-a")
+    out.add_slot("out", chan, DIR_OUTPUT)
+    out.before_execution()
+    produce(out, "out", b"World")
+    out.after_execution(5000)
+    inp.before_execution(5000)
+    assert hostmem.peek(inp.input_handle("in"), 5) == b"World"
+    with pytest.raises(GrpcStatusError) as e:
+        slots.start_transfer("out", Peer("x", H.PEER_SLOT, "u"), "t")
+    assert e.value.status == "INTERNAL"
+    with pytest.raises(GrpcStatusError) as e:
+        slots.start_transfer("in", Peer("x", H.PEER_SLOT, "u"), "t")  # unregistered once it had a peer
+    assert e.value.status == "NOT_FOUND"
+    inp.close()
+    out.close()
+    H.blob_delete("mem://early")
+
+
+def test_read_from_storage_and_write_to_storage(env):
+    """testReadFromStorage / SlotsIntegrationTest.testStorageToConsumer + testProducerToStorage."""
+    cm, slots, _ = env
+    H.blob_put("mem://pre-existing", b"test")
+    chan = cm.get_or_create("u", "wf", "exec", producer_uri="mem://pre-existing")
+    inp = slots.context("exec", "t")
+    inp.add_slot("in", chan, DIR_INPUT)
+    inp.before_execution(5000)
+    assert hostmem.peek(inp.input_handle("in"), 4) == b"test"
+    inp.close()
+
+    chan2 = cm.get_or_create("u", "wf", "exec", consumer_uri="mem://result")
+    out = slots.context("exec", "t2")
+    out.add_slot("out", chan2, DIR_OUTPUT)
+    out.before_execution()
+    produce(out, "out", b"result-bytes")
+    out.after_execution(5000)
+    assert H.blob_get("mem://result") == b"result-bytes"
+    st = cm.channels_status("exec", [chan2])[0]
+    assert len(st["producers"]) == 2 and st["consumers"] == []  # storage promoted to BACKUP producer
+    out.close()
+    H.blob_delete("mem://pre-existing")
+    H.blob_delete("mem://result")
+
+
+def test_execution_context_in_out_and_republish(env):
+    """testExecutionContext: storage → in ('Hello'), out ('World') → storage, the delivered input is
+    re-published and itself uploaded where its channel has a storage consumer."""
+    cm, slots, _ = env
+    H.blob_put("mem://key1", b"Hello")
+    chan_in = cm.get_or_create("u", "wf", "exec", producer_uri="mem://key1")
+    chan_out = cm.get_or_create("u", "wf", "exec", consumer_uri="mem://key2")
+    ctx = slots.context("exec", "tid")
+    ctx.add_slot("a/b/in", chan_in, DIR_INPUT)
+    ctx.add_slot("a/b/out", chan_out, DIR_OUTPUT)
+    ctx.before_execution(5000)
+    assert hostmem.peek(ctx.input_handle("a/b/in"), 5) == b"Hello"
+    produce(ctx, "a/b/out", b"World")
+    ctx.after_execution(5000)
+    assert H.blob_get("mem://key2") == b"World"
+    st = cm.channels_status("exec", [chan_in])[0]
+    assert "a/b/in-out" in [p["peer_id"] for p in st["producers"]]
+    ctx.close()
+    for k in ("mem://key1", "mem://key2"):
+        H.blob_delete(k)
+
+
+def test_large_data_200mib_equal(env):
+    """testLargeData: 200 × 1 MiB random bytes, delivered == sent."""
+    cm, slots, _ = env
+    data = np.random.default_rng(1).integers(0, 256, 200 << 20, dtype=np.uint8).tobytes()
+    chan = cm.get_or_create("u", "wf", "exec", consumer_uri="mem://large")
+    slots.set_chunk_bytes(2 << 20)  # the reference's chunk size
+    out = slots.context("exec", "a")
+    out.add_slot("2", chan, DIR_OUTPUT)
+    out.before_execution()
+    produce(out, "2", data)
+    out.after_execution(20000)
+    inp = slots.context("exec", "b")
+    inp.add_slot("1", chan, DIR_INPUT)
+    inp.before_execution(20000)
+    assert hostmem.peek(inp.input_handle("1"), len(data)) == data
+    inp.close()
+    out.close()
+    H.blob_delete("mem://large")
+
+
+def test_restore_read_from_offset(env):
+    """testRestoreReadFromOffset: 2 MiB, the producer fails after 1 MiB; the consumer reports
+    TransferFailed, gets a peer again and resumes at the delivered offset."""
+    cm, slots, lib = env
+    data = os.urandom(2 << 20)
+    chan = cm.get_or_create("u", "wf", "exec", consumer_uri="mem://restore")
+    slots.set_chunk_bytes(256 << 10)
+    out = slots.context("exec", "a")
+    out.add_slot("2", chan, DIR_OUTPUT)
+    out.before_execution()
+    h_out = produce(out, "2", data)
+    out.after_execution(5000)
+    H.blob_delete("mem://restore")  # leave the slot producer as the only usable source of truth for bytes
+    H.blob_put("mem://restore", data)
+    lib.hostmem_set_fail_after(h_out, 1 << 20)
+
+    inp = slots.context("exec", "b")
+    inp.add_slot("1", chan, DIR_INPUT)
+    inp.prefetch()
+    # the slot producer (priority 7) is tried first and fails after 1 MiB; failures walk its priority
+    # down until the storage backup (5) wins and the download completes from there
+    inp.before_execution(10000)
+    assert hostmem.peek(inp.input_handle("1"), len(data)) == data
+    assert cm.peer_priority(chan, "2") < H.PRIO_PRIMARY
+    inp.close()
+    out.close()
+    H.blob_delete("mem://restore")
+
+
+def test_input_restart_on_corrupt_peer(env):
+    """testInputRestart shape + digest verification: a peer that serves wrong bytes is a ReadException;
+    the consumer fails over to another holder of the same data."""
+    cm, slots, lib = env
+    data = os.urandom(300_000)
+    chan = cm.get_or_create("u", "wf", "exec", consumer_uri="mem://backup")
+    out = slots.context("exec", "a")
+    out.add_slot("p", chan, DIR_OUTPUT)
+    out.before_execution()
+    h = produce(out, "p", data)
+    out.after_execution(5000)  # uploaded to the storage backup as well
+    lib.hostmem_corrupt(h, 1234)  # the slot peer now serves one wrong byte
+    inp = slots.context("exec", "b")
+    inp.add_slot("c", chan, DIR_INPUT)
+    inp.before_execution(10000)
+    assert hostmem.peek(inp.input_handle("c"), len(data)) == data
+    inp.close()
+    out.close()
+    H.blob_delete("mem://backup")
+
+
+def test_multi_consumer_fanout(env):
+    """SlotsIntegrationTest.testMultiConsumer: one producer, three consumers, all equal 'test'."""
+    cm, slots, _ = env
+    chan = cm.get_or_create("u", "wf", "exec", consumer_uri="mem://multi")
+    ctxs = []
+    for i in range(3):
+        c = slots.context("exec", f"consumer-{i}")
+        c.add_slot(f"in{i}", chan, DIR_INPUT)
+        c.prefetch()
+        ctxs.append(c)
+    out = slots.context("exec", "producer")
+    out.add_slot("out", chan, DIR_OUTPUT)
+    out.before_execution()
+    produce(out, "out", b"test")
+    out.after_execution(5000)
+    for i, c in enumerate(ctxs):
+        c.before_execution(5000)
+        assert hostmem.peek(c.input_handle(f"in{i}"), 4) == b"test"
+    for c in ctxs:
+        c.close()
+    out.close()
+    H.blob_delete("mem://multi")
+
+
+def test_fail_open_is_a_local_fault_and_closes_the_context(env):
+    """InMemBackend.failOpen: an IOException while opening the sink fails the slot (not the peer)."""
+    cm, slots, lib = env
+    H.blob_put("mem://x", b"payload")
+    chan = cm.get_or_create("u", "wf", "exec", producer_uri="mem://x")
+    lib.hostmem_set_fail_open(1)
+    ctx = slots.context("exec", "t")
+    ctx.add_slot("in", chan, DIR_INPUT)
+    with pytest.raises(N.LzybError) as e:
+        ctx.before_execution(5000)
+    assert e.value.code == N.E_LOCAL and "Cannot open channel" in str(e.value)
+    # like the reference, the failed consumer cannot unbind while its transfer is still ACTIVE
+    # (Unbind → UNAVAILABLE, error ignored in InputSlot.clear, InputSlot.java:207-220)
+    st = cm.channels_status("exec", [chan])[0]
+    assert [c["peer_id"] for c in st["consumers"]] == ["in"]
+    ctx.close()
+    H.blob_delete("mem://x")
+
+
+def test_fail_wait_completed_fails_after_execution(env):
+    """InMemBackend.failWaitCompleted → afterExecution throws."""
+    cm, slots, lib = env
+    chan = cm.get_or_create("u", "wf", "exec", consumer_uri="mem://y")
+    ctx = slots.context("exec", "t")
+    ctx.add_slot("out", chan, DIR_OUTPUT)
+    ctx.before_execution()
+    lib.hostmem_set_fail_commit(1)
+    produce(ctx, "out", b"zzz")
+    with pytest.raises(N.LzybError) as e:
+        ctx.after_execution(5000)
+    assert "Cannot wait" in str(e.value)
+    ctx.close()
+
+
+def test_close_while_waiting_for_peer(env):
+    """InputSlot.close from another thread while WAITING_FOR_PEER (InputSlot.java:110-117)."""
+    cm, slots, _ = env
+    chan = cm.get_or_create("u", "wf", "exec", consumer_uri="mem://never")
+    ctx = slots.context("exec", "t")
+    ctx.add_slot("in", chan, DIR_INPUT)
+    ctx.prefetch()
+    threading.Timer(0.1, ctx.close).start()
+    with pytest.raises(N.LzybError):
+        ctx.before_execution(5000)
+    time.sleep(0.2)
+    slot_consumers = [c for c in cm.channels_status("exec", [chan])[0]["consumers"] if c["kind"] == "slot"]
+    assert slot_consumers == []  # clear() unbound it; only the channel's storage consumer is left
