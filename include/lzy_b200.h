@@ -177,8 +177,10 @@ int lzyb_slot_commit(lzyb_handle_t h, uint64_t digest_out[2], void* stream);
 int64_t lzyb_slot_read(lzyb_handle_t h, uint64_t offset, void* dst_host, uint64_t len);
 int lzyb_slot_info(lzyb_handle_t h, lzyb_slot_info_t* out);
 int lzyb_slot_header(lzyb_handle_t h, lzyb_frame_header_t* out);   /* D2H copy of the frame header */
-/* = backend.close(): idempotent, returns HBM to the pool, cancels in-flight work. */
+/* = backend.close(): idempotent, returns HBM to the pool, cancels in-flight work.  Frames are
+ * reference counted: every lzyb_slot_retain() needs one more close before the HBM is released. */
 int lzyb_slot_close(lzyb_handle_t h);
+int lzyb_slot_retain(lzyb_handle_t h);
 /* look a slot up by id (SlotsService.slots map, lzy/slots/.../SlotsService.java:21-30) */
 int lzyb_slot_find(const char* slot_id, lzyb_handle_t* out);
 

@@ -141,6 +141,7 @@ typedef struct lzyb_backend_ops {
     int (*input_finish_expect)(lzyb_handle_t dst, const uint64_t digest[2], void* stream);
     int (*input_to_output)(lzyb_handle_t h);
     int (*input_reset)(lzyb_handle_t h);
+    int (*slot_retain)(lzyb_handle_t h);
 } lzyb_backend_ops_t;
 int lzyb_slots_set_backend(const lzyb_backend_ops_t* ops); /* NULL = the HBM backend */
 
@@ -193,6 +194,16 @@ int lzyb_blob_put(const char* uri, const void* data, uint64_t len);
 int64_t lzyb_blob_size(const char* uri);                       /* LZYB_E_NOT_FOUND if absent */
 int64_t lzyb_blob_get(const char* uri, void* dst, uint64_t cap);
 int lzyb_blob_delete(const char* uri);
+/* HBM frame store: storage URIs with the scheme "hbm://" name frames that stay resident in HBM.
+ * A producer bound to a channel whose storage consumer is hbm://… "uploads" by handing a reference
+ * of its frame to the store (no copy); a consumer whose peer is such a storage producer pulls from
+ * that frame with the same NVLink/HBM kernel as from a slot peer.  put retains, drop releases. */
+int lzyb_frame_store_put(const char* uri, lzyb_handle_t slot);
+int lzyb_frame_store_get(const char* uri, lzyb_handle_t* slot_out);   /* LZYB_E_NOT_FOUND if absent */
+int lzyb_frame_store_drop(const char* uri);
+/* republish delivered inputs as "<slot>-out" producers (InputSlot.java:160-168); default on.  The
+ * Python runtime turns it off so that an op owns its input frame and may mutate it in place. */
+int lzyb_slots_set_republish(lzyb_handle_t slots, int on);
 
 /* ---- graph dispatch -------------------------------------------------------------------------- */
 /* Replaces BfsGraphProcessor + Algorithms (lzy/graph-executor/.../exec/BfsGraphProcessor.java:44-258,

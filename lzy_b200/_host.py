@@ -79,6 +79,10 @@ _SIGS = {
     "lzyb_blob_size": (C.c_int64, [_s]),
     "lzyb_blob_get": (C.c_int64, [_s, C.c_void_p, C.c_uint64]),
     "lzyb_blob_delete": (_i, [_s]),
+    "lzyb_frame_store_put": (_i, [_s, _H]),
+    "lzyb_frame_store_get": (_i, [_s, C.POINTER(_H)]),
+    "lzyb_frame_store_drop": (_i, [_s]),
+    "lzyb_slots_set_republish": (_i, [_H, _i]),
     "lzyb_graph_create": (_i, [_i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i, _i, C.POINTER(_H)]),
     "lzyb_graph_free": (_i, [_H]),
     "lzyb_graph_next": (_i, [_H, C.POINTER(C.c_int32), _i]),
@@ -309,6 +313,23 @@ def blob_delete(uri: str) -> None:
     _check(lib.lzyb_blob_delete(_b(uri)))
 
 
+def frame_store_put(uri: str, slot_handle: int) -> None:
+    _check(lib.lzyb_frame_store_put(_b(uri), slot_handle))
+
+
+def frame_store_get(uri: str) -> Optional[int]:
+    h = _H()
+    rc = lib.lzyb_frame_store_get(_b(uri), C.byref(h))
+    if rc == N.E_NOT_FOUND:
+        return None
+    _check(rc)
+    return h.value
+
+
+def frame_store_drop(uri: str) -> None:
+    _check(lib.lzyb_frame_store_drop(_b(uri)))
+
+
 class ExecutionContext:
     """SlotsExecutionContext (lzy/slots/src/main/java/ai/lzy/slots/SlotsExecutionContext.java:45-107)."""
 
@@ -362,6 +383,9 @@ class Slots:
 
     def set_chunk_bytes(self, n: int) -> None:
         _check(lib.lzyb_slots_set_chunk_bytes(self.h, n))
+
+    def set_republish(self, on: bool) -> None:
+        _check(lib.lzyb_slots_set_republish(self.h, int(on)))
 
     def context(self, execution_id: str, task_id: str) -> ExecutionContext:
         return ExecutionContext(self, execution_id, task_id)

@@ -142,6 +142,7 @@ _SIGNATURES = {
     "lzyb_slot_info": (C.c_int, [_H, C.POINTER(SlotInfo)]),
     "lzyb_slot_header": (C.c_int, [_H, C.POINTER(FrameHeader)]),
     "lzyb_slot_close": (C.c_int, [_H]),
+    "lzyb_slot_retain": (C.c_int, [_H]),
     "lzyb_slot_find": (C.c_int, [C.c_char_p, C.POINTER(_H)]),
     "lzyb_input_open": (C.c_int, [C.c_char_p, C.c_int, C.c_uint64, C.POINTER(_H)]),
     "lzyb_transfer_chunk": (C.c_int64, [_H, _H, C.c_uint64, C.c_uint64, _P]),
@@ -218,11 +219,12 @@ def digest_hex(d: Sequence[int]) -> str:
 class SlotHandle:
     """Thin object wrapper over one lzyb handle (an HBM frame)."""
 
-    __slots__ = ("h", "slot_id", "gpu", "nbytes", "_closed")
+    __slots__ = ("h", "slot_id", "gpu", "nbytes", "_closed", "_keepalive", "__weakref__")
 
     def __init__(self, h: int, slot_id: str, gpu: int, nbytes: int):
         self.h, self.slot_id, self.gpu, self.nbytes = h, slot_id, gpu, nbytes
         self._closed = False
+        self._keepalive = None
 
     # -- construction -----------------------------------------------------------------------
     @classmethod
@@ -317,10 +319,32 @@ class SlotHandle:
     def fault(self, kind: int, arg: int = 0) -> None:
         check(lib.lzyb_fault_inject(self.h, kind, arg))
 
+    def retain(self) -> None:
+        check(lib.lzyb_slot_retain(self.h))
+
     def close(self) -> None:
         if not self._closed:
             self._closed = True
             check(lib.lzyb_slot_close(self.h))
+
+    @classmethod
+    def adopt(cls, h: int, owned: bool = True) -> "SlotHandle":
+        """wrap a handle produced by the slots runtime (retained when `owned`, so closing is safe)"""
+        i = SlotInfo()
+        check(lib.lzyb_slot_info(h, C.byref(i)))
+        if owned:
+            check(lib.lzyb_slot_retain(h))
+        s = cls(h, f"adopted:{h}", int(i.gpu), int(i.nbytes))
+        s._closed = not owned
+        return s
+
+    def __del__(self):
+        try:
+            if not self._closed:
+                self._closed = True
+                lib.lzyb_slot_close(self.h)
+        except Exception:
+            pass
 
     def __repr__(self):
         return f"SlotHandle({self.slot_id!r}, gpu={self.gpu}, nbytes={self.nbytes}, h={self.h})"

@@ -1,0 +1,354 @@
+"""B200Runtime — the ``Runtime`` that replaces ``LocalRuntime`` / the remote worker stack for the
+slot/channel data plane on one 8×B200 box.
+
+What it stands in for (reference call stacks SURVEY §3.1/§3.2):
+
+* ``LocalRuntime.exec`` / ``__exec_call`` (pylzy/lzy/api/v1/local/runtime.py:42-179): no temp dirs, no
+  storage↔file copies, no ``python startup.py`` subprocess per op — ops run in-process on a worker
+  pinned to a GPU, arguments are zero-copy views of delivered HBM frames;
+* ``startup.process_execution`` (pylzy/lzy/api/v1/startup.py:109-170): same argument / result /
+  exception semantics (type check of results, ``lazy_arguments``, exception tuple, ``-> None``);
+* lzy-service ``CreateChannels`` / ``BuildTasks`` (lzy/lzy-service/.../operations/graph/
+  CreateChannels.java:75-104, BuildTasks.java:72-126): one channel per data URI, created with a storage
+  consumer for op outputs and a storage producer for pre-existing data; slot names
+  ``/{call.id}/{entry.id}`` (pylzy/lzy/api/v1/remote/runtime.py:326-349);
+* graph-executor dispatch (lzy/graph-executor/.../BfsGraphProcessor.java): the C++ GraphDispatcher;
+* worker staging order (lzy/worker/.../WorkerApiImpl.java:191-225): beforeExecution → op → afterExecution
+  through the C++ slots runtime, one ``Slots`` instance per GPU.
+
+Downstream prefetch: every task's input slots bind as *early consumers* when the graph starts, so each
+transfer begins the moment its producer binds — on the consumer GPU's copy stream, while other ops are
+still computing — instead of when the whole upstream task has been reported successful.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import threading
+import uuid
+from concurrent.futures import FIRST_COMPLETED, ThreadPoolExecutor, wait
+from dataclasses import dataclass, field
+from typing import TYPE_CHECKING, Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import cloudpickle
+
+from .... import _host as H
+from .... import _native as N
+from ....devmem import current_stream_ptr
+from ....proxy import proxy
+from ....serialization.types import get_type
+from ....utils import op_scope, tbpickle
+from ..exceptions import LzyExecutionException
+from ..runtime import ProgressStep, Runtime
+from ..snapshot import FrameSnapshot, Snapshot
+from ..utils.types import check_types_serialization_compatible, infer_real_types, is_subtype
+from .store import FrameStore
+
+if TYPE_CHECKING:
+    from ....core.call import LzyCall
+    from ....core.workflow import LzyWorkflow
+
+_LAZY_ARG_ATTR = "__lzy_lazy_argument__"
+
+
+@dataclass
+class B200RuntimeConfig:
+    gpus: Optional[Sequence[int]] = None        # CUDA ordinals to use; None = all visible
+    host_ring_bytes: int = 64 << 20
+    placement: str = "round_robin"               # "round_robin" | "locality" | "single"
+    prefetch: bool = True
+    max_parallel_ops: int = 0                    # 0 = 2 × GPUs
+    republish_inputs: bool = False               # "<slot>-out" seeding (InputSlot.java:160-168); ops own their inputs when off
+    chunk_bytes: int = 0                         # 0 = one launch per transfer; the reference streams 2 MiB chunks
+    copy_engine: str = "auto"                    # "auto" | "ldg" | "tma"
+    user_id: str = field(default_factory=lambda: os.environ.get("LZY_USER", "local-user"))
+
+
+class _OpFailed(Exception):
+    def __init__(self, task: int, exc_info):
+        super().__init__(f"op #{task} failed")
+        self.task, self.exc_info = task, exc_info
+
+
+class B200Runtime(Runtime):
+    def __init__(self, config: Optional[B200RuntimeConfig] = None, **kwargs):
+        self.config = config or B200RuntimeConfig(**kwargs)
+        self._workflow: Optional["LzyWorkflow"] = None
+        self._execution_id: Optional[str] = None
+        self._lock = threading.RLock()
+        self._ready = False
+        self.gpus: List[int] = []
+        self.store: Optional[FrameStore] = None
+        self.cm: Optional[H.ChannelManager] = None
+        self.workers: Dict[int, H.Slots] = {}
+        self._streams: Dict[int, Any] = {}
+        self._pool: Optional[ThreadPoolExecutor] = None
+        self._rr = 0
+        self.stats = {"ops": 0, "graphs": 0, "cached_ops": 0}
+        tbpickle.install()
+
+    # ---- bring-up ------------------------------------------------------------------------------------
+    def _ensure_ready(self) -> None:
+        with self._lock:
+            if self._ready:
+                return
+            import torch
+            if not torch.cuda.is_available():
+                raise N.NoGpuError(N.E_NOGPU, "B200Runtime needs a CUDA device: the data plane has no CPU path")
+            if self.config.gpus is None:
+                n = N.init(0, 0, self.config.host_ring_bytes)
+                self.gpus = list(range(n))
+            else:
+                first, last = min(self.config.gpus), max(self.config.gpus)
+                N.init(first, last - first + 1, self.config.host_ring_bytes)
+                self.gpus = list(self.config.gpus)
+            N.set_copy_engine({"auto": N.ENGINE_AUTO, "ldg": N.ENGINE_LDG, "tma": N.ENGINE_TMA}[self.config.copy_engine])
+            self.store = FrameStore(default_gpu=self.gpus[0])
+            self.cm = H.ChannelManager()
+            H.pump_start(self.cm)
+            for g in self.gpus:
+                w = H.Slots(self.cm, g, f"lzyb://localhost/worker?gpu={g}")
+                w.set_republish(self.config.republish_inputs)
+                if self.config.chunk_bytes:
+                    w.set_chunk_bytes(self.config.chunk_bytes)
+                self.workers[g] = w
+                self._streams[g] = torch.cuda.Stream(device=g)
+            workers = self.config.max_parallel_ops or 2 * len(self.gpus)
+            self._pool = ThreadPoolExecutor(max_workers=max(2, workers), thread_name_prefix="lzyb-op")
+            self._ready = True
+
+    # ---- Runtime ABC ----------------------------------------------------------------------------------
+    async def storage(self) -> Optional[Any]:
+        return None  # data never leaves the box: there is no external storage to register
+
+    def snapshot(self, workflow: "LzyWorkflow", storage_uri_prefix: str) -> Optional[Snapshot]:
+        self._ensure_ready()
+        return FrameSnapshot(workflow.owner.serializer_registry, storage_uri_prefix, self.store, workflow.owner.storage_name)
+
+    async def start(self, workflow: "LzyWorkflow") -> str:
+        self._ensure_ready()
+        self._workflow = workflow
+        self._execution_id = str(uuid.uuid4())
+        return self._execution_id
+
+    async def abort(self) -> None:
+        if self.cm is not None and self._execution_id:
+            self.cm.destroy_all(self._execution_id, "aborted")
+
+    async def finish(self) -> None:
+        if self.cm is not None and self._execution_id:
+            self.cm.destroy_all(self._execution_id, "finished")  # LzyChannelManagerPrivate.DestroyAll
+
+    async def exec(self, calls: List["LzyCall"], progress: Callable[[ProgressStep], None]) -> None:
+        import asyncio
+        assert self._workflow is not None
+        progress(ProgressStep.EXECUTING)
+        loop = asyncio.get_running_loop()
+        try:
+            await loop.run_in_executor(None, self._exec_graph, list(calls))
+        except BaseException:
+            progress(ProgressStep.FAILED)
+            raise
+        progress(ProgressStep.COMPLETED)
+
+    def clear(self) -> None:
+        """drop every stored frame (results of finished workflows stay readable until then)"""
+        if self.store is not None:
+            self.store.clear()
+
+    def close(self) -> None:
+        with self._lock:
+            if not self._ready:
+                return
+            self.clear()
+            for w in self.workers.values():
+                w.close()
+            H.pump_stop(self.cm)
+            self.cm.close()
+            if self._pool:
+                self._pool.shutdown(wait=False)
+            self.workers.clear()
+            self._ready = False
+
+    # ---- graph execution ----------------------------------------------------------------------------------
+    def _place(self, calls: List["LzyCall"], producers: Dict[str, int], snapshot: Snapshot) -> List[int]:
+        placement: List[int] = []
+        for i, call in enumerate(calls):
+            prov = call.get_provisioning()
+            if prov.gpu_index is not None and prov.gpu_index in self.gpus:
+                placement.append(prov.gpu_index)
+                continue
+            if self.config.placement == "single" or len(self.gpus) == 1:
+                placement.append(self.gpus[0])
+            elif self.config.placement == "locality":
+                best, best_bytes = None, -1
+                for eid in list(call.arg_entry_ids) + list(call.kwarg_entry_ids.values()):
+                    if eid in producers and producers[eid] < i:
+                        g, nb = placement[producers[eid]], 1
+                    else:
+                        uri = snapshot.get(eid).storage_uri
+                        g, nb = self.store.gpu_of(uri), self.store.nbytes_of(uri)
+                    if g is not None and nb > best_bytes:
+                        best, best_bytes = g, nb
+                placement.append(best if best is not None else self.gpus[self._rr % len(self.gpus)])
+            else:
+                placement.append(self.gpus[self._rr % len(self.gpus)])
+            self._rr += 1
+        return placement
+
+    def _exec_graph(self, calls: List["LzyCall"]) -> None:
+        wf = self._workflow
+        assert wf is not None and self.store is not None and self.cm is not None
+        snapshot = wf.snapshot
+        exec_id, user = self._execution_id or "exec", self.config.user_id
+        self.stats["graphs"] += 1
+
+        # ops whose outputs are all already supplied are dropped (lzy-service DataFlowGraph.java:51-72)
+        todo: List["LzyCall"] = []
+        for c in calls:
+            if c.cache and c.entry_ids and all(self.store.exists(snapshot.get(e).storage_uri) for e in c.entry_ids):
+                self.stats["cached_ops"] += 1
+                continue
+            todo.append(c)
+        if not todo:
+            return
+        calls = todo
+        producers: Dict[str, int] = {}
+        for i, c in enumerate(calls):
+            for eid in c.entry_ids:
+                producers[eid] = i
+        inputs_of: List[List[str]] = []
+        edges: List[Tuple[int, int]] = []
+        for i, c in enumerate(calls):
+            ins = list(dict.fromkeys(list(c.arg_entry_ids) + list(c.kwarg_entry_ids.values())))
+            inputs_of.append(ins)
+            for eid in ins:
+                if eid in producers and producers[eid] != i:
+                    edges.append((producers[eid], i))
+
+        # CreateChannels: one channel per data URI
+        channel_of: Dict[str, str] = {}
+        for i, c in enumerate(calls):
+            for eid in c.entry_ids:
+                channel_of[eid] = self.cm.get_or_create(user, wf.name, exec_id, consumer_uri=snapshot.get(eid).storage_uri)
+        for i, ins in enumerate(inputs_of):
+            for eid in ins:
+                if eid in channel_of:
+                    continue
+                uri = snapshot.get(eid).storage_uri
+                if not self.store.exists(uri):
+                    raise ValueError(f"Cannot find blob in storage by uri={uri}")
+                channel_of[eid] = self.cm.get_or_create(user, wf.name, exec_id, producer_uri=uri)
+
+        placement = self._place(calls, producers, snapshot)
+        graph = H.GraphDispatcher(len(calls), edges, allow_cycles=False)
+        ctxs: List[H.ExecutionContext] = []
+        try:
+            # BuildTasks: slot → channel assignments; every input binds right away (prefetch)
+            for i, c in enumerate(calls):
+                ctx = self.workers[placement[i]].context(exec_id, c.id)
+                for eid in inputs_of[i]:
+                    ctx.add_slot(f"/{c.id}/{eid}", channel_of[eid], H.DIR_INPUT)
+                for eid in c.entry_ids:
+                    ctx.add_slot(f"/{c.id}/{eid}", channel_of[eid], H.DIR_OUTPUT)
+                ctxs.append(ctx)
+            if self.config.prefetch:
+                for ctx in ctxs:
+                    ctx.prefetch()
+
+            running: Dict[Any, int] = {}
+            failure: Optional[_OpFailed] = None
+            while True:
+                for t in graph.next():
+                    running[self._pool.submit(self._run_task, t, calls[t], ctxs[t], placement[t], inputs_of[t])] = t
+                if not running:
+                    break
+                done, _ = wait(list(running), return_when=FIRST_COMPLETED)
+                for fut in done:
+                    t = running.pop(fut)
+                    err = fut.exception()
+                    if err is None:
+                        graph.task_done(t, True)
+                    else:
+                        graph.task_done(t, False, repr(err))
+                        if failure is None:
+                            failure = err if isinstance(err, _OpFailed) else _OpFailed(t, (type(err), err, err.__traceback__))
+                if failure is not None:
+                    graph.stop("op failed")  # first failure stops the graph (BfsGraphProcessor.java:64-68)
+                    for fut in list(running):
+                        fut.cancel()
+                    wait(list(running))
+                    break
+            if failure is not None:
+                _typ, value, tb = failure.exc_info
+                raise value.with_traceback(tb)
+            if graph.status != H.G_COMPLETED:
+                raise LzyExecutionException("graph did not complete")
+        finally:
+            for ctx in ctxs:
+                ctx.close()
+            graph.close()
+
+    # ---- one op (WorkerApiImpl.executeOp + startup.process_execution) -------------------------------------
+    def _run_task(self, t: int, call: "LzyCall", ctx: H.ExecutionContext, gpu: int, input_eids: List[str]) -> None:
+        import torch
+        wf = self._workflow
+        assert wf is not None and self.store is not None
+        snapshot, registry = wf.snapshot, wf.owner.serializer_registry
+        exc_uri = snapshot.get(call.exception_id).storage_uri
+        try:
+            ctx.before_execution(-1)  # every input fully delivered and verified
+            values: Dict[str, Any] = {}
+
+            def load(eid: str) -> Any:
+                if eid not in values:
+                    slot = N.SlotHandle.adopt(ctx.input_handle(f"/{call.id}/{eid}"), owned=True)
+                    values[eid] = self.store.unpack_slot(slot, snapshot.get(eid).typ, registry, private=True)
+                return values[eid]
+
+            def arg(eid: str) -> Any:
+                if call.lazy_arguments:
+                    return proxy(lambda e=eid: load(e), infer_real_types(snapshot.get(eid).typ), cls_attrs={_LAZY_ARG_ATTR: True})
+                return load(eid)
+
+            args = [arg(e) for e in call.arg_entry_ids]
+            kwargs = {k: arg(e) for k, e in call.kwarg_entry_ids.items()}
+            func = call.signature.func.callable
+            stream = self._streams[gpu]
+            op_scope.enter()
+            try:
+                with torch.cuda.device(gpu), torch.cuda.stream(stream):
+                    res = func(*args, **kwargs)
+            finally:
+                op_scope.leave()
+
+            outs = call.entry_ids
+            results = [res] if len(outs) == 1 else list(res)
+            with torch.cuda.device(gpu), torch.cuda.stream(stream):
+                sp = current_stream_ptr(gpu)
+                for eid, data in zip(outs, results):
+                    entry = snapshot.get(eid)
+                    if hasattr(type(data), _LAZY_ARG_ATTR):  # the op returned one of its lazy arguments
+                        data = data.__lzy_origin__
+                    real_type = get_type(data)
+                    compatible = check_types_serialization_compatible(entry.typ, real_type, registry)
+                    if not compatible or not is_subtype(real_type, entry.typ):
+                        raise TypeError(f"Invalid types: return value has type {entry.typ} but passed type {real_type}")
+                    name = f"/{call.id}/{eid}"
+
+                    def factory(nbytes, device, _name=name):
+                        return N.SlotHandle.adopt(ctx.output_open(_name, nbytes), owned=False)
+
+                    slot = self.store.pack_object(data, entry.typ, registry, factory, sp)
+                    ctx.output_done(name)
+                    values[f"out:{eid}"] = slot  # keep the packed source alive until the commit
+            ctx.after_execution(-1)  # outputs bound; "uploaded" = referenced by the HBM frame store
+            self.store.put_inline(exc_uri, None)
+            self.stats["ops"] += 1
+        except BaseException:
+            info = sys.exc_info()
+            try:
+                self.store.put_inline(exc_uri, cloudpickle.loads(cloudpickle.dumps(info)))
+            except Exception:
+                self.store.put_inline(exc_uri, (info[0], info[1], None))
+            raise _OpFailed(t, info)

@@ -1,0 +1,171 @@
+"""FrameStore — the box-local "storage" of the B200 runtime: every snapshot payload is an HBM slot
+frame addressed by its storage URI.
+
+It plays the part S3 / the file storage plays for the reference (``AsyncStorageClient``,
+pylzy/lzy/storage/api.py:59-96, and the storage peers of the channel manager,
+lzy/lzy-service/.../operations/graph/CreateChannels.java:75-104): data that exists before a graph
+runs is a *storage producer* of its channel, and every op output "lands in storage" — except that
+landing means the C++ frame store takes a reference to the producer's frame (``hbm://`` URIs,
+include/lzy_b200_host.h: lzyb_frame_store_*); nothing is copied and nothing leaves HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+import uuid
+from io import BytesIO
+from typing import Any, Dict, Optional, Type
+
+from .... import _host as H
+from .... import _native as N
+from ....devmem import current_stream_ptr
+from ....serialization.api import DeviceFrameSerializer, SerializerRegistry
+from ....serialization.builtin import FLAG_HOST_ORIGIN, FLAG_NDARRAY
+
+_FLAG_SHIFT = 16  # header.dtype: low 16 bits = enum lzyb_dtype, high 16 bits = serializer flags
+
+
+class _InfoView:
+    """slot info with the dtype code and the serializer flags separated"""
+
+    def __init__(self, info):
+        self.dtype = int(info.dtype) & 0xFFFF
+        self.flags = int(info.dtype) >> _FLAG_SHIFT
+        self.ndim = int(info.ndim)
+        self.shape = [int(info.shape[i]) for i in range(self.ndim)]
+        self.nbytes = int(info.nbytes)
+        self.gpu = int(info.gpu)
+
+
+class FrameStore:
+    def __init__(self, default_gpu: int = 0):
+        self.default_gpu = default_gpu
+        self._frames: Dict[str, N.SlotHandle] = {}
+        self._inline: Dict[str, Any] = {}  # tiny control values (exception tuples) that never need a frame
+        self._lock = threading.RLock()
+        self.bytes_put = 0
+
+    # ---- writing ------------------------------------------------------------------------------
+    def pack_object(self, data: Any, typ: Type, registry: SerializerRegistry, slot_factory, stream: int = 0):
+        """Serialize `data` into a fresh frame obtained from `slot_factory(nbytes) -> SlotHandle`.
+        Returns the slot (not yet committed)."""
+        ser = registry.find_serializer_by_instance(data)
+        if isinstance(ser, DeviceFrameSerializer) and ser.can_frame(data):
+            code, shape, nbytes, flags = ser.frame_plan(data)
+            slot = slot_factory(nbytes, getattr(data, "device", None))
+            slot.set_meta(code | (flags << _FLAG_SHIFT), shape)
+            ser.pack(data, slot, stream)
+            return slot
+        ser = registry.find_serializer_by_type(typ) or ser
+        if ser is None or isinstance(ser, DeviceFrameSerializer):
+            ser = registry.find_serializer_by_data_format("pickle")
+        buf = BytesIO()
+        ser.serialize(data, buf)
+        raw = buf.getvalue()
+        slot = slot_factory(len(raw), None)
+        slot.set_meta(N.DT_PICKLE | (FLAG_HOST_ORIGIN << _FLAG_SHIFT), (len(raw),))
+        slot.pack_host(C.cast(C.c_char_p(raw), C.c_void_p).value or 0, len(raw), stream)
+        slot._keepalive = raw
+        return slot
+
+    def put(self, prefix: str, data: Any, typ: Type, registry: SerializerRegistry, name: str = "") -> str:
+        def factory(nbytes, device):
+            gpu = device.index if device is not None and getattr(device, "type", "") == "cuda" else self.default_gpu
+            return N.SlotHandle.create_output(f"put/{name}/{uuid.uuid4()}", gpu, nbytes)
+
+        probe_gpu = getattr(getattr(data, "device", None), "index", None)
+        stream = current_stream_ptr(probe_gpu if probe_gpu is not None else self.default_gpu)
+        slot = self.pack_object(data, typ, registry, factory, stream)
+        digest = slot.commit(stream)
+        slot._keepalive = None
+        hexd = N.digest_hex(digest)
+        uri = prefix + hexd
+        with self._lock:
+            if uri in self._frames:  # equal data is stored once (snapshot.py:157-170)
+                slot.close()
+            else:
+                self._frames[uri] = slot
+                H.frame_store_put(uri, slot.h)
+                self.bytes_put += slot.nbytes
+        return hexd
+
+    def put_inline(self, uri: str, value: Any) -> None:
+        with self._lock:
+            self._inline[uri] = value
+
+    # ---- reading ------------------------------------------------------------------------------
+    def _slot(self, uri: str) -> Optional[N.SlotHandle]:
+        with self._lock:
+            s = self._frames.get(uri)
+            if s is not None:
+                return s
+            h = H.frame_store_get(uri)  # produced by an op: the slots runtime registered it
+            if h is None:
+                return None
+            s = N.SlotHandle.adopt(h, owned=True)
+            self._frames[uri] = s
+            return s
+
+    def exists(self, uri: str) -> bool:
+        with self._lock:
+            if uri in self._inline:
+                return True
+        return self._slot(uri) is not None
+
+    def unpack_slot(self, slot: N.SlotHandle, typ: Type, registry: SerializerRegistry, private: bool) -> Any:
+        info = _InfoView(slot.info())
+        if info.dtype == N.DT_PICKLE:
+            raw = C.create_string_buffer(max(1, info.nbytes))
+            if info.nbytes:
+                slot.copy_to_host(C.addressof(raw), info.nbytes)
+            ser = registry.find_serializer_by_type(typ)
+            if ser is None or isinstance(ser, DeviceFrameSerializer):
+                ser = registry.find_serializer_by_data_format("pickle")
+            return ser.deserialize(BytesIO(raw.raw[:info.nbytes]), typ if isinstance(typ, type) else None)
+        fmt = "lzyb_ndarray_frame" if info.flags & FLAG_NDARRAY else "lzyb_tensor_frame"
+        ser = registry.find_serializer_by_data_format(fmt)
+        value = ser.unpack(slot, info, private)
+        if not private and hasattr(value, "is_cuda") and value.is_cuda:
+            value = value.clone()  # a client read gets its own copy, like a fresh deserialization
+        return value
+
+    def get(self, uri: str, typ: Type, registry: SerializerRegistry) -> Any:
+        with self._lock:
+            if uri in self._inline:
+                return self._inline[uri]
+        slot = self._slot(uri)
+        if slot is None:
+            raise ValueError(f"Cannot find blob in storage by uri={uri}")
+        return self.unpack_slot(slot, typ, registry, private=False)
+
+    def alias(self, from_uri: str, to_uri: str) -> None:
+        slot = self._slot(from_uri)
+        if slot is None:
+            raise ValueError(f"no data at {from_uri}")
+        H.frame_store_put(to_uri, slot.h)
+
+    def gpu_of(self, uri: str) -> Optional[int]:
+        s = self._slot(uri)
+        return None if s is None else s.gpu
+
+    def nbytes_of(self, uri: str) -> int:
+        s = self._slot(uri)
+        return 0 if s is None else s.nbytes
+
+    # ---- lifetime -----------------------------------------------------------------------------
+    def drop(self, uri: str) -> None:
+        with self._lock:
+            self._inline.pop(uri, None)
+            s = self._frames.pop(uri, None)
+        H.frame_store_drop(uri)
+        if s is not None:
+            s.close()
+
+    def clear(self) -> None:
+        with self._lock:
+            uris = list(self._frames) + list(self._inline)
+        for u in uris:
+            self.drop(u)
+
+    def __len__(self):
+        return len(self._frames)

@@ -1,0 +1,128 @@
+"""Snapshot: the id → data table of one workflow (pylzy/lzy/api/v1/snapshot.py:19-191).
+
+``Snapshot`` and ``SnapshotEntry`` keep the reference's shape.  ``FrameSnapshot`` is the B200
+implementation of ``DefaultSnapshot``'s contract (put_data :141-172, get_data :108-139, copy_data
+:174-188) over a ``FrameStore`` that keeps every payload in an HBM slot frame:
+
+* ``put_data`` serializes *into a frame* (tensor/ndarray: the CUDA pack kernel; anything else: cloudpickle
+  bytes copied H2D), takes the frame's digest as ``data_hash`` and ``storage_uri = prefix + digest``
+  — the same content-addressing rule as ``prefix + md5`` (:154-155), so equal data is stored once;
+* ``get_data`` returns ``Result(value)`` or ``Absence`` exactly like the reference.
+"""
+from __future__ import annotations
+
+import dataclasses
+import uuid
+from abc import ABC, abstractmethod
+from typing import TYPE_CHECKING, Any, Dict, Optional, Type, cast
+
+from ...proxy_result import Absence, Either, Result
+from ...serialization.api import Schema, SerializerRegistry
+
+if TYPE_CHECKING:
+    from .b200.store import FrameStore
+
+
+@dataclasses.dataclass
+class SnapshotEntry:
+    id: str
+    name: str
+    typ: Type
+    data_scheme: Schema
+    storage_name: str
+    _storage_uri: Optional[str] = None
+    _data_hash: Optional[str] = None
+
+    @property
+    def storage_uri(self) -> str:
+        if self._storage_uri is None:
+            raise ValueError(f"Storage uri for snapshot entry with id={self.id} is not set")
+        return cast(str, self._storage_uri)
+
+    @storage_uri.setter
+    def storage_uri(self, uri: str) -> None:
+        self._storage_uri = uri
+
+    @property
+    def data_hash(self) -> str:
+        if self._data_hash is None:
+            raise ValueError(f"Data hash for snapshot entry {self.id} is not set")
+        return cast(str, self._data_hash)
+
+    @data_hash.setter
+    def data_hash(self, hsh: str) -> None:
+        self._data_hash = hsh
+
+
+class Snapshot(ABC):
+    @abstractmethod
+    def create_entry(self, name: str, typ: Type) -> SnapshotEntry:
+        ...
+
+    @abstractmethod
+    async def get_data(self, entry_id: str) -> Either:
+        ...
+
+    @abstractmethod
+    async def put_data(self, entry_id: str, data: Any) -> None:
+        ...
+
+    @abstractmethod
+    async def copy_data(self, from_entry_id: str, to_uri: str) -> None:
+        ...
+
+    @abstractmethod
+    def get(self, entry_id: str) -> SnapshotEntry:
+        ...
+
+
+class FrameSnapshot(Snapshot):
+    def __init__(self, serializer_registry: SerializerRegistry, storage_uri: str, store: "FrameStore",
+                 storage_name: str = "hbm"):
+        self._registry = serializer_registry
+        self._prefix = storage_uri
+        self._store = store
+        self._storage_name = storage_name
+        self._entries: Dict[str, SnapshotEntry] = {}
+
+    def create_entry(self, name: str, typ: Type) -> SnapshotEntry:
+        eid = str(uuid.uuid4())
+        serializer = self._registry.find_serializer_by_type(typ)
+        if serializer is None:
+            raise TypeError(f"Cannot find serializer for type {typ}")
+        if not serializer.available():
+            raise TypeError(f"Serializer for type {typ} is not available, please install {serializer.requirements()}")
+        e = SnapshotEntry(eid, name, typ, serializer.schema(typ), self._storage_name)
+        self._entries[eid] = e
+        return e
+
+    def get(self, entry_id: str) -> SnapshotEntry:
+        return self._entries[entry_id]
+
+    async def put_data(self, entry_id: str, data: Any) -> None:
+        entry = self._entries.get(entry_id)
+        if entry is None:
+            raise ValueError(f"Entry with id={entry_id} does not exist")
+        digest_hex = self._store.put(self._prefix, data, entry.typ, self._registry, name=entry.name)
+        entry.data_hash = digest_hex
+        entry.storage_uri = self._prefix + digest_hex
+
+    async def get_data(self, entry_id: str) -> Either:
+        entry = self._entries.get(entry_id)
+        if entry is None:
+            raise ValueError(f"Entry with id={entry_id} does not exist")
+        try:
+            uri = entry.storage_uri
+        except ValueError as e:
+            return Absence(e)
+        if not self._store.exists(uri):
+            return Absence(ValueError(f"Cannot find blob in storage by uri={uri}"))
+        return Result(self._store.get(uri, entry.typ, self._registry))
+
+    async def copy_data(self, from_entry_id: str, to_uri: str) -> None:
+        entry = self._entries.get(from_entry_id)
+        if entry is None:
+            raise ValueError(f"Entry with id={from_entry_id} does not exist")
+        if not self._store.exists(entry.storage_uri):
+            raise ValueError(f"Entry with id={from_entry_id} is not loaded to storage")
+        self._store.alias(entry.storage_uri, to_uri)

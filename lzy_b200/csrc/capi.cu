@@ -108,6 +108,7 @@ struct Slot {
     cudaStream_t last_stream = nullptr;
     int fault_kind = LZYB_FAULT_NONE;
     uint64_t fault_arg = 0;
+    std::atomic<int> refs{1};    // lzyb_slot_retain / lzyb_slot_close
     std::mutex mu;
     uint8_t* payload() const { return buf + HEADER_BYTES; }
 };
@@ -702,6 +703,13 @@ int lzyb_slot_header(lzyb_handle_t h, lzyb_frame_header_t* out) {
     return LZYB_OK;
 }
 
+int lzyb_slot_retain(lzyb_handle_t h) {
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    s->refs++;
+    return LZYB_OK;
+}
+
 int lzyb_slot_close(lzyb_handle_t h) {
     SlotPtr s;
     {
@@ -709,6 +717,7 @@ int lzyb_slot_close(lzyb_handle_t h) {
         auto it = g.slots.find(h);
         if (it == g.slots.end()) return LZYB_OK;  // idempotent (InputSlot.close, InputSlot.java:110-113)
         s = it->second;
+        if (--s->refs > 0) return LZYB_OK;        // another holder (the HBM frame store) keeps the frame
         g.slots.erase(it);
         auto bi = g.by_id.find(s->id);
         if (bi != g.by_id.end() && bi->second == h) g.by_id.erase(bi);

@@ -37,7 +37,7 @@ using lzyb_host::scopy;
 const lzyb_backend_ops_t kHbmBackend = {
     lzyb_slot_create, lzyb_input_open,      lzyb_slot_commit,         lzyb_slot_read,       lzyb_slot_info,
     lzyb_slot_find,   lzyb_slot_close,      lzyb_transfer_chunk,      lzyb_input_finish,    lzyb_input_write_host,
-    lzyb_input_finish_expect, lzyb_input_to_output, lzyb_input_reset,
+    lzyb_input_finish_expect, lzyb_input_to_output, lzyb_input_reset, lzyb_slot_retain,
 };
 std::atomic<const lzyb_backend_ops_t*> g_ops{&kHbmBackend};
 lzyb_backend_ops_t g_custom_ops;
@@ -56,6 +56,16 @@ std::shared_ptr<Blob> blob_find(const std::string& uri) {
     std::lock_guard<std::mutex> lk(g_blob_mu);
     auto it = g_blobs.find(uri);
     return it == g_blobs.end() ? nullptr : it->second;
+}
+
+// ---- HBM frame store ("hbm://" storage peers) -----------------------------------------------------------
+std::mutex g_frames_mu;
+std::map<std::string, lzyb_handle_t> g_frames;
+bool is_hbm_uri(const char* uri) { return uri && strncmp(uri, "hbm://", 6) == 0; }
+lzyb_handle_t frame_find(const std::string& uri) {
+    std::lock_guard<std::mutex> lk(g_frames_mu);
+    auto it = g_frames.find(uri);
+    return it == g_frames.end() ? 0 : it->second;
 }
 
 // ---- a tiny future -------------------------------------------------------------------------------------
@@ -134,6 +144,7 @@ struct SlotsInstance {
     int gpu = 0;
     std::string api_url;
     std::atomic<uint64_t> chunk_bytes{0};
+    std::atomic<bool> republish{true};
     SlotsServiceImpl service;
     std::mutex mu;
     std::vector<std::shared_ptr<ExecCtx>> contexts;
@@ -249,6 +260,7 @@ struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
 
     // StorageOutputTransfer.readFrom(backend.readFromOffset(0))
     bool upload_to_storage(const char* uri) {
+        if (is_hbm_uri(uri)) return lzyb_frame_store_put(uri, backend) == LZYB_OK;  // stays in HBM: no copy
         lzyb_slot_info_t info;
         if (ops().slot_info(backend, &info) != LZYB_OK) return false;
         auto blob = std::make_shared<Blob>();
@@ -382,6 +394,18 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
 
     std::unique_ptr<InputTransfer> make_transfer(const lzyb_peer_desc_t& p, std::string& err) {
         // TransferFactory.input(peer, offset)
+        if (p.kind == LZYB_PEER_STORAGE && is_hbm_uri(p.url)) {
+            lzyb_handle_t h = frame_find(p.url);
+            lzyb_slot_info_t info;
+            if (!h || ops().slot_info(h, &info) != LZYB_OK) {
+                err = std::string("Error while reading from storage: no frame at ") + p.url;
+                return nullptr;
+            }
+            auto t = std::make_unique<SlotPullTransfer>();
+            t->peer = h;
+            t->size = info.nbytes;
+            return t;
+        }
         if (p.kind == LZYB_PEER_STORAGE) {
             auto blob = blob_find(p.url);
             if (!blob) {
@@ -442,7 +466,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
         // re-publish the delivered bytes as producer "<slotId>-out" on the same channel
         // (InputSlot.java:160-168).  The companion joins the context before `ready` completes so that
         // an afterExecution() issued right after beforeExecution() already sees it.
-        if (ops().input_to_output(backend) == LZYB_OK) {
+        if (inst->republish.load() && ops().input_to_output(backend) == LZYB_OK) {
             auto out = std::make_shared<OutputSlotImpl>();
             out->inst = inst;
             out->id = id + "-out";
@@ -968,6 +992,50 @@ int64_t lzyb_blob_get(const char* uri, void* dst, uint64_t cap) {
     if (b->data.size() > cap) return fail(LZYB_E_ARG, "object holds %zu bytes, buffer %llu", b->data.size(), (unsigned long long)cap);
     if (!b->data.empty()) memcpy(dst, b->data.data(), b->data.size());
     return (int64_t)b->data.size();
+}
+
+int lzyb_frame_store_put(const char* uri, lzyb_handle_t slot) {
+    if (!uri || !slot) return fail(LZYB_E_ARG, "null argument");
+    int rc = ops().slot_retain(slot);
+    if (rc != LZYB_OK) return rc;
+    lzyb_handle_t old = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_frames_mu);
+        auto it = g_frames.find(uri);
+        if (it != g_frames.end()) old = it->second;
+        g_frames[uri] = slot;
+    }
+    if (old) ops().slot_close(old);
+    return LZYB_OK;
+}
+
+int lzyb_frame_store_get(const char* uri, lzyb_handle_t* out) {
+    if (!uri || !out) return fail(LZYB_E_ARG, "null argument");
+    lzyb_handle_t h = frame_find(uri);
+    if (!h) return fail(LZYB_E_NOT_FOUND, "no frame at %s", uri);
+    *out = h;
+    return LZYB_OK;
+}
+
+int lzyb_frame_store_drop(const char* uri) {
+    if (!uri) return fail(LZYB_E_ARG, "null argument");
+    lzyb_handle_t h = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_frames_mu);
+        auto it = g_frames.find(uri);
+        if (it == g_frames.end()) return LZYB_OK;
+        h = it->second;
+        g_frames.erase(it);
+    }
+    ops().slot_close(h);
+    return LZYB_OK;
+}
+
+int lzyb_slots_set_republish(lzyb_handle_t h, int on) {
+    auto s = get_inst(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slots handle");
+    s->republish = on != 0;
+    return LZYB_OK;
 }
 
 int lzyb_blob_delete(const char* uri) {

@@ -1,0 +1,109 @@
+"""Lazy proxies: an object that looks like the result of an @op but is computed at the last moment.
+
+Same observable contract as the reference's ``lzy.proxy.proxy`` (pylzy/lzy/proxy/automagic.py:150-240
+and pylzy/lzy/api/v1/utils/proxy_adapter.py:14-83):
+
+* the proxy's *class* carries ``cls_attrs`` (``__lzy_proxied__``, ``__lzy_entry_id__`` …);
+* touching any attribute or special method materialises the value exactly once; the value — or the
+  exception raised while producing it — is cached on the proxy class;
+* ``obj.__lzy_origin__`` forces materialisation and returns the real object,
+  ``obj.__lzy_materialized__`` tells whether that already happened;
+* special methods are looked up on the prototype types, so ``len(p)``, ``p == x``, ``for _ in p``,
+  ``str(p)``, ``p + 1`` behave like the real value, and proxies passed as arguments to those methods
+  are materialised first;
+* ``type(p)`` is never the real type (``type(a) is str`` is False inside an op with
+  ``lazy_arguments=True``, pylzy/tests/core/test_workflow.py:386-393).
+
+The implementation is a per-proxy class whose special methods are plain forwarding closures.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, Optional, Sequence, Type
+
+_SKIP = frozenset({
+    "__class__", "__new__", "__init__", "__getattribute__", "__setattr__", "__delattr__", "__dict__", "__slots__",
+    "__init_subclass__", "__subclasshook__", "__class_getitem__", "__weakref__", "__mro__", "__del__",
+    "__reduce__", "__reduce_ex__", "__getstate__", "__setstate__", "__getnewargs__", "__getnewargs_ex__",
+    "__sizeof__", "__doc__", "__module__", "__qualname__", "__annotations__", "__getattr__",
+})
+
+
+class _LazyMeta(type):
+    """marker metaclass: ``is_proxy`` is an isinstance check on the class of the class"""
+
+
+def is_proxy(obj: Any) -> bool:
+    return isinstance(type(obj), _LazyMeta)
+
+
+def _unwrap(x: Any) -> Any:
+    return x.__lzy_origin__ if is_proxy(x) else x
+
+
+def _resolve(cls) -> Any:
+    state = type.__getattribute__(cls, "_lzy_state")
+    if "value" in state:
+        return state["value"]
+    if "error" in state:
+        raise state["error"]
+    try:
+        state["value"] = state["constructor"]()
+    except Exception as e:  # cached: a second touch re-raises the same exception
+        state["error"] = e
+        raise
+    return state["value"]
+
+
+def _forwarder(name: str):
+    def method(self, *args, **kwargs):
+        target = _resolve(type(self))
+        args = tuple(_unwrap(a) for a in args)
+        kwargs = {k: _unwrap(v) for k, v in kwargs.items()}
+        if name == "__bool__" and not hasattr(target, "__bool__"):
+            return bool(target)
+        return getattr(target, name)(*args, **kwargs)
+
+    method.__name__ = name
+    return method
+
+
+def proxy(constructor: Callable[[], Any], proto_types: Sequence[Type], cls_attrs: Optional[Dict[str, Any]] = None,
+          obj_attrs: Optional[Dict[str, Any]] = None) -> Any:
+    cls_attrs = dict(cls_attrs or {})
+    obj_attrs = dict(obj_attrs or {})
+    own = set(cls_attrs) | set(obj_attrs)
+    ns: Dict[str, Any] = {}
+    special = {"__bool__", "__eq__", "__ne__", "__hash__", "__str__", "__repr__"}
+    for typ in proto_types:
+        for name in dir(typ):
+            if name.startswith("__") and name.endswith("__") and name not in _SKIP:
+                special.add(name)
+    for name in special:
+        ns[name] = _forwarder(name)
+
+    def __getattribute__(self, item):
+        cls = type(self)
+        if item == "__lzy_origin__":
+            return _resolve(cls)
+        if item == "__lzy_materialized__":
+            return "value" in type.__getattribute__(cls, "_lzy_state")
+        if item == "__class__":
+            return cls
+        if item in own:
+            return object.__getattribute__(self, item)
+        return getattr(_resolve(cls), item)
+
+    def __setattr__(self, item, value):
+        if item in own:
+            return object.__setattr__(self, item, value)
+        return setattr(_resolve(type(self)), item, value)
+
+    ns["__getattribute__"] = __getattribute__
+    ns["__setattr__"] = __setattr__
+    ns.update(cls_attrs)
+    ns["_lzy_state"] = {"constructor": constructor}
+    cls = _LazyMeta("LazyProxy", (object,), ns)
+    inst = object.__new__(cls)
+    for k, v in obj_attrs.items():
+        object.__setattr__(inst, k, v)
+    return inst

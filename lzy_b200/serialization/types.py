@@ -1,0 +1,31 @@
+"""Runtime type inference used for @op argument / result validation.
+
+The reference takes ``get_type`` and ``EmptyContent`` from the un-vendored ``serialzy.types``
+(call sites: pylzy/lzy/core/call.py:12-14,307,326; pylzy/lzy/api/v1/startup.py:15,63); the behaviour
+restated here is the one its tests rely on (pylzy/tests/core/test_workflow.py:73-128,290-330 and
+pylzy/lzy/api/v1/utils/types.py:76-83): containers are typed by their first element, empty containers
+are typed with the ``EmptyContent`` marker, which is compatible with any element type."""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Tuple, Type
+
+
+class EmptyContent:
+    """element type of an empty list / tuple / dict"""
+
+
+def get_type(obj: Any) -> Type:
+    if type(obj) is list:
+        if len(obj) == 0:
+            return List[EmptyContent]  # type: ignore[return-value]
+        return List[get_type(obj[0])]  # type: ignore[return-value,misc]
+    if type(obj) is tuple:
+        if len(obj) == 0:
+            return Tuple[EmptyContent]  # type: ignore[return-value]
+        return Tuple[tuple(get_type(o) for o in obj)]  # type: ignore[return-value,misc]
+    if type(obj) is dict:
+        if len(obj) == 0:
+            return Dict[EmptyContent, EmptyContent]  # type: ignore[return-value]
+        k, v = next(iter(obj.items()))
+        return Dict[get_type(k), get_type(v)]  # type: ignore[return-value,misc]
+    return type(obj)

@@ -28,6 +28,7 @@ typedef struct {
     uint64_t digest[2];
     long long fail_after; /* -1 = never */
     int fail_read;
+    int refs;
 } mem_slot_t;
 
 static mem_slot_t g_slots[MAX_SLOTS];
@@ -84,6 +85,7 @@ static int new_slot(const char* id, int gpu, uint64_t nbytes, int is_input, lzyb
             s->is_input = is_input;
             s->gpu = gpu;
             s->fail_after = -1;
+            s->refs = 1;
             *out = s->h;
             pthread_mutex_unlock(&g_mu);
             return LZYB_OK;
@@ -178,12 +180,20 @@ static int m_slot_find(const char* id, lzyb_handle_t* out) {
 static int m_slot_close(lzyb_handle_t h) {
     pthread_mutex_lock(&g_mu);
     mem_slot_t* s = find(h);
-    if (s) {
+    if (s && --s->refs <= 0) {
         free(s->data);
         s->used = 0;
     }
     pthread_mutex_unlock(&g_mu);
     return LZYB_OK;
+}
+
+static int m_slot_retain(lzyb_handle_t h) {
+    pthread_mutex_lock(&g_mu);
+    mem_slot_t* s = find(h);
+    if (s) s->refs++;
+    pthread_mutex_unlock(&g_mu);
+    return s ? LZYB_OK : err(LZYB_E_ARG, "unknown slot handle");
 }
 
 static int64_t m_transfer_chunk(lzyb_handle_t dh, lzyb_handle_t sh, uint64_t off, uint64_t max_len, void* stream) {
@@ -304,7 +314,7 @@ static int m_input_reset(lzyb_handle_t h) {
 const lzyb_backend_ops_t hostmem_backend_ops = {
     m_slot_create,    m_input_open,     m_slot_commit,         m_slot_read,       m_slot_info,
     m_slot_find,      m_slot_close,     m_transfer_chunk,      m_input_finish,    m_input_write_host,
-    m_input_finish_expect, m_input_to_output, m_input_reset,
+    m_input_finish_expect, m_input_to_output, m_input_reset, m_slot_retain,
 };
 
 /* ---- test helpers ---- */

@@ -1,0 +1,287 @@
+"""Python API semantics that do not need a GPU, on a recording/in-process
+RuntimeMock like the reference's pylzy/tests/core/test_calls.py and pylzy/tests/api/v1/test_entries.py
+(URI rules :91-330, call-time snapshot of arguments :331-384)."""
+import hashlib
+import os
+import uuid
+from typing import Dict, List, Optional, Tuple, Union
+
+import pytest
+
+from lzy_b200.api.v1 import Lzy, LzyWorkflow, materialize, materialized, op
+from lzy_b200.api.v1.utils.proxy_adapter import get_proxy_entry_id, is_lzy_proxy
+from tests.mocks import RuntimeMock
+
+
+@op
+def foo(name: str, param: int) -> str:
+    return f"{name}: {param}"
+
+
+@op
+def foo_varargs(*args) -> str:
+    return ", ".join(str(a) for a in args)
+
+
+@op
+def accept_arr(ints: List[int]) -> List[int]:
+    return ints
+
+
+@op
+def accept_arr_and_modify(ints: List[int]) -> List[int]:
+    ints.append(len(ints))
+    return ints
+
+
+@pytest.fixture
+def lzy():
+    return Lzy(runtime=RuntimeMock(), storage_uri="mem://bucket/prefix")
+
+
+def wf_name():
+    return f"wf_{uuid.uuid4().hex}"
+
+
+def test_return_annotation_is_mandatory():
+    with pytest.raises(TypeError, match="Return type is not annotated"):
+        @op
+        def no_annotation():
+            pass
+
+
+def test_op_outside_workflow_is_a_plain_call():
+    assert foo("a", 1) == "a: 1"
+    assert foo.__name__ == "foo"
+
+
+def test_literal_tuple_annotation_means_several_outputs(lzy):
+    @op
+    def two() -> (str, int):
+        return "s", 42
+
+    @op
+    def one() -> Tuple[str, int]:
+        return "s", 42
+
+    with lzy.workflow(wf_name()) as wf:
+        a, b = two()
+        t = one()
+        assert len(wf.call_queue[0].entry_ids) == 2 and len(wf.call_queue[1].entry_ids) == 1
+    assert (a, b) == ("s", 42)
+    x, y = t  # one output that unpacks by iteration
+    assert (x, y) == ("s", 42)
+
+
+def test_none_annotation_returns_real_none_but_is_queued(lzy):
+    @op
+    def nothing() -> None:
+        pass
+
+    with lzy.workflow(wf_name()) as wf:
+        r = nothing()
+        assert r is None and len(wf.call_queue) == 1
+    assert len(lzy.runtime.calls) == 1
+
+
+def test_lazy_until_touched_and_eager(lzy):
+    with lzy.workflow(wf_name()) as wf:
+        s = foo("x", 1)
+        assert is_lzy_proxy(s) and not materialized(s) and len(wf.call_queue) == 1
+        assert lzy.runtime.calls == []
+        assert s == "x: 1"  # touching materialises: barrier, then get_data
+        assert materialized(s) and len(wf.call_queue) == 0
+    eager = Lzy(runtime=RuntimeMock(), storage_uri="mem://b")
+    with eager.workflow(wf_name(), eager=True) as wf:
+        s = foo("y", 2)
+        assert type(s) is str and s == "y: 2" and len(wf.call_queue) == 0
+
+
+def test_proxy_args_are_not_put_again_and_materialized_proxies_are_local_data(lzy):
+    with lzy.workflow(wf_name()) as wf:
+        a = accept_arr([1, 2, 3])
+        b = accept_arr(a)
+        c0, c1 = wf.call_queue
+        assert c1.arg_entry_ids[0] == c0.entry_ids[0] == get_proxy_entry_id(a)
+        a.append(4)  # materialises `a`, then mutates the local object
+        c = accept_arr(a)
+        assert wf.call_queue[-1].arg_entry_ids[0] != get_proxy_entry_id(a)
+    assert materialize(c) == [1, 2, 3, 4] and materialize(b) == [1, 2, 3]
+
+
+def test_argument_type_validation_at_call_time(lzy):
+    with lzy.workflow(wf_name()):
+        with pytest.raises(TypeError, match="Invalid types: argument param"):
+            foo("a", "not an int")
+        with pytest.raises(KeyError, match="required but not provided"):
+            foo("a")
+        with pytest.raises(KeyError, match="Unexpected argument"):
+            foo("a", 1, 2)
+        with pytest.raises(KeyError, match="Unexpected key argument"):
+            foo("a", 1, nope=3)
+        with pytest.raises(TypeError):
+            accept_arr(["str"])
+        accept_arr([])  # List[EmptyContent] fits List[int]
+
+
+def test_optional_union_dict_annotations(lzy):
+    @op
+    def opt(a: Optional[str]) -> str:
+        return "none" if a is None else "not none"
+
+    @op
+    def uni(p: Union[str, int]) -> bool:
+        return isinstance(p, str)
+
+    @op
+    def d(x: Dict[int, str]) -> Dict[int, str]:
+        return x
+
+    with lzy.workflow(wf_name()):
+        assert opt(None) == "none" and opt("x") == "not none"
+        assert uni("s") == True and uni(1) == False  # noqa: E712
+        assert d({1: "2"}) == {1: "2"} and d({}) == {}
+        with pytest.raises(TypeError):
+            d({1: 1})
+
+
+def test_same_local_data_stored_once_and_uri_is_prefix_plus_hash(lzy):
+    with lzy.workflow("test") as wf:
+        foo("hehe", 42)
+        foo_varargs(42)
+        q = list(wf.call_queue)
+    snap = wf.snapshot
+    uri_1 = snap.get(q[0].arg_entry_ids[1]).storage_uri
+    uri_2 = snap.get(q[1].arg_entry_ids[0]).storage_uri
+    assert uri_1 == uri_2 and lzy.runtime.store_counts[uri_1] == 1
+    assert uri_1.startswith("mem://bucket/prefix/lzy_runs/test/inputs/")
+    assert snap.get(q[0].arg_entry_ids[1]).data_hash == uri_1.rsplit("/", 1)[1]
+
+
+def test_result_uris_without_cache(lzy):
+    with lzy.workflow("test") as wf:
+        foo("a", 1)
+        foo("a", 1)
+        calls = list(wf.call_queue)
+    snap = wf.snapshot
+    uris = [snap.get(c.entry_ids[0]).storage_uri for c in calls]
+    assert uris[0] != uris[1]
+    for c, u in zip(calls, uris):
+        assert u == f"mem://bucket/prefix/lzy_runs/test/ops/foo/{c.id}/return_0"
+        assert snap.get(c.entry_ids[0]).data_hash == hashlib.md5(u.encode()).hexdigest()
+        assert snap.get(c.exception_id).storage_uri == f"mem://bucket/prefix/lzy_runs/test/ops/foo/{c.id}/exception"
+
+
+def test_result_uris_with_cache(lzy, monkeypatch):
+    @op(cache=True, version="1.7")
+    def cached(a: int, *, k: str = "z", b: int = 0) -> int:
+        return a + b
+
+    with lzy.workflow("test") as wf:
+        cached(1, k="kk", b=2)
+        cached(1, b=2, k="kk")
+        cached(2, k="kk", b=2)
+        calls = list(wf.call_queue)
+    snap = wf.snapshot
+    uris = [snap.get(c.entry_ids[0]).storage_uri for c in calls]
+    assert uris[0] == uris[1] != uris[2]
+    h = lambda c, e: snap.get(e).data_hash
+    c = calls[0]
+    expect = "_".join([h(c, c.arg_entry_ids[0]), f"b:{h(c, c.kwarg_entry_ids['b'])}", f"k:{h(c, c.kwarg_entry_ids['k'])}"])
+    assert uris[0] == f"mem://bucket/prefix/lzy_runs/test/ops/cached/1.7/{expect}/return_0"
+    monkeypatch.setenv("LZY_USER", "igor")
+    with Lzy(runtime=RuntimeMock(), storage_uri="mem://bucket/prefix").workflow("test") as wf2:
+        cached(1, k="kk", b=2)
+        c2 = wf2.call_queue[0]
+    assert wf2.snapshot.get(c2.entry_ids[0]).storage_uri.startswith("mem://bucket/prefix/igor/lzy_runs/test/ops/cached/1.7/")
+
+
+def test_local_data_changed_by_ref_is_snapshotted_at_call_time(lzy):
+    with lzy.workflow("wf") as wf:
+        ints = []
+        for i in range(5):
+            ints.append(i)
+            accept_arr(ints)
+        calls = list(wf.call_queue)
+    arg_uris = [wf.snapshot.get(c.arg_entry_ids[0]).storage_uri for c in calls]
+    assert len(set(arg_uris)) == 5
+    assert [materialize_result(lzy, wf, c) for c in calls] == [[0], [0, 1], [0, 1, 2], [0, 1, 2, 3], [0, 1, 2, 3, 4]]
+
+
+def materialize_result(lzy, wf, call):
+    import cloudpickle
+    return cloudpickle.loads(lzy.runtime.blobs[wf.snapshot.get(call.entry_ids[0]).storage_uri])
+
+
+def test_local_data_can_not_be_changed_by_ref_inside_op(lzy):
+    with lzy.workflow("wf") as wf:
+        ints = []
+        for i in range(5):
+            accept_arr_and_modify(ints)
+        calls = list(wf.call_queue)
+    assert ints == []  # the op mutated its own copy
+    assert len({wf.snapshot.get(c.arg_entry_ids[0]).storage_uri for c in calls}) == 1
+    assert all(materialize_result(lzy, wf, c) == [0] for c in calls)
+
+
+def test_only_one_active_workflow(lzy):
+    with lzy.workflow(wf_name()):
+        with pytest.raises(RuntimeError, match="Simultaneous workflows are not supported"):
+            with lzy.workflow(wf_name()):
+                pass
+    assert LzyWorkflow.get_active() is None
+    with lzy.workflow(wf_name()):  # the failed inner enter did not poison the state
+        pass
+
+
+def test_invalid_workflow_name(lzy):
+    with pytest.raises(ValueError, match="Invalid workflow name"):
+        lzy.workflow("bad name!")
+
+
+def test_exception_in_with_block_aborts(lzy):
+    with pytest.raises(ZeroDivisionError):
+        with lzy.workflow(wf_name()):
+            foo("a", 1)
+            1 / 0
+    assert lzy.runtime.aborted == 1 and lzy.runtime.finished == 0 and lzy.runtime.calls == []
+    assert LzyWorkflow.get_active() is None
+
+
+def test_nested_op_call_inside_op_is_plain(lzy):
+    @op
+    def outer(x: int) -> str:
+        return foo("inner", x)  # no workflow is active inside an op body
+
+    with lzy.workflow(wf_name()):
+        r = outer(5)
+    assert r == "inner: 5" and len(lzy.runtime.calls) == 1
+
+
+def test_serializer_registry_rules():
+    from lzy_b200.serialization import LzySerializerRegistry
+    from lzy_b200.serialization.api import Serializer
+    from tests.support.custom_serializer import Point, PointSerializer
+
+    reg = LzySerializerRegistry()
+
+    class InMain(PointSerializer):
+        pass
+
+    InMain.__module__ = "__main__"
+    with pytest.raises(ValueError, match="__main__"):
+        reg.register_serializer(InMain())
+    reg.register_serializer(PointSerializer())
+    assert isinstance(reg.find_serializer_by_type(Point), PointSerializer)
+    imps = reg.imports()
+    assert [(i.module_name, i.class_name) for i in imps] == [("tests.support.custom_serializer", "PointSerializer")]
+    other = LzySerializerRegistry()
+    other.load_imports(imps)
+    assert isinstance(other.find_serializer_by_type(Point), PointSerializer)
+    # nested values of a registered type go through their serializer inside pickles (copyreg hook)
+    import cloudpickle
+    blob = cloudpickle.dumps({"p": Point(1, 2)})
+    assert b"point:1,2" in blob and cloudpickle.loads(blob)["p"] == Point(1, 2)
+    reg.unregister_serializer(PointSerializer())
+    other.unregister_serializer(PointSerializer())
+    assert reg.imports() == []

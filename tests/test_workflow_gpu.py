@@ -1,0 +1,467 @@
+"""The reference's own workflow tests, run against ``Lzy(runtime=B200Runtime())`` instead of
+``LocalRuntime()``: same assertions as pylzy/tests/core/test_workflow.py (34 tests on the real local
+runtime), the call-time snapshot tests of pylzy/tests/api/v1/test_entries.py:453-550, the exception
+contract of pylzy/tests/api/v1/test_startup.py:52-83, plus tensor / ndarray payloads that stay in HBM."""
+import importlib
+import traceback
+import uuid
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from lzy_b200.api.v1 import B200Runtime, Lzy, op  # noqa: E402
+from lzy_b200.api.v1.utils.proxy_adapter import is_lzy_proxy, materialize, materialized  # noqa: E402
+
+
+@op
+def foo() -> str:
+    return "Foo:"
+
+
+@op
+def bar(a: str) -> str:
+    return f"{a} Bar:"
+
+
+@op
+def baz(a: str, b: int) -> str:
+    return f"{a} Baz({b}):"
+
+
+@op
+def boo(a: str, b: str) -> str:
+    return f"{a} {b} Boo"
+
+
+@op
+def inc(numb: int) -> int:
+    return numb + 1
+
+
+@op
+def accept_unspecified_list(lst: List) -> int:
+    return len(lst)
+
+
+@op
+def accept_int_list(lst: List[int]) -> int:
+    return len(lst)
+
+
+@op
+def accept_custom_class_list(lst: List[Lzy]) -> int:
+    return len(lst)
+
+
+@op
+def return_list() -> List[int]:
+    return [1, 2, 3]
+
+
+@op
+def accept_returns_dict(d: Dict) -> Dict:
+    return d
+
+
+@op
+def accept_arr(ints: List[int]) -> List[int]:
+    return ints
+
+
+@op
+def accept_arr_and_modify(ints: List[int]) -> List[int]:
+    ints.append(len(ints))
+    return ints
+
+
+_RUNTIME = None
+
+
+@pytest.fixture
+def lzy():
+    global _RUNTIME
+    if _RUNTIME is None:
+        _RUNTIME = B200Runtime()
+    return Lzy(runtime=_RUNTIME)
+
+
+@pytest.fixture
+def workflow_name():
+    return f"test_workflow_{uuid.uuid4().hex}"
+
+
+def test_lists(lzy, workflow_name):
+    @op
+    def list2list(a: List[int]) -> List[str]:
+        return [str(i) for i in a]
+
+    with lzy.workflow(workflow_name):
+        some_list = [1, 2, 3]
+        result = list2list(some_list)
+        assert [str(i) for i in some_list] == result
+
+
+def test_invalid_list_type_returns(lzy, workflow_name):
+    @op
+    def invalid_list_type_returns() -> List[str]:
+        return [1, 2, 3]
+
+    with pytest.raises(TypeError):
+        with lzy.workflow(workflow_name):
+            invalid_list_type_returns()
+
+
+def test_tuple_types(lzy, workflow_name):
+    @op
+    def t1() -> Tuple[str, int]:
+        return "str", 42
+
+    @op
+    def t2() -> Tuple[List, List]:
+        return [1], [2]
+
+    @op
+    def t3() -> Tuple[List[int], ...]:
+        return [1], [2]
+
+    @op
+    def t4() -> (str, int):
+        return "str", 42
+
+    with lzy.workflow(workflow_name):
+        a, b = t1()
+        c, d = t2()
+        e, f = t3()
+        g, h = t4()
+    assert ("str", 42, [1], [2], [1], [2], "str", 42) == (a, b, c, d, e, f, g, h)
+
+
+def test_optional_return(lzy, workflow_name):
+    @op
+    def optional_not_none() -> Optional[str]:
+        return "s"
+
+    @op
+    def optional_none() -> Optional[str]:
+        return None
+
+    with lzy.workflow(workflow_name):
+        n = optional_none()
+        s = optional_not_none()
+        assert materialized(s) is False
+        assert s is not None
+        assert "s" == s
+        assert materialized(s)
+        assert materialized(n) is False
+        if n:
+            pytest.fail()
+        assert materialized(n) is True
+        assert None == n  # noqa: E711
+
+
+def test_optional_and_union_args(lzy, workflow_name):
+    @op
+    def optional(a: Optional[str]) -> str:
+        return "not none" if a else "none"
+
+    @op
+    def union(p: bool) -> Union[str, int]:
+        return "str" if p else 42
+
+    @op
+    def is_str(a: Union[str, int]) -> bool:
+        return isinstance(a, str)
+
+    with lzy.workflow(workflow_name):
+        assert "not none" == optional("nn") and "none" == optional(None)
+        s, lint = union(True), union(False)
+        assert 42 == sum(1 for _ in range(lint)) and 42 == lint and "str" == s
+        assert True == is_str("str") and False == is_str(1)  # noqa: E712
+
+
+def test_globals_not_materialized(lzy, workflow_name):
+    with lzy.workflow(workflow_name):
+        global s1, s2
+        s1 = foo()
+        s2 = foo()
+        assert materialized(s1) is False and materialized(s2) is False
+
+
+def test_kwargs(lzy, workflow_name):
+    with lzy.workflow(workflow_name):
+        f = foo()
+        b = bar(a=f)
+    assert "Foo: Bar:" == b
+
+
+def test_return_accept_list(lzy, workflow_name):
+    @op
+    def accept_list(lst: List[int]) -> int:
+        return len(lst)
+
+    @op
+    def accept_two(lst: List, bst: List) -> int:
+        return len(lst)
+
+    with lzy.workflow(workflow_name):
+        a = return_list()
+        i = accept_list(a)
+        j = accept_two(a, [{}])
+    assert materialized(a) is False and materialized(i) is False
+    assert 3 == i and 3 == j
+
+
+def test_empty_and_unspecified_containers(lzy, workflow_name):
+    @op
+    def specified(d: Dict[int, str]) -> Dict[int, str]:
+        return d
+
+    with lzy.workflow(workflow_name):
+        a, b, c = accept_int_list([]), accept_unspecified_list([]), accept_custom_class_list([])
+        d = accept_unspecified_list([1, 2, 3])
+        e, f = accept_returns_dict({1: "2"}), accept_returns_dict({})
+        g, h = specified({}), specified(specified({1: "2"}))
+    assert (0, 0, 0, 3, {1: "2"}, {}, {}, {1: "2"}) == (a, b, c, d, e, f, g, h)
+    with pytest.raises(TypeError):
+        with lzy.workflow(workflow_name):
+            specified({1: 1})
+
+
+def test_lazy(lzy, workflow_name):
+    with lzy.workflow(workflow_name) as wf:
+        f = foo()
+        b1 = bar(f)
+        i = inc(1)
+        b2 = baz(b1, i)
+        queue_len = len(wf.call_queue)
+    assert 4 == queue_len
+    assert not materialized(f) and not materialized(b1) and not materialized(i) and not materialized(b2)
+    assert "Foo: Bar: Baz(2):" == b2
+
+
+def test_eager(lzy, workflow_name):
+    with lzy.workflow(workflow_name, eager=True) as wf:
+        f = foo()
+        b1 = bar(f)
+        i = inc(1)
+        b2 = baz(b1, i)
+        queue_len = len(wf.call_queue)
+    assert 0 == queue_len
+    for v, t in ((f, str), (b1, str), (i, int), (b2, str)):
+        assert is_lzy_proxy(v) is False and t == type(v)
+    assert "Foo: Bar: Baz(2):" == b2
+
+
+def test_materialize(lzy, workflow_name):
+    with lzy.workflow(workflow_name) as wf:
+        f = foo()
+        b1 = bar(f)
+        i = materialize(inc(1))
+        b2 = baz(b1, i)
+        queue_len = len(wf.call_queue)
+    assert 1 == queue_len
+    assert not materialized(f) and not materialized(b1) and not materialized(b2)
+    assert is_lzy_proxy(i) is False and int == type(i)
+    assert "Foo: Bar: Baz(2):" == b2
+
+
+def test_lazy_and_eager_args_loading(lzy, workflow_name):
+    @op(lazy_arguments=True)
+    def lazy_is_str(a: str) -> bool:
+        return type(a) is str
+
+    @op(lazy_arguments=False)
+    def eager_is_str(a: str) -> bool:
+        return type(a) is str
+
+    @op(lazy_arguments=True)
+    def return_lazy_argument(arg: str) -> str:
+        return arg
+
+    with lzy.workflow(workflow_name):
+        assert lazy_is_str("str") == False  # noqa: E712
+        assert eager_is_str("str") == True  # noqa: E712
+        assert "str" == return_lazy_argument("str")
+
+
+def test_local_startup_import(lzy, workflow_name):
+    @op
+    def op_with_import() -> bool:
+        try:
+            importlib.import_module("remote")
+            importlib.import_module("local")
+            importlib.import_module("utils")
+            return True
+        except Exception:
+            return False
+
+    with lzy.workflow(workflow_name):
+        res = op_with_import()
+    assert False == res  # noqa: E712
+
+
+def test_barrier_and_complex_graph(lzy, workflow_name):
+    """pylzy/tests/scenarios/complex_graph/__init__.py: 39 40 41 42 …"""
+    with lzy.workflow(workflow_name) as wf:
+        f = foo()
+        b = bar(f)
+        o = boo(b, baz(f, 3))
+        wf.barrier()
+        assert len(wf.call_queue) == 0
+        j = inc(0)
+        for _ in range(5):
+            j = inc(j)
+    assert "Foo: Bar: Foo: Baz(3): Boo" == o and 6 == j
+
+
+def test_exception_is_reraised_with_original_type_args_and_traceback(lzy, workflow_name):
+    @op
+    def exception() -> None:
+        raise TypeError("exception")
+
+    with pytest.raises(TypeError) as e:
+        with lzy.workflow(workflow_name):
+            exception()
+    assert e.value.args == ("exception",)
+    frames = traceback.extract_tb(e.value.__traceback__)
+    assert frames[-1].name == "exception" and frames[-1].filename == __file__
+
+    @op
+    def late(x: int) -> int:
+        return 1 // x
+
+    with pytest.raises(ZeroDivisionError):
+        with lzy.workflow(workflow_name):
+            a = inc(0)
+            late(0)
+            late(a)
+    # the runtime is still usable and no workflow is left active
+    with lzy.workflow(workflow_name):
+        assert 2 == inc(1)
+
+
+def test_op_result_changed_by_ref_and_not_inside_op(lzy, workflow_name):
+    """test_entries.py:476-550 on the real runtime"""
+    with lzy.workflow(workflow_name) as wf:
+        ints: List[int] = [1, 2, 3]
+        same = accept_arr(ints)
+        accept_arr(same)
+        e1, e2 = wf.call_queue[0].entry_ids[0], wf.call_queue[1].entry_ids[0]
+    assert ints == same and wf.snapshot.get(e1).storage_uri != wf.snapshot.get(e2).storage_uri
+
+    arg_eids, ret_eids = [], []
+    with lzy.workflow(workflow_name) as wf:
+        ints = accept_arr([])
+        for i in range(5):
+            accept_arr_and_modify(ints)
+            arg_eids.append(wf.call_queue[i + 1].arg_entry_ids[0])
+            ret_eids.append(wf.call_queue[i + 1].entry_ids[0])
+    assert len({wf.snapshot.get(e).storage_uri for e in arg_eids}) == 1
+    assert [] == ints
+
+
+def test_same_local_data_is_stored_once(lzy, workflow_name):
+    with lzy.workflow(workflow_name) as wf:
+        before = len(lzy.runtime.store)
+        big = list(range(1000))
+        accept_int_list(big)
+        accept_int_list(list(range(1000)))
+        u1 = wf.snapshot.get(wf.call_queue[0].arg_entry_ids[0]).storage_uri
+        u2 = wf.snapshot.get(wf.call_queue[1].arg_entry_ids[0]).storage_uri
+        assert u1 == u2 and len(lzy.runtime.store) == before + 1
+        assert len(u1.rsplit("/", 1)[1]) == 32  # prefix + 128-bit digest hex, the md5 position
+
+
+def test_cached_op_runs_once(lzy, workflow_name):
+    counter = {"n": 0}
+
+    @op(cache=True, version="1")
+    def expensive(x: int) -> int:
+        counter["n"] += 1
+        return x * 2
+
+    for _ in range(2):
+        with lzy.workflow(workflow_name):
+            assert 42 == expensive(21)
+    assert counter["n"] == 1 and lzy.runtime.stats["cached_ops"] >= 1
+
+
+# ---- HBM-resident payloads ---------------------------------------------------------------------------
+
+def test_cuda_tensor_chain_stays_on_device_and_is_bit_exact(lzy, workflow_name):
+    @op
+    def ident(t: torch.Tensor) -> torch.Tensor:
+        assert t.is_cuda
+        return t
+
+    @op
+    def add_one(t: torch.Tensor) -> torch.Tensor:
+        return t.add_(1)  # in place: the op owns its input frame
+
+    g = torch.Generator(device="cuda:0").manual_seed(1234)
+    x = torch.empty(1024, 1024, device="cuda:0").normal_(generator=g)
+    keep = x.clone()
+    before = lzy.runtime.store.bytes_put
+    with lzy.workflow(workflow_name):
+        y = ident(ident(ident(x)))
+        z = add_one(add_one(x))
+        x.zero_()  # mutating the caller's tensor after the call must not leak into the ops
+    assert torch.equal(y, keep) and y.is_cuda
+    assert torch.equal(z, keep + 2)
+    assert lzy.runtime.store.bytes_put - before == x.numel() * 4  # x was stored once (content addressed)
+
+
+def test_ndarray_and_cpu_tensor_round_trip(lzy, workflow_name):
+    @op
+    def ident(a: np.ndarray) -> np.ndarray:
+        assert isinstance(a, np.ndarray)
+        return a
+
+    @op
+    def cpu_ident(t: torch.Tensor) -> torch.Tensor:
+        assert not t.is_cuda
+        return t
+
+    x = np.random.default_rng(42).standard_normal(262144, dtype=np.float32)  # BASELINE config C1's payload
+    t = torch.arange(1000, dtype=torch.int64)
+    with lzy.workflow(workflow_name):
+        y = ident(ident(x))
+        u = cpu_ident(t)
+    assert isinstance(materialize(y), np.ndarray) and y.dtype == np.float32 and np.array_equal(y, x)
+    assert torch.equal(u, t)
+
+
+def test_non_contiguous_tensor_and_mixed_payload(lzy, workflow_name):
+    @op
+    def column_sum(t: torch.Tensor, meta: Dict[str, int]) -> (torch.Tensor, str):
+        return t.sum(dim=0), f"rows={t.shape[0]} k={meta['k']}"
+
+    m = torch.arange(64 * 256, dtype=torch.float32, device="cuda:0").reshape(64, 256)
+    view = m[:, 32:160]  # row-pitched view → the 2-D gather pack kernel
+    with lzy.workflow(workflow_name):
+        s, txt = column_sum(view, {"k": 7})
+    assert torch.equal(s, view.sum(dim=0)) and "rows=64 k=7" == txt
+
+
+def test_diamond_graph_runs_and_failure_stops_it(lzy, workflow_name):
+    @op
+    def src() -> torch.Tensor:
+        return torch.ones(1 << 16, device="cuda")
+
+    @op
+    def scale(t: torch.Tensor, k: int) -> torch.Tensor:
+        return t * k
+
+    @op
+    def total(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> float:
+        return float((a + b + c).sum().item())
+
+    with lzy.workflow(workflow_name):
+        s = src()
+        r = total(scale(s, 1), scale(s, 2), scale(s, 3))
+    assert r == 6.0 * (1 << 16)
