@@ -352,6 +352,27 @@ def run_ours(args):
                "h2d_bytes_per_step": payload, "d2h_bytes_per_step": payload, "ms_per_step": ms_e2e / e2e_steps,
                "steps": e2e_steps, "api": "C ABI: lzyb_slot_pack_host → chain → lzyb_copy_to_host (pinned host buffers)"}
 
+    api = None
+    if not args.no_e2e:
+        api_steps = max(3, min(args.steps, 10))
+        ms_api_dev, ms_api_e2e = api_bench(args, dev, payload, shape, api_steps, world, rank)
+        if multi:
+            t = torch.tensor([ms_api_dev, ms_api_e2e], device=f"cuda:{dev}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_api_dev, ms_api_e2e = float(t[0].item()), float(t[1].item())
+        api = {"device_resident": {"value": world * N_OPS * payload / (ms_api_dev * 1e-3) / 1e9, "unit": UNIT,
+                                   "ms_per_step": ms_api_dev, "ops_per_sec": world * N_OPS / (ms_api_dev * 1e-3)},
+               "steps": api_steps,
+               "call": "with Lzy(runtime=B200Runtime()).workflow(): y = f8(...f1(x)); materialize(y)"}
+        e2e_cabi = e2e
+        e2e = {"value": world * N_OPS * payload / (ms_api_e2e * 1e-3) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": payload, "d2h_bytes_per_step": payload, "ms_per_step": ms_api_e2e, "steps": api_steps,
+               "ops_per_sec": world * N_OPS / (ms_api_e2e * 1e-3),
+               "api": "Lzy(runtime=B200Runtime()).workflow(): x.cuda() from pinned host -> 8 @op chain -> y.cpu() into pinned host",
+               "c_abi_only": e2e_cabi}
+        if rank == 0 and not multi:
+            api["c1_two_op_1MiB_ndarray_ops_per_sec"] = small_chain_ops_per_sec(dev)
+
     cpu = None
     if rank == 0 and not multi and not args.no_cpu_baseline:
         sample_bytes = 128 << 20
@@ -371,11 +392,99 @@ def run_ours(args):
                        "l2": "inputs (1 GiB/edge) larger than the 126 MB L2; no flush needed",
                        "engine": args.engine},
             "ops_per_sec": world * N_OPS * args.steps / (ms_total * 1e-3),
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "api": api, "clocks": clocks, "gpu_launches": launches,
             "launch_breakdown": {k: {"n": len(v), "avg_ms": sum(v) / len(v)} for k, v in per_kind.items()},
         }), flush=True)
     if multi:
         dist.destroy_process_group()
+
+
+def api_bench(args, dev: int, payload: int, shape, steps: int, world: int, rank: int):
+    """The same chain through the public API — the call a user makes:
+
+        with Lzy(runtime=B200Runtime()).workflow("bench"):
+            y = f8(f7(... f1(x)))
+
+    device: x already a CUDA tensor, result left on the device.
+    e2e:    x in pinned host memory; each step does x.cuda() (H2D), the chain, y.cpu() (D2H)."""
+    import numpy as np
+    import torch
+    from lzy_b200.api.v1 import B200Runtime, Lzy, materialize, op
+    globals().update(torch=torch, np=np)  # annotations are strings here (PEP 563) and are evaluated in module globals
+
+    @op
+    def ident(t: torch.Tensor) -> torch.Tensor:
+        return t
+
+    rt = B200Runtime(gpus=[dev], placement="single")
+    lzy = Lzy(runtime=rt)
+    stream = torch.cuda.current_stream(dev)
+    x = torch.empty(shape, dtype=torch.float32, device=f"cuda:{dev}").normal_()
+    host_in = torch.empty(shape, dtype=torch.float32, pin_memory=True).copy_(x)
+    host_out = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+
+    def chain(inp):
+        with lzy.workflow(f"bench-{rank}"):
+            y = inp
+            for _ in range(N_OPS):
+                y = ident(y)
+            out = materialize(y)
+        rt.clear()  # release the HBM frames of this step
+        return out
+
+    def timed(n, from_host):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(n):
+            if from_host:
+                y = chain(host_in.to(f"cuda:{dev}", non_blocking=True))
+                host_out.copy_(y, non_blocking=True)
+            else:
+                y = chain(x)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3), y
+
+    _, y = timed(2, False)
+    assert torch.equal(y, x), "API chain delivered different bytes"
+    ms_dev, _ = timed(steps, False)
+    timed(1, True)
+    ms_e2e, _ = timed(steps, True)
+    assert torch.equal(host_out, host_in)
+    rt.close()
+    return ms_dev / steps, ms_e2e / steps
+
+
+def small_chain_ops_per_sec(dev: int, reps: int = 20):
+    """BASELINE config C1 on the B200 runtime: two-@op identity chain over a 1 MiB float32 ndarray."""
+    import numpy as np
+    from lzy_b200.api.v1 import B200Runtime, Lzy, materialize, op
+    globals().update(np=np)
+
+    @op
+    def ident(a: np.ndarray) -> np.ndarray:
+        return a
+
+    rt = B200Runtime(gpus=[dev], placement="single")
+    lzy = Lzy(runtime=rt)
+    x = np.random.default_rng(42).standard_normal(262144, dtype=np.float32)
+
+    def once():
+        with lzy.workflow("c1"):
+            y = materialize(ident(ident(x)))
+        return y
+
+    for _ in range(2):
+        y = once()
+    assert np.array_equal(y, x)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    dt = time.perf_counter() - t0
+    rt.close()
+    return 2 * reps / dt
 
 
 def main():

@@ -201,6 +201,9 @@ int lzyb_blob_delete(const char* uri);
 int lzyb_frame_store_put(const char* uri, lzyb_handle_t slot);
 int lzyb_frame_store_get(const char* uri, lzyb_handle_t* slot_out);   /* LZYB_E_NOT_FOUND if absent */
 int lzyb_frame_store_drop(const char* uri);
+/* drop every frame whose URI starts with `prefix` (NULL/"" = all); returns how many were dropped */
+int lzyb_frame_store_clear(const char* prefix);
+int64_t lzyb_frame_store_bytes(void);
 /* republish delivered inputs as "<slot>-out" producers (InputSlot.java:160-168); default on.  The
  * Python runtime turns it off so that an op owns its input frame and may mutate it in place. */
 int lzyb_slots_set_republish(lzyb_handle_t slots, int on);

@@ -82,6 +82,8 @@ _SIGS = {
     "lzyb_frame_store_put": (_i, [_s, _H]),
     "lzyb_frame_store_get": (_i, [_s, C.POINTER(_H)]),
     "lzyb_frame_store_drop": (_i, [_s]),
+    "lzyb_frame_store_clear": (_i, [_s]),
+    "lzyb_frame_store_bytes": (C.c_int64, []),
     "lzyb_slots_set_republish": (_i, [_H, _i]),
     "lzyb_graph_create": (_i, [_i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i, _i, C.POINTER(_H)]),
     "lzyb_graph_free": (_i, [_H]),
@@ -328,6 +330,14 @@ def frame_store_get(uri: str) -> Optional[int]:
 
 def frame_store_drop(uri: str) -> None:
     _check(lib.lzyb_frame_store_drop(_b(uri)))
+
+
+def frame_store_clear(prefix: str = "") -> int:
+    return _check(lib.lzyb_frame_store_clear(_b(prefix)))
+
+
+def frame_store_bytes() -> int:
+    return int(lib.lzyb_frame_store_bytes())
 
 
 class ExecutionContext:

@@ -161,11 +161,17 @@ class FrameStore:
         if s is not None:
             s.close()
 
-    def clear(self) -> None:
+    def clear(self, prefix: str = "hbm://") -> None:
+        """drop every frame under `prefix`, including op outputs nobody has read yet"""
         with self._lock:
-            uris = list(self._frames) + list(self._inline)
+            uris = [u for u in list(self._frames) + list(self._inline) if u.startswith(prefix)]
         for u in uris:
             self.drop(u)
+        H.frame_store_clear(prefix)
+
+    @staticmethod
+    def resident_bytes() -> int:
+        return H.frame_store_bytes()
 
     def __len__(self):
         return len(self._frames)

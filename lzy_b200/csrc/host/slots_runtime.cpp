@@ -463,6 +463,10 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
         inst->service.unreg(id);  // got peer, unregistering
         if (!download(cur, tid, err)) return false;
         state = LZYB_IS_READY;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            handed_over = true;  // from here on the frame lives until the context is closed
+        }
         // re-publish the delivered bytes as producer "<slotId>-out" on the same channel
         // (InputSlot.java:160-168).  The companion joins the context before `ready` completes so that
         // an afterExecution() issued right after beforeExecution() already sees it.
@@ -1029,6 +1033,39 @@ int lzyb_frame_store_drop(const char* uri) {
     }
     ops().slot_close(h);
     return LZYB_OK;
+}
+
+int lzyb_frame_store_clear(const char* prefix) {
+    std::vector<lzyb_handle_t> victims;
+    {
+        std::lock_guard<std::mutex> lk(g_frames_mu);
+        const std::string p = prefix ? prefix : "";
+        for (auto it = g_frames.begin(); it != g_frames.end();) {
+            if (it->first.compare(0, p.size(), p) == 0) {
+                victims.push_back(it->second);
+                it = g_frames.erase(it);
+            } else
+                ++it;
+        }
+    }
+    for (auto h : victims) ops().slot_close(h);
+    return (int)victims.size();
+}
+
+int64_t lzyb_frame_store_bytes(void) {
+    std::vector<lzyb_handle_t> hs;
+    {
+        std::lock_guard<std::mutex> lk(g_frames_mu);
+        for (auto& kv : g_frames) hs.push_back(kv.second);
+    }
+    std::sort(hs.begin(), hs.end());
+    hs.erase(std::unique(hs.begin(), hs.end()), hs.end());
+    int64_t total = 0;
+    for (auto h : hs) {
+        lzyb_slot_info_t info;
+        if (ops().slot_info(h, &info) == LZYB_OK) total += (int64_t)info.nbytes;
+    }
+    return total;
 }
 
 int lzyb_slots_set_republish(lzyb_handle_t h, int on) {

@@ -54,6 +54,37 @@ def _resolve(cls) -> Any:
     return state["value"]
 
 
+def _unwrap_tree(x: Any) -> Any:
+    if is_proxy(x):
+        return x.__lzy_origin__
+    if isinstance(x, tuple):
+        return tuple(_unwrap_tree(v) for v in x)
+    if isinstance(x, list):
+        return [_unwrap_tree(v) for v in x]
+    if isinstance(x, dict):
+        return {k: _unwrap_tree(v) for k, v in x.items()}
+    return x
+
+
+# Library dispatch protocols (`np.array_equal(p, a)`, `torch.equal(p, t)`, `np.add(p, 1)`): numpy and
+# torch look these up on the *type* of the argument and pass the argument types along, so plain
+# forwarding would hand the libraries a type they do not know.  Materialise and call the function.
+def _array_function(self, func, types, args, kwargs):
+    return func(*_unwrap_tree(args), **_unwrap_tree(kwargs))
+
+
+def _array_ufunc(self, ufunc, method, *inputs, **kwargs):
+    return getattr(ufunc, method)(*_unwrap_tree(inputs), **_unwrap_tree(kwargs))
+
+
+def _torch_function(cls, func, types, args=(), kwargs=None):
+    return func(*_unwrap_tree(args), **_unwrap_tree(kwargs or {}))
+
+
+_PROTOCOLS = {"__array_function__": _array_function, "__array_ufunc__": _array_ufunc,
+              "__torch_function__": classmethod(_torch_function)}
+
+
 def _forwarder(name: str):
     def method(self, *args, **kwargs):
         target = _resolve(type(self))
@@ -79,7 +110,7 @@ def proxy(constructor: Callable[[], Any], proto_types: Sequence[Type], cls_attrs
             if name.startswith("__") and name.endswith("__") and name not in _SKIP:
                 special.add(name)
     for name in special:
-        ns[name] = _forwarder(name)
+        ns[name] = _PROTOCOLS.get(name) or _forwarder(name)
 
     def __getattribute__(self, item):
         cls = type(self)
@@ -89,7 +120,7 @@ def proxy(constructor: Callable[[], Any], proto_types: Sequence[Type], cls_attrs
             return "value" in type.__getattribute__(cls, "_lzy_state")
         if item == "__class__":
             return cls
-        if item in own:
+        if item in own or item in _PROTOCOLS:
             return object.__getattribute__(self, item)
         return getattr(_resolve(cls), item)
 
