@@ -160,6 +160,7 @@ def run_ours(args):
 
     from lzy_b200 import _native as N
     from lzy_b200.devmem import view_tensor
+    from lzy_b200.ring import exchange_descriptors, predecessor
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,8 +199,6 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     kern_events = []  # (start, end, kind, bytes) for every kernel launch of ours inside the timed region
-    desc_buf = torch.zeros(256, dtype=torch.uint8, device=f"cuda:{dev}")
-    all_desc = [torch.zeros(256, dtype=torch.uint8, device=f"cuda:{dev}") for _ in range(world)]
 
     def timed(kind, fn, record):
         if not record:
@@ -215,11 +214,8 @@ def run_ours(args):
         """control plane of one hop: every rank learns its predecessor's slot descriptor"""
         if not multi:
             return out_slot, None
-        d = out_slot.export()
-        desc_buf.copy_(torch.frombuffer(bytearray(bytes(d)), dtype=torch.uint8))
-        dist.all_gather(all_desc, desc_buf)
-        raw = bytes(all_desc[(rank - 1) % world].cpu().numpy().tobytes())
-        peer = N.SlotHandle.import_peer(N.IpcDesc.from_buffer_copy(raw), dev)
+        descs = exchange_descriptors(dist, bytes(out_slot.export()), f"cuda:{dev}")
+        peer = N.SlotHandle.import_peer(N.IpcDesc.from_buffer_copy(descs[predecessor(rank, world)]), dev)
         return peer, peer
 
     def chain_step(step_id, record, from_host):

@@ -1,0 +1,159 @@
+"""Multi-GPU behaviour inside one process (workers pinned one per GPU, peer access over NVSwitch):
+cross-GPU consumer-pull, fan-out, and the runtime placing an @op chain / diamond across GPUs
+(BASELINE configs C2, C3, C5 at test sizes).  Needs ≥ 2 GPUs: run with `gpurun --gpus 2`."""
+import uuid
+from typing import Dict
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+    pytest.skip("needs at least 2 GPUs", allow_module_level=True)
+
+from lzy_b200 import _native as N  # noqa: E402
+from lzy_b200.api.v1 import B200Runtime, Lzy, op  # noqa: E402
+
+NGPU = torch.cuda.device_count()
+
+
+@pytest.fixture(scope="module")
+def native_all():
+    N.init(0, 0, 64 << 20)
+    return N
+
+
+def to_host(slot):
+    out = np.empty(slot.nbytes, dtype=np.uint8)
+    slot.copy_to_host(out.ctypes.data, slot.nbytes)
+    return out
+
+
+@pytest.mark.parametrize("engine", ["ldg", "tma"])
+def test_cross_gpu_pull_is_bit_exact(native_all, engine):
+    N.set_copy_engine(N.ENGINE_TMA if engine == "tma" else N.ENGINE_LDG)
+    try:
+        n = (48 << 20) + 4096 + 7
+        a = np.random.default_rng(5).integers(0, 256, n, dtype=np.uint8)
+        t = torch.from_numpy(a).to("cuda:0")
+        out = N.SlotHandle.create_output("x/out", 0, n)
+        inp = N.SlotHandle.open_input("x/in", 1, n)
+        try:
+            out.pack(t.data_ptr(), n)
+            dg = out.commit()
+            before = N.stats()["bytes_pulled_peer"]
+            off = 0
+            while True:
+                moved = inp.transfer_chunk(out, off, 8 << 20)
+                if moved == N.EOF:
+                    break
+                off += moved
+            inp.finish(out)
+            assert N.stats()["bytes_pulled_peer"] - before == n
+            assert inp.info().gpu == 1 and tuple(inp.info().digest) == dg == oracle.digest(a)
+            assert np.array_equal(to_host(inp), a)
+        finally:
+            out.close()
+            inp.close()
+    finally:
+        N.set_copy_engine(N.ENGINE_AUTO)
+
+
+def test_broadcast_chain_to_every_gpu(native_all):
+    """C3 at test size: one producer on GPU 0, one consumer per GPU (GPU 0 included), chunk-pipelined."""
+    n = (96 << 20) + 33
+    t = torch.empty(n + 16, dtype=torch.uint8, device="cuda:0")
+    N.fill_pattern(0, t.data_ptr(), n, 7)
+    torch.cuda.synchronize(0)
+    expect = oracle.pattern(n, 7)
+    src = N.SlotHandle.create_output("bc/src", 0, n)
+    dsts = [N.SlotHandle.open_input(f"bc/dst{g}", g, n) for g in range(NGPU)]
+    try:
+        src.pack(t.data_ptr(), n)
+        dg = src.commit()
+        assert dg == oracle.digest(expect)
+        N.broadcast(src, dsts, 16 << 20)
+        for d in dsts:
+            assert d.info().state == N.ST_READY and tuple(d.info().digest) == dg
+            assert np.array_equal(to_host(d), expect)
+    finally:
+        src.close()
+        for d in dsts:
+            d.close()
+
+
+@pytest.fixture(scope="module")
+def lzy():
+    rt = B200Runtime(placement="round_robin")
+    yield Lzy(runtime=rt)
+    rt.close()
+
+
+def test_chain_round_robin_over_gpus(lzy):
+    """C2's placement rule: op k on GPU k mod G; every edge crosses NVLink."""
+    seen = []
+
+    @op
+    def hop(t: torch.Tensor) -> torch.Tensor:
+        seen.append(t.device.index)
+        return t
+
+    x = torch.empty(4096, 4096, device="cuda:0").normal_()
+    keep = x.clone()
+    before = N.stats()["bytes_pulled_peer"]
+    with lzy.workflow(f"wf{uuid.uuid4().hex}"):
+        y = x
+        for _ in range(8):
+            y = hop(y)
+    assert torch.equal(y.to("cuda:0"), keep)
+    assert len(set(seen)) == min(NGPU, 8) and N.stats()["bytes_pulled_peer"] - before >= 6 * x.numel() * 4
+
+
+def test_diamond_mixed_payloads_across_gpus(lzy):
+    """C5 at test size: source → branches (2 ops each) → sink; each edge carries a tensor and a dict."""
+    @op
+    def source() -> (torch.Tensor, Dict[str, int]):
+        return torch.arange(1 << 20, dtype=torch.float32, device="cuda"), {"hops": 0}
+
+    @op
+    def branch(t: torch.Tensor, meta: Dict[str, int], k: int) -> (torch.Tensor, Dict[str, int]):
+        return t * k, {"hops": meta["hops"] + 1, "k": k}
+
+    @op
+    def sink(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, ma: Dict[str, int], mb: Dict[str, int],
+             mc: Dict[str, int]) -> (float, int):
+        dev = a.device
+        return float((a + b.to(dev) + c.to(dev)).sum().item()), ma["hops"] + mb["hops"] + mc["hops"]
+
+    with lzy.workflow(f"wf{uuid.uuid4().hex}"):
+        t, m = source()
+        outs = []
+        for k in (1, 2, 3):
+            t1, m1 = branch(t, m, k)
+            outs.append(branch(t1, m1, 1))
+        total, hops = sink(outs[0][0], outs[1][0], outs[2][0], outs[0][1], outs[1][1], outs[2][1])
+    n = 1 << 20
+    assert total == float(6 * (n * (n - 1) // 2)) or abs(total - 6 * (n * (n - 1) / 2)) / (6 * n * n / 2) < 1e-6
+    assert hops == 6
+
+
+def test_locality_placement_follows_the_data():
+    rt = B200Runtime(placement="locality")
+    try:
+        lz = Lzy(runtime=rt)
+        where = []
+
+        @op
+        def here(t: torch.Tensor) -> int:
+            where.append(t.device.index)
+            return t.device.index
+
+        with lz.workflow(f"wf{uuid.uuid4().hex}"):
+            r = here(torch.ones(1 << 20, device="cuda:1"))
+        assert r == 1 and where == [1]
+    finally:
+        rt.close()
