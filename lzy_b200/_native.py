@@ -165,6 +165,7 @@ _SIGNATURES = {
     "lzyb_stats_reset": (C.c_int, []),
     "lzyb_set_copy_engine": (C.c_int, [C.c_int]),
     "lzyb_set_grid": (C.c_int, [C.c_int]),
+    "lzyb_set_tma_config": (C.c_int, [C.c_int]),
     "lzyb_fault_inject": (C.c_int, [_H, C.c_int, C.c_uint64]),
 }
 for _name, (_res, _args) in _SIGNATURES.items():
@@ -390,6 +391,10 @@ def fill_pattern(gpu: int, dptr: int, nbytes: int, seed: int, stream: int = 0) -
 
 def set_copy_engine(engine: int) -> None:
     check(lib.lzyb_set_copy_engine(engine))
+
+
+def set_tma_config(index: int) -> None:
+    check(lib.lzyb_set_tma_config(index))
 
 
 def set_grid(ctas_per_sm: int) -> None:

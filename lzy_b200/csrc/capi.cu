@@ -37,9 +37,27 @@ static_assert(sizeof(lzyb_frame_header_t) == 128, "frame header must be 128 byte
 static_assert(sizeof(lzyb_ipc_desc_t) == 256, "ipc descriptor must be 256 bytes");
 constexpr int CTL_SLAB = 8192;        // slots that can be live per device
 constexpr int MBOX_SLAB = 65536;      // mailboxes (pinned, all devices)
-constexpr int TMA_STAGES = 6;
-constexpr int TMA_STAGE_BYTES = 16384;
-constexpr size_t TMA_SMEM = static_cast<size_t>(TMA_STAGES) * TMA_STAGE_BYTES + 2 * TMA_STAGES * sizeof(uint64_t);
+// TMA ring shapes that can be selected at run time (lzyb_set_tma_config): {stages, stage bytes, CTAs per SM}
+struct TmaCfg {
+    int stages, stage_bytes, ctas_per_sm;
+};
+constexpr TmaCfg kTmaCfgs[] = {{6, 16384, 2}, {3, 32768, 2}, {6, 32768, 1}, {12, 16384, 1}, {8, 8192, 3}, {4, 16384, 3}};
+constexpr int kNumTmaCfgs = sizeof(kTmaCfgs) / sizeof(kTmaCfgs[0]);
+constexpr size_t tma_smem(int stages, int stage_bytes) { return static_cast<size_t>(stages) * stage_bytes + 2 * stages * sizeof(uint64_t); }
+
+template <int STAGES, int STAGE_BYTES>
+void launch_tma(const CopyParams& p, bool store, int grid, cudaStream_t st, bool& attr_set) {
+    constexpr size_t smem = tma_smem(STAGES, STAGE_BYTES);
+    if (!attr_set) {  // the opt-in shared-memory size is a per-device function attribute
+        cudaFuncSetAttribute(tma_stream_digest_kernel<STAGES, STAGE_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(tma_stream_digest_kernel<STAGES, STAGE_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    if (store)
+        tma_stream_digest_kernel<STAGES, STAGE_BYTES, true><<<grid, TMA_THREADS, smem, st>>>(p);
+    else
+        tma_stream_digest_kernel<STAGES, STAGE_BYTES, false><<<grid, TMA_THREADS, smem, st>>>(p);
+}
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -78,7 +96,7 @@ struct DeviceCtx {
     size_t pooled_bytes = 0;
     SlotCtl* ctl_slab = nullptr;
     std::vector<int> ctl_free;
-    bool tma_attr_set = false;
+    bool tma_attr[8] = {false, false, false, false, false, false, false, false};
 };
 
 struct Slot {
@@ -141,6 +159,7 @@ struct Global {
     std::map<std::pair<int, std::string>, void*> ipc_cache;
     // policy
     std::atomic<int> engine{0};
+    std::atomic<int> tma_cfg{0};
     std::atomic<int> ctas_per_sm{4};
     std::atomic<int> global_fault{LZYB_FAULT_NONE};
     // stats
@@ -248,20 +267,19 @@ int launch_stream(DeviceCtx& d, const CopyParams& p, bool store, cudaStream_t st
     if (engine == 0) engine = tma_ok ? 2 : 1;  // auto: TMA bulk when eligible (measured 8 % faster, profiles/r01_summary.md)
     if (engine == 2 && !tma_ok) engine = 1;
     if (engine == 2) {
-        if (!d.tma_attr_set) {
-            cudaFuncSetAttribute(tma_stream_digest_kernel<TMA_STAGES, TMA_STAGE_BYTES, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
-            cudaFuncSetAttribute(tma_stream_digest_kernel<TMA_STAGES, TMA_STAGE_BYTES, false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
-            d.tma_attr_set = true;
-        }
-        uint64_t tiles = p.nbytes / TMA_STAGE_BYTES;
-        int grid = d.sm_count * 2;
+        const int ci = g.tma_cfg.load();
+        const TmaCfg cfg = kTmaCfgs[ci];
+        uint64_t tiles = p.nbytes / cfg.stage_bytes;
+        int grid = d.sm_count * cfg.ctas_per_sm;
         if ((uint64_t)grid > tiles) grid = (int)(tiles ? tiles : 1);
-        if (store)
-            tma_stream_digest_kernel<TMA_STAGES, TMA_STAGE_BYTES, true><<<grid, TMA_THREADS, TMA_SMEM, st>>>(p);
-        else
-            tma_stream_digest_kernel<TMA_STAGES, TMA_STAGE_BYTES, false><<<grid, TMA_THREADS, TMA_SMEM, st>>>(p);
+        switch (ci) {
+            case 0: launch_tma<6, 16384>(p, store, grid, st, d.tma_attr[0]); break;
+            case 1: launch_tma<3, 32768>(p, store, grid, st, d.tma_attr[1]); break;
+            case 2: launch_tma<6, 32768>(p, store, grid, st, d.tma_attr[2]); break;
+            case 3: launch_tma<12, 16384>(p, store, grid, st, d.tma_attr[3]); break;
+            case 4: launch_tma<8, 8192>(p, store, grid, st, d.tma_attr[4]); break;
+            default: launch_tma<4, 16384>(p, store, grid, st, d.tma_attr[5]); break;
+        }
     } else {
         const uint64_t tile = 256ull * 8;
         uint64_t want = (nvec + tile - 1) / tile;
@@ -1373,6 +1391,12 @@ int lzyb_stats_reset(void) {
 int lzyb_set_copy_engine(int engine) {
     if (engine < 0 || engine > 2) return fail(LZYB_E_ARG, "engine must be 0 (auto), 1 (LDG/STG) or 2 (TMA bulk)");
     g.engine = engine;
+    return LZYB_OK;
+}
+
+int lzyb_set_tma_config(int index) {
+    if (index < 0 || index >= kNumTmaCfgs) return fail(LZYB_E_ARG, "tma config index must be in [0, %d)", kNumTmaCfgs);
+    g.tma_cfg = index;
     return LZYB_OK;
 }
 

@@ -719,6 +719,11 @@ void pump_loop(lzyb_handle_t cm, std::shared_ptr<Pump> p) {
                 for (auto& kv : g_instances)
                     if (kv.second->cm == cm) insts.push_back(kv.second);
             }
+            // The reference issues StartTransfer first and marks the transfer ACTIVE afterwards
+            // (ActionScheduler.java:74-91); a consumer that finishes its download in between would
+            // get FAILED_PRECONDITION from TransferCompleted.  With GPU-speed transfers that window
+            // is real, so the transfer is activated first and the channel is failed if delivery fails.
+            lzyb_cm_action_result(cm, a.channel_id, a.transfer_id, 1, "");
             int rc = LZYB_E_NOT_FOUND;
             for (auto& inst : insts) {
                 auto s = inst->service.find(a.consumer_id);
@@ -726,7 +731,7 @@ void pump_loop(lzyb_handle_t cm, std::shared_ptr<Pump> p) {
                 rc = s->start_transfer(a.producer, a.transfer_id);
                 break;
             }
-            lzyb_cm_action_result(cm, a.channel_id, a.transfer_id, rc == LZYB_OK, rc == LZYB_OK ? "" : "Cannot connect.");
+            if (rc != LZYB_OK) lzyb_cm_action_result(cm, a.channel_id, a.transfer_id, 0, "Cannot connect.");
         } else if (a.kind == LZYB_ACT_ABORT_WORKFLOW) {
             // lzy-service aborts the workflow: every context of that execution is closed
             std::vector<std::shared_ptr<ExecCtx>> ctxs;
