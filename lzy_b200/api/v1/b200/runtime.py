@@ -59,6 +59,7 @@ class B200RuntimeConfig:
     prefetch: bool = True
     max_parallel_ops: int = 0                    # 0 = 2 × GPUs
     republish_inputs: bool = False               # "<slot>-out" seeding (InputSlot.java:160-168); ops own their inputs when off
+    retain: str = "auto"                         # "auto": a frame is freed once no proxy / queued call can ask for it; "all": keep until clear()
     chunk_bytes: int = 0                         # 0 = one launch per transfer; the reference streams 2 MiB chunks
     copy_engine: str = "auto"                    # "auto" | "ldg" | "tma"
     user_id: str = field(default_factory=lambda: os.environ.get("LZY_USER", "local-user"))
@@ -123,7 +124,9 @@ class B200Runtime(Runtime):
 
     def snapshot(self, workflow: "LzyWorkflow", storage_uri_prefix: str) -> Optional[Snapshot]:
         self._ensure_ready()
-        return FrameSnapshot(workflow.owner.serializer_registry, storage_uri_prefix, self.store, workflow.owner.storage_name)
+        snap = FrameSnapshot(workflow.owner.serializer_registry, storage_uri_prefix, self.store, workflow.owner.storage_name)
+        snap.auto_release = self.config.retain == "auto"
+        return snap
 
     async def start(self, workflow: "LzyWorkflow") -> str:
         self._ensure_ready()
@@ -210,6 +213,10 @@ class B200Runtime(Runtime):
                 self.stats["cached_ops"] += 1
                 continue
             todo.append(c)
+        for c in calls:
+            if c not in todo and hasattr(snapshot, "unpin"):  # a skipped (cached) call releases its inputs too
+                for eid in list(c.arg_entry_ids) + list(c.kwarg_entry_ids.values()):
+                    snapshot.unpin(eid)
         if not todo:
             return
         calls = todo
@@ -288,6 +295,13 @@ class B200Runtime(Runtime):
             for ctx in ctxs:
                 ctx.close()
             graph.close()
+            if hasattr(snapshot, "unpin"):
+                for c in calls:
+                    for eid in c.entry_ids:
+                        snapshot.produced(eid)
+                for c in calls:
+                    for eid in list(c.arg_entry_ids) + list(c.kwarg_entry_ids.values()):
+                        snapshot.unpin(eid)
 
     # ---- one op (WorkerApiImpl.executeOp + startup.process_execution) -------------------------------------
     def _run_task(self, t: int, call: "LzyCall", ctx: H.ExecutionContext, gpu: int, input_eids: List[str]) -> None:

@@ -43,6 +43,7 @@ class FrameStore:
         self._frames: Dict[str, N.SlotHandle] = {}
         self._inline: Dict[str, Any] = {}  # tiny control values (exception tuples) that never need a frame
         self._lock = threading.RLock()
+        self._refs: Dict[str, int] = {}  # how many snapshot entries still need the frame at this URI
         self.bytes_put = 0
 
     # ---- writing ------------------------------------------------------------------------------
@@ -153,6 +154,20 @@ class FrameStore:
         return 0 if s is None else s.nbytes
 
     # ---- lifetime -----------------------------------------------------------------------------
+    def retain(self, uri: str) -> None:
+        with self._lock:
+            self._refs[uri] = self._refs.get(uri, 0) + 1
+
+    def release(self, uri: str) -> None:
+        """drop one entry's claim on `uri`; the frame goes back to the HBM pool with the last one"""
+        with self._lock:
+            n = self._refs.get(uri, 0) - 1
+            if n > 0:
+                self._refs[uri] = n
+                return
+            self._refs.pop(uri, None)
+        self.drop(uri)
+
     def drop(self, uri: str) -> None:
         with self._lock:
             self._inline.pop(uri, None)
@@ -165,6 +180,8 @@ class FrameStore:
         """drop every frame under `prefix`, including op outputs nobody has read yet"""
         with self._lock:
             uris = [u for u in list(self._frames) + list(self._inline) if u.startswith(prefix)]
+            for u in [u for u in self._refs if u.startswith(prefix)]:
+                self._refs.pop(u, None)
         for u in uris:
             self.drop(u)
         H.frame_store_clear(prefix)

@@ -12,6 +12,7 @@ implementation of ``DefaultSnapshot``'s contract (put_data :141-172, get_data :1
 from __future__ import annotations
 
 import dataclasses
+import threading
 import uuid
 from abc import ABC, abstractmethod
 from typing import TYPE_CHECKING, Any, Dict, Optional, Type, cast
@@ -84,6 +85,52 @@ class FrameSnapshot(Snapshot):
         self._store = store
         self._storage_name = storage_name
         self._entries: Dict[str, SnapshotEntry] = {}
+        # HBM is not a disk: a payload is kept only while something can still ask for it.  An entry is
+        # pinned by every queued call that consumes it and by its lazy proxy while that is alive; when
+        # the last pin goes (and the data exists) the entry gives up its claim on the frame.
+        self._lock = threading.RLock()
+        self._pins: Dict[str, int] = {}
+        self._holds: Dict[str, str] = {}      # entry id -> uri it holds a store reference on
+        self._persistent: set = set()         # cache=True results stay until runtime.clear()
+        self.auto_release = True
+
+    def pin(self, entry_id: str) -> None:
+        with self._lock:
+            self._pins[entry_id] = self._pins.get(entry_id, 0) + 1
+
+    def unpin(self, entry_id: str) -> None:
+        with self._lock:
+            n = self._pins.get(entry_id, 0) - 1
+            if n > 0:
+                self._pins[entry_id] = n
+                return
+            self._pins.pop(entry_id, None)
+        self._maybe_release(entry_id)
+
+    def persist(self, entry_id: str) -> None:
+        with self._lock:
+            self._persistent.add(entry_id)
+
+    def produced(self, entry_id: str) -> None:
+        """an op wrote this entry: take a reference on its frame (or let it go if nobody waits for it)"""
+        entry = self._entries.get(entry_id)
+        if entry is None or entry._storage_uri is None:
+            return
+        with self._lock:
+            if entry_id not in self._holds:
+                self._holds[entry_id] = entry._storage_uri
+                self._store.retain(entry._storage_uri)
+        self._maybe_release(entry_id)
+
+    def _maybe_release(self, entry_id: str) -> None:
+        if not self.auto_release:
+            return
+        with self._lock:
+            if self._pins.get(entry_id, 0) > 0 or entry_id in self._persistent:
+                return
+            uri = self._holds.pop(entry_id, None)
+        if uri is not None:
+            self._store.release(uri)
 
     def create_entry(self, name: str, typ: Type) -> SnapshotEntry:
         eid = str(uuid.uuid4())
@@ -106,6 +153,10 @@ class FrameSnapshot(Snapshot):
         digest_hex = self._store.put(self._prefix, data, entry.typ, self._registry, name=entry.name)
         entry.data_hash = digest_hex
         entry.storage_uri = self._prefix + digest_hex
+        with self._lock:
+            if entry_id not in self._holds:
+                self._holds[entry_id] = entry.storage_uri
+                self._store.retain(entry.storage_uri)
 
     async def get_data(self, entry_id: str) -> Either:
         entry = self._entries.get(entry_id)

@@ -10,6 +10,7 @@ from __future__ import annotations
 import functools
 import inspect
 import uuid
+import weakref
 from dataclasses import dataclass
 from inspect import getfullargspec
 from itertools import chain, zip_longest
@@ -74,6 +75,16 @@ class LzyCall:
         # local data goes to the snapshot here, in the constructor: it may change before the
         # dependent op actually runs
         LzyEventLoop.gather(*local_data_put_tasks)
+
+        # every input stays pinned until the runtime has executed this call (HBM-backed snapshots
+        # release a payload once nothing can ask for it any more; see FrameSnapshot)
+        pin = getattr(workflow.snapshot, "pin", None)
+        if pin is not None:
+            for eid in list(self.__args_entry_ids) + list(self.__kwargs_entry_ids.values()):
+                pin(eid)
+            if self.cache:
+                for eid in self.__entry_ids:
+                    workflow.snapshot.persist(eid)
 
     @property
     def callable_name(self) -> str:
@@ -152,8 +163,14 @@ class LazyCallWrapper:
         if single_output and inspect.isclass(self.output_types[0]) and issubclass(self.output_types[0], type(None)):
             return None
 
-        proxies = (lzy_proxy(entry_id=eid, types=infer_real_types(types), wflow=active_workflow)
-                   for eid, types in zip(lzy_call.entry_ids, lzy_call.signature.func.output_types))
+        snap = active_workflow.snapshot
+        proxies = []
+        for eid, types in zip(lzy_call.entry_ids, lzy_call.signature.func.output_types):
+            p = lzy_proxy(entry_id=eid, types=infer_real_types(types), wflow=active_workflow)
+            if hasattr(snap, "pin"):  # the result's frame lives as long as this proxy can still ask for it
+                snap.pin(eid)
+                weakref.finalize(p, snap.unpin, eid)
+            proxies.append(p)
         result = tuple(materialize(p) for p in proxies) if active_workflow.eager else tuple(proxies)
         return result[0] if single_output else result
 

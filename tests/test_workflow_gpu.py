@@ -467,19 +467,39 @@ def test_diamond_graph_runs_and_failure_stops_it(lzy, workflow_name):
     assert r == 6.0 * (1 << 16)
 
 
-def test_runtime_clear_releases_every_frame(lzy, workflow_name):
+def test_frames_live_only_while_something_can_ask_for_them(lzy, workflow_name):
+    """HBM is not a disk: x and the intermediate results are released when the graph has run; the last
+    result stays while its proxy is alive; nothing is left after that."""
     @op
     def ident(t: torch.Tensor) -> torch.Tensor:
         return t
 
+    import gc
     from lzy_b200 import _native as N
+    lzy.runtime.clear()
+    gc.collect()
+    base = N.stats()["slots_live"]
     with lzy.workflow(workflow_name):
         y = ident(ident(ident(torch.ones(1 << 20, device="cuda"))))
+    assert lzy.runtime.store.resident_bytes() == 4 << 20  # only y's frame: x and two intermediates are gone
     assert float(y.sum().item()) == float(1 << 20)
-    assert lzy.runtime.store.resident_bytes() >= 4 * (4 << 20)  # x + three op outputs, intermediate ones included
-    lzy.runtime.clear()
-    assert lzy.runtime.store.resident_bytes() == 0
     del y
-    import gc
     gc.collect()
-    assert N.stats()["slots_live"] == 0
+    assert lzy.runtime.store.resident_bytes() == 0
+    assert N.stats()["slots_live"] == base
+
+
+def test_retain_all_keeps_everything_until_clear(workflow_name):
+    @op
+    def ident(t: torch.Tensor) -> torch.Tensor:
+        return t
+
+    rt = B200Runtime(retain="all")
+    lz = Lzy(runtime=rt)
+    with lz.workflow(workflow_name):
+        y = ident(ident(torch.ones(1 << 20, device="cuda")))
+    assert rt.store.resident_bytes() == 3 * (4 << 20)
+    assert float(y.sum().item()) == float(1 << 20)
+    rt.clear()
+    assert rt.store.resident_bytes() == 0
+    rt.close()
