@@ -213,8 +213,9 @@ class B200Runtime(Runtime):
                 self.stats["cached_ops"] += 1
                 continue
             todo.append(c)
+        todo_ids = {id(c) for c in todo}  # identity, never ==: comparing calls would compare (and materialise) proxies
         for c in calls:
-            if c not in todo and hasattr(snapshot, "unpin"):  # a skipped (cached) call releases its inputs too
+            if id(c) not in todo_ids and hasattr(snapshot, "unpin"):  # a skipped (cached) call releases its inputs too
                 for eid in list(c.arg_entry_ids) + list(c.kwarg_entry_ids.values()):
                     snapshot.unpin(eid)
         if not todo:

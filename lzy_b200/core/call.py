@@ -29,7 +29,7 @@ if TYPE_CHECKING:
     from .workflow import LzyWorkflow
 
 
-@dataclass
+@dataclass(eq=False)  # identity semantics: field-wise == would touch (and materialise) proxy arguments
 class LzyCall:
     workflow: "LzyWorkflow"
     signature: CallSignature
@@ -81,6 +81,8 @@ class LzyCall:
         pin = getattr(workflow.snapshot, "pin", None)
         if pin is not None:
             for eid in list(self.__args_entry_ids) + list(self.__kwargs_entry_ids.values()):
+                pin(eid)
+            for eid in self.__entry_ids:  # held until the caller has its proxies (an eager workflow runs the call first)
                 pin(eid)
             if self.cache:
                 for eid in self.__entry_ids:
@@ -160,10 +162,12 @@ class LazyCallWrapper:
 
         single_output = len(self.output_types) == 1
         # `-> None` ops return the real None (so `is None` works) but stay queued (:232-250)
+        snap = active_workflow.snapshot
         if single_output and inspect.isclass(self.output_types[0]) and issubclass(self.output_types[0], type(None)):
+            if hasattr(snap, "unpin"):
+                snap.unpin(lzy_call.entry_ids[0])
             return None
 
-        snap = active_workflow.snapshot
         proxies = []
         for eid, types in zip(lzy_call.entry_ids, lzy_call.signature.func.output_types):
             p = lzy_proxy(entry_id=eid, types=infer_real_types(types), wflow=active_workflow)
@@ -172,6 +176,9 @@ class LazyCallWrapper:
                 weakref.finalize(p, snap.unpin, eid)
             proxies.append(p)
         result = tuple(materialize(p) for p in proxies) if active_workflow.eager else tuple(proxies)
+        if hasattr(snap, "unpin"):
+            for eid in lzy_call.entry_ids:
+                snap.unpin(eid)  # the construction-time pin; the proxies carry their own
         return result[0] if single_output else result
 
 
