@@ -167,6 +167,11 @@ int lzyb_slot_pack_2d(lzyb_handle_t h, const void* src_dptr, uint64_t rows, uint
                       uint64_t src_pitch, void* stream);
 /* Host source (ndarray / bytes): staged H2D copy into the payload, then digest scan. */
 int lzyb_slot_pack_host(lzyb_handle_t h, const void* src_host, uint64_t nbytes, void* stream);
+/* Multi-part host source: a payload assembled from several host buffers (a pickle skeleton followed by
+ * its out-of-band buffers).  Parts are written back to back at 16-byte aligned offsets (the library
+ * zero-fills the ≤ 15 padding bytes after a part); `offset` must equal the bytes already written;
+ * the part with last != 0 must end exactly at the slot's nbytes and publishes the digest. */
+int lzyb_slot_pack_host_part(lzyb_handle_t h, uint64_t offset, const void* src_host, uint64_t len, int last, void* stream);
 /* = OutputSlotBackend.waitCompleted(): make the payload final.  If the payload was written in
  * place the digest is computed by a read-only scan (1 B/B); if it was packed the digest is
  * already there.  Blocks until the frame header is valid; writes the 128-bit digest. */

@@ -137,6 +137,7 @@ _SIGNATURES = {
     "lzyb_slot_pack": (C.c_int, [_H, _P, C.c_uint64, _P]),
     "lzyb_slot_pack_2d": (C.c_int, [_H, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "lzyb_slot_pack_host": (C.c_int, [_H, _P, C.c_uint64, _P]),
+    "lzyb_slot_pack_host_part": (C.c_int, [_H, C.c_uint64, _P, C.c_uint64, C.c_int, _P]),
     "lzyb_slot_commit": (C.c_int, [_H, C.POINTER(C.c_uint64 * 2), _P]),
     "lzyb_slot_read": (C.c_int64, [_H, C.c_uint64, _P, C.c_uint64]),
     "lzyb_slot_info": (C.c_int, [_H, C.POINTER(SlotInfo)]),
@@ -264,6 +265,9 @@ class SlotHandle:
 
     def pack_host(self, src_host_ptr: int, nbytes: int, stream: int = 0) -> None:
         check(lib.lzyb_slot_pack_host(self.h, src_host_ptr, nbytes, stream or None))
+
+    def pack_host_part(self, offset: int, src_host_ptr: int, nbytes: int, last: bool, stream: int = 0) -> None:
+        check(lib.lzyb_slot_pack_host_part(self.h, offset, src_host_ptr, nbytes, int(last), stream or None))
 
     def commit(self, stream: int = 0) -> Tuple[int, int]:
         d = (C.c_uint64 * 2)()

@@ -20,8 +20,11 @@ from .... import _host as H
 from .... import _native as N
 from ....devmem import current_stream_ptr
 from ....serialization.api import DeviceFrameSerializer, SerializerRegistry
-from ....serialization.builtin import FLAG_HOST_ORIGIN, FLAG_NDARRAY
+import struct
 
+from ....serialization.builtin import FLAG_HOST_ORIGIN, FLAG_NDARRAY, FLAG_OOB, CloudpickleSerializer
+
+OOB_MIN_BYTES = 64 << 10  # below this an object is one plain pickle
 _FLAG_SHIFT = 16  # header.dtype: low 16 bits = enum lzyb_dtype, high 16 bits = serializer flags
 
 
@@ -60,14 +63,60 @@ class FrameStore:
         ser = registry.find_serializer_by_type(typ) or ser
         if ser is None or isinstance(ser, DeviceFrameSerializer):
             ser = registry.find_serializer_by_data_format("pickle")
-        buf = BytesIO()
-        ser.serialize(data, buf)
-        raw = buf.getvalue()
+        if isinstance(ser, CloudpickleSerializer):
+            skeleton, bufs = ser.dumps_oob(data)
+            if bufs and sum(b.nbytes for b in bufs) >= OOB_MIN_BYTES:
+                return self._pack_composite(skeleton, bufs, slot_factory, stream)
+            raw = skeleton if not bufs else None
+        else:
+            raw = None
+        if raw is None:
+            buf = BytesIO()
+            ser.serialize(data, buf)
+            raw = buf.getvalue()
         slot = slot_factory(len(raw), None)
         slot.set_meta(N.DT_PICKLE | (FLAG_HOST_ORIGIN << _FLAG_SHIFT), (len(raw),))
         slot.pack_host(C.cast(C.c_char_p(raw), C.c_void_p).value or 0, len(raw), stream)
         slot._keepalive = raw
         return slot
+
+    @staticmethod
+    def _pack_composite(skeleton: bytes, bufs, slot_factory, stream: int):
+        """one frame = [table][skeleton][buffer 0][buffer 1]…, every part 16-byte aligned; the table is
+        (n, skeleton_len, (offset, length) × n) as little-endian u64"""
+        pad = lambda n: (n + 15) & ~15
+        table_len = pad(8 * (2 + 2 * len(bufs)))
+        off = table_len + pad(len(skeleton))
+        entries = []
+        for b in bufs:
+            entries.append((off, b.nbytes))
+            off += pad(b.nbytes)
+        total = off
+        head = struct.pack(f"<{2 + 2 * len(bufs)}Q", len(bufs), len(skeleton), *[x for e in entries for x in e])
+        head = head.ljust(table_len, b"\0") + skeleton
+        slot = slot_factory(total, None)
+        slot.set_meta(N.DT_PICKLE | ((FLAG_HOST_ORIGIN | FLAG_OOB) << _FLAG_SHIFT), (total,))
+        keep = [head]
+        slot.pack_host_part(0, C.cast(C.c_char_p(head), C.c_void_p).value or 0, len(head), False, stream)
+        for i, (b, (o, n)) in enumerate(zip(bufs, entries)):
+            arr = (C.c_char * n).from_buffer(b) if not b.readonly else (C.c_char * n).from_buffer_copy(b)
+            keep.append(arr)
+            slot.pack_host_part(o, C.addressof(arr), n, i == len(bufs) - 1, stream)
+        slot._keepalive = (keep, bufs)
+        return slot
+
+    @staticmethod
+    def _unpack_composite(slot: N.SlotHandle, nbytes: int):
+        host = bytearray(nbytes)
+        view = (C.c_char * nbytes).from_buffer(host)
+        slot.copy_to_host(C.addressof(view), nbytes)
+        del view
+        n, skel_len = struct.unpack_from("<2Q", host, 0)
+        table = struct.unpack_from(f"<{2 * n}Q", host, 16)
+        table_len = (8 * (2 + 2 * n) + 15) & ~15
+        mv = memoryview(host)
+        buffers = [mv[table[2 * i]: table[2 * i] + table[2 * i + 1]] for i in range(n)]
+        return CloudpickleSerializer.loads_oob(mv[table_len: table_len + skel_len], buffers)
 
     def put(self, prefix: str, data: Any, typ: Type, registry: SerializerRegistry, name: str = "") -> str:
         def factory(nbytes, device):
@@ -115,6 +164,8 @@ class FrameStore:
 
     def unpack_slot(self, slot: N.SlotHandle, typ: Type, registry: SerializerRegistry, private: bool) -> Any:
         info = _InfoView(slot.info())
+        if info.dtype == N.DT_PICKLE and info.flags & FLAG_OOB:
+            return self._unpack_composite(slot, info.nbytes)
         if info.dtype == N.DT_PICKLE:
             raw = C.create_string_buffer(max(1, info.nbytes))
             if info.nbytes:

@@ -632,6 +632,51 @@ int lzyb_slot_pack_host(lzyb_handle_t h, const void* src_host, uint64_t nbytes, 
     return scan_publish(*s, d, st);
 }
 
+int lzyb_slot_pack_host_part(lzyb_handle_t h, uint64_t offset, const void* src_host, uint64_t len, int last, void* stream) {
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->is_input || s->remote) return fail(LZYB_E_STATE, "slot %s is not a local output slot", s->id.c_str());
+    if (s->state != LZYB_ST_EMPTY || s->digest_pending) return fail(LZYB_E_STATE, "slot %s already holds data", s->id.c_str());
+    if (offset & 15) return fail(LZYB_E_ARG, "part offset must be a multiple of 16");
+    if (offset != s->delivered) return fail(LZYB_E_ARG, "part offset %llu != bytes written %llu", (unsigned long long)offset,
+                                            (unsigned long long)s->delivered);
+    if (len && !src_host) return fail(LZYB_E_ARG, "null source");
+    const uint64_t padded = round_up(len, 16);
+    const uint64_t end = last ? s->nbytes : offset + padded;
+    if (offset + len > s->nbytes || end > s->nbytes || (last && offset + padded < s->nbytes))
+        return fail(LZYB_E_ARG, "part [%llu, +%llu) does not fit the %llu-byte payload", (unsigned long long)offset,
+                    (unsigned long long)len, (unsigned long long)s->nbytes);
+    DeviceCtx& d = *g.devs[s->dev];
+    DeviceGuard dg(d.ordinal);
+    cudaStream_t st = pick_stream(d, stream);
+    if (len) CU(cudaMemcpyAsync(s->payload() + offset, src_host, len, cudaMemcpyHostToDevice, st));
+    if (end > offset + len) CU(cudaMemsetAsync(s->payload() + offset + len, 0, end - (offset + len), st));
+    g.st_h2d += len;
+    CopyParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = s->payload() + offset;
+    p.nbytes = end - offset;
+    p.word_base = offset >> 3;
+    p.ctl = s->ctl;
+    p.total_nbytes = s->nbytes;
+    p.fin = FIN_NONE;
+    if (last) {
+        p.fin = FIN_PUBLISH;
+        p.dst_hdr = reinterpret_cast<lzyb_frame_header_t*>(s->buf);
+        fill_template(*s, &p.hdr_template);
+        arm_mailbox(*s, p);
+    }
+    int rc = launch_stream(d, p, false, st);
+    if (rc != LZYB_OK) return rc;
+    g.st_scan++;
+    s->delivered = end;
+    s->ctl_dirty = !last;
+    if (last) s->digest_pending = true;
+    note(*s, st);
+    return LZYB_OK;
+}
+
 int lzyb_slot_commit(lzyb_handle_t h, uint64_t digest_out[2], void* stream) {
     auto s = find(h);
     if (!s) return fail(LZYB_E_ARG, "unknown slot handle");

@@ -33,7 +33,7 @@ except Exception:  # pragma: no cover
     torch = None  # type: ignore
 
 HEADER_BYTES = 128
-FLAG_COMMITTED, FLAG_HOST_ORIGIN, FLAG_NDARRAY = 1, 2, 4
+FLAG_COMMITTED, FLAG_HOST_ORIGIN, FLAG_NDARRAY, FLAG_OOB = 1, 2, 4, 8
 
 
 def _np_to_code():
@@ -63,6 +63,24 @@ class CloudpickleSerializer(Serializer):
 
     def _deserialize(self, source: BinaryIO, schema_type: Type, user_type: Optional[Type] = None) -> Any:
         return cloudpickle.load(source)
+
+    # pickle protocol 5 with out-of-band buffers: large contiguous buffers inside the object (numpy
+    # arrays of a Bunch / dict / dataclass, pandas blocks) are not copied into the pickle stream; they
+    # travel as separate parts of the same slot frame (FrameStore.pack_object)
+    @staticmethod
+    def dumps_oob(obj: Any):
+        buffers = []
+        skeleton = cloudpickle.dumps(obj, protocol=5, buffer_callback=buffers.append)
+        views = []
+        for b in buffers:
+            mv = b.raw()
+            views.append(mv)
+        return skeleton, views
+
+    @staticmethod
+    def loads_oob(skeleton, buffers) -> Any:
+        import pickle
+        return pickle.loads(skeleton, buffers=buffers)
 
     def resolve(self, schema: Schema) -> Type:
         if schema.data_format != self.DATA_FORMAT:

@@ -503,3 +503,49 @@ def test_retain_all_keeps_everything_until_clear(workflow_name):
     rt.clear()
     assert rt.store.resident_bytes() == 0
     rt.close()
+
+
+def test_bunch_travels_as_one_composite_frame(lzy, workflow_name):
+    """BASELINE config C4's payload shape: a sklearn Bunch whose arrays ride as out-of-band parts of one
+    frame (pickle protocol 5) next to the pickled skeleton."""
+    from sklearn.utils import Bunch
+
+    @op
+    def train(b: Bunch) -> np.ndarray:
+        assert isinstance(b.data, np.ndarray) and b.data.flags.writeable
+        b.data[0, 0] += 0.0  # the op owns its copy
+        return b.data.sum(axis=0) + float(b.target.sum())
+
+    rng = np.random.default_rng(0)
+    bunch = Bunch(data=rng.standard_normal((5000, 30)), target=rng.integers(0, 2, 5000),
+                  feature_names=[f"f{i}" for i in range(30)], DESCR="d" * 4096)
+    from lzy_b200 import _native as N
+    before = N.stats()["h2d_bytes"]
+    with lzy.workflow(workflow_name):
+        r = train(bunch)
+        same = train(bunch)
+    assert np.allclose(r, bunch.data.sum(axis=0) + float(bunch.target.sum())) and np.array_equal(r, same)
+    moved = N.stats()["h2d_bytes"] - before
+    assert bunch.data.nbytes + bunch.target.nbytes <= moved < 1.2 * (bunch.data.nbytes + bunch.target.nbytes) + (1 << 16)
+
+
+def test_multi_part_host_pack_digest_matches_oracle(native):
+    import ctypes as C
+    import oracle
+    parts = [b"table-and-skeleton" * 3, bytes(range(256)) * 100 + b"xyz", b"last-part-not-a-multiple-of-16!!!"]
+    pad = lambda n: (n + 15) & ~15
+    total = sum(pad(len(p)) for p in parts[:-1]) + len(parts[-1])
+    s = native.SlotHandle.create_output("parts", 0, total)
+    try:
+        off, expect = 0, bytearray()
+        for i, p in enumerate(parts):
+            last = i == len(parts) - 1
+            s.pack_host_part(off, C.cast(C.c_char_p(p), C.c_void_p).value, len(p), last)
+            expect += p if last else p.ljust(pad(len(p)), b"\0")
+            off += pad(len(p))
+        assert s.commit() == oracle.digest(bytes(expect))
+        out = np.empty(total, dtype=np.uint8)
+        s.copy_to_host(out.ctypes.data, total)
+        assert out.tobytes() == bytes(expect)
+    finally:
+        s.close()
