@@ -215,6 +215,12 @@ int64_t lzyb_input_write_host(lzyb_handle_t dst, uint64_t offset, const void* sr
  * sources that have no frame header (host/storage peers); NULL = no expectation, the digest
  * computed while the bytes landed is published */
 int lzyb_input_finish_expect(lzyb_handle_t dst, const uint64_t digest[2], void* stream);
+/* The payload of an input slot was filled in place by an external writer that this library does not
+ * drive — an `ncclBroadcast` into lzyb_slot_device_ptr(dst) when one output fans out to many
+ * consumers.  Scans the payload, checks it against the producer's digest (NULL: publish what is
+ * there) and makes the slot READY; LZYB_E_PEER on mismatch.  Blocks. */
+int lzyb_input_adopt_external(lzyb_handle_t dst, const uint64_t digest[2], uint32_t dtype, uint32_t ndim,
+                              const uint64_t* shape, void* stream);
 /* = InputSlotBackend.toOutput() (FileInputBackend.java:38-45): the delivered bytes become an
  * output slot ("<slotId>-out" re-publication, InputSlot.java:160-168) with no copy. */
 int lzyb_input_to_output(lzyb_handle_t h);

@@ -150,6 +150,7 @@ _SIGNATURES = {
     "lzyb_input_finish": (C.c_int, [_H, _H, _P]),
     "lzyb_input_write_host": (C.c_int64, [_H, C.c_uint64, _P, C.c_uint64, _P]),
     "lzyb_input_finish_expect": (C.c_int, [_H, C.POINTER(C.c_uint64 * 2), _P]),
+    "lzyb_input_adopt_external": (C.c_int, [_H, C.POINTER(C.c_uint64 * 2), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), _P]),
     "lzyb_input_to_output": (C.c_int, [_H]),
     "lzyb_input_reset": (C.c_int, [_H]),
     "lzyb_slot_export": (C.c_int, [_H, C.POINTER(IpcDesc)]),
@@ -298,6 +299,12 @@ class SlotHandle:
 
     def write_host(self, offset: int, src_host_ptr: int, length: int, stream: int = 0) -> int:
         return check(lib.lzyb_input_write_host(self.h, offset, src_host_ptr, length, stream or None))
+
+    def adopt_external(self, digest: Optional[Sequence[int]], dtype: int = 0, shape: Sequence[int] = (), stream: int = 0) -> None:
+        """the payload was filled in place by an external writer (an NCCL broadcast): scan + verify"""
+        d = None if digest is None else C.byref((C.c_uint64 * 2)(int(digest[0]), int(digest[1])))
+        arr = (C.c_uint64 * max(1, len(shape)))(*[int(x) for x in shape])
+        check(lib.lzyb_input_adopt_external(self.h, d, dtype, len(shape), arr, stream or None))
 
     def to_output(self) -> None:
         check(lib.lzyb_input_to_output(self.h))

@@ -962,6 +962,51 @@ int lzyb_input_finish_expect(lzyb_handle_t dst_h, const uint64_t digest[2], void
     return finish_common(*dst, digest, nullptr, stream);  // digest == NULL: publish what was computed
 }
 
+int lzyb_input_adopt_external(lzyb_handle_t dst_h, const uint64_t digest[2], uint32_t dtype, uint32_t ndim,
+                              const uint64_t* shape, void* stream) {
+    auto dst = find(dst_h);
+    if (!dst) return fail(LZYB_E_ARG, "unknown slot handle");
+    if (ndim > LZYB_MAX_DIMS) return fail(LZYB_E_ARG, "ndim %u > %d", ndim, LZYB_MAX_DIMS);
+    std::lock_guard<std::mutex> lk(dst->mu);
+    if (!dst->is_input) return fail(LZYB_E_STATE, "slot %s is not an input slot", dst->id.c_str());
+    if (dst->state != LZYB_ST_EMPTY || dst->delivered != 0) return fail(LZYB_E_STATE, "slot %s already holds data", dst->id.c_str());
+    DeviceCtx& d = *g.devs[dst->dev];
+    DeviceGuard dg(d.ordinal);
+    cudaStream_t st = pick_stream(d, stream);
+    dst->dtype = dtype;
+    dst->ndim = ndim;
+    memset(dst->shape, 0, sizeof(dst->shape));
+    for (uint32_t i = 0; i < ndim && shape; ++i) dst->shape[i] = shape[i];
+    CopyParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = dst->payload();
+    p.nbytes = dst->nbytes;
+    p.ctl = dst->ctl;
+    p.total_nbytes = dst->nbytes;
+    p.fin = digest ? FIN_VERIFY : FIN_PUBLISH;
+    if (digest) {
+        p.expect[0] = digest[0];
+        p.expect[1] = digest[1];
+    }
+    p.dst_hdr = reinterpret_cast<lzyb_frame_header_t*>(dst->buf);
+    fill_template(*dst, &p.hdr_template);
+    arm_mailbox(*dst, p);
+    int rc = launch_stream(d, p, false, st);
+    if (rc != LZYB_OK) return rc;
+    g.st_scan++;
+    dst->delivered = dst->nbytes;
+    dst->digest_pending = true;
+    note(*dst, st);
+    int status = harvest(*dst);
+    if (status < 0) return status;
+    if (status == 2) {
+        input_reset_locked(*dst);
+        return fail(LZYB_E_PEER, "digest mismatch on slot %s after an external fill", dst->id.c_str());
+    }
+    dst->state = LZYB_ST_READY;
+    return LZYB_OK;
+}
+
 int64_t lzyb_input_write_host(lzyb_handle_t dst_h, uint64_t offset, const void* src_host, uint64_t len, void* stream) {
     auto dst = find(dst_h);
     if (!dst) return fail(LZYB_E_ARG, "unknown slot handle");
