@@ -363,7 +363,7 @@ class B200Runtime(Runtime):
         except BaseException:
             info = sys.exc_info()
             try:
-                self.store.put_inline(exc_uri, cloudpickle.loads(cloudpickle.dumps(info)))
+                self.store.put_inline(exc_uri, info)  # pickled (traceback included) and framed into the host ring
             except Exception:
                 self.store.put_inline(exc_uri, (info[0], info[1], None))
             raise _OpFailed(t, info)

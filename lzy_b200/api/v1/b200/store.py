@@ -25,6 +25,7 @@ import struct
 from ....serialization.builtin import FLAG_HOST_ORIGIN, FLAG_NDARRAY, FLAG_OOB, CloudpickleSerializer
 
 OOB_MIN_BYTES = 64 << 10  # below this an object is one plain pickle
+_RING = object()  # marker: the value lives in the pinned host ring
 _FLAG_SHIFT = 16  # header.dtype: low 16 bits = enum lzyb_dtype, high 16 bits = serializer flags
 
 
@@ -45,6 +46,7 @@ class FrameStore:
         self.default_gpu = default_gpu
         self._frames: Dict[str, N.SlotHandle] = {}
         self._inline: Dict[str, Any] = {}  # tiny control values (exception tuples) that never need a frame
+        self._ring: Dict[str, int] = {}    # uri -> offset of its frame in the pinned host ring
         self._lock = threading.RLock()
         self._refs: Dict[str, int] = {}  # how many snapshot entries still need the frame at this URI
         self.bytes_put = 0
@@ -140,8 +142,21 @@ class FrameStore:
         return hexd
 
     def put_inline(self, uri: str, value: Any) -> None:
+        """Small host-side control objects (an op's exception tuple) never need HBM: they are pickled,
+        framed into the pinned host ring by the CUDA frame kernel (header + digest written into the
+        ring, `lzyb_frame_host_object`) and verified by a scan when read back."""
+        if value is None:
+            with self._lock:
+                self._inline[uri] = None
+            return
+        import cloudpickle
+        off = N.frame_host_object(cloudpickle.dumps(value))
         with self._lock:
-            self._inline[uri] = value
+            old = self._ring.pop(uri, None)
+            self._ring[uri] = off
+            self._inline[uri] = _RING
+        if old is not None:
+            N.ring_release(old)
 
     # ---- reading ------------------------------------------------------------------------------
     def _slot(self, uri: str) -> Optional[N.SlotHandle]:
@@ -182,9 +197,16 @@ class FrameStore:
         return value
 
     def get(self, uri: str, typ: Type, registry: SerializerRegistry) -> Any:
+        v = None
         with self._lock:
             if uri in self._inline:
-                return self._inline[uri]
+                v = self._inline[uri]
+                if v is not _RING:
+                    return v
+                off = self._ring[uri]
+        if v is _RING:
+            import cloudpickle
+            return cloudpickle.loads(N.ring_read(off))
         slot = self._slot(uri)
         if slot is None:
             raise ValueError(f"Cannot find blob in storage by uri={uri}")
@@ -222,7 +244,12 @@ class FrameStore:
     def drop(self, uri: str) -> None:
         with self._lock:
             self._inline.pop(uri, None)
+            off = self._ring.pop(uri, None)
             s = self._frames.pop(uri, None)
+        if off is not None:
+            N.ring_release(off)
+        with self._lock:
+            pass
         H.frame_store_drop(uri)
         if s is not None:
             s.close()

@@ -552,3 +552,29 @@ def test_multi_part_host_pack_digest_matches_oracle(native):
         assert out.tobytes() == bytes(expect)
     finally:
         s.close()
+
+
+def test_exception_slot_holds_exc_info_framed_in_the_host_ring(lzy, workflow_name):
+    """startup.process_execution writes sys.exc_info() to the exception slot (startup.py:137-170);
+    test_startup.py:52-83 checks type, args and the extracted traceback of what is read back."""
+    from lzy_b200 import _native as N
+    from lzy_b200.proxy_result import Result
+    from lzy_b200.utils.event_loop import LzyEventLoop
+
+    @op
+    def failing() -> None:
+        raise ValueError("test")
+
+    frames_before = N.stats()["frame_launches"]
+    captured = {}
+    with pytest.raises(ValueError):
+        with lzy.workflow(workflow_name) as wf:
+            failing()
+            captured["call"] = wf.call_queue[0]
+            captured["snapshot"] = wf.snapshot
+    res = LzyEventLoop.run_async(captured["snapshot"].get_data(captured["call"].exception_id))
+    assert isinstance(res, Result)
+    typ, value, tb = res.value
+    assert typ is ValueError and value.args == ("test",)
+    assert traceback.extract_tb(tb)[-1].name == "failing"
+    assert N.stats()["frame_launches"] >= frames_before + 2  # framed by the CUDA kernel, verified on read
