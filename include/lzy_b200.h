@@ -259,7 +259,7 @@ int lzyb_stats_reset(void);
  * 2 = TMA bulk (cp.async.bulk + mbarrier ring) */
 int lzyb_set_copy_engine(int engine);
 int lzyb_set_grid(int ctas_per_sm);
-/* shape of the TMA shared-memory ring, for measurement: 0 = 6×16 KiB ×2 CTAs/SM (default), 1 = 3×32 KiB ×2,
+/* shape of the TMA shared-memory ring, for measurement: 0 = 6×16 KiB ×2 CTAs/SM, 1 = 3×32 KiB ×2 (default),
  * 2 = 6×32 KiB ×1, 3 = 12×16 KiB ×1, 4 = 8×8 KiB ×3, 5 = 4×16 KiB ×3 */
 int lzyb_set_tma_config(int index);
 

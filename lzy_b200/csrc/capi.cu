@@ -159,7 +159,7 @@ struct Global {
     std::map<std::pair<int, std::string>, void*> ipc_cache;
     // policy
     std::atomic<int> engine{0};
-    std::atomic<int> tma_cfg{0};
+    std::atomic<int> tma_cfg{1};  // 3 × 32 KiB, 2 CTAs/SM: best of the sweep in profiles/r01_microbench_local.jsonl
     std::atomic<int> ctas_per_sm{4};
     std::atomic<int> global_fault{LZYB_FAULT_NONE};
     // stats

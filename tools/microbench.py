@@ -77,7 +77,7 @@ def main():
             print(json.dumps(rec), flush=True)
         src.close()
         N.set_copy_engine(N.ENGINE_AUTO)
-        N.set_tma_config(0)
+        N.set_tma_config(1)
         N.set_grid(4)
 
 
