@@ -262,6 +262,8 @@ int lzyb_set_grid(int ctas_per_sm);
 /* shape of the TMA shared-memory ring, for measurement: 0 = 6×16 KiB ×2 CTAs/SM, 1 = 3×32 KiB ×2 (default),
  * 2 = 6×32 KiB ×1, 3 = 12×16 KiB ×1, 4 = 8×8 KiB ×3, 5 = 4×16 KiB ×3 */
 int lzyb_set_tma_config(int index);
+/* measurement only.  bit 0: run the TMA ring without the digest arithmetic (digests are then wrong) */
+int lzyb_set_debug_flags(int flags);
 
 /* fault injection at the backend seam (the reference's InMemBackend failOpen/failRead/failAfter,
  * lzy/slots/src/test/java/ai/lzy/slots/SlotsTest.java:866-943) */

@@ -168,6 +168,7 @@ _SIGNATURES = {
     "lzyb_set_copy_engine": (C.c_int, [C.c_int]),
     "lzyb_set_grid": (C.c_int, [C.c_int]),
     "lzyb_set_tma_config": (C.c_int, [C.c_int]),
+    "lzyb_set_debug_flags": (C.c_int, [C.c_int]),
     "lzyb_fault_inject": (C.c_int, [_H, C.c_int, C.c_uint64]),
 }
 for _name, (_res, _args) in _SIGNATURES.items():

@@ -66,7 +66,9 @@ constexpr int TMA_CONSUMER_WARPS = 8;
 constexpr int TMA_THREADS = (TMA_CONSUMER_WARPS + 2) * 32;  // + producer warp + storer warp
 
 // Dynamic shared memory: STAGES × STAGE_BYTES of payload staging, then the barriers.
-template <int STAGES, int STAGE_BYTES, bool STORE>
+// FOLD = false is a measurement-only variant (lzyb_set_debug_flags bit 0): the same ring without the
+// digest arithmetic, i.e. the ceiling of the copy structure itself.
+template <int STAGES, int STAGE_BYTES, bool STORE, bool FOLD = true>
 __global__ void __launch_bounds__(TMA_THREADS)
 tma_stream_digest_kernel(const __grid_constant__ CopyParams a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -139,13 +141,15 @@ tma_stream_digest_kernel(const __grid_constant__ CopyParams a) {
             const uint4* sv = reinterpret_cast<const uint4*>(smem + static_cast<size_t>(s) * STAGE_BYTES);
             const unsigned long long vbase = t * VEC_PER_STAGE + ctid;  // vector index within the chunk
             unsigned long long key = (a.word_base + 2ull * vbase + 1ull) * LZYB_K_POS;
-            uint4 v[ITERS];
+            if constexpr (FOLD) {
+                uint4 v[ITERS];
 #pragma unroll
-            for (int j = 0; j < ITERS; ++j) v[j] = sv[ctid + j * CTHREADS];
+                for (int j = 0; j < ITERS; ++j) v[j] = sv[ctid + j * CTHREADS];
 #pragma unroll
-            for (int j = 0; j < ITERS; ++j) {
-                fold16(v[j], key, sum, xr);
-                key += 2ull * CTHREADS * LZYB_K_POS;
+                for (int j = 0; j < ITERS; ++j) {
+                    fold16(v[j], key, sum, xr);
+                    key += 2ull * CTHREADS * LZYB_K_POS;
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
