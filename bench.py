@@ -319,8 +319,10 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    kernel_name = "stream_digest_kernel<16,8,true> (LDG.128/STG.128)" if args.engine == "ldg" else \
-        "tma_stream_digest_kernel<3,32768,true> (TMA bulk ring)"
+    if args.engine == "tma" or (args.engine == "auto" and multi):
+        kernel_name = "tma_stream_digest_kernel<3,32768,true> (TMA bulk ring)"
+    else:
+        kernel_name = "stream_digest_kernel<16,8,true> (LDG.128/STG.128, 2 tiles per CTA)"
     all_ms = [t for v in per_kind.values() for t in v]
     avg_ms = sum(all_ms) / len(all_ms)
     if not multi:

@@ -258,6 +258,8 @@ int lzyb_stats_reset(void);
 /* kernel variant for large contiguous transfers: 0 = auto, 1 = LDG/STG 16-B vectors,
  * 2 = TMA bulk (cp.async.bulk + mbarrier ring) */
 int lzyb_set_copy_engine(int engine);
+/* LDG/STG grid shape: n > 0 = persistent, n CTAs per SM; 0 = one 32 KiB tile per CTA; -T = T tiles per CTA;
+ * -1000 = auto (default) */
 int lzyb_set_grid(int ctas_per_sm);
 /* shape of the TMA shared-memory ring, for measurement: 0 = 6×16 KiB ×2 CTAs/SM, 1 = 3×32 KiB ×2 (default),
  * 2 = 6×32 KiB ×1, 3 = 12×16 KiB ×1, 4 = 8×8 KiB ×3, 5 = 4×16 KiB ×3 */

@@ -37,6 +37,7 @@ static_assert(sizeof(lzyb_frame_header_t) == 128, "frame header must be 128 byte
 static_assert(sizeof(lzyb_ipc_desc_t) == 256, "ipc descriptor must be 256 bytes");
 constexpr int CTL_SLAB = 8192;        // slots that can be live per device
 constexpr int MBOX_SLAB = 65536;      // mailboxes (pinned, all devices)
+constexpr int GRID_AUTO = -1000;      // lzyb_set_grid: let launch_stream pick the grid shape
 // TMA ring shapes that can be selected at run time (lzyb_set_tma_config): {stages, stage bytes, CTAs per SM}
 struct TmaCfg {
     int stages, stage_bytes, ctas_per_sm;
@@ -173,7 +174,7 @@ struct Global {
     // policy
     std::atomic<int> engine{0};
     std::atomic<int> tma_cfg{1};  // 3 × 32 KiB, 2 CTAs/SM: best of the sweep in profiles/r01_microbench_local.jsonl
-    std::atomic<int> ctas_per_sm{4};
+    std::atomic<int> ctas_per_sm{GRID_AUTO};
     std::atomic<int> global_fault{LZYB_FAULT_NONE};
     // stats
     std::atomic<uint64_t> st_launch{0}, st_pack{0}, st_pull{0}, st_scan{0}, st_frame{0}, st_bpack{0},
@@ -272,12 +273,16 @@ void launch_flat(const CopyParams& p, bool store, int grid, cudaStream_t st) {
 // One launch of the streaming family.  Chooses the engine (LDG/STG vectors or TMA bulk) and a
 // grid that is a multiple of the SM count for large chunks (persistent-style walk) and shrinks
 // to the work for small ones.
-int launch_stream(DeviceCtx& d, const CopyParams& p, bool store, cudaStream_t st) {
+int launch_stream(DeviceCtx& d, const CopyParams& p, bool store, cudaStream_t st, bool peer = false) {
     const int align = src_alignment(p.src, 0);
     const uint64_t nvec = p.nbytes >> 4;
     int engine = g.engine.load();
     const bool tma_ok = align == 16 && p.nbytes >= (1ull << 20) && (!store || (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0);
-    if (engine == 0) engine = tma_ok ? 2 : 1;  // auto: TMA bulk when eligible (measured 8 % faster, profiles/r01_summary.md)
+    // auto (measured, profiles/r01_summary.md §"engine policy"): a source on another GPU is NVLink-bound and the
+    // TMA ring keeps the most bytes in flight with the fewest instructions (670 vs 634 GB/s per direction when
+    // both directions are busy); a same-GPU copy is HBM-bound and an oversubscribed LDG/STG grid wins
+    // (6.47 TB/s vs 5.97 TB/s for the persistent ring).
+    if (engine == 0) engine = (peer && tma_ok) ? 2 : 1;
     if (engine == 2 && !tma_ok) engine = 1;
     if (engine == 2) {
         const int ci = g.tma_cfg.load();
@@ -296,8 +301,20 @@ int launch_stream(DeviceCtx& d, const CopyParams& p, bool store, cudaStream_t st
     } else {
         const uint64_t tile = 256ull * 8;
         uint64_t want = (nvec + tile - 1) / tile;
-        int grid = d.sm_count * g.ctas_per_sm.load();
-        if ((uint64_t)grid > want) grid = (int)(want ? want : 1);
+        int cps = g.ctas_per_sm.load();
+        if (cps == GRID_AUTO) {
+            if (!store) cps = -8;                              // read-only scan: 8 tiles per CTA
+            else if (p.nbytes >= (128ull << 20)) cps = -2;     // large copy: 2 tiles per CTA, oversubscribed
+            else cps = 4;                                      // small copy: persistent, launch-latency bound anyway
+        }
+        // cps == 0: one tile per CTA (oversubscribed grid; the block scheduler staggers the CTAs, which keeps
+        // DRAM reads and writes interleaved instead of phase-locked: profiles/r01_copy_variants.jsonl)
+        uint64_t cap = cps > 0 ? (uint64_t)d.sm_count * cps : (1ull << 30);
+        if (cps <= 0) {  // -T: T tiles per CTA (0 and -1: one)
+            const uint64_t t = cps < -1 ? (uint64_t)(-cps) : 1;
+            want = (want + t - 1) / t;
+        }
+        int grid = (int)(want < cap ? (want ? want : 1) : cap);
         switch (align) {
             case 16: launch_flat<16>(p, store, grid, st); break;
             case 8: launch_flat<8>(p, store, grid, st); break;
@@ -579,7 +596,8 @@ static int pack_common(lzyb_handle_t h, const void* src, uint64_t rows, uint64_t
         const int align = src_alignment(src, pitch);
         const uint64_t tile = 256ull * 4;
         uint64_t items = rows * ((row_bytes / 16 + tile - 1) / tile);
-        int grid = d.sm_count * g.ctas_per_sm.load();
+        int gcps = g.ctas_per_sm.load();
+        int grid = d.sm_count * (gcps > 0 ? gcps : 8);
         if ((uint64_t)grid > items) grid = (int)(items ? items : 1);
         switch (align) {
             case 16: gather2d_digest_kernel<16, 4><<<grid, 256, 0, st>>>(p); break;
@@ -882,7 +900,8 @@ int64_t lzyb_transfer_chunk(lzyb_handle_t dst_h, lzyb_handle_t src_h, uint64_t o
     }
     // the producer's payload must be final on this stream's timeline
     if (src->last_ev && src->last_stream != st) cudaStreamWaitEvent(st, src->last_ev, 0);
-    int rc = launch_stream(d, p, true, st);
+    const bool peer = src->remote || src->dev != dst->dev;
+    int rc = launch_stream(d, p, true, st, peer);
     if (rc != LZYB_OK) return rc;
     g.st_pull++;
     if (src->dev == dst->dev && !src->remote)
@@ -1217,7 +1236,7 @@ int lzyb_broadcast(lzyb_handle_t src_h, const lzyb_handle_t* dsts, int n, uint64
                     fill_template(dd, &p.hdr_template);
                     arm_mailbox(dd, p);
                 }
-                int lr = launch_stream(d, p, true, d.stream);
+                int lr = launch_stream(d, p, true, d.stream, up.dev != dd.dev);
                 if (lr != LZYB_OK) {
                     rc = lr;
                     break;
@@ -1509,7 +1528,11 @@ int lzyb_set_debug_flags(int flags) {
 }
 
 int lzyb_set_grid(int ctas_per_sm) {
-    if (ctas_per_sm < 1 || ctas_per_sm > 16) return fail(LZYB_E_ARG, "ctas_per_sm must be in [1, 16]");
+    if (ctas_per_sm == GRID_AUTO) {
+        g.ctas_per_sm = GRID_AUTO;
+        return LZYB_OK;
+    }
+    if (ctas_per_sm < -64 || ctas_per_sm > 16) return fail(LZYB_E_ARG, "ctas_per_sm must be in [-64, 16] (0 = one tile per CTA, -T = T tiles per CTA) or -1000 (auto)");
     g.ctas_per_sm = ctas_per_sm;
     return LZYB_OK;
 }

@@ -50,6 +50,35 @@ def main():
                 s.close()
             out[f"tma_cfg{cfg}_{tag}"] = 2 * n / timeit(pack, stream) / 1e6
     N.lib.lzyb_set_debug_flags(0)
+    N.set_copy_engine(N.ENGINE_LDG)
+    for cps in (4, 0, -2, -4, -8):
+        N.set_grid(cps)
+
+        def pack_l():
+            s = N.SlotHandle.create_output("c/o", 0, n)
+            s.pack(a.data_ptr(), n, sp)
+            s.commit(sp)
+            s.close()
+        out[f"ldg_cps{cps}_digest_copy"] = 2 * n / timeit(pack_l, stream) / 1e6
+        out[f"ldg_cps{cps}_scan"] = n / timeit(lambda: N.digest_device(0, a.data_ptr(), n, sp), stream) / 1e6
+    for mib in (64, 256):
+        m = mib << 20
+        for cps in (4, 0, -2):
+            N.set_grid(cps)
+
+            def pack_m():
+                s = N.SlotHandle.create_output("c/m", 0, m)
+                s.pack(a.data_ptr(), m, sp)
+                s.commit(sp)
+                s.close()
+            out[f"ldg_cps{cps}_copy_{mib}MiB"] = 2 * m / timeit(pack_m, stream) / 1e6
+        N.set_copy_engine(N.ENGINE_TMA)
+        out[f"tma_copy_{mib}MiB"] = 2 * m / timeit(pack_m, stream) / 1e6
+        N.set_copy_engine(N.ENGINE_LDG)
+    N.set_grid(-1000)
+    N.set_copy_engine(N.ENGINE_AUTO)
+    out["auto_scan"] = n / timeit(lambda: N.digest_device(0, a.data_ptr(), n, sp), stream) / 1e6
+    N.set_copy_engine(N.ENGINE_TMA)
     out["scan_only_read"] = n / timeit(lambda: N.digest_device(0, a.data_ptr(), n, sp), stream) / 1e6
     N.set_copy_engine(N.ENGINE_LDG)
     out["scan_only_read_ldg"] = n / timeit(lambda: N.digest_device(0, a.data_ptr(), n, sp), stream) / 1e6

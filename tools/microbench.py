@@ -78,7 +78,7 @@ def main():
         src.close()
         N.set_copy_engine(N.ENGINE_AUTO)
         N.set_tma_config(1)
-        N.set_grid(4)
+        N.set_grid(-1000)
 
 
 if __name__ == "__main__":
