@@ -86,6 +86,7 @@ class B200Runtime(Runtime):
         self._pool: Optional[ThreadPoolExecutor] = None
         self._rr = 0
         self.stats = {"ops": 0, "graphs": 0, "cached_ops": 0}
+        self.trace: Optional[list] = [] if os.environ.get("LZYB_TRACE") else None  # (task, phase, ms) records
         tbpickle.install()
 
     # ---- bring-up ------------------------------------------------------------------------------------
@@ -311,8 +312,14 @@ class B200Runtime(Runtime):
         assert wf is not None and self.store is not None
         snapshot, registry = wf.snapshot, wf.owner.serializer_registry
         exc_uri = snapshot.get(call.exception_id).storage_uri
+        import time as _time
+        tr = self.trace
+        _t0 = _time.perf_counter()
         try:
             ctx.before_execution(-1)  # every input fully delivered and verified
+            if tr is not None:
+                tr.append((t, "before_execution", 1e3 * (_time.perf_counter() - _t0)))
+                _t0 = _time.perf_counter()
             values: Dict[str, Any] = {}
 
             def load(eid: str) -> Any:
@@ -337,6 +344,9 @@ class B200Runtime(Runtime):
             finally:
                 op_scope.leave()
 
+            if tr is not None:
+                tr.append((t, "load+op", 1e3 * (_time.perf_counter() - _t0)))
+                _t0 = _time.perf_counter()
             outs = call.entry_ids
             results = [res] if len(outs) == 1 else list(res)
             with torch.cuda.device(gpu), torch.cuda.stream(stream):
@@ -357,7 +367,12 @@ class B200Runtime(Runtime):
                     slot = self.store.pack_object(data, entry.typ, registry, factory, sp)
                     ctx.output_done(name)
                     values[f"out:{eid}"] = slot  # keep the packed source alive until the commit
+            if tr is not None:
+                tr.append((t, "pack", 1e3 * (_time.perf_counter() - _t0)))
+                _t0 = _time.perf_counter()
             ctx.after_execution(-1)  # outputs bound; "uploaded" = referenced by the HBM frame store
+            if tr is not None:
+                tr.append((t, "after_execution", 1e3 * (_time.perf_counter() - _t0)))
             self.store.put_inline(exc_uri, None)
             self.stats["ops"] += 1
         except BaseException:

@@ -74,7 +74,8 @@ class LzyCall:
 
         # local data goes to the snapshot here, in the constructor: it may change before the
         # dependent op actually runs
-        LzyEventLoop.gather(*local_data_put_tasks)
+        if local_data_put_tasks:  # (a call whose arguments are all proxies does not need a trip to the event loop)
+            LzyEventLoop.gather(*local_data_put_tasks)
 
         # every input stays pinned until the runtime has executed this call (HBM-backed snapshots
         # release a payload once nothing can ask for it any more; see FrameSnapshot)
@@ -185,15 +186,13 @@ class LazyCallWrapper:
 def infer_and_validate_call_signature(f: Callable, *args, output_type: Sequence[type], snapshot: Snapshot,
                                       serializer_registry: SerializerRegistry, **kwargs) -> CallSignature:
     types_mapping = {}
-    argspec = getfullargspec(f)
-    annotations = inspect.get_annotations(f, eval_str=True)
+    argspec, annotations, defaults = _function_facts(f)
 
     if argspec.varkw is None:
         for kwarg in kwargs:
             if kwarg not in annotations:
                 raise KeyError(f"Unexpected key argument {kwarg}")
 
-    defaults = get_default_args(f)
     for spec_name, real_arg in zip_longest(argspec.args, range(len(args))):
         if spec_name is not None and real_arg is None and spec_name not in kwargs and spec_name not in defaults:
             raise KeyError(f"Argument {spec_name} is required but not provided")
@@ -226,6 +225,24 @@ def infer_and_validate_call_signature(f: Callable, *args, output_type: Sequence[
     arg_names = tuple(argspec.args[: len(args)] + names_for_varargs)
     return CallSignature(FuncSignature(f, types_mapping, output_type, arg_names, tuple(kwargs.keys())),
                          tuple(actual_args), actual_kwargs)
+
+
+_FACTS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _function_facts(f: Callable):
+    """argspec, evaluated annotations and defaults of an op body, computed once per function"""
+    try:
+        facts = _FACTS.get(f)
+    except TypeError:
+        facts = None
+    if facts is None:
+        facts = (getfullargspec(f), inspect.get_annotations(f, eval_str=True), get_default_args(f))
+        try:
+            _FACTS[f] = facts
+        except TypeError:
+            pass
+    return facts
 
 
 def _infer_type(snapshot: Snapshot, arg_name: str, arg: Any, type_annotations: Optional[Dict[str, Any]] = None):

@@ -98,19 +98,38 @@ def _forwarder(name: str):
     return method
 
 
+_FORWARDERS: Dict[str, Any] = {}
+_NS_CACHE: Dict[tuple, Dict[str, Any]] = {}
+
+
+def _namespace_for(proto_types: tuple) -> Dict[str, Any]:
+    """special-method forwarders for a tuple of prototype types (built once per tuple: creating a proxy
+    is on the @op call path)"""
+    ns = _NS_CACHE.get(proto_types)
+    if ns is None:
+        names = {"__bool__", "__eq__", "__ne__", "__hash__", "__str__", "__repr__"}
+        for typ in proto_types:
+            for name in dir(typ):
+                if name.startswith("__") and name.endswith("__") and name not in _SKIP:
+                    names.add(name)
+        ns = {}
+        for name in names:
+            fwd = _PROTOCOLS.get(name)
+            if fwd is None:
+                fwd = _FORWARDERS.get(name)
+                if fwd is None:
+                    fwd = _FORWARDERS[name] = _forwarder(name)
+            ns[name] = fwd
+        _NS_CACHE[proto_types] = ns
+    return ns
+
+
 def proxy(constructor: Callable[[], Any], proto_types: Sequence[Type], cls_attrs: Optional[Dict[str, Any]] = None,
           obj_attrs: Optional[Dict[str, Any]] = None) -> Any:
     cls_attrs = dict(cls_attrs or {})
     obj_attrs = dict(obj_attrs or {})
     own = set(cls_attrs) | set(obj_attrs)
-    ns: Dict[str, Any] = {}
-    special = {"__bool__", "__eq__", "__ne__", "__hash__", "__str__", "__repr__"}
-    for typ in proto_types:
-        for name in dir(typ):
-            if name.startswith("__") and name.endswith("__") and name not in _SKIP:
-                special.add(name)
-    for name in special:
-        ns[name] = _PROTOCOLS.get(name) or _forwarder(name)
+    ns: Dict[str, Any] = dict(_namespace_for(tuple(proto_types)))  # forwarders are shared, the dict is per class
 
     def __getattribute__(self, item):
         cls = type(self)
