@@ -59,10 +59,26 @@ class B200RuntimeConfig:
     prefetch: bool = True
     max_parallel_ops: int = 0                    # 0 = 2 × GPUs
     republish_inputs: bool = False               # "<slot>-out" seeding (InputSlot.java:160-168); ops own their inputs when off
+    fanout_threshold: int = 3                    # an entry consumed on ≥ this many *other* GPUs is delivered by one chunk-pipelined
+                                                 # pull chain (lzyb_broadcast) instead of one unicast per consumer; 0 = never
+    fanout_chunk_bytes: int = 64 << 20
     retain: str = "auto"                         # "auto": a frame is freed once no proxy / queued call can ask for it; "all": keep until clear()
     chunk_bytes: int = 0                         # 0 = one launch per transfer; the reference streams 2 MiB chunks
     copy_engine: str = "auto"                    # "auto" | "ldg" | "tma"
     user_id: str = field(default_factory=lambda: os.environ.get("LZY_USER", "local-user"))
+
+
+class _Fanout:
+    """one output consumed on several other GPUs: delivered once per GPU by a pull chain, then every
+    consumer takes a private same-GPU copy (the reference opens one Read stream per consumer,
+    channel-manager/.../services/SlotsService.java:457-466)"""
+
+    def __init__(self, eid: str, uri: str, src_gpu: Optional[int], gpus: List[int]):
+        from concurrent.futures import Future
+        self.eid, self.uri, self.src_gpu, self.gpus = eid, uri, src_gpu, gpus
+        self.future: "Future[Dict[int, N.SlotHandle]]" = Future()
+        self.owned: List[N.SlotHandle] = []
+        self.started = False
 
 
 class _OpFailed(Exception):
@@ -252,11 +268,27 @@ class B200Runtime(Runtime):
         placement = self._place(calls, producers, snapshot)
         graph = H.GraphDispatcher(len(calls), edges, allow_cycles=False)
         ctxs: List[H.ExecutionContext] = []
+
+        # fan-out plan: which entries are consumed on many other GPUs
+        fanout: Dict[str, _Fanout] = {}
+        if self.config.fanout_threshold and len(self.gpus) > self.config.fanout_threshold:
+            where: Dict[str, set] = {}
+            for i, ins in enumerate(inputs_of):
+                for eid in ins:
+                    where.setdefault(eid, set()).add(placement[i])
+            for eid, gset in where.items():
+                uri = snapshot.get(eid).storage_uri
+                src_gpu = placement[producers[eid]] if eid in producers else self.store.gpu_of(uri)
+                remote = sorted(g for g in gset if g != src_gpu)
+                if len(remote) >= self.config.fanout_threshold:
+                    fanout[eid] = _Fanout(eid, uri, src_gpu, remote)
         try:
             # BuildTasks: slot → channel assignments; every input binds right away (prefetch)
             for i, c in enumerate(calls):
                 ctx = self.workers[placement[i]].context(exec_id, c.id)
                 for eid in inputs_of[i]:
+                    if eid in fanout:
+                        continue  # delivered by the fan-out chain, not by a unicast transfer
                     ctx.add_slot(f"/{c.id}/{eid}", channel_of[eid], H.DIR_INPUT)
                 for eid in c.entry_ids:
                     ctx.add_slot(f"/{c.id}/{eid}", channel_of[eid], H.DIR_OUTPUT)
@@ -265,11 +297,15 @@ class B200Runtime(Runtime):
                 for ctx in ctxs:
                     ctx.prefetch()
 
+            for f in fanout.values():  # data that exists already can start travelling now
+                if f.eid not in producers:
+                    f.started = True
+                    self._pool.submit(self._do_fanout, f)
             running: Dict[Any, int] = {}
             failure: Optional[_OpFailed] = None
             while True:
                 for t in graph.next():
-                    running[self._pool.submit(self._run_task, t, calls[t], ctxs[t], placement[t], inputs_of[t])] = t
+                    running[self._pool.submit(self._run_task, t, calls[t], ctxs[t], placement[t], inputs_of[t], fanout)] = t
                 if not running:
                     break
                 done, _ = wait(list(running), return_when=FIRST_COMPLETED)
@@ -278,6 +314,11 @@ class B200Runtime(Runtime):
                     err = fut.exception()
                     if err is None:
                         graph.task_done(t, True)
+                        for eid in calls[t].entry_ids:  # its outputs are bound: start their fan-out
+                            f = fanout.get(eid)
+                            if f is not None and not f.started:
+                                f.started = True
+                                self._pool.submit(self._do_fanout, f)
                     else:
                         graph.task_done(t, False, repr(err))
                         if failure is None:
@@ -294,6 +335,11 @@ class B200Runtime(Runtime):
             if graph.status != H.G_COMPLETED:
                 raise LzyExecutionException("graph did not complete")
         finally:
+            for f in fanout.values():
+                if not f.future.done():
+                    f.future.set_exception(LzyExecutionException("graph stopped before the fan-out ran"))
+                for sl in f.owned:
+                    sl.close()
             for ctx in ctxs:
                 ctx.close()
             graph.close()
@@ -305,8 +351,25 @@ class B200Runtime(Runtime):
                     for eid in list(c.arg_entry_ids) + list(c.kwarg_entry_ids.values()):
                         snapshot.unpin(eid)
 
+    def _do_fanout(self, f: _Fanout) -> None:
+        try:
+            src = self.store._slot(f.uri)
+            if src is None:
+                raise ValueError(f"Cannot find blob in storage by uri={f.uri}")
+            dsts = [N.SlotHandle.open_input(f"fanout/{f.eid}/gpu{g}", g, src.nbytes) for g in f.gpus]
+            f.owned.extend(dsts)
+            N.broadcast(src, dsts, self.config.fanout_chunk_bytes)
+            per_gpu = {g: d for g, d in zip(f.gpus, dsts)}
+            per_gpu[src.gpu] = src
+            self.stats["fanouts"] = self.stats.get("fanouts", 0) + 1
+            f.future.set_result(per_gpu)
+        except BaseException as e:  # the consumers re-raise it
+            if not f.future.done():
+                f.future.set_exception(e)
+
     # ---- one op (WorkerApiImpl.executeOp + startup.process_execution) -------------------------------------
-    def _run_task(self, t: int, call: "LzyCall", ctx: H.ExecutionContext, gpu: int, input_eids: List[str]) -> None:
+    def _run_task(self, t: int, call: "LzyCall", ctx: H.ExecutionContext, gpu: int, input_eids: List[str],
+                  fanout: Optional[Dict[str, _Fanout]] = None) -> None:
         import torch
         wf = self._workflow
         assert wf is not None and self.store is not None
@@ -324,7 +387,15 @@ class B200Runtime(Runtime):
 
             def load(eid: str) -> Any:
                 if eid not in values:
-                    slot = N.SlotHandle.adopt(ctx.input_handle(f"/{call.id}/{eid}"), owned=True)
+                    if fanout and eid in fanout:
+                        # the chain put one copy on this GPU; the op gets a private same-GPU copy of it
+                        base = fanout[eid].future.result()[gpu]
+                        slot = N.SlotHandle.open_input(f"/{call.id}/{eid}", gpu, base.nbytes)
+                        if base.nbytes:
+                            slot.transfer_chunk(base, 0, base.nbytes)
+                        slot.finish(base)
+                    else:
+                        slot = N.SlotHandle.adopt(ctx.input_handle(f"/{call.id}/{eid}"), owned=True)
                     values[eid] = self.store.unpack_slot(slot, snapshot.get(eid).typ, registry, private=True)
                 return values[eid]
 

@@ -285,3 +285,15 @@ def test_serializer_registry_rules():
     reg.unregister_serializer(PointSerializer())
     other.unregister_serializer(PointSerializer())
     assert reg.imports() == []
+
+
+def test_install_as_lzy_aliases_the_package():
+    """unmodified user code imports `lzy.api.v1` (pylzy/readme.md quick start)"""
+    import subprocess
+    import sys
+    code = ("import lzy_b200; lzy_b200.install_as_lzy();"
+            "from lzy.api.v1 import Lzy, op;"
+            "from lzy.types import File;"
+            "import lzy_b200.api.v1 as v1; assert Lzy is v1.Lzy and op is v1.op; print('ok')")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr

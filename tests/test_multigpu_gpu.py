@@ -157,3 +157,28 @@ def test_locality_placement_follows_the_data():
         assert r == 1 and where == [1]
     finally:
         rt.close()
+
+
+@pytest.mark.skipif(NGPU < 4, reason="needs at least 4 GPUs (a producer and 3 consumers elsewhere)")
+def test_fanout_to_many_gpus_uses_the_pull_chain():
+    """C3 through the @op API: one output consumed on ≥ 3 other GPUs is delivered by one pull chain."""
+    rt = B200Runtime(placement="round_robin", fanout_threshold=3)
+    try:
+        lz = Lzy(runtime=rt)
+
+        @op
+        def produce() -> torch.Tensor:
+            return torch.arange(1 << 22, dtype=torch.float32, device="cuda")
+
+        @op
+        def consume(t: torch.Tensor, k: int) -> float:
+            t.mul_(k)  # every consumer owns its copy
+            return float(t[-1].item())
+
+        with lz.workflow(f"wf{uuid.uuid4().hex}"):
+            src = produce()
+            outs = [consume(src, k) for k in range(1, NGPU)]
+        assert [float(o) for o in outs] == [float(((1 << 22) - 1) * k) for k in range(1, NGPU)]
+        assert rt.stats.get("fanouts", 0) == 1
+    finally:
+        rt.close()

@@ -294,3 +294,50 @@ def test_close_while_waiting_for_peer(env):
     time.sleep(0.2)
     slot_consumers = [c for c in cm.channels_status("exec", [chan])[0]["consumers"] if c["kind"] == "slot"]
     assert slot_consumers == []  # clear() unbound it; only the channel's storage consumer is left
+
+
+def test_stress_many_contexts_with_random_peer_failures(env):
+    """40 producer → consumer pairs over 4 workers, a third of the producers fail part-way (the consumers
+    fail over to the storage backup); everything is delivered bit-exact and no frame leaks."""
+    import random
+    cm, slots0, lib = env
+    workers = [slots0] + [Slots(cm, 0, f"lzyb://worker-{i}") for i in range(1, 4)]
+    rnd = random.Random(7)
+    jobs = []
+    try:
+        for i in range(40):
+            data = os.urandom(rnd.choice([5, 4096, 70_001, 1 << 20]))
+            chan = cm.get_or_create("u", "wf", "stress", consumer_uri=f"mem://stress/{i}")
+            wp, wc = rnd.choice(workers), rnd.choice(workers)
+            cons = wc.context("stress", f"c{i}")
+            cons.add_slot(f"in{i}", chan, DIR_INPUT)
+            cons.prefetch()  # early consumer
+            prod = wp.context("stress", f"p{i}")
+            prod.add_slot(f"out{i}", chan, DIR_OUTPUT)
+            jobs.append((i, data, prod, cons))
+
+        def produce_all():
+            for i, data, prod, cons in jobs:
+                prod.before_execution()
+                h = prod.output_open(f"out{i}", len(data))
+                hostmem.write(h, data)
+                if i % 3 == 0 and len(data) > 64:
+                    lib.hostmem_set_fail_after(h, (len(data) // 2) & ~15)
+                prod.output_done(f"out{i}")
+
+        t = threading.Thread(target=produce_all)
+        t.start()
+        for i, data, prod, cons in jobs:
+            cons.before_execution(30000)
+            assert hostmem.peek(cons.input_handle(f"in{i}"), len(data)) == data, f"job {i}"
+        t.join()
+        for i, data, prod, cons in jobs:
+            prod.after_execution(30000)
+    finally:
+        for _, _, prod, cons in jobs:
+            cons.close()
+            prod.close()
+        for i in range(40):
+            H.blob_delete(f"mem://stress/{i}")
+        for w in workers[1:]:
+            w.close()
