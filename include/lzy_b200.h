@@ -234,9 +234,12 @@ int lzyb_peer_import(const lzyb_ipc_desc_t* desc, int onto_gpu, lzyb_handle_t* o
 /* ---- fan-out ------------------------------------------------------------------------------ */
 /* One producer, n consumers on distinct GPUs of this process (SlotsService.bind creates one
  * transfer per consumer, channel-manager/.../services/SlotsService.java:457-466; OutputSlot.read
- * one ReadThread per consumer, OutputSlot.java:66-72).  Chunk-pipelined pull chain over NVLink:
- * consumer k pulls chunk c from consumer k-1 while k-1 pulls chunk c+1 from its predecessor, so
- * the producer's egress is paid once.  All dsts end READY and verified. Blocks. */
+ * one ReadThread per consumer, OutputSlot.java:66-72).  A pull chain over NVLink: consumer k pulls
+ * from consumer k-1 while k-1 is still receiving, so the producer's egress is paid once.
+ * chunk_bytes == 0 (default): ONE kernel launch per consumer GPU, all running concurrently and
+ * handing 1 MiB chunks to each other through progress counters in peer memory (acquire/release at
+ * system scope) — needs every consumer on its own GPU.  chunk_bytes > 0: host-driven chain, one
+ * launch per (consumer, chunk), chained by CUDA events.  All dsts end READY and verified. Blocks. */
 int lzyb_broadcast(lzyb_handle_t src, const lzyb_handle_t* dsts, int n, uint64_t chunk_bytes);
 
 /* ---- pinned host ring for non-tensor objects -------------------------------------------------- */

@@ -61,7 +61,7 @@ class B200RuntimeConfig:
     republish_inputs: bool = False               # "<slot>-out" seeding (InputSlot.java:160-168); ops own their inputs when off
     fanout_threshold: int = 3                    # an entry consumed on ≥ this many *other* GPUs is delivered by one chunk-pipelined
                                                  # pull chain (lzyb_broadcast) instead of one unicast per consumer; 0 = never
-    fanout_chunk_bytes: int = 64 << 20
+    fanout_chunk_bytes: int = 0                  # 0 = device-chained kernel; > 0 = host-driven chain with that chunk size
     retain: str = "auto"                         # "auto": a frame is freed once no proxy / queued call can ask for it; "all": keep until clear()
     chunk_bytes: int = 0                         # 0 = one launch per transfer; the reference streams 2 MiB chunks
     copy_engine: str = "auto"                    # "auto" | "ldg" | "tma"

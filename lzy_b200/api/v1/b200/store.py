@@ -248,8 +248,6 @@ class FrameStore:
             s = self._frames.pop(uri, None)
         if off is not None:
             N.ring_release(off)
-        with self._lock:
-            pass
         H.frame_store_drop(uri)
         if s is not None:
             s.close()

@@ -1180,7 +1180,7 @@ int lzyb_peer_import(const lzyb_ipc_desc_t* desc, int onto_gpu, lzyb_handle_t* o
 
 // ---- fan-out: chunk-pipelined pull chain -------------------------------------------------------
 
-int lzyb_broadcast(lzyb_handle_t src_h, const lzyb_handle_t* dsts, int n, uint64_t chunk_bytes) {
+static int broadcast_host_driven(lzyb_handle_t src_h, const lzyb_handle_t* dsts, int n, uint64_t chunk_bytes) {
     if (n <= 0 || !dsts) return fail(LZYB_E_ARG, "no consumers");
     if (chunk_bytes == 0) chunk_bytes = 32ull << 20;
     chunk_bytes = round_up(chunk_bytes, 4096);
@@ -1265,6 +1265,120 @@ int lzyb_broadcast(lzyb_handle_t src_h, const lzyb_handle_t* dsts, int n, uint64
         for (auto e : row)
             if (e) cudaEventDestroy(e);
     return rc;
+}
+
+
+// Device-chained fan-out: one chain_digest_kernel launch per consumer GPU, all running at once; the
+// stages hand tiles to each other through progress counters in peer memory.
+static int broadcast_device_chained(lzyb_handle_t src_h, const lzyb_handle_t* dsts, int n) {
+    auto src = find(src_h);
+    if (!src) return fail(LZYB_E_ARG, "unknown source handle");
+    std::vector<SlotPtr> chain;
+    for (int k = 0; k < n; ++k) {
+        auto s = find(dsts[k]);
+        if (!s) return fail(LZYB_E_ARG, "unknown consumer handle #%d", k);
+        chain.push_back(s);
+    }
+    const uint64_t total = src->nbytes;
+    if (src->state != LZYB_ST_READY) return fail(LZYB_E_PEER, "peer %s has no complete data", src->id.c_str());
+    for (auto& s : chain) {
+        if (!s->is_input || s->state != LZYB_ST_EMPTY || s->delivered != 0 || s->nbytes != total)
+            return fail(LZYB_E_STATE, "consumer %s is not an empty input slot of %llu bytes", s->id.c_str(), (unsigned long long)total);
+    }
+    constexpr unsigned CHUNK_SHIFT = 5;  // 32 tiles of 32 KiB = 1 MiB per progress counter
+    const uint64_t nvec = total >> 4, tile = 256ull * 8;
+    uint64_t ntiles = (nvec + tile - 1) / tile + ((nvec % tile == 0 && (total & 15)) ? 1 : 0);
+    if (ntiles == 0) ntiles = 1;
+    const uint64_t nchunks = (ntiles + (1ull << CHUNK_SHIFT) - 1) >> CHUNK_SHIFT;
+    const uint64_t flag_bytes = frame_capacity(nchunks * sizeof(unsigned int));
+    std::vector<uint8_t*> flags(n, nullptr);
+    int rc = LZYB_OK;
+    for (int k = 0; k < n && rc == LZYB_OK; ++k) {
+        DeviceCtx& d = *g.devs[chain[k]->dev];
+        DeviceGuard dg(d.ordinal);
+        rc = alloc_frame(d, flag_bytes, &flags[k]);
+        if (rc == LZYB_OK && cudaMemsetAsync(flags[k], 0, nchunks * sizeof(unsigned int), d.stream) != cudaSuccess)
+            rc = fail(LZYB_E_LOCAL, "cannot clear progress counters");
+    }
+    for (int k = 0; k < n && rc == LZYB_OK; ++k) {  // counters are zero everywhere before anybody polls
+        DeviceCtx& d = *g.devs[chain[k]->dev];
+        DeviceGuard dg(d.ordinal);
+        if (cudaStreamSynchronize(d.stream) != cudaSuccess) rc = fail(LZYB_E_LOCAL, "stream sync failed");
+    }
+    for (int k = 0; k < n && rc == LZYB_OK; ++k) {
+        Slot& dd = *chain[k];
+        Slot& up = k == 0 ? *src : *chain[k - 1];
+        std::lock_guard<std::mutex> lk(dd.mu);
+        DeviceCtx& d = *g.devs[dd.dev];
+        DeviceGuard dg(d.ordinal);
+        CopyParams p;
+        memset(&p, 0, sizeof(p));
+        p.src = up.payload();
+        p.dst = dd.payload();
+        p.nbytes = total;
+        p.ctl = dd.ctl;
+        p.total_nbytes = total;
+        p.fin = FIN_VERIFY;
+        p.expect[0] = src->digest[0];
+        p.expect[1] = src->digest[1];
+        p.dst_hdr = reinterpret_cast<lzyb_frame_header_t*>(dd.buf);
+        dd.dtype = src->dtype;
+        dd.ndim = src->ndim;
+        memcpy(dd.shape, src->shape, sizeof(dd.shape));
+        fill_template(dd, &p.hdr_template);
+        arm_mailbox(dd, p);
+        p.wait_flags = k == 0 ? nullptr : reinterpret_cast<const unsigned int*>(flags[k - 1]);
+        p.signal_flags = k == n - 1 ? nullptr : reinterpret_cast<unsigned int*>(flags[k]);
+        p.chunk_shift = CHUNK_SHIFT;
+        if (k == 0 && src->last_ev && src->last_stream != d.stream) cudaStreamWaitEvent(d.stream, src->last_ev, 0);
+        uint64_t want = (ntiles + 1) / 2;  // 2 tiles per CTA, in order
+        chain_digest_kernel<<<(unsigned)want, 256, 0, d.stream>>>(p);
+        g.st_launch++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            rc = fail(LZYB_E_LOCAL, "chain kernel launch failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        g.st_pull++;
+        if (up.dev == dd.dev && !up.remote)
+            g.st_bpull_l += total;
+        else
+            g.st_bpull_p += total;
+        dd.delivered = total;
+        dd.state = LZYB_ST_FILLING;
+        dd.digest_pending = true;
+        note(dd, d.stream);
+    }
+    if (rc == LZYB_OK) {
+        for (int k = 0; k < n && rc == LZYB_OK; ++k) rc = lzyb_input_finish(dsts[k], src_h, nullptr);
+    }
+    for (int k = 0; k < n; ++k) {
+        if (!flags[k]) continue;
+        DeviceCtx& d = *g.devs[chain[k]->dev];
+        DeviceGuard dg(d.ordinal);
+        cudaStreamSynchronize(d.stream);
+        free_frame(d, flags[k], flag_bytes);
+    }
+    return rc;
+}
+
+int lzyb_broadcast(lzyb_handle_t src_h, const lzyb_handle_t* dsts, int n, uint64_t chunk_bytes) {
+    if (n <= 0 || !dsts) return fail(LZYB_E_ARG, "no consumers");
+    if (chunk_bytes == 0) {
+        // the device-chained kernel needs every stage on its own GPU (a stage that spins must not be able to
+        // starve the stage it waits for); otherwise fall back to the host-driven chain
+        std::vector<int> devs;
+        bool distinct = true;
+        for (int k = 0; k < n; ++k) {
+            auto s = find(dsts[k]);
+            if (!s) return fail(LZYB_E_ARG, "unknown consumer handle #%d", k);
+            for (int d : devs) distinct = distinct && d != s->dev;
+            devs.push_back(s->dev);
+        }
+        if (distinct) return broadcast_device_chained(src_h, dsts, n);
+        chunk_bytes = 64ull << 20;
+    }
+    return broadcast_host_driven(src_h, dsts, n, chunk_bytes);
 }
 
 // ---- pinned host ring --------------------------------------------------------------------------

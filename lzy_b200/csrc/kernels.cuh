@@ -65,6 +65,11 @@ struct CopyParams {
     unsigned int seq;
     // 2-D gather (rows of row_bytes, src_pitch apart); rows == 0 → flat copy
     unsigned long long rows, row_bytes, src_pitch;
+    // device-chained fan-out (chain_digest_kernel): progress counters, one per chunk of 2^chunk_shift tiles
+    const unsigned int* wait_flags;   // upstream stage's counters (peer memory); nullptr = the source is final
+    unsigned int* signal_flags;       // this stage's counters; nullptr = nobody reads from this stage
+    unsigned int chunk_shift;
+    unsigned int pad2;
     lzyb_frame_header_t hdr_template;    // magic/version/dtype/shape for FIN_PUBLISH
 };
 
@@ -278,6 +283,86 @@ gather2d_digest_kernel(const __grid_constant__ CopyParams a) {
                 const unsigned long long o = r * vpr + c;  // vector index in the packed payload
                 fold16(v[j], (a.word_base + 2ull * o + 1ull) * LZYB_K_POS, sum, xr);
                 st_stream(dstv + o, v[j]);
+            }
+        }
+    }
+    block_epilogue(a, sum, xr);
+}
+
+// ---- kernel 2b: one stage of a device-chained fan-out ---------------------------------------------
+// Every stage of the chain (one per GPU) runs this kernel over the whole payload at the same time.
+// A CTA owns one 32 KiB tile; before touching it, it waits until the upstream stage has published the
+// chunk that contains the tile (a counter of finished tiles, polled over NVLink with acquire
+// semantics); after storing it, it bumps its own counter with release semantics at system scope.  The
+// payload therefore streams through all GPUs tile by tile inside ONE launch per GPU — no per-chunk
+// launches, no host events — and the transfer of chunk c to GPU k+1 overlaps GPU k still receiving
+// chunk c+1.  Loads are coherent (not .nc): the source is being written while we run.
+__device__ __forceinline__ uint4 ld_coherent(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_sys_add(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int CHAIN_UNROLL = 8;
+constexpr long long CHAIN_TIMEOUT_CYCLES = 4000000000ll;  // ≈ 2 s: a dead upstream must not hang the GPU
+
+__global__ void __launch_bounds__(256) chain_digest_kernel(const __grid_constant__ CopyParams a) {
+    const unsigned long long nvec = a.nbytes >> 4;
+    const unsigned long long tile = 256ull * CHAIN_UNROLL;
+    const unsigned long long ntiles = (nvec + tile - 1) / tile + ((nvec % tile == 0 && (a.nbytes & 15)) ? 1 : 0);
+    unsigned long long sum = 0ull, xr = 0ull;
+    uint4* dstv = reinterpret_cast<uint4*>(a.dst);
+    const uint4* srcv = reinterpret_cast<const uint4*>(a.src);
+    for (unsigned long long t = blockIdx.x; t < (ntiles ? ntiles : 1); t += gridDim.x) {
+        const unsigned long long c = t >> a.chunk_shift;
+        if (a.wait_flags) {
+            if (threadIdx.x == 0) {
+                const unsigned long long first = c << a.chunk_shift;
+                const unsigned long long in_chunk = (ntiles - first) < (1ull << a.chunk_shift) ? (ntiles - first) : (1ull << a.chunk_shift);
+                const long long t0 = clock64();
+                while (ld_acquire_sys(a.wait_flags + c) < (unsigned int)in_chunk) {
+                    __nanosleep(256);
+                    if (clock64() - t0 > CHAIN_TIMEOUT_CYCLES) break;  // upstream never delivered: carry on, the
+                                                                       // digest check will fail the transfer
+            }
+            __syncthreads();
+        }
+        const unsigned long long base = t * tile + threadIdx.x;
+        uint4 v[CHAIN_UNROLL];
+#pragma unroll
+        for (int j = 0; j < CHAIN_UNROLL; ++j) {
+            const unsigned long long i = base + static_cast<unsigned long long>(j) * 256;
+            if (i < nvec) v[j] = ld_coherent(srcv + i);
+        }
+        unsigned long long key = (a.word_base + 2ull * base + 1ull) * LZYB_K_POS;
+#pragma unroll
+        for (int j = 0; j < CHAIN_UNROLL; ++j) {
+            const unsigned long long i = base + static_cast<unsigned long long>(j) * 256;
+            if (i < nvec) {
+                fold16(v[j], key, sum, xr);
+                st_stream(dstv + i, v[j]);
+            }
+            key += 2ull * 256 * LZYB_K_POS;
+        }
+        if (t == ntiles - 1 && (a.nbytes & 15) && threadIdx.x == 0) {
+            fold_tail(a, a.src + (nvec << 4), a.dst + (nvec << 4), a.word_base + 2ull * nvec, static_cast<int>(a.nbytes & 15ull), sum, xr);
+        }
+        if (a.signal_flags) {
+            __syncthreads();  // every thread's stores of this tile are issued
+            if (threadIdx.x == 0) {
+                __threadfence_system();
+                red_release_sys_add(a.signal_flags + c, 1u);
             }
         }
     }

@@ -63,8 +63,10 @@ def test_cross_gpu_pull_is_bit_exact(native_all, engine):
         N.set_copy_engine(N.ENGINE_AUTO)
 
 
-def test_broadcast_chain_to_every_gpu(native_all):
-    """C3 at test size: one producer on GPU 0, one consumer per GPU (GPU 0 included), chunk-pipelined."""
+@pytest.mark.parametrize("chunk", [16 << 20, 0], ids=["host-driven-16MiB", "device-chained"])
+def test_broadcast_chain_to_every_gpu(native_all, chunk):
+    """C3 at test size: one producer on GPU 0, one consumer per GPU (GPU 0 included).  chunk = 0 is the
+    device-chained kernel (one launch per GPU, progress counters in peer memory)."""
     n = (96 << 20) + 33
     t = torch.empty(n + 16, dtype=torch.uint8, device="cuda:0")
     N.fill_pattern(0, t.data_ptr(), n, 7)
@@ -76,7 +78,7 @@ def test_broadcast_chain_to_every_gpu(native_all):
         src.pack(t.data_ptr(), n)
         dg = src.commit()
         assert dg == oracle.digest(expect)
-        N.broadcast(src, dsts, 16 << 20)
+        N.broadcast(src, dsts, chunk)
         for d in dsts:
             assert d.info().state == N.ST_READY and tuple(d.info().digest) == dg
             assert np.array_equal(to_host(d), expect)

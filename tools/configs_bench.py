@@ -98,7 +98,7 @@ def c3(mib: int, reps: int):
             d.close()
         return dt, ok
 
-    for name, fn in [("pull-chain 16MiB", lambda: run_broadcast(16 << 20)), ("pull-chain 32MiB", lambda: run_broadcast(32 << 20)),
+    for name, fn in [("device-chained kernel (1 launch per GPU)", lambda: run_broadcast(0)), ("pull-chain 16MiB", lambda: run_broadcast(16 << 20)), ("pull-chain 32MiB", lambda: run_broadcast(32 << 20)),
                      ("pull-chain 64MiB", lambda: run_broadcast(64 << 20)), ("pull-chain 128MiB", lambda: run_broadcast(128 << 20)),
                      ("pull-chain 256MiB", lambda: run_broadcast(256 << 20)), ("concurrent unicasts", run_unicasts)]:
         ts = []
