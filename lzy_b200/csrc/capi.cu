@@ -1285,9 +1285,9 @@ static int broadcast_device_chained(lzyb_handle_t src_h, const lzyb_handle_t* ds
         if (!s->is_input || s->state != LZYB_ST_EMPTY || s->delivered != 0 || s->nbytes != total)
             return fail(LZYB_E_STATE, "consumer %s is not an empty input slot of %llu bytes", s->id.c_str(), (unsigned long long)total);
     }
-    constexpr unsigned CHUNK_SHIFT = 5;  // 32 tiles of 32 KiB = 1 MiB per progress counter
-    const uint64_t nvec = total >> 4, tile = 256ull * 8;
-    uint64_t ntiles = (nvec + tile - 1) / tile + ((nvec % tile == 0 && (total & 15)) ? 1 : 0);
+    constexpr unsigned CHUNK_SHIFT = 2;  // 4 spans of 256 KiB = 1 MiB per progress counter
+    const uint64_t nvec = total >> 4, span = 256ull * CHAIN_UNROLL * CHAIN_SPAN_TILES;
+    uint64_t ntiles = (nvec + span - 1) / span;  // spans
     if (ntiles == 0) ntiles = 1;
     const uint64_t nchunks = (ntiles + (1ull << CHUNK_SHIFT) - 1) >> CHUNK_SHIFT;
     const uint64_t flag_bytes = frame_capacity(nchunks * sizeof(unsigned int));
@@ -1331,8 +1331,7 @@ static int broadcast_device_chained(lzyb_handle_t src_h, const lzyb_handle_t* ds
         p.signal_flags = k == n - 1 ? nullptr : reinterpret_cast<unsigned int*>(flags[k]);
         p.chunk_shift = CHUNK_SHIFT;
         if (k == 0 && src->last_ev && src->last_stream != d.stream) cudaStreamWaitEvent(d.stream, src->last_ev, 0);
-        uint64_t want = (ntiles + 1) / 2;  // 2 tiles per CTA, in order
-        chain_digest_kernel<<<(unsigned)want, 256, 0, d.stream>>>(p);
+        chain_digest_kernel<<<(unsigned)ntiles, 256, 0, d.stream>>>(p);  // one 256 KiB span per CTA, scheduled in order
         g.st_launch++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {

@@ -315,55 +315,62 @@ __device__ __forceinline__ void red_release_sys_add(unsigned int* p, unsigned in
 }
 
 constexpr int CHAIN_UNROLL = 8;
+constexpr int CHAIN_SPAN_TILES = 8;                       // a CTA owns 8 consecutive 32 KiB tiles = 256 KiB
 constexpr long long CHAIN_TIMEOUT_CYCLES = 4000000000ll;  // ≈ 2 s: a dead upstream must not hang the GPU
 
+// progress counters count finished *spans*; chunk_shift is log2(spans per counter)
 __global__ void __launch_bounds__(256) chain_digest_kernel(const __grid_constant__ CopyParams a) {
     const unsigned long long nvec = a.nbytes >> 4;
-    const unsigned long long tile = 256ull * CHAIN_UNROLL;
-    const unsigned long long ntiles = (nvec + tile - 1) / tile + ((nvec % tile == 0 && (a.nbytes & 15)) ? 1 : 0);
+    const unsigned long long span = 256ull * CHAIN_UNROLL * CHAIN_SPAN_TILES;  // vectors per span
+    unsigned long long nspans = (nvec + span - 1) / span;
+    if (nspans == 0) nspans = 1;  // a payload shorter than one vector still has its byte tail
     unsigned long long sum = 0ull, xr = 0ull;
     uint4* dstv = reinterpret_cast<uint4*>(a.dst);
     const uint4* srcv = reinterpret_cast<const uint4*>(a.src);
-    for (unsigned long long t = blockIdx.x; t < (ntiles ? ntiles : 1); t += gridDim.x) {
-        const unsigned long long c = t >> a.chunk_shift;
+    for (unsigned long long sp = blockIdx.x; sp < nspans; sp += gridDim.x) {
+        const unsigned long long c = sp >> a.chunk_shift;
         if (a.wait_flags) {
             if (threadIdx.x == 0) {
                 const unsigned long long first = c << a.chunk_shift;
-                const unsigned long long in_chunk = (ntiles - first) < (1ull << a.chunk_shift) ? (ntiles - first) : (1ull << a.chunk_shift);
+                const unsigned long long in_chunk =
+                    (nspans - first) < (1ull << a.chunk_shift) ? (nspans - first) : (1ull << a.chunk_shift);
                 const long long t0 = clock64();
-                while (ld_acquire_sys(a.wait_flags + c) < (unsigned int)in_chunk) {
-                    __nanosleep(256);
-                    if (clock64() - t0 > CHAIN_TIMEOUT_CYCLES) break;  // upstream never delivered: carry on, the
-                                                                       // digest check will fail the transfer
+                while (ld_acquire_sys(a.wait_flags + c) < static_cast<unsigned int>(in_chunk)) {
+                    __nanosleep(128);
+                    // upstream never delivered: carry on, the digest check will fail the transfer
+                    if (clock64() - t0 > CHAIN_TIMEOUT_CYCLES) break;
+                }
             }
             __syncthreads();
         }
-        const unsigned long long base = t * tile + threadIdx.x;
-        uint4 v[CHAIN_UNROLL];
+#pragma unroll 1
+        for (int tl = 0; tl < CHAIN_SPAN_TILES; ++tl) {
+            const unsigned long long base = sp * span + static_cast<unsigned long long>(tl) * 256 * CHAIN_UNROLL + threadIdx.x;
+            if (base - threadIdx.x >= nvec) break;
+            uint4 v[CHAIN_UNROLL];
 #pragma unroll
-        for (int j = 0; j < CHAIN_UNROLL; ++j) {
-            const unsigned long long i = base + static_cast<unsigned long long>(j) * 256;
-            if (i < nvec) v[j] = ld_coherent(srcv + i);
-        }
-        unsigned long long key = (a.word_base + 2ull * base + 1ull) * LZYB_K_POS;
-#pragma unroll
-        for (int j = 0; j < CHAIN_UNROLL; ++j) {
-            const unsigned long long i = base + static_cast<unsigned long long>(j) * 256;
-            if (i < nvec) {
-                fold16(v[j], key, sum, xr);
-                st_stream(dstv + i, v[j]);
+            for (int j = 0; j < CHAIN_UNROLL; ++j) {
+                const unsigned long long i = base + static_cast<unsigned long long>(j) * 256;
+                if (i < nvec) v[j] = ld_coherent(srcv + i);
             }
-            key += 2ull * 256 * LZYB_K_POS;
+            unsigned long long key = (a.word_base + 2ull * base + 1ull) * LZYB_K_POS;
+#pragma unroll
+            for (int j = 0; j < CHAIN_UNROLL; ++j) {
+                const unsigned long long i = base + static_cast<unsigned long long>(j) * 256;
+                if (i < nvec) {
+                    fold16(v[j], key, sum, xr);
+                    st_stream(dstv + i, v[j]);
+                }
+                key += 2ull * 256 * LZYB_K_POS;
+            }
         }
-        if (t == ntiles - 1 && (a.nbytes & 15) && threadIdx.x == 0) {
-            fold_tail(a, a.src + (nvec << 4), a.dst + (nvec << 4), a.word_base + 2ull * nvec, static_cast<int>(a.nbytes & 15ull), sum, xr);
+        if (sp == nspans - 1 && (a.nbytes & 15) && threadIdx.x == 0) {
+            fold_tail(a, a.src + (nvec << 4), a.dst + (nvec << 4), a.word_base + 2ull * nvec,
+                      static_cast<int>(a.nbytes & 15ull), sum, xr);
         }
         if (a.signal_flags) {
-            __syncthreads();  // every thread's stores of this tile are issued
-            if (threadIdx.x == 0) {
-                __threadfence_system();
-                red_release_sys_add(a.signal_flags + c, 1u);
-            }
+            __syncthreads();  // every thread's stores of this span are issued (and ordered before thread 0's release)
+            if (threadIdx.x == 0) red_release_sys_add(a.signal_flags + c, 1u);
         }
     }
     block_epilogue(a, sum, xr);
