@@ -170,17 +170,17 @@ def test_fanout_to_many_gpus_uses_the_pull_chain():
 
         @op
         def produce() -> torch.Tensor:
-            return torch.arange(1 << 22, dtype=torch.float32, device="cuda")
+            return torch.arange(1 << 22, dtype=torch.int64, device="cuda")
 
         @op
-        def consume(t: torch.Tensor, k: int) -> float:
+        def consume(t: torch.Tensor, k: int) -> int:
             t.mul_(k)  # every consumer owns its copy
-            return float(t[-1].item())
+            return int(t[-1].item())
 
         with lz.workflow(f"wf{uuid.uuid4().hex}"):
             src = produce()
             outs = [consume(src, k) for k in range(1, NGPU)]
-        assert [float(o) for o in outs] == [float(((1 << 22) - 1) * k) for k in range(1, NGPU)]
+        assert [int(o) for o in outs] == [((1 << 22) - 1) * k for k in range(1, NGPU)]
         assert rt.stats.get("fanouts", 0) == 1
     finally:
         rt.close()
