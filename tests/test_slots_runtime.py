@@ -296,6 +296,21 @@ def test_close_while_waiting_for_peer(env):
     assert slot_consumers == []  # clear() unbound it; only the channel's storage consumer is left
 
 
+def test_only_producer_keeps_failing_destroys_the_channel(env):
+    """A channel whose only producer (a storage peer whose object is gone) can never deliver: every
+    TransferFailed walks the peer's priority down (SlotsService.java:249-253); once it is below zero
+    there is no producer left, the channel manager destroys channel and workflow (:255-266) and the
+    consumer's slot fails with that description."""
+    cm, slots, lib = env
+    chan = cm.get_or_create("u", "wf", "exec-np", producer_uri="mem://vanished")
+    inp = slots.context("exec-np", "b")
+    inp.add_slot("c", chan, DIR_INPUT)
+    with pytest.raises(N.LzybError, match="No more producers in channel"):
+        inp.before_execution(10000)
+    assert cm.aborted("exec-np").startswith("No more producers")
+    inp.close()
+
+
 def test_stress_many_contexts_with_random_peer_failures(env):
     """40 producer → consumer pairs over 4 workers, a third of the producers fail part-way (the consumers
     fail over to the storage backup); everything is delivered bit-exact and no frame leaks."""
@@ -305,36 +320,56 @@ def test_stress_many_contexts_with_random_peer_failures(env):
     rnd = random.Random(7)
     jobs = []
     try:
+        def flaky(i, data):
+            return i % 3 == 0 and len(data) > 64
+
         for i in range(40):
             data = os.urandom(rnd.choice([5, 4096, 70_001, 1 << 20]))
             chan = cm.get_or_create("u", "wf", "stress", consumer_uri=f"mem://stress/{i}")
             wp, wc = rnd.choice(workers), rnd.choice(workers)
             cons = wc.context("stress", f"c{i}")
             cons.add_slot(f"in{i}", chan, DIR_INPUT)
-            cons.prefetch()  # early consumer
+            if not flaky(i, data):
+                cons.prefetch()  # early consumer
             prod = wp.context("stress", f"p{i}")
             prod.add_slot(f"out{i}", chan, DIR_OUTPUT)
-            jobs.append((i, data, prod, cons))
+            jobs.append((i, data, prod, cons, threading.Event()))
+
+        errors = []
 
         def produce_all():
-            for i, data, prod, cons in jobs:
-                prod.before_execution()
-                h = prod.output_open(f"out{i}", len(data))
-                hostmem.write(h, data)
-                if i % 3 == 0 and len(data) > 64:
-                    lib.hostmem_set_fail_after(h, (len(data) // 2) & ~15)
-                prod.output_done(f"out{i}")
+            try:
+                for i, data, prod, cons, uploaded in jobs:
+                    prod.before_execution()
+                    h = prod.output_open(f"out{i}", len(data))
+                    hostmem.write(h, data)
+                    prod.output_done(f"out{i}")
+                    if flaky(i, data):
+                        # the storage backup must exist before the worker peer turns bad, otherwise the
+                        # consumer exhausts the only producer's retries and the channel is destroyed
+                        # (SlotsService.java:255-266) — test_only_producer_keeps_failing_destroys_the_channel
+                        prod.after_execution(30000)
+                        lib.hostmem_set_fail_after(h, (len(data) // 2) & ~15)
+                    uploaded.set()
+            except BaseException as e:  # surfaced in the main thread below
+                errors.append(e)
+                for j in jobs:
+                    j[4].set()
 
         t = threading.Thread(target=produce_all)
         t.start()
-        for i, data, prod, cons in jobs:
+        for i, data, prod, cons, uploaded in jobs:
+            if flaky(i, data):
+                assert uploaded.wait(30) and not errors, errors
             cons.before_execution(30000)
             assert hostmem.peek(cons.input_handle(f"in{i}"), len(data)) == data, f"job {i}"
         t.join()
-        for i, data, prod, cons in jobs:
-            prod.after_execution(30000)
+        assert not errors, errors
+        for i, data, prod, cons, _ in jobs:
+            if not flaky(i, data):
+                prod.after_execution(30000)
     finally:
-        for _, _, prod, cons in jobs:
+        for _, _, prod, cons, _ in jobs:
             cons.close()
             prod.close()
         for i in range(40):
