@@ -45,7 +45,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--payload-mib", type=int, default=1024)
-    ap.add_argument("--engine", default="auto", choices=["auto", "ldg", "tma"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "ldg", "tma", "dma"])
+    ap.add_argument("--dma-last-mib", type=int, default=0, help="last sub-chunk of copy-engine peer pulls (0 = auto)")
+    ap.add_argument("--dma-growth", type=int, default=6, help="growth factor of the sub-chunk schedule towards the front")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -184,9 +186,10 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     N.init(dev, 1, 64 << 20)
     if args.engine != "auto":
-        N.set_copy_engine({"ldg": N.ENGINE_LDG, "tma": N.ENGINE_TMA}[args.engine])
+        N.set_copy_engine({"ldg": N.ENGINE_LDG, "tma": N.ENGINE_TMA, "dma": N.ENGINE_DMA}[args.engine])
     if args.ctas_per_sm:
         N.set_grid(args.ctas_per_sm)
+    N.set_dma_schedule(args.dma_last_mib << 20, args.dma_growth)
 
     payload = args.payload_mib << 20
     n_elem = payload // 4
@@ -319,7 +322,10 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    if args.engine == "tma" or (args.engine == "auto" and multi):
+    if multi and args.engine in ("auto", "dma"):
+        kernel_name = ("copy engine in geometric sub-chunks (800+192+32 MiB) + stream_digest_kernel<16,8,false> scans "
+                       "trailing one sub-chunk behind on the sink GPU")
+    elif args.engine == "tma":
         kernel_name = "tma_stream_digest_kernel<3,32768,true> (TMA bulk ring)"
     else:
         kernel_name = "stream_digest_kernel<16,8,true> (LDG.128/STG.128, 2 tiles per CTA)"
@@ -339,7 +345,7 @@ def run_ours(args):
         roof = {"bound": "nvlink", "kernel": kernel_name + " (peer pull over CUDA-IPC mapping)", "achieved": achieved,
                 "peak": 770.0, "unit": "GB/s", "frac": achieved / 770.0, "traffic": None,
                 "peak_source": "measured peer copy 770 GB/s/dir (B200_PROFILING.md); nominal 900",
-                "avg_launch_ms": pavg, "launches_timed": len(pull),
+                "avg_launch_ms": pavg, "launches_timed": len(pull), "dma_copies": st.get("dma_copies", 0),
                 "kernel_share_of_step": sum(all_ms) / ms_total}
     traffic_file = ROOT / "profiles" / "traffic.json"
     if traffic_file.exists() and not multi:

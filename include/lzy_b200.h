@@ -127,6 +127,7 @@ typedef struct lzyb_stats {
     uint64_t slots_live;
     uint64_t hbm_bytes_live;
     uint64_t hbm_bytes_pooled;
+    uint64_t dma_copies;       /* copy-engine sub-chunk copies issued by peer pulls (engine 3 / auto)  */
 } lzyb_stats_t;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -258,9 +259,16 @@ int lzyb_fill_pattern(int gpu, void* dptr, uint64_t nbytes, uint64_t seed, void*
 int lzyb_copy_to_host(lzyb_handle_t h, uint64_t offset, void* dst_host, uint64_t len, void* stream);
 int lzyb_stats(lzyb_stats_t* out);
 int lzyb_stats_reset(void);
-/* kernel variant for large contiguous transfers: 0 = auto, 1 = LDG/STG 16-B vectors,
- * 2 = TMA bulk (cp.async.bulk + mbarrier ring) */
+/* how large contiguous transfers are carried: 0 = auto, 1 = LDG/STG 16-B vectors, 2 = TMA bulk
+ * (cp.async.bulk + mbarrier ring), 3 = peer pulls ride the copy engine in sub-chunks while a scan kernel on
+ * the sink GPU digests each landed sub-chunk in the shadow of the next copy (same-GPU work as in auto).
+ * auto = 3 for peer pulls of at least 256 MiB (the engine keeps 772 GB/s per direction with both directions of
+ * a GPU pair busy, SM loads 670), the fused kernels for everything else */
 int lzyb_set_copy_engine(int engine);
+/* sub-chunk schedule of a copy-engine pull: the last sub-chunk is last_bytes (0 = payload/32 clamped to
+ * 4..32 MiB; else a multiple of 16, at least 1 MiB), each earlier one `growth` times larger (default 6; 1 =
+ * uniform), the first takes the remainder */
+int lzyb_set_dma_schedule(uint64_t last_bytes, int growth);
 /* LDG/STG grid shape: n > 0 = persistent, n CTAs per SM; 0 = one 32 KiB tile per CTA; -T = T tiles per CTA;
  * -1000 = auto (default) */
 int lzyb_set_grid(int ctas_per_sm);

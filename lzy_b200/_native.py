@@ -30,7 +30,7 @@ DT_F16, DT_BF16, DT_F32, DT_F64, DT_BOOL = 6, 7, 8, 9, 10
 DT_U16, DT_U32, DT_U64, DT_PICKLE = 11, 12, 13, 32
 
 FAULT_NONE, FAULT_PEER_AFTER, FAULT_CORRUPT_ONCE, FAULT_LOCAL_OPEN = 0, 1, 2, 3
-ENGINE_AUTO, ENGINE_LDG, ENGINE_TMA = 0, 1, 2
+ENGINE_AUTO, ENGINE_LDG, ENGINE_TMA, ENGINE_DMA = 0, 1, 2, 3
 MAX_DIMS = 8
 
 
@@ -104,7 +104,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "kernel_launches", "pack_launches", "pull_launches", "scan_launches", "frame_launches",
         "bytes_packed", "bytes_pulled_local", "bytes_pulled_peer", "bytes_framed_host",
-        "h2d_bytes", "d2h_bytes", "slots_live", "hbm_bytes_live", "hbm_bytes_pooled")]
+        "h2d_bytes", "d2h_bytes", "slots_live", "hbm_bytes_live", "hbm_bytes_pooled", "dma_copies")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -168,6 +168,7 @@ _SIGNATURES = {
     "lzyb_set_copy_engine": (C.c_int, [C.c_int]),
     "lzyb_set_grid": (C.c_int, [C.c_int]),
     "lzyb_set_tma_config": (C.c_int, [C.c_int]),
+    "lzyb_set_dma_schedule": (C.c_int, [C.c_uint64, C.c_int]),
     "lzyb_set_debug_flags": (C.c_int, [C.c_int]),
     "lzyb_fault_inject": (C.c_int, [_H, C.c_int, C.c_uint64]),
 }
@@ -403,6 +404,10 @@ def fill_pattern(gpu: int, dptr: int, nbytes: int, seed: int, stream: int = 0) -
 
 def set_copy_engine(engine: int) -> None:
     check(lib.lzyb_set_copy_engine(engine))
+
+
+def set_dma_schedule(last_bytes: int = 0, growth: int = 6) -> None:
+    check(lib.lzyb_set_dma_schedule(last_bytes, growth))
 
 
 def set_tma_config(index: int) -> None:

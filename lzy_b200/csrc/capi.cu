@@ -37,6 +37,7 @@ static_assert(sizeof(lzyb_frame_header_t) == 128, "frame header must be 128 byte
 static_assert(sizeof(lzyb_ipc_desc_t) == 256, "ipc descriptor must be 256 bytes");
 constexpr int CTL_SLAB = 8192;        // slots that can be live per device
 constexpr int MBOX_SLAB = 65536;      // mailboxes (pinned, all devices)
+constexpr uint64_t DMA_MIN_BYTES = 256ull << 20;  // peer pulls at least this long ride the copy engine (auto policy)
 constexpr int GRID_AUTO = -1000;      // lzyb_set_grid: let launch_stream pick the grid shape
 // TMA ring shapes that can be selected at run time (lzyb_set_tma_config): {stages, stage bytes, CTAs per SM}
 struct TmaCfg {
@@ -111,6 +112,19 @@ struct DeviceCtx {
     SlotCtl* ctl_slab = nullptr;
     std::vector<int> ctl_free;
     bool tma_attr[8] = {false, false, false, false, false, false, false, false};
+    // DMA pull (launch_dma_verify): scans trail the copy engine on their own stream; events are recycled
+    cudaStream_t verify_stream = nullptr;
+    std::vector<cudaEvent_t> dma_events;
+    size_t dma_ev_next = 0;
+    cudaEvent_t next_dma_event() {
+        if (dma_events.size() < 256) {
+            cudaEvent_t e = nullptr;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            dma_events.push_back(e);
+            return e;
+        }
+        return dma_events[dma_ev_next++ % dma_events.size()];
+    }
 };
 
 struct Slot {
@@ -176,7 +190,10 @@ struct Global {
     std::atomic<int> tma_cfg{1};  // 3 × 32 KiB, 2 CTAs/SM: best of the sweep in profiles/r01_microbench_local.jsonl
     std::atomic<int> ctas_per_sm{GRID_AUTO};
     std::atomic<int> global_fault{LZYB_FAULT_NONE};
+    std::atomic<uint64_t> dma_last_bytes{0};  // last sub-chunk of a copy-engine pull (0 = total/32 in 4..32 MiB)
+    std::atomic<int> dma_growth{6};            // each earlier sub-chunk is this many times larger
     // stats
+    std::atomic<uint64_t> st_dma{0};
     std::atomic<uint64_t> st_launch{0}, st_pack{0}, st_pull{0}, st_scan{0}, st_frame{0}, st_bpack{0},
         st_bpull_l{0}, st_bpull_p{0}, st_bframe{0}, st_h2d{0}, st_d2h{0}, st_live{0}, st_hbm_live{0};
 };
@@ -282,7 +299,7 @@ int launch_stream(DeviceCtx& d, const CopyParams& p, bool store, cudaStream_t st
     // TMA ring keeps the most bytes in flight with the fewest instructions (670 vs 634 GB/s per direction when
     // both directions are busy); a same-GPU copy is HBM-bound and an oversubscribed LDG/STG grid wins
     // (6.47 TB/s vs 5.97 TB/s for the persistent ring).
-    if (engine == 0) engine = (peer && tma_ok) ? 2 : 1;
+    if (engine == 0 || engine == 3) engine = (peer && tma_ok) ? 2 : 1;  // 3 only changes how peer pulls are carried
     if (engine == 2 && !tma_ok) engine = 1;
     if (engine == 2) {
         const int ci = g.tma_cfg.load();
@@ -325,6 +342,81 @@ int launch_stream(DeviceCtx& d, const CopyParams& p, bool store, cudaStream_t st
     g.st_launch++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "kernel launch failed: %s", cudaGetErrorString(e));
+    return LZYB_OK;
+}
+
+// Pull from a frame on another GPU with the copy engine, verified by trailing scans.
+//
+// Measured on a B200 pair (tools/push_pull.cu, profiles/r01_push_pull.jsonl), 1 GiB, both directions of the
+// pair busy: SM loads over NVLink 640 (LDG) / 670 (TMA ring) GB/s per direction — the read requests of one
+// direction share the wire with the other direction's payload; SM stores (push) 705; the copy engine 772,
+// which is also its one-direction figure.  So the bytes ride the copy engine and the SMs do what only they can:
+// the digest.  The chunk is cut into sub-chunks; the scan of sub-chunk j (stream_digest_kernel, STORE = false,
+// reading the sink's own HBM at ~6 TB/s) runs on the device's verify stream while the engine copies j + 1.
+// Every engine copy costs ~14 µs of fixed latency (measured: uniform 32/64/128/256 MiB sub-chunks lose exactly
+// that per copy, and more copy streams do not hide it), and the scan of the final sub-chunk is pure tail, so
+// the schedule is geometric: a small last sub-chunk (total/32, 4..32 MiB), each earlier one `growth` (6) times
+// larger — a scan is ~8x faster than the copy that follows it, so it always finishes in that copy's shadow —
+// and the first takes the rest: 1 GiB = 800 + 192 + 32 MiB, three copies and ~11 µs of tail.  The last scan
+// carries the chunk's fin mode (FIN_VERIFY writes the header and the mailbox as in the fused kernels).
+int launch_stream(DeviceCtx& d, const CopyParams& p, bool store, cudaStream_t st, bool peer);
+
+std::vector<uint64_t> dma_schedule(uint64_t nbytes) {
+    const uint64_t ragged = nbytes & 15ull, total = nbytes - ragged;
+    const uint64_t growth = std::max<uint64_t>(1, g.dma_growth.load());
+    uint64_t last = g.dma_last_bytes.load();
+    if (last == 0) last = std::min<uint64_t>(std::max<uint64_t>((total / 32) & ~15ull, 4ull << 20), 32ull << 20);
+    std::vector<uint64_t> rev;  // sizes from the end of the chunk towards its start
+    uint64_t remaining = total, c = last;
+    while (remaining > 0) {
+        if (remaining <= c + c / 2 || rev.size() >= 60) {
+            rev.push_back(remaining);
+            break;
+        }
+        rev.push_back(c);
+        remaining -= c;
+        c *= growth;
+    }
+    if (rev.empty()) rev.push_back(0);
+    rev.front() += ragged;  // the payload's ragged tail belongs to the last sub-chunk
+    return std::vector<uint64_t>(rev.rbegin(), rev.rend());
+}
+
+int launch_dma_verify(DeviceCtx& d, const CopyParams& whole, cudaStream_t st) {
+    cudaStream_t vs = d.verify_stream;
+    // earlier chunks of this transfer (and the recycling of the sink frame) are ordered on `st`
+    cudaEvent_t ev = d.next_dma_event();
+    CU(cudaEventRecord(ev, st));
+    CU(cudaStreamWaitEvent(vs, ev, 0));
+    const std::vector<uint64_t> sizes = dma_schedule(whole.nbytes);
+    uint64_t off = 0;
+    for (size_t j = 0; j < sizes.size(); ++j) {
+        const uint64_t n = sizes[j];
+        const bool last = j + 1 == sizes.size();
+        if (n) {
+            CU(cudaMemcpyAsync(whole.dst + off, whole.src + off, n, cudaMemcpyDefault, st));
+            g.st_dma++;
+        }
+        ev = d.next_dma_event();
+        CU(cudaEventRecord(ev, st));
+        CU(cudaStreamWaitEvent(vs, ev, 0));
+        CopyParams p = whole;
+        p.src = whole.dst + off;  // scan what landed
+        p.dst = nullptr;
+        p.nbytes = n;
+        p.word_base = whole.word_base + (off >> 3);
+        if (!last) {
+            p.fin = FIN_NONE;
+            p.mbox = nullptr;
+            p.dst_hdr = nullptr;
+        }
+        int rc = launch_stream(d, p, false, vs, false);
+        if (rc != LZYB_OK) return rc;
+        off += n;
+    }
+    ev = d.next_dma_event();
+    CU(cudaEventRecord(ev, vs));
+    CU(cudaStreamWaitEvent(st, ev, 0));  // `st` continues only with a verified frame
     return LZYB_OK;
 }
 
@@ -461,6 +553,7 @@ int lzyb_init(int first_gpu, int n_gpus, uint64_t host_ring_bytes) {
         }
         d->sm_count = prop.multiProcessorCount;
         CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&d->verify_stream, cudaStreamNonBlocking));
         CU(cudaMalloc(&d->ctl_slab, sizeof(SlotCtl) * CTL_SLAB));
         CU(cudaMemset(d->ctl_slab, 0, sizeof(SlotCtl) * CTL_SLAB));
         for (int k = CTL_SLAB - 1; k >= 0; --k) d->ctl_free.push_back(k);
@@ -512,6 +605,8 @@ int lzyb_shutdown(void) {
         for (auto& kv : d->pool) cudaFree(kv.second);
         d->pool.clear();
         cudaFree(d->ctl_slab);
+        for (cudaEvent_t e : d->dma_events) cudaEventDestroy(e);
+        cudaStreamDestroy(d->verify_stream);
         cudaStreamDestroy(d->stream);
     }
     g.devs.clear();
@@ -901,7 +996,9 @@ int64_t lzyb_transfer_chunk(lzyb_handle_t dst_h, lzyb_handle_t src_h, uint64_t o
     // the producer's payload must be final on this stream's timeline
     if (src->last_ev && src->last_stream != st) cudaStreamWaitEvent(st, src->last_ev, 0);
     const bool peer = src->remote || src->dev != dst->dev;
-    int rc = launch_stream(d, p, true, st, peer);
+    const int engine = g.engine.load();
+    const bool dma = peer && (engine == 3 || (engine == 0 && len >= DMA_MIN_BYTES));
+    int rc = dma ? launch_dma_verify(d, p, st) : launch_stream(d, p, true, st, peer);
     if (rc != LZYB_OK) return rc;
     g.st_pull++;
     if (src->dev == dst->dev && !src->remote)
@@ -1614,18 +1711,30 @@ int lzyb_stats(lzyb_stats_t* out) {
     uint64_t pooled = 0;
     for (auto& d : g.devs) pooled += d->pooled_bytes;
     out->hbm_bytes_pooled = pooled;
+    out->dma_copies = g.st_dma;
     return LZYB_OK;
 }
 
 int lzyb_stats_reset(void) {
     g.st_launch = g.st_pack = g.st_pull = g.st_scan = g.st_frame = 0;
+    g.st_dma = 0;
     g.st_bpack = g.st_bpull_l = g.st_bpull_p = g.st_bframe = g.st_h2d = g.st_d2h = 0;
     return LZYB_OK;
 }
 
 int lzyb_set_copy_engine(int engine) {
-    if (engine < 0 || engine > 2) return fail(LZYB_E_ARG, "engine must be 0 (auto), 1 (LDG/STG) or 2 (TMA bulk)");
+    if (engine < 0 || engine > 3)
+        return fail(LZYB_E_ARG, "engine must be 0 (auto), 1 (LDG/STG), 2 (TMA bulk) or 3 (copy engine + trailing scan, peer pulls)");
     g.engine = engine;
+    return LZYB_OK;
+}
+
+int lzyb_set_dma_schedule(uint64_t last_bytes, int growth) {
+    if (last_bytes != 0 && (last_bytes < (1ull << 20) || (last_bytes & 15ull)))
+        return fail(LZYB_E_ARG, "last sub-chunk must be 0 (auto) or a multiple of 16 bytes, at least 1 MiB");
+    if (growth < 1 || growth > 64) return fail(LZYB_E_ARG, "growth must be in [1, 64]");
+    g.dma_last_bytes = last_bytes;
+    g.dma_growth = growth;
     return LZYB_OK;
 }
 

@@ -33,9 +33,10 @@ def to_host(slot):
     return out
 
 
-@pytest.mark.parametrize("engine", ["ldg", "tma"])
+@pytest.mark.parametrize("engine", ["ldg", "tma", "dma", "auto"])
 def test_cross_gpu_pull_is_bit_exact(native_all, engine):
-    N.set_copy_engine(N.ENGINE_TMA if engine == "tma" else N.ENGINE_LDG)
+    N.set_copy_engine({"ldg": N.ENGINE_LDG, "tma": N.ENGINE_TMA, "dma": N.ENGINE_DMA, "auto": N.ENGINE_AUTO}[engine])
+    N.set_dma_schedule(3 << 20, 1)  # several sub-chunks (and a ragged last one) per 8 MiB chunk
     try:
         n = (48 << 20) + 4096 + 7
         a = np.random.default_rng(5).integers(0, 256, n, dtype=np.uint8)
@@ -61,6 +62,40 @@ def test_cross_gpu_pull_is_bit_exact(native_all, engine):
             inp.close()
     finally:
         N.set_copy_engine(N.ENGINE_AUTO)
+        N.set_dma_schedule()
+
+
+def test_copy_engine_pull_trailing_scan_catches_corruption(native_all):
+    """The copy engine moves the bytes, the trailing scans own the digest: a peer that serves one wrong byte
+    is a ReadException at EOS exactly as with the fused kernels, and the sink can refetch elsewhere."""
+    n = (40 << 20) + 11
+    a = np.random.default_rng(6).integers(0, 256, n, dtype=np.uint8)
+    t = torch.from_numpy(a).to("cuda:0")
+    bad = N.SlotHandle.create_output("dma/bad", 0, n)
+    good = N.SlotHandle.create_output("dma/good", 0, n)
+    inp = N.SlotHandle.open_input("dma/in", 1, n)
+    N.set_copy_engine(N.ENGINE_DMA)
+    N.set_dma_schedule(4 << 20, 3)  # 40 MiB + 11 B = 24 + 12 + (4 MiB + 11 B)
+    try:
+        for s in (bad, good):
+            s.pack(t.data_ptr(), n)
+            s.commit()
+        bad.fault(N.FAULT_CORRUPT_ONCE, (17 << 20) + 5)
+        before = N.stats()["dma_copies"]
+        assert inp.transfer_chunk(bad, 0, 1 << 40) == n
+        assert N.stats()["dma_copies"] - before == 3
+        with pytest.raises(N.ReadException):
+            inp.finish(bad)
+        assert inp.info().delivered == 0
+        assert inp.transfer_chunk(good, 0, 1 << 40) == n
+        inp.finish(good)
+        assert tuple(inp.info().digest) == oracle.digest(a)
+        assert np.array_equal(to_host(inp), a)
+    finally:
+        N.set_copy_engine(N.ENGINE_AUTO)
+        N.set_dma_schedule()
+        for s in (bad, good, inp):
+            s.close()
 
 
 @pytest.mark.parametrize("chunk", [16 << 20, 0], ids=["host-driven-16MiB", "device-chained"])
