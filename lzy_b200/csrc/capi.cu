@@ -114,6 +114,7 @@ struct DeviceCtx {
     bool tma_attr[8] = {false, false, false, false, false, false, false, false};
     // DMA pull (launch_dma_verify): scans trail the copy engine on their own stream; events are recycled
     cudaStream_t verify_stream = nullptr;
+    std::mutex dma_mu;  // one copy-engine pull is issued at a time per sink GPU (event ring, verify-stream order)
     std::vector<cudaEvent_t> dma_events;
     size_t dma_ev_next = 0;
     cudaEvent_t next_dma_event() {
@@ -383,6 +384,7 @@ std::vector<uint64_t> dma_schedule(uint64_t nbytes) {
 }
 
 int launch_dma_verify(DeviceCtx& d, const CopyParams& whole, cudaStream_t st) {
+    std::lock_guard<std::mutex> issue(d.dma_mu);
     cudaStream_t vs = d.verify_stream;
     // earlier chunks of this transfer (and the recycling of the sink frame) are ordered on `st`
     cudaEvent_t ev = d.next_dma_event();

@@ -1,11 +1,13 @@
 """The reference's gRPC surface for this path, served from the B200 data plane:
 ``LzySlotsApi`` (slots-api.proto:13-47), ``LzyChannelManager`` (channel-manager.proto:13-95) and
-``LzyChannelManagerPrivate`` (channel-manager-private.proto:13-84), wire-compatible with the
+``LzyChannelManagerPrivate`` (channel-manager-private.proto:13-84), plus (§8f rank 4) ``WorkerApi``
+(worker-service.proto:14-53) with ``LongRunningService.Get`` for its operations — wire-compatible with the
 reference's stubs.  Control messages only: payload bytes move by the CUDA kernels; ``Read`` exists
 for *legacy* CPU consumers and streams 2 MiB chunks + EOS out of HBM."""
 from .protos import messages, method_types
-from .server import ChannelManagerService, SlotsApiService, serve
-from .client import ChannelManagerClient, ChannelManagerPrivateClient, SlotsApiClient
+from .server import ChannelManagerService, LongRunningService, SlotsApiService, WorkerApiService, serve
+from .client import ChannelManagerClient, ChannelManagerPrivateClient, LongRunningClient, SlotsApiClient, WorkerApiClient
 
 __all__ = ["messages", "method_types", "ChannelManagerService", "SlotsApiService", "serve", "ChannelManagerClient",
-           "ChannelManagerPrivateClient", "SlotsApiClient"]
+           "ChannelManagerPrivateClient", "SlotsApiClient", "WorkerApiService", "LongRunningService", "WorkerApiClient",
+           "LongRunningClient"]

@@ -51,3 +51,11 @@ class ChannelManagerClient(_Client):
 
 class ChannelManagerPrivateClient(_Client):
     SERVICE = "ai.lzy.v1.channel.LzyChannelManagerPrivate"
+
+
+class WorkerApiClient(_Client):
+    SERVICE = "ai.lzy.v1.worker.WorkerApi"
+
+
+class LongRunningClient(_Client):
+    SERVICE = "ai.lzy.v1.longrunning.LongRunningService"

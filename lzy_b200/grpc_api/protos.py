@@ -7,6 +7,11 @@
   ai/lzy/v1/slots/slots-api.proto:23-47        StartTransferRequest/Response, ReadDataRequest, ReadDataChunk
   ai/lzy/v1/channel/channel-manager.proto:27-95            Bind*, Unbind*, GetChannelsStatus*, TransferCompleted*, TransferFailed*
   ai/lzy/v1/channel/channel-manager-private.proto:28-84    GetOrCreate*, Destroy*, DestroyAll*, Status*, List*
+  ai/lzy/v1/common/env.proto:10-52             EnvSpec, PythonEnv, ProcessEnv, LocalModule, DockerCredentials, DockerPullPolicy
+  ai/lzy/v1/common/slot.proto:10-29            Slot{Media, Direction}
+  ai/lzy/v1/common/operation.proto:12-45       Operation, Requirements, SlotToChannelAssignment, TaskDesc, KafkaTopicDescription
+  ai/lzy/v1/worker/worker-service.proto:14-53  WorkerApi: Init*, Execute*
+  ai/lzy/v1/long-running/operation.proto:12-47 LongRunningService.Get, Operation (google.rpc.Status restated: code, message, details)
 
 A message serialized here parses with the reference's generated classes and vice versa (same
 package, names, numbers and types)."""
@@ -124,13 +129,88 @@ _chan.message_type.extend([
 _pool.Add(_chan)
 
 
+# ---- ai.lzy.v1.common: what a task description carries ----------------------------------------------------
+I32, I64, BOOL = F.TYPE_INT32, F.TYPE_INT64, F.TYPE_BOOL
+_task = descriptor_pb2.FileDescriptorProto(name="lzyb/ai/lzy/v1/common/operation.proto", package="ai.lzy.v1.common",
+                                            syntax="proto3", dependency=[_common.name])
+_env_entry = _msg("EnvEntry", [_field("key", 1, STR), _field("value", 2, STR)])
+_env_entry.options.map_entry = True
+_task.enum_type.extend([_enum("DockerPullPolicy", [("UNSPECIFIED", 0), ("ALWAYS", 1), ("IF_NOT_EXISTS", 2)])])
+_task.message_type.extend([
+    _msg("DockerCredentials", [_field("registry_name", 1, STR), _field("username", 2, STR), _field("password", 3, STR)]),
+    _msg("LocalModule", [_field("name", 1, STR), _field("uri", 2, STR)]),
+    _msg("PythonEnv", [_field("name", 1, STR), _field("yaml", 2, STR),
+                       _field("local_modules", 3, MSG, ".ai.lzy.v1.common.LocalModule", REP)]),
+    _msg("ProcessEnv", []),
+    _msg("EnvSpec", [_field("docker_pull_policy", 1, ENUM, ".ai.lzy.v1.common.DockerPullPolicy"),
+                     _field("docker_credentials", 2, MSG, ".ai.lzy.v1.common.DockerCredentials"),
+                     _field("docker_image", 3, STR),
+                     _field("env", 4, MSG, ".ai.lzy.v1.common.EnvSpec.EnvEntry", REP),
+                     _field("pyenv", 5, MSG, ".ai.lzy.v1.common.PythonEnv", oneof=0),
+                     _field("process_env", 6, MSG, ".ai.lzy.v1.common.ProcessEnv", oneof=0)],
+         oneofs=["execution_context"], nested=[_env_entry]),
+    _msg("Slot", [_field("name", 1, STR), _field("media", 2, ENUM, ".ai.lzy.v1.common.Slot.Media"),
+                  _field("contentType", 3, MSG, DS), _field("direction", 4, ENUM, ".ai.lzy.v1.common.Slot.Direction")],
+         enums=[_enum("Media", [("UNSPECIFIED", 0), ("FILE", 1), ("PIPE", 2), ("ARG", 3)]),
+                _enum("Direction", [("UNKNOWN", 0), ("INPUT", 1), ("OUTPUT", 2)])]),
+    _msg("KafkaTopicDescription", [_field("bootstrap_servers", 1, STR, label=REP), _field("username", 2, STR),
+                                   _field("password", 3, STR), _field("topic", 4, STR)]),
+    _msg("Requirements", [_field("pool_label", 1, STR), _field("zone", 2, STR)]),
+    _msg("Operation", [_field("env", 1, MSG, ".ai.lzy.v1.common.EnvSpec"),
+                       _field("requirements", 2, MSG, ".ai.lzy.v1.common.Requirements"), _field("command", 3, STR),
+                       _field("slots", 4, MSG, ".ai.lzy.v1.common.Slot", REP), _field("description", 5, STR),
+                       _field("name", 6, STR), _field("kafka_topic", 9, MSG, ".ai.lzy.v1.common.KafkaTopicDescription")]),
+    _msg("SlotToChannelAssignment", [_field("slot_name", 1, STR), _field("channel_id", 2, STR)]),
+    _msg("TaskDesc", [_field("operation", 2, MSG, ".ai.lzy.v1.common.Operation"),
+                      _field("slot_assignments", 3, MSG, ".ai.lzy.v1.common.SlotToChannelAssignment", REP)]),
+])
+_pool.Add(_task)
+
+# ---- google.rpc.Status + ai.lzy.v1.longrunning ---------------------------------------------------------------
+from google.protobuf import any_pb2, timestamp_pb2  # noqa: E402
+
+for _wkt in (any_pb2, timestamp_pb2):
+    _pool.AddSerializedFile(_wkt.DESCRIPTOR.serialized_pb)
+_rpc = descriptor_pb2.FileDescriptorProto(name="lzyb/google/rpc/status.proto", package="google.rpc", syntax="proto3",
+                                           dependency=["google/protobuf/any.proto"])
+_rpc.message_type.extend([_msg("Status", [_field("code", 1, I32), _field("message", 2, STR),
+                                          _field("details", 3, MSG, ".google.protobuf.Any", REP)])])
+_pool.Add(_rpc)
+_lro = descriptor_pb2.FileDescriptorProto(name="lzyb/ai/lzy/v1/long-running/operation.proto", package="ai.lzy.v1.longrunning",
+                                           syntax="proto3",
+                                           dependency=["google/protobuf/any.proto", "google/protobuf/timestamp.proto", _rpc.name])
+_lro.message_type.extend([
+    _msg("Operation", [_field("id", 1, STR), _field("description", 2, STR),
+                       _field("created_at", 3, MSG, ".google.protobuf.Timestamp"), _field("created_by", 4, STR),
+                       _field("modified_at", 5, MSG, ".google.protobuf.Timestamp"), _field("done", 6, BOOL),
+                       _field("metadata", 7, MSG, ".google.protobuf.Any"),
+                       _field("error", 8, MSG, ".google.rpc.Status", oneof=0),
+                       _field("response", 9, MSG, ".google.protobuf.Any", oneof=0)], oneofs=["result"]),
+    _msg("GetOperationRequest", [_field("operation_id", 1, STR)]),
+])
+_pool.Add(_lro)
+
+# ---- ai.lzy.v1.worker ----------------------------------------------------------------------------------------
+_worker = descriptor_pb2.FileDescriptorProto(name="lzyb/ai/lzy/v1/worker/worker-service.proto", package="ai.lzy.v1.worker",
+                                              syntax="proto3", dependency=[_task.name, _lro.name])
+_worker.message_type.extend([
+    _msg("InitRequest", [_field("user_id", 1, STR), _field("workflow_name", 2, STR), _field("worker_subject_name", 3, STR),
+                         _field("worker_private_key", 4, STR)]),
+    _msg("InitResponse", []),
+    _msg("ExecuteRequest", [_field("task_desc", 1, MSG, ".ai.lzy.v1.common.TaskDesc"), _field("task_id", 2, STR),
+                            _field("execution_id", 3, STR), _field("workflow_name", 4, STR), _field("user_id", 5, STR)]),
+    _msg("ExecuteResponse", [_field("rc", 1, I32), _field("description", 2, STR)]),
+])
+_pool.Add(_worker)
+
+
 def _cls(full_name):
     return message_factory.GetMessageClass(_pool.FindMessageTypeByName(full_name))
 
 
 class _Messages:
     """attribute access to message classes: ``messages.BindRequest``, ``messages.PeerDescription`` …"""
-    _packages = ("ai.lzy.v1.common", "ai.lzy.v1.slots", "ai.lzy.v1.channel")
+    _packages = ("ai.lzy.v1.common", "ai.lzy.v1.slots", "ai.lzy.v1.channel", "ai.lzy.v1.worker")
 
     def __getattr__(self, name):
         for pkg in self._packages:
@@ -144,6 +224,9 @@ class _Messages:
 
 
 messages = _Messages()
+LongRunningOperation = _cls("ai.lzy.v1.longrunning.Operation")   # (common also has an `Operation`: the task's)
+GetOperationRequest = _cls("ai.lzy.v1.longrunning.GetOperationRequest")
+RpcStatus = _cls("google.rpc.Status")
 
 # service → method → (request class name, response class name, server-streaming?)
 SERVICES: Dict[str, Dict[str, Tuple[str, str, bool]]] = {
@@ -165,9 +248,17 @@ SERVICES: Dict[str, Dict[str, Tuple[str, str, bool]]] = {
         "Status": ("StatusRequest", "StatusResponse", False),
         "List": ("ListRequest", "ListResponse", False),
     },
+    "ai.lzy.v1.worker.WorkerApi": {
+        "Init": ("InitRequest", "InitResponse", False),
+        "Execute": ("ExecuteRequest", "ai.lzy.v1.longrunning.Operation", False),
+    },
+    "ai.lzy.v1.longrunning.LongRunningService": {
+        "Get": ("ai.lzy.v1.longrunning.GetOperationRequest", "ai.lzy.v1.longrunning.Operation", False),
+    },
 }
 
 
 def method_types(service: str, method: str):
     req, resp, streaming = SERVICES[service][method]
-    return getattr(messages, req), getattr(messages, resp), streaming
+    resolve = lambda n: _cls(n) if "." in n else getattr(messages, n)  # noqa: E731
+    return resolve(req), resolve(resp), streaming

@@ -11,7 +11,7 @@ import grpc
 
 from .. import _host as H
 from .. import _native as N
-from .protos import SERVICES, messages, method_types
+from .protos import SERVICES, LongRunningOperation, messages, method_types
 
 READ_CHUNK = 2 << 20  # OutputSlot.java:241
 _STATUS = {N.E_NOT_FOUND: grpc.StatusCode.NOT_FOUND, N.E_PRECONDITION: grpc.StatusCode.FAILED_PRECONDITION,
@@ -58,12 +58,23 @@ def _status_to_proto(st: dict):
 
 
 class SlotsApiService:
+    """`slots` is a `_host.Slots`, or a `lzy_b200.worker.Worker` whose slots server exists only after
+    WorkerApi.Init — until then both calls answer UNAVAILABLE (WorkerTests.java:261-268)."""
     SERVICE = "ai.lzy.v1.slots.LzySlotsApi"
 
-    def __init__(self, slots: H.Slots):
-        self.slots = slots
+    def __init__(self, slots):
+        self._source = slots
+
+    @property
+    def slots(self) -> H.Slots:
+        return self._source if isinstance(self._source, H.Slots) else self._source.slots
+
+    def _available(self, context) -> None:
+        if self.slots is None:
+            context.abort(grpc.StatusCode.UNAVAILABLE, "worker is not initialized")
 
     def StartTransfer(self, request, context):
+        self._available(context)
         try:
             self.slots.start_transfer(request.slot_id, _peer_from_proto(request.peer), request.transfer_id)
         except N.LzybError as e:
@@ -71,6 +82,7 @@ class SlotsApiService:
         return messages.StartTransferResponse()
 
     def Read(self, request, context) -> Iterable:
+        self._available(context)
         offset = int(request.offset)
         try:
             while True:
@@ -172,6 +184,66 @@ class ChannelManagerService:
         return resp
 
 
+def _operation_to_proto(op):
+    """worker.Operation → ai.lzy.v1.longrunning.Operation; the result is ``response = Any(ExecuteResponse)``
+    as declared by the ``(ai.lzy.v1.operation)`` option of WorkerApi.Execute (worker-service.proto:17-22)"""
+    p = LongRunningOperation(id=op.id, description=op.description, created_by=op.created_by, done=op.done)
+    p.created_at.FromNanoseconds(int(op.created_at * 1e9))
+    p.modified_at.FromNanoseconds(int(op.modified_at * 1e9))
+    if op.error is not None:
+        p.error.code, p.error.message = op.error
+    elif op.response is not None:
+        p.response.Pack(messages.ExecuteResponse(rc=op.response.rc, description=op.response.description))
+    return p
+
+
+def _worker_abort(context, err):
+    context.abort(getattr(grpc.StatusCode, err.code, grpc.StatusCode.INTERNAL), err.message)
+
+
+class WorkerApiService:
+    """ai.lzy.v1.worker.WorkerApi over `lzy_b200.worker.Worker` (WorkerApiImpl.java:85-141,232-283)."""
+    SERVICE = "ai.lzy.v1.worker.WorkerApi"
+
+    def __init__(self, worker):
+        self.worker = worker
+
+    def Init(self, request, context):
+        from ..worker import WorkerStatusError
+        try:
+            self.worker.init(request.user_id, request.workflow_name, request.worker_subject_name, request.worker_private_key)
+        except WorkerStatusError as e:
+            _worker_abort(context, e)
+        return messages.InitResponse()
+
+    def Execute(self, request, context):
+        from ..worker import SlotSpec, TaskSpec, WorkerStatusError
+        op = request.task_desc.operation
+        task = TaskSpec(task_id=request.task_id, execution_id=request.execution_id, workflow_name=request.workflow_name,
+                        user_id=request.user_id, command=op.command, name=op.name, env=op.env,
+                        slots=[SlotSpec(s.name, int(s.direction)) for s in op.slots],
+                        slot_assignments={a.slot_name: a.channel_id for a in request.task_desc.slot_assignments})
+        try:
+            return _operation_to_proto(self.worker.execute(task, _idk(context)))
+        except WorkerStatusError as e:
+            _worker_abort(context, e)
+
+
+class LongRunningService:
+    """ai.lzy.v1.longrunning.LongRunningService.Get for the worker's operations (what the graph executor polls)."""
+    SERVICE = "ai.lzy.v1.longrunning.LongRunningService"
+
+    def __init__(self, worker):
+        self.worker = worker
+
+    def Get(self, request, context):
+        from ..worker import WorkerStatusError
+        try:
+            return _operation_to_proto(self.worker.get_operation(request.operation_id))
+        except WorkerStatusError as e:
+            _worker_abort(context, e)
+
+
 def _generic_handler(service: str, impl) -> grpc.GenericRpcHandler:
     handlers: Dict[str, grpc.RpcMethodHandler] = {}
     for method in SERVICES[service]:
@@ -183,7 +255,7 @@ def _generic_handler(service: str, impl) -> grpc.GenericRpcHandler:
 
 
 def serve(address: str = "127.0.0.1:0", slots: Optional[H.Slots] = None, cm: Optional[H.ChannelManager] = None,
-          max_workers: int = 8):
+          max_workers: int = 8, worker=None):
     """start a server with whichever services were given; returns (server, bound port)"""
     server = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers),
                          options=[("grpc.max_send_message_length", 8 << 20), ("grpc.max_receive_message_length", 8 << 20)])
@@ -192,6 +264,11 @@ def serve(address: str = "127.0.0.1:0", slots: Optional[H.Slots] = None, cm: Opt
     if cm is not None:
         svc = ChannelManagerService(cm)
         server.add_generic_rpc_handlers((_generic_handler(svc.SERVICE, svc), _generic_handler(svc.PRIVATE_SERVICE, svc)))
+    if worker is not None:
+        if slots is None:
+            server.add_generic_rpc_handlers((_generic_handler(SlotsApiService.SERVICE, SlotsApiService(worker)),))
+        server.add_generic_rpc_handlers((_generic_handler(WorkerApiService.SERVICE, WorkerApiService(worker)),
+                                         _generic_handler(LongRunningService.SERVICE, LongRunningService(worker))))
     port = server.add_insecure_port(address)
     server.start()
     return server, port

@@ -24,6 +24,8 @@ def load():
     lib.hostmem_write.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
     lib.hostmem_peek.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
     lib.hostmem_peek.restype = C.c_int64
+    lib.hostmem_size.argtypes = [C.c_uint64]
+    lib.hostmem_size.restype = C.c_int64
     lib.hostmem_set_fail_after.argtypes = [C.c_uint64, C.c_longlong]
     lib.hostmem_set_fail_read.argtypes = [C.c_uint64, C.c_int]
     lib.hostmem_corrupt.argtypes = [C.c_uint64, C.c_uint64]
@@ -53,3 +55,33 @@ def peek(h, n, offset=0) -> bytes:
     got = load().hostmem_peek(h, offset, buf, n)
     assert got >= 0
     return buf.raw[:got]
+
+
+def size(h) -> int:
+    n = load().hostmem_size(h)
+    assert n >= 0
+    return int(n)
+
+
+class HostmemMount:
+    """Test stand-in for `lzy_b200.api.v1.startup.FrameMount`: slot paths resolve to the in-memory backend's
+    slots of one execution context and objects cross as their serializers' byte streams."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def read(self, path, typ, serializers):
+        from io import BytesIO
+        h = self.ctx.input_handle(path)
+        ser = serializers.find_serializer_by_type(typ)
+        return ser.deserialize(BytesIO(peek(h, size(h))), typ if isinstance(typ, type) else None)
+
+    def write(self, path, typ, data, serializers):
+        from io import BytesIO
+        ser = serializers.find_serializer_by_type(typ)
+        buf = BytesIO()
+        ser.serialize(data, buf)
+        raw = buf.getvalue()
+        h = self.ctx.output_open(path, len(raw))
+        write(h, raw)
+        self.ctx.output_done(path)

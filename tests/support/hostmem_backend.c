@@ -341,6 +341,13 @@ int64_t hostmem_peek(lzyb_handle_t h, uint64_t off, void* dst, uint64_t len) {
     pthread_mutex_unlock(&g_mu);
     return rc;
 }
+int64_t hostmem_size(lzyb_handle_t h) {
+    pthread_mutex_lock(&g_mu);
+    mem_slot_t* s = find(h);
+    int64_t rc = s ? (int64_t)s->nbytes : -1;
+    pthread_mutex_unlock(&g_mu);
+    return rc;
+}
 int hostmem_set_fail_after(lzyb_handle_t h, long long n) {
     pthread_mutex_lock(&g_mu);
     mem_slot_t* s = find(h);

@@ -1,0 +1,157 @@
+"""The op-side entry point (`lzy_b200.api.v1.startup`) against the reference's own startup tests
+(pylzy/tests/api/v1/test_startup.py:15-83: test_startup, test_startup_with_exception) and the invariants of
+SURVEY Appendix A.1 that live in it (lazy arguments, result type check, None in the exception slot on
+success, results from the main process only).  The mount is a dict of byte streams — the role the temp files
+under ``_lzy_mount`` play in the reference's tests."""
+import os
+import traceback
+from io import BytesIO
+from tempfile import NamedTemporaryFile
+
+import pytest
+
+from lzy_b200.api.v1 import startup
+from lzy_b200.api.v1.startup import ProcessingRequest, SlotMount
+from lzy_b200.api.v1.utils.pickle import pickle, unpickle
+from lzy_b200.serialization.registry import LzySerializerRegistry
+from lzy_b200.types import File
+
+
+class BytesMount(SlotMount):
+    def __init__(self):
+        self.files = {}
+        self.reads = []
+
+    def put(self, path, typ, value, ser):
+        buf = BytesIO()
+        ser.find_serializer_by_type(typ).serialize(value, buf)
+        self.files[path] = buf.getvalue()
+
+    def get(self, path, typ, ser):
+        return ser.find_serializer_by_type(typ).deserialize(BytesIO(self.files[path]), typ if isinstance(typ, type) else None)
+
+    def read(self, path, typ, serializers):
+        self.reads.append(path)
+        return self.get(path, typ, serializers)
+
+    def write(self, path, typ, data, serializers):
+        self.put(path, typ, data, serializers)
+
+
+def request(op, ser, **kw):
+    base = dict(logger_config={}, serializers=ser.imports(), op=op, args_paths=[], kwargs_paths={}, output_paths=[],
+                exception_path=(tuple, "/c/exc"))
+    base.update(kw)
+    return ProcessingRequest(**base)
+
+
+def test_pickled_request_round_trips_as_ascii():
+    s = pickle({"a": (1, 2.5, "x")})
+    assert s.isascii() and " " not in s and unpickle(s) == {"a": (1, 2.5, "x")}
+
+
+def test_startup():
+    def test(a: str, *, b: File) -> str:
+        with b.open("r") as f:
+            return a + f.readline()
+
+    with NamedTemporaryFile() as data_file:
+        with open(data_file.name, "w") as f:
+            f.write("2")
+        ser, mount = LzySerializerRegistry(), BytesMount()
+        mount.put("/c/a", str, "4", ser)
+        mount.put("/c/b", File, File(data_file.name), ser)
+        req = request(test, ser, args_paths=[(str, "/c/a")], kwargs_paths={"b": (File, "/c/b")}, output_paths=[(str, "/c/ret")])
+        startup.main(pickle(req), mount)
+        assert mount.get("/c/ret", str, ser) == "42"
+        assert mount.get("/c/exc", type(None), ser) is None  # success leaves None in the exception slot
+
+
+def test_startup_with_exception():
+    def test() -> None:
+        raise ValueError("test")
+
+    ser, mount = LzySerializerRegistry(), BytesMount()
+    req = request(test, ser)
+    original_traceback = None
+    try:
+        startup.main(pickle(req), mount)
+    except ValueError as e:
+        original_traceback = e.__traceback__
+    assert original_traceback is not None
+    exc = mount.get("/c/exc", tuple, ser)
+    assert type(exc[1]) is ValueError and exc[1].args == ("test",)
+    current = traceback.extract_tb(exc[2])
+    assert traceback.extract_tb(original_traceback)[-len(current):] == current
+    assert "/c/ret" not in mount.files
+
+
+def test_lazy_arguments_are_read_on_first_touch_and_only_once():
+    def op(a: str, b: str) -> str:
+        lazy = type(a) is not str  # a proxy, not the object (tests/core/test_workflow.py:386-403)
+        return f"{lazy}:{a + a}"  # b is never touched
+
+    ser, mount = LzySerializerRegistry(), BytesMount()
+    mount.put("/c/a", str, "x", ser)
+    mount.put("/c/b", str, "y", ser)
+    req = request(op, ser, args_paths=[(str, "/c/a"), (str, "/c/b")], output_paths=[(str, "/c/ret")], lazy_arguments=True)
+    startup.main(pickle(req), mount)
+    assert mount.reads == ["/c/a"] and mount.get("/c/ret", str, ser) == "True:xx"
+
+    mount.reads.clear()
+    req = request(op, ser, args_paths=[(str, "/c/a"), (str, "/c/b")], output_paths=[(str, "/c/ret")], lazy_arguments=False)
+    startup.main(pickle(req), mount)
+    assert mount.reads == ["/c/a", "/c/b"] and mount.get("/c/ret", str, ser) == "False:xx"
+
+
+def test_returning_a_lazy_argument_writes_the_real_object():
+    def ident(a: str) -> str:
+        return a
+
+    ser, mount = LzySerializerRegistry(), BytesMount()
+    mount.put("/c/a", str, "payload", ser)
+    req = request(ident, ser, args_paths=[(str, "/c/a")], output_paths=[(str, "/c/ret")])
+    startup.main(pickle(req), mount)
+    assert mount.get("/c/ret", str, ser) == "payload"
+
+
+def test_wrong_result_type_goes_to_the_exception_slot():
+    def bad() -> int:
+        return "not an int"  # type: ignore[return-value]
+
+    ser, mount = LzySerializerRegistry(), BytesMount()
+    req = request(bad, ser, output_paths=[(int, "/c/ret")])
+    with pytest.raises(TypeError, match="Invalid types"):
+        startup.main(pickle(req), mount)
+    exc = mount.get("/c/exc", tuple, ser)
+    assert exc[0] is TypeError and "/c/ret" not in mount.files
+
+
+def test_multiple_outputs_are_zipped_with_their_slots():
+    def two() -> (int, str):
+        return 7, "seven"
+
+    ser, mount = LzySerializerRegistry(), BytesMount()
+    req = request(two, ser, output_paths=[(int, "/c/r0"), (str, "/c/r1")])
+    startup.main(pickle(req), mount)
+    assert mount.get("/c/r0", int, ser) == 7 and mount.get("/c/r1", str, ser) == "seven"
+
+
+def test_only_the_main_process_writes_results():
+    def op() -> int:
+        return 1
+
+    ser, mount = LzySerializerRegistry(), BytesMount()
+    os.environ[startup.MAIN_PID_ENV_VAR] = str(os.getpid() + 1)  # as inherited by a replica (DDP) of the op process
+    try:
+        startup.main(pickle(request(op, ser, output_paths=[(int, "/c/ret")])), mount)
+    finally:
+        os.environ.pop(startup.MAIN_PID_ENV_VAR, None)
+    assert mount.files == {}
+    startup.main(pickle(request(op, ser, output_paths=[(int, "/c/ret")])), mount)
+    assert mount.get("/c/ret", int, ser) == 1 and startup.MAIN_PID_ENV_VAR not in os.environ
+
+
+def test_main_needs_a_mount():
+    with pytest.raises(AssertionError, match="no slot mount"):
+        startup.main("AAAA")
