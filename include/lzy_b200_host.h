@@ -142,6 +142,8 @@ typedef struct lzyb_backend_ops {
     int (*input_to_output)(lzyb_handle_t h);
     int (*input_reset)(lzyb_handle_t h);
     int (*slot_retain)(lzyb_handle_t h);
+    /* optional (may be NULL): dtype / shape of a frame that is being filled from storage */
+    int (*slot_set_meta)(lzyb_handle_t h, uint32_t dtype, uint32_t ndim, const uint64_t* shape);
 } lzyb_backend_ops_t;
 int lzyb_slots_set_backend(const lzyb_backend_ops_t* ops); /* NULL = the HBM backend */
 
@@ -204,6 +206,21 @@ int lzyb_frame_store_drop(const char* uri);
 /* drop every frame whose URI starts with `prefix` (NULL/"" = all); returns how many were dropped */
 int lzyb_frame_store_clear(const char* prefix);
 int64_t lzyb_frame_store_bytes(void);
+/* Spill tier below the frame store — the part of the reference's storage peers that outlives HBM residency
+ * (BACKUP producers, PeerDao.java:44-53; cached op results under stable URIs, core/workflow.py:247-281).
+ * set_spill: directory for spilled frames (NULL / "" switches the tier off) and the GPU a frame is loaded
+ * onto when nobody says otherwise.  spill: write the resident frame at `uri` to <dir>/<escaped uri> as
+ * [128-byte lzyb_frame_header_t][payload] (temp file + rename; keeps the frame resident).  get falls back to
+ * the tier: a URI that is not resident but has a spill file is read into a fresh frame — digest verified
+ * against the header while it lands, LZYB_E_PEER if the file is corrupt — registered and returned; load does
+ * the same onto a chosen GPU.  spilled: 1 / 0.  unspill: delete the file.  A file without the frame magic is a
+ * foreign object: its bytes become a DT_BYTES payload whose digest is computed on the way in. */
+int lzyb_frame_store_set_spill(const char* dir, int default_gpu);
+int lzyb_frame_store_spill(const char* uri);
+int lzyb_frame_store_load(const char* uri, int gpu, lzyb_handle_t* slot_out);
+int lzyb_frame_store_spilled(const char* uri);
+int lzyb_frame_store_resident(const char* uri);   /* 1 / 0; never loads */
+int lzyb_frame_store_unspill(const char* uri);
 /* republish delivered inputs as "<slot>-out" producers (InputSlot.java:160-168); default on.  The
  * Python runtime turns it off so that an op owns its input frame and may mutate it in place. */
 int lzyb_slots_set_republish(lzyb_handle_t slots, int on);

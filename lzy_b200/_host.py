@@ -84,6 +84,12 @@ _SIGS = {
     "lzyb_frame_store_drop": (_i, [_s]),
     "lzyb_frame_store_clear": (_i, [_s]),
     "lzyb_frame_store_bytes": (C.c_int64, []),
+    "lzyb_frame_store_set_spill": (_i, [_s, C.c_int]),
+    "lzyb_frame_store_spill": (_i, [_s]),
+    "lzyb_frame_store_load": (_i, [_s, C.c_int, C.POINTER(_H)]),
+    "lzyb_frame_store_spilled": (_i, [_s]),
+    "lzyb_frame_store_resident": (_i, [_s]),
+    "lzyb_frame_store_unspill": (_i, [_s]),
     "lzyb_slots_set_republish": (_i, [_H, _i]),
     "lzyb_graph_create": (_i, [_i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i, _i, C.POINTER(_H)]),
     "lzyb_graph_free": (_i, [_H]),
@@ -338,6 +344,36 @@ def frame_store_clear(prefix: str = "") -> int:
 
 def frame_store_bytes() -> int:
     return int(lib.lzyb_frame_store_bytes())
+
+
+def frame_store_set_spill(directory: Optional[str], default_gpu: int = 0) -> None:
+    """the tier below HBM residency: spilled frames live as files under `directory` (None switches it off)"""
+    _check(lib.lzyb_frame_store_set_spill(_b(directory or ""), default_gpu))
+
+
+def frame_store_spill(uri: str) -> None:
+    _check(lib.lzyb_frame_store_spill(_b(uri)))
+
+
+def frame_store_load(uri: str, gpu: int) -> Optional[int]:
+    h = _H()
+    rc = lib.lzyb_frame_store_load(_b(uri), gpu, C.byref(h))
+    if rc == N.E_NOT_FOUND:
+        return None
+    _check(rc)
+    return h.value
+
+
+def frame_store_spilled(uri: str) -> bool:
+    return _check(lib.lzyb_frame_store_spilled(_b(uri))) == 1
+
+
+def frame_store_resident(uri: str) -> bool:
+    return _check(lib.lzyb_frame_store_resident(_b(uri))) == 1
+
+
+def frame_store_unspill(uri: str) -> None:
+    _check(lib.lzyb_frame_store_unspill(_b(uri)))
 
 
 class ExecutionContext:

@@ -64,7 +64,9 @@ class B200RuntimeConfig:
     fanout_chunk_bytes: int = 0                  # 0 = device-chained kernel; > 0 = host-driven chain with that chunk size
     retain: str = "auto"                         # "auto": a frame is freed once no proxy / queued call can ask for it; "all": keep until clear()
     chunk_bytes: int = 0                         # 0 = one launch per transfer; the reference streams 2 MiB chunks
-    copy_engine: str = "auto"                    # "auto" | "ldg" | "tma"
+    copy_engine: str = "auto"                    # "auto" | "ldg" | "tma" | "dma"
+    spill_dir: Optional[str] = None              # tier below HBM: evicted frames and cache=True results live here as files
+    hbm_budget_bytes: int = 0                    # resident frame-store bytes above which LRU frames are evicted (0 = never)
     user_id: str = field(default_factory=lambda: os.environ.get("LZY_USER", "local-user"))
 
 
@@ -120,8 +122,11 @@ class B200Runtime(Runtime):
                 first, last = min(self.config.gpus), max(self.config.gpus)
                 N.init(first, last - first + 1, self.config.host_ring_bytes)
                 self.gpus = list(self.config.gpus)
-            N.set_copy_engine({"auto": N.ENGINE_AUTO, "ldg": N.ENGINE_LDG, "tma": N.ENGINE_TMA}[self.config.copy_engine])
+            N.set_copy_engine({"auto": N.ENGINE_AUTO, "ldg": N.ENGINE_LDG, "tma": N.ENGINE_TMA,
+                               "dma": N.ENGINE_DMA}[self.config.copy_engine])
             self.store = FrameStore(default_gpu=self.gpus[0])
+            if self.config.spill_dir or self.config.hbm_budget_bytes:
+                self.store.configure_tier(self.config.spill_dir, self.config.hbm_budget_bytes)
             self.cm = H.ChannelManager()
             H.pump_start(self.cm)
             for g in self.gpus:

@@ -7,6 +7,12 @@ lzy/lzy-service/.../operations/graph/CreateChannels.java:75-104): data that exis
 runs is a *storage producer* of its channel, and every op output "lands in storage" — except that
 landing means the C++ frame store takes a reference to the producer's frame (``hbm://`` URIs,
 include/lzy_b200_host.h: lzyb_frame_store_*); nothing is copied and nothing leaves HBM.
+
+Below HBM sits an optional *spill tier* (``configure_tier``; lzyb_frame_store_set_spill / spill / load): with an
+HBM budget, the least recently used frames are written to files and dropped from HBM — they stay fetchable under
+the same URI, by clients and by consumers of their channels, exactly like the reference's BACKUP storage
+producers (channel-manager PeerDao.java:44-53) — and ``cache=True`` results are written there as soon as they
+exist, so a later process finds them under their stable URIs (pylzy/lzy/core/workflow.py:247-281) and skips the op.
 """
 from __future__ import annotations
 
@@ -50,6 +56,70 @@ class FrameStore:
         self._lock = threading.RLock()
         self._refs: Dict[str, int] = {}  # how many snapshot entries still need the frame at this URI
         self.bytes_put = 0
+        # spill tier
+        self.spill_dir: Optional[str] = None
+        self.hbm_budget_bytes: int = 0
+        self._durable: set = set()       # URIs whose spill file outlives this process (cache=True results)
+        self._spilled_here: set = set()  # URIs this process spilled to make room: their files go when the data goes
+        self._touch: Dict[str, int] = {}  # uri -> logical time of the last use (LRU order for eviction)
+        self._clock = 0
+        self.evictions = 0
+        self.reloads = 0
+
+    # ---- spill tier ---------------------------------------------------------------------------
+    def configure_tier(self, spill_dir: Optional[str], hbm_budget_bytes: int = 0) -> None:
+        """`spill_dir`: where frames go when they leave HBM (None = no tier: HBM or nothing).
+        `hbm_budget_bytes`: resident bytes above which least-recently-used frames are evicted (0 = never)."""
+        if hbm_budget_bytes and not spill_dir:
+            raise ValueError("an HBM budget needs a spill directory: evicted frames must stay fetchable")
+        H.frame_store_set_spill(spill_dir, self.default_gpu)
+        self.spill_dir, self.hbm_budget_bytes = spill_dir, int(hbm_budget_bytes)
+
+    def _touched(self, uri: str) -> None:
+        self._clock += 1
+        self._touch[uri] = self._clock
+
+    def persist(self, uri: str) -> bool:
+        """write the frame at `uri` to the spill tier and keep the file beyond this process"""
+        if not self.spill_dir:
+            return False
+        with self._lock:
+            self._durable.add(uri)
+        if not H.frame_store_spilled(uri) and H.frame_store_resident(uri):
+            H.frame_store_spill(uri)
+        return H.frame_store_spilled(uri)
+
+    def evict(self, uri: str) -> bool:
+        """spill (if needed) and drop the HBM copy; the URI stays readable"""
+        if not self.spill_dir or not H.frame_store_resident(uri):
+            return False
+        if not H.frame_store_spilled(uri):
+            H.frame_store_spill(uri)
+            with self._lock:
+                self._spilled_here.add(uri)
+        with self._lock:
+            s = self._frames.pop(uri, None)
+        H.frame_store_drop(uri)
+        if s is not None:
+            s.close()
+        self.evictions += 1
+        return True
+
+    def enforce_budget(self, protect: Optional[str] = None) -> int:
+        """evict least-recently-used frames (never `protect`) until the resident bytes fit the budget; returns
+        how many went"""
+        if not self.hbm_budget_bytes or not self.spill_dir:
+            return 0
+        n = 0
+        while H.frame_store_bytes() > self.hbm_budget_bytes:
+            with self._lock:
+                known = (set(self._refs) | set(self._frames)) - {protect}
+                victims = sorted((u for u in known if u not in self._inline), key=lambda u: self._touch.get(u, 0))
+            victim = next((u for u in victims if H.frame_store_resident(u)), None)
+            if victim is None or not self.evict(victim):
+                break
+            n += 1
+        return n
 
     # ---- writing ------------------------------------------------------------------------------
     def pack_object(self, data: Any, typ: Type, registry: SerializerRegistry, slot_factory, stream: int = 0):
@@ -139,6 +209,8 @@ class FrameStore:
                 self._frames[uri] = slot
                 H.frame_store_put(uri, slot.h)
                 self.bytes_put += slot.nbytes
+            self._touched(uri)
+        self.enforce_budget()
         return hexd
 
     def put_inline(self, uri: str, value: Any) -> None:
@@ -161,21 +233,26 @@ class FrameStore:
     # ---- reading ------------------------------------------------------------------------------
     def _slot(self, uri: str) -> Optional[N.SlotHandle]:
         with self._lock:
+            self._touched(uri)
             s = self._frames.get(uri)
             if s is not None:
                 return s
-            h = H.frame_store_get(uri)  # produced by an op: the slots runtime registered it
+            was_resident = H.frame_store_resident(uri)
+            h = H.frame_store_get(uri)  # produced by an op (the slots runtime registered it), or back from the spill tier
             if h is None:
                 return None
+            if not was_resident:
+                self.reloads += 1
             s = N.SlotHandle.adopt(h, owned=True)
             self._frames[uri] = s
             return s
 
     def exists(self, uri: str) -> bool:
         with self._lock:
-            if uri in self._inline:
+            if uri in self._inline or uri in self._frames:
                 return True
-        return self._slot(uri) is not None
+        # resident in the C++ store (an op produced it) or waiting in the spill tier; asking does not load it
+        return H.frame_store_resident(uri) or (self.spill_dir is not None and H.frame_store_spilled(uri))
 
     def unpack_slot(self, slot: N.SlotHandle, typ: Type, registry: SerializerRegistry, private: bool) -> Any:
         info = _InfoView(slot.info())
@@ -207,9 +284,12 @@ class FrameStore:
         if v is _RING:
             import cloudpickle
             return cloudpickle.loads(N.ring_read(off))
+        reloads = self.reloads
         slot = self._slot(uri)
         if slot is None:
             raise ValueError(f"Cannot find blob in storage by uri={uri}")
+        if self.reloads != reloads:
+            self.enforce_budget(protect=uri)  # what came back from the tier pushes something colder out
         return self.unpack_slot(slot, typ, registry, private=False)
 
     def alias(self, from_uri: str, to_uri: str) -> None:
@@ -246,16 +326,21 @@ class FrameStore:
             self._inline.pop(uri, None)
             off = self._ring.pop(uri, None)
             s = self._frames.pop(uri, None)
+            self._touch.pop(uri, None)
+            scratch = uri in self._spilled_here and uri not in self._durable
+            self._spilled_here.discard(uri)
         if off is not None:
             N.ring_release(off)
         H.frame_store_drop(uri)
         if s is not None:
             s.close()
+        if scratch:
+            H.frame_store_unspill(uri)  # an evicted frame nobody can ask for any more; durable files stay
 
     def clear(self, prefix: str = "hbm://") -> None:
         """drop every frame under `prefix`, including op outputs nobody has read yet"""
         with self._lock:
-            uris = [u for u in list(self._frames) + list(self._inline) if u.startswith(prefix)]
+            uris = [u for u in set(self._frames) | set(self._inline) | set(self._spilled_here) if u.startswith(prefix)]
             for u in [u for u in self._refs if u.startswith(prefix)]:
                 self._refs.pop(u, None)
         for u in uris:

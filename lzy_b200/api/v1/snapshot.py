@@ -120,7 +120,11 @@ class FrameSnapshot(Snapshot):
             if entry_id not in self._holds:
                 self._holds[entry_id] = entry._storage_uri
                 self._store.retain(entry._storage_uri)
+            persistent = entry_id in self._persistent
+        if persistent:
+            self._store.persist(entry._storage_uri)  # cache=True: written to the spill tier (if there is one) now
         self._maybe_release(entry_id)
+        self._store.enforce_budget()
 
     def _maybe_release(self, entry_id: str) -> None:
         if not self.auto_release:

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -24,6 +25,10 @@
 #include <thread>
 #include <unordered_map>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../../include/lzy_b200_host.h"
 #include "host_common.h"
@@ -37,7 +42,7 @@ using lzyb_host::scopy;
 const lzyb_backend_ops_t kHbmBackend = {
     lzyb_slot_create, lzyb_input_open,      lzyb_slot_commit,         lzyb_slot_read,       lzyb_slot_info,
     lzyb_slot_find,   lzyb_slot_close,      lzyb_transfer_chunk,      lzyb_input_finish,    lzyb_input_write_host,
-    lzyb_input_finish_expect, lzyb_input_to_output, lzyb_input_reset, lzyb_slot_retain,
+    lzyb_input_finish_expect, lzyb_input_to_output, lzyb_input_reset, lzyb_slot_retain, lzyb_slot_set_meta,
 };
 std::atomic<const lzyb_backend_ops_t*> g_ops{&kHbmBackend};
 lzyb_backend_ops_t g_custom_ops;
@@ -62,10 +67,186 @@ std::shared_ptr<Blob> blob_find(const std::string& uri) {
 std::mutex g_frames_mu;
 std::map<std::string, lzyb_handle_t> g_frames;
 bool is_hbm_uri(const char* uri) { return uri && strncmp(uri, "hbm://", 6) == 0; }
-lzyb_handle_t frame_find(const std::string& uri) {
+lzyb_handle_t frame_resident(const std::string& uri) {
     std::lock_guard<std::mutex> lk(g_frames_mu);
     auto it = g_frames.find(uri);
     return it == g_frames.end() ? 0 : it->second;
+}
+
+// ---- spill tier: frames that left HBM (or another process' HBM) stay fetchable from files ------------------
+std::mutex g_spill_mu;       // guards the configuration
+std::string g_spill_dir;
+int g_spill_gpu = 0;
+std::mutex g_spill_load_mu;  // one load at a time: two consumers of one spilled URI must share the frame
+
+std::string spill_dir() {
+    std::lock_guard<std::mutex> lk(g_spill_mu);
+    return g_spill_dir;
+}
+
+// file name of a URI: readable, collision-free, bounded ('%XX' escapes; long names end in a 128-bit FNV-1a tag)
+std::string spill_path(const std::string& dir, const std::string& uri) {
+    static const char* hex = "0123456789abcdef";
+    std::string name;
+    for (unsigned char c : uri) {
+        if (isalnum(c) || c == '.' || c == '_' || c == '-')
+            name.push_back((char)c);
+        else {
+            name.push_back('%');
+            name.push_back(hex[c >> 4]);
+            name.push_back(hex[c & 15]);
+        }
+    }
+    if (name.size() > 200) {
+        uint64_t h1 = 0xcbf29ce484222325ull, h2 = 0x84222325cbf29ce4ull;
+        for (unsigned char c : uri) {
+            h1 = (h1 ^ c) * 0x100000001b3ull;
+            h2 = (h2 ^ (c + 0x9eull)) * 0x100000001b3ull;
+        }
+        char tag[40];
+        snprintf(tag, sizeof(tag), "-%016llx%016llx", (unsigned long long)h1, (unsigned long long)h2);
+        name = name.substr(0, 160) + tag;
+    }
+    return dir + "/" + name + ".lzyb";
+}
+
+bool read_fully(int fd, void* dst, uint64_t n) {
+    uint8_t* p = static_cast<uint8_t*>(dst);
+    while (n) {
+        ssize_t r = ::read(fd, p, n > (1ull << 30) ? (1ull << 30) : n);
+        if (r <= 0) return false;
+        p += r;
+        n -= (uint64_t)r;
+    }
+    return true;
+}
+
+bool write_fully(int fd, const void* src, uint64_t n) {
+    const uint8_t* p = static_cast<const uint8_t*>(src);
+    while (n) {
+        ssize_t w = ::write(fd, p, n > (1ull << 30) ? (1ull << 30) : n);
+        if (w <= 0) return false;
+        p += w;
+        n -= (uint64_t)w;
+    }
+    return true;
+}
+
+constexpr uint64_t SPILL_STEP = 64ull << 20;
+
+int spill_write(const std::string& path, lzyb_handle_t slot) {
+    lzyb_slot_info_t info;
+    int rc = ops().slot_info(slot, &info);
+    if (rc != LZYB_OK) return rc;
+    if (info.state != LZYB_ST_READY) return fail(LZYB_E_STATE, "only a complete frame can be spilled");
+    lzyb_frame_header_t hdr;
+    memset(&hdr, 0, sizeof(hdr));
+    memcpy(hdr.magic, "LZYB200", 8);
+    hdr.version = LZYB_ABI_VERSION;
+    hdr.dtype = info.dtype;
+    hdr.nbytes = info.nbytes;
+    hdr.ndim = info.ndim;
+    hdr.flags = 1;
+    memcpy(hdr.shape, info.shape, sizeof(hdr.shape));
+    hdr.digest[0] = info.digest[0];
+    hdr.digest[1] = info.digest[1];
+    const std::string tmp = path + ".tmp." + std::to_string((long long)getpid());
+    int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return fail(LZYB_E_LOCAL, "cannot create %s: %s", tmp.c_str(), strerror(errno));
+    bool ok = write_fully(fd, &hdr, sizeof(hdr));
+    std::vector<uint8_t> buf(std::min<uint64_t>(std::max<uint64_t>(info.nbytes, 1), SPILL_STEP));
+    for (uint64_t off = 0; ok && off < info.nbytes;) {
+        int64_t n = ops().slot_read(slot, off, buf.data(), std::min<uint64_t>(info.nbytes - off, buf.size()));
+        if (n <= 0) {
+            ok = false;
+            break;
+        }
+        ok = write_fully(fd, buf.data(), (uint64_t)n);
+        off += (uint64_t)n;
+    }
+    ok = ok && ::fsync(fd) == 0;
+    ::close(fd);
+    if (!ok || ::rename(tmp.c_str(), path.c_str()) != 0) {
+        ::unlink(tmp.c_str());
+        return fail(LZYB_E_LOCAL, "cannot write %s", path.c_str());
+    }
+    return LZYB_OK;
+}
+
+// read a spill file into a fresh frame on `gpu`; the digest computed while the bytes land is checked against
+// the header's (a foreign file has no header: its digest becomes the published one)
+int spill_read(const std::string& path, const std::string& uri, int gpu, lzyb_handle_t* out) {
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return fail(LZYB_E_NOT_FOUND, "no frame at %s", uri.c_str());
+    struct stat st;
+    if (::fstat(fd, &st) != 0) {
+        ::close(fd);
+        return fail(LZYB_E_LOCAL, "cannot stat %s", path.c_str());
+    }
+    lzyb_frame_header_t hdr;
+    memset(&hdr, 0, sizeof(hdr));
+    bool framed = (uint64_t)st.st_size >= sizeof(hdr) && read_fully(fd, &hdr, sizeof(hdr)) && memcmp(hdr.magic, "LZYB200", 8) == 0 &&
+                  hdr.nbytes + sizeof(hdr) == (uint64_t)st.st_size && hdr.ndim <= LZYB_MAX_DIMS;
+    uint64_t nbytes = framed ? hdr.nbytes : (uint64_t)st.st_size;
+    if (!framed) ::lseek(fd, 0, SEEK_SET);
+    static std::atomic<uint64_t> seq{0};
+    const std::string slot_id = "spill/" + std::to_string(++seq) + "/" + uri;
+    lzyb_handle_t h = 0;
+    int rc = ops().input_open(slot_id.c_str(), gpu, nbytes, &h);
+    if (rc != LZYB_OK) {
+        ::close(fd);
+        return rc;
+    }
+    if (framed && ops().slot_set_meta) rc = ops().slot_set_meta(h, hdr.dtype, hdr.ndim, hdr.shape);
+    std::vector<uint8_t> buf(std::min<uint64_t>(std::max<uint64_t>(nbytes, 1), SPILL_STEP));
+    for (uint64_t off = 0; rc == LZYB_OK && off < nbytes;) {
+        const uint64_t step = std::min<uint64_t>(nbytes - off, buf.size());
+        if (!read_fully(fd, buf.data(), step)) {
+            rc = fail(LZYB_E_LOCAL, "short read from %s", path.c_str());
+            break;
+        }
+        int64_t n = ops().input_write_host(h, off, buf.data(), step, nullptr);
+        if (n < 0) {
+            rc = (int)n;
+            break;
+        }
+        off += (uint64_t)n;
+    }
+    ::close(fd);
+    if (rc == LZYB_OK) rc = ops().input_finish_expect(h, framed ? hdr.digest : nullptr, nullptr);
+    if (rc != LZYB_OK) {
+        const std::string why = lzyb_last_error();
+        ops().slot_close(h);
+        return fail(rc, "spilled frame %s is unusable: %s", uri.c_str(), why.c_str());
+    }
+    *out = h;
+    return LZYB_OK;
+}
+
+// resident frame, or — when the spill tier holds the URI — a frame loaded from it (registered, so that every
+// later consumer shares it).  LZYB_E_NOT_FOUND if neither; the loader's error if the file exists but is unusable.
+int frame_lookup(const std::string& uri, int gpu, lzyb_handle_t* out) {
+    if ((*out = frame_resident(uri))) return LZYB_OK;
+    const std::string dir = spill_dir();
+    if (dir.empty()) return LZYB_E_NOT_FOUND;
+    const std::string path = spill_path(dir, uri);
+    if (::access(path.c_str(), R_OK) != 0) return LZYB_E_NOT_FOUND;
+    std::lock_guard<std::mutex> lk(g_spill_load_mu);
+    if ((*out = frame_resident(uri))) return LZYB_OK;
+    if (gpu < 0) {
+        std::lock_guard<std::mutex> cfg(g_spill_mu);
+        gpu = g_spill_gpu;
+    }
+    int rc = spill_read(path, uri, gpu, out);
+    if (rc != LZYB_OK) return rc;
+    std::lock_guard<std::mutex> fl(g_frames_mu);
+    g_frames[uri] = *out;  // the store owns the loader's reference
+    return LZYB_OK;
+}
+
+lzyb_handle_t frame_find(const std::string& uri) {
+    lzyb_handle_t h = 0;
+    return frame_lookup(uri, -1, &h) == LZYB_OK ? h : 0;
 }
 
 // ---- a tiny future -------------------------------------------------------------------------------------
@@ -312,6 +493,10 @@ struct InputTransfer {
 struct SlotPullTransfer : InputTransfer {
     lzyb_handle_t peer = 0;
     uint64_t size = 0;
+    bool retained = false;  // a frame-store frame may be evicted to the spill tier while we read it: hold it
+    ~SlotPullTransfer() override {
+        if (retained) ops().slot_close(peer);
+    }
     int64_t transfer_chunk_to(lzyb_handle_t sink, uint64_t offset, uint64_t max_len) override {
         return ops().transfer_chunk(sink, peer, offset, max_len, nullptr);
     }
@@ -395,14 +580,22 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
     std::unique_ptr<InputTransfer> make_transfer(const lzyb_peer_desc_t& p, std::string& err) {
         // TransferFactory.input(peer, offset)
         if (p.kind == LZYB_PEER_STORAGE && is_hbm_uri(p.url)) {
-            lzyb_handle_t h = frame_find(p.url);
+            // resident, or spilled: then it is loaded straight onto this worker's GPU
+            lzyb_handle_t h = 0;
             lzyb_slot_info_t info;
-            if (!h || ops().slot_info(h, &info) != LZYB_OK) {
-                err = std::string("Error while reading from storage: no frame at ") + p.url;
+            int rc = frame_lookup(p.url, inst->gpu, &h);
+            if (rc != LZYB_OK || ops().slot_retain(h) != LZYB_OK) {
+                err = std::string("Error while reading from storage: ") +
+                      (rc == LZYB_OK || rc == LZYB_E_NOT_FOUND ? std::string("no frame at ") + p.url : std::string(lzyb_last_error()));
                 return nullptr;
             }
             auto t = std::make_unique<SlotPullTransfer>();
             t->peer = h;
+            t->retained = true;
+            if (ops().slot_info(h, &info) != LZYB_OK) {
+                err = std::string("Error while reading from storage: ") + lzyb_last_error();
+                return nullptr;
+            }
             t->size = info.nbytes;
             return t;
         }
@@ -1020,9 +1213,56 @@ int lzyb_frame_store_put(const char* uri, lzyb_handle_t slot) {
 
 int lzyb_frame_store_get(const char* uri, lzyb_handle_t* out) {
     if (!uri || !out) return fail(LZYB_E_ARG, "null argument");
-    lzyb_handle_t h = frame_find(uri);
-    if (!h) return fail(LZYB_E_NOT_FOUND, "no frame at %s", uri);
-    *out = h;
+    int rc = frame_lookup(uri, -1, out);
+    if (rc == LZYB_E_NOT_FOUND) return fail(LZYB_E_NOT_FOUND, "no frame at %s", uri);
+    return rc;  // LZYB_OK, or why an existing spill file could not be used
+}
+
+int lzyb_frame_store_set_spill(const char* dir, int default_gpu) {
+    std::lock_guard<std::mutex> lk(g_spill_mu);
+    if (!dir || !*dir) {
+        g_spill_dir.clear();
+        return LZYB_OK;
+    }
+    if (::mkdir(dir, 0755) != 0 && errno != EEXIST) return fail(LZYB_E_LOCAL, "cannot create %s: %s", dir, strerror(errno));
+    g_spill_dir = dir;
+    g_spill_gpu = default_gpu;
+    return LZYB_OK;
+}
+
+int lzyb_frame_store_spill(const char* uri) {
+    if (!uri) return fail(LZYB_E_ARG, "null argument");
+    const std::string dir = spill_dir();
+    if (dir.empty()) return fail(LZYB_E_STATE, "no spill directory configured");
+    lzyb_handle_t h = frame_resident(uri);
+    if (!h) return fail(LZYB_E_NOT_FOUND, "no resident frame at %s", uri);
+    return spill_write(spill_path(dir, uri), h);
+}
+
+int lzyb_frame_store_load(const char* uri, int gpu, lzyb_handle_t* out) {
+    if (!uri || !out) return fail(LZYB_E_ARG, "null argument");
+    int rc = frame_lookup(uri, gpu, out);
+    if (rc == LZYB_E_NOT_FOUND) return fail(LZYB_E_NOT_FOUND, "no frame at %s", uri);
+    return rc;
+}
+
+int lzyb_frame_store_resident(const char* uri) {
+    if (!uri) return fail(LZYB_E_ARG, "null argument");
+    return frame_resident(uri) ? 1 : 0;
+}
+
+int lzyb_frame_store_spilled(const char* uri) {
+    if (!uri) return fail(LZYB_E_ARG, "null argument");
+    const std::string dir = spill_dir();
+    if (dir.empty()) return 0;
+    return ::access(spill_path(dir, uri).c_str(), R_OK) == 0 ? 1 : 0;
+}
+
+int lzyb_frame_store_unspill(const char* uri) {
+    if (!uri) return fail(LZYB_E_ARG, "null argument");
+    const std::string dir = spill_dir();
+    if (dir.empty()) return LZYB_OK;
+    ::unlink(spill_path(dir, uri).c_str());
     return LZYB_OK;
 }
 

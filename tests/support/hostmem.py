@@ -15,7 +15,8 @@ def load():
         return _lib
     src = Path(__file__).resolve().parent / "hostmem_backend.c"
     libdir = ROOT / "lzy_b200" / "lib"
-    if not _SO.exists() or _SO.stat().st_mtime < src.stat().st_mtime:
+    deps = [src, ROOT / "include" / "lzy_b200.h", ROOT / "include" / "lzy_b200_host.h"]  # the ops table is ABI
+    if not _SO.exists() or _SO.stat().st_mtime < max(d.stat().st_mtime for d in deps):
         _SO.parent.mkdir(exist_ok=True)
         subprocess.run(["gcc", "-O1", "-fPIC", "-shared", "-Wall", "-o", str(_SO), str(src), f"-L{libdir}",
                         "-llzy_b200", f"-Wl,-rpath,{libdir}", "-lpthread"], check=True)
@@ -55,6 +56,18 @@ def peek(h, n, offset=0) -> bytes:
     got = load().hostmem_peek(h, offset, buf, n)
     assert got >= 0
     return buf.raw[:got]
+
+
+def info(h):
+    from lzy_b200 import _native as N
+    out = N.SlotInfo()
+    assert load().hostmem_info(C.c_uint64(h), C.byref(out)) == 0
+    return out
+
+
+def set_meta(h, dtype: int, shape) -> None:
+    arr = (C.c_uint64 * max(1, len(shape)))(*shape)
+    assert load().hostmem_set_meta(C.c_uint64(h), C.c_uint32(dtype), C.c_uint32(len(shape)), arr) == 0
 
 
 def size(h) -> int:

@@ -26,6 +26,8 @@ typedef struct {
     uint64_t nbytes, delivered;
     int state, is_input, gpu;
     uint64_t digest[2];
+    uint32_t dtype, ndim;
+    uint64_t shape[LZYB_MAX_DIMS];
     long long fail_after; /* -1 = never */
     int fail_read;
     int refs;
@@ -162,8 +164,24 @@ static int m_slot_info(lzyb_handle_t h, lzyb_slot_info_t* out) {
     out->delivered = s->delivered;
     out->digest[0] = s->digest[0];
     out->digest[1] = s->digest[1];
+    out->dtype = s->dtype;
+    out->ndim = s->ndim;
+    memcpy(out->shape, s->shape, sizeof(out->shape));
     pthread_mutex_unlock(&g_mu);
     return LZYB_OK;
+}
+
+static int m_slot_set_meta(lzyb_handle_t h, uint32_t dtype, uint32_t ndim, const uint64_t* shape) {
+    pthread_mutex_lock(&g_mu);
+    mem_slot_t* s = find(h);
+    if (s) {
+        s->dtype = dtype;
+        s->ndim = ndim;
+        memset(s->shape, 0, sizeof(s->shape));
+        for (uint32_t i = 0; i < ndim && i < LZYB_MAX_DIMS; ++i) s->shape[i] = shape[i];
+    }
+    pthread_mutex_unlock(&g_mu);
+    return s ? LZYB_OK : err(LZYB_E_ARG, "unknown slot handle");
 }
 
 static int m_slot_find(const char* id, lzyb_handle_t* out) {
@@ -314,7 +332,7 @@ static int m_input_reset(lzyb_handle_t h) {
 const lzyb_backend_ops_t hostmem_backend_ops = {
     m_slot_create,    m_input_open,     m_slot_commit,         m_slot_read,       m_slot_info,
     m_slot_find,      m_slot_close,     m_transfer_chunk,      m_input_finish,    m_input_write_host,
-    m_input_finish_expect, m_input_to_output, m_input_reset, m_slot_retain,
+    m_input_finish_expect, m_input_to_output, m_input_reset, m_slot_retain, m_slot_set_meta,
 };
 
 /* ---- test helpers ---- */
@@ -341,6 +359,10 @@ int64_t hostmem_peek(lzyb_handle_t h, uint64_t off, void* dst, uint64_t len) {
     pthread_mutex_unlock(&g_mu);
     return rc;
 }
+int hostmem_set_meta(lzyb_handle_t h, uint32_t dtype, uint32_t ndim, const uint64_t* shape) {
+    return m_slot_set_meta(h, dtype, ndim, shape);
+}
+int hostmem_info(lzyb_handle_t h, lzyb_slot_info_t* out) { return m_slot_info(h, out); }
 int64_t hostmem_size(lzyb_handle_t h) {
     pthread_mutex_lock(&g_mu);
     mem_slot_t* s = find(h);

@@ -1,0 +1,145 @@
+"""The spill tier below the HBM frame store (include/lzy_b200_host.h: lzyb_frame_store_set_spill / spill / load)
+— SURVEY §8(f) row 3: a frame that left HBM stays fetchable as a BACKUP storage producer
+(channel-manager PeerDao.java:44-53), cached results survive under stable URIs (core/workflow.py:247-281).
+Host logic only, over the in-memory slot backend; the HBM side of the same calls is tests/test_spill_gpu.py."""
+import os
+import struct
+
+import pytest
+
+from lzy_b200 import _host as H
+from lzy_b200 import _native as N
+from lzy_b200._host import DIR_INPUT, DIR_OUTPUT, ChannelManager, Slots
+from tests.support import hostmem
+
+
+@pytest.fixture
+def env(tmp_path):
+    lib = hostmem.install()
+    cm = ChannelManager(seed=4)
+    H.pump_start(cm)
+    slots = Slots(cm, 0, "lzyb://worker-0")
+    H.frame_store_set_spill(str(tmp_path / "spill"), 0)
+    yield cm, slots, lib, tmp_path / "spill"
+    H.frame_store_clear("")
+    H.frame_store_set_spill(None)
+    slots.close()
+    H.pump_stop(cm)
+    cm.close()
+    hostmem.uninstall()
+    assert lib.hostmem_live_slots() == 0, "a slot frame leaked"
+
+
+def produce_to_store(cm, slots, lib, uri, data, dtype=0, shape=()):
+    """an op output whose channel's storage consumer is `uri`: after afterExecution the frame store holds it"""
+    chan = cm.get_or_create("u", "wf", "exec", consumer_uri=uri)
+    ctx = slots.context("exec", "p-" + uri[-6:])
+    ctx.add_slot("out", chan, DIR_OUTPUT)
+    ctx.before_execution()
+    h = ctx.output_open("out", len(data))
+    if shape:
+        hostmem.set_meta(h, dtype, shape)
+    hostmem.write(h, data)
+    ctx.output_done("out")
+    ctx.after_execution(5000)
+    return ctx, chan
+
+
+def test_spill_file_is_header_plus_payload_and_loads_back_verified(env):
+    cm, slots, lib, d = env
+    data = os.urandom((3 << 20) + 7)
+    ctx, _ = produce_to_store(cm, slots, lib, "hbm://t/a", data, dtype=N.DT_F32, shape=(3, 5, 7))
+    assert not H.frame_store_spilled("hbm://t/a")
+    H.frame_store_spill("hbm://t/a")
+    assert H.frame_store_spilled("hbm://t/a")
+    (f,) = list(d.iterdir())
+    raw = f.read_bytes()
+    assert len(raw) == 128 + len(data) and raw[:8] == b"LZYB200\0" and raw[128:] == data
+    version, dtype, nbytes, ndim, flags = struct.unpack_from("<IIQII", raw, 8)
+    assert (version, dtype, nbytes, ndim, flags & 1) == (N.lib.lzyb_abi_version(), N.DT_F32, len(data), 3, 1)
+    assert struct.unpack_from("<3Q", raw, 32) == (3, 5, 7)
+    resident = H.frame_store_get("hbm://t/a")
+    digest = tuple(hostmem.info(resident).digest)
+    assert struct.unpack_from("<2Q", raw, 96) == digest
+
+    ctx.close()
+    H.frame_store_drop("hbm://t/a")  # leaves HBM …
+    assert lib.hostmem_live_slots() == 0
+    h = H.frame_store_get("hbm://t/a")  # … and comes back from the tier, once, verified against the header
+    assert h is not None and h == H.frame_store_get("hbm://t/a")
+    info = hostmem.info(h)
+    assert hostmem.peek(h, len(data)) == data and tuple(info.digest) == digest
+    assert (info.dtype, info.ndim, tuple(info.shape[:3])) == (N.DT_F32, 3, (3, 5, 7))
+
+
+def test_evicted_frame_is_still_a_storage_producer_for_later_consumers(env):
+    """the reference's BACKUP semantics: the op's worker is gone, the channel's storage peer serves the data"""
+    cm, slots, lib, d = env
+    data = os.urandom(1 << 20)
+    ctx, chan = produce_to_store(cm, slots, lib, "hbm://t/evicted", data)
+    H.frame_store_spill("hbm://t/evicted")
+    ctx.close()                              # the slot producer unbinds
+    H.frame_store_drop("hbm://t/evicted")    # and the frame leaves "HBM"
+    cons = slots.context("exec", "late")
+    cons.add_slot("in", chan, DIR_INPUT)
+    cons.before_execution(10000)
+    assert hostmem.peek(cons.input_handle("in"), len(data)) == data
+    cons.close()
+
+
+def test_corrupt_spill_file_is_a_read_error_not_wrong_data(env):
+    cm, slots, lib, d = env
+    data = os.urandom(300_000)
+    ctx, chan = produce_to_store(cm, slots, lib, "hbm://t/rot", data)
+    H.frame_store_spill("hbm://t/rot")
+    ctx.close()
+    H.frame_store_drop("hbm://t/rot")
+    (f,) = list(d.iterdir())
+    raw = bytearray(f.read_bytes())
+    raw[128 + 1234] ^= 0x40
+    f.write_bytes(bytes(raw))
+    with pytest.raises(N.LzybError, match="unusable"):
+        H.frame_store_get("hbm://t/rot")
+    assert lib.hostmem_live_slots() == 0  # the half-filled frame was returned
+
+
+def test_foreign_file_without_header_is_a_bytes_payload(env):
+    """an object some other tool put under the URI's name (no frame magic): payload = the file"""
+    cm, slots, lib, d = env
+    d.mkdir(exist_ok=True)
+    name = "hbm%3a%2f%2ft%2fforeign.lzyb"
+    (d / name).write_bytes(b"plain old bytes")
+    assert H.frame_store_spilled("hbm://t/foreign")
+    h = H.frame_store_get("hbm://t/foreign")
+    assert hostmem.peek(h, 64) == b"plain old bytes"
+    H.frame_store_unspill("hbm://t/foreign")
+    assert not H.frame_store_spilled("hbm://t/foreign") and not (d / name).exists()
+
+
+def test_long_uris_get_bounded_distinct_file_names(env):
+    cm, slots, lib, d = env
+    base = "hbm://bucket/lzy_runs/wf/ops/fn/0.0.1/" + "_".join(["d41d8cd98f00b204e9800998ecf8427e"] * 12)
+    ctxs = []
+    for i in range(2):
+        ctx, _ = produce_to_store(cm, slots, lib, f"{base}/return_{i}", bytes([i]) * 100)
+        H.frame_store_spill(f"{base}/return_{i}")
+        ctxs.append(ctx)
+    names = sorted(p.name for p in d.iterdir())
+    assert len(names) == 2 and all(len(n) < 255 for n in names)
+    for ctx in ctxs:
+        ctx.close()
+    for i in range(2):
+        H.frame_store_drop(f"{base}/return_{i}")
+        assert hostmem.peek(H.frame_store_get(f"{base}/return_{i}"), 100) == bytes([i]) * 100
+
+
+def test_without_a_spill_directory_the_tier_is_off(env):
+    cm, slots, lib, d = env
+    H.frame_store_set_spill(None)
+    ctx, _ = produce_to_store(cm, slots, lib, "hbm://t/x", b"abc" * 100)
+    with pytest.raises(N.LzybError):
+        H.frame_store_spill("hbm://t/x")
+    assert not H.frame_store_spilled("hbm://t/x")
+    ctx.close()
+    H.frame_store_drop("hbm://t/x")
+    assert H.frame_store_get("hbm://t/x") is None
