@@ -81,7 +81,7 @@ typedef struct lzyb_frame_header {
     uint64_t xr;
 } lzyb_frame_header_t;         /* sizeof == 128 */
 
-typedef struct lzyb_slot_info {
+typedef struct lzyb_slot_info_s {
     uint64_t nbytes;
     int32_t gpu;
     int32_t state;             /* enum lzyb_slot_state                                             */
@@ -112,7 +112,7 @@ typedef struct lzyb_ipc_desc {
     uint8_t reserved[64];
 } lzyb_ipc_desc_t;             /* sizeof == 256 */
 
-typedef struct lzyb_stats {
+typedef struct lzyb_stats_s {
     uint64_t kernel_launches;  /* launches of this library's kernels since init / last reset       */
     uint64_t pack_launches;
     uint64_t pull_launches;

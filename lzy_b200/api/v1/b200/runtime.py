@@ -25,6 +25,7 @@ from __future__ import annotations
 import os
 import sys
 import threading
+import time
 import uuid
 from concurrent.futures import FIRST_COMPLETED, ThreadPoolExecutor, wait
 from dataclasses import dataclass, field
@@ -373,6 +374,19 @@ class B200Runtime(Runtime):
                 f.future.set_exception(e)
 
     # ---- one op (WorkerApiImpl.executeOp + startup.process_execution) -------------------------------------
+    def _phase_marker(self, task: int) -> Callable[[str], None]:
+        """LZYB_TRACE=1: (task, phase, ms since the previous mark) records in `self.trace`; otherwise a no-op"""
+        if self.trace is None:
+            return lambda phase: None
+        last = [time.perf_counter()]
+
+        def mark(phase: str) -> None:
+            now = time.perf_counter()
+            self.trace.append((task, phase, 1e3 * (now - last[0])))
+            last[0] = now
+
+        return mark
+
     def _run_task(self, t: int, call: "LzyCall", ctx: H.ExecutionContext, gpu: int, input_eids: List[str],
                   fanout: Optional[Dict[str, _Fanout]] = None) -> None:
         import torch
@@ -380,14 +394,10 @@ class B200Runtime(Runtime):
         assert wf is not None and self.store is not None
         snapshot, registry = wf.snapshot, wf.owner.serializer_registry
         exc_uri = snapshot.get(call.exception_id).storage_uri
-        import time as _time
-        tr = self.trace
-        _t0 = _time.perf_counter()
+        mark = self._phase_marker(t)
         try:
             ctx.before_execution(-1)  # every input fully delivered and verified
-            if tr is not None:
-                tr.append((t, "before_execution", 1e3 * (_time.perf_counter() - _t0)))
-                _t0 = _time.perf_counter()
+            mark("before_execution")
             values: Dict[str, Any] = {}
 
             def load(eid: str) -> Any:
@@ -420,9 +430,7 @@ class B200Runtime(Runtime):
             finally:
                 op_scope.leave()
 
-            if tr is not None:
-                tr.append((t, "load+op", 1e3 * (_time.perf_counter() - _t0)))
-                _t0 = _time.perf_counter()
+            mark("load+op")
             outs = call.entry_ids
             results = [res] if len(outs) == 1 else list(res)
             with torch.cuda.device(gpu), torch.cuda.stream(stream):
@@ -443,12 +451,9 @@ class B200Runtime(Runtime):
                     slot = self.store.pack_object(data, entry.typ, registry, factory, sp)
                     ctx.output_done(name)
                     values[f"out:{eid}"] = slot  # keep the packed source alive until the commit
-            if tr is not None:
-                tr.append((t, "pack", 1e3 * (_time.perf_counter() - _t0)))
-                _t0 = _time.perf_counter()
+            mark("pack")
             ctx.after_execution(-1)  # outputs bound; "uploaded" = referenced by the HBM frame store
-            if tr is not None:
-                tr.append((t, "after_execution", 1e3 * (_time.perf_counter() - _t0)))
+            mark("after_execution")
             self.store.put_inline(exc_uri, None)
             self.stats["ops"] += 1
         except BaseException:

@@ -17,6 +17,7 @@ exist, so a later process finds them under their stable URIs (pylzy/lzy/core/wor
 from __future__ import annotations
 
 import ctypes as C
+import struct
 import threading
 import uuid
 from io import BytesIO
@@ -26,8 +27,6 @@ from .... import _host as H
 from .... import _native as N
 from ....devmem import current_stream_ptr
 from ....serialization.api import DeviceFrameSerializer, SerializerRegistry
-import struct
-
 from ....serialization.builtin import FLAG_HOST_ORIGIN, FLAG_NDARRAY, FLAG_OOB, CloudpickleSerializer
 
 OOB_MIN_BYTES = 64 << 10  # below this an object is one plain pickle
