@@ -3,6 +3,8 @@ annotation (mandatory — ``TypeError`` at decoration time otherwise) and replac
 ``LazyCallWrapper``."""
 from __future__ import annotations
 
+import inspect
+
 from typing import Any, Callable, Optional, Sequence, TypeVar
 
 from ..api.v1.utils.types import infer_return_type
@@ -14,7 +16,15 @@ FuncT = TypeVar("FuncT", bound=Callable[..., Any])
 
 
 def _pretty(f: Callable) -> str:
-    return f"{getattr(f, '__module__', '?')}.{getattr(f, '__qualname__', repr(f))}"
+    """"function `name` at file:line" — the wording of pylzy/lzy/utils/format.py:6-27, which the reference's tests
+    match on (tests/core/test_calls.py:352-356)"""
+    text = f"{type(f).__name__} `{getattr(f, '__name__', repr(f))}`"
+    target = f.__func__ if inspect.ismethod(f) else f
+    if inspect.isfunction(target):
+        text += f" at {inspect.getfile(target)}"
+        if hasattr(target, "__code__"):
+            text += f":{target.__code__.co_firstlineno}"
+    return text
 
 
 def op(func: Optional[FuncT] = None, *, env: Optional[LzyEnvironment] = None, output_types: Optional[Sequence[type]] = None,

@@ -12,7 +12,8 @@ and pylzy/lzy/api/v1/utils/proxy_adapter.py:14-83):
   ``str(p)``, ``p + 1`` behave like the real value, and proxies passed as arguments to those methods
   are materialised first;
 * ``type(p)`` is never the real type (``type(a) is str`` is False inside an op with
-  ``lazy_arguments=True``, pylzy/tests/core/test_workflow.py:386-393).
+  ``lazy_arguments=True``, pylzy/tests/core/test_workflow.py:386-393) but ``p.__class__`` is, so
+  ``isinstance(p, T)`` answers for the materialised value (pylzy/tests/proxy/test_proxy.py:48-71,280-284).
 
 The implementation is a per-proxy class whose special methods are plain forwarding closures.
 """
@@ -137,8 +138,8 @@ def proxy(constructor: Callable[[], Any], proto_types: Sequence[Type], cls_attrs
             return _resolve(cls)
         if item == "__lzy_materialized__":
             return "value" in type.__getattribute__(cls, "_lzy_state")
-        if item == "__class__":
-            return cls
+        if item == "__class__":  # isinstance(p, T) asks this: answered by the real object (automagic.py:66-81)
+            return type(_resolve(cls))
         if item in own or item in _PROTOCOLS:
             return object.__getattribute__(self, item)
         return getattr(_resolve(cls), item)

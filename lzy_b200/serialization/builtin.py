@@ -14,6 +14,7 @@ generic cloudpickle fallback.
 from __future__ import annotations
 
 import ctypes as C
+import logging
 import os
 import uuid
 from typing import Any, BinaryIO, Callable, Dict, Optional, Tuple, Type, Union
@@ -41,6 +42,9 @@ def _np_to_code():
     return {"uint8": N.DT_U8, "int8": N.DT_I8, "int16": N.DT_I16, "int32": N.DT_I32, "int64": N.DT_I64,
             "float16": N.DT_F16, "float32": N.DT_F32, "float64": N.DT_F64, "bool": N.DT_BOOL,
             "uint16": N.DT_U16, "uint32": N.DT_U32, "uint64": N.DT_U64}
+
+
+_LOG = logging.getLogger(__name__)
 
 
 class CloudpickleSerializer(Serializer):
@@ -86,6 +90,14 @@ class CloudpickleSerializer(Serializer):
         if schema.data_format != self.DATA_FORMAT:
             raise ValueError(f"Invalid data format {schema.data_format}")
         return object
+
+
+def _version_key(v: str):
+    parts = []
+    for piece in str(v).split("."):
+        digits = "".join(ch for ch in piece if ch.isdigit())
+        parts.append(int(digits) if digits else 0)
+    return tuple(parts)
 
 
 class FileSerializer(Serializer):
@@ -146,6 +158,13 @@ class FileSerializer(Serializer):
             raise ValueError(f"Invalid data format {schema.data_format}")
         if schema.schema_format != StandardSchemaFormats.no_schema.name:
             raise ValueError(f"Invalid schema format {schema.schema_format}")
+        # version drift is reported, not refused (pylzy/lzy/serialization/file.py:72-76)
+        from .. import __version__
+        if "pylzy" not in schema.meta:
+            _LOG.warning("No pylzy version in meta")
+        elif _version_key(schema.meta["pylzy"]) > _version_key(__version__):
+            _LOG.warning("Installed version of pylzy %s is older than used for serialization %s", __version__,
+                         schema.meta["pylzy"])
         return File
 
 

@@ -39,8 +39,13 @@ class LzySerializerRegistry(SerializerRegistry):
         if priority is None and self.__dict__.get("_LzySerializerRegistry__inited"):
             priority = 100 + len(self.__user_serializers)  # user serializers win over the pickle fallback
         super().register_serializer(serializer, priority)
-        if self.__dict__.get("_LzySerializerRegistry__inited"):
+        user = bool(self.__dict__.get("_LzySerializerRegistry__inited"))
+        if user:
             self.__user_serializers.add(type(serializer))
+        # an instance of a serializer's type nested inside a pickled object travels through that serializer
+        # (registry.py:34-46 hooks every by-type serializer into copyreg).  The device-frame serializers stay
+        # out: arrays inside a pickle ride as protocol-5 out-of-band buffers of one composite frame instead.
+        if user or isinstance(serializer, FileSerializer):
             try:
                 t = serializer.supported_types()
                 if isinstance(t, type):
