@@ -155,3 +155,29 @@ def test_only_the_main_process_writes_results():
 def test_main_needs_a_mount():
     with pytest.raises(AssertionError, match="no slot mount"):
         startup.main("AAAA")
+
+
+def test_a_request_pickled_by_a_stock_client_resolves_to_this_package():
+    """cloudpickle stores `ProcessingRequest` by reference to ``lzy.api.v1.startup``; with `install_as_lzy()` that
+    name is this package's module object, so the request a stock pylzy client put on the command line runs here"""
+    import importlib
+
+    import lzy_b200
+    lzy_b200.install_as_lzy()
+    assert importlib.import_module("lzy.api.v1.startup") is startup  # the same module object, not a second copy
+
+    def op(a: str) -> str:
+        return a.upper()
+
+    ser, mount = LzySerializerRegistry(), BytesMount()
+    mount.put("/c/a", str, "x", ser)
+    req = request(op, ser, args_paths=[(str, "/c/a")], output_paths=[(str, "/c/ret")])
+    ProcessingRequest.__module__ = "lzy.api.v1.startup"  # what the class is called in a stock client's pickle
+    try:
+        arg = pickle(req)
+    finally:
+        ProcessingRequest.__module__ = "lzy_b200.api.v1.startup"
+    import base64
+    assert b"lzy.api.v1.startup" in base64.b64decode(arg) and b"lzy_b200.api.v1.startup" not in base64.b64decode(arg)
+    startup.main(arg, mount)
+    assert mount.get("/c/ret", str, ser) == "X"
