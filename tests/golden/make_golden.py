@@ -8,6 +8,10 @@
   md5_of_str) and pylzy/lzy/storage/async_/fs.py (FsStorageClient read/write 8096-byte loops,
   path_from_uri).  `lzy.api.v1` itself cannot be imported (serialzy, envzy, generated protobuf
   stubs are absent), so the modules are loaded by file path.
+* reference_proxy_vectors.json — answers of the reference's own lazy proxy (pylzy/lzy/proxy/automagic.py, loaded
+  by file path) to the probes of tests/golden/proxy_battery.py; tests/test_lazy_proxy.py holds ours to them.
+* reference_pickle_vectors.json — what the reference's request encoding (pylzy/lzy/api/v1/utils/pickle.py) emits
+  for a few objects; ours must decode them and encode the same text.
 * digest_vectors.json — known answers of the data plane's digest from the oracle's C restatement
   cross-checked with the pure-Python definition in tests/test_abi_and_oracle.py.
 """
@@ -72,6 +76,20 @@ def main():
     out["path_from_uri"] = [{"in": u, "out": p(u)} for u in
                             ["file:///tmp/lzy_storage/a", "file:///tmp/lzy_storage/lzy_runs/wf/inputs/abc"]]
     (ROOT / "tests/golden/reference_leaf_vectors.json").write_text(json.dumps(out, indent=1))
+
+    proxy_battery = load(ROOT / "tests/golden/proxy_battery.py", "proxy_battery")  # (REF/tests shadows ours on sys.path)
+    automagic = load(REF / "lzy/proxy/automagic.py", "ref_automagic")
+    answers = json.loads(json.dumps(proxy_battery.run(automagic.proxy), default=str))
+    (ROOT / "tests/golden/reference_proxy_vectors.json").write_text(json.dumps(answers, indent=1, sort_keys=True))
+
+    ref_pickle = load(REF / "lzy/api/v1/utils/pickle.py", "ref_pickle")
+    objs = [None, 42, -1.5, "ʎzy", b"\x00\xff", [1, "two", 3.0], {"k": (1, 2), "n": None}, (str, "/call/entry"), {1, 2, 3}]
+    pv = []
+    for o in objs:
+        text = ref_pickle.pickle(o)
+        assert ref_pickle.unpickle(text) == o
+        pv.append({"repr": repr(o), "text": text})
+    (ROOT / "tests/golden/reference_pickle_vectors.json").write_text(json.dumps(pv, indent=1))
 
     vecs = [{"name": "empty", "hex": ""}, {"name": "Hello", "hex": b"Hello".hex()},
             {"name": "one-word", "hex": bytes(range(8)).hex()}, {"name": "17-bytes", "hex": bytes(range(17)).hex()},

@@ -202,3 +202,16 @@ def test_union_of_declared_types():
     p1, p2 = proxy(lambda: "str", (int, str)), proxy(lambda: 10, (int, str))
     assert p1 + "str" == "strstr"
     assert isinstance(p2, int) and sum(1 for _ in range(p2)) == 10
+
+
+def test_same_answers_as_the_reference_proxy_on_the_shared_battery():
+    """tests/golden/reference_proxy_vectors.json was produced by running tests/golden/proxy_battery.py against the
+    reference's own `lzy.proxy.proxy` (pylzy/lzy/proxy/automagic.py) in the authoring container"""
+    import json
+    from pathlib import Path
+
+    from tests.golden import proxy_battery
+    golden = json.loads((Path(__file__).parent / "golden" / "reference_proxy_vectors.json").read_text())
+    ours = json.loads(json.dumps(proxy_battery.run(proxy), default=str))
+    assert set(ours) == set(golden)
+    assert {k: ours[k] for k in golden if ours[k] != golden[k]} == {}

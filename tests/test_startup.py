@@ -181,3 +181,13 @@ def test_a_request_pickled_by_a_stock_client_resolves_to_this_package():
     assert b"lzy.api.v1.startup" in base64.b64decode(arg) and b"lzy_b200.api.v1.startup" not in base64.b64decode(arg)
     startup.main(arg, mount)
     assert mount.get("/c/ret", str, ser) == "X"
+
+
+def test_request_encoding_matches_the_reference_text_for_text():
+    """tests/golden/reference_pickle_vectors.json: output of the reference's own pickle() (utils/pickle.py:7-12)"""
+    import json
+    from pathlib import Path
+    for v in json.loads((Path(__file__).parent / "golden" / "reference_pickle_vectors.json").read_text()):
+        obj = unpickle(v["text"])
+        assert repr(obj) == v["repr"]
+        assert pickle(obj) == v["text"]
