@@ -150,7 +150,8 @@ int spill_write(const std::string& path, lzyb_handle_t slot) {
     memcpy(hdr.shape, info.shape, sizeof(hdr.shape));
     hdr.digest[0] = info.digest[0];
     hdr.digest[1] = info.digest[1];
-    const std::string tmp = path + ".tmp." + std::to_string((long long)getpid());
+    static std::atomic<uint64_t> tmp_seq{0};  // two writers of one URI (threads or processes) never share a temp file
+    const std::string tmp = path + ".tmp." + std::to_string((long long)getpid()) + "." + std::to_string(++tmp_seq);
     int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
     if (fd < 0) return fail(LZYB_E_LOCAL, "cannot create %s: %s", tmp.c_str(), strerror(errno));
     bool ok = write_fully(fd, &hdr, sizeof(hdr));

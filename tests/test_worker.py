@@ -233,3 +233,73 @@ def test_worker_api_over_grpc(env):
         for c in (wapi, ops, sapi):
             c.close()
         server.stop(0)
+
+
+def test_diamond_graph_driven_through_two_workers_over_grpc(env):
+    """What the reference's graph executor does with its workers, end to end on this repository's pieces: channels
+    from CreateChannels' rule (storage consumer per result, storage producer per existing input), tasks released by
+    the dispatcher when their producers have succeeded (BfsGraphProcessor), each sent to a worker as
+    WorkerApi.Execute and polled through LongRunningService.Get; b and c pull a's result slot to slot from the
+    other worker, d pulls from both."""
+    cm, w0 = env
+    w1 = Worker(cm, 0, "lzyb://worker-1", mount_factory=hostmem.HostmemMount)
+    servers, clients = [], []
+    try:
+        for w in (w0, w1):
+            server, port = serve("127.0.0.1:0", worker=w)
+            servers.append(server)
+            clients.append((WorkerApiClient(f"127.0.0.1:{port}"), LongRunningClient(f"127.0.0.1:{port}")))
+            clients[-1][0].call("Init", M.InitRequest(user_id="uid", workflow_name="wf"))
+
+        # a: "x" -> "xa";  b, c: t -> t + "b" / "c";  d: (l, r) -> l + "|" + r
+        def tag(suffix):
+            def f(t: str) -> str:
+                return t + suffix
+            return f
+
+        def join(l: str, r: str) -> str:
+            return l + "|" + r
+
+        tasks = [make_task(cm, tag("a"), [(str, "x")], task_id="a"),
+                 make_task(cm, tag("b"), [(str, "?")], task_id="b"),
+                 make_task(cm, tag("c"), [(str, "?")], task_id="c"),
+                 make_task(cm, join, [(str, "?"), (str, "?")], task_id="d")]
+        tasks[1].slot_assignments["/b/arg0"] = tasks[0].slot_assignments["/a/ret0"]
+        tasks[2].slot_assignments["/c/arg0"] = tasks[0].slot_assignments["/a/ret0"]
+        tasks[3].slot_assignments["/d/arg0"] = tasks[1].slot_assignments["/b/ret0"]
+        tasks[3].slot_assignments["/d/arg1"] = tasks[2].slot_assignments["/c/ret0"]
+        placement = [0, 1, 0, 1]
+        graph = H.GraphDispatcher(4, [(0, 1), (0, 2), (1, 3), (2, 3)], allow_cycles=False)
+        running, order = {}, []
+        deadline = time.time() + 60
+        while graph.status not in (H.G_COMPLETED, H.G_FAILED):
+            assert time.time() < deadline
+            for t in graph.next():
+                task = tasks[t]
+                req = M.ExecuteRequest(task_id=task.task_id, execution_id=task.execution_id, workflow_name="wf", user_id="uid")
+                req.task_desc.operation.command = task.command
+                for s in task.slots:
+                    req.task_desc.operation.slots.add(name=s.name, direction=s.direction)
+                for name, chan in task.slot_assignments.items():
+                    req.task_desc.slot_assignments.add(slot_name=name, channel_id=chan)
+                running[t] = clients[placement[t]][0].call("Execute", req).id
+                order.append(t)
+            for t, op_id in list(running.items()):
+                op = clients[placement[t]][1].call("Get", GetOperationRequest(operation_id=op_id))
+                if op.done:
+                    resp = M.ExecuteResponse()
+                    assert op.response.Unpack(resp)
+                    graph.task_done(t, resp.rc == 0, resp.description)
+                    del running[t]
+            time.sleep(0.002)
+        assert graph.status == H.G_COMPLETED
+        assert order[0] == 0 and order[-1] == 3 and set(order[1:3]) == {1, 2}
+        assert dec(str, H.blob_get("mem://exec-1/d/ret0")) == "xab|xac"
+        graph.close()
+    finally:
+        for wapi, ops in clients:
+            wapi.close()
+            ops.close()
+        for s in servers:
+            s.stop(0)
+        w1.close()
