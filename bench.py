@@ -389,10 +389,10 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and not multi and not args.no_cpu_baseline:
-        sample_bytes = 128 << 20
+        sample_bytes = 256 << 20  # ≈ 10–20 s of CPU work on the pool's hosts: a quarter of the real edge size
         dt = cpu_chain_seconds(sample_bytes)
         cpu = {"value": N_OPS * sample_bytes / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{N_OPS}-op identity chain, 128 MiB fp32 per edge, one subprocess per op, {dt:.1f} s",
+               "sample": f"{N_OPS}-op identity chain, {sample_bytes >> 20} MiB fp32 per edge, one subprocess per op, {dt:.1f} s",
                "host_cores": os.cpu_count()}
 
     if rank == 0:
