@@ -386,10 +386,9 @@ std::vector<uint64_t> dma_schedule(uint64_t nbytes) {
 int launch_dma_verify(DeviceCtx& d, const CopyParams& whole, cudaStream_t st) {
     std::lock_guard<std::mutex> issue(d.dma_mu);
     cudaStream_t vs = d.verify_stream;
-    // earlier chunks of this transfer (and the recycling of the sink frame) are ordered on `st`
-    cudaEvent_t ev = d.next_dma_event();
-    CU(cudaEventRecord(ev, st));
-    CU(cudaStreamWaitEvent(vs, ev, 0));
+    // Earlier chunks of this transfer (and the recycling of the sink frame) are ordered on `st`; every scan
+    // waits for an event recorded on `st` after its copy, so it is ordered after all of that as well.
+    cudaEvent_t ev = nullptr;
     const std::vector<uint64_t> sizes = dma_schedule(whole.nbytes);
     uint64_t off = 0;
     for (size_t j = 0; j < sizes.size(); ++j) {
