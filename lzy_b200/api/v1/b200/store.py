@@ -25,7 +25,7 @@ from typing import Any, Dict, Optional, Type
 
 from .... import _host as H
 from .... import _native as N
-from ....devmem import current_stream_ptr
+from ....devmem import caller_stream_scope, current_stream_ptr
 from ....serialization.api import DeviceFrameSerializer, SerializerRegistry
 from ....serialization.builtin import FLAG_HOST_ORIGIN, FLAG_NDARRAY, FLAG_OOB, CloudpickleSerializer
 
@@ -195,9 +195,11 @@ class FrameStore:
             return N.SlotHandle.create_output(f"put/{name}/{uuid.uuid4()}", gpu, nbytes)
 
         probe_gpu = getattr(getattr(data, "device", None), "index", None)
-        stream = current_stream_ptr(probe_gpu if probe_gpu is not None else self.default_gpu)
-        slot = self.pack_object(data, typ, registry, factory, stream)
-        digest = slot.commit(stream)
+        gpu = probe_gpu if probe_gpu is not None else self.default_gpu
+        with caller_stream_scope(gpu):  # the caller filled `data` on its own stream: pack in that stream's order
+            stream = current_stream_ptr(gpu)
+            slot = self.pack_object(data, typ, registry, factory, stream)
+            digest = slot.commit(stream)  # waits for the pack: `data` may be reused as soon as put returns
         slot._keepalive = None
         hexd = N.digest_hex(digest)
         uri = prefix + hexd
@@ -289,7 +291,13 @@ class FrameStore:
             raise ValueError(f"Cannot find blob in storage by uri={uri}")
         if self.reloads != reloads:
             self.enforce_budget(protect=uri)  # what came back from the tier pushes something colder out
-        return self.unpack_slot(slot, typ, registry, private=False)
+        with caller_stream_scope(slot.gpu):  # the caller will use the value on its own stream
+            value = self.unpack_slot(slot, typ, registry, private=False)
+            if getattr(value, "is_cuda", False):
+                # the copy must have left the frame before the frame can be released (clear / eviction)
+                import torch
+                torch.cuda.current_stream(slot.gpu).synchronize()
+        return value
 
     def alias(self, from_uri: str, to_uri: str) -> None:
         slot = self._slot(from_uri)

@@ -2,11 +2,13 @@
 streams).  A slot's HBM frame is owned by liblzy_b200; the view must not outlive the slot."""
 from __future__ import annotations
 
+import contextlib
 from typing import Sequence
 
 import torch
 
 from . import _native as N
+from .utils.event_loop import caller_stream
 
 _TORCH_TO_DT = {
     torch.uint8: N.DT_U8, torch.int8: N.DT_I8, torch.int16: N.DT_I16, torch.int32: N.DT_I32,
@@ -61,3 +63,16 @@ def current_stream_ptr(gpu: int) -> int:
     """cudaStream_t of torch's current stream.  The C ABI reserves NULL for "the library's own
     stream", so the legacy default stream (handle 0) is passed as cudaStreamLegacy (0x1)."""
     return int(torch.cuda.current_stream(gpu).cuda_stream) or 1
+
+
+@contextlib.contextmanager
+def caller_stream_scope(gpu: int):
+    """Inside a coroutine started with ``LzyEventLoop.run_async``: make the *caller's* current stream on `gpu`
+    the current one for the block, so that work on a tensor the caller handed in (or will receive) is ordered
+    with the caller's own work on it.  Elsewhere: a no-op."""
+    s = caller_stream(gpu)
+    if s is None:
+        yield
+        return
+    with torch.cuda.stream(s):
+        yield

@@ -3,10 +3,32 @@
 from __future__ import annotations
 
 import asyncio
+import contextvars
+import sys
 from threading import Lock, Thread
-from typing import Awaitable, Optional, Sequence, TypeVar
+from typing import Any, Awaitable, Dict, Optional, Sequence, TypeVar
 
 T = TypeVar("T")
+
+# CUDA streams are per thread.  A caller hands tensors in (put_data) and takes tensors out (get_data) with its own
+# current stream in mind — the H2D copy that fills an argument, the D2H copy that reads a result — but the
+# coroutine that touches them runs on the workflow thread.  run_async therefore carries the caller's current
+# stream of every device into the coroutine's context; the frame store packs / clones on that stream
+# (`caller_stream`), which keeps both sides of the hand-over in one stream order.
+_CALLER_STREAMS: contextvars.ContextVar = contextvars.ContextVar("lzyb_caller_streams", default=None)
+
+
+def _capture_streams() -> Optional[Dict[int, Any]]:
+    torch = sys.modules.get("torch")
+    if torch is None or not torch.cuda.is_available() or not torch.cuda.is_initialized():
+        return None
+    return {d: torch.cuda.current_stream(d) for d in range(torch.cuda.device_count())}
+
+
+def caller_stream(gpu: int) -> Optional[Any]:
+    """the stream that was current on `gpu` in the thread that called run_async (None outside such a call)"""
+    streams = _CALLER_STREAMS.get()
+    return None if streams is None else streams.get(gpu)
 
 
 class LzyEventLoop:
@@ -31,7 +53,15 @@ class LzyEventLoop:
 
     @classmethod
     def run_async(cls, fun: Awaitable[T]) -> T:
-        return asyncio.run_coroutine_threadsafe(fun, cls._get()._loop).result()
+        streams = _capture_streams()
+        if streams is None:
+            return asyncio.run_coroutine_threadsafe(fun, cls._get()._loop).result()
+
+        async def with_caller_streams():
+            _CALLER_STREAMS.set(streams)  # the task's own context: child tasks inherit it, other tasks do not see it
+            return await fun
+
+        return asyncio.run_coroutine_threadsafe(with_caller_streams(), cls._get()._loop).result()
 
     @classmethod
     def gather(cls, *args: Awaitable[T]) -> Sequence[T]:

@@ -416,6 +416,42 @@ def test_cuda_tensor_chain_stays_on_device_and_is_bit_exact(lzy, workflow_name):
     assert lzy.runtime.store.bytes_put - before == x.numel() * 4  # x was stored once (content addressed)
 
 
+def _late_filled_tensor_through_an_op(lzy, workflow_name):
+    """an argument that is still being produced on the caller's (non-default, non-blocking) stream when the op is
+    called, and a result the caller reads on that same stream right after materialising it"""
+    @op
+    def ident(t: torch.Tensor) -> torch.Tensor:
+        return t
+
+    s = torch.cuda.Stream(0)
+    with torch.cuda.stream(s):
+        t = torch.zeros(1 << 22, device="cuda:0")
+        s.synchronize()
+        torch.cuda._sleep(int(3e8))  # ~150 ms of busy GPU time on `s` …
+        t.fill_(7.0)                 # … so the real content exists long after the host has moved on
+        with lzy.workflow(workflow_name):
+            y = materialize(ident(t))
+        host = torch.empty(1 << 22, pin_memory=True)
+        host.copy_(y, non_blocking=True)
+        s.synchronize()
+    return float(host.min()), float(host.max())
+
+
+def test_arguments_and_results_follow_the_callers_stream(lzy, workflow_name):
+    """put_data / get_data run on the workflow thread; they must still be ordered with the *caller's* current CUDA
+    stream (utils/event_loop.py carries it across), or a pack reads an argument before the H2D / kernel that fills
+    it and a D2H reads a result before the copy out of the frame"""
+    assert _late_filled_tensor_through_an_op(lzy, workflow_name) == (7.0, 7.0)
+
+
+def test_without_stream_propagation_the_hazard_is_real(lzy, workflow_name, monkeypatch):
+    """negative control for the test above: with the caller's streams not carried over, the pack runs on the
+    workflow thread's default stream and snapshots the argument before it was filled"""
+    from lzy_b200.utils import event_loop
+    monkeypatch.setattr(event_loop, "_capture_streams", lambda: None)
+    assert _late_filled_tensor_through_an_op(lzy, workflow_name) != (7.0, 7.0)
+
+
 def test_ndarray_and_cpu_tensor_round_trip(lzy, workflow_name):
     @op
     def ident(a: np.ndarray) -> np.ndarray:
