@@ -143,3 +143,42 @@ def test_without_a_spill_directory_the_tier_is_off(env):
     ctx.close()
     H.frame_store_drop("hbm://t/x")
     assert H.frame_store_get("hbm://t/x") is None
+
+
+def test_concurrent_consumers_of_one_spilled_uri_share_a_single_load(env):
+    import threading
+    cm, slots, lib, d = env
+    data = os.urandom(2 << 20)
+    ctx, chan = produce_to_store(cm, slots, lib, "hbm://t/shared", data)
+    H.frame_store_spill("hbm://t/shared")
+    ctx.close()
+    H.frame_store_drop("hbm://t/shared")
+    assert lib.hostmem_live_slots() == 0
+    got, errors = [], []
+
+    def fetch():
+        try:
+            got.append(H.frame_store_get("hbm://t/shared"))
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=fetch) for _ in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors and len(set(got)) == 1 and got[0] is not None
+    assert lib.hostmem_live_slots() == 1  # one frame, not eight
+
+    # … and several input slots bound to the channel at once are all served from it
+    ctxs = []
+    for i in range(4):
+        c = slots.context("exec", f"c{i}")
+        c.add_slot(f"in{i}", chan, DIR_INPUT)
+        c.prefetch()
+        ctxs.append(c)
+    for i, c in enumerate(ctxs):
+        c.before_execution(10000)
+        assert hostmem.peek(c.input_handle(f"in{i}"), len(data)) == data
+    for c in ctxs:
+        c.close()
