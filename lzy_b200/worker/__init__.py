@@ -111,14 +111,13 @@ def run_startup_in_process(command: str, ctx: H.ExecutionContext, worker: "Worke
     it: 0, or 1 when the entry point raised (the op's exception is already in its exception slot)."""
     from ..api.v1 import startup
     from ..utils import op_scope
-    parts = command.split()
-    if not parts:
-        raise ValueError("empty command")
+    from ..utils.argv_codec import request_token
+    token = request_token(command)
     with worker.device_scope():
         mount = worker.mount_factory(ctx)
         op_scope.enter()
         try:
-            startup.main(parts[-1], mount)
+            startup.main(token, mount)
             return 0
         except Exception:
             traceback.print_exc(file=sys.stderr)
