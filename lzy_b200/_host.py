@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 from . import _native as N
 

@@ -31,8 +31,6 @@ from concurrent.futures import FIRST_COMPLETED, ThreadPoolExecutor, wait
 from dataclasses import dataclass, field
 from typing import TYPE_CHECKING, Any, Callable, Dict, List, Optional, Sequence, Tuple
 
-import cloudpickle
-
 from .... import _host as H
 from .... import _native as N
 from ....devmem import current_stream_ptr

@@ -1,7 +1,7 @@
 """Thin blocking clients for the kept gRPC surface (what the reference's generated stubs do)."""
 from __future__ import annotations
 
-from typing import Iterator, Optional
+from typing import Optional
 
 import grpc
 
