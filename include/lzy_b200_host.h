@@ -221,6 +221,12 @@ int lzyb_frame_store_load(const char* uri, int gpu, lzyb_handle_t* slot_out);
 int lzyb_frame_store_spilled(const char* uri);
 int lzyb_frame_store_resident(const char* uri);   /* 1 / 0; never loads */
 int lzyb_frame_store_unspill(const char* uri);
+/* Per-transfer records of this worker's input slots (most recent 4096), as a JSON array of
+ *   {"slot_id","channel_id","peer_id","peer_kind":"slot"|"storage","bytes","ns","failovers","ok","error"}
+ * — bytes delivered, wall time from the first peer to READY (or failure), the peer the bytes finally came from and
+ * how many producers were tried.  The reference keeps no data-plane metric at all.  Returns the bytes
+ * needed including the terminator (may exceed cap); clear != 0 empties the log. */
+int64_t lzyb_slots_transfer_log(lzyb_handle_t slots, char* json_out, uint64_t cap, int clear);
 /* republish delivered inputs as "<slot>-out" producers (InputSlot.java:160-168); default on.  The
  * Python runtime turns it off so that an op owns its input frame and may mutate it in place. */
 int lzyb_slots_set_republish(lzyb_handle_t slots, int on);

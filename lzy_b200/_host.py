@@ -79,6 +79,7 @@ _SIGS = {
     "lzyb_blob_size": (C.c_int64, [_s]),
     "lzyb_blob_get": (C.c_int64, [_s, C.c_void_p, C.c_uint64]),
     "lzyb_blob_delete": (_i, [_s]),
+    "lzyb_slots_transfer_log": (C.c_int64, [_H, C.c_char_p, C.c_uint64, C.c_int]),
     "lzyb_frame_store_put": (_i, [_s, _H]),
     "lzyb_frame_store_get": (_i, [_s, C.POINTER(_H)]),
     "lzyb_frame_store_drop": (_i, [_s]),
@@ -429,6 +430,17 @@ class Slots:
 
     def set_chunk_bytes(self, n: int) -> None:
         _check(lib.lzyb_slots_set_chunk_bytes(self.h, n))
+
+    def transfer_log(self, clear: bool = False) -> List[dict]:
+        """one record per finished input transfer: bytes, ns, final peer, failovers, outcome"""
+        import json
+        need = _check(lib.lzyb_slots_transfer_log(self.h, None, 0, 0))
+        while True:
+            buf = C.create_string_buffer(int(need) + 4096)
+            got = _check(lib.lzyb_slots_transfer_log(self.h, buf, len(buf), int(clear)))
+            if got <= len(buf):
+                return json.loads(buf.value.decode())
+            need = got
 
     def set_republish(self, on: bool) -> None:
         _check(lib.lzyb_slots_set_republish(self.h, int(on)))

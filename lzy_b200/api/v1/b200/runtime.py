@@ -175,6 +175,16 @@ class B200Runtime(Runtime):
             raise
         progress(ProgressStep.COMPLETED)
 
+    def transfer_log(self, clear: bool = False) -> List[dict]:
+        """per-transfer records of every worker (bytes, ns, final peer, failovers, outcome), tagged with the
+        consumer's GPU — include/lzy_b200_host.h: lzyb_slots_transfer_log"""
+        out: List[dict] = []
+        for gpu, worker in self.workers.items():
+            for rec in worker.transfer_log(clear):
+                rec["gpu"] = gpu
+                out.append(rec)
+        return out
+
     def clear(self) -> None:
         """drop every stored frame (results of finished workflows stay readable until then)"""
         if self.store is not None:

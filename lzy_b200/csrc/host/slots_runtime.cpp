@@ -17,10 +17,12 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <shared_mutex>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -320,7 +322,24 @@ struct SlotsServiceImpl {
     }
 };
 
+// One finished (or failed) input transfer: what the reference never records ("no data-plane byte /
+// throughput metric exists") — bytes, wall time, where they finally came from, how many producers were tried.
+struct TransferRecord {
+    std::string slot_id, channel_id, peer_id, error;
+    int peer_kind = 0;
+    uint64_t bytes = 0, ns = 0;
+    int failovers = 0;
+    bool ok = false;
+};
+
 struct SlotsInstance {
+    std::mutex log_mu;
+    std::deque<TransferRecord> transfer_log;  // the most recent 4096
+    void record(TransferRecord r) {
+        std::lock_guard<std::mutex> lk(log_mu);
+        if (transfer_log.size() >= 4096) transfer_log.pop_front();
+        transfer_log.push_back(std::move(r));
+    }
     lzyb_handle_t handle = 0;
     lzyb_handle_t cm = 0;
     int gpu = 0;
@@ -690,9 +709,28 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
     }
 
     bool download(lzyb_peer_desc_t cur, std::string tid, std::string& err) {
+        TransferRecord rec;
+        rec.slot_id = id;
+        rec.channel_id = channel_id;
+        const auto t0 = std::chrono::steady_clock::now();
+        const bool ok = download_loop(cur, tid, err, rec);
+        rec.ok = ok;
+        rec.ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        if (!rec.ok) rec.error = err;
+        if (backend) {
+            lzyb_slot_info_t info;
+            if (ops().slot_info(backend, &info) == LZYB_OK) rec.bytes = rec.ok ? info.nbytes : info.delivered;
+        }
+        inst->record(std::move(rec));
+        return ok;
+    }
+
+    bool download_loop(lzyb_peer_desc_t cur, std::string tid, std::string& err, TransferRecord& rec) {
         // InputSlot.download (InputSlot.java:223-295)
         uint64_t offset = 0;
         std::string terr;
+        rec.peer_id = cur.peer_id;
+        rec.peer_kind = cur.kind;
         auto transfer = make_transfer(cur, terr);
         std::string peer_fail_reason = transfer ? "" : terr;
         bool need_new_peer = !transfer;
@@ -711,6 +749,9 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
                 }
                 cur = np.peer;
                 tid = np.transfer_id;
+                rec.peer_id = cur.peer_id;
+                rec.peer_kind = cur.kind;
+                rec.failovers++;
                 need_new_peer = false;
                 peer_fail_reason.clear();
                 transfer = make_transfer(cur, terr);
@@ -1312,6 +1353,52 @@ int64_t lzyb_frame_store_bytes(void) {
         if (ops().slot_info(h, &info) == LZYB_OK) total += (int64_t)info.nbytes;
     }
     return total;
+}
+
+int64_t lzyb_slots_transfer_log(lzyb_handle_t h, char* json_out, uint64_t cap, int clear) {
+    auto s = get_inst(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slots handle");
+    std::ostringstream os;
+    auto quote = [&os](const std::string& v) {
+        os << '"';
+        for (char c : v) {
+            if (c == '"' || c == '\\')
+                os << '\\' << c;
+            else if ((unsigned char)c < 0x20)
+                os << ' ';
+            else
+                os << c;
+        }
+        os << '"';
+    };
+    {
+        std::lock_guard<std::mutex> lk(s->log_mu);
+        os << '[';
+        bool first = true;
+        for (const auto& r : s->transfer_log) {
+            if (!first) os << ',';
+            first = false;
+            os << "{\"slot_id\":";
+            quote(r.slot_id);
+            os << ",\"channel_id\":";
+            quote(r.channel_id);
+            os << ",\"peer_id\":";
+            quote(r.peer_id);
+            os << ",\"peer_kind\":\"" << (r.peer_kind == LZYB_PEER_STORAGE ? "storage" : "slot") << "\",\"bytes\":" << r.bytes
+               << ",\"ns\":" << r.ns << ",\"failovers\":" << r.failovers << ",\"ok\":" << (r.ok ? "true" : "false") << ",\"error\":";
+            quote(r.error);
+            os << '}';
+        }
+        os << ']';
+        if (clear) s->transfer_log.clear();
+    }
+    const std::string out = os.str();
+    if (json_out && cap) {
+        const uint64_t n = std::min<uint64_t>(cap - 1, out.size());
+        memcpy(json_out, out.data(), n);
+        json_out[n] = 0;
+    }
+    return (int64_t)out.size() + 1;
 }
 
 int lzyb_slots_set_republish(lzyb_handle_t h, int on) {

@@ -376,3 +376,45 @@ def test_stress_many_contexts_with_random_peer_failures(env):
             H.blob_delete(f"mem://stress/{i}")
         for w in workers[1:]:
             w.close()
+
+
+def test_transfer_log_records_bytes_time_source_and_failovers(env):
+    """what the reference never measures: every input transfer leaves a record"""
+    cm, slots, lib = env
+    slots.transfer_log(clear=True)
+    data = os.urandom(1 << 20)
+    chan = cm.get_or_create("u", "wf", "exec-log", consumer_uri="mem://log/backup")
+    out = slots.context("exec-log", "a")
+    out.add_slot("/log/out", chan, DIR_OUTPUT)
+    out.before_execution()
+    h = produce(out, "/log/out", data)
+    out.after_execution(5000)
+
+    ok = slots.context("exec-log", "b")
+    ok.add_slot("/log/in1", chan, DIR_INPUT)
+    ok.before_execution(10000)
+    lib.hostmem_set_fail_after(h, 4096)  # from now on the slot producer dies early: consumers end up on the backup
+    failing = slots.context("exec-log", "c")
+    failing.add_slot("/log/in2", chan, DIR_INPUT)
+    failing.before_execution(10000)
+    assert hostmem.peek(failing.input_handle("/log/in2"), len(data)) == data
+
+    log = {r["slot_id"]: r for r in slots.transfer_log()}
+    first, second = log["/log/in1"], log["/log/in2"]
+    assert first["ok"] and first["bytes"] == len(data) and first["failovers"] == 0 and first["peer_kind"] == "slot"
+    assert first["peer_id"] == "/log/out" and first["ns"] > 0 and first["error"] == "" and first["channel_id"] == chan
+    assert second["ok"] and second["bytes"] == len(data) and second["failovers"] >= 1 and second["peer_kind"] == "storage"
+    assert slots.transfer_log(clear=True) and slots.transfer_log() == []
+    for c in (ok, failing, out):
+        c.close()
+    H.blob_delete("mem://log/backup")
+
+    # a transfer that can never succeed is recorded as such
+    gone = cm.get_or_create("u", "wf", "exec-log2", producer_uri="mem://log/vanished")
+    lost = slots.context("exec-log2", "d")
+    lost.add_slot("/log/in3", gone, DIR_INPUT)
+    with pytest.raises(N.LzybError):
+        lost.before_execution(10000)
+    (rec,) = slots.transfer_log()
+    assert not rec["ok"] and rec["slot_id"] == "/log/in3" and "No more producers" in rec["error"]
+    lost.close()
