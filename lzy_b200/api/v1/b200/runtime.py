@@ -68,6 +68,50 @@ class B200RuntimeConfig:
     hbm_budget_bytes: int = 0                    # resident frame-store bytes above which LRU frames are evicted (0 = never)
     user_id: str = field(default_factory=lambda: os.environ.get("LZY_USER", "local-user"))
 
+    # deployment knobs without touching code: LZY_B200_<FIELD> (upper case) overrides a field that was left at its
+    # default; explicit keyword arguments always win.  Lists are comma separated, sizes accept k/m/g suffixes.
+    ENV_PREFIX = "LZY_B200_"
+
+    @classmethod
+    def from_env(cls, environ: Optional[Dict[str, str]] = None, **explicit: Any) -> "B200RuntimeConfig":
+        import dataclasses
+        env = os.environ if environ is None else environ
+        values: Dict[str, Any] = {}
+        for f in dataclasses.fields(cls):
+            raw = env.get(cls.ENV_PREFIX + f.name.upper())
+            if raw is None or f.name in explicit:
+                continue
+            try:
+                values[f.name] = cls._parse(f.name, raw)
+            except ValueError as e:
+                raise ValueError(f"{cls.ENV_PREFIX}{f.name.upper()}={raw!r}: {e}") from None
+        values.update(explicit)
+        return cls(**values)
+
+    @staticmethod
+    def _parse(name: str, raw: str) -> Any:
+        raw = raw.strip()
+        if name == "gpus":
+            return None if raw.lower() in ("", "all") else [int(x) for x in raw.split(",") if x.strip()]
+        if name in ("prefetch", "republish_inputs"):
+            if raw.lower() in ("1", "true", "yes", "on"):
+                return True
+            if raw.lower() in ("0", "false", "no", "off"):
+                return False
+            raise ValueError("expected a boolean")
+        if name in ("host_ring_bytes", "fanout_chunk_bytes", "chunk_bytes", "hbm_budget_bytes"):
+            mult = {"k": 1 << 10, "m": 1 << 20, "g": 1 << 30}.get(raw[-1:].lower())
+            return int(float(raw[:-1]) * mult) if mult else int(raw)
+        if name in ("max_parallel_ops", "fanout_threshold"):
+            return int(raw)
+        if name == "spill_dir":
+            return raw or None
+        choices = {"placement": ("round_robin", "locality", "single"), "retain": ("auto", "all"),
+                   "copy_engine": ("auto", "ldg", "tma", "dma")}.get(name)
+        if choices and raw not in choices:
+            raise ValueError(f"expected one of {choices}")
+        return raw
+
 
 class _Fanout:
     """one output consumed on several other GPUs: delivered once per GPU by a pull chain, then every
@@ -90,7 +134,7 @@ class _OpFailed(Exception):
 
 class B200Runtime(Runtime):
     def __init__(self, config: Optional[B200RuntimeConfig] = None, **kwargs):
-        self.config = config or B200RuntimeConfig(**kwargs)
+        self.config = config or B200RuntimeConfig.from_env(**kwargs)
         self._workflow: Optional["LzyWorkflow"] = None
         self._execution_id: Optional[str] = None
         self._lock = threading.RLock()

@@ -297,3 +297,21 @@ def test_install_as_lzy_aliases_the_package():
             "import lzy_b200.api.v1 as v1; assert Lzy is v1.Lzy and op is v1.op; print('ok')")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
+
+
+def test_runtime_config_env_overrides():
+    """LZY_B200_* environment overrides for deployment knobs; explicit arguments win"""
+    from lzy_b200.api.v1.b200.runtime import B200RuntimeConfig
+    env = {"LZY_B200_GPUS": "2, 3", "LZY_B200_HBM_BUDGET_BYTES": "1.5g", "LZY_B200_SPILL_DIR": "/nvme/spill",
+           "LZY_B200_PREFETCH": "off", "LZY_B200_COPY_ENGINE": "dma", "LZY_B200_FANOUT_THRESHOLD": "5", "UNRELATED": "x"}
+    c = B200RuntimeConfig.from_env(env)
+    got = (c.gpus, c.hbm_budget_bytes, c.spill_dir, c.prefetch, c.copy_engine, c.fanout_threshold)
+    assert got == ([2, 3], int(1.5 * (1 << 30)), "/nvme/spill", False, "dma", 5)
+    assert c.placement == "round_robin" and c.chunk_bytes == 0  # untouched fields keep their defaults
+    assert B200RuntimeConfig.from_env(env, gpus=[0], prefetch=True).gpus == [0]
+    assert B200RuntimeConfig.from_env(env, prefetch=True).prefetch is True
+    assert B200RuntimeConfig.from_env({"LZY_B200_GPUS": "all"}).gpus is None
+    assert B200RuntimeConfig.from_env({}) == B200RuntimeConfig(user_id=B200RuntimeConfig.from_env({}).user_id)
+    for bad in ({"LZY_B200_PLACEMENT": "random"}, {"LZY_B200_PREFETCH": "maybe"}, {"LZY_B200_CHUNK_BYTES": "2x"}):
+        with pytest.raises(ValueError, match="LZY_B200_"):
+            B200RuntimeConfig.from_env(bad)
