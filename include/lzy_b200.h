@@ -269,6 +269,9 @@ int lzyb_set_copy_engine(int engine);
  * 4..32 MiB; else a multiple of 16, at least 1 MiB), each earlier one `growth` times larger (default 6; 1 =
  * uniform), the first takes the remainder */
 int lzyb_set_dma_schedule(uint64_t last_bytes, int growth);
+/* the sub-chunk sizes a copy-engine pull of nbytes would use under the current schedule, first to last (pure
+ * arithmetic, needs no GPU): writes at most cap entries, returns how many there are */
+int lzyb_dma_schedule(uint64_t nbytes, uint64_t* sizes_out, int cap);
 /* LDG/STG grid shape: n > 0 = persistent, n CTAs per SM; 0 = one 32 KiB tile per CTA; -T = T tiles per CTA;
  * -1000 = auto (default) */
 int lzyb_set_grid(int ctas_per_sm);

@@ -169,6 +169,7 @@ _SIGNATURES = {
     "lzyb_set_grid": (C.c_int, [C.c_int]),
     "lzyb_set_tma_config": (C.c_int, [C.c_int]),
     "lzyb_set_dma_schedule": (C.c_int, [C.c_uint64, C.c_int]),
+    "lzyb_dma_schedule": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint64), C.c_int]),
     "lzyb_set_debug_flags": (C.c_int, [C.c_int]),
     "lzyb_fault_inject": (C.c_int, [_H, C.c_int, C.c_uint64]),
 }
@@ -408,6 +409,12 @@ def set_copy_engine(engine: int) -> None:
 
 def set_dma_schedule(last_bytes: int = 0, growth: int = 6) -> None:
     check(lib.lzyb_set_dma_schedule(last_bytes, growth))
+
+
+def dma_schedule(nbytes: int) -> list:
+    buf = (C.c_uint64 * 64)()
+    n = lib.lzyb_dma_schedule(nbytes, buf, 64)
+    return [int(buf[i]) for i in range(min(n, 64))]
 
 
 def set_tma_config(index: int) -> None:

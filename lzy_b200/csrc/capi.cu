@@ -1739,6 +1739,12 @@ int lzyb_set_dma_schedule(uint64_t last_bytes, int growth) {
     return LZYB_OK;
 }
 
+int lzyb_dma_schedule(uint64_t nbytes, uint64_t* sizes_out, int cap) {
+    const std::vector<uint64_t> sizes = dma_schedule(nbytes);
+    for (size_t i = 0; i < sizes.size() && (int)i < cap; ++i) sizes_out[i] = sizes[i];
+    return (int)sizes.size();
+}
+
 int lzyb_set_tma_config(int index) {
     if (index < 0 || index >= kNumTmaCfgs) return fail(LZYB_E_ARG, "tma config index must be in [0, %d)", kNumTmaCfgs);
     g.tma_cfg = index;

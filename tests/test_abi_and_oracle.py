@@ -154,3 +154,31 @@ def test_reference_leaf_module_golden_vectors():
         assert oracle.fs_copy(np.frombuffer(data, np.uint8), np.empty(len(data), np.uint8)) == v["loop_iterations"]
     for v in g["path_from_uri"]:
         assert L.path_from_uri(v["in"]) == v["out"]
+
+
+def test_copy_engine_pull_schedule_arithmetic():
+    """launch_dma_verify's sub-chunk plan (capi.cu: dma_schedule) is pure arithmetic and callable without a GPU:
+    the pieces tile the chunk exactly, every boundary is 16-byte aligned (digest word positions), the ragged tail
+    rides in the last piece, pieces shrink geometrically towards the end, and there are only a few of them."""
+    import random
+
+    from lzy_b200 import _native as N
+    try:
+        assert N.dma_schedule(1 << 30) == [800 << 20, 192 << 20, 32 << 20]
+        assert N.dma_schedule(4 << 30) == [2720 << 20, 1152 << 20, 192 << 20, 32 << 20]
+        assert N.dma_schedule(256 << 20) == [200 << 20, 48 << 20, 8 << 20]
+        assert N.dma_schedule(100) == [100] and N.dma_schedule(0) == [0]
+        rnd = random.Random(5)
+        for _ in range(300):
+            n = rnd.choice([rnd.randrange(1, 1 << 12), rnd.randrange(1, 1 << 26), rnd.randrange(1 << 26, 1 << 34)])
+            sizes = N.dma_schedule(n)
+            assert sum(sizes) == n and 1 <= len(sizes) <= 8
+            assert all(s % 16 == 0 for s in sizes[:-1]) and sizes[-1] % 16 == n % 16
+            assert all(a >= b for a, b in zip(sizes[1:-1], sizes[2:]))  # geometric tail; the first piece takes the rest
+        N.check(N.lib.lzyb_set_dma_schedule(3 << 20, 1))  # uniform 3 MiB pieces (tests use this to force many copies)
+        assert N.dma_schedule(8 << 20) == [2 << 20, 3 << 20, 3 << 20]
+        assert N.dma_schedule((40 << 20) + 11)[-1] == (3 << 20) + 11
+        with pytest.raises(N.LzybError):
+            N.check(N.lib.lzyb_set_dma_schedule(100, 6))
+    finally:
+        N.lib.lzyb_set_dma_schedule(0, 6)
