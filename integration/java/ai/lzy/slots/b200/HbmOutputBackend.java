@@ -8,7 +8,7 @@ import java.nio.channels.ReadableByteChannel;
 
 /**
  * {@link OutputSlotBackend} over an HBM slot frame; takes the place of {@code OutputPipeBackend}
- * (lzy/slots/src/main/java/ai/lzy/slots/backends/OutputPipeBackend.java:18-70).  The op writes its result into
+ * (lzy/slots/src/main/java/ai/lzy/slots/backends/OutputPipeBackend.java:18-69).  The op writes its result into
  * the frame ({@link #devicePtr()}) or hands a device pointer to {@link #pack}; {@link #waitCompleted()} is the
  * commit: one CUDA launch frames the payload and publishes its 128-bit digest.
  */

@@ -1,6 +1,6 @@
 """What is known about an ``@op`` when it is called: the function with the types its parameters and results were
 given (annotation, inference or the producing op — core/call.py), and the concrete arguments of one call.  Same
-attribute surface as pylzy/lzy/api/v1/signatures.py:19-47, which the reference's tests read
+attribute surface as pylzy/lzy/api/v1/signatures.py:19-46, which the reference's tests read
 (tests/core/test_calls.py)."""
 from __future__ import annotations
 

@@ -1,4 +1,4 @@
-"""Type helpers for @op signatures (pylzy/lzy/api/v1/utils/types.py:23-83)."""
+"""Type helpers for @op signatures (pylzy/lzy/api/v1/utils/types.py:23-79)."""
 from __future__ import annotations
 
 import inspect

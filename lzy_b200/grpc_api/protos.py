@@ -10,7 +10,7 @@
   ai/lzy/v1/common/env.proto:10-52             EnvSpec, PythonEnv, ProcessEnv, LocalModule, DockerCredentials, DockerPullPolicy
   ai/lzy/v1/common/slot.proto:10-29            Slot{Media, Direction}
   ai/lzy/v1/common/operation.proto:12-45       Operation, Requirements, SlotToChannelAssignment, TaskDesc, KafkaTopicDescription
-  ai/lzy/v1/worker/worker-service.proto:14-53  WorkerApi: Init*, Execute*
+  ai/lzy/v1/worker/worker-service.proto:14-50  WorkerApi: Init*, Execute*
   ai/lzy/v1/long-running/operation.proto:12-47 LongRunningService.Get, Operation (google.rpc.Status restated: code, message, details)
 
 A message serialized here parses with the reference's generated classes and vice versa (same

@@ -1,6 +1,6 @@
 """Lazy proxies: an object that looks like the result of an @op but is computed at the last moment.
 
-Same observable contract as the reference's ``lzy.proxy.proxy`` (pylzy/lzy/proxy/automagic.py:150-240
+Same observable contract as the reference's ``lzy.proxy.proxy`` (pylzy/lzy/proxy/automagic.py:150-189
 and pylzy/lzy/api/v1/utils/proxy_adapter.py:14-83):
 
 * the proxy's *class* carries ``cls_attrs`` (``__lzy_proxied__``, ``__lzy_entry_id__`` …);

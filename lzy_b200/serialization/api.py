@@ -1,7 +1,7 @@
 """Serializer interface and registry.
 
 Shape of the third-party ``serialzy`` API the reference builds on (visible through
-pylzy/lzy/serialization/file.py:16-88, pylzy/lzy/serialization/registry.py:20-82 and
+pylzy/lzy/serialization/file.py:16-87, pylzy/lzy/serialization/registry.py:20-82 and
 pylzy/tests/scenarios/custom_serializer/serializer.py:9-33): a serializer says which types it
 handles, writes an object to a binary stream with **no framing of its own added by the base class**,
 reads it back, and describes the data with a ``Schema``.  When the real ``serialzy`` is importable

@@ -3,7 +3,7 @@
 The reference takes ``get_type`` and ``EmptyContent`` from the un-vendored ``serialzy.types``
 (call sites: pylzy/lzy/core/call.py:12-14,307,326; pylzy/lzy/api/v1/startup.py:15,63); the behaviour
 restated here is the one its tests rely on (pylzy/tests/core/test_workflow.py:73-128,290-330 and
-pylzy/lzy/api/v1/utils/types.py:76-83): containers are typed by their first element, empty containers
+pylzy/lzy/api/v1/utils/types.py:76-79): containers are typed by their first element, empty containers
 are typed with the ``EmptyContent`` marker, which is compatible with any element type."""
 from __future__ import annotations
 

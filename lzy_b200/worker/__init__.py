@@ -1,5 +1,5 @@
 """The worker's staging step either side of the slot data plane — ``WorkerApi.Init`` / ``WorkerApi.Execute``
-(lzy/worker-api/src/main/proto/ai/lzy/v1/worker/worker-service.proto:14-53) as the reference's
+(lzy/worker-api/src/main/proto/ai/lzy/v1/worker/worker-service.proto:14-50) as the reference's
 ``WorkerApiImpl`` performs them (lzy/worker/src/main/java/ai/lzy/worker/WorkerApiImpl.java:85-300), so the
 reference's scheduler / graph executor can drive a per-GPU worker of this repository unchanged:
 

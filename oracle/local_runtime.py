@@ -69,7 +69,7 @@ class HashingIO:
         return getattr(self.__dict__["io_stream"], name)
 
 
-def path_from_uri(uri: str) -> str:  # fs.py:53-57
+def path_from_uri(uri: str) -> str:  # fs.py:53-56
     parsed = urlparse(uri)
     return os.path.abspath(os.path.join(parsed.netloc, parsed.path))
 

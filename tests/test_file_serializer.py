@@ -1,5 +1,5 @@
 """`FileSerializer` — the one serializer whose bytes the reference itself defines (SURVEY §8 row a8,
-pylzy/lzy/serialization/file.py:16-88): ``b"permissions"`` + ``oct(mode & 0o777)`` + the file's bytes, with a
+pylzy/lzy/serialization/file.py:16-87): ``b"permissions"`` + ``oct(mode & 0o777)`` + the file's bytes, with a
 header-less stream still accepted.  Scenarios of pylzy/tests/serialization/test_file.py:32-126, plus the exact
 bytes."""
 import logging
