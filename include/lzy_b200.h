@@ -201,7 +201,9 @@ int lzyb_input_open(const char* slot_id, int gpu, uint64_t nbytes, lzyb_handle_t
  * multiple of 16.  Same-GPU peers are an HBM copy; other GPUs are read over NVLink through the
  * peer mapping.  Returns bytes moved, LZYB_EOF when offset == nbytes, LZYB_E_PEER / LZYB_E_LOCAL.
  * stream == NULL: runs on the library's copy stream of dst's GPU and returns after completion
- * (Java-like blocking); otherwise asynchronous on `stream`. */
+ * (Java-like blocking); otherwise asynchronous on `stream`.  Asynchronous callers keep `src_peer` open until
+ * `stream` has passed the transfer (lzyb_input_finish, which waits for the verdict, is such a point): closing the
+ * last reference of a frame waits for the writes into it, not for readers the library was not told about. */
 int64_t lzyb_transfer_chunk(lzyb_handle_t dst, lzyb_handle_t src_peer, uint64_t offset,
                             uint64_t max_len, void* stream);
 /* End of stream (the EOS control message, slots-api.proto:33-47): compare the accumulated
