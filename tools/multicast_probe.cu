@@ -56,6 +56,21 @@ __global__ void __launch_bounds__(256) multicast_copy(const uint4* __restrict__ 
         if (base + j * 256ull < nvec) multimem_st_v4(mc_dst + base + j * 256ull, v[j]);
 }
 
+// persistent variant: 4 CTAs per SM walk the tiles grid-stride (fewer, longer-lived store streams)
+__global__ void __launch_bounds__(256) multicast_copy_persistent(const uint4* __restrict__ src, uint4* mc_dst, unsigned long long nvec) {
+    const unsigned long long ntiles = (nvec + 2047) / 2048;
+    for (unsigned long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const unsigned long long base = t * 2048ull + threadIdx.x;
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (base + j * 256ull < nvec) v[j] = src[base + j * 256ull];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (base + j * 256ull < nvec) multimem_st_v4(mc_dst + base + j * 256ull, v[j]);
+    }
+}
+
 __global__ void fill(uint4* p, unsigned long long nvec) {
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nvec; i += (unsigned long long)gridDim.x * blockDim.x)
         p[i] = make_uint4((unsigned)i, (unsigned)(i >> 32) ^ 0x9e3779b9u, (unsigned)(i * 2654435761ull), 0x7fc00001u /* a NaN pattern: bits must survive */);
@@ -162,6 +177,33 @@ int main() {
         RT(cudaEventElapsedTime(&ms, e0, e1));
         ms /= reps;
 
+        // other carriers of the same multicast stream: a persistent SM kernel, and the copy engine writing the
+        // multicast mapping directly
+        float ms_persist = 0, ms_ce = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            RT(cudaEventRecord(e0));
+            for (int r = 0; r < (pass ? reps : 2); ++r) multicast_copy_persistent<<<148 * 4, 256>>>(src, (uint4*)mcva, nvec);
+            RT(cudaEventRecord(e1));
+            RT(cudaEventSynchronize(e1));
+        }
+        RT(cudaGetLastError());
+        RT(cudaEventElapsedTime(&ms_persist, e0, e1));
+        ms_persist /= reps;
+        bool ce_ok = true;
+        for (int pass = 0; pass < 2 && ce_ok; ++pass) {
+            RT(cudaEventRecord(e0));
+            for (int r = 0; r < (pass ? reps : 2); ++r)
+                if (cudaMemcpyAsync((void*)mcva, src, payload, cudaMemcpyDeviceToDevice) != cudaSuccess) ce_ok = false;
+            RT(cudaEventRecord(e1));
+            if (cudaEventSynchronize(e1) != cudaSuccess) ce_ok = false;
+        }
+        if (ce_ok) {
+            RT(cudaEventElapsedTime(&ms_ce, e0, e1));
+            ms_ce /= reps;
+        } else {
+            cudaGetLastError();
+        }
+
         unsigned long long bad_total = 0;
         for (int d = 0; d < team; ++d) {
             RT(cudaSetDevice(d));
@@ -193,8 +235,9 @@ int main() {
         ums /= reps;
 
         printf("{\"team\": %d, \"receivers\": %d, \"payload_GiB\": 1, \"multicast_ms\": %.4f, \"multicast_GBps_per_receiver\": %.1f, "
-               "\"unicasts_ms\": %.4f, \"mismatching_samples\": %llu, \"granularity\": %zu}\n",
-               team, team - 1, ms, payload / ms / 1e6, ums, bad_total, gran);
+               "\"multicast_persistent_ms\": %.4f, \"multicast_copy_engine_ms\": %.4f, \"unicasts_ms\": %.4f, "
+               "\"mismatching_samples\": %llu, \"granularity\": %zu}\n",
+               team, team - 1, ms, payload / ms / 1e6, ms_persist, ms_ce, ums, bad_total, gran);
         fflush(stdout);
 
         for (int d = 1; d < team; ++d) cudaStreamDestroy(st[d]);
