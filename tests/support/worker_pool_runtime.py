@@ -1,0 +1,285 @@
+"""TEST INFRASTRUCTURE: a `Runtime` that executes a workflow's calls the way the reference's *remote* stack does —
+pylzy's RemoteRuntime builds one task per call (slots "/{call.id}/{entry.id}", a command line carrying the pickled
+ProcessingRequest, pylzy/lzy/api/v1/remote/runtime.py:303-420), lzy-service creates one channel per data URI
+(CreateChannels.java:75-104), the graph executor releases tasks whose producers have finished
+(BfsGraphProcessor.java:176-258) and each task goes to a worker as WorkerApi.Execute — composed from this
+repository's own parts: `GraphDispatcher`, `ChannelManager`, `lzy_b200.worker.Worker`, `api.v1.startup`, the C++
+slots runtime.  Slots run over the in-memory test backend and payloads are serializer byte streams, so the whole
+stack runs without a GPU; the reference's workflow scenarios can then be asserted on the driver's CPU box too
+(tests/test_workflow_host.py).  The product's own runtime for a GPU box is `B200Runtime`.
+"""
+from __future__ import annotations
+
+import hashlib
+import time
+import uuid
+from io import BytesIO
+from typing import Any, Callable, Dict, List, Optional, Type
+
+from lzy_b200 import _host as H
+from lzy_b200.api.v1.exceptions import LzyExecutionException
+from lzy_b200.api.v1.runtime import ProgressStep, Runtime
+from lzy_b200.api.v1.snapshot import Snapshot, SnapshotEntry
+from lzy_b200.api.v1.startup import ProcessingRequest
+from lzy_b200.api.v1.utils.pickle import pickle
+from lzy_b200.proxy_result import Absence, Result
+from lzy_b200.utils import tbpickle
+from lzy_b200.worker import DIR_INPUT, DIR_OUTPUT, SlotSpec, TaskSpec, Worker
+from tests.support import hostmem
+
+tbpickle.install()
+
+
+class BlobSnapshot(Snapshot):
+    """`DefaultSnapshot`'s rules (pylzy/lzy/api/v1/snapshot.py:93-191) over the C++ host blob store: the payload is
+    the serializer's byte stream, the URI of local data is prefix + md5 of those bytes, equal data is stored once."""
+
+    def __init__(self, registry, prefix: str, storage_name: str = "mem"):
+        self.registry, self.prefix, self.storage_name = registry, prefix, storage_name
+        self.entries: Dict[str, SnapshotEntry] = {}
+        self.store_counts: Dict[str, int] = {}
+
+    def create_entry(self, name: str, typ: Type) -> SnapshotEntry:
+        ser = self.registry.find_serializer_by_type(typ)
+        if ser is None:
+            raise TypeError(f"Cannot find serializer for type {typ}")
+        if not ser.available():
+            raise TypeError(f"Serializer for type {typ} is not available, please install {ser.requirements()}")
+        e = SnapshotEntry(str(uuid.uuid4()), name, typ, ser.schema(typ), self.storage_name)
+        self.entries[e.id] = e
+        return e
+
+    def get(self, entry_id: str) -> SnapshotEntry:
+        return self.entries[entry_id]
+
+    async def put_data(self, entry_id: str, data: Any) -> None:
+        e = self.entries.get(entry_id)
+        if e is None:
+            raise ValueError(f"Entry with id={entry_id} does not exist")
+        buf = BytesIO()
+        self.registry.find_serializer_by_type(e.typ).serialize(data, buf)
+        raw = buf.getvalue()
+        e.data_hash = hashlib.md5(raw).hexdigest()
+        e.storage_uri = self.prefix + "/" + e.data_hash
+        if not H.blob_exists(e.storage_uri):
+            H.blob_put(e.storage_uri, raw)
+            self.store_counts[e.storage_uri] = self.store_counts.get(e.storage_uri, 0) + 1
+
+    async def get_data(self, entry_id: str):
+        e = self.entries.get(entry_id)
+        if e is None:
+            raise ValueError(f"Entry with id={entry_id} does not exist")
+        try:
+            uri = e.storage_uri
+        except ValueError as err:
+            return Absence(err)
+        if not H.blob_exists(uri):
+            return Absence(ValueError(f"Cannot find blob in storage by uri={uri}"))
+        ser = self.registry.find_serializer_by_type(e.typ)
+        return Result(ser.deserialize(BytesIO(H.blob_get(uri)), e.typ if isinstance(e.typ, type) else None))
+
+    async def copy_data(self, from_entry_id: str, to_uri: str) -> None:
+        H.blob_put(to_uri, H.blob_get(self.entries[from_entry_id].storage_uri))
+
+    def uris(self) -> List[str]:
+        return [e._storage_uri for e in self.entries.values() if e._storage_uri]
+
+
+class WorkerPoolRuntime(Runtime):
+    def __init__(self, n_workers: int = 2, user_id: str = "test-user"):
+        self.n_workers, self.user_id = n_workers, user_id
+        self.cm: Optional[H.ChannelManager] = None
+        self.workers: List[Worker] = []
+        self.workflow = None
+        self.execution_id: Optional[str] = None
+        self.calls: List[Any] = []          # every call ever handed to exec (what RuntimeMock records)
+        self.executed: List[str] = []       # callable names in the order tasks were released
+        self.skipped_cached = 0
+        self._snapshots: List[BlobSnapshot] = []
+        self._rr = 0
+        self._owner = None
+        self._generation = 0
+
+    # ---- bring-up / teardown ---------------------------------------------------------------------------------
+    def _ensure(self) -> None:
+        if self.cm is not None:
+            return
+        hostmem.install()
+        self.cm = H.ChannelManager(seed=1)
+        H.pump_start(self.cm)
+
+    def _allocate(self, workflow_name: str) -> None:
+        """the allocator's part: a worker serves one (user, workflow) owner (WorkerApiImpl.java:232-283), so another
+        workflow gets fresh workers"""
+        if self.workers and self._owner == (self.user_id, workflow_name):
+            return
+        for w in self.workers:
+            w.close()
+        self._generation += 1
+        self.workers = [Worker(self.cm, 0, f"lzyb://pool-worker-{self._generation}-{i}", mount_factory=hostmem.HostmemMount)
+                        for i in range(self.n_workers)]
+        self._owner = (self.user_id, workflow_name)
+        for w in self.workers:
+            w.init(self.user_id, workflow_name)
+
+    def close(self) -> None:
+        if self.cm is None:
+            return
+        for w in self.workers:
+            w.close()
+        H.pump_stop(self.cm)
+        self.cm.close()
+        self.cm, self.workers = None, []
+        for snap in self._snapshots:
+            for uri in snap.uris():
+                H.blob_delete(uri)
+        self._snapshots.clear()
+        hostmem.uninstall()
+
+    # ---- Runtime ABC ---------------------------------------------------------------------------------------------
+    async def storage(self):
+        return None
+
+    def snapshot(self, workflow, storage_uri_prefix: str) -> Snapshot:
+        snap = BlobSnapshot(workflow.owner.serializer_registry, storage_uri_prefix)
+        self._snapshots.append(snap)
+        return snap
+
+    async def start(self, workflow) -> str:
+        self._ensure()
+        self._allocate(workflow.name)
+        self.workflow = workflow
+        self.execution_id = str(uuid.uuid4())
+        return self.execution_id
+
+    async def abort(self) -> None:
+        self._finish("aborted")
+
+    async def finish(self) -> None:
+        self._finish("finished")
+
+    def _finish(self, reason: str) -> None:
+        if self.cm is not None and self.execution_id:
+            for w in self.workers:
+                w.release_execution(self.execution_id)
+            self.cm.destroy_all(self.execution_id, reason)
+            self.execution_id = None
+
+    async def exec(self, calls, progress: Callable[[ProgressStep], None]) -> None:
+        import asyncio
+        self.calls.extend(calls)
+        progress(ProgressStep.WAITING)
+        try:
+            await asyncio.get_running_loop().run_in_executor(None, self._exec_graph, list(calls), progress)
+        except BaseException:
+            progress(ProgressStep.FAILED)
+            raise
+        progress(ProgressStep.COMPLETED)
+
+    # ---- the graph ---------------------------------------------------------------------------------------------------
+    def _exec_graph(self, calls: List[Any], progress) -> None:
+        wf, cm = self.workflow, self.cm
+        snap: BlobSnapshot = wf.snapshot
+        registry = wf.owner.serializer_registry
+        exec_id = self.execution_id
+
+        # ops whose outputs are all already supplied are dropped (lzy-service DataFlowGraph.java:51-72)
+        todo = []
+        for c in calls:
+            if c.cache and c.entry_ids and all(H.blob_exists(snap.get(e).storage_uri) for e in c.entry_ids):
+                self.skipped_cached += 1
+                continue
+            todo.append(c)
+        if not todo:
+            return
+        producer_of = {eid: i for i, c in enumerate(todo) for eid in c.entry_ids}
+
+        # CreateChannels: one channel per data URI; results get a storage consumer, existing data a storage producer
+        channel: Dict[str, str] = {}
+        for c in todo:
+            for eid in list(c.entry_ids) + [c.exception_id]:
+                channel[eid] = cm.get_or_create(self.user_id, wf.name, exec_id, consumer_uri=snap.get(eid).storage_uri)
+        tasks: List[TaskSpec] = []
+        edges = set()
+        for i, c in enumerate(todo):
+            slots, assign = [], {}
+            args_paths, kwargs_paths, outs = [], {}, []
+
+            def input_slot(eid):
+                if eid not in channel:
+                    uri = snap.get(eid).storage_uri
+                    if not H.blob_exists(uri):
+                        raise ValueError(f"Cannot find blob in storage by uri={uri}")
+                    channel[eid] = cm.get_or_create(self.user_id, wf.name, exec_id, producer_uri=uri)
+                if eid in producer_of and producer_of[eid] != i:
+                    edges.add((producer_of[eid], i))
+                path = f"/{c.id}/{eid}"
+                if path not in assign:
+                    assign[path] = channel[eid]
+                    slots.append(SlotSpec(path, DIR_INPUT))
+                return snap.get(eid).typ, path
+
+            for eid in c.arg_entry_ids:
+                args_paths.append(input_slot(eid))
+            for name, eid in c.kwarg_entry_ids.items():
+                kwargs_paths[name] = input_slot(eid)
+            for eid in c.entry_ids:
+                path = f"/{c.id}/{eid}"
+                assign[path] = channel[eid]
+                slots.append(SlotSpec(path, DIR_OUTPUT))
+                outs.append((snap.get(eid).typ, path))
+            exc_path = f"/{c.id}/{c.exception_id}"
+            assign[exc_path] = channel[c.exception_id]
+            slots.append(SlotSpec(exc_path, DIR_OUTPUT))
+            request = ProcessingRequest({}, registry.imports(), c.signature.func.callable, args_paths, kwargs_paths, outs,
+                                        (tuple, exc_path), lazy_arguments=c.lazy_arguments)
+            command = " ".join(["python -u", "$(python -c 'import lzy.api.v1.startup as startup; print(startup.__file__)')",
+                                pickle(request)])
+            tasks.append(TaskSpec(task_id=c.id, execution_id=exec_id, workflow_name=wf.name, user_id=self.user_id,
+                                  command=command, slots=slots, slot_assignments=assign, name=c.callable_name))
+
+        graph = H.GraphDispatcher(len(todo), sorted(edges), allow_cycles=False)
+        running: Dict[int, Any] = {}
+        failed: Optional[int] = None
+        progress(ProgressStep.EXECUTING)
+        try:
+            deadline = time.time() + 120
+            while graph.status not in (H.G_COMPLETED, H.G_FAILED):
+                if time.time() > deadline:
+                    raise LzyExecutionException("graph did not finish in time")
+                for t in graph.next():
+                    worker = self.workers[self._rr % len(self.workers)]
+                    self._rr += 1
+                    self.executed.append(todo[t].callable_name)
+                    running[t] = (worker, worker.execute(tasks[t]).id)
+                for t, (worker, op_id) in list(running.items()):
+                    op = worker.get_operation(op_id)
+                    if not op.done:
+                        continue
+                    del running[t]
+                    ok = op.error is None and op.response is not None and op.response.rc == 0
+                    if not ok and failed is None:
+                        failed = t
+                    graph.task_done(t, ok, "" if ok else (op.response.description if op.response else str(op.error)))
+                time.sleep(0.001)
+            if failed is not None or graph.status == H.G_FAILED:
+                self._raise_failure(todo[failed] if failed is not None else None, snap, graph)
+        finally:
+            for worker, op_id in running.values():  # tasks still in flight when the graph stopped
+                worker.wait_operation(op_id, timeout=30)
+            graph.close()
+
+    def _raise_failure(self, call, snap: BlobSnapshot, graph) -> None:
+        """RemoteRuntime.exec's Failed branch (remote/runtime.py:190-205): re-raise the op's own exception"""
+        if call is not None:
+            uri = snap.get(call.exception_id).storage_uri
+            deadline = time.time() + 10
+            while not H.blob_exists(uri) and time.time() < deadline:  # the exception slot uploads asynchronously
+                time.sleep(0.005)
+            if H.blob_exists(uri):
+                ser = snap.registry.find_serializer_by_type(tuple)
+                info = ser.deserialize(BytesIO(H.blob_get(uri)), tuple)
+                if info is not None:
+                    raise info[1].with_traceback(info[2])
+        _, description, _ = graph.error()
+        raise LzyExecutionException(f"Failed executing graph: {description}")
