@@ -34,6 +34,7 @@ from typing import TYPE_CHECKING, Any, Callable, Dict, List, Optional, Sequence,
 from .... import _host as H
 from .... import _native as N
 from ....devmem import current_stream_ptr
+from ....env import applied_env
 from ....proxy import proxy
 from ....serialization.types import get_type
 from ....utils import op_scope, tbpickle
@@ -477,7 +478,7 @@ class B200Runtime(Runtime):
             stream = self._streams[gpu]
             op_scope.enter()
             try:
-                with torch.cuda.device(gpu), torch.cuda.stream(stream):
+                with torch.cuda.device(gpu), torch.cuda.stream(stream), applied_env(call.get_env_vars()):
                     res = func(*args, **kwargs)
             finally:
                 op_scope.leave()

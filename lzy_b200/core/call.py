@@ -20,7 +20,7 @@ from ..api.v1.signatures import CallSignature, FuncSignature
 from ..api.v1.snapshot import Snapshot
 from ..api.v1.utils.proxy_adapter import get_proxy_entry_id, is_lzy_proxy, lzy_proxy, materialize, materialized
 from ..api.v1.utils.types import check_types_serialization_compatible, get_default_args, infer_real_types, is_subtype
-from ..env import LzyEnvironment, Provisioning
+from ..env import LzyEnvironment, Provisioning, WithEnvironmentMixin
 from ..serialization.api import SerializerRegistry
 from ..serialization.types import get_type
 from ..utils.event_loop import LzyEventLoop
@@ -125,7 +125,7 @@ class LzyCall:
 
 
 @dataclass(frozen=True)
-class LazyCallWrapper:
+class LazyCallWrapper(WithEnvironmentMixin):
     function: Callable[..., Any]
     output_types: Sequence[type]
     env: LzyEnvironment

@@ -8,7 +8,7 @@ from typing import Any, ClassVar, Optional, Type
 
 from ..api.v1.runtime import Runtime
 from ..api.v1.snapshot import Snapshot
-from ..env import LzyEnvironment
+from ..env import LzyEnvironment, WithEnvironmentMixin
 from ..serialization.registry import LzySerializerRegistry
 from .workflow import LzyWorkflow
 
@@ -19,7 +19,7 @@ def _default_runtime() -> Runtime:
 
 
 @dataclass(frozen=True)
-class Lzy:
+class Lzy(WithEnvironmentMixin):
     env: LzyEnvironment = field(default_factory=LzyEnvironment)
     runtime: Runtime = field(default_factory=_default_runtime)
     serializer_registry: LzySerializerRegistry = field(default_factory=LzySerializerRegistry)

@@ -9,12 +9,12 @@ from __future__ import annotations
 import logging
 import os
 import re
-from dataclasses import dataclass
+from dataclasses import dataclass, replace
 from typing import TYPE_CHECKING, Any, ClassVar, List, Optional, Set
 
 from ..api.v1.snapshot import Snapshot
 from ..api.v1.utils.hashing import md5_of_str
-from ..env import LzyEnvironment
+from ..env import LzyEnvironment, WithEnvironmentMixin
 from ..utils import op_scope
 from ..utils.event_loop import LzyEventLoop
 
@@ -29,13 +29,17 @@ _LOG = logging.getLogger("lzy_b200.workflow")
 
 
 @dataclass
-class LzyWorkflow:
+class LzyWorkflow(WithEnvironmentMixin):
     instance: ClassVar[Optional["LzyWorkflow"]] = None
     name: str
     owner: "Lzy"
     env: LzyEnvironment
     eager: bool = False
     interactive: bool = True
+
+    def with_fields(self, **kwargs: Any) -> "LzyWorkflow":
+        """a copy with some declaration changed — before the workflow is entered (pylzy/lzy/env/base.py Deconstructible)"""
+        return replace(self, **kwargs)
 
     @classmethod
     def get_active(cls) -> Optional["LzyWorkflow"]:

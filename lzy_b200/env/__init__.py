@@ -1,9 +1,16 @@
 """Minimal environment objects.  Environment capture (conda/pip/docker, pylzy/lzy/env/*) is out of scope
-for the data plane; ``Provisioning.gpu_count`` is read only to place an op."""
+for the data plane; ``Provisioning.gpu_count`` is read only to place an op.  What is kept is the
+part an op can observe: environment variables declared on ``Lzy``, a workflow or an ``@op`` reach the op body
+(pylzy/tests/scenarios/complex_graph/__init__.py:12-20), later levels overriding earlier ones
+(pylzy/lzy/core/call.py:58-61), through the same ``with_env_vars`` / ``with_provisioning`` / ``with_env`` methods
+(pylzy/lzy/env/mixin.py:18-75)."""
 from __future__ import annotations
 
+import contextlib
+import os
+import threading
 from dataclasses import dataclass, field, replace
-from typing import Any, Dict, Optional
+from typing import Any, Dict, Mapping, Optional
 
 
 @dataclass(frozen=True)
@@ -39,3 +46,54 @@ class LzyEnvironment:
 
     def get_env_vars(self) -> Dict[str, str]:
         return self.env_vars
+
+
+class WithEnvironmentMixin:
+    """``with_env`` / ``with_env_vars`` / ``with_provisioning`` for anything that has an ``env`` and a
+    ``with_fields`` (``Lzy``, ``LzyWorkflow``) or its own ``with_env`` (the ``@op`` wrapper).  Each call returns a
+    new object; a level's declaration replaces that level's field, levels combine at call time."""
+    env: LzyEnvironment
+
+    def with_env(self, env: LzyEnvironment):
+        return self.with_fields(env=env)  # type: ignore[attr-defined]
+
+    def with_env_vars(self, *args: Mapping[str, str], **kwargs: str):
+        if args and kwargs or len(args) > 1:
+            raise NotImplementedError("wrong argument types")
+        env_vars = dict(args[0]) if args else dict(kwargs)
+        for k, v in env_vars.items():
+            if not isinstance(k, str) or not isinstance(v, str):
+                raise TypeError("environment variables are str → str")
+        return self.with_env(self.env.with_fields(env_vars=env_vars))
+
+    def with_provisioning(self, *args: Provisioning, **kwargs: Any):
+        if args and kwargs or len(args) > 1:
+            raise NotImplementedError("wrong argument types")
+        if args and not isinstance(args[0], Provisioning):
+            raise TypeError("bad argument types")
+        provisioning = args[0] if args else Provisioning(**kwargs)
+        return self.with_env(self.env.with_fields(provisioning=provisioning))
+
+
+_ENV_LOCK = threading.RLock()
+
+
+@contextlib.contextmanager
+def applied_env(env_vars: Optional[Mapping[str, str]]):
+    """Run a block with `env_vars` in ``os.environ`` (restored afterwards).  The reference gives every op its own
+    process; here ops of one worker share one, so blocks that set variables take turns while ops that declare
+    none do not wait for anybody."""
+    if not env_vars:
+        yield
+        return
+    with _ENV_LOCK:
+        saved = {k: os.environ.get(k) for k in env_vars}
+        os.environ.update({k: str(v) for k, v in env_vars.items()})
+        try:
+            yield
+        finally:
+            for k, old in saved.items():
+                if old is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = old

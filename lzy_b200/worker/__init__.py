@@ -33,6 +33,7 @@ import uuid
 from typing import Any, Callable, Dict, List, Mapping, Optional, Sequence, Tuple
 
 from .. import _host as H
+from ..env import applied_env
 
 _LOG = logging.getLogger(__name__)
 
@@ -103,6 +104,14 @@ class Operation:
 MountFactory = Callable[[H.ExecutionContext], Any]
 EnvFactory = Callable[[Any], Any]
 CommandRunner = Callable[[str, H.ExecutionContext, "Worker"], int]
+
+
+def _env_vars(spec: Any) -> Dict[str, str]:
+    """a plain mapping, or an ``LME.EnvSpec`` message whose ``env`` field is the map (env.proto:10-21)"""
+    if spec is None:
+        return {}
+    inner = getattr(spec, "env", None)
+    return dict(inner) if inner is not None and not callable(inner) else dict(spec) if isinstance(spec, Mapping) else {}
 
 
 def run_startup_in_process(command: str, ctx: H.ExecutionContext, worker: "Worker") -> int:
@@ -249,7 +258,8 @@ class Worker:
                 ctx.add_slot(slot.name, task.slot_assignments[slot.name], slot.direction)
             _LOG.info("Waiting for slots...")
             ctx.before_execution(-1)
-            rc = self.command_runner(task.command, ctx, self)
+            with applied_env(_env_vars(task.env)):  # Operation.env.env: the variables the op asked for
+                rc = self.command_runner(task.command, ctx, self)
             if rc == 0:
                 message = "Success"
                 ctx.after_execution(-1)

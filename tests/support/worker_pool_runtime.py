@@ -86,6 +86,8 @@ class BlobSnapshot(Snapshot):
 
 
 class WorkerPoolRuntime(Runtime):
+    _live = 0  # runtimes that installed the in-memory backend: the last one to close removes it
+
     def __init__(self, n_workers: int = 2, user_id: str = "test-user"):
         self.n_workers, self.user_id = n_workers, user_id
         self.cm: Optional[H.ChannelManager] = None
@@ -105,6 +107,7 @@ class WorkerPoolRuntime(Runtime):
         if self.cm is not None:
             return
         hostmem.install()
+        WorkerPoolRuntime._live += 1
         self.cm = H.ChannelManager(seed=1)
         H.pump_start(self.cm)
 
@@ -134,7 +137,9 @@ class WorkerPoolRuntime(Runtime):
             for uri in snap.uris():
                 H.blob_delete(uri)
         self._snapshots.clear()
-        hostmem.uninstall()
+        WorkerPoolRuntime._live -= 1
+        if WorkerPoolRuntime._live == 0:
+            hostmem.uninstall()
 
     # ---- Runtime ABC ---------------------------------------------------------------------------------------------
     async def storage(self):
@@ -236,7 +241,8 @@ class WorkerPoolRuntime(Runtime):
             command = " ".join(["python -u", "$(python -c 'import lzy.api.v1.startup as startup; print(startup.__file__)')",
                                 pickle(request)])
             tasks.append(TaskSpec(task_id=c.id, execution_id=exec_id, workflow_name=wf.name, user_id=self.user_id,
-                                  command=command, slots=slots, slot_assignments=assign, name=c.callable_name))
+                                  command=command, slots=slots, slot_assignments=assign, name=c.callable_name,
+                                  env=c.get_env_vars()))
 
         graph = H.GraphDispatcher(len(todo), sorted(edges), allow_cycles=False)
         running: Dict[int, Any] = {}

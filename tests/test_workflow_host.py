@@ -119,3 +119,158 @@ def test_diamond_runs_in_dependency_order_and_a_failure_stops_the_graph(lzy, wor
             out = sink(branch(s, 1), bad(s))
             materialize(out)
     assert "sink" not in lzy.runtime.executed[before:]  # its producers never both succeeded
+
+
+# ---- the reference's end-to-end scenarios (pylzy/tests/scenarios/*; PyApiTest.java:17-138 diffs their stdout) -------
+def test_scenario_complex_graph_env_vars_and_none(lzy, workflow_name, capsys):
+    """complex_graph/__init__.py:6-28, expected output `39 40 41 a=1,b=1 kek None 42`"""
+    import os
+
+    @op
+    def repeatable_op(a: int) -> int:
+        print(a)
+        return a + 1
+
+    @op
+    def just_return_none(a: int, b: int) -> None:
+        print(f"a={a},b={b}")
+        print(os.environ["LOL"])
+        return None
+
+    assert "LOL" not in os.environ
+    with lzy.workflow(workflow_name, interactive=False).with_env_vars({"LOL": "kek"}):
+        a = 39
+        for _ in range(3):
+            a = repeatable_op(a)
+        res = just_return_none(1, 1)
+        print(res)
+        print(a)
+    words = capsys.readouterr().out.split()
+    # the independent op may run beside the chain on the other worker: same lines, chain order kept
+    assert sorted(words) == sorted(["None", "39", "40", "41", "a=1,b=1", "kek", "42"])
+    assert [w for w in words if w in ("39", "40", "41", "42")] == ["39", "40", "41", "42"]
+    assert words.index("a=1,b=1") + 1 == words.index("kek") and words[0] == "None"
+    assert "LOL" not in os.environ  # restored after the op
+
+
+def test_env_vars_combine_lzy_then_workflow_then_op(workflow_name):
+    import os
+
+    from tests.support.worker_pool_runtime import WorkerPoolRuntime
+
+    @op
+    def read() -> str:
+        return ",".join(os.environ.get(k, "-") for k in ("A", "B", "C"))
+
+    rt = WorkerPoolRuntime(n_workers=1)
+    try:
+        lzy = Lzy(runtime=rt, storage_uri="mem://bucket/env").with_env_vars(A="lzy", B="lzy", C="lzy")
+        with lzy.workflow(workflow_name).with_env_vars(B="wf", C="wf"):
+            assert read.with_env_vars({"C": "op"})() == "lzy,wf,op"
+            assert read() == "lzy,wf,wf"
+    finally:
+        rt.close()
+
+
+def test_scenario_exception_reaches_the_caller_and_is_not_cached(lzy, workflow_name, capsys):
+    """exception_serialize, exec_fail and cached_exception: the op's own exception type comes back, and a failed
+    cache=True op runs again next time (there is no result to reuse)"""
+    @op(cache=True, version="1.0")
+    def raises() -> None:
+        print("exception was raised")
+        raise ValueError("test")
+
+    for _ in range(2):
+        with pytest.raises(ValueError, match="test"):
+            with lzy.workflow(workflow_name, interactive=False):
+                raises()
+    assert capsys.readouterr().out.count("exception was raised") == 2
+
+
+def test_scenario_repeated_ops_and_executions_use_the_cache(lzy, workflow_name, capsys):
+    """repeated_execs_use_cache + fully_cached_graph: `foo was called` once, bar (cache=False) every time, a fully
+    cached second execution starts no task at all"""
+    @op(cache=True, version="1.1")
+    def foo_with_print(name: str, value: int) -> str:
+        print("foo was called")
+        return f"{name} is {value}"
+
+    @op(cache=False)
+    def bar_with_print(message: str) -> str:
+        return f"message from bar: {message}"
+
+    @op(cache=True, version="1.0")
+    def cached_bar(message: str) -> str:
+        print("bar was called")
+        return f"message from bar: {message}"
+
+    with lzy.workflow(workflow_name, interactive=False):
+        for _ in range(3):
+            assert bar_with_print(foo_with_print("number", 42)) == "message from bar: number is 42"
+    with lzy.workflow(workflow_name, interactive=False):
+        assert bar_with_print(foo_with_print("number", 42)) == "message from bar: number is 42"
+    assert capsys.readouterr().out.count("foo was called") == 1
+
+    before = len(lzy.runtime.executed)
+    for _ in range(2):
+        with lzy.workflow(workflow_name, interactive=False):
+            assert cached_bar(foo_with_print("number", 42)) == "message from bar: number is 42"
+    out = capsys.readouterr().out
+    assert out.count("bar was called") == 1 and "foo was called" not in out
+    assert lzy.runtime.executed[before:] == ["cached_bar"]
+
+
+def test_scenario_two_executions_of_one_workflow_name(lzy, workflow_name):
+    @op
+    def return_42() -> int:
+        return 42
+
+    @op
+    def return_13() -> int:
+        return 13
+
+    with lzy.workflow(workflow_name, interactive=False):
+        assert return_42() == 42
+    with lzy.workflow(workflow_name, interactive=False):
+        assert return_13() == 13
+
+
+def test_scenario_files_travel_by_content(lzy, workflow_name, tmp_path):
+    """file_test/__init__.py:14-58 without the whiteboard half: a File nested in a dataclass argument, three File
+    results, contents intact and independent of the caller's files"""
+    import dataclasses
+
+    from lzy_b200.types import File
+
+    @dataclasses.dataclass
+    class CustomFileField:
+        file: File
+
+    b_path, c_path = str(tmp_path / "b.txt"), str(tmp_path / "c.txt")
+
+    @op
+    def a(f1: CustomFileField) -> (File, File, File):
+        with f1.file.open("a") as fl:
+            fl.write("buzz")
+        with open(b_path, "w") as fl:
+            fl.write("Lol")
+        with open(c_path, "w") as fl:
+            fl.write("Kek")
+        return f1.file, File(b_path), File(c_path)
+
+    @op
+    def b() -> (int, str):
+        return 42, "42"
+
+    src = tmp_path / "a.txt"
+    src.write_text("fizz")
+    with lzy.workflow(workflow_name, interactive=False):
+        f1, f2, f3 = a(CustomFileField(File(str(src))))
+        texts = []
+        for f in (f1, f2, f3):
+            with f.open("r") as fh:
+                texts.append(fh.read())
+        i, s = b()
+        assert (int(i), str(s)) == (42, "42")
+    assert texts == ["fizzbuzz", "Lol", "Kek"]
+    assert src.read_text() == "fizz"  # the op appended to its own copy
