@@ -274,3 +274,18 @@ def test_scenario_files_travel_by_content(lzy, workflow_name, tmp_path):
         assert (int(i), str(s)) == (42, "42")
     assert texts == ["fizzbuzz", "Lol", "Kek"]
     assert src.read_text() == "fizz"  # the op appended to its own copy
+
+
+def test_scenario_large_input_output_round_trip(lzy, workflow_name):
+    """large_input_output/__init__.py:10-21 at a tenth of its size: a DataFrame goes in, comes back, equal"""
+    import numpy as np
+    import pandas as pd
+
+    @op
+    def accept_return(df: pd.DataFrame) -> pd.DataFrame:
+        return df
+
+    data = pd.DataFrame(np.random.default_rng(0).random((500_000, 3)), columns=["a", "b", "c"])
+    with lzy.workflow(workflow_name, interactive=False):
+        back = materialize(accept_return(data))
+    assert back is not data and back.equals(data)
