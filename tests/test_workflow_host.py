@@ -289,3 +289,33 @@ def test_scenario_large_input_output_round_trip(lzy, workflow_name):
     with lzy.workflow(workflow_name, interactive=False):
         back = materialize(accept_return(data))
     assert back is not data and back.equals(data)
+
+
+def test_scenario_custom_serializer_is_shipped_to_the_op_side_as_an_import(workflow_name):
+    """custom_serializer/__init__.py:19-24 and registry.py:60-71: a serializer registered on
+    `lzy.serializer_registry` travels in the request as (module, class, priority); the op side builds its own
+    registry from those imports — here a fresh `LzySerializerRegistry` inside `startup.main` — and the payload on
+    the wire is the custom serializer's bytes"""
+    from lzy_b200 import _host as H
+    from tests.support.custom_serializer import Point, PointSerializer
+    from tests.support.worker_pool_runtime import WorkerPoolRuntime
+
+    @op
+    def mirror(p: Point) -> Point:
+        return Point(p.y, p.x)
+
+    rt = WorkerPoolRuntime(n_workers=1)
+    try:
+        lzy = Lzy(runtime=rt, storage_uri="mem://bucket/custom")
+        lzy.serializer_registry.register_serializer(PointSerializer())
+        assert [(i.module_name, i.class_name) for i in lzy.serializer_registry.imports()] == \
+            [("tests.support.custom_serializer", "PointSerializer")]
+        with lzy.workflow(workflow_name) as wf:
+            out = mirror(Point(3, 4))
+            assert materialize(out) == Point(4, 3)
+            call = wf.owner.runtime.calls[-1]
+            arg_uri = wf.snapshot.get(call.arg_entry_ids[0]).storage_uri
+            ret_uri = wf.snapshot.get(call.entry_ids[0]).storage_uri
+            assert H.blob_get(arg_uri) == b"point:3,4" and H.blob_get(ret_uri) == b"point:4,3"
+    finally:
+        rt.close()
