@@ -43,8 +43,8 @@ class LzyWorkflow(WithEnvironmentMixin):
 
     @classmethod
     def get_active(cls) -> Optional["LzyWorkflow"]:
-        if op_scope.inside_op():  # an op body sees no workflow, as in the reference's op subprocess
-            return None
+        if op_scope.inside_op():  # an op body sees only a workflow it opened itself, as in the reference's op subprocess
+            return op_scope.get_workflow()
         return cls.instance
 
     @classmethod
@@ -60,6 +60,7 @@ class LzyWorkflow(WithEnvironmentMixin):
         self.__filled_entry_ids: Set[str] = set()
         self.__call_queue: List["LzyCall"] = []
         self.__started = False
+        self.__nested = False
         self.__snapshot: Optional[Snapshot] = None
         self.__execution_id: Optional[str] = None
 
@@ -102,7 +103,13 @@ class LzyWorkflow(WithEnvironmentMixin):
                 parts.append(self.__user)
             parts.extend(["lzy_runs", self.name, "inputs/"])
             storage_uri = "/".join(parts)
+            # the op thread that opens a workflow owns it: decided here, in the caller's thread (the coroutine
+            # below runs on the workflow thread)
+            self.__nested = op_scope.inside_op()
+            if self.get_active() is not None:
+                raise RuntimeError("Simultaneous workflows are not supported")
             self.__execution_id = LzyEventLoop.run_async(self.__start())
+            self.__activate(self)
             self.__snapshot = self.owner.make_snapshot(self, storage_uri)
             return self
         except Exception:
@@ -130,28 +137,32 @@ class LzyWorkflow(WithEnvironmentMixin):
                 finally:
                     raise exc_val
 
+    def __activate(self, workflow: Optional["LzyWorkflow"]) -> None:
+        if self.__nested:
+            op_scope.set_workflow(workflow)
+        else:
+            self.set_active(workflow)
+
     def __abort(self):
         try:
             LzyEventLoop.run_async(self.owner.runtime.abort())
         finally:
-            self.set_active(None)
+            if self.__started:
+                self.__activate(None)
             self.__started = False
 
     def __destroy(self):
         try:
             LzyEventLoop.run_async(self.owner.runtime.finish())
         finally:
-            self.set_active(None)
+            self.__activate(None)
             self.__started = False
 
     async def __start(self) -> str:
         if self.__started:
             raise RuntimeError("Workflow already started")
-        if self.get_active() is not None:
-            raise RuntimeError("Simultaneous workflows are not supported")
         workflow_id = await self.owner.runtime.start(self)
         self.__started = True
-        self.set_active(self)
         return workflow_id
 
     async def _barrier(self) -> None:

@@ -1,5 +1,6 @@
-"""Thread-local marker set while an op body runs on a worker thread.  Inside it there is no active
-workflow — exactly as inside the reference's op subprocess — so nested ``@op`` calls are plain calls."""
+"""Thread-local marker set while an op body runs on a worker thread.  Inside it the caller's workflow is not
+visible — exactly as inside the reference's op subprocess — so nested ``@op`` calls are plain calls, and an op
+may open a workflow of its own (pylzy/tests/scenarios/nested_workflows), which then belongs to that op's thread."""
 import threading
 
 _scope = threading.local()
@@ -15,3 +16,12 @@ def leave() -> None:
 
 def inside_op() -> bool:
     return bool(getattr(_scope, "depth", 0))
+
+
+def get_workflow():
+    """the workflow opened *inside* the op running on this thread, if any"""
+    return getattr(_scope, "workflow", None)
+
+
+def set_workflow(workflow) -> None:
+    _scope.workflow = workflow

@@ -319,3 +319,30 @@ def test_scenario_custom_serializer_is_shipped_to_the_op_side_as_an_import(workf
             assert H.blob_get(arg_uri) == b"point:3,4" and H.blob_get(ret_uri) == b"point:4,3"
     finally:
         rt.close()
+
+
+@op
+def _inner_double(x: int) -> int:
+    return x * 2
+
+
+@op
+def _outer_with_its_own_workflow(x: int) -> int:
+    rt = WorkerPoolRuntime(n_workers=1)
+    try:
+        with Lzy(runtime=rt, storage_uri="mem://bucket/inner").workflow("inner_" + uuid.uuid4().hex):
+            return int(materialize(_inner_double(x))) + 1
+    finally:
+        rt.close()
+
+
+def test_scenario_nested_workflow_inside_an_op(lzy, workflow_name):
+    """nested_workflows/__init__.py: an op may open a workflow of its own (in the reference because it runs in its
+    own process; here the workflow belongs to the op's thread) while the caller's stays active; outside an op a
+    second simultaneous workflow is still refused (core/workflow.py:205-215)"""
+    with lzy.workflow(workflow_name) as outer:
+        assert materialize(_outer_with_its_own_workflow(20)) == 41
+        assert type(outer).get_active() is outer
+        with pytest.raises(RuntimeError, match="Simultaneous workflows are not supported"):
+            with lzy.workflow(workflow_name + "_second"):
+                pass
