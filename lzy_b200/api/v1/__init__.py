@@ -4,7 +4,7 @@ from ...core.call import LazyCallWrapper, LzyCall
 from ...core.lzy import Lzy
 from ...core.op import op
 from ...core.workflow import LzyWorkflow
-from ...env import LzyEnvironment, Provisioning
+from ...env import LzyEnvironment, Provisioning, env_vars, provisioning
 from .b200 import B200Runtime, B200RuntimeConfig
 from .exceptions import LzyExecutionException
 from .runtime import ProgressStep, Runtime
@@ -13,4 +13,4 @@ from .utils.proxy_adapter import is_lzy_proxy, materialize, materialized
 
 __all__ = ["Lzy", "op", "LzyWorkflow", "LzyCall", "LazyCallWrapper", "Runtime", "ProgressStep", "B200Runtime",
            "B200RuntimeConfig", "Snapshot", "SnapshotEntry", "LzyEnvironment", "Provisioning",
-           "LzyExecutionException", "is_lzy_proxy", "materialize", "materialized"]
+           "LzyExecutionException", "is_lzy_proxy", "materialize", "materialized", "env_vars", "provisioning"]

@@ -75,6 +75,25 @@ class WithEnvironmentMixin:
         return self.with_env(self.env.with_fields(provisioning=provisioning))
 
 
+def _applier(method: str, *args: Any, **kwargs: Any):
+    """decorator form of a ``with_*`` method (pylzy/lzy/env/shortcuts.py): ``@env_vars(A="1")`` above ``@op``, or
+    applied to a ``Lzy`` / workflow object"""
+    def wrapper(subject):
+        if not isinstance(subject, WithEnvironmentMixin):
+            raise TypeError(f"decorator/function {method.replace('with_', '')} can be applied only to "
+                            f"@op-decorated functions, Lzy and LzyWorkflow objects")
+        return getattr(subject, method)(*args, **kwargs)
+    return wrapper
+
+
+def env_vars(*args: Mapping[str, str], **kwargs: str):
+    return _applier("with_env_vars", *args, **kwargs)
+
+
+def provisioning(*args: Provisioning, **kwargs: Any):
+    return _applier("with_provisioning", *args, **kwargs)
+
+
 _ENV_LOCK = threading.RLock()
 
 

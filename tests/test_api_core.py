@@ -315,3 +315,27 @@ def test_runtime_config_env_overrides():
     for bad in ({"LZY_B200_PLACEMENT": "random"}, {"LZY_B200_PREFETCH": "maybe"}, {"LZY_B200_CHUNK_BYTES": "2x"}):
         with pytest.raises(ValueError, match="LZY_B200_"):
             B200RuntimeConfig.from_env(bad)
+
+
+def test_env_shortcut_decorators_and_their_refusals():
+    """pylzy/lzy/env/shortcuts.py: `@env_vars(...)` / `@provisioning(...)` above `@op` (or applied to Lzy / a
+    workflow); anything else is refused"""
+    from lzy_b200.api.v1 import Provisioning, env_vars, provisioning
+
+    @env_vars(A="1")
+    @provisioning(gpu_count=2)
+    @op
+    def f() -> int:
+        return 1
+
+    assert f.env.get_env_vars() == {"A": "1"} and f.env.get_provisioning().gpu_count == 2 and f() == 1
+    lzy = env_vars({"B": "2"})(Lzy(runtime=RuntimeMock()))
+    assert lzy.env.get_env_vars() == {"B": "2"}
+    wf = provisioning(Provisioning(gpu_index=3))(lzy.workflow(wf_name()))
+    assert wf.env.get_provisioning().gpu_index == 3
+    with pytest.raises(TypeError, match="can be applied only to"):
+        env_vars(A="1")(lambda: None)
+    with pytest.raises(TypeError):
+        f.with_env_vars({"A": 1})
+    with pytest.raises(NotImplementedError):
+        f.with_env_vars({"A": "1"}, B="2")
