@@ -54,7 +54,7 @@ class LzyCall:
                 arg_name = sign.func.arg_names[i]
                 eid = workflow.snapshot.create_entry(name=self.callable_name + "." + arg_name,
                                                      typ=sign.func.input_types[arg_name]).id
-                local_data_put_tasks.append(workflow.snapshot.put_data(eid, arg))
+                local_data_put_tasks.append(workflow.snapshot.put_data(eid, _plain(arg)))
             self.__args_entry_ids.append(eid)
 
         self.__kwargs_entry_ids: Dict[str, str] = {}
@@ -64,7 +64,7 @@ class LzyCall:
             else:
                 eid = workflow.snapshot.create_entry(name=self.callable_name + "." + kwarg_name,
                                                      typ=sign.func.input_types[kwarg_name]).id
-                local_data_put_tasks.append(workflow.snapshot.put_data(eid, kwarg))
+                local_data_put_tasks.append(workflow.snapshot.put_data(eid, _plain(kwarg)))
             self.__kwargs_entry_ids[kwarg_name] = eid
 
         self.__entry_ids: List[str] = []
@@ -122,6 +122,12 @@ class LzyCall:
 
     def get_env_vars(self) -> Dict[str, str]:
         return self.final_env.get_env_vars()
+
+
+def _plain(value: Any) -> Any:
+    """local data as it is stored: results of other ops sitting inside a list / tuple / dict stand for their values"""
+    from ..proxy import _unwrap_tree
+    return _unwrap_tree(value) if type(value) in (list, tuple, dict) else value
 
 
 @dataclass(frozen=True)

@@ -18,6 +18,11 @@ LARGE_TUPLE = 64
 
 
 def get_type(obj: Any) -> Type:
+    from ..proxy import is_proxy
+    if is_proxy(obj):
+        # the result of another op placed inside a local container (`f([a, b, c])`, tests/core/test_workflow.py:435-447)
+        # is described by the value it stands for; asking materialises it, as touching it in any other way would
+        return get_type(obj.__lzy_origin__)
     if type(obj) is list:
         if len(obj) == 0:
             return List[EmptyContent]  # type: ignore[return-value]

@@ -346,3 +346,65 @@ def test_scenario_nested_workflow_inside_an_op(lzy, workflow_name):
         with pytest.raises(RuntimeError, match="Simultaneous workflows are not supported"):
             with lzy.workflow(workflow_name + "_second"):
                 pass
+
+
+# ---- remaining cases of pylzy/tests/core/test_workflow.py that the shared scenarios do not already cover ----------
+def test_tuple_with_ellipsis_unpacks_and_union_results_behave_like_their_values(lzy, workflow_name):
+    from typing import List, Tuple, Union
+
+    @op
+    def returns_tuple() -> Tuple[List[int], ...]:
+        return [1], [2]
+
+    @op
+    def union(p: bool) -> Union[str, int]:
+        return "str" if p else 42
+
+    with lzy.workflow(workflow_name):
+        a, b = returns_tuple()
+        s, n = union(True), union(False)
+        assert sum(1 for _ in range(n)) == 42 and n == 42 and s == "str"
+    assert a == [1] and b == [2]
+
+
+def test_typed_dict_round_trip_and_refusal(lzy, workflow_name):
+    from typing import Dict
+
+    @op
+    def echo(d: Dict[int, str]) -> Dict[int, str]:
+        return d
+
+    with lzy.workflow(workflow_name):
+        res = echo(echo({1: "2"}))
+    assert res == {1: "2"}
+    with pytest.raises(TypeError):
+        with lzy.workflow(workflow_name):
+            echo({1: 1})
+
+
+def test_proxies_inside_a_list_argument(lzy, workflow_name):
+    """test_lazy_list (:435-447): results of other ops placed in a plain list argument"""
+    from typing import List
+
+    @op
+    def foo() -> str:
+        return "Foo:"
+
+    @op
+    def lens(strings: List[str], strings2: List[str]) -> (int, int):
+        return len(strings), len(strings2)
+
+    with lzy.workflow(workflow_name):
+        a, b, c = foo(), foo(), foo()
+        n1, n2 = lens([a, b, c], strings2=[a, b, c])
+    assert (n1, n2) == (3, 3)
+
+
+def test_returning_the_argument(lzy, workflow_name):
+    @op
+    def return_argument(arg: str) -> str:
+        return arg
+
+    with lzy.workflow(workflow_name):
+        res = return_argument("str")
+    assert res == "str"
