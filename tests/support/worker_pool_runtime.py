@@ -88,8 +88,12 @@ class BlobSnapshot(Snapshot):
 class WorkerPoolRuntime(Runtime):
     _live = 0  # runtimes that installed the in-memory backend: the last one to close removes it
 
-    def __init__(self, n_workers: int = 2, user_id: str = "test-user"):
-        self.n_workers, self.user_id = n_workers, user_id
+    def __init__(self, n_workers: int = 2, user_id: str = "test-user", over_grpc: bool = False):
+        """over_grpc: every worker sits behind its own WorkerApi / LongRunningService / LzySlotsApi server and is
+        driven through the wire messages, as the reference's graph executor drives a worker VM"""
+        self.n_workers, self.user_id, self.over_grpc = n_workers, user_id, over_grpc
+        self._servers: List[Any] = []
+        self._clients: Dict[int, Any] = {}
         self.cm: Optional[H.ChannelManager] = None
         self.workers: List[Worker] = []
         self.workflow = None
@@ -116,23 +120,77 @@ class WorkerPoolRuntime(Runtime):
         workflow gets fresh workers"""
         if self.workers and self._owner == (self.user_id, workflow_name):
             return
-        for w in self.workers:
-            w.close()
+        self._release_workers()
         self._generation += 1
         self.workers = [Worker(self.cm, 0, f"lzyb://pool-worker-{self._generation}-{i}", mount_factory=hostmem.HostmemMount)
                         for i in range(self.n_workers)]
         self._owner = (self.user_id, workflow_name)
+        if self.over_grpc:
+            from lzy_b200.grpc_api import LongRunningClient, WorkerApiClient, messages, serve
+            for i, w in enumerate(self.workers):
+                server, port = serve("127.0.0.1:0", worker=w)
+                self._servers.append(server)
+                self._clients[i] = (WorkerApiClient(f"127.0.0.1:{port}"), LongRunningClient(f"127.0.0.1:{port}"))
+                self._clients[i][0].call("Init", messages.InitRequest(user_id=self.user_id, workflow_name=workflow_name))
+        else:
+            for w in self.workers:
+                w.init(self.user_id, workflow_name)
+
+    def _release_workers(self) -> None:
+        for wapi, ops in self._clients.values():
+            wapi.close()
+            ops.close()
+        self._clients.clear()
+        for server in self._servers:
+            server.stop(0)
+        self._servers.clear()
         for w in self.workers:
-            w.init(self.user_id, workflow_name)
+            w.close()
+        self.workers = []
+
+    # ---- one task to one worker: direct calls, or the wire ------------------------------------------------------
+    def _submit(self, index: int, task: TaskSpec) -> str:
+        if not self.over_grpc:
+            return self.workers[index].execute(task).id
+        from lzy_b200.grpc_api import messages
+        req = messages.ExecuteRequest(task_id=task.task_id, execution_id=task.execution_id, workflow_name=task.workflow_name,
+                                      user_id=task.user_id)
+        req.task_desc.operation.command = task.command
+        req.task_desc.operation.name = task.name
+        for k, v in (task.env or {}).items():
+            req.task_desc.operation.env.env[k] = v
+        for slot in task.slots:
+            req.task_desc.operation.slots.add(name=slot.name, direction=slot.direction)
+        for name, chan in task.slot_assignments.items():
+            req.task_desc.slot_assignments.add(slot_name=name, channel_id=chan)
+        return self._clients[index][0].call("Execute", req).id
+
+    def _poll(self, index: int, op_id: str):
+        """None while the task runs, else (ok, description)"""
+        if not self.over_grpc:
+            op = self.workers[index].get_operation(op_id)
+            if not op.done:
+                return None
+            ok = op.error is None and op.response is not None and op.response.rc == 0
+            return ok, (op.response.description if op.response else str(op.error))
+        from lzy_b200.grpc_api import messages
+        from lzy_b200.grpc_api.protos import GetOperationRequest
+        op = self._clients[index][1].call("Get", GetOperationRequest(operation_id=op_id))
+        if not op.done:
+            return None
+        if op.WhichOneof("result") != "response":
+            return False, op.error.message
+        resp = messages.ExecuteResponse()
+        op.response.Unpack(resp)
+        return resp.rc == 0, resp.description
 
     def close(self) -> None:
         if self.cm is None:
             return
-        for w in self.workers:
-            w.close()
+        self._release_workers()
         H.pump_stop(self.cm)
         self.cm.close()
-        self.cm, self.workers = None, []
+        self.cm = None
         for snap in self._snapshots:
             for uri in snap.uris():
                 H.blob_delete(uri)
@@ -254,25 +312,27 @@ class WorkerPoolRuntime(Runtime):
                 if time.time() > deadline:
                     raise LzyExecutionException("graph did not finish in time")
                 for t in graph.next():
-                    worker = self.workers[self._rr % len(self.workers)]
+                    index = self._rr % len(self.workers)
                     self._rr += 1
                     self.executed.append(todo[t].callable_name)
-                    running[t] = (worker, worker.execute(tasks[t]).id)
-                for t, (worker, op_id) in list(running.items()):
-                    op = worker.get_operation(op_id)
-                    if not op.done:
+                    running[t] = (index, self._submit(index, tasks[t]))
+                for t, (index, op_id) in list(running.items()):
+                    outcome = self._poll(index, op_id)
+                    if outcome is None:
                         continue
                     del running[t]
-                    ok = op.error is None and op.response is not None and op.response.rc == 0
+                    ok, description = outcome
                     if not ok and failed is None:
                         failed = t
-                    graph.task_done(t, ok, "" if ok else (op.response.description if op.response else str(op.error)))
+                    graph.task_done(t, ok, "" if ok else description)
                 time.sleep(0.001)
             if failed is not None or graph.status == H.G_FAILED:
                 self._raise_failure(todo[failed] if failed is not None else None, snap, graph)
         finally:
-            for worker, op_id in running.values():  # tasks still in flight when the graph stopped
-                worker.wait_operation(op_id, timeout=30)
+            deadline = time.time() + 30
+            for index, op_id in running.values():  # tasks still in flight when the graph stopped
+                while self._poll(index, op_id) is None and time.time() < deadline:
+                    time.sleep(0.002)
             graph.close()
 
     def _raise_failure(self, call, snap: BlobSnapshot, graph) -> None:

@@ -408,3 +408,37 @@ def test_returning_the_argument(lzy, workflow_name):
     with lzy.workflow(workflow_name):
         res = return_argument("str")
     assert res == "str"
+
+
+# ---- the same stack with every worker behind its gRPC servers ---------------------------------------------------------
+@pytest.fixture
+def lzy_over_grpc():
+    rt = WorkerPoolRuntime(n_workers=2, over_grpc=True)
+    yield Lzy(runtime=rt, storage_uri="mem://bucket/grpc")
+    rt.close()
+
+
+def test_workflows_driven_through_worker_api_on_the_wire(lzy_over_grpc, workflow_name, capsys):
+    """WorkerApi.Execute / LongRunningService.Get messages instead of method calls (what the reference's graph
+    executor sends a worker VM): env vars ride in Operation.env.env, failures come back as rc + description and the
+    caller still gets the op's own exception from its exception entry"""
+    import os
+
+    lzy = lzy_over_grpc
+
+    @op
+    def inc(x: int) -> int:
+        print(os.environ.get("MODE", "-"))
+        return x + 1
+
+    @op
+    def fail(x: int) -> int:
+        raise KeyError("nope")
+
+    with lzy.workflow(workflow_name).with_env_vars(MODE="wire"):
+        assert materialize(inc(inc(inc(1)))) == 4
+    assert capsys.readouterr().out.split() == ["wire", "wire", "wire"]
+    with pytest.raises(KeyError, match="nope"):
+        with lzy.workflow(workflow_name + "_f"):
+            materialize(inc(fail(1)))
+    assert lzy.runtime.executed.count("inc") == 3  # the consumer of the failed op never started
