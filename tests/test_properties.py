@@ -1,0 +1,121 @@
+"""Property-based checks (hypothesis) of the pieces whose contracts are algebraic: the digest composes over any
+8-byte-aligned chunking and any chunk order, differs when a byte or the length differs, and agrees between the C
+restatement and the pure-Python definition; a stream with offset resume delivers exactly the source; the request
+codec and the File byte format round-trip arbitrary values; the copy-engine sub-chunk plan always tiles its chunk."""
+import os
+import tempfile
+from io import BytesIO
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+import oracle
+from lzy_b200 import _native as N
+from lzy_b200.serialization.registry import LzySerializerRegistry
+from lzy_b200.types import File
+from lzy_b200.utils.argv_codec import decode, encode
+
+from tests.test_abi_and_oracle import py_digest  # the independent pure-Python statement of include/lzyb_digest.h
+
+payloads = st.binary(min_size=0, max_size=4096)
+
+
+@settings(max_examples=150, deadline=None)
+@given(payloads)
+def test_c_digest_equals_the_python_definition(data):
+    assert oracle.digest(np.frombuffer(data, dtype=np.uint8)) == py_digest(data)
+
+
+@settings(max_examples=150, deadline=None)
+@given(payloads, st.lists(st.integers(min_value=0, max_value=512), max_size=6), st.randoms(use_true_random=False))
+def test_digest_composes_over_any_aligned_chunking_in_any_order(data, cuts, rnd):
+    a = np.frombuffer(data, dtype=np.uint8)
+    bounds = sorted({0, len(data), *[min(len(data), 8 * c) for c in cuts]})
+    chunks = list(zip(bounds[:-1], bounds[1:]))
+    rnd.shuffle(chunks)
+    acc = (0, 0)
+    for lo, hi in chunks:
+        acc = oracle.digest_partial(a[lo:hi], lo, acc)
+    assert oracle.digest_finalize(acc[0], acc[1], len(data)) == oracle.digest(a)
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.binary(min_size=1, max_size=2048), st.data())
+def test_digest_sees_every_byte_its_position_and_the_length(data, draw):
+    a = np.frombuffer(data, dtype=np.uint8)
+    base = oracle.digest(a)
+    i = draw.draw(st.integers(min_value=0, max_value=len(data) - 1))
+    flipped = bytearray(data)
+    flipped[i] ^= 1 << draw.draw(st.integers(min_value=0, max_value=7))
+    assert oracle.digest(np.frombuffer(bytes(flipped), dtype=np.uint8)) != base
+    assert oracle.digest(np.frombuffer(data + b"\0", dtype=np.uint8)) != base  # zero padding is not free
+    if len(data) >= 16 and data[:8] != data[8:16]:
+        swapped = data[8:16] + data[:8] + data[16:]
+        assert oracle.digest(np.frombuffer(swapped, dtype=np.uint8)) != base   # order matters
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.binary(min_size=0, max_size=3 << 16), st.integers(min_value=0, max_value=3 << 16))
+def test_stream_with_a_failure_and_offset_resume_delivers_the_source(data, fail_at):
+    src = np.frombuffer(data, dtype=np.uint8)
+    dst = np.zeros(len(data), dtype=np.uint8)
+    fail_at = min(fail_at, len(data))
+    chunks, position = oracle.stream_copy(src, dst, 0, fail_after=fail_at)  # (2 MiB chunks sent, bytes delivered so far)
+    assert position <= len(data) and np.array_equal(dst[:position], src[:position])
+    assert chunks == -(-position // (2 << 20))
+    _, end = oracle.stream_copy(src, dst, position)  # the consumer reopens at the offset it holds
+    assert end == len(data) and np.array_equal(dst, src)
+
+
+values = st.recursive(st.none() | st.booleans() | st.integers() | st.floats(allow_nan=False) | st.text() | st.binary(),
+                      lambda inner: st.lists(inner, max_size=4) | st.tuples(inner, inner) | st.dictionaries(st.text(max_size=5), inner, max_size=4),
+                      max_leaves=12)
+
+
+@settings(max_examples=150, deadline=None)
+@given(values)
+def test_request_codec_round_trips_and_stays_one_shell_word(value):
+    text = encode(value)
+    assert text.isascii() and not any(c.isspace() for c in text) and decode(text) == value
+
+
+def test_request_codec_refuses_what_is_not_base64():
+    for bad in ("not base64!", "AAA", "ʎzy"):
+        with pytest.raises((ValueError, UnicodeEncodeError)):
+            decode(bad)
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(st.binary(max_size=20000), st.integers(min_value=0, max_value=0o777))
+def test_file_serializer_round_trips_content_and_mode(content, mode):
+    ser = LzySerializerRegistry().find_serializer_by_type(File)
+    with tempfile.NamedTemporaryFile(delete=False) as f:
+        f.write(content)
+    try:
+        os.chmod(f.name, mode | 0o400)  # the serializer has to be able to read it back
+        buf = BytesIO()
+        ser.serialize(File(f.name), buf)
+        assert buf.getvalue() == b"permissions" + oct(mode | 0o400).encode() + content
+        buf.seek(0)
+        back = ser.deserialize(buf, File)
+        try:
+            with back.open("rb") as fh:
+                assert fh.read() == content
+            assert back.stat().st_mode & 0o777 == mode | 0o400
+        finally:
+            os.chmod(str(back), 0o600)
+            os.unlink(str(back))
+    finally:
+        os.chmod(f.name, 0o600)
+        os.unlink(f.name)
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.integers(min_value=0, max_value=1 << 36))
+def test_copy_engine_plan_always_tiles_its_chunk(nbytes):
+    sizes = N.dma_schedule(nbytes)
+    assert sum(sizes) == nbytes and 1 <= len(sizes) <= 8
+    assert all(s % 16 == 0 for s in sizes[:-1])
+    assert nbytes < (8 << 20) or sizes[-1] <= (32 << 20) + 15  # a short tail scan
