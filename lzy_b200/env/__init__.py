@@ -94,25 +94,40 @@ def provisioning(*args: Provisioning, **kwargs: Any):
     return _applier("with_provisioning", *args, **kwargs)
 
 
-_ENV_LOCK = threading.RLock()
+_ENV_COND = threading.Condition()
+_ENV_IN_USE: Dict[str, list] = {}  # variable -> [value, how many running ops set it, what it was before]
 
 
 @contextlib.contextmanager
 def applied_env(env_vars: Optional[Mapping[str, str]]):
     """Run a block with `env_vars` in ``os.environ`` (restored afterwards).  The reference gives every op its own
-    process; here ops of one worker share one, so blocks that set variables take turns while ops that declare
-    none do not wait for anybody."""
+    process; here the ops of one worker share one, so a variable belongs to the ops that are running with it: ops
+    that agree on a value share it, an op that wants another value for the same name waits until the current users
+    are done, and ops that declare no variables never wait for anybody."""
     if not env_vars:
         yield
         return
-    with _ENV_LOCK:
-        saved = {k: os.environ.get(k) for k in env_vars}
-        os.environ.update({k: str(v) for k, v in env_vars.items()})
-        try:
-            yield
-        finally:
-            for k, old in saved.items():
-                if old is None:
-                    os.environ.pop(k, None)
-                else:
-                    os.environ[k] = old
+    wanted = {k: str(v) for k, v in env_vars.items()}
+    with _ENV_COND:
+        _ENV_COND.wait_for(lambda: all(k not in _ENV_IN_USE or _ENV_IN_USE[k][0] == v for k, v in wanted.items()))
+        for k, v in wanted.items():
+            slot = _ENV_IN_USE.get(k)
+            if slot is None:
+                _ENV_IN_USE[k] = [v, 1, os.environ.get(k)]
+                os.environ[k] = v
+            else:
+                slot[1] += 1
+    try:
+        yield
+    finally:
+        with _ENV_COND:
+            for k in wanted:
+                slot = _ENV_IN_USE[k]
+                slot[1] -= 1
+                if slot[1] == 0:
+                    del _ENV_IN_USE[k]
+                    if slot[2] is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = slot[2]
+            _ENV_COND.notify_all()

@@ -339,3 +339,49 @@ def test_env_shortcut_decorators_and_their_refusals():
         f.with_env_vars({"A": 1})
     with pytest.raises(NotImplementedError):
         f.with_env_vars({"A": "1"}, B="2")
+
+
+def test_applied_env_shares_agreeing_values_and_serialises_conflicting_ones():
+    """ops of one worker share a process: a variable belongs to the ops running with it"""
+    import threading
+    import time
+
+    from lzy_b200.env import applied_env
+    assert "LZYB_T" not in os.environ
+    with applied_env(None):
+        assert "LZYB_T" not in os.environ
+    seen, order, gate = [], [], threading.Event()
+
+    def op_body(value, hold):
+        with applied_env({"LZYB_T": value}):
+            order.append(("in", value))
+            seen.append(os.environ["LZYB_T"])
+            if hold:
+                gate.wait(5)
+            order.append(("out", value))
+
+    a = threading.Thread(target=op_body, args=("1", True))
+    a.start()
+    while ("in", "1") not in order:
+        time.sleep(0.001)
+    b = threading.Thread(target=op_body, args=("1", False))  # same value: shares it, does not wait
+    b.start()
+    b.join(5)
+    assert not b.is_alive() and os.environ["LZYB_T"] == "1"     # still set: `a` is using it
+    c = threading.Thread(target=op_body, args=("2", False))  # other value: waits for `a`
+    c.start()
+    time.sleep(0.05)
+    assert ("in", "2") not in order
+    gate.set()
+    a.join(5)
+    c.join(5)
+    last_out_1 = max(i for i, e in enumerate(order) if e == ("out", "1"))
+    assert seen == ["1", "1", "2"] and last_out_1 < order.index(("in", "2"))
+    assert "LZYB_T" not in os.environ
+    os.environ["LZYB_T"] = "before"
+    try:
+        with applied_env({"LZYB_T": "during"}):
+            assert os.environ["LZYB_T"] == "during"
+        assert os.environ["LZYB_T"] == "before"
+    finally:
+        del os.environ["LZYB_T"]
