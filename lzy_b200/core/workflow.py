@@ -38,7 +38,10 @@ class LzyWorkflow(WithEnvironmentMixin):
     interactive: bool = True
 
     def with_fields(self, **kwargs: Any) -> "LzyWorkflow":
-        """a copy with some declaration changed — before the workflow is entered (pylzy/lzy/env/base.py Deconstructible)"""
+        """a copy with some declaration changed — only before the workflow is used: once it has calls, a snapshot
+        or an execution it carries state a copy could not share (pylzy/lzy/core/workflow.py:77-96)"""
+        if self.__filled_entry_ids or self.__call_queue or self.__started or self.__snapshot or self.__execution_id:
+            raise RuntimeError("It's forbidden to change LzyWorkflow fields after start working with it")
         return replace(self, **kwargs)
 
     @classmethod

@@ -385,3 +385,11 @@ def test_applied_env_shares_agreeing_values_and_serialises_conflicting_ones():
         assert os.environ["LZYB_T"] == "before"
     finally:
         del os.environ["LZYB_T"]
+
+
+def test_workflow_declarations_are_frozen_once_it_is_in_use(lzy):
+    wf = lzy.workflow(wf_name()).with_env_vars(A="1")  # before use: a new object each time
+    assert wf.env.get_env_vars() == {"A": "1"} and wf.with_env_vars(B="2") is not wf
+    with wf:
+        with pytest.raises(RuntimeError, match="forbidden to change LzyWorkflow fields"):
+            wf.with_env_vars(C="3")
