@@ -173,6 +173,31 @@ def test_large_data_200mib_equal(env):
     H.blob_delete("mem://large")
 
 
+def test_large_read_from_storage_and_large_write_to_storage(env):
+    """testLargeReadFromStorage / testLargeWriteToStorage (SlotsTest.java:695-801): 200 MiB through the storage peer
+    in each direction, delivered == stored"""
+    cm, slots, _ = env
+    data = np.random.default_rng(2).integers(0, 256, 200 << 20, dtype=np.uint8).tobytes()
+    H.blob_put("mem://large-in", data)
+    chan = cm.get_or_create("u", "wf", "exec-ls", producer_uri="mem://large-in")
+    inp = slots.context("exec-ls", "r")
+    inp.add_slot("/ls/in", chan, DIR_INPUT)
+    inp.before_execution(30000)
+    assert hostmem.peek(inp.input_handle("/ls/in"), len(data)) == data
+    inp.close()
+    H.blob_delete("mem://large-in")
+
+    chan2 = cm.get_or_create("u", "wf", "exec-ls", consumer_uri="mem://large-out")
+    out = slots.context("exec-ls", "w")
+    out.add_slot("/ls/out", chan2, DIR_OUTPUT)
+    out.before_execution()
+    produce(out, "/ls/out", data)
+    out.after_execution(30000)
+    assert H.blob_get("mem://large-out") == data
+    out.close()
+    H.blob_delete("mem://large-out")
+
+
 def test_restore_read_from_offset(env):
     """testRestoreReadFromOffset: 2 MiB, the producer fails after 1 MiB; the consumer reports
     TransferFailed, gets a peer again and resumes at the delivered offset."""
