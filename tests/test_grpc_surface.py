@@ -4,6 +4,7 @@ Scenarios: ApiTest.testSimple / testEarlyConsumer over the wire; a *legacy* cons
 slot with `Read` (2 MiB chunks + EOS, offset honoured, OutputSlot.java:238-265); status codes
 (SlotsService.java:36,44,55,63; channel-manager SlotsService.java:184-187,219-222)."""
 import os
+import time
 
 import grpc
 import pytest
@@ -164,3 +165,102 @@ def test_start_transfer_over_grpc_reaches_waiting_input_slot(stack):
     out.close()
     H.blob_delete("mem://st")
     H.pump_start(cm)
+
+
+def test_deferred_start_transfer_is_delivered_over_the_wire():
+    """A channel manager without the in-process pump: its START_TRANSFER actions go out as LzySlotsApi.StartTransfer
+    to the consumer's worker (`RemoteActionPump`, ActionScheduler.startTransfer :61-106).  Early consumer on one
+    worker, producer on another, each worker behind its own slots server."""
+    from lzy_b200.grpc_api import RemoteActionPump
+    hostmem.install()
+    cm = H.ChannelManager(seed=3)
+    servers, workers = [], []
+    pump = None
+    try:
+        for _ in range(2):
+            # a worker's URL is what it puts into BindRequest.peer_url: here directly its gRPC target
+            probe, port = serve("127.0.0.1:0")  # find a free port, then bind the slots server to it
+            probe.stop(0)
+            w = H.Slots(cm, 0, f"127.0.0.1:{port}")
+            server, bound = serve(f"127.0.0.1:{port}", slots=w)
+            assert bound == port
+            servers.append(server)
+            workers.append(w)
+        pump = RemoteActionPump(cm).start()
+        data = os.urandom(300_000)
+        chan = cm.get_or_create("u", "wf", "exec-wire", consumer_uri="mem://wire/out")
+        cons = workers[0].context("exec-wire", "c")
+        cons.add_slot("/wire/in", chan, H.DIR_INPUT)
+        cons.prefetch()  # binds first: no producer yet, so it waits for StartTransfer
+        prod = workers[1].context("exec-wire", "p")
+        prod.add_slot("/wire/out", chan, H.DIR_OUTPUT)
+        prod.before_execution()
+        h = prod.output_open("/wire/out", len(data))
+        hostmem.write(h, data)
+        prod.output_done("/wire/out")
+        cons.before_execution(10000)
+        assert hostmem.peek(cons.input_handle("/wire/in"), len(data)) == data
+        prod.after_execution(10000)
+        deadline = time.time() + 5  # the download can finish before the StartTransfer RPC itself has returned
+        while pump.delivered == 0 and time.time() < deadline:
+            time.sleep(0.005)
+        assert pump.delivered == 1 and pump.failed == 0
+        cons.close()
+        prod.close()
+
+        # a consumer whose worker is gone: delivery fails, the channel is dropped and the workflow must be aborted
+        chan2 = cm.get_or_create("u", "wf", "exec-wire2", consumer_uri="mem://wire/out2")
+        lost = H.Slots(cm, 0, "127.0.0.1:1")  # nobody listens there
+        ghost = lost.context("exec-wire2", "c")
+        ghost.add_slot("/wire/in2", chan2, H.DIR_INPUT)
+        ghost.prefetch()
+        prod2 = workers[1].context("exec-wire2", "p")
+        prod2.add_slot("/wire/out2", chan2, H.DIR_OUTPUT)
+        prod2.before_execution()
+        h2 = prod2.output_open("/wire/out2", 4)
+        hostmem.write(h2, b"data")
+        prod2.output_done("/wire/out2")
+        deadline = time.time() + 15
+        while pump.failed == 0 and time.time() < deadline:
+            time.sleep(0.01)
+        assert pump.failed == 1 and cm.aborted("exec-wire2")
+        ghost.close()
+        prod2.close()
+        lost.close()
+    finally:
+        if pump is not None:
+            pump.stop()
+        for s in servers:
+            s.stop(0)
+        for w in workers:
+            w.close()
+        for uri in ("mem://wire/out", "mem://wire/out2"):
+            H.blob_delete(uri)
+        cm.close()
+        hostmem.uninstall()
+
+
+def test_channel_manager_service_entry_point_serves_the_private_api():
+    """`python -m lzy_b200.grpc_api channel-manager`: a separate process, no GPU"""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    proc = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "channel-manager", "--port", "0", "--seed", "1"],
+                            cwd=str(root), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    try:
+        line = proc.stdout.readline()
+        assert line.startswith("channel-manager listening on"), line
+        target = line.strip().rsplit(" ", 1)[-1]
+        priv, pub = ChannelManagerPrivateClient(target), ChannelManagerClient(target)
+        chan = priv.call("GetOrCreate", M.GetOrCreateRequest(execution_id="e", workflow_name="wf", user_id="u",
+                                                             producer=storage_peer("s3://bucket/x"))).channel_id
+        resp = pub.call("Bind", M.BindRequest(execution_id="e", channel_id=chan, peer_id="c1", peer_url="w:1", role=1))
+        assert resp.peer.storage_peer.storage_uri == "s3://bucket/x" and resp.transfer_id
+        st = priv.call("Status", M.StatusRequest(channel_id=chan)).channel
+        assert [p.peer_id for p in st.consumers] == ["c1"] and len(st.producers) == 1
+        priv.close()
+        pub.close()
+    finally:
+        proc.terminate()
+        assert proc.wait(timeout=15) == 0
