@@ -147,6 +147,21 @@ typedef struct lzyb_backend_ops {
 } lzyb_backend_ops_t;
 int lzyb_slots_set_backend(const lzyb_backend_ops_t* ops); /* NULL = the HBM backend */
 
+/* How the slot state machines reach the channel manager (LzyChannelManager.Bind / Unbind / TransferCompleted /
+ * TransferFailed, channel-manager.proto:13-58).  Default: the in-process matcher (lzyb_cm_* above, the `cm` handle is
+ * a lzyb_cm_create handle).  A worker whose channel manager is another process installs a table that performs the
+ * RPCs; `cm` is then an opaque cookie chosen by the installer and passed through unchanged.  Same signatures, same
+ * result codes (a gRPC status maps to its LZYB_E_* image) and lzyb_set_last_error for the description. */
+typedef struct lzyb_cm_client_ops {
+    int (*bind)(lzyb_handle_t cm, const char* idempotency_key, const char* channel_id, const char* peer_id,
+                const char* execution_id, const char* peer_url, int role, lzyb_bind_result_t* out);
+    int (*unbind)(lzyb_handle_t cm, const char* channel_id, const char* peer_id);
+    int (*transfer_completed)(lzyb_handle_t cm, const char* idempotency_key, const char* channel_id, const char* transfer_id);
+    int (*transfer_failed)(lzyb_handle_t cm, const char* idempotency_key, const char* channel_id, const char* transfer_id,
+                           const char* description, lzyb_bind_result_t* out);
+} lzyb_cm_client_ops_t;
+int lzyb_slots_set_cm_client(const lzyb_cm_client_ops_t* ops); /* NULL = the in-process matcher */
+
 #define LZYB_DIR_INPUT 1
 #define LZYB_DIR_OUTPUT 2
 

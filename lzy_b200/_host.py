@@ -79,6 +79,7 @@ _SIGS = {
     "lzyb_blob_size": (C.c_int64, [_s]),
     "lzyb_blob_get": (C.c_int64, [_s, C.c_void_p, C.c_uint64]),
     "lzyb_blob_delete": (_i, [_s]),
+    "lzyb_slots_set_cm_client": (_i, [C.c_void_p]),
     "lzyb_slots_transfer_log": (C.c_int64, [_H, C.c_char_p, C.c_uint64, C.c_int]),
     "lzyb_frame_store_put": (_i, [_s, _H]),
     "lzyb_frame_store_get": (_i, [_s, C.POINTER(_H)]),

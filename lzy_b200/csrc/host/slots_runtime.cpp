@@ -50,6 +50,12 @@ std::atomic<const lzyb_backend_ops_t*> g_ops{&kHbmBackend};
 lzyb_backend_ops_t g_custom_ops;
 const lzyb_backend_ops_t& ops() { return *g_ops.load(); }
 
+// ---- the matcher as the slots see it: in-process calls by default, a client of a remote channel manager otherwise ----
+const lzyb_cm_client_ops_t kLocalMatcher = {lzyb_cm_bind, lzyb_cm_unbind, lzyb_cm_transfer_completed, lzyb_cm_transfer_failed};
+std::atomic<const lzyb_cm_client_ops_t*> g_cmc{&kLocalMatcher};
+lzyb_cm_client_ops_t g_custom_cmc;
+const lzyb_cm_client_ops_t& cmc() { return *g_cmc.load(); }
+
 // ---- host blob store (storage peers) -----------------------------------------------------------------
 struct Blob {
     std::vector<uint8_t> data;
@@ -434,7 +440,7 @@ struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
         }
         inst->service.reg(shared_from_this());  // enable requests from outside
         lzyb_bind_result_t res;
-        int rc = lzyb_cm_bind(inst->cm, inst->next_idk("bind").c_str(), channel_id.c_str(), id.c_str(),
+        int rc = cmc().bind(inst->cm, inst->next_idk("bind").c_str(), channel_id.c_str(), id.c_str(),
                               ctx ? ctx->execution_id.c_str() : "", inst->api_url.c_str(), LZYB_ROLE_PRODUCER, &res);
         if (rc != LZYB_OK) {
             complete_.fail_with(std::string("Error while binding output slot: ") + lzyb_last_error());
@@ -446,12 +452,12 @@ struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
             if (!ok) {
                 std::string why = res.peer.kind == LZYB_PEER_STORAGE ? lzyb_last_error() : "Cannot create transfer for peer";
                 lzyb_bind_result_t dummy;
-                lzyb_cm_transfer_failed(inst->cm, inst->next_idk("fail").c_str(), channel_id.c_str(), res.transfer_id,
+                cmc().transfer_failed(inst->cm, inst->next_idk("fail").c_str(), channel_id.c_str(), res.transfer_id,
                                         why.c_str(), &dummy);
                 complete_.fail_with("Error while transferring data to peer " + std::string(res.peer.peer_id) + ": " + why);
                 return;
             }
-            if (lzyb_cm_transfer_completed(inst->cm, inst->next_idk("done").c_str(), channel_id.c_str(), res.transfer_id) != LZYB_OK) {
+            if (cmc().transfer_completed(inst->cm, inst->next_idk("done").c_str(), channel_id.c_str(), res.transfer_id) != LZYB_OK) {
                 complete_.fail_with(std::string("Error while binding output slot: ") + lzyb_last_error());
                 return;
             }
@@ -491,7 +497,7 @@ struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
         }
         inst->service.unreg(id);
         complete_.fail_with("Slot closed before ready");
-        lzyb_cm_unbind(inst->cm, channel_id.c_str(), id.c_str());
+        cmc().unbind(inst->cm, channel_id.c_str(), id.c_str());
         if (backend && own_backend) ops().slot_close(backend);
     }
 
@@ -650,7 +656,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
         inst->service.reg(shared_from_this());  // registering before bind
         lzyb_bind_result_t resp;
         if (is_closed()) return false;
-        int rc = lzyb_cm_bind(inst->cm, inst->next_idk("bind").c_str(), channel_id.c_str(), id.c_str(),
+        int rc = cmc().bind(inst->cm, inst->next_idk("bind").c_str(), channel_id.c_str(), id.c_str(),
                               ctx ? ctx->execution_id.c_str() : "", inst->api_url.c_str(), LZYB_ROLE_CONSUMER, &resp);
         if (rc != LZYB_OK) {
             err = std::string("Bind failed: ") + lzyb_last_error();
@@ -741,7 +747,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
             }
             if (need_new_peer) {
                 lzyb_bind_result_t np;
-                int rc = lzyb_cm_transfer_failed(inst->cm, inst->next_idk("failed").c_str(), channel_id.c_str(), tid.c_str(),
+                int rc = cmc().transfer_failed(inst->cm, inst->next_idk("failed").c_str(), channel_id.c_str(), tid.c_str(),
                                                  peer_fail_reason.c_str(), &np);
                 if (rc != LZYB_OK || !np.has_peer) {
                     err = std::string("Cannot get data from any peer: ") + lzyb_last_error();
@@ -791,7 +797,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
                     err = std::string("Error while reading into backend: ") + lzyb_last_error();
                     return false;
                 }
-                if (lzyb_cm_transfer_completed(inst->cm, inst->next_idk("completed").c_str(), channel_id.c_str(), tid.c_str()) != LZYB_OK) {
+                if (cmc().transfer_completed(inst->cm, inst->next_idk("completed").c_str(), channel_id.c_str(), tid.c_str()) != LZYB_OK) {
                     err = std::string("TransferCompleted failed: ") + lzyb_last_error();
                     return false;
                 }
@@ -816,7 +822,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
         state = LZYB_IS_CLOSED;
         inst->service.unreg(id);
         ready_.fail_with("Closed before ready");
-        lzyb_cm_unbind(inst->cm, channel_id.c_str(), id.c_str());  // error ignored
+        cmc().unbind(inst->cm, channel_id.c_str(), id.c_str());  // error ignored
     }
 
     void close() override {
@@ -998,6 +1004,17 @@ int lzyb_slots_set_backend(const lzyb_backend_ops_t* o) {
     }
     g_custom_ops = *o;
     g_ops = &g_custom_ops;
+    return LZYB_OK;
+}
+
+int lzyb_slots_set_cm_client(const lzyb_cm_client_ops_t* o) {
+    if (!o) {
+        g_cmc = &kLocalMatcher;
+        return LZYB_OK;
+    }
+    if (!o->bind || !o->unbind || !o->transfer_completed || !o->transfer_failed) return fail(LZYB_E_ARG, "incomplete client table");
+    g_custom_cmc = *o;
+    g_cmc = &g_custom_cmc;
     return LZYB_OK;
 }
 

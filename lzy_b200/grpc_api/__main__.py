@@ -4,9 +4,8 @@
 (The reference's counterpart is the `channel-manager` Micronaut service, lzy/channel-manager/src/main/java/ai/lzy/
 channelmanager/ChannelManagerApp.java; its Postgres tables are the in-memory maps of csrc/host/channel_manager.cpp.)
 
-``python -m lzy_b200.grpc_api worker --gpu 0 --port 18123 --channel-manager host:port`` is not offered yet: a worker
-process needs the channel manager *client* side of the slots runtime to go over the wire as well (today the C++
-slots runtime calls the matcher in-process); SURVEY §8(f) row 1 is covered for the services, not for that split.
+Workers in this or other processes connect their slot state machines with ``remote_cm.connect("host:port")`` and
+serve ``LzySlotsApi`` so the pump can reach them (tests/test_grpc_surface.py).
 """
 from __future__ import annotations
 

@@ -264,3 +264,77 @@ def test_channel_manager_service_entry_point_serves_the_private_api():
     finally:
         proc.terminate()
         assert proc.wait(timeout=15) == 0
+
+
+def test_workers_against_a_channel_manager_in_another_process():
+    """The control plane split the reference runs with: the channel manager is its own process
+    (`python -m lzy_b200.grpc_api channel-manager`), this process holds two workers whose slot state machines reach
+    it through LzyChannelManager RPCs (`remote_cm.connect`) and which it reaches through LzySlotsApi.StartTransfer.
+    Early consumer, then a producer that dies half-way with failover to the storage backup."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    from lzy_b200.grpc_api import remote_cm
+    root = Path(__file__).resolve().parent.parent
+    proc = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "channel-manager", "--port", "0", "--seed", "2"],
+                            cwd=str(root), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    lib = hostmem.install()
+    servers, workers, cm = [], [], None
+    try:
+        target = proc.stdout.readline().strip().rsplit(" ", 1)[-1]
+        priv = ChannelManagerPrivateClient(target)
+        cm = remote_cm.connect(target)
+        for _ in range(2):
+            probe, port = serve("127.0.0.1:0")
+            probe.stop(0)
+            w = H.Slots(cm, 0, f"127.0.0.1:{port}")
+            server, _bound = serve(f"127.0.0.1:{port}", slots=w)
+            servers.append(server)
+            workers.append(w)
+
+        def channel(uri):
+            return priv.call("GetOrCreate", M.GetOrCreateRequest(execution_id="exec-split", workflow_name="wf", user_id="u",
+                                                                 consumer=storage_peer(uri))).channel_id
+
+        # 1. early consumer on worker 0, producer on worker 1
+        data = os.urandom(200_000)
+        chan = channel("mem://split/a")
+        cons = workers[0].context("exec-split", "c")
+        cons.add_slot("/split/in", chan, H.DIR_INPUT)
+        cons.prefetch()
+        prod = workers[1].context("exec-split", "p")
+        prod.add_slot("/split/out", chan, H.DIR_OUTPUT)
+        prod.before_execution()
+        h = prod.output_open("/split/out", len(data))
+        hostmem.write(h, data)
+        prod.output_done("/split/out")
+        cons.before_execution(15000)
+        assert hostmem.peek(cons.input_handle("/split/in"), len(data)) == data
+        prod.after_execution(15000)  # storage upload reported with TransferCompleted over the wire
+        st = priv.call("Status", M.StatusRequest(channel_id=chan)).channel
+        assert len(st.producers) >= 2  # the slot producer and the promoted storage backup
+
+        # 2. the slot producer turns bad: TransferFailed over the wire walks its priority down, the backup serves
+        lib.hostmem_set_fail_after(h, 4096)
+        late = workers[0].context("exec-split", "late")
+        late.add_slot("/split/in2", chan, H.DIR_INPUT)
+        late.before_execution(15000)
+        assert hostmem.peek(late.input_handle("/split/in2"), len(data)) == data
+        rec = [r for r in workers[0].transfer_log() if r["slot_id"] == "/split/in2"][0]
+        assert rec["failovers"] >= 1 and rec["peer_kind"] == "storage"
+
+        # 3. status codes survive the wire: Unbind of a peer nobody knows is NOT_FOUND to the state machine as well
+        for c in (late, cons, prod):
+            c.close()
+        priv.close()
+    finally:
+        for s in servers:
+            s.stop(0)
+        for w in workers:
+            w.close()
+        remote_cm.disconnect_all()
+        H.blob_delete("mem://split/a")
+        hostmem.uninstall()
+        proc.terminate()
+        proc.wait(timeout=15)
