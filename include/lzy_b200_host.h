@@ -144,6 +144,10 @@ typedef struct lzyb_backend_ops {
     int (*slot_retain)(lzyb_handle_t h);
     /* optional (may be NULL): dtype / shape of a frame that is being filled from storage */
     int (*slot_set_meta)(lzyb_handle_t h, uint32_t dtype, uint32_t ndim, const uint64_t* shape);
+    /* optional (may be NULL): a committed frame as a descriptor another worker process can map, and the mapping
+     * of such a descriptor as a local read-only source (HBM backend: CUDA IPC, lzyb_slot_export / lzyb_peer_import) */
+    int (*slot_export)(lzyb_handle_t h, lzyb_ipc_desc_t* out);
+    int (*peer_import)(const lzyb_ipc_desc_t* desc, int onto_gpu, lzyb_handle_t* out);
 } lzyb_backend_ops_t;
 int lzyb_slots_set_backend(const lzyb_backend_ops_t* ops); /* NULL = the HBM backend */
 
@@ -161,6 +165,16 @@ typedef struct lzyb_cm_client_ops {
                            const char* description, lzyb_bind_result_t* out);
 } lzyb_cm_client_ops_t;
 int lzyb_slots_set_cm_client(const lzyb_cm_client_ops_t* ops); /* NULL = the in-process matcher */
+
+/* Slot peers that live in another worker process.  A consumer whose peer is not in this process's registry asks the
+ * resolver for the peer's descriptor — given the peer's URL (what that worker put into BindRequest.peer_url, e.g.
+ * "cuda+ipc://host:port?gpu=3") and its id — and maps it with the backend's peer_import; the transfer then pulls from
+ * the mapping exactly as from a local peer.  The other side of that question is lzyb_slots_describe: the descriptor of
+ * a producer slot registered on this worker (NOT_FOUND otherwise, as LzySlotsApi.Read answers).  On the wire the pair is
+ * one additive RPC next to LzySlotsApi (lzy_b200/grpc_api: LzybPeerApi.Describe); nothing in the reference's protos changes. */
+typedef int (*lzyb_peer_resolver_t)(const char* peer_url, const char* peer_id, lzyb_ipc_desc_t* out);
+int lzyb_slots_set_peer_resolver(lzyb_peer_resolver_t resolver); /* NULL = peers must be local (default) */
+int lzyb_slots_describe(lzyb_handle_t slots, const char* peer_id, lzyb_ipc_desc_t* out);
 
 #define LZYB_DIR_INPUT 1
 #define LZYB_DIR_OUTPUT 2

@@ -80,6 +80,8 @@ _SIGS = {
     "lzyb_blob_get": (C.c_int64, [_s, C.c_void_p, C.c_uint64]),
     "lzyb_blob_delete": (_i, [_s]),
     "lzyb_slots_set_cm_client": (_i, [C.c_void_p]),
+    "lzyb_slots_set_peer_resolver": (_i, [C.c_void_p]),
+    "lzyb_slots_describe": (_i, [_H, _s, C.c_void_p]),
     "lzyb_slots_transfer_log": (C.c_int64, [_H, C.c_char_p, C.c_uint64, C.c_int]),
     "lzyb_frame_store_put": (_i, [_s, _H]),
     "lzyb_frame_store_get": (_i, [_s, C.POINTER(_H)]),
@@ -442,6 +444,12 @@ class Slots:
             if got <= len(buf):
                 return json.loads(buf.value.decode())
             need = got
+
+    def describe(self, peer_id: str) -> bytes:
+        """the 256-byte descriptor of a producer slot of this worker, for a consumer in another process"""
+        desc = N.IpcDesc()
+        _check(lib.lzyb_slots_describe(self.h, _b(peer_id), C.byref(desc)))
+        return bytes(desc)
 
     def set_republish(self, on: bool) -> None:
         _check(lib.lzyb_slots_set_republish(self.h, int(on)))

@@ -45,6 +45,7 @@ const lzyb_backend_ops_t kHbmBackend = {
     lzyb_slot_create, lzyb_input_open,      lzyb_slot_commit,         lzyb_slot_read,       lzyb_slot_info,
     lzyb_slot_find,   lzyb_slot_close,      lzyb_transfer_chunk,      lzyb_input_finish,    lzyb_input_write_host,
     lzyb_input_finish_expect, lzyb_input_to_output, lzyb_input_reset, lzyb_slot_retain, lzyb_slot_set_meta,
+    lzyb_slot_export, lzyb_peer_import,
 };
 std::atomic<const lzyb_backend_ops_t*> g_ops{&kHbmBackend};
 lzyb_backend_ops_t g_custom_ops;
@@ -55,6 +56,9 @@ const lzyb_cm_client_ops_t kLocalMatcher = {lzyb_cm_bind, lzyb_cm_unbind, lzyb_c
 std::atomic<const lzyb_cm_client_ops_t*> g_cmc{&kLocalMatcher};
 lzyb_cm_client_ops_t g_custom_cmc;
 const lzyb_cm_client_ops_t& cmc() { return *g_cmc.load(); }
+
+// ---- peers in other worker processes ---------------------------------------------------------------------------------
+std::atomic<lzyb_peer_resolver_t> g_peer_resolver{nullptr};
 
 // ---- host blob store (storage peers) -----------------------------------------------------------------
 struct Blob {
@@ -636,17 +640,33 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
             return t;
         }
         lzyb_handle_t h = 0;
+        bool imported = false;
         if (ops().slot_find(p.peer_id, &h) != LZYB_OK) {
-            err = std::string("Cannot read from slot peer ") + p.peer_id + ": " + lzyb_last_error();
-            return nullptr;
+            // not in this process: another worker holds it.  Ask that worker for the frame's descriptor and map it
+            // (TransferFactory.input would open a gRPC stream to peer_url here, SlotInputTransfer.java:43-60).
+            const std::string local_err = lzyb_last_error();
+            lzyb_peer_resolver_t resolve = g_peer_resolver.load();
+            lzyb_ipc_desc_t desc;
+            if (!resolve || !ops().peer_import || p.url[0] == 0 || inst->api_url == p.url) {
+                err = std::string("Cannot read from slot peer ") + p.peer_id + ": " + local_err;
+                return nullptr;
+            }
+            memset(&desc, 0, sizeof(desc));
+            if (resolve(p.url, p.peer_id, &desc) != LZYB_OK || ops().peer_import(&desc, inst->gpu, &h) != LZYB_OK) {
+                err = std::string("Cannot read from slot peer ") + p.peer_id + " at " + p.url + ": " + lzyb_last_error();
+                return nullptr;
+            }
+            imported = true;
         }
         lzyb_slot_info_t info;
         if (ops().slot_info(h, &info) != LZYB_OK) {
             err = std::string("Cannot read from slot peer ") + p.peer_id + ": " + lzyb_last_error();
+            if (imported) ops().slot_close(h);
             return nullptr;
         }
         auto t = std::make_unique<SlotPullTransfer>();
         t->peer = h;
+        t->retained = imported;  // the mapping belongs to this transfer: closed with it
         t->size = info.nbytes;
         return t;
     }
@@ -1005,6 +1025,25 @@ int lzyb_slots_set_backend(const lzyb_backend_ops_t* o) {
     g_custom_ops = *o;
     g_ops = &g_custom_ops;
     return LZYB_OK;
+}
+
+int lzyb_slots_set_peer_resolver(lzyb_peer_resolver_t resolver) {
+    g_peer_resolver = resolver;
+    return LZYB_OK;
+}
+
+int lzyb_slots_describe(lzyb_handle_t h, const char* peer_id, lzyb_ipc_desc_t* out) {
+    auto inst = get_inst(h);
+    if (!inst) return fail(LZYB_E_ARG, "unknown slots handle");
+    if (!peer_id || !out) return fail(LZYB_E_ARG, "null argument");
+    auto s = inst->service.find(peer_id);
+    if (!s) return fail(LZYB_E_NOT_FOUND, "Slot not found: %s", peer_id);
+    if (s->is_input()) return fail(LZYB_E_UNIMPLEMENTED, "Slot %s is an input slot", peer_id);
+    if (!ops().slot_export) return fail(LZYB_E_UNIMPLEMENTED, "this backend cannot export frames");
+    lzyb_handle_t frame = 0;
+    int rc = ops().slot_find(peer_id, &frame);
+    if (rc != LZYB_OK) return fail(LZYB_E_NOT_FOUND, "Slot %s has no frame: %s", peer_id, lzyb_last_error());
+    return ops().slot_export(frame, out);
 }
 
 int lzyb_slots_set_cm_client(const lzyb_cm_client_ops_t* o) {

@@ -59,3 +59,7 @@ class WorkerApiClient(_Client):
 
 class LongRunningClient(_Client):
     SERVICE = "ai.lzy.v1.longrunning.LongRunningService"
+
+
+class PeerApiClient(_Client):
+    SERVICE = "ai.lzy.b200.v1.LzybPeerApi"

@@ -13,6 +13,9 @@
   ai/lzy/v1/worker/worker-service.proto:14-50  WorkerApi: Init*, Execute*
   ai/lzy/v1/long-running/operation.proto:12-47 LongRunningService.Get, Operation (google.rpc.Status restated: code, message, details)
 
+and one additive service of this repository's own (package ai.lzy.b200.v1, nothing of the reference's changes):
+  LzybPeerApi.Describe(peer_id) -> the 256-byte lzyb_ipc_desc_t of a producer slot (include/lzy_b200_host.h: lzyb_slots_describe)
+
 A message serialized here parses with the reference's generated classes and vice versa (same
 package, names, numbers and types)."""
 from __future__ import annotations
@@ -204,6 +207,15 @@ _worker.message_type.extend([
 _pool.Add(_worker)
 
 
+# ---- ai.lzy.b200.v1: the one additive RPC (peers in other worker processes) ------------------------------------
+_peer = descriptor_pb2.FileDescriptorProto(name="lzyb/ai/lzy/b200/v1/peer-api.proto", package="ai.lzy.b200.v1", syntax="proto3")
+_peer.message_type.extend([
+    _msg("DescribeRequest", [_field("peer_id", 1, STR)]),
+    _msg("DescribeResponse", [_field("descriptor", 1, BYTES)]),
+])
+_pool.Add(_peer)
+
+
 def _cls(full_name):
     return message_factory.GetMessageClass(_pool.FindMessageTypeByName(full_name))
 
@@ -227,6 +239,8 @@ messages = _Messages()
 LongRunningOperation = _cls("ai.lzy.v1.longrunning.Operation")   # (common also has an `Operation`: the task's)
 GetOperationRequest = _cls("ai.lzy.v1.longrunning.GetOperationRequest")
 RpcStatus = _cls("google.rpc.Status")
+DescribeRequest = _cls("ai.lzy.b200.v1.DescribeRequest")
+DescribeResponse = _cls("ai.lzy.b200.v1.DescribeResponse")
 
 # service → method → (request class name, response class name, server-streaming?)
 SERVICES: Dict[str, Dict[str, Tuple[str, str, bool]]] = {
@@ -251,6 +265,9 @@ SERVICES: Dict[str, Dict[str, Tuple[str, str, bool]]] = {
     "ai.lzy.v1.worker.WorkerApi": {
         "Init": ("InitRequest", "InitResponse", False),
         "Execute": ("ExecuteRequest", "ai.lzy.v1.longrunning.Operation", False),
+    },
+    "ai.lzy.b200.v1.LzybPeerApi": {
+        "Describe": ("ai.lzy.b200.v1.DescribeRequest", "ai.lzy.b200.v1.DescribeResponse", False),
     },
     "ai.lzy.v1.longrunning.LongRunningService": {
         "Get": ("ai.lzy.v1.longrunning.GetOperationRequest", "ai.lzy.v1.longrunning.Operation", False),

@@ -11,7 +11,7 @@ import grpc
 
 from .. import _host as H
 from .. import _native as N
-from .protos import SERVICES, LongRunningOperation, messages, method_types
+from .protos import SERVICES, DescribeResponse, LongRunningOperation, messages, method_types
 
 READ_CHUNK = 2 << 20  # OutputSlot.java:241
 _STATUS = {N.E_NOT_FOUND: grpc.StatusCode.NOT_FOUND, N.E_PRECONDITION: grpc.StatusCode.FAILED_PRECONDITION,
@@ -184,6 +184,24 @@ class ChannelManagerService:
         return resp
 
 
+class PeerApiService:
+    """ai.lzy.b200.v1.LzybPeerApi — the additive RPC a consumer in another worker process uses to map a producer's
+    frame: Describe(peer_id) → lzyb_ipc_desc_t (same NOT_FOUND / UNAVAILABLE behaviour as LzySlotsApi.Read)."""
+    SERVICE = "ai.lzy.b200.v1.LzybPeerApi"
+
+    def __init__(self, slots):
+        self._source = slots
+
+    def Describe(self, request, context):
+        slots = self._source if isinstance(self._source, H.Slots) else self._source.slots
+        if slots is None:
+            context.abort(grpc.StatusCode.UNAVAILABLE, "worker is not initialized")
+        try:
+            return DescribeResponse(descriptor=slots.describe(request.peer_id))
+        except N.LzybError as e:
+            _abort(context, e)
+
+
 def _operation_to_proto(op):
     """worker.Operation → ai.lzy.v1.longrunning.Operation; the result is ``response = Any(ExecuteResponse)``
     as declared by the ``(ai.lzy.v1.operation)`` option of WorkerApi.Execute (worker-service.proto:17-22)"""
@@ -260,13 +278,15 @@ def serve(address: str = "127.0.0.1:0", slots: Optional[H.Slots] = None, cm: Opt
     server = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers),
                          options=[("grpc.max_send_message_length", 8 << 20), ("grpc.max_receive_message_length", 8 << 20)])
     if slots is not None:
-        server.add_generic_rpc_handlers((_generic_handler(SlotsApiService.SERVICE, SlotsApiService(slots)),))
+        server.add_generic_rpc_handlers((_generic_handler(SlotsApiService.SERVICE, SlotsApiService(slots)),
+                                         _generic_handler(PeerApiService.SERVICE, PeerApiService(slots))))
     if cm is not None:
         svc = ChannelManagerService(cm)
         server.add_generic_rpc_handlers((_generic_handler(svc.SERVICE, svc), _generic_handler(svc.PRIVATE_SERVICE, svc)))
     if worker is not None:
         if slots is None:
-            server.add_generic_rpc_handlers((_generic_handler(SlotsApiService.SERVICE, SlotsApiService(worker)),))
+            server.add_generic_rpc_handlers((_generic_handler(SlotsApiService.SERVICE, SlotsApiService(worker)),
+                                             _generic_handler(PeerApiService.SERVICE, PeerApiService(worker))))
         server.add_generic_rpc_handlers((_generic_handler(WorkerApiService.SERVICE, WorkerApiService(worker)),
                                          _generic_handler(LongRunningService.SERVICE, LongRunningService(worker))))
     port = server.add_insecure_port(address)

@@ -38,4 +38,6 @@ int lzyb_input_to_output(lzyb_handle_t) { unreachable("input_to_output"); }
 int lzyb_input_reset(lzyb_handle_t) { unreachable("input_reset"); }
 int lzyb_slot_retain(lzyb_handle_t) { unreachable("slot_retain"); }
 int lzyb_slot_set_meta(lzyb_handle_t, uint32_t, uint32_t, const uint64_t*) { unreachable("slot_set_meta"); }
+int lzyb_slot_export(lzyb_handle_t, lzyb_ipc_desc_t*) { unreachable("slot_export"); }
+int lzyb_peer_import(const lzyb_ipc_desc_t*, int, lzyb_handle_t*) { unreachable("peer_import"); }
 }

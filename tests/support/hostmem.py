@@ -19,7 +19,7 @@ def load():
     if not _SO.exists() or _SO.stat().st_mtime < max(d.stat().st_mtime for d in deps):
         _SO.parent.mkdir(exist_ok=True)
         subprocess.run(["gcc", "-O1", "-fPIC", "-shared", "-Wall", "-o", str(_SO), str(src), f"-L{libdir}",
-                        "-llzy_b200", f"-Wl,-rpath,{libdir}", "-lpthread"], check=True)
+                        "-llzy_b200", f"-Wl,-rpath,{libdir}", "-lpthread", "-lrt"], check=True)
     from lzy_b200 import _native  # noqa: F401  (liblzy_b200.so must be loaded first)
     lib = C.CDLL(str(_SO))
     lib.hostmem_write.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]

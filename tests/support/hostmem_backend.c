@@ -8,10 +8,14 @@
  * by tests/ so the InputSlot / OutputSlot / execution-context logic runs on a box without a GPU.
  * Digests use the shared definition (include/lzyb_digest.h) so verification behaves like the HBM path.
  */
+#include <fcntl.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/lzy_b200_host.h"
 #include "../../include/lzyb_digest.h"
@@ -31,6 +35,8 @@ typedef struct {
     long long fail_after; /* -1 = never */
     int fail_read;
     int refs;
+    int mapped;          /* data is an mmap of another process's export (peer_import) */
+    char shm_name[64];   /* this slot has been exported under that POSIX shm name */
 } mem_slot_t;
 
 static mem_slot_t g_slots[MAX_SLOTS];
@@ -199,7 +205,11 @@ static int m_slot_close(lzyb_handle_t h) {
     pthread_mutex_lock(&g_mu);
     mem_slot_t* s = find(h);
     if (s && --s->refs <= 0) {
-        free(s->data);
+        if (s->mapped)
+            munmap(s->data, s->nbytes ? s->nbytes : 1);
+        else
+            free(s->data);
+        if (s->shm_name[0]) shm_unlink(s->shm_name);
         s->used = 0;
     }
     pthread_mutex_unlock(&g_mu);
@@ -329,10 +339,98 @@ static int m_input_reset(lzyb_handle_t h) {
     return s ? LZYB_OK : err(LZYB_E_ARG, "unknown slot handle");
 }
 
+/* The cross-process path of this backend, standing in for CUDA IPC: an export publishes a copy of the committed
+ * payload as a POSIX shared-memory object whose name rides in the descriptor's 64 handle bytes; an import maps it
+ * read-only and registers it as a READY source slot. */
+static int m_slot_export(lzyb_handle_t h, lzyb_ipc_desc_t* out) {
+    pthread_mutex_lock(&g_mu);
+    mem_slot_t* s = find(h);
+    int rc = LZYB_OK;
+    if (!s || s->state != LZYB_ST_READY) {
+        rc = err(LZYB_E_STATE, "slot is not committed");
+    } else {
+        if (!s->shm_name[0]) {
+            snprintf(s->shm_name, sizeof(s->shm_name), "/lzyb-hostmem-%d-%llx", (int)getpid(), (unsigned long long)s->h);
+            int fd = shm_open(s->shm_name, O_CREAT | O_RDWR | O_TRUNC, 0600);
+            if (fd < 0 || ftruncate(fd, (off_t)(s->nbytes ? s->nbytes : 1)) != 0) {
+                rc = err(LZYB_E_LOCAL, "cannot create shared memory");
+                s->shm_name[0] = 0;
+            } else if (s->nbytes) {
+                void* p = mmap(NULL, s->nbytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+                if (p == MAP_FAILED) {
+                    rc = err(LZYB_E_LOCAL, "cannot map shared memory");
+                } else {
+                    memcpy(p, s->data, s->nbytes);
+                    munmap(p, s->nbytes);
+                }
+            }
+            if (fd >= 0) close(fd);
+        }
+        if (rc == LZYB_OK) {
+            memset(out, 0, sizeof(*out));
+            memcpy(out->ipc_handle, s->shm_name, strlen(s->shm_name) + 1);
+            out->buffer_bytes = s->nbytes;
+            out->nbytes = s->nbytes;
+            out->gpu = s->gpu;
+            out->pid = (int32_t)getpid();
+            out->digest[0] = s->digest[0];
+            out->digest[1] = s->digest[1];
+            out->dtype = s->dtype;
+            out->ndim = s->ndim;
+            memcpy(out->shape, s->shape, sizeof(out->shape));
+        }
+    }
+    pthread_mutex_unlock(&g_mu);
+    return rc;
+}
+
+static int m_peer_import(const lzyb_ipc_desc_t* desc, int gpu, lzyb_handle_t* out) {
+    char name[65];
+    memcpy(name, desc->ipc_handle, 64);
+    name[64] = 0;
+    int fd = shm_open(name, O_RDONLY, 0);
+    if (fd < 0) return err(LZYB_E_PEER, "cannot open the peer's shared memory");
+    void* p = mmap(NULL, desc->nbytes ? desc->nbytes : 1, PROT_READ, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return err(LZYB_E_PEER, "cannot map the peer's shared memory");
+    pthread_mutex_lock(&g_mu);
+    int rc = LZYB_E_LOCAL;
+    for (int i = 0; i < MAX_SLOTS; ++i) {
+        if (g_slots[i].used) continue;
+        mem_slot_t* s = &g_slots[i];
+        memset(s, 0, sizeof(*s));
+        s->used = 1;
+        s->h = g_next++;
+        snprintf(s->id, sizeof(s->id), "import:%d:%s", desc->pid, name);
+        s->data = (uint8_t*)p;
+        s->mapped = 1;
+        s->nbytes = s->delivered = desc->nbytes;
+        s->state = LZYB_ST_READY;
+        s->gpu = gpu;
+        s->digest[0] = desc->digest[0];
+        s->digest[1] = desc->digest[1];
+        s->dtype = desc->dtype;
+        s->ndim = desc->ndim;
+        memcpy(s->shape, desc->shape, sizeof(s->shape));
+        s->fail_after = -1;
+        s->refs = 1;
+        *out = s->h;
+        rc = LZYB_OK;
+        break;
+    }
+    pthread_mutex_unlock(&g_mu);
+    if (rc != LZYB_OK) {
+        munmap(p, desc->nbytes ? desc->nbytes : 1);
+        return err(LZYB_E_LOCAL, "too many slots");
+    }
+    return LZYB_OK;
+}
+
 const lzyb_backend_ops_t hostmem_backend_ops = {
     m_slot_create,    m_input_open,     m_slot_commit,         m_slot_read,       m_slot_info,
     m_slot_find,      m_slot_close,     m_transfer_chunk,      m_input_finish,    m_input_write_host,
     m_input_finish_expect, m_input_to_output, m_input_reset, m_slot_retain, m_slot_set_meta,
+    m_slot_export, m_peer_import,
 };
 
 /* ---- test helpers ---- */

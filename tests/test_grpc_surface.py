@@ -338,3 +338,71 @@ def test_workers_against_a_channel_manager_in_another_process():
         hostmem.uninstall()
         proc.terminate()
         proc.wait(timeout=15)
+
+
+def test_consumer_pulls_from_a_producer_in_another_process():
+    """Three processes: channel manager, a producer worker, and (here) a consumer worker.  The consumer's Bind names
+    a slot peer that is not in its own registry, so the transfer factory asks the peer's worker for the frame's
+    descriptor (LzybPeerApi.Describe → lzyb_slots_describe) and maps it (the backend's peer_import: CUDA IPC on a GPU
+    box, POSIX shared memory in the in-memory test backend), then pulls and verifies as from a local peer."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import oracle
+    from lzy_b200.grpc_api import peers, remote_cm
+    root = Path(__file__).resolve().parent.parent
+    nbytes, seed = (3 << 20) + 17, 11
+    cm_proc = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "channel-manager", "--port", "0", "--seed", "4"],
+                               cwd=str(root), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    producer = None
+    hostmem.install()
+    peers.install()
+    slots = server = None
+    try:
+        cm_target = cm_proc.stdout.readline().strip().rsplit(" ", 1)[-1]
+        priv = ChannelManagerPrivateClient(cm_target)
+        chan = priv.call("GetOrCreate", M.GetOrCreateRequest(execution_id="exec-mp", workflow_name="wf", user_id="u",
+                                                             consumer=storage_peer("mem://mp/unused"))).channel_id
+        producer = subprocess.Popen([sys.executable, str(root / "tests/support/remote_worker.py"), cm_target, chan,
+                                     str(nbytes), str(seed)], cwd=str(root), stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                    stderr=subprocess.PIPE, text=True)
+        line = producer.stdout.readline()
+        assert line.startswith("READY"), line + producer.stderr.read()
+        producer_url = line.split()[1]
+
+        cm = remote_cm.connect(cm_target)
+        probe, port = serve("127.0.0.1:0")
+        probe.stop(0)
+        slots = H.Slots(cm, 0, f"127.0.0.1:{port}")
+        server, _ = serve(f"127.0.0.1:{port}", slots=slots)
+        before = peers.resolved
+        cons = slots.context("exec-mp", "consumer")
+        cons.add_slot("/local/in", chan, H.DIR_INPUT)
+        cons.before_execution(20000)
+        want = oracle.pattern(nbytes, seed).tobytes()
+        assert hostmem.peek(cons.input_handle("/local/in"), nbytes) == want
+        (rec,) = [r for r in slots.transfer_log() if r["slot_id"] == "/local/in"]
+        assert rec["ok"] and rec["peer_kind"] == "slot" and rec["peer_id"] == "/remote/out" and rec["bytes"] == nbytes
+        assert peers.resolved == before + 1  # one descriptor fetched from the other worker
+        st = priv.call("Status", M.StatusRequest(channel_id=chan)).channel
+        assert any(p.slot_peer.peer_url == producer_url for p in st.producers)
+        cons.close()
+        priv.close()
+    finally:
+        if producer is not None:
+            try:
+                producer.stdin.write("bye\n")
+                producer.stdin.flush()
+                producer.wait(timeout=20)
+            except Exception:  # noqa: BLE001
+                producer.kill()
+        if server is not None:
+            server.stop(0)
+        if slots is not None:
+            slots.close()
+        peers.uninstall()
+        remote_cm.disconnect_all()
+        hostmem.uninstall()
+        cm_proc.terminate()
+        cm_proc.wait(timeout=15)
