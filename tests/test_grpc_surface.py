@@ -406,3 +406,17 @@ def test_consumer_pulls_from_a_producer_in_another_process():
         hostmem.uninstall()
         cm_proc.terminate()
         cm_proc.wait(timeout=15)
+
+
+def test_worker_entry_point_refuses_to_start_without_a_gpu():
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for GPU-less boxes")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "lzy_b200.grpc_api", "worker", "--gpu", "0", "--port", "18999",
+                        "--channel-manager", "127.0.0.1:1"], cwd=str(root), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3 and "needs a CUDA device" in r.stdout
