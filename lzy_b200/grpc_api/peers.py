@@ -36,6 +36,9 @@ def _resolve(url: bytes, peer_id: bytes, out) -> int:
     except grpc.RpcError as e:
         N.lib.lzyb_set_last_error((e.details() or str(e.code())).encode())
         return _CODES.get(e.code(), N.E_PEER)
+    except Exception as e:  # noqa: BLE001 — an exception escaping a ctypes callback would read as rc 0
+        N.lib.lzyb_set_last_error(f"peer resolver failed: {type(e).__name__}: {e}".encode()[:500])
+        return N.E_PEER
     if len(raw) != C.sizeof(N.IpcDesc):
         N.lib.lzyb_set_last_error(b"peer sent a malformed descriptor")
         return N.E_PEER

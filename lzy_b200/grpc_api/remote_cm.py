@@ -77,6 +77,18 @@ def _fill(out, peer, transfer_id: str) -> None:
     r.transfer_id = transfer_id.encode()
 
 
+def _guarded(fn):
+    """an exception escaping a ctypes callback would be printed and read as rc 0: turn it into INTERNAL"""
+    def wrapper(*args):
+        try:
+            return fn(*args)
+        except Exception as e:  # noqa: BLE001
+            N.lib.lzyb_set_last_error(f"channel manager client failed: {type(e).__name__}: {e}".encode()[:500])
+            return N.E_INTERNAL
+    return wrapper
+
+
+@_guarded
 def _bind(cookie, idk, channel_id, peer_id, execution_id, peer_url, role, out) -> int:
     try:
         resp = _remotes[cookie].client.call("Bind", messages.BindRequest(
@@ -88,6 +100,7 @@ def _bind(cookie, idk, channel_id, peer_id, execution_id, peer_url, role, out) -
     return N.OK
 
 
+@_guarded
 def _unbind(cookie, channel_id, peer_id) -> int:
     try:
         _remotes[cookie].client.call("Unbind", messages.UnbindRequest(peer_id=_s(peer_id), channel_id=_s(channel_id)))
@@ -96,6 +109,7 @@ def _unbind(cookie, channel_id, peer_id) -> int:
     return N.OK
 
 
+@_guarded
 def _completed(cookie, idk, channel_id, transfer_id) -> int:
     try:
         _remotes[cookie].client.call("TransferCompleted", messages.TransferCompletedRequest(
@@ -105,6 +119,7 @@ def _completed(cookie, idk, channel_id, transfer_id) -> int:
     return N.OK
 
 
+@_guarded
 def _failed(cookie, idk, channel_id, transfer_id, description, out) -> int:
     try:
         resp = _remotes[cookie].client.call("TransferFailed", messages.TransferFailedRequest(
