@@ -5,10 +5,10 @@
 reference's stubs.  Control messages only: payload bytes move by the CUDA kernels; ``Read`` exists
 for *legacy* CPU consumers and streams 2 MiB chunks + EOS out of HBM."""
 from .protos import messages, method_types
-from .server import ChannelManagerService, LongRunningService, SlotsApiService, WorkerApiService, serve
+from .server import ChannelManagerService, LongRunningService, PeerApiService, SlotsApiService, WorkerApiService, serve
 from .pump import RemoteActionPump
-from .client import ChannelManagerClient, ChannelManagerPrivateClient, LongRunningClient, SlotsApiClient, WorkerApiClient
+from .client import ChannelManagerClient, ChannelManagerPrivateClient, LongRunningClient, PeerApiClient, SlotsApiClient, WorkerApiClient
 
 __all__ = ["messages", "method_types", "ChannelManagerService", "SlotsApiService", "serve", "ChannelManagerClient",
            "ChannelManagerPrivateClient", "SlotsApiClient", "WorkerApiService", "LongRunningService", "WorkerApiClient",
-           "LongRunningClient", "RemoteActionPump"]
+           "LongRunningClient", "RemoteActionPump", "PeerApiService", "PeerApiClient"]

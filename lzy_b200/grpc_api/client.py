@@ -12,6 +12,7 @@ class _Client:
     SERVICE = ""
 
     def __init__(self, target: str):
+        self.target = target
         self.channel = grpc.insecure_channel(target, options=[("grpc.max_receive_message_length", 8 << 20)])
         for method in SERVICES[self.SERVICE]:
             req_cls, resp_cls, streaming = method_types(self.SERVICE, method)

@@ -420,3 +420,34 @@ def test_worker_entry_point_refuses_to_start_without_a_gpu():
     r = subprocess.run([sys.executable, "-m", "lzy_b200.grpc_api", "worker", "--gpu", "0", "--port", "18999",
                         "--channel-manager", "127.0.0.1:1"], cwd=str(root), capture_output=True, text=True, timeout=120)
     assert r.returncode == 3 and "needs a CUDA device" in r.stdout
+
+
+def test_unreachable_remote_peer_is_a_read_failure_and_the_backup_serves(stack):
+    """a slot producer registered by a worker that has since died: resolving it fails, the consumer reports
+    TransferFailed until the channel manager hands out the storage backup; Describe of an unknown slot is NOT_FOUND"""
+    from lzy_b200.grpc_api import PeerApiClient, peers
+    from lzy_b200.grpc_api.protos import DescribeRequest
+    cm, slots, pub, priv, sapi = stack
+    peers.install()
+    try:
+        data = os.urandom(50_000)
+        H.blob_put("mem://ghost/backup", data)
+        chan = cm.get_or_create("u", "wf", "exec-ghost", producer_uri="mem://ghost/backup")
+        cm.bind(chan, H.ROLE_PRODUCER, "/ghost/out", "127.0.0.1:1", "exec-ghost")  # PRIMARY, but nobody is there
+        cons = slots.context("exec-ghost", "c")
+        cons.add_slot("/ghost/in", chan, H.DIR_INPUT)
+        cons.before_execution(20000)
+        assert hostmem.peek(cons.input_handle("/ghost/in"), len(data)) == data
+        (rec,) = [r for r in slots.transfer_log() if r["slot_id"] == "/ghost/in"]
+        assert rec["failovers"] >= 1 and rec["peer_kind"] == "storage"
+        assert cm.peer_priority(chan, "/ghost/out") < H.PRIO_PRIMARY
+        cons.close()
+
+        client = PeerApiClient(sapi.target)
+        with pytest.raises(grpc.RpcError) as e:
+            client.call("Describe", DescribeRequest(peer_id="/no/such/slot"))
+        assert e.value.code() == grpc.StatusCode.NOT_FOUND
+        client.close()
+    finally:
+        peers.uninstall()
+        H.blob_delete("mem://ghost/backup")
