@@ -236,6 +236,38 @@ int spill_read(const std::string& path, const std::string& uri, int gpu, lzyb_ha
     return LZYB_OK;
 }
 
+// ---- "file://" storage peers: the box-local durable storage (what FsStorageClient is to the reference's local
+// runtime, pylzy/lzy/storage/async_/fs.py) — same file format as the spill tier, reachable from every process ----------
+bool is_file_uri(const char* uri) { return uri && strncmp(uri, "file://", 7) == 0; }
+std::string file_path_of(const std::string& uri) { return uri.substr(7); }
+
+void make_parent_dirs(const std::string& path) {
+    for (size_t i = 1; i < path.size(); ++i)
+        if (path[i] == '/') ::mkdir(path.substr(0, i).c_str(), 0755);
+}
+
+// what a stored file says about itself without reading the payload
+struct StoredFile {
+    bool framed = false;
+    lzyb_frame_header_t hdr{};
+    uint64_t nbytes = 0;
+};
+
+bool stat_stored_file(const std::string& path, StoredFile* out) {
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    bool ok = ::fstat(fd, &st) == 0;
+    if (ok) {
+        out->framed = (uint64_t)st.st_size >= sizeof(out->hdr) && read_fully(fd, &out->hdr, sizeof(out->hdr)) &&
+                      memcmp(out->hdr.magic, "LZYB200", 8) == 0 && out->hdr.nbytes + sizeof(out->hdr) == (uint64_t)st.st_size &&
+                      out->hdr.ndim <= LZYB_MAX_DIMS;
+        out->nbytes = out->framed ? out->hdr.nbytes : (uint64_t)st.st_size;
+    }
+    ::close(fd);
+    return ok;
+}
+
 // resident frame, or — when the spill tier holds the URI — a frame loaded from it (registered, so that every
 // later consumer shares it).  LZYB_E_NOT_FOUND if neither; the loader's error if the file exists but is unusable.
 int frame_lookup(const std::string& uri, int gpu, lzyb_handle_t* out) {
@@ -472,6 +504,11 @@ struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
     // StorageOutputTransfer.readFrom(backend.readFromOffset(0))
     bool upload_to_storage(const char* uri) {
         if (is_hbm_uri(uri)) return lzyb_frame_store_put(uri, backend) == LZYB_OK;  // stays in HBM: no copy
+        if (is_file_uri(uri)) {  // durable and visible to every process of the box
+            const std::string path = file_path_of(uri);
+            make_parent_dirs(path);
+            return spill_write(path, backend) == LZYB_OK;
+        }
         lzyb_slot_info_t info;
         if (ops().slot_info(backend, &info) != LZYB_OK) return false;
         auto blob = std::make_shared<Blob>();
@@ -532,6 +569,43 @@ struct SlotPullTransfer : InputTransfer {
     }
     int finish(lzyb_handle_t sink) override { return ops().input_finish(sink, peer, nullptr); }
     uint64_t nbytes() const override { return size; }
+};
+
+// StorageInputTransfer over a "file://" object: header (if any) → dtype / shape / digest, payload streamed into the sink
+struct FileTransfer : InputTransfer {
+    std::string path;
+    StoredFile info;
+    bool sent = false;
+    int64_t transfer_chunk_to(lzyb_handle_t sink, uint64_t offset, uint64_t) override {
+        if (sent || (offset >= info.nbytes && info.nbytes != 0)) return LZYB_EOF;
+        if (offset != 0 && ops().input_reset(sink) != LZYB_OK) return LZYB_E_LOCAL;  // restart: the digest covers the whole object
+        int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return fail(LZYB_E_PEER, "Error while reading from storage: cannot open %s", path.c_str());
+        if (info.framed) {
+            ::lseek(fd, sizeof(lzyb_frame_header_t), SEEK_SET);
+            if (ops().slot_set_meta) ops().slot_set_meta(sink, info.hdr.dtype, info.hdr.ndim, info.hdr.shape);
+        }
+        std::vector<uint8_t> buf(std::min<uint64_t>(std::max<uint64_t>(info.nbytes, 1), SPILL_STEP));
+        int64_t rc = (int64_t)info.nbytes;
+        for (uint64_t off = 0; off < info.nbytes;) {
+            const uint64_t step = std::min<uint64_t>(info.nbytes - off, buf.size());
+            if (!read_fully(fd, buf.data(), step)) {
+                rc = fail(LZYB_E_PEER, "Error while reading from storage: short read from %s", path.c_str());
+                break;
+            }
+            int64_t n = ops().input_write_host(sink, off, buf.data(), step, nullptr);
+            if (n < 0) {
+                rc = n;
+                break;
+            }
+            off += (uint64_t)n;
+        }
+        ::close(fd);
+        if (rc >= 0) sent = true;
+        return rc;
+    }
+    int finish(lzyb_handle_t sink) override { return ops().input_finish_expect(sink, info.framed ? info.hdr.digest : nullptr, nullptr); }
+    uint64_t nbytes() const override { return info.nbytes; }
 };
 
 // StorageInputTransfer: the whole object in one go, then EOF (StorageInputTransfer.java:32-41)
@@ -627,6 +701,15 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
                 return nullptr;
             }
             t->size = info.nbytes;
+            return t;
+        }
+        if (p.kind == LZYB_PEER_STORAGE && is_file_uri(p.url)) {
+            auto t = std::make_unique<FileTransfer>();
+            t->path = file_path_of(p.url);
+            if (!stat_stored_file(t->path, &t->info)) {
+                err = std::string("Error while reading from storage: no object at ") + p.url;
+                return nullptr;
+            }
             return t;
         }
         if (p.kind == LZYB_PEER_STORAGE) {

@@ -340,7 +340,7 @@ def test_workers_against_a_channel_manager_in_another_process():
         proc.wait(timeout=15)
 
 
-def test_consumer_pulls_from_a_producer_in_another_process():
+def test_consumer_pulls_from_a_producer_in_another_process(tmp_path):
     """Three processes: channel manager, a producer worker, and (here) a consumer worker.  The consumer's Bind names
     a slot peer that is not in its own registry, so the transfer factory asks the peer's worker for the frame's
     descriptor (LzybPeerApi.Describe → lzyb_slots_describe) and maps it (the backend's peer_import: CUDA IPC on a GPU
@@ -362,8 +362,9 @@ def test_consumer_pulls_from_a_producer_in_another_process():
     try:
         cm_target = cm_proc.stdout.readline().strip().rsplit(" ", 1)[-1]
         priv = ChannelManagerPrivateClient(cm_target)
+        backup = tmp_path / "store" / "mp.lzyb"  # a file:// storage consumer: the producer process uploads its output there
         chan = priv.call("GetOrCreate", M.GetOrCreateRequest(execution_id="exec-mp", workflow_name="wf", user_id="u",
-                                                             consumer=storage_peer("mem://mp/unused"))).channel_id
+                                                             consumer=storage_peer(f"file://{backup}"))).channel_id
         producer = subprocess.Popen([sys.executable, str(root / "tests/support/remote_worker.py"), cm_target, chan,
                                      str(nbytes), str(seed)], cwd=str(root), stdin=subprocess.PIPE, stdout=subprocess.PIPE,
                                     stderr=subprocess.PIPE, text=True)
@@ -388,6 +389,21 @@ def test_consumer_pulls_from_a_producer_in_another_process():
         st = priv.call("Status", M.StatusRequest(channel_id=chan)).channel
         assert any(p.slot_peer.peer_url == producer_url for p in st.producers)
         cons.close()
+
+        # the producer's process goes away; its output survives as the channel's file:// backup, which a late consumer
+        # in this process reads after the dead slot peer has used up its retries
+        assert backup.exists()
+        producer.stdin.write("bye\n")
+        producer.stdin.flush()
+        producer.wait(timeout=20)
+        producer = None
+        late = slots.context("exec-mp", "late")
+        late.add_slot("/local/in2", chan, H.DIR_INPUT)
+        late.before_execution(30000)
+        assert hostmem.peek(late.input_handle("/local/in2"), nbytes) == want
+        (rec2,) = [r for r in slots.transfer_log() if r["slot_id"] == "/local/in2"]
+        assert rec2["ok"] and rec2["peer_kind"] == "storage"
+        late.close()
         priv.close()
     finally:
         if producer is not None:

@@ -182,3 +182,59 @@ def test_concurrent_consumers_of_one_spilled_uri_share_a_single_load(env):
         assert hostmem.peek(c.input_handle(f"in{i}"), len(data)) == data
     for c in ctxs:
         c.close()
+
+
+# ---- "file://" storage peers: the durable, box-wide storage --------------------------------------------------------
+def test_file_storage_peer_upload_download_meta_and_corruption(env, tmp_path):
+    """an op output whose channel's storage consumer is a file:// URI lands as [header][payload]; any later consumer
+    (any process of the box) reads it back with dtype / shape / digest; a rotten file is a read failure"""
+    cm, slots, lib, d = env
+    data = os.urandom((1 << 20) + 3)
+    uri = f"file://{tmp_path}/store/deep/obj.lzyb"
+    chan = cm.get_or_create("u", "wf", "exec-f", consumer_uri=uri)
+    out = slots.context("exec-f", "p")
+    out.add_slot("/f/out", chan, DIR_OUTPUT)
+    out.before_execution()
+    h = out.output_open("/f/out", len(data))
+    hostmem.set_meta(h, N.DT_I64, (7, 11))
+    hostmem.write(h, data)
+    out.output_done("/f/out")
+    out.after_execution(10000)
+    raw = (tmp_path / "store/deep/obj.lzyb").read_bytes()
+    assert raw[:8] == b"LZYB200\0" and raw[128:] == data
+    out.close()  # the slot producer is gone: the file is all there is
+
+    cons = slots.context("exec-f", "c")
+    cons.add_slot("/f/in", chan, DIR_INPUT)
+    cons.before_execution(10000)
+    got = cons.input_handle("/f/in")
+    info = hostmem.info(got)
+    assert hostmem.peek(got, len(data)) == data and (info.dtype, info.ndim, tuple(info.shape[:2])) == (N.DT_I64, 2, (7, 11))
+    cons.close()
+
+    rotten = bytearray(raw)
+    rotten[128 + 99] ^= 1
+    (tmp_path / "store/deep/obj.lzyb").write_bytes(bytes(rotten))
+    bad = slots.context("exec-f", "c2")
+    bad.add_slot("/f/in2", chan, DIR_INPUT)
+    with pytest.raises(N.LzybError, match="No more producers|Cannot get data"):
+        bad.before_execution(10000)  # the only producer keeps failing its digest: the channel is given up
+    bad.close()
+
+
+def test_pre_existing_plain_file_is_a_storage_producer(env, tmp_path):
+    cm, slots, lib, d = env
+    p = tmp_path / "input.bin"
+    p.write_bytes(b"bytes somebody else wrote")
+    chan = cm.get_or_create("u", "wf", "exec-f2", producer_uri=f"file://{p}")
+    cons = slots.context("exec-f2", "c")
+    cons.add_slot("/f2/in", chan, DIR_INPUT)
+    cons.before_execution(10000)
+    assert hostmem.peek(cons.input_handle("/f2/in"), 64) == b"bytes somebody else wrote"
+    cons.close()
+    missing = cm.get_or_create("u", "wf", "exec-f3", producer_uri=f"file://{tmp_path}/nope")
+    lost = slots.context("exec-f3", "c")
+    lost.add_slot("/f3/in", missing, DIR_INPUT)
+    with pytest.raises(N.LzybError):
+        lost.before_execution(10000)
+    lost.close()
