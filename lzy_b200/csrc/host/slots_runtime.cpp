@@ -683,11 +683,14 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
 
     std::unique_ptr<InputTransfer> make_transfer(const lzyb_peer_desc_t& p, std::string& err) {
         // TransferFactory.input(peer, offset)
-        if (p.kind == LZYB_PEER_STORAGE && is_hbm_uri(p.url)) {
-            // resident, or spilled: then it is loaded straight onto this worker's GPU
-            lzyb_handle_t h = 0;
+        // a storage peer is served from the frame store whenever the frame is there (resident, or spilled: then it is
+        // loaded straight onto this worker's GPU) — for "hbm://" URIs that is the only place, for the others a cache
+        lzyb_handle_t cached = 0;
+        const int lookup = p.kind == LZYB_PEER_STORAGE ? frame_lookup(p.url, inst->gpu, &cached) : LZYB_E_NOT_FOUND;
+        if (p.kind == LZYB_PEER_STORAGE && (is_hbm_uri(p.url) || lookup == LZYB_OK)) {
+            lzyb_handle_t h = cached;
             lzyb_slot_info_t info;
-            int rc = frame_lookup(p.url, inst->gpu, &h);
+            int rc = lookup;
             if (rc != LZYB_OK || ops().slot_retain(h) != LZYB_OK) {
                 err = std::string("Error while reading from storage: ") +
                       (rc == LZYB_OK || rc == LZYB_E_NOT_FOUND ? std::string("no frame at ") + p.url : std::string(lzyb_last_error()));
