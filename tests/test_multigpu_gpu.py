@@ -150,6 +150,22 @@ def test_chain_round_robin_over_gpus(lzy):
     assert len(set(seen)) == min(NGPU, 8) and N.stats()["bytes_pulled_peer"] - before >= 6 * x.numel() * 4
 
 
+def test_long_edges_through_the_runtime_ride_the_copy_engine(lzy):
+    """a 256 MiB edge between ops on different GPUs takes the auto policy's copy-engine carrier inside the slots
+    runtime's download loop (not only when lzyb_transfer_chunk is called by hand), and stays bit-exact"""
+    @op
+    def hop(t: torch.Tensor) -> torch.Tensor:
+        return t
+
+    x = torch.empty(8192, 8192, device="cuda:0").normal_()  # 256 MiB
+    keep = x.clone()
+    before = N.stats()["dma_copies"]
+    with lzy.workflow(f"wf{uuid.uuid4().hex}"):
+        y = hop(hop(x))
+    assert torch.equal(y.to("cuda:0"), keep)
+    assert N.stats()["dma_copies"] - before >= 3  # at least one cross-GPU edge of ≥ 256 MiB: 3 sub-chunks each
+
+
 def test_diamond_mixed_payloads_across_gpus(lzy):
     """C5 at test size: source → branches (2 ops each) → sink; each edge carries a tensor and a dict."""
     @op
