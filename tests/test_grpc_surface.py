@@ -467,3 +467,105 @@ def test_unreachable_remote_peer_is_a_read_failure_and_the_backup_serves(stack):
     finally:
         peers.uninstall()
         H.blob_delete("mem://ghost/backup")
+
+
+def test_tasks_on_worker_processes_exchange_data_across_processes(tmp_path):
+    """The CPU rehearsal of tests/test_multiprocess_gpu.py: a channel manager process and two worker *processes*
+    (in-memory backend), driven only through WorkerApi.Execute / LongRunningService.Get.  Task `make` runs on worker
+    A; task `check` runs on worker B, pulls A's output across the process boundary (LzybPeerApi.Describe + the
+    backend's import) and verifies it inside the op body."""
+    import socket
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    from lzy_b200.api.v1.startup import ProcessingRequest
+    from lzy_b200.api.v1.utils.pickle import pickle
+    from lzy_b200.grpc_api import LongRunningClient, WorkerApiClient
+    from lzy_b200.grpc_api.protos import GetOperationRequest
+    root = Path(__file__).resolve().parent.parent
+    n = 300_000
+
+    def make() -> bytes:
+        return bytes(i % 251 for i in range(n))
+
+    def check(b: bytes) -> int:
+        assert b == bytes(i % 251 for i in range(n))
+        return len(b)
+
+    def free_port():
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            return s.getsockname()[1]
+
+    def execute(target, task_id, op, args_paths, outs, slots, assign):
+        wapi, ops = WorkerApiClient(target), LongRunningClient(target)
+        try:
+            request = ProcessingRequest({}, [], op, args_paths, {}, outs, (tuple, f"/{task_id}/exc"), lazy_arguments=False)
+            req = M.ExecuteRequest(task_id=task_id, execution_id="exec-wp", workflow_name="wf", user_id="u")
+            req.task_desc.operation.command = "python -u startup.py " + pickle(request)
+            for name, direction in slots:
+                req.task_desc.operation.slots.add(name=name, direction=direction)
+            for name, chan in assign.items():
+                req.task_desc.slot_assignments.add(slot_name=name, channel_id=chan)
+            op_msg = wapi.call("Execute", req)
+            deadline = time.time() + 60
+            while not op_msg.done:
+                assert time.time() < deadline
+                time.sleep(0.01)
+                op_msg = ops.call("Get", GetOperationRequest(operation_id=op_msg.id))
+            resp = M.ExecuteResponse()
+            assert op_msg.WhichOneof("result") == "response" and op_msg.response.Unpack(resp)
+            return resp
+        finally:
+            wapi.close()
+            ops.close()
+
+    procs = []
+    try:
+        cm = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "channel-manager", "--port", "0", "--seed", "6"],
+                              cwd=str(root), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        procs.append(cm)
+        cm_target = cm.stdout.readline().strip().rsplit(" ", 1)[-1]
+        targets = []
+        for _ in range(2):
+            port = free_port()
+            w = subprocess.Popen([sys.executable, str(root / "tests/support/remote_worker_api.py"), cm_target, str(port)],
+                                 cwd=str(root), stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            procs.append(w)
+            line = w.stdout.readline()
+            assert line.startswith("READY"), line + w.stderr.read()
+            targets.append(f"127.0.0.1:{port}")
+            init = WorkerApiClient(targets[-1])
+            init.call("Init", M.InitRequest(user_id="u", workflow_name="wf"))
+            init.close()
+        priv = ChannelManagerPrivateClient(cm_target)
+
+        def channel(name):
+            return priv.call("GetOrCreate", M.GetOrCreateRequest(execution_id="exec-wp", workflow_name="wf", user_id="u",
+                                                                 consumer=storage_peer(f"file://{tmp_path}/{name}"))).channel_id
+
+        data = channel("make.ret")
+        r = execute(targets[0], "make", make, [], [(bytes, "/make/ret")], [("/make/ret", 2), ("/make/exc", 2)],
+                    {"/make/ret": data, "/make/exc": channel("make.exc")})
+        assert (r.rc, r.description) == (0, "Success")
+        r = execute(targets[1], "check", check, [(bytes, "/check/arg")], [(int, "/check/ret")],
+                    [("/check/arg", 1), ("/check/ret", 2), ("/check/exc", 2)],
+                    {"/check/arg": data, "/check/ret": channel("check.ret"), "/check/exc": channel("check.exc")})
+        assert (r.rc, r.description) == (0, "Success")
+        assert (tmp_path / "check.ret").exists() and (tmp_path / "make.ret").stat().st_size >= n
+        priv.close()
+    finally:
+        for p in procs[1:]:
+            try:
+                p.stdin.write("bye\n")
+                p.stdin.flush()
+            except Exception:  # noqa: BLE001
+                pass
+        for p in procs[1:]:
+            try:
+                p.wait(timeout=20)
+            except subprocess.TimeoutExpired:
+                p.kill()
+        procs[0].terminate()
+        procs[0].wait(timeout=15)
