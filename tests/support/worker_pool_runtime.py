@@ -30,12 +30,64 @@ from tests.support import hostmem
 tbpickle.install()
 
 
+class BlobStorage:
+    """the C++ host blob store of this process (mem:// URIs)"""
+
+    def exists(self, uri: str) -> bool:
+        return H.blob_exists(uri)
+
+    def get(self, uri: str) -> bytes:
+        return H.blob_get(uri)
+
+    def put(self, uri: str, raw: bytes) -> None:
+        H.blob_put(uri, raw)
+
+    def delete(self, uri: str) -> None:
+        H.blob_delete(uri)
+
+
+class FileStorage:
+    """file:// URIs — what every process of the box can reach.  Objects written by a worker carry the 128-byte
+    frame header of the spill format; objects written by the client are plain byte streams."""
+
+    @staticmethod
+    def _path(uri: str) -> str:
+        assert uri.startswith("file://"), uri
+        return uri[7:]
+
+    def exists(self, uri: str) -> bool:
+        import os
+        return os.path.exists(self._path(uri))
+
+    def get(self, uri: str) -> bytes:
+        with open(self._path(uri), "rb") as f:
+            raw = f.read()
+        return raw[128:] if raw[:8] == b"LZYB200\0" else raw
+
+    def put(self, uri: str, raw: bytes) -> None:
+        import os
+        path = self._path(uri)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = f"{path}.tmp.{os.getpid()}"
+        with open(tmp, "wb") as f:
+            f.write(raw)
+        os.replace(tmp, path)
+
+    def delete(self, uri: str) -> None:
+        import os
+        try:
+            os.unlink(self._path(uri))
+        except FileNotFoundError:
+            pass
+
+
 class BlobSnapshot(Snapshot):
     """`DefaultSnapshot`'s rules (pylzy/lzy/api/v1/snapshot.py:93-191) over the C++ host blob store: the payload is
     the serializer's byte stream, the URI of local data is prefix + md5 of those bytes, equal data is stored once."""
 
-    def __init__(self, registry, prefix: str, storage_name: str = "mem"):
+    def __init__(self, registry, prefix: str, storage_name: str = "mem", storage=None):
         self.registry, self.prefix, self.storage_name = registry, prefix, storage_name
+        self.storage = storage or BlobStorage()
         self.entries: Dict[str, SnapshotEntry] = {}
         self.store_counts: Dict[str, int] = {}
 
@@ -61,8 +113,8 @@ class BlobSnapshot(Snapshot):
         raw = buf.getvalue()
         e.data_hash = hashlib.md5(raw).hexdigest()
         e.storage_uri = self.prefix + "/" + e.data_hash
-        if not H.blob_exists(e.storage_uri):
-            H.blob_put(e.storage_uri, raw)
+        if not self.storage.exists(e.storage_uri):
+            self.storage.put(e.storage_uri, raw)
             self.store_counts[e.storage_uri] = self.store_counts.get(e.storage_uri, 0) + 1
 
     async def get_data(self, entry_id: str):
@@ -73,13 +125,13 @@ class BlobSnapshot(Snapshot):
             uri = e.storage_uri
         except ValueError as err:
             return Absence(err)
-        if not H.blob_exists(uri):
+        if not self.storage.exists(uri):
             return Absence(ValueError(f"Cannot find blob in storage by uri={uri}"))
         ser = self.registry.find_serializer_by_type(e.typ)
-        return Result(ser.deserialize(BytesIO(H.blob_get(uri)), e.typ if isinstance(e.typ, type) else None))
+        return Result(ser.deserialize(BytesIO(self.storage.get(uri)), e.typ if isinstance(e.typ, type) else None))
 
     async def copy_data(self, from_entry_id: str, to_uri: str) -> None:
-        H.blob_put(to_uri, H.blob_get(self.entries[from_entry_id].storage_uri))
+        self.storage.put(to_uri, self.storage.get(self.entries[from_entry_id].storage_uri))
 
     def uris(self) -> List[str]:
         return [e._storage_uri for e in self.entries.values() if e._storage_uri]
@@ -94,6 +146,7 @@ class WorkerPoolRuntime(Runtime):
         self.n_workers, self.user_id, self.over_grpc = n_workers, user_id, over_grpc
         self._servers: List[Any] = []
         self._clients: Dict[int, Any] = {}
+        self.storage = BlobStorage()
         self.cm: Optional[H.ChannelManager] = None
         self.workers: List[Worker] = []
         self.workflow = None
@@ -148,6 +201,13 @@ class WorkerPoolRuntime(Runtime):
             w.close()
         self.workers = []
 
+    # ---- the private channel-manager API: a local matcher here, RPCs in the process-per-worker subclass ---------------
+    def _get_or_create(self, workflow_name: str, execution_id: str, **peer) -> str:
+        return self.cm.get_or_create(self.user_id, workflow_name, execution_id, **peer)
+
+    def _destroy_all(self, execution_id: str, reason: str) -> None:
+        self.cm.destroy_all(execution_id, reason)
+
     # ---- one task to one worker: direct calls, or the wire ------------------------------------------------------
     def _submit(self, index: int, task: TaskSpec) -> str:
         if not self.over_grpc:
@@ -193,7 +253,7 @@ class WorkerPoolRuntime(Runtime):
         self.cm = None
         for snap in self._snapshots:
             for uri in snap.uris():
-                H.blob_delete(uri)
+                self.storage.delete(uri)
         self._snapshots.clear()
         WorkerPoolRuntime._live -= 1
         if WorkerPoolRuntime._live == 0:
@@ -204,7 +264,7 @@ class WorkerPoolRuntime(Runtime):
         return None
 
     def snapshot(self, workflow, storage_uri_prefix: str) -> Snapshot:
-        snap = BlobSnapshot(workflow.owner.serializer_registry, storage_uri_prefix)
+        snap = BlobSnapshot(workflow.owner.serializer_registry, storage_uri_prefix, storage=self.storage)
         self._snapshots.append(snap)
         return snap
 
@@ -225,7 +285,7 @@ class WorkerPoolRuntime(Runtime):
         if self.cm is not None and self.execution_id:
             for w in self.workers:
                 w.release_execution(self.execution_id)
-            self.cm.destroy_all(self.execution_id, reason)
+            self._destroy_all(self.execution_id, reason)
             self.execution_id = None
 
     async def exec(self, calls, progress: Callable[[ProgressStep], None]) -> None:
@@ -249,7 +309,7 @@ class WorkerPoolRuntime(Runtime):
         # ops whose outputs are all already supplied are dropped (lzy-service DataFlowGraph.java:51-72)
         todo = []
         for c in calls:
-            if c.cache and c.entry_ids and all(H.blob_exists(snap.get(e).storage_uri) for e in c.entry_ids):
+            if c.cache and c.entry_ids and all(self.storage.exists(snap.get(e).storage_uri) for e in c.entry_ids):
                 self.skipped_cached += 1
                 continue
             todo.append(c)
@@ -261,7 +321,7 @@ class WorkerPoolRuntime(Runtime):
         channel: Dict[str, str] = {}
         for c in todo:
             for eid in list(c.entry_ids) + [c.exception_id]:
-                channel[eid] = cm.get_or_create(self.user_id, wf.name, exec_id, consumer_uri=snap.get(eid).storage_uri)
+                channel[eid] = self._get_or_create(wf.name, exec_id, consumer_uri=snap.get(eid).storage_uri)
         tasks: List[TaskSpec] = []
         edges = set()
         for i, c in enumerate(todo):
@@ -271,9 +331,9 @@ class WorkerPoolRuntime(Runtime):
             def input_slot(eid):
                 if eid not in channel:
                     uri = snap.get(eid).storage_uri
-                    if not H.blob_exists(uri):
+                    if not self.storage.exists(uri):
                         raise ValueError(f"Cannot find blob in storage by uri={uri}")
-                    channel[eid] = cm.get_or_create(self.user_id, wf.name, exec_id, producer_uri=uri)
+                    channel[eid] = self._get_or_create(wf.name, exec_id, producer_uri=uri)
                 if eid in producer_of and producer_of[eid] != i:
                     edges.add((producer_of[eid], i))
                 path = f"/{c.id}/{eid}"
@@ -340,12 +400,113 @@ class WorkerPoolRuntime(Runtime):
         if call is not None:
             uri = snap.get(call.exception_id).storage_uri
             deadline = time.time() + 10
-            while not H.blob_exists(uri) and time.time() < deadline:  # the exception slot uploads asynchronously
+            while not self.storage.exists(uri) and time.time() < deadline:  # the exception slot uploads asynchronously
                 time.sleep(0.005)
-            if H.blob_exists(uri):
+            if self.storage.exists(uri):
                 ser = snap.registry.find_serializer_by_type(tuple)
-                info = ser.deserialize(BytesIO(H.blob_get(uri)), tuple)
+                info = ser.deserialize(BytesIO(self.storage.get(uri)), tuple)
                 if info is not None:
                     raise info[1].with_traceback(info[2])
         _, description, _ = graph.error()
         raise LzyExecutionException(f"Failed executing graph: {description}")
+
+
+class ProcessPoolRuntime(WorkerPoolRuntime):
+    """The same runtime with every part in its own process, as the reference deploys it: a channel-manager service
+    (`python -m lzy_b200.grpc_api channel-manager`), N worker processes (tests/support/remote_worker_api.py: WorkerApi +
+    LzySlotsApi + LzybPeerApi, in-memory backend with its shared-memory export), this process as the client that
+    builds tasks and polls operations.  Data lives under file:// URIs so that every process reaches it: the client
+    writes arguments there, workers upload results there and pull each other's outputs slot to slot."""
+
+    def __init__(self, root_dir: str, n_workers: int = 2, user_id: str = "test-user"):
+        super().__init__(n_workers=n_workers, user_id=user_id, over_grpc=True)
+        self.storage = FileStorage()
+        self.root_dir = root_dir
+        self._cm_proc = None
+        self._worker_procs: List[Any] = []
+        self._priv = None
+
+    def _ensure(self) -> None:
+        if self._cm_proc is not None:
+            return
+        import subprocess
+        import sys
+        from pathlib import Path
+
+        from lzy_b200.grpc_api import ChannelManagerPrivateClient
+        self._repo = Path(__file__).resolve().parent.parent.parent
+        self._cm_proc = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "channel-manager", "--port", "0", "--seed", "1"],
+                                         cwd=str(self._repo), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self._cm_target = self._cm_proc.stdout.readline().strip().rsplit(" ", 1)[-1]
+        self._priv = ChannelManagerPrivateClient(self._cm_target)
+        self.cm = self._priv  # (only its presence is checked by the base class)
+
+    def _allocate(self, workflow_name: str) -> None:
+        if self._worker_procs and self._owner == (self.user_id, workflow_name):
+            return
+        import socket
+        import subprocess
+        import sys
+
+        from lzy_b200.grpc_api import LongRunningClient, WorkerApiClient, messages
+        self._release_workers()
+        self._owner = (self.user_id, workflow_name)
+        for i in range(self.n_workers):
+            with socket.socket() as sock:
+                sock.bind(("127.0.0.1", 0))
+                port = sock.getsockname()[1]
+            proc = subprocess.Popen([sys.executable, str(self._repo / "tests/support/remote_worker_api.py"), self._cm_target, str(port)],
+                                    cwd=str(self._repo), stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            assert proc.stdout.readline().startswith("READY")
+            self._worker_procs.append(proc)
+            self._clients[i] = (WorkerApiClient(f"127.0.0.1:{port}"), LongRunningClient(f"127.0.0.1:{port}"))
+            self._clients[i][0].call("Init", messages.InitRequest(user_id=self.user_id, workflow_name=workflow_name))
+        self.workers = list(range(self.n_workers))  # placeholders: the base class only counts them
+
+    def _release_workers(self) -> None:
+        for wapi, ops in self._clients.values():
+            wapi.close()
+            ops.close()
+        self._clients.clear()
+        for proc in self._worker_procs:
+            try:
+                proc.stdin.write("bye\n")
+                proc.stdin.flush()
+            except Exception:  # noqa: BLE001
+                pass
+        for proc in self._worker_procs:
+            try:
+                proc.wait(timeout=20)
+            except Exception:  # noqa: BLE001
+                proc.kill()
+        self._worker_procs = []
+        self.workers = []
+
+    def _get_or_create(self, workflow_name: str, execution_id: str, producer_uri=None, consumer_uri=None) -> str:
+        from lzy_b200.grpc_api import messages
+        req = messages.GetOrCreateRequest(execution_id=execution_id, workflow_name=workflow_name, user_id=self.user_id)
+        if producer_uri is not None:
+            req.producer.storage_uri = producer_uri
+        else:
+            req.consumer.storage_uri = consumer_uri
+        return self._priv.call("GetOrCreate", req).channel_id
+
+    def _destroy_all(self, execution_id: str, reason: str) -> None:
+        from lzy_b200.grpc_api import messages
+        self._priv.call("DestroyAll", messages.DestroyAllRequest(execution_id=execution_id, reason=reason))
+
+    def _finish(self, reason: str) -> None:
+        if self._priv is not None and self.execution_id:
+            self._destroy_all(self.execution_id, reason)
+            self.execution_id = None
+
+    def close(self) -> None:
+        if self._cm_proc is None:
+            return
+        self._release_workers()
+        self._priv.close()
+        self._cm_proc.terminate()
+        self._cm_proc.wait(timeout=15)
+        self._cm_proc, self.cm = None, None
+        import shutil
+        shutil.rmtree(self.root_dir, ignore_errors=True)

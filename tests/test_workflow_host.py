@@ -442,3 +442,57 @@ def test_workflows_driven_through_worker_api_on_the_wire(lzy_over_grpc, workflow
         with lzy.workflow(workflow_name + "_f"):
             materialize(inc(fail(1)))
     assert lzy.runtime.executed.count("inc") == 3  # the consumer of the failed op never started
+
+
+# ---- and with every part in its own process ------------------------------------------------------------------------------
+@op
+def _mp_double(x: int) -> int:
+    return x * 2
+
+
+@op
+def _mp_join(a: str, b: str) -> str:
+    return a + "|" + b
+
+
+@op
+def _mp_tag(t: str, suffix: str) -> str:
+    return t + suffix
+
+
+@op
+def _mp_fail(x: int) -> int:
+    raise LookupError(f"no {x}")
+
+
+def test_workflows_on_a_channel_manager_process_and_worker_processes(tmp_path, workflow_name):
+    """A channel-manager process, two worker processes, this process as the client: arguments and results under
+    file:// URIs, consecutive tasks on different workers exchange data across the process boundary, an op's own
+    exception comes back with its type, `cache=True` results are found again by a second workflow."""
+    from lzy_b200.types import File
+    from tests.support.worker_pool_runtime import ProcessPoolRuntime
+
+    @op(cache=True, version="1")
+    def cached_len(f: File) -> int:
+        with f.open("rb") as fh:
+            return len(fh.read())
+
+    rt = ProcessPoolRuntime(str(tmp_path / "store"), n_workers=2)
+    try:
+        lzy = Lzy(runtime=rt, storage_uri=f"file://{tmp_path}/store")
+        with lzy.workflow(workflow_name):
+            y = _mp_double(_mp_double(_mp_double(5)))          # three hops, alternating workers
+            s = _mp_tag("s", "0")
+            d = _mp_join(_mp_tag(s, "1"), _mp_tag(s, "2"))     # a diamond
+            assert materialize(y) == 40 and materialize(d) == "s01|s02"
+        with pytest.raises(LookupError, match="no 7"):
+            with lzy.workflow(workflow_name):
+                materialize(_mp_double(_mp_fail(7)))
+        src = tmp_path / "payload.bin"
+        src.write_bytes(b"x" * 12345)
+        for _ in range(2):
+            with lzy.workflow(workflow_name):
+                assert materialize(cached_len(File(str(src)))) == 12345
+        assert rt.executed.count("cached_len") == 1 and rt.skipped_cached == 1
+    finally:
+        rt.close()
