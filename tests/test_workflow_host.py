@@ -496,3 +496,23 @@ def test_workflows_on_a_channel_manager_process_and_worker_processes(tmp_path, w
         assert rt.executed.count("cached_len") == 1 and rt.skipped_cached == 1
     finally:
         rt.close()
+
+
+def test_arrays_travel_as_frame_streams_when_there_is_no_hbm(lzy, workflow_name):
+    """ndarray / CPU tensor arguments and results through the serializers' byte-stream form (header + C-order bytes,
+    the same layout a frame has in HBM): dtype, shape and bytes survive, non-contiguous inputs arrive contiguous"""
+    import numpy as np
+    import torch
+
+    @op
+    def scale(a: np.ndarray, t: torch.Tensor) -> (np.ndarray, torch.Tensor):
+        assert a.flags["C_CONTIGUOUS"] and t.is_contiguous() and not t.is_cuda
+        return a * 2, t + 1
+
+    a = np.arange(3 * 5 * 7, dtype=np.int64).reshape(3, 5, 7)[:, ::2, :]      # a strided view
+    t = torch.arange(24, dtype=torch.float32).reshape(4, 6).t()                # a transposed view
+    with lzy.workflow(workflow_name):
+        ra, rt = scale(a, t)
+        ra, rt = materialize(ra), materialize(rt)
+    assert ra.dtype == np.int64 and ra.shape == (3, 3, 7) and np.array_equal(ra, a * 2)
+    assert rt.dtype == torch.float32 and tuple(rt.shape) == (6, 4) and torch.equal(rt, t + 1)
