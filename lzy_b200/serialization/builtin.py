@@ -232,7 +232,7 @@ class NdarrayFrameSerializer(DeviceFrameSerializer):
         return out
 
     def _serialize(self, obj, dest: BinaryIO) -> None:
-        a = np.ascontiguousarray(obj)
+        a = np.require(obj, requirements="C")  # not ascontiguousarray: that turns a 0-d array into shape (1,)
         code, shape, nbytes = self._plan(a)
         dest.write(_header_bytes(code, shape, nbytes, FLAG_HOST_ORIGIN | FLAG_NDARRAY))
         dest.write(a.tobytes() if a.nbytes < (1 << 20) else memoryview(a).cast("B"))

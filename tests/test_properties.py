@@ -119,3 +119,32 @@ def test_copy_engine_plan_always_tiles_its_chunk(nbytes):
     assert sum(sizes) == nbytes and 1 <= len(sizes) <= 8
     assert all(s % 16 == 0 for s in sizes[:-1])
     assert nbytes < (8 << 20) or sizes[-1] <= (32 << 20) + 15  # a short tail scan
+
+
+_DTYPES = ["uint8", "int8", "int16", "int32", "int64", "float16", "float32", "float64", "bool"]
+
+
+@settings(max_examples=80, deadline=None)
+@given(st.sampled_from(_DTYPES), st.lists(st.integers(min_value=0, max_value=7), min_size=0, max_size=4), st.integers(0, 2 ** 31))
+def test_array_stream_form_round_trips_dtype_shape_and_bytes(dtype, shape, seed):
+    """the byte-stream form of the frame serializers (what storage holds when a payload is not in HBM): header +
+    C-order bytes, for ndarray and for CPU torch tensors"""
+    import torch
+    reg = LzySerializerRegistry()
+    rng = np.random.default_rng(seed)
+    a = (rng.integers(0, 2, shape).astype(bool) if dtype == "bool" else
+         rng.integers(-100, 100, shape).astype(dtype) if "int" in dtype else rng.standard_normal(shape).astype(dtype))
+    ser = reg.find_serializer_by_type(np.ndarray)
+    buf = BytesIO()
+    ser.serialize(a, buf)
+    buf.seek(0)
+    back = ser.deserialize(buf, np.ndarray)
+    assert back.dtype == a.dtype and back.shape == a.shape and back.tobytes() == a.tobytes()
+
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    tser = reg.find_serializer_by_type(torch.Tensor)
+    buf = BytesIO()
+    tser.serialize(t, buf)
+    buf.seek(0)
+    tback = tser.deserialize(buf, torch.Tensor)
+    assert tback.dtype == t.dtype and tuple(tback.shape) == tuple(t.shape) and torch.equal(tback, t)
