@@ -34,6 +34,7 @@ from typing import TYPE_CHECKING, Any, Callable, Dict, List, Optional, Sequence,
 from .... import _host as H
 from .... import _native as N
 from ....devmem import current_stream_ptr
+from ....core.dataflow import plan_dataflow
 from ....env import applied_env
 from ....proxy import proxy
 from ....serialization.types import get_type
@@ -282,25 +283,19 @@ class B200Runtime(Runtime):
         exec_id, user = self._execution_id or "exec", self.config.user_id
         self.stats["graphs"] += 1
 
-        # ops whose outputs are all already supplied are dropped (lzy-service DataFlowGraph.java:51-72)
-        todo: List["LzyCall"] = []
-        for c in calls:
-            if c.cache and c.entry_ids and all(self.store.exists(snapshot.get(e).storage_uri) for e in c.entry_ids):
-                self.stats["cached_ops"] += 1
-                continue
-            todo.append(c)
-        todo_ids = {id(c) for c in todo}  # identity, never ==: comparing calls would compare (and materialise) proxies
-        for c in calls:
-            if id(c) not in todo_ids and hasattr(snapshot, "unpin"):  # a skipped (cached) call releases its inputs too
+        # ops whose outputs are all already supplied — in storage, or by an earlier op of this graph — are dropped
+        # (lzy-service DataFlowGraph.java:51-72); the graph is keyed by data URI
+        plan = plan_dataflow(calls, lambda eid: snapshot.get(eid).storage_uri, self.store.exists)
+        self.stats["cached_ops"] += len(plan.cached)
+        self.stats["duplicate_ops"] = self.stats.get("duplicate_ops", 0) + len(plan.duplicates)
+        if hasattr(snapshot, "unpin"):
+            for c in plan.dropped:  # a dropped call releases its inputs too
                 for eid in list(c.arg_entry_ids) + list(c.kwarg_entry_ids.values()):
                     snapshot.unpin(eid)
-        if not todo:
+        if not plan.calls:
             return
-        calls = todo
-        producers: Dict[str, int] = {}
-        for i, c in enumerate(calls):
-            for eid in c.entry_ids:
-                producers[eid] = i
+        calls = plan.calls
+        producers: Dict[str, int] = plan.supplier  # result entry -> the op that supplies its URI
         inputs_of: List[List[str]] = []
         edges: List[Tuple[int, int]] = []
         for i, c in enumerate(calls):
@@ -314,6 +309,9 @@ class B200Runtime(Runtime):
         channel_of: Dict[str, str] = {}
         for i, c in enumerate(calls):
             for eid in c.entry_ids:
+                channel_of[eid] = self.cm.get_or_create(user, wf.name, exec_id, consumer_uri=snapshot.get(eid).storage_uri)
+        for eid in producers:  # results of dropped duplicates share their supplier's URI, hence its channel
+            if eid not in channel_of:
                 channel_of[eid] = self.cm.get_or_create(user, wf.name, exec_id, consumer_uri=snapshot.get(eid).storage_uri)
         for i, ins in enumerate(inputs_of):
             for eid in ins:
@@ -373,7 +371,7 @@ class B200Runtime(Runtime):
                     err = fut.exception()
                     if err is None:
                         graph.task_done(t, True)
-                        for eid in calls[t].entry_ids:  # its outputs are bound: start their fan-out
+                        for eid in plan.outputs_of(t):  # its outputs are bound: start their fan-out
                             f = fanout.get(eid)
                             if f is not None and not f.started:
                                 f.started = True

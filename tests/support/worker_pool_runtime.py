@@ -22,6 +22,7 @@ from lzy_b200.api.v1.runtime import ProgressStep, Runtime
 from lzy_b200.api.v1.snapshot import Snapshot, SnapshotEntry
 from lzy_b200.api.v1.startup import ProcessingRequest
 from lzy_b200.api.v1.utils.pickle import pickle
+from lzy_b200.core.dataflow import plan_dataflow
 from lzy_b200.proxy_result import Absence, Result
 from lzy_b200.utils import tbpickle
 from lzy_b200.worker import DIR_INPUT, DIR_OUTPUT, SlotSpec, TaskSpec, Worker
@@ -154,6 +155,7 @@ class WorkerPoolRuntime(Runtime):
         self.calls: List[Any] = []          # every call ever handed to exec (what RuntimeMock records)
         self.executed: List[str] = []       # callable names in the order tasks were released
         self.skipped_cached = 0
+        self.dropped_duplicates = 0
         self._snapshots: List[BlobSnapshot] = []
         self._rr = 0
         self._owner = None
@@ -307,20 +309,21 @@ class WorkerPoolRuntime(Runtime):
         exec_id = self.execution_id
 
         # ops whose outputs are all already supplied are dropped (lzy-service DataFlowGraph.java:51-72)
-        todo = []
-        for c in calls:
-            if c.cache and c.entry_ids and all(self.storage.exists(snap.get(e).storage_uri) for e in c.entry_ids):
-                self.skipped_cached += 1
-                continue
-            todo.append(c)
+        plan = plan_dataflow(calls, lambda eid: snap.get(eid).storage_uri, self.storage.exists)
+        self.skipped_cached += len(plan.cached)
+        self.dropped_duplicates += len(plan.duplicates)
+        todo = plan.calls
         if not todo:
             return
-        producer_of = {eid: i for i, c in enumerate(todo) for eid in c.entry_ids}
+        producer_of = plan.supplier
 
         # CreateChannels: one channel per data URI; results get a storage consumer, existing data a storage producer
         channel: Dict[str, str] = {}
         for c in todo:
             for eid in list(c.entry_ids) + [c.exception_id]:
+                channel[eid] = self._get_or_create(wf.name, exec_id, consumer_uri=snap.get(eid).storage_uri)
+        for eid in plan.supplier:  # results of dropped duplicates: the channel of the URI they share with their supplier
+            if eid not in channel:
                 channel[eid] = self._get_or_create(wf.name, exec_id, consumer_uri=snap.get(eid).storage_uri)
         tasks: List[TaskSpec] = []
         edges = set()

@@ -393,3 +393,32 @@ def test_workflow_declarations_are_frozen_once_it_is_in_use(lzy):
     with wf:
         with pytest.raises(RuntimeError, match="forbidden to change LzyWorkflow fields"):
             wf.with_env_vars(C="3")
+
+
+def test_dataflow_plan_is_keyed_by_uri():
+    """lzy-service DataFlowGraph.java:51-72: one supplier per output URI; an op whose outputs are all supplied is
+    dropped (its results point at the supplier); a partial overlap is an error; cached results are not resubmitted."""
+    from types import SimpleNamespace
+    from lzy_b200.core.dataflow import plan_dataflow
+
+    uri = {"a0": "s/f/h1/return_0", "b0": "s/f/h1/return_0", "c0": "s/g/1/return_0", "d0": "s/f/h2/return_0",
+           "e0": "s/p/h/return_0", "e1": "s/p/h/return_1", "f0": "s/p/h/return_0", "f1": "s/p/h/return_1",
+           "g0": "s/old/return_0"}
+
+    def call(cache, *eids):
+        return SimpleNamespace(cache=cache, entry_ids=list(eids))
+
+    a, b, c, d = call(True, "a0"), call(True, "b0"), call(False, "c0"), call(True, "d0")
+    e, f, g, none = call(True, "e0", "e1"), call(True, "f0", "f1"), call(True, "g0"), call(False)
+    plan = plan_dataflow([a, b, c, d, e, g, f, none, none], uri.__getitem__, {"s/old/return_0"}.__contains__)
+    assert plan.calls == [a, c, d, e, none, none] and plan.duplicates == [b, f] and plan.cached == [g]
+    assert plan.supplier == {"a0": 0, "b0": 0, "c0": 1, "d0": 2, "e0": 3, "e1": 3, "f0": 3, "f1": 3}
+    assert plan.outputs_of(0) == ["a0", "b0"] and plan.outputs_of(3) == ["e0", "e1", "f0", "f1"] and plan.outputs_of(1) == ["c0"]
+    assert plan.dropped == [g, b, f]
+
+    # an op with results but cache=False whose URI is in storage still runs (only cache=True consults storage)
+    assert plan_dataflow([call(False, "g0")], uri.__getitem__, lambda u: True).calls != []
+    # supplying one of two URIs that are already supplied is refused
+    uri["h0"], uri["h1"] = "s/p/h/return_0", "s/other/return_1"
+    with pytest.raises(RuntimeError, match="Output slot with uri 's/p/h/return_0' already exists"):
+        plan_dataflow([e, call(True, "h0", "h1")], uri.__getitem__, lambda u: False)

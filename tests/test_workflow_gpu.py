@@ -391,6 +391,29 @@ def test_cached_op_runs_once(lzy, workflow_name):
     assert counter["n"] == 1 and lzy.runtime.stats["cached_ops"] >= 1
 
 
+def test_identical_cached_calls_in_one_graph_run_once(lzy, workflow_name):
+    """lzy-service DataFlowGraph.java:51-72: the graph is keyed by data URI — the second of two equal cache=True calls
+    of one barrier is dropped and its consumers read the first one's result"""
+    counter = {"n": 0}
+
+    @op(cache=True, version="1")
+    def produce(name: str) -> str:
+        counter["n"] += 1
+        return f"My name is {name}"
+
+    @op
+    def greet(message: str, who: str) -> str:
+        return f"{who}: {message}"
+
+    before = lzy.runtime.stats.get("duplicate_ops", 0)
+    with lzy.workflow(workflow_name) as wf:
+        first, second = produce("Graceful"), produce("Graceful")
+        a, b = greet(first, "a"), greet(second, "b")
+        wf.barrier()
+        assert (a, b) == ("a: My name is Graceful", "b: My name is Graceful") and first == second
+    assert counter["n"] == 1 and lzy.runtime.stats["duplicate_ops"] == before + 1
+
+
 # ---- HBM-resident payloads ---------------------------------------------------------------------------
 
 def test_cuda_tensor_chain_stays_on_device_and_is_bit_exact(lzy, workflow_name):

@@ -516,3 +516,26 @@ def test_arrays_travel_as_frame_streams_when_there_is_no_hbm(lzy, workflow_name)
         ra, rt = materialize(ra), materialize(rt)
     assert ra.dtype == np.int64 and ra.shape == (3, 3, 7) and np.array_equal(ra, a * 2)
     assert rt.dtype == torch.float32 and tuple(rt.shape) == (6, 4) and torch.equal(rt, t + 1)
+
+
+def test_identical_cached_calls_in_one_graph_run_once(lzy, workflow_name, capsys):
+    """DataFlowGraph.java:51-72: a graph is keyed by data URI — the second of two equal cache=True calls submitted in
+    one barrier is dropped, its consumers are wired to the first one's result."""
+    @op(cache=True, version="1.0")
+    def message_producer(name: str) -> str:
+        print("message producer was called")
+        return f"My name is {name}"
+
+    @op(cache=False)
+    def bar(message: str, name: str) -> str:
+        return f"message from '{name}' bar: {message}"
+
+    before = lzy.runtime.dropped_duplicates
+    with lzy.workflow(workflow_name, interactive=False) as wf:
+        first, second = message_producer("Graceful"), message_producer("Graceful")
+        a, b = bar(first, "a"), bar(second, "b")
+        wf.barrier()
+        assert a == "message from 'a' bar: My name is Graceful" and b == "message from 'b' bar: My name is Graceful"
+        assert second == "My name is Graceful" and first == second
+    assert capsys.readouterr().out.count("message producer was called") == 1
+    assert lzy.runtime.dropped_duplicates == before + 1
