@@ -401,8 +401,8 @@ class B200Runtime(Runtime):
                 ctx.close()
             graph.close()
             if hasattr(snapshot, "unpin"):
-                for c in calls:
-                    for eid in c.entry_ids:
+                for i in range(len(calls)):
+                    for eid in plan.outputs_of(i):  # dropped duplicates hold the shared frame in their own right
                         snapshot.produced(eid)
                 for c in calls:
                     for eid in list(c.arg_entry_ids) + list(c.kwarg_entry_ids.values()):
