@@ -2,7 +2,7 @@
 identity; ``workflow(name, eager=..., interactive=...)`` opens a workflow."""
 from __future__ import annotations
 
-import inspect
+import sys
 from dataclasses import dataclass, field, replace
 from typing import Any, ClassVar, Optional, Type
 
@@ -33,7 +33,7 @@ class Lzy(WithEnvironmentMixin):
 
     def workflow(self, name: str, *, eager: bool = False, interactive: bool = True,
                  env: Optional[LzyEnvironment] = None) -> LzyWorkflow:
-        frame = inspect.stack()[1].frame
+        frame = sys._getframe(1)  # the caller's frame; inspect.stack() would also read source lines of every frame
         namespace = {**frame.f_globals, **frame.f_locals}
         env = env or LzyEnvironment()
         env = env.with_fields(namespace={**namespace, **env.get_namespace()})
