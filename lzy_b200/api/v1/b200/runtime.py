@@ -137,8 +137,9 @@ class _OpFailed(Exception):
 class B200Runtime(Runtime):
     def __init__(self, config: Optional[B200RuntimeConfig] = None, **kwargs):
         self.config = config or B200RuntimeConfig.from_env(**kwargs)
-        self._workflow: Optional["LzyWorkflow"] = None
-        self._execution_id: Optional[str] = None
+        # started workflows, innermost last: an op body may open a workflow of its own on this very runtime while
+        # its caller's graph is still running (the reference gives it a process of its own)
+        self._active: List[Tuple["LzyWorkflow", str]] = []
         self._lock = threading.RLock()
         self._ready = False
         self.gpus: List[int] = []
@@ -197,21 +198,39 @@ class B200Runtime(Runtime):
 
     async def start(self, workflow: "LzyWorkflow") -> str:
         self._ensure_ready()
-        self._workflow = workflow
-        self._execution_id = str(uuid.uuid4())
-        return self._execution_id
+        execution_id = str(uuid.uuid4())
+        with self._lock:
+            self._active.append((workflow, execution_id))
+        return execution_id
+
+    def _stop(self, reason: str) -> None:
+        """abort() / finish() of the innermost started workflow; nothing to do when none was started
+        (pylzy/lzy/api/v1/remote/runtime.py:204-243: `if not self.__running: return`, state reset afterwards)"""
+        with self._lock:
+            if not self._active:
+                return
+            _workflow, execution_id = self._active.pop()
+        if self.cm is not None:
+            self.cm.destroy_all(execution_id, reason)  # LzyChannelManagerPrivate.DestroyAll
 
     async def abort(self) -> None:
-        if self.cm is not None and self._execution_id:
-            self.cm.destroy_all(self._execution_id, "aborted")
+        self._stop("aborted")
 
     async def finish(self) -> None:
-        if self.cm is not None and self._execution_id:
-            self.cm.destroy_all(self._execution_id, "finished")  # LzyChannelManagerPrivate.DestroyAll
+        self._stop("finished")
+
+    def _execution_of(self, workflow: "LzyWorkflow") -> str:
+        with self._lock:
+            for wf, execution_id in reversed(self._active):
+                if wf is workflow:
+                    return execution_id
+        raise ValueError("Runtime is not running")  # remote/runtime.py:146-147
 
     async def exec(self, calls: List["LzyCall"], progress: Callable[[ProgressStep], None]) -> None:
         import asyncio
-        assert self._workflow is not None
+        with self._lock:
+            if not self._active:
+                raise ValueError("Runtime is not running")
         progress(ProgressStep.EXECUTING)
         loop = asyncio.get_running_loop()
         try:
@@ -277,10 +296,12 @@ class B200Runtime(Runtime):
         return placement
 
     def _exec_graph(self, calls: List["LzyCall"]) -> None:
-        wf = self._workflow
-        assert wf is not None and self.store is not None and self.cm is not None
+        if not calls:
+            return
+        wf = calls[0].workflow  # the graph's own workflow: not necessarily the innermost one that is active
+        assert self.store is not None and self.cm is not None
         snapshot = wf.snapshot
-        exec_id, user = self._execution_id or "exec", self.config.user_id
+        exec_id, user = self._execution_of(wf), self.config.user_id
         self.stats["graphs"] += 1
 
         # ops whose outputs are all already supplied — in storage, or by an earlier op of this graph — are dropped
@@ -441,8 +462,8 @@ class B200Runtime(Runtime):
     def _run_task(self, t: int, call: "LzyCall", ctx: H.ExecutionContext, gpu: int, input_eids: List[str],
                   fanout: Optional[Dict[str, _Fanout]] = None) -> None:
         import torch
-        wf = self._workflow
-        assert wf is not None and self.store is not None
+        wf = call.workflow
+        assert self.store is not None
         snapshot, registry = wf.snapshot, wf.owner.serializer_registry
         exc_uri = snapshot.get(call.exception_id).storage_uri
         mark = self._phase_marker(t)

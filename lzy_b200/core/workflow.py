@@ -147,11 +147,15 @@ class LzyWorkflow(WithEnvironmentMixin):
             self.set_active(workflow)
 
     def __abort(self):
+        if not self.__started:
+            # nothing of this workflow is running: the runtime is left alone (pylzy/tests/api/v1/test_remote_runtime.py
+            # :65-76, "should NOT be aborted if not started") — in particular a refused second workflow does not
+            # take down the one that is active
+            return
         try:
             LzyEventLoop.run_async(self.owner.runtime.abort())
         finally:
-            if self.__started:
-                self.__activate(None)
+            self.__activate(None)
             self.__started = False
 
     def __destroy(self):

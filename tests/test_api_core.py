@@ -234,6 +234,29 @@ def test_only_one_active_workflow(lzy):
         pass
 
 
+def test_a_refused_second_workflow_leaves_the_active_one_running(lzy):
+    with lzy.workflow(wf_name()):
+        with pytest.raises(RuntimeError, match="Simultaneous workflows are not supported"):
+            with lzy.workflow(wf_name()):
+                pass
+        assert lzy.runtime.aborted == 0  # the refused workflow started nothing, so it had nothing to abort
+        assert foo("a", 1) == "a: 1"    # and the first one still runs ops
+    assert lzy.runtime.aborted == 0 and lzy.runtime.finished == 1
+
+
+def test_error_on_start_is_not_an_abort(lzy, monkeypatch):
+    """pylzy/tests/api/v1/test_remote_runtime.py:65-76: the body is not entered, nothing is aborted"""
+    async def refuse(workflow):
+        raise ConnectionError("cannot start")
+
+    monkeypatch.setattr(lzy.runtime, "start", refuse)
+    entered = False
+    with pytest.raises(ConnectionError):
+        with lzy.workflow(wf_name()):
+            entered = True
+    assert not entered and lzy.runtime.aborted == 0 and LzyWorkflow.get_active() is None
+
+
 def test_invalid_workflow_name(lzy):
     with pytest.raises(ValueError, match="Invalid workflow name"):
         lzy.workflow("bad name!")
@@ -422,3 +445,39 @@ def test_dataflow_plan_is_keyed_by_uri():
     uri["h0"], uri["h1"] = "s/p/h/return_0", "s/other/return_1"
     with pytest.raises(RuntimeError, match="Output slot with uri 's/p/h/return_0' already exists"):
         plan_dataflow([e, call(True, "h0", "h1")], uri.__getitem__, lambda u: False)
+
+
+def test_hbm_runtime_lifecycle_without_a_device(monkeypatch):
+    """pylzy/lzy/api/v1/remote/runtime.py:141-147,204-243 (and tests/api/v1/test_remote_runtime.py:65-76): exec on a
+    runtime that is not running is refused, abort / finish of a runtime that never started do nothing, each workflow
+    has its own execution — also when an op opens a nested one on the same runtime."""
+    import asyncio
+    from types import SimpleNamespace
+    from lzy_b200.api.v1.b200.runtime import B200Runtime
+
+    rt = B200Runtime()
+    monkeypatch.setattr(rt, "_ensure_ready", lambda: None)
+    destroyed = []
+    rt.cm = SimpleNamespace(destroy_all=lambda execution_id, reason: destroyed.append((execution_id, reason)))
+    run = asyncio.run
+
+    run(rt.abort())
+    run(rt.finish())
+    assert destroyed == []
+    with pytest.raises(ValueError, match="Runtime is not running"):
+        run(rt.exec([], lambda step: None))
+
+    outer, inner = SimpleNamespace(name="outer"), SimpleNamespace(name="inner")
+    outer_id = run(rt.start(outer))
+    inner_id = run(rt.start(inner))
+    assert outer_id != inner_id and rt._execution_of(outer) == outer_id and rt._execution_of(inner) == inner_id
+    run(rt.finish())
+    assert destroyed == [(inner_id, "finished")] and rt._execution_of(outer) == outer_id
+    with pytest.raises(ValueError, match="Runtime is not running"):
+        rt._execution_of(inner)
+    run(rt.abort())
+    assert destroyed == [(inner_id, "finished"), (outer_id, "aborted")]
+    run(rt.abort())  # a second abort finds nothing to do
+    assert len(destroyed) == 2
+    with pytest.raises(ValueError, match="Runtime is not running"):
+        run(rt.exec([], lambda step: None))
