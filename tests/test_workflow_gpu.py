@@ -3,6 +3,7 @@
 runtime), the call-time snapshot tests of pylzy/tests/api/v1/test_entries.py:453-550, the exception
 contract of pylzy/tests/api/v1/test_startup.py:52-83, plus tensor / ndarray payloads that stay in HBM."""
 import importlib
+import os
 import traceback
 import uuid
 from typing import Dict, List, Optional, Tuple, Union
@@ -412,6 +413,26 @@ def test_identical_cached_calls_in_one_graph_run_once(lzy, workflow_name):
         wf.barrier()
         assert (a, b) == ("a: My name is Graceful", "b: My name is Graceful") and first == second
     assert counter["n"] == 1 and lzy.runtime.stats["duplicate_ops"] == before + 1
+
+
+@pytest.mark.skipif(not os.environ.get("LZYB_UNVALIDATED"), reason="written after this round's GPU minutes were "
+                    "spent; tools/validate_gpu.sh runs it first thing next round (LZYB_UNVALIDATED=1)")
+def test_nested_workflow_on_the_same_runtime(lzy, workflow_name):
+    """nested_workflows scenario with one runtime for both levels: the op's own workflow gets its own execution,
+    the caller's graph goes on afterwards"""
+    @op
+    def double(x: int) -> int:
+        return 2 * x
+
+    @op
+    def outer(x: int) -> int:
+        with lzy.workflow(workflow_name + "_inner"):
+            return int(materialize(double(x))) + 1
+
+    with lzy.workflow(workflow_name):
+        first = outer(20)
+        second = double(first)
+        assert (first, second) == (41, 82)
 
 
 # ---- HBM-resident payloads ---------------------------------------------------------------------------
