@@ -1,8 +1,15 @@
-"""Type helpers for @op signatures (pylzy/lzy/api/v1/utils/types.py:23-79)."""
+"""What the ``@op`` machinery needs to know about annotations — the same questions pylzy asks in
+pylzy/lzy/api/v1/utils/types.py:23-79, answered here over this package's serializer registry:
+
+* which concrete classes may a value declared as ``T`` have (a proxy must answer ``isinstance`` for them),
+* what does the function return (one entry, or several for a literal ``-> (A, B)``),
+* which parameters have defaults,
+* can the serializer chosen for an annotation write a value of some runtime type,
+* is a runtime type acceptable for an annotation (with the empty-container rule)."""
 from __future__ import annotations
 
 import inspect
-from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Type, Union, get_type_hints
+from typing import Any, Callable, Dict, List, Sequence, Tuple, Type, Union, get_type_hints
 
 from beartype.door import is_subhint
 from typing_extensions import get_args, get_origin
@@ -11,53 +18,60 @@ from ....proxy_result import Absence, Either, Result
 from ....serialization.api import SerializerRegistry
 from ....serialization.types import EmptyContent
 
+_NOT_DECLARED = object()
+# get_type() of an empty list / tuple / dict: it fits every annotation of the same container kind
+_EMPTY_CONTAINER_KIND = {List[EmptyContent]: List, Tuple[EmptyContent]: Tuple, Dict[EmptyContent, EmptyContent]: Dict}
+
 
 def infer_real_types(typ: Type) -> Sequence[Type]:
-    origin: Optional[Type] = get_origin(typ)
-    result: List[Type] = []
-    if origin is not None:
-        if origin == Union:  # type: ignore[comparison-overlap]
-            for arg in get_args(typ):
-                result.extend(infer_real_types(arg))
-            return result
+    """``Union[A, List[B]]`` → ``[A, list]``; a generic alias → its origin; a plain class → itself"""
+    origin = get_origin(typ)
+    if origin is None:
+        return (typ,)
+    if origin is not Union:
         return (origin,)
-    return (typ,)
+    members: List[Type] = []
+    for member in get_args(typ):
+        members += infer_real_types(member)
+    return members
 
 
 def infer_return_type(func: Callable) -> Either:
-    hints = get_type_hints(func)
-    if "return" not in hints:
+    """``Result`` of a tuple of output types — one element unless the annotation is itself a tuple of types
+    (``-> (A, B)`` declares two outputs, ``-> Tuple[A, B]`` one) — or ``Absence`` when nothing is declared"""
+    declared = get_type_hints(func).get("return", _NOT_DECLARED)
+    if declared is _NOT_DECLARED:
         return Absence()
-    typ = hints["return"]
-    if isinstance(typ, tuple):  # `-> (A, B)`: several outputs
-        return Result(typ)
-    return Result((typ,))
+    return Result(declared if isinstance(declared, tuple) else (declared,))
 
 
 def get_default_args(func: Callable) -> Dict[str, Any]:
-    signature = inspect.signature(func)
-    return {k: v.default for k, v in signature.parameters.items() if v.default is not inspect.Parameter.empty}
+    defaults: Dict[str, Any] = {}
+    for name, parameter in inspect.signature(func).parameters.items():
+        if parameter.default is not parameter.empty:
+            defaults[name] = parameter.default
+    return defaults
 
 
 def check_types_serialization_compatible(annotation: Type, typ: Type, registry: SerializerRegistry) -> bool:
+    """would the serializer that the registry picks for `annotation` (for any member of a Union) take a `typ`?"""
     if annotation == typ:
         return True
-    for annotation_type in infer_real_types(annotation):
-        serializer = registry.find_serializer_by_type(annotation_type)
+    for candidate in infer_real_types(annotation):
+        serializer = registry.find_serializer_by_type(candidate)
         if serializer is None:
             continue
         supported = serializer.supported_types()
-        ok = supported == typ if isinstance(supported, type) else supported(typ)
-        if ok:
+        if (supported == typ) if isinstance(supported, type) else supported(typ):
             return True
     return False
 
 
 def is_subtype(subtype: Type, supertype: Type) -> bool:
-    if subtype == List[EmptyContent]:
-        subtype = supertype if is_subhint(supertype, List) else List  # type: ignore[assignment]
-    elif subtype == Tuple[EmptyContent]:
-        subtype = supertype if is_subhint(supertype, Tuple) else Tuple  # type: ignore[assignment]
-    elif subtype == Dict[EmptyContent, EmptyContent]:
-        subtype = supertype if is_subhint(supertype, Dict) else Dict  # type: ignore[assignment]
+    try:
+        kind = _EMPTY_CONTAINER_KIND.get(subtype)
+    except TypeError:  # an unhashable annotation object is certainly not one of the three
+        kind = None
+    if kind is not None:
+        subtype = supertype if is_subhint(supertype, kind) else kind
     return is_subhint(subtype, supertype)

@@ -1,20 +1,26 @@
-"""LzyCall / LazyCallWrapper (pylzy/lzy/core/call.py:38-327).
+"""Calling an ``@op`` — the behaviour of pylzy/lzy/core/call.py:38-327, built from three pieces:
 
-Calling an ``@op`` inside an active workflow validates the arguments against the annotations, creates
-snapshot entries for arguments, results and the exception, **snapshots every local argument right
-away** (``put_data`` at call time, :62-100 — later mutation of the caller's object must not leak into
-the op), queues the call and hands back lazy proxies (or real values when the workflow is eager).
-Outside a workflow the op is a plain function call (:207-209)."""
+``LazyCallWrapper``   what ``@op`` puts in place of the function.  Outside an active workflow it simply calls the
+                      function (:207-209).  Inside one it binds the arguments (``infer_and_validate_call_signature``),
+                      records an ``LzyCall``, queues it and answers with lazy proxies — real values when the workflow is
+                      eager, the real ``None`` for ``-> None`` ops (:232-250).
+``LzyCall``           one recorded call: snapshot entries for every argument, every result and the exception, the
+                      environment frozen at call time (:58-61).  **Local arguments are written to the snapshot right
+                      here** (:96-100): what the op will see is what the caller passed, whatever happens to the
+                      caller's object afterwards.
+``infer_and_validate_call_signature``  arity checks (``KeyError``), types of the arguments — from the producing op for
+                      a proxy, from the annotation, else from the value — and the check of each annotated argument
+                      against its annotation (``TypeError``, :303-312).
+
+An HBM-backed snapshot (``FrameSnapshot``) additionally wants to know who can still ask for an entry: inputs stay
+pinned until the runtime has run the call, results while their proxies are alive."""
 from __future__ import annotations
 
 import functools
 import inspect
 import uuid
 import weakref
-from dataclasses import dataclass
-from inspect import getfullargspec
-from itertools import chain, zip_longest
-from typing import TYPE_CHECKING, Any, Callable, Dict, List, Mapping, Optional, Sequence, Tuple
+from typing import TYPE_CHECKING, Any, Callable, Dict, List, Mapping, NamedTuple, Optional, Sequence, Tuple
 
 from ..api.v1.signatures import CallSignature, FuncSignature
 from ..api.v1.snapshot import Snapshot
@@ -29,65 +35,50 @@ if TYPE_CHECKING:
     from .workflow import LzyWorkflow
 
 
-@dataclass(eq=False)  # identity semantics: field-wise == would touch (and materialise) proxy arguments
+# ---- one recorded call ---------------------------------------------------------------------------------------------
 class LzyCall:
-    workflow: "LzyWorkflow"
-    signature: CallSignature
-    call_env: LzyEnvironment
-    description: str
-    version: str
-    cache: bool
-    lazy_arguments: bool
+    """identity semantics on purpose: comparing two calls field by field would compare — and so materialise — their
+    proxy arguments"""
 
-    def __post_init__(self):
+    def __init__(self, workflow: "LzyWorkflow", signature: CallSignature, call_env: LzyEnvironment, description: str,
+                 version: str, cache: bool, lazy_arguments: bool):
+        self.workflow, self.signature, self.call_env = workflow, signature, call_env
+        self.description, self.version, self.cache, self.lazy_arguments = description, version, cache, lazy_arguments
         self.id: str = str(uuid.uuid4())
-        self.final_env: LzyEnvironment = self.workflow.owner.env.combine(self.workflow.env).combine(self.call_env)
+        # the environment is fixed now: later changes of the Lzy / workflow environment do not reach this call
+        self.final_env: LzyEnvironment = workflow.owner.env.combine(workflow.env).combine(call_env)
         self.final_env.validate()
-        sign, workflow = self.signature, self.workflow
-        local_data_put_tasks = []
 
-        self.__args_entry_ids: List[str] = []
-        for i, arg in enumerate(sign.args):
-            if is_lzy_proxy(arg):
-                eid = get_proxy_entry_id(arg)
-            else:
-                arg_name = sign.func.arg_names[i]
-                eid = workflow.snapshot.create_entry(name=self.callable_name + "." + arg_name,
-                                                     typ=sign.func.input_types[arg_name]).id
-                local_data_put_tasks.append(workflow.snapshot.put_data(eid, _plain(arg)))
-            self.__args_entry_ids.append(eid)
+        snapshot, func = workflow.snapshot, signature.func
+        label = func.callable.__name__
+        uploads = []
 
-        self.__kwargs_entry_ids: Dict[str, str] = {}
-        for kwarg_name, kwarg in sign.kwargs.items():
-            if is_lzy_proxy(kwarg):
-                eid = get_proxy_entry_id(kwarg)
-            else:
-                eid = workflow.snapshot.create_entry(name=self.callable_name + "." + kwarg_name,
-                                                     typ=sign.func.input_types[kwarg_name]).id
-                local_data_put_tasks.append(workflow.snapshot.put_data(eid, _plain(kwarg)))
-            self.__kwargs_entry_ids[kwarg_name] = eid
+        def input_entry(parameter: str, value: Any) -> str:
+            if is_lzy_proxy(value):  # the result of another op: its entry already exists
+                return get_proxy_entry_id(value)
+            entry = snapshot.create_entry(name=f"{label}.{parameter}", typ=func.input_types[parameter])
+            uploads.append(snapshot.put_data(entry.id, _plain(value)))
+            return entry.id
 
-        self.__entry_ids: List[str] = []
-        for i, arg_typ in enumerate(sign.func.output_types):
-            self.__entry_ids.append(workflow.snapshot.create_entry(self.callable_name + f".return_{i}", arg_typ).id)
-        self.__exception_id: str = workflow.snapshot.create_entry(self.callable_name + ".exception", tuple).id
+        self._arg_entries: List[str] = [input_entry(func.arg_names[i], v) for i, v in enumerate(signature.args)]
+        self._kwarg_entries: Dict[str, str] = {name: input_entry(name, v) for name, v in signature.kwargs.items()}
+        self._result_entries: List[str] = [snapshot.create_entry(f"{label}.return_{i}", typ).id
+                                           for i, typ in enumerate(func.output_types)]
+        self._exception_entry: str = snapshot.create_entry(f"{label}.exception", tuple).id
+        if uploads:  # (a call whose arguments are all proxies needs no trip to the workflow thread)
+            LzyEventLoop.gather(*uploads)
 
-        # local data goes to the snapshot here, in the constructor: it may change before the
-        # dependent op actually runs
-        if local_data_put_tasks:  # (a call whose arguments are all proxies does not need a trip to the event loop)
-            LzyEventLoop.gather(*local_data_put_tasks)
-
-        # every input stays pinned until the runtime has executed this call (HBM-backed snapshots
-        # release a payload once nothing can ask for it any more; see FrameSnapshot)
-        pin = getattr(workflow.snapshot, "pin", None)
+        pin = getattr(snapshot, "pin", None)
         if pin is not None:
-            for eid in list(self.__args_entry_ids) + list(self.__kwargs_entry_ids.values()):
-                pin(eid)
-            for eid in self.__entry_ids:  # held until the caller has its proxies (an eager workflow runs the call first)
-                pin(eid)
-            if self.cache:
-                for eid in self.__entry_ids:
-                    workflow.snapshot.persist(eid)
+            for eid in self.input_entry_ids():
+                pin(eid)  # until the runtime has executed (or dropped) this call
+            for eid in self._result_entries:
+                pin(eid)  # until the caller holds its proxies (an eager workflow runs the call before that)
+                if cache:
+                    snapshot.persist(eid)
+
+    def input_entry_ids(self) -> List[str]:
+        return [*self._arg_entries, *self._kwarg_entries.values()]
 
     @property
     def callable_name(self) -> str:
@@ -103,25 +94,28 @@ class LzyCall:
 
     @property
     def arg_entry_ids(self) -> Sequence[str]:
-        return self.__args_entry_ids
+        return self._arg_entries
 
     @property
     def kwarg_entry_ids(self) -> Mapping[str, str]:
-        return self.__kwargs_entry_ids
+        return self._kwarg_entries
 
     @property
     def entry_ids(self) -> Sequence[str]:
-        return self.__entry_ids
+        return self._result_entries
 
     @property
     def exception_id(self) -> str:
-        return self.__exception_id
+        return self._exception_entry
 
     def get_provisioning(self) -> Provisioning:
         return self.final_env.get_provisioning()
 
     def get_env_vars(self) -> Dict[str, str]:
         return self.final_env.get_env_vars()
+
+    def __repr__(self) -> str:
+        return f"LzyCall({self.callable_name}, id={self.id})"
 
 
 def _plain(value: Any) -> Any:
@@ -130,130 +124,123 @@ def _plain(value: Any) -> Any:
     return _unwrap_tree(value) if type(value) in (list, tuple, dict) else value
 
 
-@dataclass(frozen=True)
+# ---- what @op leaves in place of the function ----------------------------------------------------------------------
 class LazyCallWrapper(WithEnvironmentMixin):
-    function: Callable[..., Any]
-    output_types: Sequence[type]
-    env: LzyEnvironment
-    description: str
-    version: str
-    cache: bool
-    lazy_arguments: bool
-
-    def __post_init__(self):
-        for attr in functools.WRAPPER_ASSIGNMENTS:
-            try:
-                object.__setattr__(self, attr, getattr(self.function, attr))
-            except (AttributeError, TypeError):
-                pass
-        object.__setattr__(self, "__wrapped__", self.function)
+    def __init__(self, function: Callable[..., Any], output_types: Sequence[type], env: LzyEnvironment, description: str,
+                 version: str, cache: bool, lazy_arguments: bool):
+        self.function, self.output_types, self.env = function, output_types, env
+        self.description, self.version, self.cache, self.lazy_arguments = description, version, cache, lazy_arguments
+        functools.update_wrapper(self, function)  # __name__, __doc__, __module__, __wrapped__ …
 
     def with_env(self, env: LzyEnvironment) -> "LazyCallWrapper":
         return LazyCallWrapper(self.function, self.output_types, env, self.description, self.version, self.cache,
                                self.lazy_arguments)
 
-    def __call__(self, *args, **kwargs) -> Any:
+    def _returns_none(self) -> bool:
+        only = self.output_types[0] if len(self.output_types) == 1 else None
+        return inspect.isclass(only) and issubclass(only, type(None))
+
+    def __call__(self, *args: Any, **kwargs: Any) -> Any:
         from .workflow import LzyWorkflow
 
-        active_workflow: Optional[LzyWorkflow] = LzyWorkflow.get_active()
-        if active_workflow is None:
+        workflow = LzyWorkflow.get_active()
+        if workflow is None:
             return self.function(*args, **kwargs)
 
-        signature = infer_and_validate_call_signature(
-            self.function, *args, output_type=self.output_types, snapshot=active_workflow.snapshot,
-            serializer_registry=active_workflow.owner.serializer_registry, **kwargs)
-        lzy_call = LzyCall(workflow=active_workflow, signature=signature, call_env=self.env,
-                           description=self.description, version=self.version, cache=self.cache,
-                           lazy_arguments=self.lazy_arguments)
-        active_workflow.register_call(lzy_call)
+        snapshot = workflow.snapshot
+        signature = infer_and_validate_call_signature(self.function, *args, output_type=self.output_types, snapshot=snapshot,
+                                                      serializer_registry=workflow.owner.serializer_registry, **kwargs)
+        call = LzyCall(workflow, signature, self.env, self.description, self.version, self.cache, self.lazy_arguments)
+        workflow.register_call(call)  # an eager workflow executes it right here
 
-        single_output = len(self.output_types) == 1
-        # `-> None` ops return the real None (so `is None` works) but stay queued (:232-250)
-        snap = active_workflow.snapshot
-        if single_output and inspect.isclass(self.output_types[0]) and issubclass(self.output_types[0], type(None)):
-            if hasattr(snap, "unpin"):
-                snap.unpin(lzy_call.entry_ids[0])
-            return None
-
-        proxies = []
-        for eid, types in zip(lzy_call.entry_ids, lzy_call.signature.func.output_types):
-            p = lzy_proxy(entry_id=eid, types=infer_real_types(types), wflow=active_workflow)
-            if hasattr(snap, "pin"):  # the result's frame lives as long as this proxy can still ask for it
-                snap.pin(eid)
-                weakref.finalize(p, snap.unpin, eid)
-            proxies.append(p)
-        result = tuple(materialize(p) for p in proxies) if active_workflow.eager else tuple(proxies)
-        if hasattr(snap, "unpin"):
-            for eid in lzy_call.entry_ids:
-                snap.unpin(eid)  # the construction-time pin; the proxies carry their own
-        return result[0] if single_output else result
-
-
-def infer_and_validate_call_signature(f: Callable, *args, output_type: Sequence[type], snapshot: Snapshot,
-                                      serializer_registry: SerializerRegistry, **kwargs) -> CallSignature:
-    types_mapping = {}
-    argspec, annotations, defaults = _function_facts(f)
-
-    if argspec.varkw is None:
-        for kwarg in kwargs:
-            if kwarg not in annotations:
-                raise KeyError(f"Unexpected key argument {kwarg}")
-
-    for spec_name, real_arg in zip_longest(argspec.args, range(len(args))):
-        if spec_name is not None and real_arg is None and spec_name not in kwargs and spec_name not in defaults:
-            raise KeyError(f"Argument {spec_name} is required but not provided")
-        if argspec.varargs is None and real_arg is not None and spec_name is None:
-            raise KeyError(f"Unexpected argument at position {real_arg}")
-
-    names_for_varargs = [str(uuid.uuid4())[:8] for _ in range(len(args) - len(argspec.args))]
-    actual_args: List[Any] = [None] * len(args)
-    actual_kwargs = {}
-
-    for i, (name, arg) in enumerate(chain(zip(chain(argspec.args, names_for_varargs), args), kwargs.items())):
-        from_varargs = len(argspec.args) < i < len(args)
-        if from_varargs:
-            inferred_type = _infer_type(snapshot, name, arg)
+        pin, unpin = getattr(snapshot, "pin", None), getattr(snapshot, "unpin", None)
+        answer: Any
+        if self._returns_none():
+            answer = None  # the real None, so that `is None` holds; the call stays queued all the same
         else:
-            inferred_type = _infer_type(snapshot, name, arg, annotations)
-            if name in annotations:
-                typ = inferred_type if is_lzy_proxy(arg) else get_type(arg)
-                compatible = check_types_serialization_compatible(annotations[name], typ, serializer_registry)
-                if not compatible or not is_subtype(typ, annotations[name]):
-                    raise TypeError(f"Invalid types: argument {name} has type {annotations[name]} but passed type {typ}")
-        types_mapping[name] = inferred_type
-        # a proxy that has already been materialised is treated as local data
-        value = materialize(arg) if is_lzy_proxy(arg) and materialized(arg) else arg
-        if i < len(args):
-            actual_args[i] = value
-        else:
-            actual_kwargs[name] = value
+            handles = []
+            for eid, declared in zip(call.entry_ids, signature.func.output_types):
+                handle = lzy_proxy(entry_id=eid, types=infer_real_types(declared), wflow=workflow)
+                if pin is not None:  # the result's frame lives as long as this proxy can still ask for it
+                    pin(eid)
+                    weakref.finalize(handle, unpin, eid)
+                handles.append(materialize(handle) if workflow.eager else handle)
+            answer = handles[0] if len(handles) == 1 else tuple(handles)
+        if unpin is not None:
+            for eid in call.entry_ids:
+                unpin(eid)  # the construction-time pin; the proxies carry their own
+        return answer
 
-    arg_names = tuple(argspec.args[: len(args)] + names_for_varargs)
-    return CallSignature(FuncSignature(f, types_mapping, output_type, arg_names, tuple(kwargs.keys())),
-                         tuple(actual_args), actual_kwargs)
+
+# ---- binding the arguments of one call -------------------------------------------------------------------------
+class _Facts(NamedTuple):
+    spec: inspect.FullArgSpec
+    annotations: Dict[str, Any]
+    defaults: Dict[str, Any]
 
 
 _FACTS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 
-def _function_facts(f: Callable):
-    """argspec, evaluated annotations and defaults of an op body, computed once per function"""
+def _function_facts(f: Callable) -> _Facts:
+    """argspec, evaluated annotations and defaults of an op body — computed once per function"""
     try:
-        facts = _FACTS.get(f)
-    except TypeError:
-        facts = None
-    if facts is None:
-        facts = (getfullargspec(f), inspect.get_annotations(f, eval_str=True), get_default_args(f))
+        known = _FACTS.get(f)
+    except TypeError:  # not weak-referenceable
+        known = None
+    if known is None:
+        known = _Facts(inspect.getfullargspec(f), inspect.get_annotations(f, eval_str=True), get_default_args(f))
         try:
-            _FACTS[f] = facts
+            _FACTS[f] = known
         except TypeError:
             pass
-    return facts
+    return known
 
 
-def _infer_type(snapshot: Snapshot, arg_name: str, arg: Any, type_annotations: Optional[Dict[str, Any]] = None):
-    if is_lzy_proxy(arg):
-        return snapshot.get(get_proxy_entry_id(arg)).typ
-    if type_annotations and arg_name in type_annotations:
-        return type_annotations[arg_name]
-    return get_type(arg)
+def _refuse_bad_arity(facts: _Facts, n_positional: int, kwargs: Mapping[str, Any]) -> None:
+    spec = facts.spec
+    if spec.varkw is None:
+        for name in kwargs:
+            if name not in facts.annotations:
+                raise KeyError(f"Unexpected key argument {name}")
+    for name in spec.args[n_positional:]:
+        if name not in kwargs and name not in facts.defaults:
+            raise KeyError(f"Argument {name} is required but not provided")
+    if spec.varargs is None and n_positional > len(spec.args):
+        raise KeyError(f"Unexpected argument at position {len(spec.args)}")
+
+
+def _as_local_data(value: Any) -> Any:
+    """a proxy that has been materialised already is plain local data again"""
+    return materialize(value) if is_lzy_proxy(value) and materialized(value) else value
+
+
+def infer_and_validate_call_signature(f: Callable, *args: Any, output_type: Sequence[type], snapshot: Snapshot,
+                                      serializer_registry: SerializerRegistry, **kwargs: Any) -> CallSignature:
+    facts = _function_facts(f)
+    _refuse_bad_arity(facts, len(args), kwargs)
+    declared = facts.spec.args
+    vararg_names = [uuid.uuid4().hex[:8] for _ in args[len(declared):]]  # *args become entries with made-up names
+    positional_names = [*declared[:len(args)], *vararg_names]
+
+    def type_of(name: str, value: Any, annotated: bool) -> Any:
+        if is_lzy_proxy(value):
+            produced_as = snapshot.get(get_proxy_entry_id(value)).typ
+            actual = produced_as
+        else:
+            produced_as, actual = None, get_type(value)
+        if not annotated:
+            return actual
+        wanted = facts.annotations[name]
+        if not (check_types_serialization_compatible(wanted, actual, serializer_registry) and is_subtype(actual, wanted)):
+            raise TypeError(f"Invalid types: argument {name} has type {wanted} but passed type {actual}")
+        return produced_as if produced_as is not None else wanted
+
+    types: Dict[str, Any] = {}
+    for index, (name, value) in enumerate(zip(positional_names, args)):
+        types[name] = type_of(name, value, annotated=index < len(declared) and name in facts.annotations)
+    for name, value in kwargs.items():
+        types[name] = type_of(name, value, annotated=name in facts.annotations)
+
+    return CallSignature(FuncSignature(f, types, output_type, tuple(positional_names), tuple(kwargs)),
+                         tuple(_as_local_data(v) for v in args), {k: _as_local_data(v) for k, v in kwargs.items()})

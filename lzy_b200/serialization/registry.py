@@ -1,17 +1,27 @@
-"""LzySerializerRegistry — the registry users see on ``lzy.serializer_registry``
-(pylzy/lzy/serialization/registry.py:20-82): built-ins, user serializers tracked so that they can be
-shipped to the op side as (module, class, priority) imports, the ``__main__`` ban, and copyreg hooks
-so that values of registered types nested inside pickled objects go through their serializer."""
+"""``lzy.serializer_registry`` — what pylzy/lzy/serialization/registry.py:20-82 gives its users, over this package's
+serializers:
+
+* the built-ins (device frames for tensors / ndarrays, ``File``, cloudpickle as the last resort);
+* user serializers, remembered by class so that the op side can be told to import them
+  (``imports()`` → ``SerializerImport(module, class, priority)`` → ``load_imports()``), and refused when they live in
+  ``__main__`` (the op side could not import them);
+* values of a registered type *nested* inside a pickled object go through their serializer too, by way of
+  ``copyreg`` — for user serializers and ``File``; arrays inside a pickle instead ride as protocol-5 out-of-band
+  buffers of one composite frame, so the device-frame serializers are kept out of ``copyreg``."""
 from __future__ import annotations
 
 import copyreg
 import importlib
 from dataclasses import dataclass
 from io import BytesIO
-from typing import Any, Optional, Sequence, Set, Type
+from typing import Any, Dict, List, Optional, Sequence, Type
 
 from .api import Serializer, SerializerRegistry
 from .builtin import CloudpickleSerializer, FileSerializer, NdarrayFrameSerializer, TensorFrameSerializer
+
+_BUILTINS = ((TensorFrameSerializer, 10), (NdarrayFrameSerializer, 11), (FileSerializer, 20),
+             (CloudpickleSerializer, 1_000_000))  # the fallback always comes last
+_FIRST_USER_PRIORITY = 100  # user serializers without a priority line up here: before the pickle fallback
 
 
 @dataclass
@@ -21,64 +31,68 @@ class SerializerImport:
     priority: int
 
 
+def _exact_type_of(serializer: Serializer) -> Optional[type]:
+    """the one class a by-type serializer stands for (None for predicate serializers or missing libraries)"""
+    try:
+        supported = serializer.supported_types()
+    except (ImportError, ModuleNotFoundError):
+        return None
+    return supported if isinstance(supported, type) else None
+
+
 class LzySerializerRegistry(SerializerRegistry):
     def __init__(self):
         super().__init__()
-        self.__inited = False
-        self.__user_serializers: Set[Type[Serializer]] = set()
-        self.register_serializer(TensorFrameSerializer(), 10)
-        self.register_serializer(NdarrayFrameSerializer(), 11)
-        self.register_serializer(FileSerializer(), 20)
-        self.register_serializer(CloudpickleSerializer(), 1_000_000)  # the fallback always comes last
-        self.__inited = True
+        self._user_classes: Dict[Type[Serializer], None] = {}  # insertion-ordered set
+        self._open_for_users = False
+        for cls, priority in _BUILTINS:
+            self.register_serializer(cls(), priority)
+        self._open_for_users = True
 
+    # ---- registration -----------------------------------------------------------------------------------------------
     def register_serializer(self, serializer: Serializer, priority: Optional[int] = None) -> None:
-        if type(serializer).__module__ == "__main__":
+        cls = type(serializer)
+        if cls.__module__ == "__main__":
             raise ValueError("Cannot register serializers from the __main__ module. "
                              "Please move serializer class to an external file.")
-        if priority is None and self.__dict__.get("_LzySerializerRegistry__inited"):
-            priority = 100 + len(self.__user_serializers)  # user serializers win over the pickle fallback
+        from_user = self._open_for_users
+        if from_user and priority is None:
+            priority = _FIRST_USER_PRIORITY + len(self._user_classes)
         super().register_serializer(serializer, priority)
-        user = bool(self.__dict__.get("_LzySerializerRegistry__inited"))
-        if user:
-            self.__user_serializers.add(type(serializer))
-        # an instance of a serializer's type nested inside a pickled object travels through that serializer
-        # (registry.py:34-46 hooks every by-type serializer into copyreg).  The device-frame serializers stay
-        # out: arrays inside a pickle ride as protocol-5 out-of-band buffers of one composite frame instead.
-        if user or isinstance(serializer, FileSerializer):
-            try:
-                t = serializer.supported_types()
-                if isinstance(t, type):
-                    copyreg.dispatch_table[t] = self.__reducer
-            except (ImportError, ModuleNotFoundError):
-                pass
+        if from_user:
+            self._user_classes[cls] = None
+        if from_user or isinstance(serializer, FileSerializer):
+            typ = _exact_type_of(serializer)
+            if typ is not None:
+                copyreg.dispatch_table[typ] = self._reduce_nested
 
     def unregister_serializer(self, serializer: Serializer) -> None:
         super().unregister_serializer(serializer)
-        self.__user_serializers.discard(type(serializer))
-        try:
-            t = serializer.supported_types()
-            if isinstance(t, type):
-                copyreg.dispatch_table.pop(t, None)
-        except (ImportError, ModuleNotFoundError):
-            pass
+        self._user_classes.pop(type(serializer), None)
+        typ = _exact_type_of(serializer)
+        if typ is not None:
+            copyreg.dispatch_table.pop(typ, None)
 
+    # ---- shipping user serializers to the op side -----------------------------------------------------------------
     def imports(self) -> Sequence[SerializerImport]:
-        return [SerializerImport(s.__module__, s.__name__, self._serializer_priorities[s]) for s in self.__user_serializers]
+        shipped: List[SerializerImport] = []
+        for cls in self._user_classes:
+            shipped.append(SerializerImport(cls.__module__, cls.__name__, self._serializer_priorities[cls]))
+        return shipped
 
     def load_imports(self, imports: Sequence[SerializerImport]) -> None:
-        for imp in imports:
-            module = importlib.import_module(imp.module_name)
-            cls = getattr(module, imp.class_name)
-            if cls not in self._serializer_priorities:
-                self.register_serializer(cls(), imp.priority)
+        for wanted in imports:
+            cls = getattr(importlib.import_module(wanted.module_name), wanted.class_name)
+            if cls not in self._serializer_priorities:  # already here (same process, or loaded twice)
+                self.register_serializer(cls(), wanted.priority)
 
-    def __constructor(self, data_format: str, data: bytes) -> Any:
-        serializer = self.find_serializer_by_data_format(data_format)
-        return serializer.deserialize(BytesIO(data))  # type: ignore[union-attr]
-
-    def __reducer(self, obj: Any):
+    # ---- nested values inside pickles -------------------------------------------------------------------------------
+    def _reduce_nested(self, obj: Any):
         serializer = self.find_serializer_by_instance(obj)
-        buffer = BytesIO()
-        serializer.serialize(obj, buffer)  # type: ignore[union-attr]
-        return self.__constructor, (serializer.data_format(), buffer.getvalue())  # type: ignore[union-attr]
+        raw = BytesIO()
+        serializer.serialize(obj, raw)  # type: ignore[union-attr]
+        return self._revive_nested, (serializer.data_format(), raw.getvalue())  # type: ignore[union-attr]
+
+    def _revive_nested(self, data_format: str, raw: bytes) -> Any:
+        serializer = self.find_serializer_by_data_format(data_format)
+        return serializer.deserialize(BytesIO(raw))  # type: ignore[union-attr]
