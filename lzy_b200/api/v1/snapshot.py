@@ -11,11 +11,10 @@ implementation of ``DefaultSnapshot``'s contract (put_data :141-172, get_data :1
 """
 from __future__ import annotations
 
-import dataclasses
 import threading
 import uuid
 from abc import ABC, abstractmethod
-from typing import TYPE_CHECKING, Any, Dict, Optional, Type, cast
+from typing import TYPE_CHECKING, Any, Dict, Optional, Type
 
 from ...proxy_result import Absence, Either, Result
 from ...serialization.api import Schema, SerializerRegistry
@@ -24,35 +23,42 @@ if TYPE_CHECKING:
     from .b200.store import FrameStore
 
 
-@dataclasses.dataclass
+class _AssignedLater:
+    """an attribute that exists from the start but has a value only once somebody decided it: reading it earlier
+    is an error, not ``None`` (pylzy/lzy/api/v1/snapshot.py:33-53 does the same for both fields below)"""
+
+    def __init__(self, complaint: str):
+        self._complaint = complaint
+
+    def __set_name__(self, owner, name: str) -> None:
+        self._slot = "_" + name
+
+    def __get__(self, entry, owner=None):
+        if entry is None:
+            return self
+        value = getattr(entry, self._slot)
+        if value is None:
+            raise ValueError(self._complaint.format(entry=entry))
+        return value
+
+    def __set__(self, entry, value) -> None:
+        setattr(entry, self._slot, value)
+
+
 class SnapshotEntry:
-    id: str
-    name: str
-    typ: Type
-    data_scheme: Schema
-    storage_name: str
-    _storage_uri: Optional[str] = None
-    _data_hash: Optional[str] = None
+    """one row of a workflow's data table: an argument, a result or an exception.  `storage_uri` and `data_hash`
+    are decided later — for local data when it is stored (content address), for results when the call queue is
+    submitted (core/workflow.py)."""
+    storage_uri = _AssignedLater("Storage uri for snapshot entry with id={entry.id} is not set")
+    data_hash = _AssignedLater("Data hash for snapshot entry {entry.id} is not set")
 
-    @property
-    def storage_uri(self) -> str:
-        if self._storage_uri is None:
-            raise ValueError(f"Storage uri for snapshot entry with id={self.id} is not set")
-        return cast(str, self._storage_uri)
+    def __init__(self, id: str, name: str, typ: Type, data_scheme: Schema, storage_name: str,
+                 storage_uri: Optional[str] = None, data_hash: Optional[str] = None):
+        self.id, self.name, self.typ, self.data_scheme, self.storage_name = id, name, typ, data_scheme, storage_name
+        self._storage_uri, self._data_hash = storage_uri, data_hash
 
-    @storage_uri.setter
-    def storage_uri(self, uri: str) -> None:
-        self._storage_uri = uri
-
-    @property
-    def data_hash(self) -> str:
-        if self._data_hash is None:
-            raise ValueError(f"Data hash for snapshot entry {self.id} is not set")
-        return cast(str, self._data_hash)
-
-    @data_hash.setter
-    def data_hash(self, hsh: str) -> None:
-        self._data_hash = hsh
+    def __repr__(self) -> str:
+        return f"SnapshotEntry(id={self.id!r}, name={self.name!r}, typ={self.typ!r}, uri={self._storage_uri!r})"
 
 
 class Snapshot(ABC):

@@ -71,41 +71,73 @@ class FrameMount(SlotMount):
 
 def read_data(path: str, typ: Type, serializers: SerializerRegistry, logger: Logger, mount: SlotMount,
               cache: Optional[Dict[str, Any]] = None) -> Any:
-    """startup.py:31-49; the read cache lives for one execution (the reference's is per process = per op)."""
+    """one input slot as a Python object (pylzy startup.py:31-49).  Within one execution a slot is read once: the
+    `cache` dict plays the part of the reference's per-process read cache."""
     if cache is not None and path in cache:
         return cache[path]
-    ser = serializers.find_serializer_by_type(typ)
-    logger.info("Reading %s with serializer %s", path.split("/")[-1], type(ser).__name__)
-    data = mount.read(path, typ, serializers)
+    chosen = serializers.find_serializer_by_type(typ)
+    logger.info("Reading %s with serializer %s", path.rsplit("/", 1)[-1], type(chosen).__name__)
+    value = mount.read(path, typ, serializers)
     if cache is not None:
-        cache[path] = data
-    return data
+        cache[path] = value
+    return value
 
 
 def write_data(path: str, typ: Type, data: Any, serializers: SerializerRegistry, logger: Logger, mount: SlotMount) -> None:
-    """startup.py:52-77: serializer must exist and be available; a lazy argument returned as a result is
-    unwrapped; the value's real type must be compatible with the annotation."""
-    ser = serializers.find_serializer_by_type(typ)
-    if ser is None:
+    """one result into its output slot (pylzy startup.py:52-77): the declared type needs a usable serializer, a lazy
+    argument handed back as a result stands for its value, and the value's real type must fit the declaration."""
+    chosen = serializers.find_serializer_by_type(typ)
+    if chosen is None:
         raise ValueError(f"Cannot find serializer for type {typ}")
-    if not ser.available():
-        raise ValueError(f"Serializer for type {typ} is not available, please install {ser.requirements()}")
-    if hasattr(type(data), _LAZY_ARGUMENT):  # if input argument is a return value
+    if not chosen.available():
+        raise ValueError(f"Serializer for type {typ} is not available, please install {chosen.requirements()}")
+    if hasattr(type(data), _LAZY_ARGUMENT):
         data = data.__lzy_origin__
-    real_type = get_type(data)
-    compatible = check_types_serialization_compatible(typ, real_type, serializers)
-    if not compatible or not is_subtype(real_type, typ):
-        raise TypeError(f"Invalid types: return value has type {typ} but passed type {real_type}")
-    logger.info("Writing %s with serializer %s", path.split("/")[-1], type(ser))
+    actual = get_type(data)
+    if not (check_types_serialization_compatible(typ, actual, serializers) and is_subtype(actual, typ)):
+        raise TypeError(f"Invalid types: return value has type {typ} but passed type {actual}")
+    logger.info("Writing %s with serializer %s", path.rsplit("/", 1)[-1], type(chosen))
     mount.write(path, typ, data, serializers)
 
 
 def _get_main_pid() -> int:
-    """startup.py:80-106: a program replicated by subprocesses (DDP) re-runs this entry point; only the
-    initial process — the one that set LZY_OP_MAIN_PID — writes results."""
-    if MAIN_PID_ENV_VAR not in os.environ:
-        os.environ[MAIN_PID_ENV_VAR] = str(os.getpid())
-    return int(os.environ[MAIN_PID_ENV_VAR])
+    """A program that replicates itself through subprocesses (DDP) runs this entry point again in every replica.
+    The first process to get here leaves its pid in ``LZY_OP_MAIN_PID`` for its children to inherit; only that
+    process writes results (pylzy startup.py:80-106)."""
+    return int(os.environ.setdefault(MAIN_PID_ENV_VAR, str(os.getpid())))
+
+
+class _Execution:
+    """one run of one op over its slots: arguments in, body, results (or the exception) out"""
+
+    def __init__(self, serializers: SerializerRegistry, logger: Logger, mount: SlotMount, exception_path: Tuple[Type, str],
+                 lazy_arguments: bool):
+        self.serializers, self.logger, self.mount = serializers, logger, mount
+        self.exception_type, self.exception_slot = exception_path
+        self.lazy_arguments = lazy_arguments
+        self._already_read: Dict[str, Any] = {}
+
+    def put(self, typ: Type, path: str, value: Any) -> None:
+        write_data(path, typ, value, self.serializers, self.logger, self.mount)
+
+    def report_failure(self, what: str, error: BaseException, *details: Any) -> None:
+        """log, then leave ``sys.exc_info()`` in the exception slot (the caller re-raises from it)"""
+        self.logger.error(what, error, *details)
+        self.put(self.exception_type, self.exception_slot, sys.exc_info())
+
+    def argument(self, typ: Type, path: str) -> Any:
+        def fetch() -> Any:
+            return read_data(path, typ, self.serializers, self.logger, self.mount, self._already_read)
+
+        if self.lazy_arguments:  # read on first touch, if ever
+            return proxy(fetch, infer_real_types(typ), cls_attrs={_LAZY_ARGUMENT: True})
+        return fetch()
+
+    def publish(self, output_paths: Sequence[Tuple[Type, str]], result: Any) -> None:
+        values = [result] if len(output_paths) == 1 else result
+        for (typ, path), value in zip(output_paths, values):
+            self.put(typ, path, value)
+        self.put(type(None), self.exception_slot, None)  # "no exception"
 
 
 def process_execution(
@@ -119,61 +151,47 @@ def process_execution(
     lazy_arguments: bool,
     mount: SlotMount,
 ) -> None:
-    """startup.py:109-170, step for step."""
-    pid = os.getpid()
-    main_pid = _get_main_pid()
-    logger.debug("Starting process with pid %d (ppid %d, main pid %s)", pid, os.getppid(), main_pid)
+    """pylzy startup.py:109-170 — the order of effects is kept: arguments are read (or wrapped lazily), the op runs,
+    the main-pid marker is dropped, the main process writes every result and then ``None`` into the exception slot;
+    a failure in any phase leaves ``sys.exc_info()`` in the exception slot and is re-raised."""
+    run = _Execution(serializers, logger, mount, exception_path, lazy_arguments)
+    me, main_pid = os.getpid(), _get_main_pid()
+    logger.debug("Starting process with pid %d (ppid %d, main pid %s)", me, os.getppid(), main_pid)
+
     logger.info("Reading arguments...")
-    exc_typ, exc_path = exception_path
-    cache: Dict[str, Any] = {}
-
-    def argument(typ: Type, path: str) -> Any:
-        if lazy_arguments:
-            return proxy(lambda: read_data(path, typ, serializers, logger, mount, cache), infer_real_types(typ),
-                         cls_attrs={_LAZY_ARGUMENT: True})
-        return read_data(path, typ, serializers, logger, mount, cache)
-
     try:
-        args = [argument(typ, path) for typ, path in args_paths]
-        kwargs = {name: argument(typ, path) for name, (typ, path) in kwargs_paths.items()}
+        positional = [run.argument(typ, path) for typ, path in args_paths]
+        named = {name: run.argument(*described) for name, described in kwargs_paths.items()}
     except Exception as e:
-        logger.error("Error while reading arguments: %s", e)
-        write_data(exc_path, exc_typ, sys.exc_info(), serializers, logger, mount)
+        run.report_failure("Error while reading arguments: %s", e)
         raise
 
     logger.info("Executing operation '%s'", getattr(op, "__name__", op))
-    start = time.time()
+    began = time.time()
     try:
-        res = op(*args, **kwargs)
+        result = op(*positional, **named)
     except Exception as e:
-        logger.error("Execution completed with error `%s` in %s", e, time.time() - start)
-        write_data(exc_path, exc_typ, sys.exc_info(), serializers, logger, mount)
+        run.report_failure("Execution completed with error `%s` in %s", e, time.time() - began)
         raise
     finally:
         os.environ.pop(MAIN_PID_ENV_VAR, None)
-    logger.info("Execution completed in %s sec", time.time() - start)
+    logger.info("Execution completed in %s sec", time.time() - began)
 
-    if main_pid != pid:
-        logger.debug("Don't write results from not main process with pid %d", pid)
+    if me != main_pid:
+        logger.debug("Don't write results from not main process with pid %d", me)
         return
-
     logger.info("Writing results...")
     try:
-        if len(output_paths) == 1:
-            write_data(output_paths[0][1], output_paths[0][0], res, serializers, logger, mount)
-        else:
-            for out, data in zip(output_paths, res):
-                write_data(out[1], out[0], data, serializers, logger, mount)
-        write_data(exc_path, type(None), None, serializers, logger, mount)
+        run.publish(output_paths, result)
     except Exception as e:
-        logger.error("Error while writing result: %s", e)
-        write_data(exc_path, exc_typ, sys.exc_info(), serializers, logger, mount)
+        run.report_failure("Error while writing result: %s", e)
         raise
 
 
 @dataclasses.dataclass
 class ProcessingRequest:
-    """startup.py:173-182 — field for field, so a request pickled by a stock client has the same shape."""
+    """what the client pickles into the task's command line (pylzy startup.py:173-182) — field for field, so that a
+    request pickled by a stock client has the shape this entry point expects"""
     logger_config: Dict[str, Any]
     serializers: Sequence[SerializerImport]
     op: Callable
@@ -184,34 +202,30 @@ class ProcessingRequest:
     lazy_arguments: bool = True
 
 
+def _stage(what: str, action: Callable[[], Any]) -> Any:
+    """the preparatory stages report their failure on stderr (there is no logger yet) and let it propagate"""
+    try:
+        return action()
+    except Exception as e:
+        sys.stderr.write(f"Error while {what}: {e}")
+        sys.stderr.flush()
+        raise
+
+
 def main(arg: str, mount: Optional[SlotMount] = None) -> None:
-    """startup.py:185-220.  `mount` is supplied by the worker that runs the task (the reference reads
-    ``LZY_MOUNT`` from the environment and asserts it is set, startup.py:39-40)."""
+    """pylzy startup.py:185-220: unpickle the request, import the user's serializers, configure logging, run.  The
+    `mount` comes from the worker that runs the task (the reference takes ``LZY_MOUNT`` from the environment and
+    asserts that it is set, :39-40)."""
     if mount is None:
         raise AssertionError("no slot mount: this entry point runs inside a worker that owns the task's slots")
-    try:
-        req = cast(ProcessingRequest, unpickle(arg))
-    except Exception as e:
-        sys.stderr.write(f"Error while unpickling request: {e}")
-        sys.stderr.flush()
-        raise
+    request = cast(ProcessingRequest, _stage("unpickling request", lambda: unpickle(arg)))
     tbpickle.install()  # the exception slot carries sys.exc_info(), traceback included
     registry = LzySerializerRegistry()
-    try:
-        registry.load_imports(req.serializers)
-    except Exception as e:
-        sys.stderr.write(f"Error while loading serializers: {e}")
-        sys.stderr.flush()
-        raise
-    try:
-        if req.logger_config:
-            logging.config.dictConfig(req.logger_config)
-    except Exception as e:
-        sys.stderr.write(f"Error while logging configuration: {e}")
-        sys.stderr.flush()
-        raise
+    _stage("loading serializers", lambda: registry.load_imports(request.serializers))
+    if request.logger_config:
+        _stage("logging configuration", lambda: logging.config.dictConfig(request.logger_config))
     logger = logging.getLogger(NAME)
     logger.info("Starting execution...")
-    process_execution(registry, req.op, req.args_paths, req.kwargs_paths, req.output_paths, req.exception_path, logger,
-                      req.lazy_arguments, mount)
+    process_execution(registry, request.op, request.args_paths, request.kwargs_paths, request.output_paths,
+                      request.exception_path, logger, request.lazy_arguments, mount)
     logger.info("Finishing execution...")

@@ -1,15 +1,21 @@
-"""LzyWorkflow (pylzy/lzy/core/workflow.py:39-298): the call queue, the barrier, result-URI rules.
+"""``LzyWorkflow`` — the ``with lzy.workflow(...)`` object (behaviour of pylzy/lzy/core/workflow.py:39-298).
 
-Only one workflow may be active per process (:205-215).  Calls are lazy: they run when a proxy is
-touched, on ``barrier()`` or on exit; ``eager=True`` runs each call immediately (:118-124,154-171).
-Result URIs (``cache=False``: ``<storage>/lzy_runs/<wf>/ops/<fn>/<call.id>/return_<i>``; ``cache=True``:
-``<storage>/[<user>/]lzy_runs/<wf>/ops/<fn>/<version>/<input hashes>/return_<i>``) follow :247-298."""
+* One workflow is active per process (:205-215); an op body — a thread here, a process of its own in the
+  reference — sees none of its caller's and may open its own.
+* ``@op`` calls are queued and run by ``barrier()``: when a proxy is touched, on request, or on leaving the
+  ``with`` block; an eager workflow runs each call as it is registered (:118-124, :154-171).
+* Just before a queue is handed to the runtime every result gets its storage URI (:247-298):
+  ``cache=False``  ``<storage>/lzy_runs/<workflow>/ops/<function>/<call id>/return_<i>``
+  ``cache=True``   ``<storage>/[<user>/]lzy_runs/<workflow>/ops/<function>/<version>/<argument hashes>/return_<i>``
+  (hashes joined by ``_``, keyword arguments as ``name:hash`` sorted by name — equal calls meet at equal URIs, which
+  is all that caching is); the exception of a call always lives under its call id.
+* Leaving the block cleanly finishes the execution; any exception (the block's own, or one from the last barrier)
+  aborts it and is re-raised."""
 from __future__ import annotations
 
 import logging
 import os
 import re
-from dataclasses import dataclass, replace
 from typing import TYPE_CHECKING, Any, ClassVar, List, Optional, Set
 
 from ..api.v1.snapshot import Snapshot
@@ -24,199 +30,167 @@ if TYPE_CHECKING:
 
 USER_ENV = "LZY_USER"
 NAME_VALID_SYMBOLS = "letters, digits, '-', '_'"
-_NAME_RE = re.compile(r"^[A-Za-z0-9_\-]+$")
+_VALID_NAME = re.compile(r"[A-Za-z0-9_\-]+")
 _LOG = logging.getLogger("lzy_b200.workflow")
 
 
-@dataclass
 class LzyWorkflow(WithEnvironmentMixin):
     instance: ClassVar[Optional["LzyWorkflow"]] = None
-    name: str
-    owner: "Lzy"
-    env: LzyEnvironment
-    eager: bool = False
-    interactive: bool = True
 
-    def with_fields(self, **kwargs: Any) -> "LzyWorkflow":
-        """a copy with some declaration changed — only before the workflow is used: once it has calls, a snapshot
-        or an execution it carries state a copy could not share (pylzy/lzy/core/workflow.py:77-96)"""
-        if self.__filled_entry_ids or self.__call_queue or self.__started or self.__snapshot or self.__execution_id:
+    def __init__(self, name: str, owner: "Lzy", env: LzyEnvironment, eager: bool = False, interactive: bool = True):
+        if not _VALID_NAME.fullmatch(name or ""):
+            raise ValueError(f"Invalid workflow name. Name can contain only {NAME_VALID_SYMBOLS}")
+        self.name, self.owner, self.env, self.eager, self.interactive = name, owner, env, eager, interactive
+        self._user = os.getenv(USER_ENV)
+        self._queue: List["LzyCall"] = []
+        self._uri_assigned: Set[str] = set()   # entries whose storage URI has been decided
+        self._snapshot: Optional[Snapshot] = None
+        self._execution: Optional[str] = None
+        self._running = False
+        self._opened_inside_op = False
+
+    # ---- declarations ---------------------------------------------------------------------------------------------
+    def with_fields(self, **changes: Any) -> "LzyWorkflow":
+        """a copy with some declaration changed.  Only an untouched workflow can be copied (:77-96): once it has
+        calls, a snapshot or an execution it carries state a copy could not share."""
+        if self._running or self._queue or self._uri_assigned or self._snapshot is not None or self._execution is not None:
             raise RuntimeError("It's forbidden to change LzyWorkflow fields after start working with it")
-        return replace(self, **kwargs)
+        declared = dict(name=self.name, owner=self.owner, env=self.env, eager=self.eager, interactive=self.interactive)
+        declared.update(changes)
+        return type(self)(**declared)
 
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}(name={self.name!r}, eager={self.eager}, interactive={self.interactive})"
+
+    # ---- which workflow is active ---------------------------------------------------------------------------------
     @classmethod
     def get_active(cls) -> Optional["LzyWorkflow"]:
-        if op_scope.inside_op():  # an op body sees only a workflow it opened itself, as in the reference's op subprocess
-            return op_scope.get_workflow()
+        if op_scope.inside_op():
+            return op_scope.get_workflow()  # only a workflow this op body opened itself
         return cls.instance
 
     @classmethod
     def set_active(cls, instance: Optional["LzyWorkflow"]) -> None:
+        # subclasses (Lzy._workflow_class) and the base class answer get_active() alike
         for klass in cls.__mro__:
             if isinstance(klass, type) and issubclass(klass, LzyWorkflow):
                 klass.instance = instance
 
-    def __post_init__(self) -> None:
-        if not _NAME_RE.match(self.name or ""):
-            raise ValueError(f"Invalid workflow name. Name can contain only {NAME_VALID_SYMBOLS}")
-        self.__user = os.getenv(USER_ENV)
-        self.__filled_entry_ids: Set[str] = set()
-        self.__call_queue: List["LzyCall"] = []
-        self.__started = False
-        self.__nested = False
-        self.__snapshot: Optional[Snapshot] = None
-        self.__execution_id: Optional[str] = None
+    def _mark_active(self, on: bool) -> None:
+        if self._opened_inside_op:
+            op_scope.set_workflow(self if on else None)
+        else:
+            self.set_active(self if on else None)
 
+    # ---- state the rest of the API reads ------------------------------------------------------------------------
     @property
     def log(self) -> logging.Logger:
         return _LOG
 
     @property
     def snapshot(self) -> Snapshot:
-        if self.__snapshot is None:
+        if self._snapshot is None:
             raise ValueError("Workflow is not yet started")
-        return self.__snapshot
+        return self._snapshot
 
     @property
     def execution_id(self) -> str:
-        if self.__execution_id is None:
+        if self._execution is None:
             raise ValueError("Workflow is not yet started")
-        return self.__execution_id
+        return self._execution
 
     @property
     def filled_entry_ids(self) -> Set[str]:
-        return self.__filled_entry_ids
+        return self._uri_assigned
 
     @property
     def call_queue(self) -> List["LzyCall"]:
-        return self.__call_queue
+        return self._queue
 
-    def register_call(self, call: "LzyCall") -> Any:
-        self.__call_queue.append(call)
+    # ---- the call queue -------------------------------------------------------------------------------------------
+    def register_call(self, call: "LzyCall") -> None:
+        self._queue.append(call)
         if self.eager:
             self.barrier()
 
     def barrier(self) -> None:
         LzyEventLoop.run_async(self._barrier())
 
+    async def _barrier(self) -> None:
+        if not self._queue:
+            return
+        for call in self._queue:
+            self._assign_uris(call)
+        submitted, self._queue = self._queue, []  # whatever happens to this graph, it is not submitted twice
+        await self.owner.runtime.exec(submitted, lambda step: self.log.info(f"Graph status: {step.name}"))
+
+    # ---- entering and leaving -----------------------------------------------------------------------------------
     def __enter__(self) -> "LzyWorkflow":
+        # whose workflow this is gets decided here, in the caller's thread: the coroutines run on the workflow thread
+        self._opened_inside_op = op_scope.inside_op()
         try:
-            parts = [self.owner.storage_uri]
-            if self.__user is not None:
-                parts.append(self.__user)
-            parts.extend(["lzy_runs", self.name, "inputs/"])
-            storage_uri = "/".join(parts)
-            # the op thread that opens a workflow owns it: decided here, in the caller's thread (the coroutine
-            # below runs on the workflow thread)
-            self.__nested = op_scope.inside_op()
+            if self._running:
+                raise RuntimeError("Workflow already started")
             if self.get_active() is not None:
                 raise RuntimeError("Simultaneous workflows are not supported")
-            self.__execution_id = LzyEventLoop.run_async(self.__start())
-            self.__activate(self)
-            self.__snapshot = self.owner.make_snapshot(self, storage_uri)
-            return self
+            self._execution = LzyEventLoop.run_async(self.owner.runtime.start(self))
+            self._running = True
+            self._mark_active(True)
+            where = [self.owner.storage_uri] + ([] if self._user is None else [self._user])
+            self._snapshot = self.owner.make_snapshot(self, "/".join(where + ["lzy_runs", self.name, "inputs/"]))
         except Exception:
-            try:
-                self.__abort()
-            finally:
-                raise
+            self._leave(aborting=True)
+            raise
+        return self
 
     def __exit__(self, exc_type, exc_val, exc_tb) -> None:
+        if not self._running:
+            self.log.warning("Exiting workflow that has not been started")
+            return
+        failure = exc_val
+        if failure is None:
+            try:
+                self.barrier()
+            except Exception as e:  # pylint: disable=broad-exception-caught
+                failure = e
         try:
-            if not self.__started:
-                self.log.warning("Exiting workflow that has not been started")
-                return
-            if exc_val is None:
-                try:
-                    self.barrier()
-                except Exception as e:  # pylint: disable=broad-exception-caught
-                    exc_val = e
+            self._leave(aborting=failure is not None)
         finally:
-            if exc_val is None:
-                self.__destroy()
-            else:
-                try:
-                    self.__abort()
-                finally:
-                    raise exc_val
+            if failure is not None:
+                raise failure
 
-    def __activate(self, workflow: Optional["LzyWorkflow"]) -> None:
-        if self.__nested:
-            op_scope.set_workflow(workflow)
+    def _leave(self, aborting: bool) -> None:
+        if not self._running:
+            # nothing of this workflow is running, so the runtime is left alone (pylzy/tests/api/v1/
+            # test_remote_runtime.py:65-76: "should NOT be aborted if not started") — in particular a refused
+            # second workflow does not take down the one that is active
+            return
+        runtime = self.owner.runtime
+        try:
+            LzyEventLoop.run_async(runtime.abort() if aborting else runtime.finish())
+        finally:
+            self._mark_active(False)
+            self._running = False
+
+    # ---- storage URIs of results ---------------------------------------------------------------------------------
+    def _assign_uris(self, call: "LzyCall") -> None:
+        storage, ops_dir = self.owner.storage_uri, f"lzy_runs/{self.name}/ops/{call.callable_name}"
+        per_call = f"{storage}/{ops_dir}/{call.id}"
+        if call.cache:
+            hash_of = lambda eid: self.snapshot.get(eid).data_hash  # noqa: E731
+            inputs = [hash_of(eid) for eid in call.arg_entry_ids]
+            inputs += [f"{name}:{hash_of(call.kwarg_entry_ids[name])}" for name in sorted(call.kwargs)]
+            results_at = "/".join(filter(None, [storage, self._user, ops_dir, call.version, "_".join(inputs)]))
         else:
-            self.set_active(workflow)
-
-    def __abort(self):
-        if not self.__started:
-            # nothing of this workflow is running: the runtime is left alone (pylzy/tests/api/v1/test_remote_runtime.py
-            # :65-76, "should NOT be aborted if not started") — in particular a refused second workflow does not
-            # take down the one that is active
-            return
-        try:
-            LzyEventLoop.run_async(self.owner.runtime.abort())
-        finally:
-            self.__activate(None)
-            self.__started = False
-
-    def __destroy(self):
-        try:
-            LzyEventLoop.run_async(self.owner.runtime.finish())
-        finally:
-            self.__activate(None)
-            self.__started = False
-
-    async def __start(self) -> str:
-        if self.__started:
-            raise RuntimeError("Workflow already started")
-        workflow_id = await self.owner.runtime.start(self)
-        self.__started = True
-        return workflow_id
-
-    async def _barrier(self) -> None:
-        if not self.__call_queue:
-            return
-        for call in self.__call_queue:
-            if call.cache:
-                self.__gen_results_uri_in_cache(call)
-            else:
-                self.__gen_results_uri_skip_cache(call)
-        queue, self.__call_queue = self.__call_queue, []
-        try:
-            await self.owner.runtime.exec(queue, lambda x: self.log.info(f"Graph status: {x.name}"))
-        except BaseException:
-            # the reference leaves the queue intact when exec raises (the assignment below it is never
-            # reached, workflow.py:230-234) and the workflow is aborted by __exit__; same net effect
-            self.__call_queue = []
-            raise
-
-    def __gen_results_uri_in_cache(self, call: "LzyCall"):
-        args_hashes = [self.snapshot.get(eid).data_hash for eid in call.arg_entry_ids]
-        kwargs_hashes = [f"{name}:{self.snapshot.get(call.kwarg_entry_ids[name]).data_hash}" for name in sorted(call.kwargs.keys())]
-        inputs_hashes_concat = "_".join([*args_hashes, *kwargs_hashes])
-        parts = [self.owner.storage_uri, self.__user or "", "lzy_runs", self.name, "ops", call.callable_name, call.version,
-                 inputs_hashes_concat]
-        uri_prefix = "/".join(filter(bool, parts))
+            results_at = per_call
         for i, eid in enumerate(call.entry_ids):
-            if eid not in self.__filled_entry_ids:
-                entry = self.snapshot.get(eid)
-                entry.storage_uri = uri_prefix + f"/return_{i}"
-                entry.data_hash = md5_of_str(entry.storage_uri)
-                self.__filled_entry_ids.add(eid)
-        self.__fill_exception_entry(call)
+            self._place(eid, f"{results_at}/return_{i}")
+        self._place(call.exception_id, f"{per_call}/exception")
 
-    def __gen_results_uri_skip_cache(self, call: "LzyCall"):
-        for i, eid in enumerate(call.entry_ids):
-            if eid not in self.__filled_entry_ids:
-                entry = self.snapshot.get(eid)
-                entry.storage_uri = f"{self.owner.storage_uri}/lzy_runs/{self.name}/ops/{call.callable_name}/{call.id}/return_{i}"
-                entry.data_hash = md5_of_str(entry.storage_uri)
-                self.__filled_entry_ids.add(eid)
-        self.__fill_exception_entry(call)
-
-    def __fill_exception_entry(self, call: "LzyCall"):
-        eid = call.exception_id
-        if eid not in self.__filled_entry_ids:
-            entry = self.snapshot.get(eid)
-            entry.storage_uri = f"{self.owner.storage_uri}/lzy_runs/{self.name}/ops/{call.callable_name}/{call.id}/exception"
-            entry.data_hash = md5_of_str(entry.storage_uri)
-            self.__filled_entry_ids.add(eid)
+    def _place(self, entry_id: str, uri: str) -> None:
+        if entry_id in self._uri_assigned:
+            return
+        entry = self.snapshot.get(entry_id)
+        entry.storage_uri = uri
+        entry.data_hash = md5_of_str(uri)
+        self._uri_assigned.add(entry_id)
