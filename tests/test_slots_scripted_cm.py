@@ -280,3 +280,29 @@ def test_unknown_slots_and_double_start_transfer(env):
     assert [r["transfer_id"] for r in cm.made("completed")] == ["t-1"]
     inp.close()
     out.close()
+
+
+def test_close_is_idempotent_and_ignores_unbind_errors(env):
+    """OutputSlot.close / InputSlot.close (OutputSlot.java:90-133, InputSlot.java:195-221): Unbind failures are
+    swallowed, the backing frames are released all the same (the fixture checks for leaks), a second close is a
+    no-op and makes no second Unbind."""
+    cm, slots, _ = env
+    cm.on_unbind("2").complete_exceptionally("channel is gone", N.E_NOT_FOUND)
+    cm.on_unbind("1").complete_exceptionally("try later", N.E_UNAVAILABLE)
+    out = slots.context("exec", "a")
+    out.add_slot("2", "chan", DIR_OUTPUT)
+    out.before_execution()
+    produce(out, "2", b"Hello")
+    out.after_execution(5000)
+    inp = slots.context("exec", "b")
+    inp.add_slot("1", "chan", DIR_INPUT)
+    inp.prefetch()
+    wait_for(lambda: inp.input_state("1") == H.IS_WAITING_FOR_PEER)
+    inp.close()  # while still waiting for a peer
+    out.close()
+    inp.close()
+    out.close()
+    assert sorted(r["peer_id"] for r in cm.made("unbind")) == ["1", "2"]
+    with pytest.raises(GrpcStatusError) as e:
+        slots.read("2", 0)
+    assert e.value.status == "NOT_FOUND"  # unregistered from the slots server
