@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -328,6 +329,73 @@ struct Completion {
     }
 };
 
+// ---- slot threads ----------------------------------------------------------------------------------------
+// Every slot runs its state machine on a thread of its own, as in the reference (InputSlot and OutputSlot.PrepareThread
+// are Threads): it may block for as long as it likes — waiting for a peer, for the op to finish its output.  The
+// threads are recycled: one that has finished a slot waits a little for the next slot instead of being created anew
+// (two creations + joins per op otherwise).  The pool grows on demand and is never destroyed: its idle threads may
+// outlive main().
+class SlotThreads {
+public:
+    struct Ticket {
+        std::mutex mu;
+        std::condition_variable cv;
+        bool done = false;
+        void wait() {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return done; });
+        }
+    };
+    using TicketPtr = std::shared_ptr<Ticket>;
+
+    TicketPtr run(std::function<void()> body) {
+        auto ticket = std::make_shared<Ticket>();
+        bool spawn;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            queue_.emplace_back(std::move(body), ticket);
+            spawn = queue_.size() > (size_t)idle_;
+            if (!spawn) cv_.notify_one();
+        }
+        if (spawn) std::thread([this] { serve(); }).detach();
+        return ticket;
+    }
+
+private:
+    void serve() {
+        for (;;) {
+            std::pair<std::function<void()>, TicketPtr> job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                if (queue_.empty()) {
+                    ++idle_;
+                    bool got = cv_.wait_for(lk, std::chrono::seconds(2), [&] { return !queue_.empty(); });
+                    --idle_;
+                    if (!got) return;
+                }
+                job = std::move(queue_.front());
+                queue_.pop_front();
+            }
+            job.first();
+            job.first = nullptr;  // drop what the body captured (the slot) before announcing the end
+            {
+                std::lock_guard<std::mutex> lk(job.second->mu);
+                job.second->done = true;
+            }
+            job.second->cv.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::pair<std::function<void()>, TicketPtr>> queue_;
+    int idle_ = 0;
+};
+
+SlotThreads& slot_threads() {
+    static SlotThreads* pool = new SlotThreads;
+    return *pool;
+}
+
 struct SlotsInstance;
 struct ExecCtx;
 
@@ -427,11 +495,7 @@ struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
     std::mutex mu;
     std::condition_variable cv;
     bool data_done = false, closed = false;
-    std::thread prepare;
-
-    ~OutputSlotImpl() override {
-        if (prepare.joinable()) prepare.detach();
-    }
+    SlotThreads::TicketPtr prepare;  // PrepareThread
     bool is_input() const override { return false; }
     Completion& before() override { return before_; }
     Completion& after() override { return complete_; }
@@ -450,7 +514,7 @@ struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
     void start() {
         before_.complete();
         auto self = shared_from_this();
-        prepare = std::thread([self] { self->run(); });
+        prepare = slot_threads().run([self] { self->run(); });
     }
 
     void signal_data_done() {
@@ -543,7 +607,7 @@ struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
     }
 
     void join() override {
-        if (prepare.joinable()) prepare.join();
+        if (prepare) prepare->wait();
     }
 };
 
@@ -648,11 +712,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
     bool have_peer = false, closed = false, handed_over = false;
     lzyb_peer_desc_t peer{};
     std::string transfer_id;
-    std::thread thr;
-
-    ~InputSlotImpl() override {
-        if (thr.joinable()) thr.detach();
-    }
+    SlotThreads::TicketPtr thr;
     bool is_input() const override { return true; }
     Completion& before() override { return ready_; }
     Completion& after() override { return after_; }
@@ -674,7 +734,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
     void start() {
         after_.complete();
         auto self = shared_from_this();
-        thr = std::thread([self] {
+        thr = slot_threads().run([self] {
             std::string err;
             if (!self->run(err)) self->ready_.fail_with(err.empty() ? "Closed before ready" : err);
             self->clear();
@@ -941,7 +1001,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
     }
 
     void join() override {
-        if (thr.joinable()) thr.join();
+        if (thr) thr->wait();
     }
 
     void release_frame() {

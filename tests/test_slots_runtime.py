@@ -58,6 +58,11 @@ def test_simple_producer_then_consumer(env):
     inp.before_execution(5000)
     assert hostmem.peek(inp.input_handle("1"), 5) == b"Hello"
     inp.after_execution(5000)  # waits for the "1-out" companion to be bound
+    # the consumer peer is unbound by the input slot's own thread once it is done (InputSlot.clear(), InputSlot.java
+    # :195-221) — not ordered against afterExecution(), in the reference either
+    deadline = time.time() + 5
+    while cm.channels_status("exec", [chan])[0]["consumers"] and time.time() < deadline:
+        time.sleep(0.002)
     st = cm.channels_status("exec", [chan])[0]
     producers = sorted(p["peer_id"] for p in st["producers"] if p["kind"] == "slot")
     assert producers == ["1-out", "2"] and st["consumers"] == []
