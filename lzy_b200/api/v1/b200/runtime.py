@@ -495,17 +495,17 @@ class B200Runtime(Runtime):
             kwargs = {k: arg(e) for k, e in call.kwarg_entry_ids.items()}
             func = call.signature.func.callable
             stream = self._streams[gpu]
-            op_scope.enter()
-            try:
-                with torch.cuda.device(gpu), torch.cuda.stream(stream), applied_env(call.get_env_vars()):
-                    res = func(*args, **kwargs)
-            finally:
-                op_scope.leave()
-
-            mark("load+op")
-            outs = call.entry_ids
-            results = [res] if len(outs) == 1 else list(res)
+            # one device / stream scope for the body and the packing of its results (entering it costs tens of µs)
             with torch.cuda.device(gpu), torch.cuda.stream(stream):
+                op_scope.enter()
+                try:
+                    with applied_env(call.get_env_vars()):
+                        res = func(*args, **kwargs)
+                finally:
+                    op_scope.leave()
+                mark("load+op")
+                outs = call.entry_ids
+                results = [res] if len(outs) == 1 else list(res)
                 sp = current_stream_ptr(gpu)
                 for eid, data in zip(outs, results):
                     entry = snapshot.get(eid)
