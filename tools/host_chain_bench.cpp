@@ -41,12 +41,14 @@ struct Phase {
 int main(int argc, char** argv) {
     const int steps = argc > 1 ? atoi(argv[1]) : 2000, n_ops = argc > 2 ? atoi(argv[2]) : 8;
     const bool prefetch = argc > 3 ? atoi(argv[3]) != 0 : true;
+    const bool republish = argc > 4 ? atoi(argv[4]) != 0 : false;  // "<slot>-out" companions: off in B200Runtime's default
     lzyb_slots_set_backend(&hostmem_backend_ops);
     lzyb_handle_t cm = 0, slots = 0;
     CHECK(lzyb_cm_create(&cm));
     CHECK(lzyb_cm_seed(cm, 7));
     CHECK(lzyb_cm_pump_start(cm));
     CHECK(lzyb_slots_create(cm, 0, "lzyb://worker-0", &slots));
+    CHECK(lzyb_slots_set_republish(slots, republish ? 1 : 0));
     const char payload[256] = "x";
     using clk = std::chrono::steady_clock;
     clk::time_point t0;
@@ -119,7 +121,7 @@ int main(int argc, char** argv) {
     lzyb_slots_free(slots);
     lzyb_cm_pump_stop(cm);
     lzyb_cm_free(cm);
-    printf("{\"steps\": %d, \"ops_per_step\": %d, \"prefetch\": %s, \"us_per_op\": %.1f, \"live_slots\": %d}\n", steps, n_ops,
-           prefetch ? "true" : "false", us / steps / n_ops, hostmem_live_slots());
+    printf("{\"steps\": %d, \"ops_per_step\": %d, \"prefetch\": %s, \"republish\": %s, \"us_per_op\": %.1f, \"live_slots\": %d}\n", steps,
+           n_ops, prefetch ? "true" : "false", republish ? "true" : "false", us / steps / n_ops, hostmem_live_slots());
     return 0;
 }
