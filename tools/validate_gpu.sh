@@ -16,3 +16,5 @@ print("bench:", round(r["value"], 1), r["unit"], "| ms/step", round(r["ms_per_st
       "| e2e", round(r["e2e"]["value"], 1), "| launches", r["gpu_launches"], "| clocks", r["clocks"]["sm_mhz"], r["clocks"]["reasons"])
 PY
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | cut -c1-200
+# per-op phase costs through the API (host changes of the previous round's tail show up here)
+LZYB_TRACE=1 timeout 200 python tools/profile_chain.py > gpurun_out/profile_chain.txt 2>&1; tail -12 gpurun_out/profile_chain.txt
