@@ -85,8 +85,10 @@ int fail(int code, const char* fmt, ...) {
 #define CU(expr)                                                                                  \
     do {                                                                                          \
         cudaError_t _e = (expr);                                                                  \
-        if (_e != cudaSuccess)                                                                    \
+        if (_e != cudaSuccess) {                                                                  \
+            cudaGetLastError(); /* reported here: do not leave it for this thread's next launch check */ \
             return fail(LZYB_E_LOCAL, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                         \
     } while (0)
 
 struct DeviceGuard {
