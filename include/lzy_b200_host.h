@@ -259,6 +259,9 @@ int64_t lzyb_slots_transfer_log(lzyb_handle_t slots, char* json_out, uint64_t ca
 /* republish delivered inputs as "<slot>-out" producers (InputSlot.java:160-168); default on.  The
  * Python runtime turns it off so that an op owns its input frame and may mutate it in place. */
 int lzyb_slots_set_republish(lzyb_handle_t slots, int on);
+/* observability: how many OS threads the slot state machines have created so far in this process (they are recycled:
+ * a finished slot's thread serves the next slot, so this stays near the peak number of slots blocked at once) */
+uint64_t lzyb_slots_threads_spawned(void);
 
 /* ---- graph dispatch -------------------------------------------------------------------------- */
 /* Replaces BfsGraphProcessor + Algorithms (lzy/graph-executor/.../exec/BfsGraphProcessor.java:44-258,

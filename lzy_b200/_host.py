@@ -79,6 +79,7 @@ _SIGS = {
     "lzyb_blob_size": (C.c_int64, [_s]),
     "lzyb_blob_get": (C.c_int64, [_s, C.c_void_p, C.c_uint64]),
     "lzyb_blob_delete": (_i, [_s]),
+    "lzyb_slots_threads_spawned": (C.c_uint64, []),
     "lzyb_slots_set_cm_client": (_i, [C.c_void_p]),
     "lzyb_slots_set_peer_resolver": (_i, [C.c_void_p]),
     "lzyb_slots_describe": (_i, [_H, _s, C.c_void_p]),

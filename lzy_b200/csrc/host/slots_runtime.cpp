@@ -357,9 +357,13 @@ public:
             spawn = queue_.size() > (size_t)idle_;
             if (!spawn) cv_.notify_one();
         }
-        if (spawn) std::thread([this] { serve(); }).detach();
+        if (spawn) {
+            ++spawned_;
+            std::thread([this] { serve(); }).detach();
+        }
         return ticket;
     }
+    uint64_t spawned() const { return spawned_.load(); }
 
 private:
     void serve() {
@@ -389,6 +393,7 @@ private:
     std::condition_variable cv_;
     std::deque<std::pair<std::function<void()>, TicketPtr>> queue_;
     int idle_ = 0;
+    std::atomic<uint64_t> spawned_{0};
 };
 
 SlotThreads& slot_threads() {
@@ -1172,6 +1177,8 @@ int lzyb_slots_set_backend(const lzyb_backend_ops_t* o) {
     g_ops = &g_custom_ops;
     return LZYB_OK;
 }
+
+uint64_t lzyb_slots_threads_spawned(void) { return slot_threads().spawned(); }
 
 int lzyb_slots_set_peer_resolver(lzyb_peer_resolver_t resolver) {
     g_peer_resolver = resolver;

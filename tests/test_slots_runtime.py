@@ -448,3 +448,33 @@ def test_transfer_log_records_bytes_time_source_and_failovers(env):
     (rec,) = slots.transfer_log()
     assert not rec["ok"] and rec["slot_id"] == "/log/in3" and "No more producers" in rec["error"]
     lost.close()
+
+
+def _os_threads() -> int:
+    with open("/proc/self/status") as f:
+        return next(int(line.split()[1]) for line in f if line.startswith("Threads:"))
+
+
+def test_slot_threads_are_recycled(env):
+    """every slot has a thread to block on, but a finished slot's thread serves the next slot: a long run of ops
+    does not create a thread per slot (host/slots_runtime.cpp: SlotThreads)"""
+    cm, slots, _ = env
+    seen = []
+    spawned_before = H.lib.lzyb_slots_threads_spawned()
+    for k in range(150):
+        chan = cm.get_or_create("u", "wf", "exec", consumer_uri=f"hbm://recycle/{k}")
+        out = slots.context("exec", f"p{k}")
+        out.add_slot(f"/p{k}/out", chan, DIR_OUTPUT)
+        out.before_execution()
+        produce(out, f"/p{k}/out", b"payload")
+        out.after_execution(5000)
+        inp = slots.context("exec", f"c{k}")
+        inp.add_slot(f"/c{k}/in", chan, DIR_INPUT)
+        inp.before_execution(5000)
+        assert hostmem.peek(inp.input_handle(f"/c{k}/in"), 7) == b"payload"
+        inp.close()
+        out.close()
+        seen.append(_os_threads())
+    H.frame_store_clear("hbm://recycle/")
+    assert max(seen[50:]) <= max(seen[:50]) + 2, f"thread count keeps growing: {seen[:5]} … {seen[-5:]}"
+    assert H.lib.lzyb_slots_threads_spawned() - spawned_before <= 8, "300 slots ran on a handful of threads"
