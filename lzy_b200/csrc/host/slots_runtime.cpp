@@ -16,6 +16,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -354,7 +355,7 @@ public:
         {
             std::lock_guard<std::mutex> lk(mu_);
             queue_.emplace_back(std::move(body), ticket);
-            spawn = queue_.size() > (size_t)idle_;
+            spawn = one_shot_ || queue_.size() > (size_t)idle_;
             if (!spawn) cv_.notify_one();
         }
         if (spawn) {
@@ -372,6 +373,7 @@ private:
             {
                 std::unique_lock<std::mutex> lk(mu_);
                 if (queue_.empty()) {
+                    if (one_shot_) return;
                     ++idle_;
                     bool got = cv_.wait_for(lk, std::chrono::seconds(2), [&] { return !queue_.empty(); });
                     --idle_;
@@ -394,6 +396,11 @@ private:
     std::deque<std::pair<std::function<void()>, TicketPtr>> queue_;
     int idle_ = 0;
     std::atomic<uint64_t> spawned_{0};
+    // LZYB_SLOT_THREADS=fresh: a new thread per slot, as before the pool (for A/B measurements)
+    const bool one_shot_ = [] {
+        const char* v = getenv("LZYB_SLOT_THREADS");
+        return v && strcmp(v, "fresh") == 0;
+    }();
 };
 
 SlotThreads& slot_threads() {

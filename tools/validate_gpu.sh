@@ -18,3 +18,5 @@ PY
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | cut -c1-200
 # per-op phase costs through the API (host changes of the previous round's tail show up here)
 LZYB_TRACE=1 timeout 200 python tools/profile_chain.py > gpurun_out/profile_chain.txt 2>&1; tail -12 gpurun_out/profile_chain.txt
+# A/B of the recycled slot threads (LZYB_SLOT_THREADS=fresh = one new thread per slot, as before)
+LZYB_SLOT_THREADS=fresh LZYB_TRACE=1 timeout 200 python tools/profile_chain.py > gpurun_out/profile_chain_fresh_threads.txt 2>&1; tail -4 gpurun_out/profile_chain_fresh_threads.txt
