@@ -13,7 +13,8 @@ python - <<'PY'
 import json
 r = json.load(open("gpurun_out/bench.json"))
 print("bench:", round(r["value"], 1), r["unit"], "| ms/step", round(r["ms_per_step"], 3), "| roofline frac", round(r["roofline"]["frac"], 4),
-      "| e2e", round(r["e2e"]["value"], 1), "| launches", r["gpu_launches"], "| clocks", r["clocks"]["sm_mhz"], r["clocks"]["reasons"])
+      "| e2e", round(r["e2e"]["value"], 1), "| e2e duplex", (r["e2e"].get("duplex") or {}).get("value"),
+      "| launches", r["gpu_launches"], "| clocks", r["clocks"]["sm_mhz"], r["clocks"]["reasons"])
 PY
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | cut -c1-200
 # per-op phase costs through the API (host changes of the previous round's tail show up here)
