@@ -148,3 +148,49 @@ def test_array_stream_form_round_trips_dtype_shape_and_bytes(dtype, shape, seed)
     buf.seek(0)
     tback = tser.deserialize(buf, torch.Tensor)
     assert tback.dtype == t.dtype and tuple(tback.shape) == tuple(t.shape) and torch.equal(tback, t)
+
+
+# ---- argument binding agrees with Python's own -----------------------------------------------------------------------
+@settings(max_examples=200, deadline=None)
+@given(st.integers(0, 3), st.integers(0, 3), st.booleans(), st.booleans(), st.integers(0, 5),
+       st.lists(st.sampled_from(["p0", "p1", "p2", "zz"]), unique=True, max_size=3))
+def test_call_binding_accepts_exactly_what_python_would(n_params, n_defaults, varargs, varkw, n_args, kw_names):
+    """the arity rules of infer_and_validate_call_signature (pylzy/lzy/core/call.py:266-287: KeyError for a missing,
+    an unexpected positional or an unknown keyword argument) against inspect.Signature.bind on generated functions;
+    a parameter given both ways is left to the op's own call, as in the reference"""
+    import inspect
+    from types import SimpleNamespace
+
+    from lzy_b200.core.call import infer_and_validate_call_signature
+    from lzy_b200.serialization.registry import LzySerializerRegistry
+
+    n_defaults = min(n_defaults, n_params)
+    params = [f"p{i}: int" + (" = 0" if i >= n_params - n_defaults else "") for i in range(n_params)]
+    if varargs:
+        params.append("*rest")
+    if varkw:
+        params.append("**named")
+    scope: dict = {}
+    exec(f"def f({', '.join(params)}) -> int:\n    return 0\n", scope)
+    f = scope["f"]
+    args = tuple(range(n_args))
+    kwargs = {name: 1 for name in kw_names}
+    if any(name in [f"p{i}" for i in range(min(n_args, n_params))] for name in kwargs):
+        return  # given both positionally and by name
+    try:
+        inspect.signature(f).bind(*args, **kwargs)
+        python_accepts = True
+    except TypeError:
+        python_accepts = False
+    snapshot = SimpleNamespace(get=lambda eid: None)
+    try:
+        sig = infer_and_validate_call_signature(f, *args, output_type=(int,), snapshot=snapshot,
+                                                serializer_registry=LzySerializerRegistry(), **kwargs)
+        ours_accepts = True
+    except KeyError:
+        ours_accepts = False
+    assert ours_accepts == python_accepts, (params, args, kwargs)
+    if ours_accepts:
+        assert sig.args == args and sig.kwargs == kwargs
+        assert len(sig.func.arg_names) == n_args and list(sig.func.arg_names[:n_params]) == [f"p{i}" for i in range(min(n_args, n_params))]
+        assert set(sig.func.input_types) == set(sig.func.arg_names) | set(kwargs)
