@@ -194,3 +194,58 @@ def test_call_binding_accepts_exactly_what_python_would(n_params, n_defaults, va
         assert sig.args == args and sig.kwargs == kwargs
         assert len(sig.func.arg_names) == n_args and list(sig.func.arg_names[:n_params]) == [f"p{i}" for i in range(min(n_args, n_params))]
         assert set(sig.func.input_types) == set(sig.func.arg_names) | set(kwargs)
+
+
+# ---- the dataflow planner ------------------------------------------------------------------------------------------
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.tuples(st.booleans(), st.lists(st.integers(0, 6), unique=True, max_size=3)), max_size=8),
+       st.sets(st.integers(0, 6), max_size=3))
+def test_dataflow_plan_invariants(call_specs, stored):
+    """lzy-service DataFlowGraph.java:51-72 as invariants: one supplier per URI; a dropped duplicate's results all
+    point at kept suppliers of the very same URIs; cached calls are exactly the cache=True calls whose results are
+    all stored; order of the kept calls is submission order; partial overlaps are refused"""
+    from types import SimpleNamespace
+
+    from lzy_b200.core.dataflow import plan_dataflow
+
+    uri_of, calls = {}, []
+    for i, (cache, uris) in enumerate(call_specs):
+        eids = []
+        for j, u in enumerate(uris):
+            eid = f"c{i}e{j}"
+            uri_of[eid] = f"uri-{u}"
+            eids.append(eid)
+        calls.append(SimpleNamespace(cache=cache, entry_ids=eids, n=i))
+    exists = lambda u: int(u.split("-")[1]) in stored  # noqa: E731
+
+    # what must happen, restated naively
+    supplied, expect_error = set(), False
+    for c in calls:
+        us = [uri_of[e] for e in c.entry_ids]
+        if c.cache and us and all(exists(u) for u in us):
+            continue
+        if us and all(u in supplied for u in us):
+            continue
+        if any(u in supplied for u in us):
+            expect_error = True
+            break
+        supplied.update(us)
+    if expect_error:
+        with pytest.raises(RuntimeError, match="already exists"):
+            plan_dataflow(calls, uri_of.__getitem__, exists)
+        return
+
+    plan = plan_dataflow(calls, uri_of.__getitem__, exists)
+    assert sorted(c.n for c in plan.calls + plan.cached + plan.duplicates) == list(range(len(calls)))
+    assert [c.n for c in plan.calls] == sorted(c.n for c in plan.calls)
+    for c in plan.cached:
+        assert c.cache and c.entry_ids and all(exists(uri_of[e]) for e in c.entry_ids)
+    kept_uris = [uri_of[e] for c in plan.calls for e in c.entry_ids]
+    assert len(kept_uris) == len(set(kept_uris)), "two suppliers for one URI"
+    for i, c in enumerate(plan.calls):
+        assert all(plan.supplier[e] == i for e in c.entry_ids)
+    for d in plan.duplicates:
+        for e in d.entry_ids:
+            supplier = plan.calls[plan.supplier[e]]
+            assert uri_of[e] in {uri_of[x] for x in supplier.entry_ids} and supplier.n < d.n
+            assert e in plan.outputs_of(plan.supplier[e])
