@@ -249,3 +249,57 @@ def test_dataflow_plan_invariants(call_specs, stored):
             supplier = plan.calls[plan.supplier[e]]
             assert uri_of[e] in {uri_of[x] for x in supplier.entry_ids} and supplier.n < d.n
             assert e in plan.outputs_of(plan.supplier[e])
+
+
+# ---- who keeps a frame alive -----------------------------------------------------------------------------------------
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.tuples(st.sampled_from(["put", "pin", "unpin", "produce", "persist"]), st.integers(0, 3)), max_size=40))
+def test_frame_snapshot_holds_exactly_what_somebody_can_still_ask_for(script):
+    """FrameSnapshot's bookkeeping under arbitrary interleavings: a frame is referenced by each entry that holds it
+    (once), never by an entry that is unpinned and not persistent, never released twice; equal local data shares one
+    frame with one reference per entry"""
+    import asyncio
+
+    from lzy_b200.api.v1.snapshot import FrameSnapshot
+    from lzy_b200.serialization.registry import LzySerializerRegistry
+    from tests.test_frame_snapshot import DictStore
+
+    store = DictStore()
+    snap = FrameSnapshot(LzySerializerRegistry(), "hbm://p/", store)
+    entries = [snap.create_entry(f"e{i}", int) for i in range(4)]
+    pins, held, has_data, persistent = [0] * 4, [False] * 4, [False] * 4, [False] * 4
+
+    def let_go_if_unwanted(i):  # the model of FrameSnapshot._maybe_release
+        if held[i] and pins[i] == 0 and not persistent[i]:
+            held[i] = False
+
+    for action, i in script:
+        e = entries[i]
+        if action == "put" and not has_data[i]:
+            asyncio.run(snap.put_data(e.id, i % 2))  # entries 0/2 and 1/3 carry equal data
+            has_data[i] = held[i] = True
+        elif action == "produce" and not has_data[i]:
+            e.storage_uri = f"hbm://results/{i}"
+            store.data[e.storage_uri] = i
+            snap.produced(e.id)
+            has_data[i] = held[i] = True
+            let_go_if_unwanted(i)  # a result nobody waits for goes as soon as it exists
+        elif action == "pin":
+            snap.pin(e.id)
+            pins[i] += 1
+        elif action == "unpin" and pins[i] > 0:
+            snap.unpin(e.id)
+            pins[i] -= 1
+            let_go_if_unwanted(i)
+        elif action == "persist":
+            snap.persist(e.id)
+            persistent[i] = True
+        else:
+            continue
+        holding = {}
+        for j, ent in enumerate(entries):
+            if held[j]:
+                holding[ent._storage_uri] = holding.get(ent._storage_uri, 0) + 1
+        assert store.refs == holding, (action, i, store.refs, holding)
+        for uri in holding:
+            assert store.exists(uri), "a frame somebody still holds was dropped"
