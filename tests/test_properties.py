@@ -303,3 +303,37 @@ def test_frame_snapshot_holds_exactly_what_somebody_can_still_ask_for(script):
         assert store.refs == holding, (action, i, store.refs, holding)
         for uri in holding:
             assert store.exists(uri), "a frame somebody still holds was dropped"
+
+
+def test_applied_env_under_contention():
+    """ops of one worker share a process: while an op runs, the variables it declared have its values — whatever the
+    other ops declare — and everything is restored afterwards; no schedule deadlocks (all of an op's variables are
+    taken in one step)"""
+    import os
+    import random
+    import threading
+
+    from lzy_b200.env import applied_env
+
+    names = ["LZYB_T_A", "LZYB_T_B", "LZYB_T_C"]
+    os.environ["LZYB_T_C"] = "outer"
+    errors = []
+
+    def worker(seed):
+        rnd = random.Random(seed)
+        for _ in range(120):
+            wanted = {n: rnd.choice(["1", "2"]) for n in names if rnd.random() < 0.6}
+            with applied_env(wanted):
+                for _ in range(3):
+                    seen = {n: os.environ.get(n) for n in wanted}
+                    if seen != wanted:
+                        errors.append((wanted, seen))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    assert not any(t.is_alive() for t in threads), "deadlock"
+    assert errors == []
+    assert os.environ.pop("LZYB_T_C") == "outer" and "LZYB_T_A" not in os.environ and "LZYB_T_B" not in os.environ
