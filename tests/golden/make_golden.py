@@ -10,6 +10,8 @@
   stubs are absent), so the modules are loaded by file path.
 * reference_proxy_vectors.json — answers of the reference's own lazy proxy (pylzy/lzy/proxy/automagic.py, loaded
   by file path) to the probes of tests/golden/proxy_battery.py; tests/test_lazy_proxy.py holds ours to them.
+* reference_types_vectors.json — answers of the reference's own annotation helpers (pylzy/lzy/api/v1/utils/types.py) to the
+  questions of tests/golden/types_battery.py; tests/test_call_signatures.py holds ours to them.
 * reference_pickle_vectors.json — what the reference's request encoding (pylzy/lzy/api/v1/utils/pickle.py) emits
   for a few objects; ours must decode them and encode the same text.
 * digest_vectors.json — known answers of the data plane's digest from the oracle's C restatement
@@ -81,6 +83,24 @@ def main():
     automagic = load(REF / "lzy/proxy/automagic.py", "ref_automagic")
     answers = json.loads(json.dumps(proxy_battery.run(automagic.proxy), default=str))
     (ROOT / "tests/golden/reference_proxy_vectors.json").write_text(json.dumps(answers, indent=1, sort_keys=True))
+
+    # the annotation helpers: the reference's own module, its absent third party `serialzy` replaced by two-name stubs
+    # (the helpers only name SerializerRegistry in a signature and compare against EmptyContent)
+    serialzy_stub, api_stub, types_stub = types.ModuleType("serialzy"), types.ModuleType("serialzy.api"), types.ModuleType("serialzy.types")
+    api_stub.SerializerRegistry = type("SerializerRegistry", (), {})
+    types_stub.EmptyContent = type("EmptyContent", (), {})
+    sys.modules.update({"serialzy": serialzy_stub, "serialzy.api": api_stub, "serialzy.types": types_stub})
+    ref_types = load(REF / "lzy/api/v1/utils/types.py", "ref_types")
+    ref_result = load(REF / "lzy/proxy/result.py", "ref_result")
+    from lzy.proxy.result import Absence as RefAbsence, Result as RefResult  # the classes ref_types itself imported
+    types_battery = load(ROOT / "tests/golden/types_battery.py", "types_battery")
+    answers = types_battery.run(dict(
+        infer_real_types=ref_types.infer_real_types, infer_return_type=ref_types.infer_return_type,
+        get_default_args=ref_types.get_default_args, is_subtype=ref_types.is_subtype,
+        check_types_serialization_compatible=ref_types.check_types_serialization_compatible,
+        EmptyContent=types_stub.EmptyContent, Absence=RefAbsence, Result=RefResult))
+    del ref_result
+    (ROOT / "tests/golden/reference_types_vectors.json").write_text(json.dumps(answers, indent=1, sort_keys=True))
 
     ref_pickle = load(REF / "lzy/api/v1/utils/pickle.py", "ref_pickle")
     objs = [None, 42, -1.5, "ʎzy", b"\x00\xff", [1, "two", 3.0], {"k": (1, 2), "n": None}, (str, "/call/entry"), {1, 2, 3}]

@@ -222,3 +222,28 @@ def test_outside_a_workflow_and_bad_declarations(lzy):
     with pytest.raises(ValueError, match="Invalid workflow name. Name can contain only"):
         with lzy.workflow("test test"):
             pass
+
+
+def test_annotation_helpers_answer_as_the_reference_module_does():
+    """tests/golden/reference_types_vectors.json holds what pylzy/lzy/api/v1/utils/types.py itself (executed in the
+    authoring container, tests/golden/make_golden.py) answers to tests/golden/types_battery.py: real types of unions
+    and generics, declared return types, defaults, the subtype relation with the empty-container rule, and whether
+    the serializer picked for an annotation takes a runtime type"""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    from lzy_b200.api.v1.utils import types as T
+    from lzy_b200.proxy_result import Absence, Result
+    from lzy_b200.serialization.types import EmptyContent
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("types_battery", golden / "types_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+    ours = battery.run(dict(
+        infer_real_types=T.infer_real_types, infer_return_type=T.infer_return_type, get_default_args=T.get_default_args,
+        is_subtype=T.is_subtype, check_types_serialization_compatible=T.check_types_serialization_compatible,
+        EmptyContent=EmptyContent, Absence=Absence, Result=Result))
+    reference = json.loads((golden / "reference_types_vectors.json").read_text())
+    assert json.loads(json.dumps(ours)) == reference
