@@ -12,6 +12,9 @@
   by file path) to the probes of tests/golden/proxy_battery.py; tests/test_lazy_proxy.py holds ours to them.
 * reference_types_vectors.json — answers of the reference's own annotation helpers (pylzy/lzy/api/v1/utils/types.py) to the
   questions of tests/golden/types_battery.py; tests/test_call_signatures.py holds ours to them.
+* reference_call_vectors.json — what the reference's own argument binding (pylzy/lzy/core/call.py:
+  infer_and_validate_call_signature) does with the calls of tests/golden/call_battery.py: refusals with their messages,
+  entry names, types, local data.
 * reference_pickle_vectors.json — what the reference's request encoding (pylzy/lzy/api/v1/utils/pickle.py) emits
   for a few objects; ours must decode them and encode the same text.
 * digest_vectors.json — known answers of the data plane's digest from the oracle's C restatement
@@ -101,6 +104,48 @@ def main():
         EmptyContent=types_stub.EmptyContent, Absence=RefAbsence, Result=RefResult))
     del ref_result
     (ROOT / "tests/golden/reference_types_vectors.json").write_text(json.dumps(answers, indent=1, sort_keys=True))
+
+    # argument binding: the reference's own lzy/core/call.py.  Its imports of the environment / logging / snapshot
+    # layers are stubbed (they only supply names for annotations and base classes); serialzy's get_type and
+    # EmptyContent come from this package, the same ones our side of the battery uses
+    import logging
+    from lzy_b200.serialization import types as our_types
+    from lzy_b200.serialization.registry import LzySerializerRegistry
+
+    def stub(name, **attrs):
+        module = types.ModuleType(name)
+        module.__dict__.update(attrs)
+        sys.modules[name] = module
+        return module
+
+    def load_as(path, name):
+        spec = importlib.util.spec_from_file_location(name, path)
+        module = importlib.util.module_from_spec(spec)
+        sys.modules[name] = module
+        spec.loader.exec_module(module)
+        return module
+
+    types_stub.EmptyContent, types_stub.get_type = our_types.EmptyContent, our_types.get_type
+    api_stub.Schema = type("Schema", (), {})
+    for name, attrs in {
+        "lzy.env": {}, "lzy.env.provisioning": {}, "lzy.env.provisioning.provisioning": {"Provisioning": object},
+        "lzy.env.python": {}, "lzy.env.python.base": {"ModulePathsList": list, "PackagesDict": dict},
+        "lzy.env.container": {}, "lzy.env.container.base": {"BaseContainer": object},
+        "lzy.env.environment": {"LzyEnvironment": type("LzyEnvironment", (), {}), "EnvVarsType": dict},
+        "lzy.env.mixin": {"WithEnvironmentMixin": type("WithEnvironmentMixin", (), {})},
+        "lzy.logs": {}, "lzy.logs.config": {"get_logger": logging.getLogger},
+        "lzy.api": {}, "lzy.api.v1": {}, "lzy.api.v1.snapshot": {"Snapshot": object}, "lzy.api.v1.utils": {},
+    }.items():
+        stub(name, **attrs)
+    load_as(REF / "lzy/api/v1/signatures.py", "lzy.api.v1.signatures")
+    load_as(REF / "lzy/api/v1/utils/types.py", "lzy.api.v1.utils.types")
+    ref_adapter = load_as(REF / "lzy/api/v1/utils/proxy_adapter.py", "lzy.api.v1.utils.proxy_adapter")
+    ref_call = load_as(REF / "lzy/core/call.py", "ref_call")
+    call_battery = load(ROOT / "tests/golden/call_battery.py", "call_battery")
+    bound = call_battery.run(dict(bind=ref_call.infer_and_validate_call_signature, lzy_proxy=ref_adapter.lzy_proxy,
+                                  materialize=ref_adapter.materialize, is_lzy_proxy=ref_adapter.is_lzy_proxy,
+                                  Result=RefResult, registry=LzySerializerRegistry()))
+    (ROOT / "tests/golden/reference_call_vectors.json").write_text(json.dumps(bound, indent=1, sort_keys=True))
 
     ref_pickle = load(REF / "lzy/api/v1/utils/pickle.py", "ref_pickle")
     objs = [None, 42, -1.5, "ʎzy", b"\x00\xff", [1, "two", 3.0], {"k": (1, 2), "n": None}, (str, "/call/entry"), {1, 2, 3}]

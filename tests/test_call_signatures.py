@@ -247,3 +247,30 @@ def test_annotation_helpers_answer_as_the_reference_module_does():
         EmptyContent=EmptyContent, Absence=Absence, Result=Result))
     reference = json.loads((golden / "reference_types_vectors.json").read_text())
     assert json.loads(json.dumps(ours)) == reference
+
+
+def test_argument_binding_answers_as_the_reference_function_does():
+    """tests/golden/reference_call_vectors.json: 55 calls bound by pylzy/lzy/core/call.py's own
+    infer_and_validate_call_signature (executed in the authoring container) — refusals with their exact messages,
+    the names arguments get as entries (made-up names of varargs normalised), the types recorded for them, the values
+    that travel as local data (proxies stay proxies, materialised ones become values)"""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    from lzy_b200.api.v1.utils import proxy_adapter
+    from lzy_b200.core.call import infer_and_validate_call_signature
+    from lzy_b200.proxy_result import Result
+    from lzy_b200.serialization.registry import LzySerializerRegistry
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("call_battery", golden / "call_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+    ours = battery.run(dict(bind=infer_and_validate_call_signature, lzy_proxy=proxy_adapter.lzy_proxy,
+                            materialize=proxy_adapter.materialize, is_lzy_proxy=proxy_adapter.is_lzy_proxy,
+                            Result=Result, registry=LzySerializerRegistry()))
+    reference = json.loads((golden / "reference_call_vectors.json").read_text())
+    assert set(ours) == set(reference) and len(reference) == 55
+    for label, expected in reference.items():
+        assert json.loads(json.dumps(ours[label])) == expected, label
