@@ -15,6 +15,8 @@
 * reference_call_vectors.json — what the reference's own argument binding (pylzy/lzy/core/call.py:
   infer_and_validate_call_signature) does with the calls of tests/golden/call_battery.py: refusals with their messages,
   entry names, types, local data.
+* reference_uri_vectors.json — the storage URIs (and entry hashes) the reference's own LzyWorkflow assigns to the results and
+  exceptions of the calls of tests/golden/uri_battery.py, without and with LZY_USER: the cache naming contract.
 * reference_pickle_vectors.json — what the reference's request encoding (pylzy/lzy/api/v1/utils/pickle.py) emits
   for a few objects; ours must decode them and encode the same text.
 * digest_vectors.json — known answers of the data plane's digest from the oracle's C restatement
@@ -146,6 +148,47 @@ def main():
                                   materialize=ref_adapter.materialize, is_lzy_proxy=ref_adapter.is_lzy_proxy,
                                   Result=RefResult, registry=LzySerializerRegistry()))
     (ROOT / "tests/golden/reference_call_vectors.json").write_text(json.dumps(bound, indent=1, sort_keys=True))
+
+    # result URIs: the reference's own LzyWorkflow (whiteboard / logging / environment imports stubbed), its two
+    # private URI rules driven directly over the battery's fake calls and snapshot
+    from types import SimpleNamespace
+
+    class WithLogger:
+        def __post_init__(self):
+            pass
+
+        @property
+        def log(self):
+            return logging.getLogger("reference")
+
+    for name, attrs in {
+        "ai": {}, "ai.lzy": {}, "ai.lzy.v1": {}, "ai.lzy.v1.whiteboard": {}, "ai.lzy.v1.whiteboard.whiteboard_pb2": {"Whiteboard": object},
+        "lzy.api.v1.remote": {}, "lzy.api.v1.remote.lzy_service_client": {"USER_ENV": "LZY_USER"},
+        "lzy.api.v1.whiteboards": {"WritableWhiteboard": object}, "lzy.env.base": {"WithLogger": WithLogger},
+    }.items():
+        stub(name, **attrs)
+    sys.modules["lzy.api.v1.snapshot"].DefaultSnapshot = object
+    load_as(REF / "lzy/api/v1/utils/hashing.py", "lzy.api.v1.utils.hashing")
+    load_as(REF / "lzy/api/v1/utils/validation.py", "lzy.api.v1.utils.validation")
+    ref_workflow = load_as(REF / "lzy/core/workflow.py", "ref_workflow")
+    uri_battery = load(ROOT / "tests/golden/uri_battery.py", "uri_battery")
+
+    def ref_make(name, storage, snapshot):
+        w = ref_workflow.LzyWorkflow(name=name, owner=SimpleNamespace(storage_uri=storage), env=None)
+        w._LzyWorkflow__snapshot = snapshot
+        return w
+
+    def ref_assign(w, call):
+        (w._LzyWorkflow__gen_results_uri_in_cache if call.cache else w._LzyWorkflow__gen_results_uri_skip_cache)(call)
+
+    uris = []
+    for user in (None, "igor"):
+        os.environ.pop("LZY_USER", None)
+        if user is not None:
+            os.environ["LZY_USER"] = user
+        uris.append(uri_battery.run(dict(make_workflow=ref_make, assign=ref_assign), user))
+    os.environ.pop("LZY_USER", None)
+    (ROOT / "tests/golden/reference_uri_vectors.json").write_text(json.dumps(uris, indent=1, sort_keys=True))
 
     ref_pickle = load(REF / "lzy/api/v1/utils/pickle.py", "ref_pickle")
     objs = [None, 42, -1.5, "ʎzy", b"\x00\xff", [1, "two", 3.0], {"k": (1, 2), "n": None}, (str, "/call/entry"), {1, 2, 3}]

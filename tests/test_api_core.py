@@ -481,3 +481,30 @@ def test_hbm_runtime_lifecycle_without_a_device(monkeypatch):
     assert len(destroyed) == 2
     with pytest.raises(ValueError, match="Runtime is not running"):
         run(rt.exec([], lambda step: None))
+
+
+def test_result_uris_are_the_ones_the_reference_workflow_assigns(monkeypatch):
+    """tests/golden/reference_uri_vectors.json: what pylzy/lzy/core/workflow.py's own URI rules (executed in the
+    authoring container) give the results and exceptions of twelve calls on two storages, without and with
+    LZY_USER — cached and uncached, argument order, keyword order, versions, no arguments at all"""
+    import importlib.util
+    import json
+    from pathlib import Path
+    from types import SimpleNamespace
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("uri_battery", golden / "uri_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+
+    def make(name, storage, snapshot):
+        wf = LzyWorkflow(name=name, owner=SimpleNamespace(storage_uri=storage), env=None)
+        wf._snapshot = snapshot
+        return wf
+
+    for expected in json.loads((golden / "reference_uri_vectors.json").read_text()):
+        monkeypatch.delenv("LZY_USER", raising=False)
+        if expected["user"] is not None:
+            monkeypatch.setenv("LZY_USER", expected["user"])
+        ours = battery.run(dict(make_workflow=make, assign=lambda wf, call: wf._assign_uris(call)), expected["user"])
+        assert ours == expected
