@@ -17,6 +17,9 @@
   entry names, types, local data.
 * reference_uri_vectors.json — the storage URIs (and entry hashes) the reference's own LzyWorkflow assigns to the results and
   exceptions of the calls of tests/golden/uri_battery.py, without and with LZY_USER: the cache naming contract.
+* reference_startup_vectors.json — the reference's own op-side entry point (pylzy/lzy/api/v1/startup.py: process_execution)
+  run over slot files for the scenarios of tests/golden/startup_battery.py: which slots get written, what the
+  exception slot holds, what is raised, what is left of LZY_OP_MAIN_PID.
 * reference_pickle_vectors.json — what the reference's request encoding (pylzy/lzy/api/v1/utils/pickle.py) emits
   for a few objects; ours must decode them and encode the same text.
 * digest_vectors.json — known answers of the data plane's digest from the oracle's C restatement
@@ -189,6 +192,32 @@ def main():
         uris.append(uri_battery.run(dict(make_workflow=ref_make, assign=ref_assign), user))
     os.environ.pop("LZY_USER", None)
     (ROOT / "tests/golden/reference_uri_vectors.json").write_text(json.dumps(uris, indent=1, sort_keys=True))
+
+    # the op-side entry point: the reference's own process_execution over slot files in a temporary LZY_MOUNT, with
+    # this package's serializer registry on both sides (serialzy is absent)
+    from lzy_b200.serialization.registry import SerializerImport
+    from lzy_b200.utils import tbpickle
+    tbpickle.install()  # sys.exc_info() goes into the exception slot, traceback included
+    load_as(REF / "lzy/api/v1/utils/pickle.py", "lzy.api.v1.utils.pickle")
+    sys.modules["lzy.logs.config"].configure_logging = lambda config: None
+    sys.modules["lzy.logs.config"].get_remote_logger = logging.getLogger
+    stub("lzy.serialization")
+    stub("lzy.serialization.registry", LzySerializerRegistry=LzySerializerRegistry, SerializerImport=SerializerImport)
+    ref_startup = load_as(REF / "lzy/api/v1/startup.py", "ref_startup")
+    startup_battery = load(ROOT / "tests/golden/startup_battery.py", "startup_battery")
+
+    def ref_execute(mount, registry, op, args_paths, kwargs_paths, output_paths, exception_path, lazy, logger):
+        os.environ["LZY_MOUNT"] = mount
+        try:
+            ref_startup.process_execution(registry, op, args_paths, kwargs_paths, output_paths, exception_path, logger, lazy)
+        finally:
+            os.environ.pop("LZY_MOUNT", None)
+
+    logging.disable(logging.CRITICAL)
+    with tempfile.TemporaryDirectory() as d:
+        executed = startup_battery.run(dict(execute=ref_execute), LzySerializerRegistry(), d)
+    logging.disable(logging.NOTSET)
+    (ROOT / "tests/golden/reference_startup_vectors.json").write_text(json.dumps(executed, indent=1, sort_keys=True))
 
     ref_pickle = load(REF / "lzy/api/v1/utils/pickle.py", "ref_pickle")
     objs = [None, 42, -1.5, "ʎzy", b"\x00\xff", [1, "two", 3.0], {"k": (1, 2), "n": None}, (str, "/call/entry"), {1, 2, 3}]

@@ -191,3 +191,51 @@ def test_request_encoding_matches_the_reference_text_for_text():
         obj = unpickle(v["text"])
         assert repr(obj) == v["repr"]
         assert pickle(obj) == v["text"]
+
+
+def test_process_execution_behaves_as_the_reference_entry_point_does(tmp_path):
+    """tests/golden/reference_startup_vectors.json: thirteen scenarios run through pylzy/lzy/api/v1/startup.py's own
+    process_execution over slot files (in the authoring container) — plain, keyword and multiple results, an op that
+    raises, a result of the wrong type, ``-> None``, lazy and eager arguments, a lazy argument handed back as the
+    result, a replica that is not the main process, unreadable inputs (eager: refused before the op runs and the
+    main-pid marker stays, as there; lazy and untouched: never read).  Ours runs over a directory mount."""
+    import importlib.util
+    import json
+    import logging
+    from pathlib import Path
+
+    from lzy_b200.api.v1 import startup
+    from lzy_b200.serialization.registry import LzySerializerRegistry
+    from lzy_b200.utils import tbpickle
+
+    tbpickle.install()
+
+    class DirMount:
+        def __init__(self, directory):
+            self.directory = directory
+
+        def read(self, path, typ, serializers):
+            with open(self.directory + path, "rb") as f:
+                return serializers.find_serializer_by_type(typ).deserialize(f)
+
+        def write(self, path, typ, data, serializers):
+            with open(self.directory + path, "wb") as f:
+                serializers.find_serializer_by_type(typ).serialize(data, f)
+
+    def execute(mount, registry, op, args_paths, kwargs_paths, output_paths, exception_path, lazy, logger):
+        startup.process_execution(registry, op, args_paths, kwargs_paths, output_paths, exception_path, logger, lazy,
+                                  DirMount(mount))
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("startup_battery", golden / "startup_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+    logging.disable(logging.CRITICAL)
+    try:
+        ours = battery.run(dict(execute=execute), LzySerializerRegistry(), str(tmp_path))
+    finally:
+        logging.disable(logging.NOTSET)
+    reference = json.loads((golden / "reference_startup_vectors.json").read_text())
+    assert set(ours) == set(reference) and len(reference) == 13
+    for tag, expected in reference.items():
+        assert json.loads(json.dumps(ours[tag])) == expected, tag
