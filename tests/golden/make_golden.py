@@ -15,6 +15,9 @@
 * reference_call_vectors.json — what the reference's own argument binding (pylzy/lzy/core/call.py:
   infer_and_validate_call_signature) does with the calls of tests/golden/call_battery.py: refusals with their messages,
   entry names, types, local data.
+* reference_lzycall_vectors.json — what constructing the reference's own LzyCall does to a recording snapshot for the calls of
+  tests/golden/lzycall_battery.py: entries created, local arguments written at construction, proxies reusing their
+  producers' entries, the environment combined Lzy → workflow → call.
 * reference_uri_vectors.json — the storage URIs (and entry hashes) the reference's own LzyWorkflow assigns to the results and
   exceptions of the calls of tests/golden/uri_battery.py, without and with LZY_USER: the cache naming contract.
 * reference_startup_vectors.json — the reference's own op-side entry point (pylzy/lzy/api/v1/startup.py: process_execution)
@@ -151,6 +154,12 @@ def main():
                                   materialize=ref_adapter.materialize, is_lzy_proxy=ref_adapter.is_lzy_proxy,
                                   Result=RefResult, registry=LzySerializerRegistry()))
     (ROOT / "tests/golden/reference_call_vectors.json").write_text(json.dumps(bound, indent=1, sort_keys=True))
+
+    # recording a call: the reference's own LzyCall over a recording snapshot
+    lzycall_battery = load(ROOT / "tests/golden/lzycall_battery.py", "lzycall_battery")
+    recorded = lzycall_battery.run(dict(bind=ref_call.infer_and_validate_call_signature, LzyCall=ref_call.LzyCall,
+                                        lzy_proxy=ref_adapter.lzy_proxy, Result=RefResult, registry=LzySerializerRegistry()))
+    (ROOT / "tests/golden/reference_lzycall_vectors.json").write_text(json.dumps(recorded, indent=1, sort_keys=True))
 
     # result URIs: the reference's own LzyWorkflow (whiteboard / logging / environment imports stubbed), its two
     # private URI rules driven directly over the battery's fake calls and snapshot

@@ -274,3 +274,27 @@ def test_argument_binding_answers_as_the_reference_function_does():
     assert set(ours) == set(reference) and len(reference) == 55
     for label, expected in reference.items():
         assert json.loads(json.dumps(ours[label])) == expected, label
+
+
+def test_recording_a_call_touches_the_snapshot_as_the_reference_class_does():
+    """tests/golden/reference_lzycall_vectors.json: pylzy/lzy/core/call.py's own LzyCall constructed (in the authoring
+    container) over a recording snapshot — entries are created for local arguments, results and the exception in
+    that order and under those names, local arguments are written at construction, arguments that are results of
+    other ops reuse their entries, the environment is combined Lzy → workflow → call and validated"""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    from lzy_b200.api.v1.utils import proxy_adapter
+    from lzy_b200.core import call as core_call
+    from lzy_b200.proxy_result import Result
+    from lzy_b200.serialization.registry import LzySerializerRegistry
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("lzycall_battery", golden / "lzycall_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+    ours = battery.run(dict(bind=core_call.infer_and_validate_call_signature, LzyCall=core_call.LzyCall,
+                            lzy_proxy=proxy_adapter.lzy_proxy, Result=Result, registry=LzySerializerRegistry()))
+    reference = json.loads((golden / "reference_lzycall_vectors.json").read_text())
+    assert json.loads(json.dumps(ours)) == reference
