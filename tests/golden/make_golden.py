@@ -18,6 +18,9 @@
 * reference_lzycall_vectors.json — what constructing the reference's own LzyCall does to a recording snapshot for the calls of
   tests/golden/lzycall_battery.py: entries created, local arguments written at construction, proxies reusing their
   producers' entries, the environment combined Lzy → workflow → call.
+* reference_snapshot_vectors.json — the reference's own DefaultSnapshot on its own FsStorageClient over a temporary directory, for
+  the script of tests/golden/snapshot_battery.py: content addresses (prefix + md5 of the serialized bytes), equal data
+  stored once, what reading answers; the oracle's restatement (oracle/local_runtime.py) is held to it.
 * reference_uri_vectors.json — the storage URIs (and entry hashes) the reference's own LzyWorkflow assigns to the results and
   exceptions of the calls of tests/golden/uri_battery.py, without and with LZY_USER: the cache naming contract.
 * reference_startup_vectors.json — the reference's own op-side entry point (pylzy/lzy/api/v1/startup.py: process_execution)
@@ -227,6 +230,36 @@ def main():
         executed = startup_battery.run(dict(execute=ref_execute), LzySerializerRegistry(), d)
     logging.disable(logging.NOTSET)
     (ROOT / "tests/golden/reference_startup_vectors.json").write_text(json.dumps(executed, indent=1, sort_keys=True))
+
+    # the workflow's data table: the reference's own DefaultSnapshot over its own FsStorageClient in a temporary directory
+    import contextlib
+    sys.modules["lzy.logs.config"].get_syslog_color = lambda: "white"
+    ref_snapshot = load_as(REF / "lzy/api/v1/snapshot.py", "ref_snapshot")
+    snapshot_battery = load(ROOT / "tests/golden/snapshot_battery.py", "snapshot_battery")
+    with tempfile.TemporaryDirectory() as d:
+        prefix, inputs = "file://" + d + "/lzy_runs/wf/inputs/", d + "/lzy_runs/wf/inputs"
+        snap = ref_snapshot.DefaultSnapshot(LzySerializerRegistry(), prefix, fs.FsStorageClient(), "storage")
+
+        def quiet(coro):  # the progress bars go to stdout
+            with contextlib.redirect_stdout(io.StringIO()):
+                return asyncio.run(coro)
+
+        def get(entry):
+            answer = quiet(snap.get_data(entry.id))
+            return ("result", repr(answer.value)) if isinstance(answer, RefResult) else ("absence", str(answer.cause))
+
+        def attr(entry, name):
+            try:
+                return getattr(entry, name)
+            except ValueError:
+                return None
+
+        table = snapshot_battery.run(dict(
+            create=snap.create_entry, put=lambda entry, value: quiet(snap.put_data(entry.id, value)), get=get,
+            uri=lambda entry: attr(entry, "storage_uri"), hash=lambda entry: attr(entry, "data_hash"),
+            set_uri=lambda entry, uri: setattr(entry, "storage_uri", uri),
+            stored=lambda: sorted(os.listdir(inputs)) if os.path.isdir(inputs) else []), prefix)
+    (ROOT / "tests/golden/reference_snapshot_vectors.json").write_text(json.dumps(table, indent=1, sort_keys=True))
 
     ref_pickle = load(REF / "lzy/api/v1/utils/pickle.py", "ref_pickle")
     objs = [None, 42, -1.5, "ʎzy", b"\x00\xff", [1, "two", 3.0], {"k": (1, 2), "n": None}, (str, "/call/entry"), {1, 2, 3}]

@@ -182,3 +182,33 @@ def test_copy_engine_pull_schedule_arithmetic():
             N.check(N.lib.lzyb_set_dma_schedule(100, 6))
     finally:
         N.lib.lzyb_set_dma_schedule(0, 6)
+
+
+def test_oracle_snapshot_matches_the_reference_snapshot_on_a_real_directory(tmp_path):
+    """tests/golden/reference_snapshot_vectors.json: pylzy's own DefaultSnapshot over its own FsStorageClient (executed
+    in the authoring container) — the oracle's restatement, which the CPU baseline and the local-path parity tests
+    run on, gives the same content addresses (md5 for md5), stores equal data once and reads back the same"""
+    import importlib.util
+    import json
+    import os
+    from pathlib import Path
+
+    from oracle import local_runtime
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("snapshot_battery", golden / "snapshot_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+    prefix, inputs = f"file://{tmp_path}/lzy_runs/wf/inputs/", f"{tmp_path}/lzy_runs/wf/inputs"
+    snap = local_runtime.OracleSnapshot(prefix)
+
+    def get(entry):
+        found, value = snap.get_data(entry.id)
+        return ("result", repr(value)) if found else ("absence", "")
+
+    ours = battery.run(dict(
+        create=snap.create_entry, put=lambda entry, value: snap.put_data(entry.id, value), get=get,
+        uri=lambda entry: entry.storage_uri, hash=lambda entry: entry.data_hash,
+        set_uri=lambda entry, uri: setattr(entry, "storage_uri", uri),
+        stored=lambda: sorted(os.listdir(inputs)) if os.path.isdir(inputs) else []), prefix)
+    assert json.loads(json.dumps(ours)) == json.loads((golden / "reference_snapshot_vectors.json").read_text())
