@@ -21,6 +21,8 @@
 * reference_snapshot_vectors.json — the reference's own DefaultSnapshot on its own FsStorageClient over a temporary directory, for
   the script of tests/golden/snapshot_battery.py: content addresses (prefix + md5 of the serialized bytes), equal data
   stored once, what reading answers; the oracle's restatement (oracle/local_runtime.py) is held to it.
+* reference_order_vectors.json — the order in which the reference's own LocalRuntime.exec runs the calls of forty seeded random
+  graphs (tests/golden/order_battery.py); the oracle's topo_order is held to it.
 * reference_uri_vectors.json — the storage URIs (and entry hashes) the reference's own LzyWorkflow assigns to the results and
   exceptions of the calls of tests/golden/uri_battery.py, without and with LZY_USER: the cache naming contract.
 * reference_startup_vectors.json — the reference's own op-side entry point (pylzy/lzy/api/v1/startup.py: process_execution)
@@ -260,6 +262,31 @@ def main():
             set_uri=lambda entry, uri: setattr(entry, "storage_uri", uri),
             stored=lambda: sorted(os.listdir(inputs)) if os.path.isdir(inputs) else []), prefix)
     (ROOT / "tests/golden/reference_snapshot_vectors.json").write_text(json.dumps(table, indent=1, sort_keys=True))
+
+    # execution order of one barrier: the reference's own LocalRuntime.exec, its per-call execution replaced by a recorder
+    stub("lzy.api.v1.local")
+    load_as(REF / "lzy/api/v1/exceptions.py", "lzy.api.v1.exceptions")
+    load_as(REF / "lzy/api/v1/runtime.py", "lzy.api.v1.runtime")
+    sys.modules["lzy.api.v1.startup"] = ref_startup
+    sys.modules["lzy.logs.config"].get_logging_config = dict
+    sys.modules["lzy.logs.config"].COLOURS, sys.modules["lzy.logs.config"].RESET_COLOR = {}, ""
+    ref_local = load_as(REF / "lzy/api/v1/local/runtime.py", "ref_local_runtime")
+    order_battery = load(ROOT / "tests/golden/order_battery.py", "order_battery")
+
+    def ref_order(calls):
+        runtime = ref_local.LocalRuntime()
+        runtime._LocalRuntime__workflow = object()
+        seen = []
+
+        async def record(call):
+            seen.append(call.id)
+
+        runtime._LocalRuntime__exec_call = record
+        asyncio.run(runtime.exec(calls, lambda step: None))
+        return seen
+
+    (ROOT / "tests/golden/reference_order_vectors.json").write_text(
+        json.dumps(order_battery.run(dict(order=ref_order)), indent=1, sort_keys=True))
 
     ref_pickle = load(REF / "lzy/api/v1/utils/pickle.py", "ref_pickle")
     objs = [None, 42, -1.5, "ʎzy", b"\x00\xff", [1, "two", 3.0], {"k": (1, 2), "n": None}, (str, "/call/entry"), {1, 2, 3}]

@@ -212,3 +212,20 @@ def test_oracle_snapshot_matches_the_reference_snapshot_on_a_real_directory(tmp_
         set_uri=lambda entry, uri: setattr(entry, "storage_uri", uri),
         stored=lambda: sorted(os.listdir(inputs)) if os.path.isdir(inputs) else []), prefix)
     assert json.loads(json.dumps(ours)) == json.loads((golden / "reference_snapshot_vectors.json").read_text())
+
+
+def test_oracle_runs_calls_in_the_order_the_reference_local_runtime_does():
+    """tests/golden/reference_order_vectors.json: execution orders of pylzy's own LocalRuntime.exec (run in the
+    authoring container with the per-call execution replaced by a recorder) for forty seeded random graphs"""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    from oracle.local_runtime import OracleLocalRuntime
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("order_battery", golden / "order_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+    ours = battery.run(dict(order=lambda calls: [c.id for c in OracleLocalRuntime.topo_order(calls)]))
+    assert ours == json.loads((golden / "reference_order_vectors.json").read_text())

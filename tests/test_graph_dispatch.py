@@ -148,3 +148,35 @@ def test_lockstep_with_bfs_oracle(seed):
             o.change_status(t, T_SUCCESS)
             g.task_done(t)
     assert o.status == "COMPLETED" and g.status == H.G_COMPLETED
+
+
+def test_every_order_of_the_reference_local_runtime_is_a_valid_dispatch_order():
+    """the reference's local runtime runs the calls of a barrier one at a time in a DFS-topological order
+    (tests/golden/reference_order_vectors.json, produced by its own LocalRuntime.exec); the C++ dispatcher's rule — a
+    task may start once the producers of all its inputs have finished — must admit each of those sequences"""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("order_battery", golden / "order_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+    orders = json.loads((golden / "reference_order_vectors.json").read_text())
+    for name, calls in battery.graphs().items():
+        index = {c.id: i for i, c in enumerate(calls)}
+        producer = {eid: i for i, c in enumerate(calls) for eid in c.entry_ids}
+        edges = sorted({(producer[e], i) for i, c in enumerate(calls)
+                        for e in list(c.arg_entry_ids) + list(c.kwarg_entry_ids.values()) if e in producer and producer[e] != i})
+        g = H.GraphDispatcher(len(calls), edges, allow_cycles=False)
+        try:
+            ready = set(g.next())
+            for call_id in orders[name]:
+                task = index[call_id]
+                assert task in ready, f"{name}: {call_id} ran before its producers"
+                ready.discard(task)
+                g.task_done(task, True)
+                ready |= set(g.next())
+            assert not ready and g.status == H.G_COMPLETED
+        finally:
+            g.close()
