@@ -23,6 +23,8 @@
   stored once, what reading answers; the oracle's restatement (oracle/local_runtime.py) is held to it.
 * reference_order_vectors.json — the order in which the reference's own LocalRuntime.exec runs the calls of forty seeded random
   graphs (tests/golden/order_battery.py); the oracle's topo_order is held to it.
+* reference_file_vectors.json — the reference's own FileSerializer (pylzy/lzy/serialization/file.py) on the files and streams of
+  tests/golden/file_battery.py: the raw_file byte format and how streams with / without / shorter than the header read.
 * reference_uri_vectors.json — the storage URIs (and entry hashes) the reference's own LzyWorkflow assigns to the results and
   exceptions of the calls of tests/golden/uri_battery.py, without and with LZY_USER: the cache naming contract.
 * reference_startup_vectors.json — the reference's own op-side entry point (pylzy/lzy/api/v1/startup.py: process_execution)
@@ -287,6 +289,26 @@ def main():
 
     (ROOT / "tests/golden/reference_order_vectors.json").write_text(
         json.dumps(order_battery.run(dict(order=ref_order)), indent=1, sort_keys=True))
+
+    # File payloads: the reference's own FileSerializer (its serialzy base class stubbed: only _check_types_valid is used)
+    import collections
+    import enum
+    api_stub.Schema = collections.namedtuple("Schema", "data_format schema_format meta")
+    api_stub.StandardSchemaFormats = enum.Enum("StandardSchemaFormats", "no_schema")
+    api_stub.VersionBoundary = object
+    stub("serialzy.base", DefaultSchemaSerializerByReference=type("DefaultSchemaSerializerByReference", (), {
+        "_check_types_valid": lambda self, schema_type, user_type: None}))
+    for name in ("ai.lzy.v1.workflow",):
+        stub(name)
+    stub("ai.lzy.v1.workflow.workflow_pb2", VmPoolSpec=object)
+    ref_lzy_types = load_as(REF / "lzy/types.py", "lzy.types")
+    ref_file = load_as(REF / "lzy/serialization/file.py", "ref_file_serializer")
+    file_battery = load(ROOT / "tests/golden/file_battery.py", "file_battery")
+    ref_file_serializer = ref_file.FileSerializer()
+    with tempfile.TemporaryDirectory() as d:
+        files = file_battery.run(dict(File=ref_lzy_types.File, serialize=ref_file_serializer._serialize,
+                                      deserialize=lambda source: ref_file_serializer._deserialize(source, ref_lzy_types.File)), d)
+    (ROOT / "tests/golden/reference_file_vectors.json").write_text(json.dumps(files, indent=1, sort_keys=True))
 
     ref_pickle = load(REF / "lzy/api/v1/utils/pickle.py", "ref_pickle")
     objs = [None, 42, -1.5, "ʎzy", b"\x00\xff", [1, "two", 3.0], {"k": (1, 2), "n": None}, (str, "/call/entry"), {1, 2, 3}]

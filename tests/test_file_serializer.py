@@ -99,3 +99,24 @@ def test_a_file_nested_in_another_object_is_carried_by_value(registry, source):
     with back.file.open() as f:
         assert f.read() == CONTENT
     os.unlink(str(back.file))
+
+
+def test_raw_file_format_is_the_one_the_reference_serializer_writes_and_reads(tmp_path):
+    """tests/golden/reference_file_vectors.json: pylzy/lzy/serialization/file.py's own FileSerializer (executed in the
+    authoring container) on fifteen files (content × mode) and seven streams — byte for byte on the way out, content
+    and permissions on the way in, headerless and too-short streams included"""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    from lzy_b200.serialization.builtin import FileSerializer
+    from lzy_b200.types import File
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("file_battery", golden / "file_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+    ser = FileSerializer()
+    ours = battery.run(dict(File=File, serialize=ser._serialize, deserialize=lambda source: ser._deserialize(source, File)),
+                       str(tmp_path))
+    assert json.loads(json.dumps(ours)) == json.loads((golden / "reference_file_vectors.json").read_text())
