@@ -10,6 +10,8 @@
   stubs are absent), so the modules are loaded by file path.
 * reference_proxy_vectors.json — answers of the reference's own lazy proxy (pylzy/lzy/proxy/automagic.py, loaded
   by file path) to the probes of tests/golden/proxy_battery.py; tests/test_lazy_proxy.py holds ours to them.
+* reference_materialize_vectors.json — how the reference's own lzy_proxy (api/v1/utils/proxy_adapter.py) obtains a value over a
+  fake workflow (tests/golden/materialize_battery.py): supplied value, snapshot, one barrier, the raised reasons.
 * reference_types_vectors.json — answers of the reference's own annotation helpers (pylzy/lzy/api/v1/utils/types.py) to the
   questions of tests/golden/types_battery.py; tests/test_call_signatures.py holds ours to them.
 * reference_call_vectors.json — what the reference's own argument binding (pylzy/lzy/core/call.py:
@@ -161,6 +163,15 @@ def main():
                                   materialize=ref_adapter.materialize, is_lzy_proxy=ref_adapter.is_lzy_proxy,
                                   Result=RefResult, registry=LzySerializerRegistry()))
     (ROOT / "tests/golden/reference_call_vectors.json").write_text(json.dumps(bound, indent=1, sort_keys=True))
+
+    # touching a proxy: the reference's own lzy_proxy over a fake workflow (snapshot answers scripted, barrier recorded)
+    from lzy.proxy.result import Absence as RefAbsence2
+    materialize_battery = load(ROOT / "tests/golden/materialize_battery.py", "materialize_battery")
+    touched = materialize_battery.run(dict(
+        lzy_proxy=ref_adapter.lzy_proxy, materialize=ref_adapter.materialize, materialized=ref_adapter.materialized,
+        is_lzy_proxy=ref_adapter.is_lzy_proxy, get_proxy_entry_id=ref_adapter.get_proxy_entry_id, Result=RefResult,
+        Absence=RefAbsence2))
+    (ROOT / "tests/golden/reference_materialize_vectors.json").write_text(json.dumps(touched, indent=1, sort_keys=True))
 
     # recording a call: the reference's own LzyCall over a recording snapshot
     lzycall_battery = load(ROOT / "tests/golden/lzycall_battery.py", "lzycall_battery")

@@ -215,3 +215,26 @@ def test_same_answers_as_the_reference_proxy_on_the_shared_battery():
     ours = json.loads(json.dumps(proxy_battery.run(proxy), default=str))
     assert set(ours) == set(golden)
     assert {k: ours[k] for k in golden if ours[k] != golden[k]} == {}
+
+
+def test_entry_proxies_obtain_their_value_as_the_reference_adapter_does():
+    """tests/golden/reference_materialize_vectors.json: pylzy/lzy/api/v1/utils/proxy_adapter.py's own lzy_proxy (executed
+    in the authoring container) over a fake workflow whose snapshot answers are scripted — a supplied value asks
+    nobody; a stored one is read without a barrier; otherwise exactly one barrier and a second read; an Absence with
+    a cause raises the cause, one without raises RuntimeError naming entry and workflow; the markers (is proxy,
+    entry id, materialized) compute nothing; a second touch reads nothing again"""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    from lzy_b200.api.v1.utils import proxy_adapter as adapter
+    from lzy_b200.proxy_result import Absence, Result
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("materialize_battery", golden / "materialize_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+    ours = battery.run(dict(lzy_proxy=adapter.lzy_proxy, materialize=adapter.materialize, materialized=adapter.materialized,
+                            is_lzy_proxy=adapter.is_lzy_proxy, get_proxy_entry_id=adapter.get_proxy_entry_id,
+                            Result=Result, Absence=Absence))
+    assert json.loads(json.dumps(ours)) == json.loads((golden / "reference_materialize_vectors.json").read_text())
