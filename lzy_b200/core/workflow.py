@@ -29,8 +29,9 @@ if TYPE_CHECKING:
     from .lzy import Lzy
 
 USER_ENV = "LZY_USER"
-NAME_VALID_SYMBOLS = "letters, digits, '-', '_'"
-_VALID_NAME = re.compile(r"[A-Za-z0-9_\-]+")
+NAME_VALID_SYMBOLS = "[alphanumeric characters,_,-]"  # the wording of pylzy/lzy/api/v1/utils/validation.py:3
+# what `re.match("^[a-zA-Z0-9_-]*$", name)` accepts there (:6-7) — the empty name and one trailing newline included
+_VALID_NAME = re.compile(r"[A-Za-z0-9_-]*\n?")
 _LOG = logging.getLogger("lzy_b200.workflow")
 
 
@@ -38,7 +39,7 @@ class LzyWorkflow(WithEnvironmentMixin):
     instance: ClassVar[Optional["LzyWorkflow"]] = None
 
     def __init__(self, name: str, owner: "Lzy", env: LzyEnvironment, eager: bool = False, interactive: bool = True):
-        if not _VALID_NAME.fullmatch(name or ""):
+        if not isinstance(name, str) or not _VALID_NAME.fullmatch(name):
             raise ValueError(f"Invalid workflow name. Name can contain only {NAME_VALID_SYMBOLS}")
         self.name, self.owner, self.env, self.eager, self.interactive = name, owner, env, eager, interactive
         self._user = os.getenv(USER_ENV)

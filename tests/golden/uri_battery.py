@@ -68,4 +68,11 @@ def run(ns: Dict[str, Any], user) -> Dict[str, Any]:
         assert before == {eid: (e.storage_uri, e.data_hash) for eid, e in snapshot.entries.items()}
         out[storage] = {eid: {"uri": e.storage_uri, "hash": e.data_hash} for eid, e in snapshot.entries.items()
                         if ".r" in eid or eid.endswith(".exc")}
-    return {"user": user, "storages": out}
+    names = {}
+    for name in ["wf", "wf-1", "wf_1", "WF9", "", "wf 1", "wf!", "wf.1", "wf/1", "ʎzy", "wf\n", "-", "a" * 300, "wf\t", "wf\n\n"]:
+        try:
+            ns["make_workflow"](name, "s3://b", Snapshot())
+            names[repr(name[:12])] = "accepted"
+        except ValueError as e:
+            names[repr(name[:12])] = str(e)
+    return {"user": user, "storages": out, "workflow names": names}
