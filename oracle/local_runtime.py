@@ -218,38 +218,39 @@ class OracleLocalRuntime:
 
     @staticmethod
     def topo_order(calls: List[Call]) -> List[Call]:
-        graph: Dict[str, List[Call]] = defaultdict(list)
-        eid_to_call: Dict[str, Call] = {}
-        used: Dict[str, bool] = defaultdict(lambda: False)
+        """The order LocalRuntime.exec runs one barrier in (local/runtime.py:44-85): a depth-first walk over *entries*
+        — from every result entry to the results of the calls that read it — taken in reverse finishing order, each
+        call run at the first of its results.  Quirks kept: a walk's starting entry is not marked as reached (it may
+        finish twice; the per-call de-duplication absorbs that), readers are visited positional arguments first.
+        Pinned by tests/golden/reference_order_vectors.json (the reference's own exec on forty random graphs)."""
+        readers: Dict[str, List[Call]] = defaultdict(list)
+        produced_by: Dict[str, Call] = {}
         for call in calls:
-            for eid in call.arg_entry_ids:
-                graph[eid].append(call)
-            for eid in call.kwarg_entry_ids.values():
-                graph[eid].append(call)
+            for eid in [*call.arg_entry_ids, *call.kwarg_entry_ids.values()]:
+                readers[eid].append(call)
             for eid in call.entry_ids:
-                eid_to_call[eid] = call
-        ans: List[str] = []
+                produced_by[eid] = call
+        reached: set = set()
+        finished: List[str] = []
 
-        def dfs(eid: str):
-            for c in graph[eid]:
-                for edge in c.entry_ids:
-                    if not used[edge]:
-                        used[edge] = True
-                        dfs(edge)
-            ans.append(eid)
+        def walk(eid: str) -> None:
+            for reader in readers[eid]:
+                for result in reader.entry_ids:
+                    if result not in reached:
+                        reached.add(result)
+                        walk(result)
+            finished.append(eid)
 
-        for eid in list(eid_to_call.keys()):
-            if not used[eid]:
-                dfs(eid)
-        ans.reverse()
-        done: Dict[str, bool] = defaultdict(lambda: False)
+        for eid in list(produced_by):
+            if eid not in reached:
+                walk(eid)
         order: List[Call] = []
-        for eid in ans:
-            c = eid_to_call[eid]
-            if done[c.id]:
-                continue
-            order.append(c)
-            done[c.id] = True
+        scheduled: set = set()
+        for eid in reversed(finished):
+            call = produced_by[eid]
+            if call.id not in scheduled:
+                scheduled.add(call.id)
+                order.append(call)
         return order
 
     def _exec_call(self, call: Call) -> None:  # local/runtime.py:87-179
