@@ -74,24 +74,22 @@ def path_from_uri(uri: str) -> str:  # fs.py:53-56
     return os.path.abspath(os.path.join(parsed.netloc, parsed.path))
 
 
+def _pump(source, sink) -> None:
+    """the storage client's copy loop: 8096 bytes at a time until a read comes back empty (fs.py:19-25, 33-38)"""
+    for piece in iter(lambda: source.read(FS_CHUNK), b""):
+        sink.write(piece)
+
+
 def fs_read(uri: str, dest) -> None:  # fs.py:15-25
-    with open(path_from_uri(uri), "rb") as f:
-        while True:
-            read = f.read(FS_CHUNK)
-            if not read:
-                break
-            dest.write(read)
+    with open(path_from_uri(uri), "rb") as stored:
+        _pump(stored, dest)
 
 
 def fs_write(uri: str, data) -> None:  # fs.py:27-38
-    path = path_from_uri(uri)
-    os.makedirs(Path(path).parent.absolute(), exist_ok=True)
-    with open(path, "wb") as f:
-        while True:
-            read = data.read(FS_CHUNK)
-            if not read:
-                break
-            f.write(read)
+    target = Path(path_from_uri(uri))
+    target.parent.absolute().mkdir(parents=True, exist_ok=True)
+    with open(target, "wb") as stored:
+        _pump(data, stored)
 
 
 def pickle_request(obj: Any) -> str:  # utils/pickle.py:7-8
