@@ -27,6 +27,9 @@
   graphs (tests/golden/order_battery.py); the oracle's topo_order is held to it.
 * reference_file_vectors.json — the reference's own FileSerializer (pylzy/lzy/serialization/file.py) on the files and streams of
   tests/golden/file_battery.py: the raw_file byte format and how streams with / without / shorter than the header read.
+* reference_wrapper_vectors.json — the reference's own @op decorator and LazyCallWrapper (core/op.py, core/call.py) on
+  tests/golden/wrapper_battery.py: what the decorator records, the unannotated refusal, plain calls outside a workflow,
+  proxies / None / eager values inside one.
 * reference_uri_vectors.json — the storage URIs (and entry hashes) the reference's own LzyWorkflow assigns to the results and
   exceptions of the calls of tests/golden/uri_battery.py, without and with LZY_USER: the cache naming contract.
 * reference_startup_vectors.json — the reference's own op-side entry point (pylzy/lzy/api/v1/startup.py: process_execution)
@@ -178,6 +181,35 @@ def main():
     recorded = lzycall_battery.run(dict(bind=ref_call.infer_and_validate_call_signature, LzyCall=ref_call.LzyCall,
                                         lzy_proxy=ref_adapter.lzy_proxy, Result=RefResult, registry=LzySerializerRegistry()))
     (ROOT / "tests/golden/reference_lzycall_vectors.json").write_text(json.dumps(recorded, indent=1, sort_keys=True))
+
+    # @op and calling the wrapper: the reference's own decorator and LazyCallWrapper; the active workflow is a fake
+    class BatteryEnv:
+        def combine(self, other):
+            return self
+
+        def validate(self):
+            pass
+
+    class ActiveWorkflow:
+        instance = None
+
+        @classmethod
+        def get_active(cls):
+            return cls.instance
+
+    sys.modules["lzy.env.environment"].LzyEnvironment = BatteryEnv
+    stub("lzy.core")
+    ref_call_module = load_as(REF / "lzy/core/call.py", "lzy.core.call")
+    stub("lzy.core.workflow", LzyWorkflow=ActiveWorkflow)
+    stub("lzy.utils.format", pretty_function=load(REF / "lzy/utils/format.py", "ref_format").pretty_function)
+    ref_op = load_as(REF / "lzy/core/op.py", "ref_op")
+    wrapper_battery = load(ROOT / "tests/golden/wrapper_battery.py", "wrapper_battery")
+    wrapped = wrapper_battery.run(dict(op=ref_op.op, LzyWorkflow=ActiveWorkflow, is_lzy_proxy=ref_adapter.is_lzy_proxy,
+                                       get_proxy_entry_id=ref_adapter.get_proxy_entry_id, Result=RefResult, Env=BatteryEnv,
+                                       registry=LzySerializerRegistry()))
+    del ref_call_module
+    del sys.modules["lzy.core.workflow"]
+    (ROOT / "tests/golden/reference_wrapper_vectors.json").write_text(json.dumps(wrapped, indent=1, sort_keys=True))
 
     # result URIs: the reference's own LzyWorkflow (whiteboard / logging / environment imports stubbed), its two
     # private URI rules driven directly over the battery's fake calls and snapshot

@@ -508,3 +508,39 @@ def test_result_uris_are_the_ones_the_reference_workflow_assigns(monkeypatch):
             monkeypatch.setenv("LZY_USER", expected["user"])
         ours = battery.run(dict(make_workflow=make, assign=lambda wf, call: wf._assign_uris(call)), expected["user"])
         assert ours == expected
+
+
+def test_decorating_and_calling_an_op_behaves_as_the_reference_wrapper_does():
+    """tests/golden/reference_wrapper_vectors.json: pylzy's own ``op`` and ``LazyCallWrapper`` (executed in the authoring
+    container) on tests/golden/wrapper_battery.py — recorded result types and options, name and docstring carried over,
+    the refusal of an unannotated function, plain calls outside a workflow; inside one every call is registered once
+    and answered with one proxy per result bound to the call's result entries (a tuple for several), the real None
+    for ``-> None``, values instead of proxies when the workflow is eager"""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    from lzy_b200.api.v1.utils import proxy_adapter
+    from lzy_b200.proxy_result import Result
+    from lzy_b200.serialization.registry import LzySerializerRegistry
+
+    class Env:
+        def combine(self, other):
+            return self
+
+        def validate(self):
+            pass
+
+        def get_env_vars(self):
+            return {}
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("wrapper_battery", golden / "wrapper_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+    assert LzyWorkflow.instance is None
+    ours = battery.run(dict(op=op, LzyWorkflow=LzyWorkflow, is_lzy_proxy=proxy_adapter.is_lzy_proxy,
+                            get_proxy_entry_id=proxy_adapter.get_proxy_entry_id, Result=Result, Env=Env,
+                            registry=LzySerializerRegistry()))
+    assert LzyWorkflow.instance is None
+    assert json.loads(json.dumps(ours)) == json.loads((golden / "reference_wrapper_vectors.json").read_text())
