@@ -203,13 +203,22 @@ class B200Runtime(Runtime):
             self._active.append((workflow, execution_id))
         return execution_id
 
-    def _stop(self, reason: str) -> None:
-        """abort() / finish() of the innermost started workflow; nothing to do when none was started
-        (pylzy/lzy/api/v1/remote/runtime.py:204-243: `if not self.__running: return`, state reset afterwards)"""
+    def _stop(self, reason: str, workflow: Optional["LzyWorkflow"] = None) -> None:
+        """abort() / finish(): of `workflow` if given (nothing to do when it never started here), else of the innermost
+        started workflow; nothing to do when none was started (pylzy/lzy/api/v1/remote/runtime.py:204-243: `if not
+        self.__running: return`, state reset afterwards)"""
         with self._lock:
-            if not self._active:
-                return
-            _workflow, execution_id = self._active.pop()
+            if workflow is None:
+                if not self._active:
+                    return
+                _workflow, execution_id = self._active.pop()
+            else:
+                for i in range(len(self._active) - 1, -1, -1):
+                    if self._active[i][0] is workflow:
+                        _workflow, execution_id = self._active.pop(i)
+                        break
+                else:
+                    return
         if self.cm is not None:
             self.cm.destroy_all(execution_id, reason)  # LzyChannelManagerPrivate.DestroyAll
 
@@ -218,6 +227,14 @@ class B200Runtime(Runtime):
 
     async def finish(self) -> None:
         self._stop("finished")
+
+    # LzyWorkflow prefers these two when a runtime has them: with several executions alive (an op that opened a
+    # workflow of its own) "the innermost one" is not always the one that is ending
+    async def abort_workflow(self, workflow: "LzyWorkflow") -> None:
+        self._stop("aborted", workflow)
+
+    async def finish_workflow(self, workflow: "LzyWorkflow") -> None:
+        self._stop("finished", workflow)
 
     def _execution_of(self, workflow: "LzyWorkflow") -> str:
         with self._lock:

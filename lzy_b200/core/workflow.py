@@ -48,6 +48,7 @@ class LzyWorkflow(WithEnvironmentMixin):
         self._snapshot: Optional[Snapshot] = None
         self._execution: Optional[str] = None
         self._running = False
+        self._start_attempted = False
         self._opened_inside_op = False
 
     # ---- declarations ---------------------------------------------------------------------------------------------
@@ -134,6 +135,7 @@ class LzyWorkflow(WithEnvironmentMixin):
                 raise RuntimeError("Workflow already started")
             if self.get_active() is not None:
                 raise RuntimeError("Simultaneous workflows are not supported")
+            self._start_attempted = True
             self._execution = LzyEventLoop.run_async(self.owner.runtime.start(self))
             self._running = True
             self._mark_active(True)
@@ -161,17 +163,24 @@ class LzyWorkflow(WithEnvironmentMixin):
                 raise failure
 
     def _leave(self, aborting: bool) -> None:
-        if not self._running:
-            # nothing of this workflow is running, so the runtime is left alone (pylzy/tests/api/v1/
-            # test_remote_runtime.py:65-76: "should NOT be aborted if not started") — in particular a refused
-            # second workflow does not take down the one that is active
+        """finish() after a clean block, abort() otherwise — also when ``start`` itself raised, as the reference does
+        (its runtime decides what an abort without a start means, pylzy/tests/api/v1/test_remote_runtime.py:65-76).
+        A workflow that was *refused* before it asked the runtime for anything — another one is active — leaves the
+        runtime and the active workflow alone; the reference aborts the running execution in that case."""
+        if not self._start_attempted:
             return
-        runtime = self.owner.runtime
+        runtime, started = self.owner.runtime, self._running
+        # a runtime that keeps several executions apart (nested workflows) is told whose end this is
+        by_workflow = getattr(runtime, "abort_workflow" if aborting else "finish_workflow", None)
         try:
-            LzyEventLoop.run_async(runtime.abort() if aborting else runtime.finish())
+            if by_workflow is not None:
+                LzyEventLoop.run_async(by_workflow(self))
+            else:
+                LzyEventLoop.run_async(runtime.abort() if aborting else runtime.finish())
         finally:
-            self._mark_active(False)
-            self._running = False
+            if started:
+                self._mark_active(False)
+            self._running = self._start_attempted = False
 
     # ---- storage URIs of results ---------------------------------------------------------------------------------
     def _assign_uris(self, call: "LzyCall") -> None:

@@ -30,6 +30,9 @@
 * reference_wrapper_vectors.json — the reference's own @op decorator and LazyCallWrapper (core/op.py, core/call.py) on
   tests/golden/wrapper_battery.py: what the decorator records, the unannotated refusal, plain calls outside a workflow,
   proxies / None / eager values inside one.
+* reference_lifecycle_vectors.json — the reference's own LzyWorkflow entered, used and left over a recording runtime
+  (tests/golden/lifecycle_battery.py): start / exec(n) / finish / abort in order, what is raised, the active workflow,
+  the snapshot prefix.
 * reference_uri_vectors.json — the storage URIs (and entry hashes) the reference's own LzyWorkflow assigns to the results and
   exceptions of the calls of tests/golden/uri_battery.py, without and with LZY_USER: the cache naming contract.
 * reference_startup_vectors.json — the reference's own op-side entry point (pylzy/lzy/api/v1/startup.py: process_execution)
@@ -242,6 +245,33 @@ def main():
 
     def ref_assign(w, call):
         (w._LzyWorkflow__gen_results_uri_in_cache if call.cache else w._LzyWorkflow__gen_results_uri_skip_cache)(call)
+
+    # entering / using / leaving a workflow: the same reference class driving a recording runtime
+    lifecycle_battery = load(ROOT / "tests/golden/lifecycle_battery.py", "lifecycle_battery")
+
+    class RecordingSnapshot:
+        def __init__(self, registry, prefix, client, storage_name):
+            self.prefix, self.entries = prefix, {}
+
+        def get(self, eid):
+            return self.entries[eid]
+
+    ref_workflow.DefaultSnapshot = RecordingSnapshot
+
+    def ref_make_started(name, runtime, log, eager):
+        owner = SimpleNamespace(storage_uri="s3://bucket/prefix", runtime=runtime, serializer_registry=None,
+                                storage_client=None, storage_name="storage")
+        return ref_workflow.LzyWorkflow(name=name, owner=owner, env=None, eager=eager)
+
+    lifecycles = []
+    for user in (None, "igor"):
+        os.environ.pop("LZY_USER", None)
+        if user is not None:
+            os.environ["LZY_USER"] = user
+        lifecycles.append(lifecycle_battery.run(dict(
+            make_workflow=ref_make_started, active=lambda: getattr(ref_workflow.LzyWorkflow.get_active(), "name", None)), user))
+    os.environ.pop("LZY_USER", None)
+    (ROOT / "tests/golden/reference_lifecycle_vectors.json").write_text(json.dumps(lifecycles, indent=1, sort_keys=True))
 
     uris = []
     for user in (None, "igor"):

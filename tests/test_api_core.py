@@ -244,8 +244,10 @@ def test_a_refused_second_workflow_leaves_the_active_one_running(lzy):
     assert lzy.runtime.aborted == 0 and lzy.runtime.finished == 1
 
 
-def test_error_on_start_is_not_an_abort(lzy, monkeypatch):
-    """pylzy/tests/api/v1/test_remote_runtime.py:65-76: the body is not entered, nothing is aborted"""
+def test_error_on_start_hands_the_decision_to_the_runtime(lzy, monkeypatch):
+    """pylzy/tests/api/v1/test_remote_runtime.py:65-76: the body is not entered; the workflow tells the runtime to abort
+    (as the reference's does — what an abort without a start means is the runtime's business: RemoteRuntime and
+    B200Runtime do nothing then), and no workflow is left active"""
     async def refuse(workflow):
         raise ConnectionError("cannot start")
 
@@ -254,7 +256,7 @@ def test_error_on_start_is_not_an_abort(lzy, monkeypatch):
     with pytest.raises(ConnectionError):
         with lzy.workflow(wf_name()):
             entered = True
-    assert not entered and lzy.runtime.aborted == 0 and LzyWorkflow.get_active() is None
+    assert not entered and lzy.runtime.aborted == 1 and lzy.runtime.finished == 0 and LzyWorkflow.get_active() is None
 
 
 def test_invalid_workflow_name(lzy):
@@ -479,6 +481,15 @@ def test_hbm_runtime_lifecycle_without_a_device(monkeypatch):
     assert destroyed == [(inner_id, "finished"), (outer_id, "aborted")]
     run(rt.abort())  # a second abort finds nothing to do
     assert len(destroyed) == 2
+
+    # told whose end it is (LzyWorkflow does that when the runtime offers it), the runtime ends that one only
+    outer_id, inner_id = run(rt.start(outer)), run(rt.start(inner))
+    run(rt.abort_workflow(SimpleNamespace(name="never started")))
+    assert len(destroyed) == 2 and rt._execution_of(inner) == inner_id
+    run(rt.finish_workflow(outer))  # not the innermost
+    assert destroyed[-1] == (outer_id, "finished") and rt._execution_of(inner) == inner_id
+    run(rt.abort_workflow(inner))
+    assert destroyed[-1] == (inner_id, "aborted")
     with pytest.raises(ValueError, match="Runtime is not running"):
         run(rt.exec([], lambda step: None))
 
@@ -544,3 +555,39 @@ def test_decorating_and_calling_an_op_behaves_as_the_reference_wrapper_does():
                             registry=LzySerializerRegistry()))
     assert LzyWorkflow.instance is None
     assert json.loads(json.dumps(ours)) == json.loads((golden / "reference_wrapper_vectors.json").read_text())
+
+
+def test_workflow_lifecycle_drives_a_runtime_as_the_reference_workflow_does(monkeypatch):
+    """tests/golden/reference_lifecycle_vectors.json: pylzy's own LzyWorkflow (executed in the authoring container) over a
+    recording runtime — start on entry; queued calls run on exit, on barrier() (an empty queue asks nobody) or one by
+    one when eager; finish after a clean block; abort — without running the queue — after an exception in the block,
+    after a failed graph, and after a start that raised; nothing left active; local data under
+    ``<storage>/[<user>/]lzy_runs/<name>/inputs/``"""
+    import importlib.util
+    import json
+    from pathlib import Path
+    from types import SimpleNamespace
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("lifecycle_battery", golden / "lifecycle_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+
+    def make(name, runtime, log, eager):
+        snapshot = SimpleNamespace(prefix=None, entries={})
+        snapshot.get = snapshot.entries.__getitem__
+
+        def make_snapshot(workflow, prefix):
+            snapshot.prefix = prefix
+            return snapshot
+
+        owner = SimpleNamespace(storage_uri="s3://bucket/prefix", runtime=runtime, make_snapshot=make_snapshot)
+        return LzyWorkflow(name=name, owner=owner, env=None, eager=eager)
+
+    for expected in json.loads((golden / "reference_lifecycle_vectors.json").read_text()):
+        monkeypatch.delenv("LZY_USER", raising=False)
+        if expected["user"] is not None:
+            monkeypatch.setenv("LZY_USER", expected["user"])
+        ours = battery.run(dict(make_workflow=make, active=lambda: getattr(LzyWorkflow.get_active(), "name", None)),
+                           expected["user"])
+        assert json.loads(json.dumps(ours)) == expected
