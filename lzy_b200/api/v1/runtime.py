@@ -9,7 +9,11 @@ Call order, as ``LzyWorkflow`` drives it (pylzy/lzy/core/workflow.py:173-236):
     exec(calls, progress) …            once per barrier, with the queued calls in submission order
     finish()  |  abort()               once, on ``__exit__``: finish after a clean block, abort after any exception
 
-``snapshot()`` is this package's one addition: the workflow asks its runtime for the ``Snapshot`` to keep entries
+A runtime that keeps several executions apart (an op body may open a workflow of its own on the same runtime) can
+additionally offer ``finish_workflow(workflow)`` / ``abort_workflow(workflow)``; ``LzyWorkflow`` calls those instead of
+``finish()`` / ``abort()`` when they exist.  Stock runtimes need not know about them.
+
+``snapshot()`` is this package's other addition: the workflow asks its runtime for the ``Snapshot`` to keep entries
 in, where the reference hard-wires ``DefaultSnapshot`` over a storage client (pylzy/lzy/core/workflow.py:133-146;
 the alternative seam named in pylzy/lzy/api/v1/snapshot.py:55-74).  The HBM runtime answers with a snapshot whose
 entries are frames in device memory."""
