@@ -38,6 +38,9 @@
 * reference_startup_vectors.json — the reference's own op-side entry point (pylzy/lzy/api/v1/startup.py: process_execution)
   run over slot files for the scenarios of tests/golden/startup_battery.py: which slots get written, what the
   exception slot holds, what is raised, what is left of LZY_OP_MAIN_PID.
+* reference_request_vector.json — a ProcessingRequest built from the reference's own dataclass and encoded by its own pickle():
+  the text a stock client puts on a task's command line; after install_as_lzy() ours must decode it into its own
+  ProcessingRequest with the same fields.
 * reference_pickle_vectors.json — what the reference's request encoding (pylzy/lzy/api/v1/utils/pickle.py) emits
   for a few objects; ours must decode them and encode the same text.
 * digest_vectors.json — known answers of the data plane's digest from the oracle's C restatement
@@ -382,6 +385,32 @@ def main():
         files = file_battery.run(dict(File=ref_lzy_types.File, serialize=ref_file_serializer._serialize,
                                       deserialize=lambda source: ref_file_serializer._deserialize(source, ref_lzy_types.File)), d)
     (ROOT / "tests/golden/reference_file_vectors.json").write_text(json.dumps(files, indent=1, sort_keys=True))
+
+    # a task's command-line request as a stock client pickles it: the reference's own ProcessingRequest dataclass, its module
+    # registered under its real name so that the pickle refers to lzy.api.v1.startup, encoded by the reference's own
+    # pickle().  (SerializerImport's home, lzy/serialization/registry.py, cannot be loaded without serialzy: a dataclass
+    # with the same three fields and the same module path stands in — a pickle holds nothing else of it.)
+    import dataclasses
+
+    @dataclasses.dataclass
+    class SerializerImportStandIn:
+        module_name: str
+        class_name: str
+        priority: int
+
+    SerializerImportStandIn.__module__, SerializerImportStandIn.__qualname__ = "lzy.serialization.registry", "SerializerImport"
+    SerializerImportStandIn.__name__ = "SerializerImport"
+    sys.modules["lzy.serialization.registry"].SerializerImport = SerializerImportStandIn
+    stock_startup = load_as(REF / "lzy/api/v1/startup.py", "lzy.api.v1.startup")
+    stock_request = stock_startup.ProcessingRequest(
+        {"version": 1}, [SerializerImportStandIn("some.module", "SomeSerializer", 7)], len, [(list, "/call-1/e-1")],
+        {"k": (int, "/call-1/e-2")}, [(int, "/call-1/e-3")], (tuple, "/call-1/e-4"), lazy_arguments=False)
+    (ROOT / "tests/golden/reference_request_vector.json").write_text(json.dumps({
+        "text": sys.modules["lzy.api.v1.utils.pickle"].pickle(stock_request),
+        "fields": {"logger_config": {"version": 1}, "serializers": [["some.module", "SomeSerializer", 7]], "op": "builtins.len",
+                   "args_paths": [["list", "/call-1/e-1"]], "kwargs_paths": {"k": ["int", "/call-1/e-2"]},
+                   "output_paths": [["int", "/call-1/e-3"]], "exception_path": ["tuple", "/call-1/e-4"], "lazy_arguments": False}},
+        indent=1))
 
     ref_pickle = load(REF / "lzy/api/v1/utils/pickle.py", "ref_pickle")
     objs = [None, 42, -1.5, "ʎzy", b"\x00\xff", [1, "two", 3.0], {"k": (1, 2), "n": None}, (str, "/call/entry"), {1, 2, 3}]

@@ -239,3 +239,28 @@ def test_process_execution_behaves_as_the_reference_entry_point_does(tmp_path):
     assert set(ours) == set(reference) and len(reference) == 13
     for tag, expected in reference.items():
         assert json.loads(json.dumps(ours[tag])) == expected, tag
+
+
+def test_a_request_encoded_by_the_reference_dataclass_decodes_into_ours():
+    """tests/golden/reference_request_vector.json: a ProcessingRequest built from pylzy's own dataclass and encoded by its
+    own pickle() (in the authoring container) — what a stock client puts on a task's command line.  With
+    install_as_lzy() the names in it (lzy.api.v1.startup.ProcessingRequest, lzy.serialization.registry.SerializerImport)
+    resolve to this package's classes and every field arrives"""
+    import json
+    from pathlib import Path
+
+    import lzy_b200
+    from lzy_b200.api.v1.utils.pickle import unpickle
+    from lzy_b200.serialization.registry import SerializerImport
+
+    lzy_b200.install_as_lzy()
+    vector = json.loads((Path(__file__).parent / "golden" / "reference_request_vector.json").read_text())
+    req = unpickle(vector["text"])
+    assert type(req) is ProcessingRequest and all(type(s) is SerializerImport for s in req.serializers)
+    fields = vector["fields"]
+    assert req.logger_config == fields["logger_config"] and req.op is len and req.lazy_arguments is fields["lazy_arguments"]
+    assert [[s.module_name, s.class_name, s.priority] for s in req.serializers] == fields["serializers"]
+    named = lambda typ, path: [typ.__name__, path]  # noqa: E731
+    assert [named(*p) for p in req.args_paths] == fields["args_paths"]
+    assert {k: named(*p) for k, p in req.kwargs_paths.items()} == fields["kwargs_paths"]
+    assert [named(*p) for p in req.output_paths] == fields["output_paths"] and named(*req.exception_path) == fields["exception_path"]
