@@ -41,6 +41,8 @@
 * reference_request_vector.json — a ProcessingRequest built from the reference's own dataclass and encoded by its own pickle():
   the text a stock client puts on a task's command line; after install_as_lzy() ours must decode it into its own
   ProcessingRequest with the same fields.
+* reference_registry_vectors.json — the reference's own LzySerializerRegistry subclass (serialization/registry.py) over a stand-in base
+  on tests/golden/registry_battery.py: user serializers shipped as imports, load_imports, the __main__ ban, copyreg.
 * reference_pickle_vectors.json — what the reference's request encoding (pylzy/lzy/api/v1/utils/pickle.py) emits
   for a few objects; ours must decode them and encode the same text.
 * digest_vectors.json — known answers of the data plane's digest from the oracle's C restatement
@@ -411,6 +413,29 @@ def main():
                    "args_paths": [["list", "/call-1/e-1"]], "kwargs_paths": {"k": ["int", "/call-1/e-2"]},
                    "output_paths": [["int", "/call-1/e-3"]], "exception_path": ["tuple", "/call-1/e-4"], "lazy_arguments": False}},
         indent=1))
+
+    # lzy.serializer_registry: the reference's own subclass over a stand-in for serialzy's DefaultSerializerRegistry (this
+    # package's base registry plus the empty _type_registry the subclass iterates) — what is pinned is the subclass's own
+    # logic: user serializers tracked and shipped as imports, the __main__ ban, copyreg hooks
+    from lzy_b200.serialization.api import SerializerRegistry as OurBaseRegistry
+
+    class StandInDefaultRegistry(OurBaseRegistry):
+        def __init__(self):
+            super().__init__()
+            self._type_registry = {}
+
+    api_stub.Serializer = object
+    stub("serialzy.registry", DefaultSerializerRegistry=StandInDefaultRegistry)
+    sys.modules["serialzy.base"].DefaultSchemaSerializerByReference = type("DefaultSchemaSerializerByReference", (), {
+        "_check_types_valid": lambda self, schema_type, user_type: None,
+        "handles": lambda self, typ: typ == self.supported_types(),
+        "serialize": lambda self, obj, dest: self._serialize(obj, dest),
+        "deserialize": lambda self, source, typ=None: self._deserialize(source, typ)})
+    load_as(REF / "lzy/serialization/file.py", "lzy.serialization.file")
+    ref_registry = load_as(REF / "lzy/serialization/registry.py", "ref_registry")
+    registry_battery = load(ROOT / "tests/golden/registry_battery.py", "registry_battery")
+    (ROOT / "tests/golden/reference_registry_vectors.json").write_text(
+        json.dumps(registry_battery.run(dict(new_registry=ref_registry.LzySerializerRegistry)), indent=1, sort_keys=True))
 
     ref_pickle = load(REF / "lzy/api/v1/utils/pickle.py", "ref_pickle")
     objs = [None, 42, -1.5, "ʎzy", b"\x00\xff", [1, "two", 3.0], {"k": (1, 2), "n": None}, (str, "/call/entry"), {1, 2, 3}]

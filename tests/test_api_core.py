@@ -591,3 +591,22 @@ def test_workflow_lifecycle_drives_a_runtime_as_the_reference_workflow_does(monk
         ours = battery.run(dict(make_workflow=make, active=lambda: getattr(LzyWorkflow.get_active(), "name", None)),
                            expected["user"])
         assert json.loads(json.dumps(ours)) == expected
+
+
+def test_user_serializers_are_tracked_and_shipped_as_the_reference_registry_does():
+    """tests/golden/reference_registry_vectors.json: pylzy's own LzySerializerRegistry (executed in the authoring container
+    over a stand-in for serialzy's base registry) — built-ins are not shipped, user serializers are, as (module, class,
+    priority); load_imports brings them up elsewhere; ``__main__`` is refused with the reference's message;
+    unregistering forgets and removes the copyreg hook; a registered type nested in a pickle round-trips"""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    from lzy_b200.serialization.registry import LzySerializerRegistry
+
+    golden = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("registry_battery", golden / "registry_battery.py")
+    battery = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(battery)
+    ours = battery.run(dict(new_registry=LzySerializerRegistry))
+    assert json.loads(json.dumps(ours)) == json.loads((golden / "reference_registry_vectors.json").read_text())
