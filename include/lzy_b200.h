@@ -255,6 +255,11 @@ int lzyb_ring_frame_info(uint64_t ring_off, lzyb_frame_header_t* out);
 int lzyb_ring_release(uint64_t ring_off);
 
 /* ---- utilities ----------------------------------------------------------------------------- */
+/* Content address of a framed value = payload digest ⊕ (dtype|flags, ndim, shape): what storage URIs and the
+ * snapshot's data_hash are built from (the reference's md5 covers the serialized stream, dtype and shape
+ * included: pylzy/lzy/api/v1/snapshot.py:147-155).  Pure host arithmetic (include/lzyb_digest.h), needs no GPU. */
+int lzyb_content_key(const uint64_t digest[2], uint32_t dtype_flags, uint32_t ndim, const uint64_t* shape,
+                     uint64_t key_out[2]);
 int lzyb_digest_device(int gpu, const void* dptr, uint64_t nbytes, uint64_t digest_out[2], void* stream);
 /* deterministic 64-bit LCG fill (BASELINE config C3's payload) */
 int lzyb_fill_pattern(int gpu, void* dptr, uint64_t nbytes, uint64_t seed, void* stream);
@@ -289,7 +294,9 @@ enum lzyb_fault {
     LZYB_FAULT_NONE = 0,
     LZYB_FAULT_PEER_AFTER = 1,   /* transfer_chunk returns LZYB_E_PEER once `arg` bytes were delivered */
     LZYB_FAULT_CORRUPT_ONCE = 2, /* flip one payload byte at offset `arg` after the next chunk lands   */
-    LZYB_FAULT_LOCAL_OPEN = 3    /* next input_open fails with LZYB_E_LOCAL                            */
+    LZYB_FAULT_LOCAL_OPEN = 3,   /* next input_open fails with LZYB_E_LOCAL                            */
+    LZYB_FAULT_SLAB_RESERVE = 4  /* (handle 0) treat `arg` per-device slot control entries as taken, so slab
+                                    exhaustion can be provoked without 8192 live slots; 0 restores          */
 };
 int lzyb_fault_inject(lzyb_handle_t slot_or_zero, int kind, uint64_t arg);
 

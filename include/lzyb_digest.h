@@ -58,4 +58,28 @@ LZYB_HD void lzyb_digest_finalize(uint64_t sum, uint64_t xr, uint64_t nbytes, ui
     out[1] = lo ^ (hi >> 1);
 }
 
+/*
+ * Content address of a framed VALUE.  The payload digest is blind to how the bytes are to be read: dtype,
+ * serializer flags, rank and shape live in the frame header, so zeros(4, f32) and zeros(4, i32), or one buffer
+ * viewed as (2, 8) and as (4, 4), share a payload digest.  The reference hashes the serialized stream, which
+ * carries dtype and shape (pylzy/lzy/api/v1/snapshot.py:147-155), so its md5 tells such values apart; the key
+ * below does the same for a frame: an order-dependent chain over (dtype|flags, ndim, shape[0..ndim)) folded into
+ * both halves of the digest.  Storage URIs, `data_hash` and hence `cache=True` result URIs are built from this
+ * key, never from the bare payload digest.
+ *
+ * Scope: like the digest itself this is an error-detecting / de-duplicating code over honest data, not a
+ * cryptographic hash — (sum, xor) of bijectively mixed words admits constructed second preimages.
+ */
+#define LZYB_K_META 0xA0761D6478BD642Full
+
+LZYB_HD void lzyb_content_key_fold(const uint64_t digest[2], uint32_t dtype_flags, uint32_t ndim, const uint64_t* shape,
+                              uint64_t out[2]) {
+    uint64_t h = lzyb_mix64((((uint64_t)dtype_flags << 32) | (uint64_t)ndim) ^ LZYB_K_META);
+    for (uint32_t i = 0; i < ndim; ++i) h = lzyb_mix64(h ^ lzyb_mix64(shape[i] + ((uint64_t)i + 1ull) * LZYB_K_POS));
+    uint64_t hi = lzyb_mix64(digest[0] ^ h);
+    uint64_t lo = lzyb_mix64(digest[1] + ((h << 32) | (h >> 32)) + LZYB_K_LEN);
+    out[0] = hi;
+    out[1] = lo ^ (hi >> 1);
+}
+
 #endif /* LZYB_DIGEST_H */

@@ -158,6 +158,9 @@ struct Slot {
     int fault_kind = LZYB_FAULT_NONE;
     uint64_t fault_arg = 0;
     std::atomic<int> refs{1};    // lzyb_slot_retain / lzyb_slot_close
+    // asynchronous readers of this frame inside this process (consumer stream → event recorded after its last
+    // pull launch): close waits for them before the frame goes back to the pool
+    std::vector<std::pair<cudaStream_t, cudaEvent_t>> readers;
     std::mutex mu;
     uint8_t* payload() const { return buf + HEADER_BYTES; }
 };
@@ -193,6 +196,7 @@ struct Global {
     std::atomic<int> tma_cfg{1};  // 3 × 32 KiB, 2 CTAs/SM: best of the sweep in profiles/r01_microbench_local.jsonl
     std::atomic<int> ctas_per_sm{GRID_AUTO};
     std::atomic<int> global_fault{LZYB_FAULT_NONE};
+    std::atomic<int> ctl_reserve{0};  // test hook (LZYB_FAULT_SLAB_RESERVE): pretend this many SlotCtl entries are taken
     std::atomic<uint64_t> dma_last_bytes{0};  // last sub-chunk of a copy-engine pull (0 = total/32 in 4..32 MiB)
     std::atomic<int> dma_growth{6};            // each earlier sub-chunk is this many times larger
     // stats
@@ -469,21 +473,30 @@ int new_slot(const char* slot_id, int gpu, uint64_t nbytes, bool is_input, lzyb_
     if (rc != LZYB_OK) return rc;
     {
         std::lock_guard<std::mutex> lk(d.mu);
-        if (d.ctl_free.empty()) {
-            free_frame(d, s->buf, s->cap);
-            return fail(LZYB_E_LOCAL, "too many live slots on GPU %d", gpu);
+        if (!d.ctl_free.empty() && (int)d.ctl_free.size() > g.ctl_reserve.load()) {
+            s->ctl_idx = d.ctl_free.back();
+            d.ctl_free.pop_back();
+            s->ctl = d.ctl_slab + s->ctl_idx;
         }
-        s->ctl_idx = d.ctl_free.back();
-        d.ctl_free.pop_back();
-        s->ctl = d.ctl_slab + s->ctl_idx;
+    }
+    if (s->ctl_idx < 0) {  // decided under d.mu, undone outside it: free_frame takes d.mu itself
+        free_frame(d, s->buf, s->cap);
+        return fail(LZYB_E_LOCAL, "too many live slots on GPU %d", gpu);
     }
     {
         std::lock_guard<std::mutex> lk(g.mbox_mu);
-        if (g.mbox_free.empty()) return fail(LZYB_E_LOCAL, "out of mailboxes");
-        s->mbox_idx = g.mbox_free.back();
-        g.mbox_free.pop_back();
-        s->mbox = g.mbox_slab + s->mbox_idx;
-        memset((void*)s->mbox, 0, sizeof(Mailbox));
+        if (!g.mbox_free.empty()) {
+            s->mbox_idx = g.mbox_free.back();
+            g.mbox_free.pop_back();
+            s->mbox = g.mbox_slab + s->mbox_idx;
+            memset((void*)s->mbox, 0, sizeof(Mailbox));
+        }
+    }
+    if (s->mbox_idx < 0) {  // give back what this slot already took
+        free_frame(d, s->buf, s->cap);
+        std::lock_guard<std::mutex> lk(d.mu);
+        d.ctl_free.push_back(s->ctl_idx);
+        return fail(LZYB_E_LOCAL, "out of mailboxes");
     }
     s->handle = g.next_handle++;
     {
@@ -922,6 +935,11 @@ int lzyb_slot_close(lzyb_handle_t h) {
         cudaEventDestroy(s->last_ev);
         s->last_ev = nullptr;
     }
+    for (auto& r : s->readers) {  // pulls other slots of this process queued against this frame
+        cudaEventSynchronize(r.second);
+        cudaEventDestroy(r.second);
+    }
+    s->readers.clear();
     if (s->remote) {
         // the mapping stays in g.ipc_cache (closed at shutdown)
     } else if (s->buf) {
@@ -1016,6 +1034,16 @@ int64_t lzyb_transfer_chunk(lzyb_handle_t dst_h, lzyb_handle_t src_h, uint64_t o
     if (!stream) {
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "transfer failed: %s", cudaGetErrorString(e));
+    } else if (!src->remote) {
+        // an asynchronous reader: the source frame must not be recycled under it (one event per consumer stream)
+        cudaEvent_t ev = nullptr;
+        for (auto& r : src->readers)
+            if (r.first == st) ev = r.second;
+        if (!ev) {
+            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            src->readers.emplace_back(st, ev);
+        }
+        cudaEventRecord(ev, st);
     }
     return (int64_t)len;
 }
@@ -1229,6 +1257,11 @@ int lzyb_peer_import(const lzyb_ipc_desc_t* desc, int onto_gpu, lzyb_handle_t* o
     int di = onto_gpu - g.first;
     if (di < 0 || di >= (int)g.devs.size()) return fail(LZYB_E_ARG, "GPU %d is not managed by this process", onto_gpu);
     if (desc->pid == (int32_t)getpid()) return fail(LZYB_E_ARG, "descriptor comes from this process; use the slot handle");
+    // the descriptor crossed a process boundary: nothing in it is trusted to size an access
+    if (desc->ndim > LZYB_MAX_DIMS) return fail(LZYB_E_PEER, "peer descriptor: ndim %u > %d", desc->ndim, LZYB_MAX_DIMS);
+    if (desc->buffer_bytes < HEADER_BYTES || desc->nbytes > desc->buffer_bytes - HEADER_BYTES)
+        return fail(LZYB_E_PEER, "peer descriptor: payload of %llu bytes does not fit its %llu-byte frame",
+                    (unsigned long long)desc->nbytes, (unsigned long long)desc->buffer_bytes);
     DeviceCtx& d = *g.devs[di];
     DeviceGuard dg(d.ordinal);
     cudaIpcMemHandle_t mh;
@@ -1663,6 +1696,13 @@ int lzyb_ring_release(uint64_t ring_off) {
 
 // ---- utilities ---------------------------------------------------------------------------------
 
+int lzyb_content_key(const uint64_t digest[2], uint32_t dtype_flags, uint32_t ndim, const uint64_t* shape, uint64_t key_out[2]) {
+    if (!digest || !key_out || (ndim && !shape)) return fail(LZYB_E_ARG, "null argument");
+    if (ndim > LZYB_MAX_DIMS) return fail(LZYB_E_ARG, "ndim %u > %d", ndim, LZYB_MAX_DIMS);
+    lzyb_content_key_fold(digest, dtype_flags, ndim, shape, key_out);
+    return LZYB_OK;
+}
+
 int lzyb_digest_device(int gpu, const void* dptr, uint64_t nbytes, uint64_t digest_out[2], void* stream) {
     if (!g.inited) return fail(LZYB_E_STATE, "lzyb_init has not been called (or found no GPU)");
     int di = gpu - g.first;
@@ -1770,6 +1810,10 @@ int lzyb_set_grid(int ctas_per_sm) {
 
 int lzyb_fault_inject(lzyb_handle_t h, int kind, uint64_t arg) {
     if (h == 0) {
+        if (kind == LZYB_FAULT_SLAB_RESERVE) {
+            g.ctl_reserve = (int)std::min<uint64_t>(arg, CTL_SLAB);
+            return LZYB_OK;
+        }
         g.global_fault = kind;
         return LZYB_OK;
     }

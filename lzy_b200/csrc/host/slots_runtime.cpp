@@ -200,8 +200,15 @@ int spill_read(const std::string& path, const std::string& uri, int gpu, lzyb_ha
     }
     lzyb_frame_header_t hdr;
     memset(&hdr, 0, sizeof(hdr));
-    bool framed = (uint64_t)st.st_size >= sizeof(hdr) && read_fully(fd, &hdr, sizeof(hdr)) && memcmp(hdr.magic, "LZYB200", 8) == 0 &&
-                  hdr.nbytes + sizeof(hdr) == (uint64_t)st.st_size && hdr.ndim <= LZYB_MAX_DIMS;
+    const bool magic = (uint64_t)st.st_size >= sizeof(hdr) && read_fully(fd, &hdr, sizeof(hdr)) && memcmp(hdr.magic, "LZYB200", 8) == 0;
+    const bool framed = magic && hdr.nbytes + sizeof(hdr) == (uint64_t)st.st_size && hdr.ndim <= LZYB_MAX_DIMS;
+    if (magic && !framed) {
+        // a frame file that contradicts itself (truncated payload, impossible rank) is rotten, not foreign: serving
+        // header + partial payload as bytes would hand consumers wrong data under a valid-looking digest
+        ::close(fd);
+        return fail(LZYB_E_PEER, "corrupt frame file for %s: header says %llu payload bytes, ndim %u; file has %llu bytes", uri.c_str(),
+                    (unsigned long long)hdr.nbytes, hdr.ndim, (unsigned long long)st.st_size);
+    }
     uint64_t nbytes = framed ? hdr.nbytes : (uint64_t)st.st_size;
     if (!framed) ::lseek(fd, 0, SEEK_SET);
     static std::atomic<uint64_t> seq{0};
@@ -251,6 +258,7 @@ void make_parent_dirs(const std::string& path) {
 // what a stored file says about itself without reading the payload
 struct StoredFile {
     bool framed = false;
+    bool corrupt = false;  // carries the frame magic but its header contradicts the file
     lzyb_frame_header_t hdr{};
     uint64_t nbytes = 0;
 };
@@ -261,9 +269,10 @@ bool stat_stored_file(const std::string& path, StoredFile* out) {
     struct stat st;
     bool ok = ::fstat(fd, &st) == 0;
     if (ok) {
-        out->framed = (uint64_t)st.st_size >= sizeof(out->hdr) && read_fully(fd, &out->hdr, sizeof(out->hdr)) &&
-                      memcmp(out->hdr.magic, "LZYB200", 8) == 0 && out->hdr.nbytes + sizeof(out->hdr) == (uint64_t)st.st_size &&
-                      out->hdr.ndim <= LZYB_MAX_DIMS;
+        const bool magic = (uint64_t)st.st_size >= sizeof(out->hdr) && read_fully(fd, &out->hdr, sizeof(out->hdr)) &&
+                           memcmp(out->hdr.magic, "LZYB200", 8) == 0;
+        out->framed = magic && out->hdr.nbytes + sizeof(out->hdr) == (uint64_t)st.st_size && out->hdr.ndim <= LZYB_MAX_DIMS;
+        out->corrupt = magic && !out->framed;
         out->nbytes = out->framed ? out->hdr.nbytes : (uint64_t)st.st_size;
     }
     ::close(fd);
@@ -783,6 +792,10 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
             t->path = file_path_of(p.url);
             if (!stat_stored_file(t->path, &t->info)) {
                 err = std::string("Error while reading from storage: no object at ") + p.url;
+                return nullptr;
+            }
+            if (t->info.corrupt) {  // a rotten frame file is a read fault of this peer, never foreign bytes
+                err = std::string("Error while reading from storage: corrupt frame file at ") + p.url;
                 return nullptr;
             }
             return t;
