@@ -60,7 +60,8 @@ enum lzyb_slot_state {
     LZYB_ST_FILLING = 1,   /* input slot: download in progress (InputSlot.State.DOWNLOADING)       */
     LZYB_ST_READY = 2,     /* committed / fully downloaded and verified                            */
     LZYB_ST_FAILED = 3,
-    LZYB_ST_CLOSED = 4
+    LZYB_ST_CLOSED = 4,
+    LZYB_ST_MOVED = 5      /* output slot whose frame went to its sole consumer (lzyb_slot_set_movable)      */
 };
 
 #define LZYB_MAX_DIMS 8
@@ -128,6 +129,8 @@ typedef struct lzyb_stats_s {
     uint64_t hbm_bytes_live;
     uint64_t hbm_bytes_pooled;
     uint64_t dma_copies;       /* copy-engine sub-chunk copies issued by peer pulls (engine 3 / auto)  */
+    uint64_t push_launches;    /* push_kernel launches (source side of a GPU→GPU transfer)             */
+    uint64_t frames_moved;     /* same-GPU deliveries done by ownership hand-over instead of a copy    */
 } lzyb_stats_t;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -187,6 +190,13 @@ int lzyb_slot_header(lzyb_handle_t h, lzyb_frame_header_t* out);   /* D2H copy o
  * reference counted: every lzyb_slot_retain() needs one more close before the HBM is released. */
 int lzyb_slot_close(lzyb_handle_t h);
 int lzyb_slot_retain(lzyb_handle_t h);
+/* The owner of a committed output slot declares that the channel has exactly ONE consumer and no other reader (what
+ * the channel manager knows from its peer table, channel-manager/.../services/SlotsService.java:440-519).  A whole-
+ * payload lzyb_transfer_chunk from this slot by a consumer on the same GPU then MOVES the frame instead of copying
+ * it — InputSlotBackend.toOutput()'s ownership hand-over (FileInputBackend.java:38-45) applied to the producer →
+ * consumer edge — provided nobody else holds the frame (no lzyb_slot_retain outstanding).  The producer slot reads
+ * LZYB_ST_MOVED afterwards (further reads fail with LZYB_E_PEER).  Off by default: a slot may have late consumers. */
+int lzyb_slot_set_movable(lzyb_handle_t h, int movable);
 /* look a slot up by id (SlotsService.slots map, lzy/slots/.../SlotsService.java:21-30) */
 int lzyb_slot_find(const char* slot_id, lzyb_handle_t* out);
 
@@ -233,6 +243,20 @@ int lzyb_input_reset(lzyb_handle_t h);
 /* ---- cross-process peers -------------------------------------------------------------------- */
 int lzyb_slot_export(lzyb_handle_t h, lzyb_ipc_desc_t* out);
 int lzyb_peer_import(const lzyb_ipc_desc_t* desc, int onto_gpu, lzyb_handle_t* out);
+/* Producer-issued PUSH between worker processes (the in-process case is inside lzyb_transfer_chunk).  SM-issued
+ * NVLink traffic costs a pull 1.31 wire bytes per payload byte once both directions of a GPU are busy (requests share
+ * the wire with the payload it serves) and a push 1.19 (profiles/r02_peer_variants_ncu.csv), so between processes the
+ * consumer exports its empty input frame, the PRODUCER's process runs push_kernel into it, and the consumer's GPU runs
+ * landed_scan_kernel, which digests every chunk as its progress counter (in the frame's trailer, written by the
+ * pusher with red.release.sys) says it has landed.  No copy engine, no cross-process event: the consumer learns
+ * completion and verdict from its own scan.
+ *   consumer:  lzyb_input_open → lzyb_sink_export(desc) → [desc travels to the producer] →
+ *              lzyb_input_expect_push(dst, producer's slot descriptor, offset, len, stream) → lzyb_input_finish_expect
+ *   producer:  lzyb_slot_push(src, sink desc, offset, len, stream)
+ * offset/len as in lzyb_transfer_chunk (offset % 16 == 0; len == 0 means "to the end"). */
+int lzyb_sink_export(lzyb_handle_t input, lzyb_ipc_desc_t* out);
+int lzyb_slot_push(lzyb_handle_t src, const lzyb_ipc_desc_t* sink, uint64_t offset, uint64_t len, void* stream);
+int64_t lzyb_input_expect_push(lzyb_handle_t dst, const lzyb_ipc_desc_t* producer, uint64_t offset, uint64_t len, void* stream);
 
 /* ---- fan-out ------------------------------------------------------------------------------ */
 /* One producer, n consumers on distinct GPUs of this process (SlotsService.bind creates one
@@ -268,10 +292,14 @@ int lzyb_stats(lzyb_stats_t* out);
 int lzyb_stats_reset(void);
 /* how large contiguous transfers are carried: 0 = auto, 1 = LDG/STG 16-B vectors, 2 = TMA bulk
  * (cp.async.bulk + mbarrier ring), 3 = peer pulls ride the copy engine in sub-chunks while a scan kernel on
- * the sink GPU digests each landed sub-chunk in the shadow of the next copy (same-GPU work as in auto).
- * auto = 3 for peer pulls of at least 256 MiB (the engine keeps 772 GB/s per direction with both directions of
- * a GPU pair busy, SM loads 670), the fused kernels for everything else */
+ * the sink GPU digests each landed sub-chunk in the shadow of the next copy (same-GPU work as in auto),
+ * 4 = GPU→GPU transfers inside this process are pushed by push_kernel on the source GPU with landed_scan_kernel
+ * trailing on the sink GPU (same-GPU work as in auto).
+ * auto = 4 for in-process GPU→GPU transfers of at least lzyb_set_push_min_bytes (default 8 MiB); a source mapped
+ * from another process is pulled: TMA ring below 256 MiB, 3 from there (its owner can push: lzyb_slot_push);
+ * the fused LDG/STG kernel for everything on one GPU.  The copy engine is never used by auto inside one process. */
 int lzyb_set_copy_engine(int engine);
+int lzyb_set_push_min_bytes(uint64_t nbytes);
 /* sub-chunk schedule of a copy-engine pull: the last sub-chunk is last_bytes (0 = payload/32 clamped to
  * 4..32 MiB; else a multiple of 16, at least 1 MiB), each earlier one `growth` times larger (default 6; 1 =
  * uniform), the first takes the remainder */

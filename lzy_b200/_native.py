@@ -23,14 +23,14 @@ E_PEER, E_LOCAL, E_ARG, E_STATE, E_NOGPU = -2, -3, -4, -5, -6
 E_NOT_FOUND, E_PRECONDITION, E_UNAVAILABLE, E_INTERNAL = -7, -8, -9, -10
 E_UNIMPLEMENTED, E_INVALID, E_EXISTS = -11, -12, -13
 
-ST_EMPTY, ST_FILLING, ST_READY, ST_FAILED, ST_CLOSED = 0, 1, 2, 3, 4
+ST_EMPTY, ST_FILLING, ST_READY, ST_FAILED, ST_CLOSED, ST_MOVED = 0, 1, 2, 3, 4, 5
 
 DT_BYTES, DT_U8, DT_I8, DT_I16, DT_I32, DT_I64 = 0, 1, 2, 3, 4, 5
 DT_F16, DT_BF16, DT_F32, DT_F64, DT_BOOL = 6, 7, 8, 9, 10
 DT_U16, DT_U32, DT_U64, DT_PICKLE = 11, 12, 13, 32
 
-FAULT_NONE, FAULT_PEER_AFTER, FAULT_CORRUPT_ONCE, FAULT_LOCAL_OPEN = 0, 1, 2, 3
-ENGINE_AUTO, ENGINE_LDG, ENGINE_TMA, ENGINE_DMA = 0, 1, 2, 3
+FAULT_NONE, FAULT_PEER_AFTER, FAULT_CORRUPT_ONCE, FAULT_LOCAL_OPEN, FAULT_SLAB_RESERVE = 0, 1, 2, 3, 4
+ENGINE_AUTO, ENGINE_LDG, ENGINE_TMA, ENGINE_DMA, ENGINE_PUSH = 0, 1, 2, 3, 4
 MAX_DIMS = 8
 
 
@@ -104,7 +104,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "kernel_launches", "pack_launches", "pull_launches", "scan_launches", "frame_launches",
         "bytes_packed", "bytes_pulled_local", "bytes_pulled_peer", "bytes_framed_host",
-        "h2d_bytes", "d2h_bytes", "slots_live", "hbm_bytes_live", "hbm_bytes_pooled", "dma_copies")]
+        "h2d_bytes", "d2h_bytes", "slots_live", "hbm_bytes_live", "hbm_bytes_pooled", "dma_copies",
+        "push_launches", "frames_moved")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -144,6 +145,7 @@ _SIGNATURES = {
     "lzyb_slot_header": (C.c_int, [_H, C.POINTER(FrameHeader)]),
     "lzyb_slot_close": (C.c_int, [_H]),
     "lzyb_slot_retain": (C.c_int, [_H]),
+    "lzyb_slot_set_movable": (C.c_int, [_H, C.c_int]),
     "lzyb_slot_find": (C.c_int, [C.c_char_p, C.POINTER(_H)]),
     "lzyb_input_open": (C.c_int, [C.c_char_p, C.c_int, C.c_uint64, C.POINTER(_H)]),
     "lzyb_transfer_chunk": (C.c_int64, [_H, _H, C.c_uint64, C.c_uint64, _P]),
@@ -155,6 +157,10 @@ _SIGNATURES = {
     "lzyb_input_reset": (C.c_int, [_H]),
     "lzyb_slot_export": (C.c_int, [_H, C.POINTER(IpcDesc)]),
     "lzyb_peer_import": (C.c_int, [C.POINTER(IpcDesc), C.c_int, C.POINTER(_H)]),
+    "lzyb_sink_export": (C.c_int, [_H, C.POINTER(IpcDesc)]),
+    "lzyb_slot_push": (C.c_int, [_H, C.POINTER(IpcDesc), C.c_uint64, C.c_uint64, _P]),
+    "lzyb_input_expect_push": (C.c_int64, [_H, C.POINTER(IpcDesc), C.c_uint64, C.c_uint64, _P]),
+    "lzyb_content_key": (C.c_int, [C.POINTER(C.c_uint64 * 2), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64 * 2)]),
     "lzyb_broadcast": (C.c_int, [_H, C.POINTER(_H), C.c_int, C.c_uint64]),
     "lzyb_frame_host_object": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "lzyb_ring_read": (C.c_int64, [C.c_uint64, _P, C.c_uint64]),
@@ -166,6 +172,7 @@ _SIGNATURES = {
     "lzyb_stats": (C.c_int, [C.POINTER(Stats)]),
     "lzyb_stats_reset": (C.c_int, []),
     "lzyb_set_copy_engine": (C.c_int, [C.c_int]),
+    "lzyb_set_push_min_bytes": (C.c_int, [C.c_uint64]),
     "lzyb_set_grid": (C.c_int, [C.c_int]),
     "lzyb_set_tma_config": (C.c_int, [C.c_int]),
     "lzyb_set_dma_schedule": (C.c_int, [C.c_uint64, C.c_int]),
@@ -312,6 +319,26 @@ class SlotHandle:
     def to_output(self) -> None:
         check(lib.lzyb_input_to_output(self.h))
 
+    # -- producer-issued push between processes (include/lzy_b200.h: lzyb_sink_export / lzyb_slot_push / lzyb_input_expect_push)
+    def sink_export(self) -> IpcDesc:
+        """consumer side: describe this (empty) input frame so that the producer's process can push into it"""
+        d = IpcDesc()
+        check(lib.lzyb_sink_export(self.h, C.byref(d)))
+        return d
+
+    def push(self, sink: IpcDesc, offset: int = 0, length: int = 0, stream: int = 0) -> None:
+        """producer side: push_kernel on this slot's GPU, stores landing in the sink frame over NVLink"""
+        check(lib.lzyb_slot_push(self.h, C.byref(sink), offset, length, stream or None))
+
+    def expect_push(self, producer: IpcDesc, offset: int = 0, length: int = 0, stream: int = 0) -> int:
+        """consumer side: landed_scan_kernel digests the chunks as the producer's push lands them; finish with
+        ``finish_expect(producer.digest)``"""
+        return check(lib.lzyb_input_expect_push(self.h, C.byref(producer), offset, length, stream or None))
+
+    def set_movable(self, movable: bool = True) -> None:
+        """declare a sole consumer: a whole-payload same-GPU transfer from this slot hands the frame over"""
+        check(lib.lzyb_slot_set_movable(self.h, int(movable)))
+
     def reset(self) -> None:
         check(lib.lzyb_input_reset(self.h))
 
@@ -405,6 +432,20 @@ def fill_pattern(gpu: int, dptr: int, nbytes: int, seed: int, stream: int = 0) -
 
 def set_copy_engine(engine: int) -> None:
     check(lib.lzyb_set_copy_engine(engine))
+
+
+def set_push_min_bytes(nbytes: int) -> None:
+    check(lib.lzyb_set_push_min_bytes(nbytes))
+
+
+def content_key(digest: Sequence[int], dtype_flags: int, shape: Sequence[int]) -> Tuple[int, int]:
+    """content address of a framed value: the payload digest with (dtype|flags, ndim, shape) folded in
+    (include/lzyb_digest.h: lzyb_content_key_fold).  Host arithmetic; works without a GPU."""
+    d = (C.c_uint64 * 2)(int(digest[0]), int(digest[1]))
+    out = (C.c_uint64 * 2)()
+    arr = (C.c_uint64 * max(1, len(shape)))(*[int(x) for x in shape])
+    check(lib.lzyb_content_key(C.byref(d), dtype_flags & 0xFFFFFFFF, len(shape), arr, C.byref(out)))
+    return int(out[0]), int(out[1])
 
 
 def set_dma_schedule(last_bytes: int = 0, growth: int = 6) -> None:

@@ -201,7 +201,10 @@ class FrameStore:
             slot = self.pack_object(data, typ, registry, factory, stream)
             digest = slot.commit(stream)  # waits for the pack: `data` may be reused as soon as put returns
         slot._keepalive = None
-        hexd = N.digest_hex(digest)
+        # the address covers how the bytes are to be read, not only the bytes: equal payloads of another dtype, shape
+        # or serializer are different values (the reference's md5 runs over the serialized stream, snapshot.py:147-155)
+        info = slot.info()
+        hexd = N.digest_hex(N.content_key(digest, int(info.dtype), [int(info.shape[i]) for i in range(int(info.ndim))]))
         uri = prefix + hexd
         with self._lock:
             if uri in self._frames:  # equal data is stored once (snapshot.py:157-170)

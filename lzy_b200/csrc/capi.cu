@@ -26,6 +26,7 @@
 
 #include "host/host_common.h"
 #include "kernels.cuh"
+#include "push_kernels.cuh"
 #include "tma_kernels.cuh"
 
 using namespace lzyb;
@@ -39,6 +40,9 @@ constexpr int CTL_SLAB = 8192;        // slots that can be live per device
 constexpr int MBOX_SLAB = 65536;      // mailboxes (pinned, all devices)
 constexpr uint64_t DMA_MIN_BYTES = 256ull << 20;  // peer pulls at least this long ride the copy engine (auto policy)
 constexpr int GRID_AUTO = -1000;      // lzyb_set_grid: let launch_stream pick the grid shape
+constexpr uint64_t PUSH_MIN_DEFAULT = 8ull << 20;  // peer transfers at least this long go as push + landed-scan (auto policy)
+constexpr int PUSH_MAX_INFLIGHT = 6;   // concurrent inbound pushes per sink GPU; beyond that a transfer falls back to a pull
+                                       // (scan CTAs wait resident for their chunks: bounded, so outbound pushes always find SM room)
 // TMA ring shapes that can be selected at run time (lzyb_set_tma_config): {stages, stage bytes, CTAs per SM}
 struct TmaCfg {
     int stages, stage_bytes, ctas_per_sm;
@@ -116,6 +120,8 @@ struct DeviceCtx {
     bool tma_attr[8] = {false, false, false, false, false, false, false, false};
     // DMA pull (launch_dma_verify): scans trail the copy engine on their own stream; events are recycled
     cudaStream_t verify_stream = nullptr;
+    cudaStream_t push_stream = nullptr;  // this GPU as a SOURCE: push kernels of in-process transfers are issued here
+    std::atomic<int> push_inflight{0};   // this GPU as a SINK: landed-scan kernels not yet harvested
     std::mutex dma_mu;  // one copy-engine pull is issued at a time per sink GPU (event ring, verify-stream order)
     std::vector<cudaEvent_t> dma_events;
     size_t dma_ev_next = 0;
@@ -157,6 +163,9 @@ struct Slot {
     cudaStream_t last_stream = nullptr;
     int fault_kind = LZYB_FAULT_NONE;
     uint64_t fault_arg = 0;
+    bool movable = false;        // the owner declared a sole consumer: a whole-payload same-GPU pull moves the frame
+    bool push_counted = false;   // holds one unit of its sink device's push_inflight
+    bool push_dirty = false;     // a landed-scan may have left progress counters non-zero (timed out / reset mid-way)
     std::atomic<int> refs{1};    // lzyb_slot_retain / lzyb_slot_close
     // asynchronous readers of this frame inside this process (consumer stream → event recorded after its last
     // pull launch): close waits for them before the frame goes back to the pool
@@ -199,6 +208,8 @@ struct Global {
     std::atomic<int> ctl_reserve{0};  // test hook (LZYB_FAULT_SLAB_RESERVE): pretend this many SlotCtl entries are taken
     std::atomic<uint64_t> dma_last_bytes{0};  // last sub-chunk of a copy-engine pull (0 = total/32 in 4..32 MiB)
     std::atomic<int> dma_growth{6};            // each earlier sub-chunk is this many times larger
+    std::atomic<uint64_t> push_min{PUSH_MIN_DEFAULT};
+    std::atomic<uint64_t> st_push{0}, st_moves{0};
     // stats
     std::atomic<uint64_t> st_dma{0};
     std::atomic<uint64_t> st_launch{0}, st_pack{0}, st_pull{0}, st_scan{0}, st_frame{0}, st_bpack{0},
@@ -215,8 +226,10 @@ uint64_t frame_capacity(uint64_t nbytes) {
         while (c < need) c <<= 1;
         return c;
     }
-    return round_up(need, 2ull << 20);  // large: 2 MiB granules (one TLB page each)
+    // large: 2 MiB granules (one TLB page each); the last 16 KiB are the progress counters of push transfers
+    return round_up(need + PUSH_TRAILER_BYTES, 2ull << 20);
 }
+bool has_trailer(uint64_t cap) { return cap > (1ull << 20); }
 
 SlotPtr find(lzyb_handle_t h) {
     std::shared_lock<std::shared_mutex> lk(g.reg_mu);
@@ -249,6 +262,14 @@ int alloc_frame(DeviceCtx& d, uint64_t cap, uint8_t** out) {
         cudaGetLastError();
         return fail(LZYB_E_LOCAL, "cudaMalloc(%llu) failed on GPU %d: %s", (unsigned long long)cap, d.ordinal,
                     cudaGetErrorString(e));
+    }
+    if (has_trailer(cap)) {  // counters are zero at rest; pooled frames keep that invariant (landed_scan_kernel resets what it consumes)
+        e = cudaMemset(static_cast<uint8_t*>(p) + cap - PUSH_TRAILER_BYTES, 0, PUSH_TRAILER_BYTES);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(p);
+            return fail(LZYB_E_LOCAL, "cudaMemset of a frame trailer failed on GPU %d: %s", d.ordinal, cudaGetErrorString(e));
+        }
     }
     *out = static_cast<uint8_t*>(p);
     return LZYB_OK;
@@ -306,7 +327,7 @@ int launch_stream(DeviceCtx& d, const CopyParams& p, bool store, cudaStream_t st
     // TMA ring keeps the most bytes in flight with the fewest instructions (670 vs 634 GB/s per direction when
     // both directions are busy); a same-GPU copy is HBM-bound and an oversubscribed LDG/STG grid wins
     // (6.47 TB/s vs 5.97 TB/s for the persistent ring).
-    if (engine == 0 || engine == 3) engine = (peer && tma_ok) ? 2 : 1;  // 3 only changes how peer pulls are carried
+    if (engine == 0 || engine >= 3) engine = (peer && tma_ok) ? 2 : 1;  // 3 and 4 only change how peer transfers are carried
     if (engine == 2 && !tma_ok) engine = 1;
     if (engine == 2) {
         const int ci = g.tma_cfg.load();
@@ -427,6 +448,83 @@ int launch_dma_verify(DeviceCtx& d, const CopyParams& whole, cudaStream_t st) {
     return LZYB_OK;
 }
 
+// ---- push + landed-scan: the hand-written NVLink carrier (push_kernels.cuh) ---------------------------------
+unsigned int* frame_flags(uint8_t* buf, uint64_t cap) { return reinterpret_cast<unsigned int*>(buf + cap - PUSH_TRAILER_BYTES); }
+
+int launch_push(DeviceCtx& sd, const uint8_t* src, uint8_t* dst, uint64_t nbytes, unsigned int* flags, cudaStream_t ps) {
+    PushParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.src = src;
+    pp.dst = dst;
+    pp.nbytes = nbytes;
+    pp.flags = flags;
+    pp.chunk_shift = push_chunk_shift(nbytes);
+    const uint64_t ntiles = (nbytes + PUSH_TILE_BYTES - 1) / PUSH_TILE_BYTES;
+    const uint64_t nchunks = (ntiles + (1ull << pp.chunk_shift) - 1) >> pp.chunk_shift;
+    int grid = sd.sm_count * PUSH_CTAS_PER_SM;
+    if ((uint64_t)grid > nchunks) grid = (int)(nchunks ? nchunks : 1);
+    const bool v256 = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 31) == 0;
+    if (v256)
+        push_kernel<true><<<grid, 256, 0, ps>>>(pp);
+    else
+        push_kernel<false><<<grid, 256, 0, ps>>>(pp);
+    g.st_launch++;
+    g.st_push++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "push launch failed: %s", cudaGetErrorString(e));
+    return LZYB_OK;
+}
+
+// `scan` describes the sink side of the chunk (src = the sink's own payload bytes, dst = nullptr, ctl / fin / mailbox set)
+int launch_landed_scan(DeviceCtx& dd, CopyParams scan, unsigned int* flags, cudaStream_t st) {
+    scan.dst = nullptr;
+    scan.signal_flags = flags;
+    scan.chunk_shift = push_chunk_shift(scan.nbytes);
+    const uint64_t ntiles = (scan.nbytes + PUSH_TILE_BYTES - 1) / PUSH_TILE_BYTES;
+    const uint64_t nchunks = (ntiles + (1ull << scan.chunk_shift) - 1) >> scan.chunk_shift;
+    int grid = dd.sm_count / 2;  // every CTA resident with room to spare: a CTA waiting for a late chunk blocks nobody
+    if ((uint64_t)grid > nchunks) grid = (int)(nchunks ? nchunks : 1);
+    landed_scan_kernel<<<grid, 256, 0, st>>>(scan);
+    g.st_launch++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "landed-scan launch failed: %s", cudaGetErrorString(e));
+    return LZYB_OK;
+}
+
+void add_reader(Slot& s, cudaStream_t st) {
+    cudaEvent_t ev = nullptr;
+    for (auto& r : s.readers)
+        if (r.first == st) ev = r.second;
+    if (!ev) {
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        s.readers.emplace_back(st, ev);
+    }
+    cudaEventRecord(ev, st);
+}
+
+// Both halves of an in-process transfer between two GPUs.  `p` is the chunk as lzyb_transfer_chunk built it
+// (src on the source GPU, dst on the sink GPU); the caller's device is the sink's.
+int launch_push_pair(DeviceCtx& sd, DeviceCtx& dd, Slot& src, Slot& dst, const CopyParams& p, cudaStream_t st) {
+    unsigned int* flags = frame_flags(dst.buf, dst.cap);
+    {
+        // the push may start once everything queued on the sink stream so far has run (an earlier chunk's scan resets
+        // the counters it consumed) and once the producer's payload is final
+        std::lock_guard<std::mutex> issue(dd.dma_mu);
+        cudaEvent_t ev = dd.next_dma_event();
+        CU(cudaEventRecord(ev, st));
+        DeviceGuard sg(sd.ordinal);
+        CU(cudaStreamWaitEvent(sd.push_stream, ev, 0));
+        if (src.last_ev) CU(cudaStreamWaitEvent(sd.push_stream, src.last_ev, 0));
+        int rc = launch_push(sd, p.src, p.dst, p.nbytes, flags, sd.push_stream);
+        if (rc != LZYB_OK) return rc;
+        add_reader(src, sd.push_stream);  // neither frame is recycled under a push that is still running
+        add_reader(dst, sd.push_stream);
+    }
+    CopyParams scan = p;
+    scan.src = p.dst;
+    return launch_landed_scan(dd, scan, flags, st);
+}
+
 void arm_mailbox(Slot& s, CopyParams& p) {
     s.seq++;
     s.mbox->status = 0;
@@ -449,6 +547,11 @@ int harvest(Slot& s) {
     s.sum = s.mbox->sum;
     s.xr = s.mbox->xr;
     s.ctl_dirty = false;
+    if (s.push_counted) {
+        g.devs[s.dev]->push_inflight--;
+        s.push_counted = false;
+    }
+    if (s.mbox->status == 1u) s.push_dirty = false;  // a verified landed-scan consumed and reset every counter
     return static_cast<int>(s.mbox->status);
 }
 
@@ -570,6 +673,7 @@ int lzyb_init(int first_gpu, int n_gpus, uint64_t host_ring_bytes) {
         d->sm_count = prop.multiProcessorCount;
         CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&d->verify_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&d->push_stream, cudaStreamNonBlocking));
         CU(cudaMalloc(&d->ctl_slab, sizeof(SlotCtl) * CTL_SLAB));
         CU(cudaMemset(d->ctl_slab, 0, sizeof(SlotCtl) * CTL_SLAB));
         for (int k = CTL_SLAB - 1; k >= 0; --k) d->ctl_free.push_back(k);
@@ -623,6 +727,7 @@ int lzyb_shutdown(void) {
         cudaFree(d->ctl_slab);
         for (cudaEvent_t e : d->dma_events) cudaEventDestroy(e);
         cudaStreamDestroy(d->verify_stream);
+        cudaStreamDestroy(d->push_stream);
         cudaStreamDestroy(d->stream);
     }
     g.devs.clear();
@@ -915,6 +1020,15 @@ int lzyb_slot_retain(lzyb_handle_t h) {
     return LZYB_OK;
 }
 
+int lzyb_slot_set_movable(lzyb_handle_t h, int movable) {
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->is_input || s->remote) return fail(LZYB_E_STATE, "slot %s is not a local output slot", s->id.c_str());
+    s->movable = movable != 0;
+    return LZYB_OK;
+}
+
 int lzyb_slot_close(lzyb_handle_t h) {
     SlotPtr s;
     {
@@ -940,6 +1054,11 @@ int lzyb_slot_close(lzyb_handle_t h) {
         cudaEventDestroy(r.second);
     }
     s->readers.clear();
+    if (s->push_counted) {
+        d.push_inflight--;
+        s->push_counted = false;
+    }
+    if (s->push_dirty && !s->remote && s->buf && has_trailer(s->cap)) cudaMemset(frame_flags(s->buf, s->cap), 0, PUSH_TRAILER_BYTES);
     if (s->remote) {
         // the mapping stays in g.ipc_cache (closed at shutdown)
     } else if (s->buf) {
@@ -994,6 +1113,34 @@ int64_t lzyb_transfer_chunk(lzyb_handle_t dst_h, lzyb_handle_t src_h, uint64_t o
     DeviceGuard dg(d.ordinal);
     cudaStream_t st = pick_stream(d, stream);
     const bool last = offset + len == dst->nbytes;
+    // ---- move instead of copy (InputSlotBackend.toOutput's ownership hand-over, FileInputBackend.java:38-45, applied
+    // to the producer→consumer edge): the producer's owner declared a sole consumer (lzyb_slot_set_movable), nobody else
+    // holds the frame (refs == 1), both slots sit on one GPU and the consumer asks for the whole payload.  The two
+    // slots swap frames: the consumer owns the committed frame (header and digest as the producer published them — the
+    // bytes never left this GPU, there is nothing to re-verify), the producer keeps the consumer's empty one and reads
+    // as MOVED from now on.  Any second holder (frame store, proxy, another consumer's retain) keeps the copy path.
+    if (src->movable && src->refs.load() == 1 && !src->remote && !dst->remote && src->dev == dst->dev && offset == 0 &&
+        len == dst->nbytes && dst->delivered == 0 && src->cap == dst->cap && src->fault_kind == LZYB_FAULT_NONE) {
+        if (src->last_ev && src->last_stream != st) cudaStreamWaitEvent(st, src->last_ev, 0);
+        for (auto& r : src->readers) cudaStreamWaitEvent(st, r.second, 0);  // earlier readers of the frame finish first
+        std::swap(src->buf, dst->buf);
+        dst->dtype = src->dtype;
+        dst->ndim = src->ndim;
+        memcpy(dst->shape, src->shape, sizeof(dst->shape));
+        dst->digest[0] = src->digest[0];
+        dst->digest[1] = src->digest[1];
+        dst->sum = src->sum;
+        dst->xr = src->xr;
+        dst->delivered = dst->nbytes;
+        dst->state = LZYB_ST_READY;
+        dst->digest_pending = false;
+        src->state = LZYB_ST_MOVED;
+        src->movable = false;
+        note(*dst, st);
+        g.st_moves++;
+        g.st_bpull_l += len;
+        return (int64_t)len;
+    }
     CopyParams p;
     memset(&p, 0, sizeof(p));
     p.src = src->payload() + offset;
@@ -1018,8 +1165,27 @@ int64_t lzyb_transfer_chunk(lzyb_handle_t dst_h, lzyb_handle_t src_h, uint64_t o
     if (src->last_ev && src->last_stream != st) cudaStreamWaitEvent(st, src->last_ev, 0);
     const bool peer = src->remote || src->dev != dst->dev;
     const int engine = g.engine.load();
-    const bool dma = peer && (engine == 3 || (engine == 0 && len >= DMA_MIN_BYTES));
-    int rc = dma ? launch_dma_verify(d, p, st) : launch_stream(d, p, true, st, peer);
+    // auto: an in-process transfer between two GPUs is PUSHED by a kernel on the source GPU while a scan on the sink GPU
+    // digests what has landed (push_kernels.cuh); a source mapped from another process can only be pulled from here
+    // (its owner pushes through lzyb_slot_push): the TMA ring below 256 MiB, the copy engine + trailing scans above
+    bool push = peer && !src->remote && !dst->remote && has_trailer(dst->cap) &&
+                (engine == 4 || (engine == 0 && len >= g.push_min.load()));
+    if (push && !dst->push_counted) {
+        if (d.push_inflight.fetch_add(1) >= PUSH_MAX_INFLIGHT && engine != 4) {
+            d.push_inflight--;
+            push = false;
+        } else {
+            dst->push_counted = true;
+        }
+    }
+    const bool dma = !push && peer && (engine == 3 || (engine == 0 && len >= DMA_MIN_BYTES));
+    int rc;
+    if (push) {
+        dst->push_dirty = true;
+        rc = launch_push_pair(*g.devs[src->dev], d, *src, *dst, p, st);
+    } else {
+        rc = dma ? launch_dma_verify(d, p, st) : launch_stream(d, p, true, st, peer);
+    }
     if (rc != LZYB_OK) return rc;
     g.st_pull++;
     if (src->dev == dst->dev && !src->remote)
@@ -1055,6 +1221,17 @@ static int input_reset_locked(Slot& s) {
     if (s.ctl_dirty) {
         CU(cudaMemset(s.ctl, 0, sizeof(SlotCtl)));
         s.ctl_dirty = false;
+    }
+    if (s.push_counted) {
+        d.push_inflight--;
+        s.push_counted = false;
+    }
+    if (s.push_dirty && !s.remote && has_trailer(s.cap)) {
+        // a push that was cut short may still be running and may have left counters behind: let it finish, then
+        // restore the zero-at-rest invariant of the trailer
+        for (auto& r : s.readers) cudaEventSynchronize(r.second);
+        CU(cudaMemset(frame_flags(s.buf, s.cap), 0, PUSH_TRAILER_BYTES));
+        s.push_dirty = false;
     }
     s.delivered = 0;
     s.digest_pending = false;
@@ -1309,6 +1486,130 @@ int lzyb_peer_import(const lzyb_ipc_desc_t* desc, int onto_gpu, lzyb_handle_t* o
     g.st_live++;
     *out = s->handle;
     return LZYB_OK;
+}
+
+// ---- producer-issued push between processes ---------------------------------------------------------------------
+
+int lzyb_sink_export(lzyb_handle_t h, lzyb_ipc_desc_t* out) {
+    auto s = find(h);
+    if (!s || !out) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (!s->is_input || s->remote) return fail(LZYB_E_STATE, "slot %s is not a local input slot", s->id.c_str());
+    if (s->state == LZYB_ST_READY || s->state == LZYB_ST_CLOSED || s->state == LZYB_ST_FAILED)
+        return fail(LZYB_E_STATE, "slot %s cannot receive (state %d)", s->id.c_str(), s->state);
+    if (!has_trailer(s->cap)) return fail(LZYB_E_ARG, "slot %s is too small to be pushed into (no counter trailer)", s->id.c_str());
+    DeviceCtx& d = *g.devs[s->dev];
+    DeviceGuard dg(d.ordinal);
+    memset(out, 0, sizeof(*out));
+    cudaIpcMemHandle_t mh;
+    CU(cudaIpcGetMemHandle(&mh, s->buf));
+    memcpy(out->ipc_handle, &mh, 64);
+    out->buffer_bytes = s->cap;
+    out->nbytes = s->nbytes;
+    out->gpu = d.ordinal;
+    out->pid = (int32_t)getpid();
+    return LZYB_OK;
+}
+
+static int map_peer_frame(DeviceCtx& d, const lzyb_ipc_desc_t* desc, void** base) {
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, desc->ipc_handle, 64);
+    std::lock_guard<std::mutex> lk(g.ipc_mu);
+    auto key = std::make_pair(d.ordinal, std::string(reinterpret_cast<const char*>(desc->ipc_handle), 64));
+    auto it = g.ipc_cache.find(key);
+    if (it != g.ipc_cache.end()) {
+        *base = it->second;
+        return LZYB_OK;
+    }
+    cudaError_t e = cudaIpcOpenMemHandle(base, mh, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(LZYB_E_PEER, "cannot map peer frame (pid %d gpu %d): %s", desc->pid, desc->gpu, cudaGetErrorString(e));
+    }
+    g.ipc_cache.emplace(key, *base);
+    return LZYB_OK;
+}
+
+int lzyb_slot_push(lzyb_handle_t src_h, const lzyb_ipc_desc_t* sink, uint64_t offset, uint64_t len, void* stream) {
+    auto src = find(src_h);
+    if (!src || !sink) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(src->mu);
+    if (src->state != LZYB_ST_READY || src->remote) return fail(LZYB_E_STATE, "slot %s is not a committed local slot", src->id.c_str());
+    if (sink->pid == (int32_t)getpid()) return fail(LZYB_E_ARG, "sink belongs to this process; use lzyb_transfer_chunk");
+    if (sink->nbytes != src->nbytes) return fail(LZYB_E_PEER, "sink expects %llu bytes, slot %s holds %llu", (unsigned long long)sink->nbytes,
+                                                  src->id.c_str(), (unsigned long long)src->nbytes);
+    if (!has_trailer(sink->buffer_bytes) || sink->buffer_bytes < HEADER_BYTES + PUSH_TRAILER_BYTES ||
+        sink->nbytes > sink->buffer_bytes - HEADER_BYTES - PUSH_TRAILER_BYTES)
+        return fail(LZYB_E_PEER, "sink descriptor: %llu payload bytes do not fit its %llu-byte frame", (unsigned long long)sink->nbytes,
+                    (unsigned long long)sink->buffer_bytes);
+    if ((offset & 15) || offset > src->nbytes) return fail(LZYB_E_ARG, "bad offset %llu", (unsigned long long)offset);
+    if (len == 0 || offset + len > src->nbytes) len = src->nbytes - offset;
+    if (len == 0) return LZYB_OK;
+    DeviceCtx& d = *g.devs[src->dev];
+    DeviceGuard dg(d.ordinal);
+    void* base = nullptr;
+    int rc = map_peer_frame(d, sink, &base);
+    if (rc != LZYB_OK) return rc;
+    cudaStream_t st = pick_stream(d, stream);
+    if (src->last_ev && src->last_stream != st) CU(cudaStreamWaitEvent(st, src->last_ev, 0));
+    uint8_t* sb = static_cast<uint8_t*>(base);
+    rc = launch_push(d, src->payload() + offset, sb + HEADER_BYTES + offset, len, frame_flags(sb, sink->buffer_bytes), st);
+    if (rc != LZYB_OK) return rc;
+    add_reader(*src, st);
+    g.st_bpull_p += len;
+    if (!stream) CU(cudaStreamSynchronize(st));
+    return LZYB_OK;
+}
+
+int64_t lzyb_input_expect_push(lzyb_handle_t dst_h, const lzyb_ipc_desc_t* producer, uint64_t offset, uint64_t len, void* stream) {
+    auto dst = find(dst_h);
+    if (!dst || !producer) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(dst->mu);
+    if (!dst->is_input || dst->remote) return fail(LZYB_E_STATE, "slot %s is not a local input slot", dst->id.c_str());
+    if (dst->state == LZYB_ST_CLOSED || dst->state == LZYB_ST_FAILED) return fail(LZYB_E_LOCAL, "sink %s already closed", dst->id.c_str());
+    if (dst->state == LZYB_ST_READY || dst->digest_pending) return LZYB_EOF;
+    if (!has_trailer(dst->cap)) return fail(LZYB_E_ARG, "slot %s is too small to be pushed into", dst->id.c_str());
+    if (producer->nbytes != dst->nbytes) return fail(LZYB_E_PEER, "peer holds %llu bytes, sink expects %llu", (unsigned long long)producer->nbytes,
+                                                      (unsigned long long)dst->nbytes);
+    if (producer->ndim > LZYB_MAX_DIMS) return fail(LZYB_E_PEER, "peer descriptor: ndim %u > %d", producer->ndim, LZYB_MAX_DIMS);
+    if (offset != dst->delivered || (offset & 15)) return fail(LZYB_E_ARG, "offset %llu != delivered %llu", (unsigned long long)offset,
+                                                               (unsigned long long)dst->delivered);
+    if (len == 0 || offset + len > dst->nbytes) len = dst->nbytes - offset;
+    if (len == 0) return LZYB_EOF;
+    const bool last = offset + len == dst->nbytes;
+    if (!last && (len & 15)) return fail(LZYB_E_ARG, "intermediate chunks must be multiples of 16 bytes");
+    DeviceCtx& d = *g.devs[dst->dev];
+    DeviceGuard dg(d.ordinal);
+    cudaStream_t st = pick_stream(d, stream);
+    CopyParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = dst->payload() + offset;
+    p.nbytes = len;
+    p.word_base = offset >> 3;
+    p.ctl = dst->ctl;
+    p.total_nbytes = dst->nbytes;
+    p.fin = FIN_NONE;
+    if (last) {
+        p.fin = FIN_VERIFY;
+        p.expect[0] = producer->digest[0];
+        p.expect[1] = producer->digest[1];
+        p.dst_hdr = reinterpret_cast<lzyb_frame_header_t*>(dst->buf);
+        dst->dtype = producer->dtype;
+        dst->ndim = producer->ndim;
+        memcpy(dst->shape, producer->shape, sizeof(dst->shape));
+        fill_template(*dst, &p.hdr_template);
+        arm_mailbox(*dst, p);
+    }
+    dst->push_dirty = true;
+    int rc = launch_landed_scan(d, p, frame_flags(dst->buf, dst->cap), st);
+    if (rc != LZYB_OK) return rc;
+    g.st_pull++;
+    dst->delivered += len;
+    dst->state = LZYB_ST_FILLING;
+    dst->ctl_dirty = !last;
+    if (last) dst->digest_pending = true;
+    note(*dst, st);
+    return (int64_t)len;
 }
 
 // ---- fan-out: chunk-pipelined pull chain -------------------------------------------------------
@@ -1755,20 +2056,29 @@ int lzyb_stats(lzyb_stats_t* out) {
     for (auto& d : g.devs) pooled += d->pooled_bytes;
     out->hbm_bytes_pooled = pooled;
     out->dma_copies = g.st_dma;
+    out->push_launches = g.st_push;
+    out->frames_moved = g.st_moves;
     return LZYB_OK;
 }
 
 int lzyb_stats_reset(void) {
     g.st_launch = g.st_pack = g.st_pull = g.st_scan = g.st_frame = 0;
     g.st_dma = 0;
+    g.st_push = g.st_moves = 0;
     g.st_bpack = g.st_bpull_l = g.st_bpull_p = g.st_bframe = g.st_h2d = g.st_d2h = 0;
     return LZYB_OK;
 }
 
 int lzyb_set_copy_engine(int engine) {
-    if (engine < 0 || engine > 3)
-        return fail(LZYB_E_ARG, "engine must be 0 (auto), 1 (LDG/STG), 2 (TMA bulk) or 3 (copy engine + trailing scan, peer pulls)");
+    if (engine < 0 || engine > 4)
+        return fail(LZYB_E_ARG, "engine must be 0 (auto), 1 (LDG/STG), 2 (TMA bulk), 3 (copy engine + trailing scan, peer pulls) or "
+                                "4 (push kernel + landed scan, in-process peer transfers)");
     g.engine = engine;
+    return LZYB_OK;
+}
+
+int lzyb_set_push_min_bytes(uint64_t nbytes) {
+    g.push_min = nbytes ? nbytes : PUSH_MIN_DEFAULT;
     return LZYB_OK;
 }
 

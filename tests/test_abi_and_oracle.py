@@ -102,6 +102,46 @@ def test_digest_detects_small_integer_permutations():
     assert oracle.digest(x) != oracle.digest(y)
 
 
+def py_content_key(digest, dtype_flags, shape):
+    """independent pure-Python statement of lzyb_content_key_fold (include/lzyb_digest.h)"""
+    M = (1 << 64) - 1
+    K_POS, K1, K2, K_LEN, K_META = (0x9E3779B97F4A7C15, 0xFF51AFD7ED558CCD, 0xC4CEB9FE1A85EC53, 0xD6E8FEB86659FD93,
+                                    0xA0761D6478BD642F)
+
+    def mix(x):
+        x = (x * K1) & M
+        x ^= x >> 32
+        x = (x * K2) & M
+        x ^= x >> 29
+        return x
+
+    h = mix((((dtype_flags & 0xFFFFFFFF) << 32) | len(shape)) ^ K_META)
+    for i, d in enumerate(shape):
+        h = mix(h ^ mix((d + (i + 1) * K_POS) & M))
+    hi = mix(digest[0] ^ h)
+    lo = mix((digest[1] + (((h << 32) | (h >> 32)) & M) + K_LEN) & M)
+    return hi, lo ^ (hi >> 1)
+
+
+def test_content_key_tells_apart_values_that_share_their_bytes():
+    """the payload digest is blind to dtype / shape / serializer flags, so zeros(4, f32) and
+    zeros(4, i32) or one buffer seen as (2, 8) and (4, 4) had one URI.  The reference's md5 runs over the serialized
+    stream, which carries both (snapshot.py:147-155).  The content key folds the header metadata in."""
+    from lzy_b200 import _native as N
+    d = oracle.digest(np.zeros(16, dtype=np.uint8))
+    cases = [(N.DT_F32, (4,)), (N.DT_I32, (4,)), (N.DT_F32, (2, 2)), (N.DT_F32, (1, 4)), (N.DT_F32, (4, 1)),
+             (N.DT_F32 | (1 << 16), (4,)), (N.DT_PICKLE, (16,)), (N.DT_U8, (16,)), (N.DT_U8, (2, 8)), (N.DT_U8, (8, 2)),
+             (N.DT_U8, (4, 4)), (N.DT_U8, ())]
+    keys = [N.content_key(d, dt, sh) for dt, sh in cases]
+    assert len(set(keys)) == len(keys)
+    for (dt, sh), k in zip(cases, keys):
+        assert k == py_content_key(d, dt, sh)
+        assert k == N.content_key(d, dt, sh)  # a function of its inputs only
+    # and it still depends on every bit of the payload digest
+    assert N.content_key((d[0] ^ 1, d[1]), N.DT_F32, (4,)) != keys[0]
+    assert N.content_key((d[0], d[1] ^ (1 << 63)), N.DT_F32, (4,)) != keys[0]
+
+
 def test_partial_digests_compose():
     a = np.random.default_rng(3).integers(0, 256, 5 * (1 << 20) + 11, dtype=np.uint8)
     acc = (0, 0)

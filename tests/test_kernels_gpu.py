@@ -14,6 +14,8 @@ pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 
+from lzy_b200.devmem import view_bytes  # noqa: E402
+
 SIZES = [0, 1, 7, 8, 15, 16, 17, 255, 4096, 4097, 65535, (2 << 20) - 1, 2 << 20, (2 << 20) + 1, (8 << 20) + 13]
 
 
@@ -330,3 +332,103 @@ def test_stats_count_our_kernels(native):
     t = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda:0")
     native.digest_device(0, t.data_ptr(), 1 << 20)
     assert native.stats()["kernel_launches"] == before + 1
+
+
+def test_sole_consumer_on_the_same_gpu_gets_the_frame_not_a_copy(native):
+    """`FileInputBackend.toOutput()` hands a file over by ownership (FileInputBackend.java:38-45); the
+    same-GPU producer → consumer edge does the same once the producer's owner has declared a sole consumer and nobody
+    else holds the frame.  No kernel runs; the consumer owns the committed frame, the producer reads MOVED."""
+    N = native
+    n = (6 << 20) + 5
+    a = np.random.default_rng(11).integers(0, 256, n, dtype=np.uint8)
+    t = torch.from_numpy(a).cuda()
+    out = N.SlotHandle.create_output("mv/out", 0, n)
+    out.set_meta(N.DT_U8, (n,))
+    out.pack(t.data_ptr(), n)
+    dg = out.commit()
+    src_ptr = out.device_ptr()
+    inp = N.SlotHandle.open_input("mv/in", 0, n)
+    try:
+        out.set_movable(True)
+        before = N.stats()
+        assert inp.transfer_chunk(out, 0, 1 << 40) == n
+        inp.finish(out)
+        after = N.stats()
+        assert after["kernel_launches"] == before["kernel_launches"]  # nothing was copied, nothing re-scanned
+        assert after["frames_moved"] - before["frames_moved"] == 1
+        assert inp.device_ptr() == src_ptr and out.device_ptr() != src_ptr
+        assert inp.info().state == N.ST_READY and tuple(inp.info().digest) == dg == oracle.digest(a)
+        assert inp.info().dtype == N.DT_U8 and inp.info().ndim == 1 and inp.info().shape[0] == n
+        assert out.info().state == N.ST_MOVED
+        assert np.array_equal(view_bytes(inp.device_ptr(), n, 0).cpu().numpy(), a)
+        hdr = inp.header()
+        assert bytes(hdr.magic)[:7] == b"LZYB200" and int(hdr.nbytes) == n and tuple(hdr.digest) == dg
+        assert inp.transfer_chunk(out, n, 1 << 20) == N.EOF
+        late = N.SlotHandle.open_input("mv/late", 0, n)
+        with pytest.raises(N.ReadException):  # a second consumer that was promised not to exist
+            late.transfer_chunk(out, 0, 1 << 40)
+        late.close()
+        # the consumer can re-publish what it now owns (InputSlot "-out" re-publication) and serve it by copy
+        inp.to_output()
+        again = N.SlotHandle.open_input("mv/again", 0, n)
+        assert again.transfer_chunk(inp, 0, 1 << 40) == n
+        again.finish(inp)
+        assert np.array_equal(view_bytes(again.device_ptr(), n, 0).cpu().numpy(), a)
+        again.close()
+    finally:
+        out.close()
+        inp.close()
+
+
+@pytest.mark.parametrize("why", ["not declared", "second holder", "partial request"])
+def test_the_copy_stays_whenever_someone_else_may_read_the_frame(native, why):
+    """snapshot-at-call-time (pylzy tests/api/v1/test_entries.py:331-384): a frame that a proxy, the frame store or a
+    second consumer can still ask for is never handed over"""
+    N = native
+    n = (3 << 20) + 32
+    a = np.random.default_rng(12).integers(0, 256, n, dtype=np.uint8)
+    t = torch.from_numpy(a).cuda()
+    out = N.SlotHandle.create_output(f"mvc/{why}/out", 0, n)
+    out.pack(t.data_ptr(), n)
+    out.commit()
+    inp = N.SlotHandle.open_input(f"mvc/{why}/in", 0, n)
+    try:
+        if why != "not declared":
+            out.set_movable(True)
+        if why == "second holder":
+            out.retain()
+        src_ptr = out.device_ptr()
+        before = N.stats()["frames_moved"]
+        step = (1 << 20) if why == "partial request" else (1 << 40)
+        off = 0
+        while True:
+            moved = inp.transfer_chunk(out, off, step)
+            if moved == N.EOF:
+                break
+            off += moved
+        inp.finish(out)
+        assert N.stats()["frames_moved"] == before
+        assert out.info().state == N.ST_READY and out.device_ptr() == src_ptr and inp.device_ptr() != src_ptr
+        assert np.array_equal(view_bytes(inp.device_ptr(), n, 0).cpu().numpy(), a)
+        assert np.array_equal(view_bytes(out.device_ptr(), n, 0).cpu().numpy(), a)
+    finally:
+        if why == "second holder":
+            out.close()
+        out.close()
+        inp.close()
+
+
+def test_slot_slab_exhaustion_is_an_error_not_a_hang(native):
+    """with every per-device slot control entry taken, slot creation used to free the frame while
+    holding the device mutex that free_frame takes — a self-deadlock.  Provoked through the reserve hook."""
+    N = native
+    N.lib.lzyb_fault_inject(0, N.FAULT_SLAB_RESERVE, 1 << 20)
+    try:
+        live = N.stats()["slots_live"]
+        with pytest.raises(N.LzybError, match="too many live slots"):
+            N.SlotHandle.create_output("slab/out", 0, 4 << 20)
+        assert N.stats()["slots_live"] == live
+    finally:
+        N.lib.lzyb_fault_inject(0, N.FAULT_SLAB_RESERVE, 0)
+    s = N.SlotHandle.create_output("slab/ok", 0, 4 << 20)  # and the frame it had taken went back to the pool
+    s.close()

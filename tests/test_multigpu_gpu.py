@@ -33,9 +33,10 @@ def to_host(slot):
     return out
 
 
-@pytest.mark.parametrize("engine", ["ldg", "tma", "dma", "auto"])
+@pytest.mark.parametrize("engine", ["ldg", "tma", "dma", "push", "auto"])
 def test_cross_gpu_pull_is_bit_exact(native_all, engine):
-    N.set_copy_engine({"ldg": N.ENGINE_LDG, "tma": N.ENGINE_TMA, "dma": N.ENGINE_DMA, "auto": N.ENGINE_AUTO}[engine])
+    N.set_copy_engine({"ldg": N.ENGINE_LDG, "tma": N.ENGINE_TMA, "dma": N.ENGINE_DMA, "push": N.ENGINE_PUSH,
+                       "auto": N.ENGINE_AUTO}[engine])
     N.set_dma_schedule(3 << 20, 1)  # several sub-chunks (and a ragged last one) per 8 MiB chunk
     try:
         n = (48 << 20) + 4096 + 7
@@ -95,6 +96,115 @@ def test_copy_engine_pull_trailing_scan_catches_corruption(native_all):
         N.set_copy_engine(N.ENGINE_AUTO)
         N.set_dma_schedule()
         for s in (bad, good, inp):
+            s.close()
+
+
+@pytest.mark.parametrize("n,step", [((64 << 20) + 4096 + 7, 0), ((8 << 20) + 16, 0), (32768 * 3 + 5, 0), ((40 << 20) + 48, (8 << 20) + 16),
+                                    ((1 << 20) + 1, 0), (1 << 30, 0)],
+                         ids=["64MiB-ragged", "8MiB+16", "3tiles+5", "chunked-16B-offsets", "1MiB+1", "1GiB"])
+def test_push_and_landed_scan_deliver_bit_exact(native_all, n, step):
+    """The default carrier between two GPUs of one process: push_kernel on the source GPU, landed_scan_kernel on the
+    sink GPU digesting each chunk as its counter says it has landed.  Byte equality against the source, the digest
+    against the oracle, no copy engine, and the frame's counters back at zero (a second delivery into the recycled
+    frame works)."""
+    N.set_copy_engine(N.ENGINE_PUSH)
+    try:
+        if n >= (256 << 20):
+            t = torch.empty(n, dtype=torch.uint8, device="cuda:0")
+            N.fill_pattern(0, t.data_ptr(), n, 21)
+            torch.cuda.synchronize(0)
+            a = None
+        else:
+            a = np.random.default_rng(n & 0xFFFF).integers(0, 256, n, dtype=np.uint8)
+            t = torch.from_numpy(a).to("cuda:0")
+        out = N.SlotHandle.create_output("push/out", 0, n)
+        out.pack(t.data_ptr(), n)
+        dg = out.commit()
+        if a is not None:
+            assert dg == oracle.digest(a)
+        for life in range(2):  # the second life reuses the pooled frame: its counters must be zero again
+            inp = N.SlotHandle.open_input(f"push/in{life}", 1, n)
+            before = N.stats()
+            off = 0
+            while True:
+                moved = inp.transfer_chunk(out, off, step or (1 << 40))
+                if moved == N.EOF:
+                    break
+                off += moved
+            inp.finish(out)
+            after = N.stats()
+            assert after["dma_copies"] == before["dma_copies"]
+            pushes = 0 if n < (1 << 20) else (1 if not step else -(-n // step))  # small frames carry no counter trailer: fused pull
+            assert after["push_launches"] - before["push_launches"] == pushes
+            assert after["bytes_pulled_peer"] - before["bytes_pulled_peer"] == n
+            assert inp.info().gpu == 1 and inp.info().state == N.ST_READY and tuple(inp.info().digest) == dg
+            got = torch.empty(n, dtype=torch.uint8, device="cuda:1")
+            from lzy_b200.devmem import view_bytes
+            got.copy_(view_bytes(inp.device_ptr(), n, 1))
+            assert torch.equal(got.to("cuda:0"), t)
+            inp.close()
+        out.close()
+    finally:
+        N.set_copy_engine(N.ENGINE_AUTO)
+
+
+def test_push_catches_a_corrupted_source_and_the_sink_refetches(native_all):
+    """the landed-scan owns the verdict: one wrong byte served by a peer is a ReadException at EOS, the sink is reset
+    (counters included) and fetches from another producer — SlotsTest.testRestoreReadFromOffset's failover, with the
+    new carrier"""
+    n = (24 << 20) + 11
+    a = np.random.default_rng(8).integers(0, 256, n, dtype=np.uint8)
+    t = torch.from_numpy(a).to("cuda:0")
+    bad = N.SlotHandle.create_output("pushc/bad", 0, n)
+    good = N.SlotHandle.create_output("pushc/good", 0, n)
+    inp = N.SlotHandle.open_input("pushc/in", 1, n)
+    try:
+        for s in (bad, good):
+            s.pack(t.data_ptr(), n)
+            s.commit()
+        bad.fault(N.FAULT_CORRUPT_ONCE, (9 << 20) + 3)
+        before = N.stats()["push_launches"]
+        assert inp.transfer_chunk(bad, 0, 1 << 40) == n      # auto: ≥ 8 MiB between GPUs of one process = push
+        assert N.stats()["push_launches"] - before == 1
+        with pytest.raises(N.ReadException):
+            inp.finish(bad)
+        assert inp.info().delivered == 0
+        assert inp.transfer_chunk(good, 0, 1 << 40) == n
+        inp.finish(good)
+        assert tuple(inp.info().digest) == oracle.digest(a)
+        assert np.array_equal(to_host(inp), a)
+    finally:
+        for s in (bad, good, inp):
+            s.close()
+
+
+def test_both_directions_at_once_are_bit_exact(native_all):
+    """the ring's situation: GPU 0 → GPU 1 and GPU 1 → GPU 0 in flight together on their own streams, each GPU running
+    a push kernel (as source) and a landed-scan (as sink) at the same time"""
+    n = (192 << 20) + 64
+    ts, outs, inps, streams = [], [], [], []
+    for g in (0, 1):
+        t = torch.empty(n, dtype=torch.uint8, device=f"cuda:{g}")
+        N.fill_pattern(g, t.data_ptr(), n, 31 + g)
+        torch.cuda.synchronize(g)
+        ts.append(t)
+        o = N.SlotHandle.create_output(f"bidir/out{g}", g, n)
+        o.pack(t.data_ptr(), n)
+        o.commit()
+        outs.append(o)
+        streams.append(torch.cuda.Stream(device=g))
+    try:
+        for g in (0, 1):
+            inps.append(N.SlotHandle.open_input(f"bidir/in{g}", g, n))
+        for g in (0, 1):  # queue both before waiting for either
+            assert inps[g].transfer_chunk(outs[1 - g], 0, n, int(streams[g].cuda_stream)) == n
+        for g in (0, 1):
+            inps[g].finish(outs[1 - g], int(streams[g].cuda_stream))
+            assert tuple(inps[g].info().digest) == tuple(outs[1 - g].info().digest) == oracle.digest(oracle.pattern(n, 31 + 1 - g))
+            from lzy_b200.devmem import view_bytes
+            assert torch.equal(view_bytes(inps[g].device_ptr(), n, g).to(f"cuda:{1 - g}"), ts[1 - g])
+    finally:
+        for s in outs + inps:
             s.close()
 
 

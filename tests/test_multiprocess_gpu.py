@@ -118,3 +118,53 @@ def test_consumer_process_pulls_over_cuda_ipc_from_producer_process():
                 p.wait(timeout=20)
             except subprocess.TimeoutExpired:
                 p.kill()
+
+
+@pytest.mark.parametrize("nbytes", [(96 << 20) + 4096 + 7, (2 << 20) + 1])
+def test_producer_process_pushes_into_the_consumer_process_frame(nbytes):
+    """The hand-written carrier between worker PROCESSES: the consumer exports its empty input frame (CUDA IPC), the
+    producer's process runs push_kernel into it over NVLink, the consumer's GPU runs landed_scan_kernel, which digests
+    every chunk as the progress counters in the frame's trailer say it has landed.  No copy engine, no cross-process
+    event; the delivered bytes equal the counter-based pattern of the oracle, twice (the second delivery reuses the
+    pooled frame, so the counters were left at zero)."""
+    import numpy as np
+
+    import oracle
+    from lzy_b200 import _native as N
+    from lzy_b200.devmem import view_bytes
+
+    seed = 77
+    child = subprocess.Popen([sys.executable, str(ROOT / "tests" / "support" / "ipc_push_child.py"), "0", str(nbytes), str(seed)],
+                             stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, cwd=str(ROOT))
+    try:
+        producer = N.IpcDesc.from_buffer_copy(bytes.fromhex(child.stdout.readline().strip()))
+        assert int(producer.nbytes) == nbytes and int(producer.gpu) == 0
+        N.init(0, 0, 64 << 20)  # idempotent: the session may have initialised the library already (all visible GPUs)
+        expect = oracle.pattern(nbytes, seed)
+        assert tuple(producer.digest) == oracle.digest(expect)
+        for life in range(2):
+            inp = N.SlotHandle.open_input(f"ipcpush/in{life}", 1, nbytes)
+            sink = inp.sink_export()
+            stream = torch.cuda.Stream(device=1)
+            sp = int(stream.cuda_stream)
+            assert inp.expect_push(producer, 0, 0, sp) == nbytes   # the scan is waiting on the GPU before a byte has moved
+            child.stdin.write(bytes(sink).hex() + "\n")
+            child.stdin.flush()
+            word, pushes, dma = child.stdout.readline().split()
+            assert word == "pushed" and int(pushes) == life + 1 and int(dma) == 0
+            inp.finish_expect(producer.digest, sp)
+            info = inp.info()
+            assert info.state == N.ST_READY and tuple(info.digest) == tuple(producer.digest)
+            assert info.dtype == N.DT_U8 and info.ndim == 1 and info.shape[0] == nbytes
+            got = view_bytes(inp.device_ptr(), nbytes, 1).cpu().numpy()
+            assert np.array_equal(got, expect)
+            assert N.stats()["dma_copies"] == 0
+            inp.close()
+        # a push that never comes is a peer fault after the scan's timeout, not a hang: covered by the fault tests of
+        # the in-process pair (tests/test_multigpu_gpu.py); here only the clean shutdown
+        child.stdin.write("quit\n")
+        child.stdin.flush()
+        assert child.wait(timeout=60) == 0
+    finally:
+        if child.poll() is None:
+            child.kill()
