@@ -110,7 +110,7 @@ typedef struct lzyb_ipc_desc {
     uint32_t dtype;
     uint32_t ndim;
     uint64_t shape[LZYB_MAX_DIMS];
-    uint8_t reserved[64];
+    uint8_t reserved[64];      /* [0..8): arrival word of a push sink (lzyb_sink_export), else zero        */
 } lzyb_ipc_desc_t;             /* sizeof == 256 */
 
 typedef struct lzyb_stats_s {
@@ -129,7 +129,7 @@ typedef struct lzyb_stats_s {
     uint64_t hbm_bytes_live;
     uint64_t hbm_bytes_pooled;
     uint64_t dma_copies;       /* copy-engine sub-chunk copies issued by peer pulls (engine 3 / auto)  */
-    uint64_t push_launches;    /* push_kernel launches (source side of a GPU→GPU transfer)             */
+    uint64_t push_launches;    /* streaming-kernel launches on the SOURCE GPU of a GPU→GPU transfer (pushes)  */
     uint64_t frames_moved;     /* same-GPU deliveries done by ownership hand-over instead of a copy    */
 } lzyb_stats_t;
 
@@ -243,17 +243,21 @@ int lzyb_input_reset(lzyb_handle_t h);
 /* ---- cross-process peers -------------------------------------------------------------------- */
 int lzyb_slot_export(lzyb_handle_t h, lzyb_ipc_desc_t* out);
 int lzyb_peer_import(const lzyb_ipc_desc_t* desc, int onto_gpu, lzyb_handle_t* out);
-/* Producer-issued PUSH between worker processes (the in-process case is inside lzyb_transfer_chunk).  SM-issued
- * NVLink traffic costs a pull 1.31 wire bytes per payload byte once both directions of a GPU are busy (requests share
- * the wire with the payload it serves) and a push 1.19 (profiles/r02_peer_variants_ncu.csv), so between processes the
- * consumer exports its empty input frame, the PRODUCER's process runs push_kernel into it, and the consumer's GPU runs
- * landed_scan_kernel, which digests every chunk as its progress counter (in the frame's trailer, written by the
- * pusher with red.release.sys) says it has landed.  No copy engine, no cross-process event: the consumer learns
- * completion and verdict from its own scan.
+/* Producer-issued PUSH between worker processes (inside one process lzyb_transfer_chunk does it by itself).
+ * SM-issued NVLink traffic crosses the link in 128-byte packets: a pull costs 1.31 wire bytes per payload byte once
+ * both directions of a GPU are busy (its requests share the wire with the payload the same GPU serves), a push 1.19
+ * (profiles/r02_peer_variants_ncu.csv).  So between processes the consumer exports its EMPTY input frame and the
+ * PRODUCER's process launches the streaming kernel (TMA ring: cp.async.bulk global → shared → peer global, digest folded
+ * from the shared-memory stages) with that frame as its destination.  The verdict is the digest of what was pushed
+ * against the digest the producer committed; the pushing kernel writes the sink's frame header, the verdict and —
+ * last, with release semantics at system scope — the arrival word the consumer chose into the frame's trailer.
+ * The consumer's GPU runs a one-thread arrival_wait_kernel on that word and fills the slot's mailbox: no copy
+ * engine, no cross-process event, the consumer's stream continues with a complete frame.
  *   consumer:  lzyb_input_open → lzyb_sink_export(desc) → [desc travels to the producer] →
- *              lzyb_input_expect_push(dst, producer's slot descriptor, offset, len, stream) → lzyb_input_finish_expect
- *   producer:  lzyb_slot_push(src, sink desc, offset, len, stream)
- * offset/len as in lzyb_transfer_chunk (offset % 16 == 0; len == 0 means "to the end"). */
+ *              lzyb_input_expect_push(dst, producer's slot descriptor, 0, 0, stream) → lzyb_input_finish_expect
+ *   producer:  lzyb_slot_push(src, sink desc, 0, 0, stream)
+ * A push carries the whole payload (offset 0, len 0 or nbytes); offset-resumed partial deliveries take the pull path
+ * (lzyb_peer_import + lzyb_transfer_chunk).  A push that never comes is LZYB_E_PEER after ≈ 4 s, not a hang. */
 int lzyb_sink_export(lzyb_handle_t input, lzyb_ipc_desc_t* out);
 int lzyb_slot_push(lzyb_handle_t src, const lzyb_ipc_desc_t* sink, uint64_t offset, uint64_t len, void* stream);
 int64_t lzyb_input_expect_push(lzyb_handle_t dst, const lzyb_ipc_desc_t* producer, uint64_t offset, uint64_t len, void* stream);
@@ -293,11 +297,13 @@ int lzyb_stats_reset(void);
 /* how large contiguous transfers are carried: 0 = auto, 1 = LDG/STG 16-B vectors, 2 = TMA bulk
  * (cp.async.bulk + mbarrier ring), 3 = peer pulls ride the copy engine in sub-chunks while a scan kernel on
  * the sink GPU digests each landed sub-chunk in the shadow of the next copy (same-GPU work as in auto),
- * 4 = GPU→GPU transfers inside this process are pushed by push_kernel on the source GPU with landed_scan_kernel
- * trailing on the sink GPU (same-GPU work as in auto).
- * auto = 4 for in-process GPU→GPU transfers of at least lzyb_set_push_min_bytes (default 8 MiB); a source mapped
- * from another process is pulled: TMA ring below 256 MiB, 3 from there (its owner can push: lzyb_slot_push);
- * the fused LDG/STG kernel for everything on one GPU.  The copy engine is never used by auto inside one process. */
+ * 4 = GPU→GPU transfers inside this process are PUSHED: the streaming kernel (TMA ring, digest folded from shared
+ * memory) runs on the SOURCE GPU and stores into the sink frame through the peer mapping (same-GPU work as in auto).
+ * auto = 4 for in-process GPU→GPU transfers of at least lzyb_set_push_min_bytes (default 4 MiB; below that the
+ * cross-device hand-shake outweighs the wire); a source mapped from another process is pulled — TMA ring below
+ * 256 MiB, 3 from there — unless its owner pushes (lzyb_slot_push); the fused LDG/STG kernel for everything on one GPU.
+ * The copy engine is never used by auto inside one process.  1 and 2 are consumer pulls: the digest is then taken
+ * from the bytes as they LAND (a push verifies what it hands to the wire, push_kernels.cuh). */
 int lzyb_set_copy_engine(int engine);
 int lzyb_set_push_min_bytes(uint64_t nbytes);
 /* sub-chunk schedule of a copy-engine pull: the last sub-chunk is last_bytes (0 = payload/32 clamped to

@@ -148,6 +148,9 @@ typedef struct lzyb_backend_ops {
      * of such a descriptor as a local read-only source (HBM backend: CUDA IPC, lzyb_slot_export / lzyb_peer_import) */
     int (*slot_export)(lzyb_handle_t h, lzyb_ipc_desc_t* out);
     int (*peer_import)(const lzyb_ipc_desc_t* desc, int onto_gpu, lzyb_handle_t* out);
+    /* optional (may be NULL): declare that a committed output frame has exactly one consumer, which may then take the
+     * frame over instead of copying it (HBM backend: lzyb_slot_set_movable) */
+    int (*slot_set_movable)(lzyb_handle_t h, int movable);
 } lzyb_backend_ops_t;
 int lzyb_slots_set_backend(const lzyb_backend_ops_t* ops); /* NULL = the HBM backend */
 
@@ -189,6 +192,14 @@ int lzyb_slots_set_chunk_bytes(lzyb_handle_t slots, uint64_t chunk_bytes);
 int lzyb_ctx_create(lzyb_handle_t slots, const char* execution_id, const char* task_id, lzyb_handle_t* out);
 /* one LMS.Slot + its channel assignment (model/.../slot.proto:10-30, operation.proto:31-37) */
 int lzyb_ctx_add_slot(lzyb_handle_t ctx, const char* slot_name, const char* channel_id, int direction);
+/* the same with hints.  LZYB_SLOTF_SOLE_CONSUMER (output slots): the graph has exactly ONE consumer of this output, on
+ * this worker's GPU, and nobody else (no client proxy, no cached result, no fan-out) can ask for it — what the
+ * reference's channel manager could read off its peer table (channel-manager/.../services/SlotsService.java:440-519).
+ * The slot's frame is then not referenced by the `hbm://` store ("uploading" to a store nobody reads would only pin
+ * the frame) and is marked movable, so the consumer's InputSlot takes the frame over instead of copying it
+ * (FileInputBackend.toOutput's ownership hand-over, FileInputBackend.java:38-45). */
+#define LZYB_SLOTF_SOLE_CONSUMER 1u
+int lzyb_ctx_add_slot_flags(lzyb_handle_t ctx, const char* slot_name, const char* channel_id, int direction, uint32_t flags);
 /* beforeExecution(): build the slots; block until every input is READY (or a slot failed) */
 int lzyb_ctx_before_execution(lzyb_handle_t ctx, int timeout_ms);
 /* non-blocking half of beforeExecution(): create the slots and let the inputs bind/download in the

@@ -63,6 +63,7 @@ _SIGS = {
     "lzyb_slots_set_chunk_bytes": (_i, [_H, C.c_uint64]),
     "lzyb_ctx_create": (_i, [_H, _s, _s, C.POINTER(_H)]),
     "lzyb_ctx_add_slot": (_i, [_H, _s, _s, _i]),
+    "lzyb_ctx_add_slot_flags": (_i, [_H, _s, _s, _i, C.c_uint32]),
     "lzyb_ctx_before_execution": (_i, [_H, _i]),
     "lzyb_ctx_prefetch": (_i, [_H]),
     "lzyb_ctx_input_handle": (_i, [_H, _s, C.POINTER(_H)]),
@@ -381,6 +382,9 @@ def frame_store_unspill(uri: str) -> None:
     _check(lib.lzyb_frame_store_unspill(_b(uri)))
 
 
+SLOTF_SOLE_CONSUMER = 1
+
+
 class ExecutionContext:
     """SlotsExecutionContext (lzy/slots/src/main/java/ai/lzy/slots/SlotsExecutionContext.java:45-107)."""
 
@@ -389,8 +393,9 @@ class ExecutionContext:
         _check(lib.lzyb_ctx_create(slots.h, _b(execution_id), _b(task_id), C.byref(h)))
         self.h, self.slots = h.value, slots
 
-    def add_slot(self, name: str, channel_id: str, direction: int) -> None:
-        _check(lib.lzyb_ctx_add_slot(self.h, _b(name), _b(channel_id), direction))
+    def add_slot(self, name: str, channel_id: str, direction: int, sole_consumer: bool = False) -> None:
+        """`sole_consumer` (outputs): exactly one consumer, on this GPU, and no other reader — it takes the frame over"""
+        _check(lib.lzyb_ctx_add_slot_flags(self.h, _b(name), _b(channel_id), direction, SLOTF_SOLE_CONSUMER if sole_consumer else 0))
 
     def prefetch(self) -> None:
         _check(lib.lzyb_ctx_prefetch(self.h))

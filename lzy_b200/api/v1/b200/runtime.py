@@ -65,7 +65,7 @@ class B200RuntimeConfig:
     fanout_chunk_bytes: int = 0                  # 0 = device-chained kernel; > 0 = host-driven chain with that chunk size
     retain: str = "auto"                         # "auto": a frame is freed once no proxy / queued call can ask for it; "all": keep until clear()
     chunk_bytes: int = 0                         # 0 = one launch per transfer; the reference streams 2 MiB chunks
-    copy_engine: str = "auto"                    # "auto" | "ldg" | "tma" | "dma"
+    copy_engine: str = "auto"                    # "auto" | "ldg" | "tma" | "dma" | "push"
     spill_dir: Optional[str] = None              # tier below HBM: evicted frames and cache=True results live here as files
     hbm_budget_bytes: int = 0                    # resident frame-store bytes above which LRU frames are evicted (0 = never)
     user_id: str = field(default_factory=lambda: os.environ.get("LZY_USER", "local-user"))
@@ -109,7 +109,7 @@ class B200RuntimeConfig:
         if name == "spill_dir":
             return raw or None
         choices = {"placement": ("round_robin", "locality", "single"), "retain": ("auto", "all"),
-                   "copy_engine": ("auto", "ldg", "tma", "dma")}.get(name)
+                   "copy_engine": ("auto", "ldg", "tma", "dma", "push")}.get(name)
         if choices and raw not in choices:
             raise ValueError(f"expected one of {choices}")
         return raw
@@ -169,7 +169,7 @@ class B200Runtime(Runtime):
                 N.init(first, last - first + 1, self.config.host_ring_bytes)
                 self.gpus = list(self.config.gpus)
             N.set_copy_engine({"auto": N.ENGINE_AUTO, "ldg": N.ENGINE_LDG, "tma": N.ENGINE_TMA,
-                               "dma": N.ENGINE_DMA}[self.config.copy_engine])
+                               "dma": N.ENGINE_DMA, "push": N.ENGINE_PUSH}[self.config.copy_engine])
             self.store = FrameStore(default_gpu=self.gpus[0])
             if self.config.spill_dir or self.config.hbm_budget_bytes:
                 self.store.configure_tier(self.config.spill_dir, self.config.hbm_budget_bytes)

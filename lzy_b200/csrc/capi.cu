@@ -40,9 +40,7 @@ constexpr int CTL_SLAB = 8192;        // slots that can be live per device
 constexpr int MBOX_SLAB = 65536;      // mailboxes (pinned, all devices)
 constexpr uint64_t DMA_MIN_BYTES = 256ull << 20;  // peer pulls at least this long ride the copy engine (auto policy)
 constexpr int GRID_AUTO = -1000;      // lzyb_set_grid: let launch_stream pick the grid shape
-constexpr uint64_t PUSH_MIN_DEFAULT = 8ull << 20;  // peer transfers at least this long go as push + landed-scan (auto policy)
-constexpr int PUSH_MAX_INFLIGHT = 6;   // concurrent inbound pushes per sink GPU; beyond that a transfer falls back to a pull
-                                       // (scan CTAs wait resident for their chunks: bounded, so outbound pushes always find SM room)
+constexpr uint64_t PUSH_MIN_DEFAULT = 4ull << 20;  // in-process GPU→GPU transfers at least this long are pushed from the source GPU (auto policy)
 // TMA ring shapes that can be selected at run time (lzyb_set_tma_config): {stages, stage bytes, CTAs per SM}
 struct TmaCfg {
     int stages, stage_bytes, ctas_per_sm;
@@ -121,7 +119,6 @@ struct DeviceCtx {
     // DMA pull (launch_dma_verify): scans trail the copy engine on their own stream; events are recycled
     cudaStream_t verify_stream = nullptr;
     cudaStream_t push_stream = nullptr;  // this GPU as a SOURCE: push kernels of in-process transfers are issued here
-    std::atomic<int> push_inflight{0};   // this GPU as a SINK: landed-scan kernels not yet harvested
     std::mutex dma_mu;  // one copy-engine pull is issued at a time per sink GPU (event ring, verify-stream order)
     std::vector<cudaEvent_t> dma_events;
     size_t dma_ev_next = 0;
@@ -164,8 +161,7 @@ struct Slot {
     int fault_kind = LZYB_FAULT_NONE;
     uint64_t fault_arg = 0;
     bool movable = false;        // the owner declared a sole consumer: a whole-payload same-GPU pull moves the frame
-    bool push_counted = false;   // holds one unit of its sink device's push_inflight
-    bool push_dirty = false;     // a landed-scan may have left progress counters non-zero (timed out / reset mid-way)
+    uint64_t push_seq = 0;       // input slot exported as a push sink: the sequence word the producer must write on completion
     std::atomic<int> refs{1};    // lzyb_slot_retain / lzyb_slot_close
     // asynchronous readers of this frame inside this process (consumer stream → event recorded after its last
     // pull launch): close waits for them before the frame goes back to the pool
@@ -210,6 +206,7 @@ struct Global {
     std::atomic<int> dma_growth{6};            // each earlier sub-chunk is this many times larger
     std::atomic<uint64_t> push_min{PUSH_MIN_DEFAULT};
     std::atomic<uint64_t> st_push{0}, st_moves{0};
+    std::atomic<uint64_t> next_push_seq{1};  // arrival words never repeat within this process
     // stats
     std::atomic<uint64_t> st_dma{0};
     std::atomic<uint64_t> st_launch{0}, st_pack{0}, st_pull{0}, st_scan{0}, st_frame{0}, st_bpack{0},
@@ -448,50 +445,10 @@ int launch_dma_verify(DeviceCtx& d, const CopyParams& whole, cudaStream_t st) {
     return LZYB_OK;
 }
 
-// ---- push + landed-scan: the hand-written NVLink carrier (push_kernels.cuh) ---------------------------------
-unsigned int* frame_flags(uint8_t* buf, uint64_t cap) { return reinterpret_cast<unsigned int*>(buf + cap - PUSH_TRAILER_BYTES); }
+// ---- the NVLink carrier: the streaming kernel launched on the SOURCE GPU (push_kernels.cuh) -----------------------
+unsigned long long* frame_trailer(uint8_t* buf, uint64_t cap) { return reinterpret_cast<unsigned long long*>(buf + cap - PUSH_TRAILER_BYTES); }
 
-int launch_push(DeviceCtx& sd, const uint8_t* src, uint8_t* dst, uint64_t nbytes, unsigned int* flags, cudaStream_t ps) {
-    PushParams pp;
-    memset(&pp, 0, sizeof(pp));
-    pp.src = src;
-    pp.dst = dst;
-    pp.nbytes = nbytes;
-    pp.flags = flags;
-    pp.chunk_shift = push_chunk_shift(nbytes);
-    const uint64_t ntiles = (nbytes + PUSH_TILE_BYTES - 1) / PUSH_TILE_BYTES;
-    const uint64_t nchunks = (ntiles + (1ull << pp.chunk_shift) - 1) >> pp.chunk_shift;
-    int grid = sd.sm_count * PUSH_CTAS_PER_SM;
-    if ((uint64_t)grid > nchunks) grid = (int)(nchunks ? nchunks : 1);
-    const bool v256 = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 31) == 0;
-    if (v256)
-        push_kernel<true><<<grid, 256, 0, ps>>>(pp);
-    else
-        push_kernel<false><<<grid, 256, 0, ps>>>(pp);
-    g.st_launch++;
-    g.st_push++;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "push launch failed: %s", cudaGetErrorString(e));
-    return LZYB_OK;
-}
-
-// `scan` describes the sink side of the chunk (src = the sink's own payload bytes, dst = nullptr, ctl / fin / mailbox set)
-int launch_landed_scan(DeviceCtx& dd, CopyParams scan, unsigned int* flags, cudaStream_t st) {
-    scan.dst = nullptr;
-    scan.signal_flags = flags;
-    scan.chunk_shift = push_chunk_shift(scan.nbytes);
-    const uint64_t ntiles = (scan.nbytes + PUSH_TILE_BYTES - 1) / PUSH_TILE_BYTES;
-    const uint64_t nchunks = (ntiles + (1ull << scan.chunk_shift) - 1) >> scan.chunk_shift;
-    int grid = dd.sm_count / 2;  // every CTA resident with room to spare: a CTA waiting for a late chunk blocks nobody
-    if ((uint64_t)grid > nchunks) grid = (int)(nchunks ? nchunks : 1);
-    landed_scan_kernel<<<grid, 256, 0, st>>>(scan);
-    g.st_launch++;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "landed-scan launch failed: %s", cudaGetErrorString(e));
-    return LZYB_OK;
-}
-
-void add_reader(Slot& s, cudaStream_t st) {
+cudaEvent_t add_reader(Slot& s, cudaStream_t st) {
     cudaEvent_t ev = nullptr;
     for (auto& r : s.readers)
         if (r.first == st) ev = r.second;
@@ -500,29 +457,31 @@ void add_reader(Slot& s, cudaStream_t st) {
         s.readers.emplace_back(st, ev);
     }
     cudaEventRecord(ev, st);
+    return ev;
 }
 
-// Both halves of an in-process transfer between two GPUs.  `p` is the chunk as lzyb_transfer_chunk built it
-// (src on the source GPU, dst on the sink GPU); the caller's device is the sink's.
-int launch_push_pair(DeviceCtx& sd, DeviceCtx& dd, Slot& src, Slot& dst, const CopyParams& p, cudaStream_t st) {
-    unsigned int* flags = frame_flags(dst.buf, dst.cap);
+// An in-process transfer between two GPUs.  `p` is the chunk as lzyb_transfer_chunk built it (src on the source GPU,
+// dst / header on the sink GPU, ctl on the sink GPU — reached through the peer mapping —, mailbox in pinned host memory);
+// the caller's current device is the sink's.  The kernel runs on the source GPU's push stream; the sink stream `st`
+// continues only after it (cross-device event), so everything queued on `st` afterwards sees a complete, verified frame.
+int launch_push_inproc(DeviceCtx& sd, DeviceCtx& dd, Slot& src, Slot& dst, const CopyParams& p, cudaStream_t st) {
+    cudaEvent_t done = nullptr;
     {
-        // the push may start once everything queued on the sink stream so far has run (an earlier chunk's scan resets
-        // the counters it consumed) and once the producer's payload is final
+        // the push may start once everything queued on the sink stream so far has run and the producer's payload is final
         std::lock_guard<std::mutex> issue(dd.dma_mu);
         cudaEvent_t ev = dd.next_dma_event();
         CU(cudaEventRecord(ev, st));
         DeviceGuard sg(sd.ordinal);
         CU(cudaStreamWaitEvent(sd.push_stream, ev, 0));
         if (src.last_ev) CU(cudaStreamWaitEvent(sd.push_stream, src.last_ev, 0));
-        int rc = launch_push(sd, p.src, p.dst, p.nbytes, flags, sd.push_stream);
+        int rc = launch_stream(sd, p, true, sd.push_stream, true);
         if (rc != LZYB_OK) return rc;
-        add_reader(src, sd.push_stream);  // neither frame is recycled under a push that is still running
-        add_reader(dst, sd.push_stream);
+        g.st_push++;
+        add_reader(src, sd.push_stream);         // neither frame is recycled under a push that is still running
+        done = add_reader(dst, sd.push_stream);
     }
-    CopyParams scan = p;
-    scan.src = p.dst;
-    return launch_landed_scan(dd, scan, flags, st);
+    CU(cudaStreamWaitEvent(st, done, 0));
+    return LZYB_OK;
 }
 
 void arm_mailbox(Slot& s, CopyParams& p) {
@@ -547,11 +506,6 @@ int harvest(Slot& s) {
     s.sum = s.mbox->sum;
     s.xr = s.mbox->xr;
     s.ctl_dirty = false;
-    if (s.push_counted) {
-        g.devs[s.dev]->push_inflight--;
-        s.push_counted = false;
-    }
-    if (s.mbox->status == 1u) s.push_dirty = false;  // a verified landed-scan consumed and reset every counter
     return static_cast<int>(s.mbox->status);
 }
 
@@ -1054,11 +1008,6 @@ int lzyb_slot_close(lzyb_handle_t h) {
         cudaEventDestroy(r.second);
     }
     s->readers.clear();
-    if (s->push_counted) {
-        d.push_inflight--;
-        s->push_counted = false;
-    }
-    if (s->push_dirty && !s->remote && s->buf && has_trailer(s->cap)) cudaMemset(frame_flags(s->buf, s->cap), 0, PUSH_TRAILER_BYTES);
     if (s->remote) {
         // the mapping stays in g.ipc_cache (closed at shutdown)
     } else if (s->buf) {
@@ -1165,27 +1114,17 @@ int64_t lzyb_transfer_chunk(lzyb_handle_t dst_h, lzyb_handle_t src_h, uint64_t o
     if (src->last_ev && src->last_stream != st) cudaStreamWaitEvent(st, src->last_ev, 0);
     const bool peer = src->remote || src->dev != dst->dev;
     const int engine = g.engine.load();
-    // auto: an in-process transfer between two GPUs is PUSHED by a kernel on the source GPU while a scan on the sink GPU
-    // digests what has landed (push_kernels.cuh); a source mapped from another process can only be pulled from here
-    // (its owner pushes through lzyb_slot_push): the TMA ring below 256 MiB, the copy engine + trailing scans above
-    bool push = peer && !src->remote && !dst->remote && has_trailer(dst->cap) &&
-                (engine == 4 || (engine == 0 && len >= g.push_min.load()));
-    if (push && !dst->push_counted) {
-        if (d.push_inflight.fetch_add(1) >= PUSH_MAX_INFLIGHT && engine != 4) {
-            d.push_inflight--;
-            push = false;
-        } else {
-            dst->push_counted = true;
-        }
-    }
+    // auto: an in-process transfer between two GPUs is PUSHED — the streaming kernel runs on the source GPU and stores
+    // through the peer mapping (push_kernels.cuh: posted writes keep 700 GB/s per direction where pulls drop to 671 once
+    // both directions are busy).  A source mapped from another process can only be pulled from here (its owner pushes
+    // through lzyb_slot_push): the TMA ring below 256 MiB, the copy engine + trailing scans above.
+    const bool push = peer && !src->remote && !dst->remote && (engine == 4 || (engine == 0 && len >= g.push_min.load()));
     const bool dma = !push && peer && (engine == 3 || (engine == 0 && len >= DMA_MIN_BYTES));
     int rc;
-    if (push) {
-        dst->push_dirty = true;
-        rc = launch_push_pair(*g.devs[src->dev], d, *src, *dst, p, st);
-    } else {
+    if (push)
+        rc = launch_push_inproc(*g.devs[src->dev], d, *src, *dst, p, st);
+    else
         rc = dma ? launch_dma_verify(d, p, st) : launch_stream(d, p, true, st, peer);
-    }
     if (rc != LZYB_OK) return rc;
     g.st_pull++;
     if (src->dev == dst->dev && !src->remote)
@@ -1201,15 +1140,7 @@ int64_t lzyb_transfer_chunk(lzyb_handle_t dst_h, lzyb_handle_t src_h, uint64_t o
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "transfer failed: %s", cudaGetErrorString(e));
     } else if (!src->remote) {
-        // an asynchronous reader: the source frame must not be recycled under it (one event per consumer stream)
-        cudaEvent_t ev = nullptr;
-        for (auto& r : src->readers)
-            if (r.first == st) ev = r.second;
-        if (!ev) {
-            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-            src->readers.emplace_back(st, ev);
-        }
-        cudaEventRecord(ev, st);
+        add_reader(*src, st);  // an asynchronous reader: the source frame must not be recycled under it
     }
     return (int64_t)len;
 }
@@ -1222,17 +1153,7 @@ static int input_reset_locked(Slot& s) {
         CU(cudaMemset(s.ctl, 0, sizeof(SlotCtl)));
         s.ctl_dirty = false;
     }
-    if (s.push_counted) {
-        d.push_inflight--;
-        s.push_counted = false;
-    }
-    if (s.push_dirty && !s.remote && has_trailer(s.cap)) {
-        // a push that was cut short may still be running and may have left counters behind: let it finish, then
-        // restore the zero-at-rest invariant of the trailer
-        for (auto& r : s.readers) cudaEventSynchronize(r.second);
-        CU(cudaMemset(frame_flags(s.buf, s.cap), 0, PUSH_TRAILER_BYTES));
-        s.push_dirty = false;
-    }
+    for (auto& r : s.readers) cudaEventSynchronize(r.second);  // a push into this frame that is still running finishes first
     s.delivered = 0;
     s.digest_pending = false;
     s.state = LZYB_ST_EMPTY;
@@ -1275,6 +1196,7 @@ static int finish_common(Slot& dst, const uint64_t expect[2], const Slot* src, v
     }
     int st = harvest(dst);
     if (st < 0) return st;
+    if (st == 1 && expect && (dst.digest[0] != expect[0] || dst.digest[1] != expect[1])) st = 2;  // verdict of another frame
     if (st == 2) {
         input_reset_locked(dst);
         return fail(LZYB_E_PEER, "digest mismatch on slot %s: delivered bytes differ from what the producer committed",
@@ -1495,9 +1417,10 @@ int lzyb_sink_export(lzyb_handle_t h, lzyb_ipc_desc_t* out) {
     if (!s || !out) return fail(LZYB_E_ARG, "unknown slot handle");
     std::lock_guard<std::mutex> lk(s->mu);
     if (!s->is_input || s->remote) return fail(LZYB_E_STATE, "slot %s is not a local input slot", s->id.c_str());
-    if (s->state == LZYB_ST_READY || s->state == LZYB_ST_CLOSED || s->state == LZYB_ST_FAILED)
-        return fail(LZYB_E_STATE, "slot %s cannot receive (state %d)", s->id.c_str(), s->state);
-    if (!has_trailer(s->cap)) return fail(LZYB_E_ARG, "slot %s is too small to be pushed into (no counter trailer)", s->id.c_str());
+    if (s->state != LZYB_ST_EMPTY || s->delivered != 0 || s->digest_pending)
+        return fail(LZYB_E_STATE, "slot %s cannot receive a push (state %d, %llu bytes delivered)", s->id.c_str(), s->state,
+                    (unsigned long long)s->delivered);
+    if (!has_trailer(s->cap)) return fail(LZYB_E_ARG, "slot %s is too small to be pushed into (no trailer): pull it", s->id.c_str());
     DeviceCtx& d = *g.devs[s->dev];
     DeviceGuard dg(d.ordinal);
     memset(out, 0, sizeof(*out));
@@ -1508,6 +1431,8 @@ int lzyb_sink_export(lzyb_handle_t h, lzyb_ipc_desc_t* out) {
     out->nbytes = s->nbytes;
     out->gpu = d.ordinal;
     out->pid = (int32_t)getpid();
+    s->push_seq = g.next_push_seq++ | ((uint64_t)(uint32_t)getpid() << 40);  // never 0, never repeated for this frame
+    memcpy(out->reserved, &s->push_seq, sizeof(uint64_t));  // reserved[0..8): the arrival word the producer must write
     return LZYB_OK;
 }
 
@@ -1538,13 +1463,15 @@ int lzyb_slot_push(lzyb_handle_t src_h, const lzyb_ipc_desc_t* sink, uint64_t of
     if (sink->pid == (int32_t)getpid()) return fail(LZYB_E_ARG, "sink belongs to this process; use lzyb_transfer_chunk");
     if (sink->nbytes != src->nbytes) return fail(LZYB_E_PEER, "sink expects %llu bytes, slot %s holds %llu", (unsigned long long)sink->nbytes,
                                                   src->id.c_str(), (unsigned long long)src->nbytes);
-    if (!has_trailer(sink->buffer_bytes) || sink->buffer_bytes < HEADER_BYTES + PUSH_TRAILER_BYTES ||
-        sink->nbytes > sink->buffer_bytes - HEADER_BYTES - PUSH_TRAILER_BYTES)
+    if (!has_trailer(sink->buffer_bytes) || sink->nbytes > sink->buffer_bytes - HEADER_BYTES - PUSH_TRAILER_BYTES)
         return fail(LZYB_E_PEER, "sink descriptor: %llu payload bytes do not fit its %llu-byte frame", (unsigned long long)sink->nbytes,
                     (unsigned long long)sink->buffer_bytes);
-    if ((offset & 15) || offset > src->nbytes) return fail(LZYB_E_ARG, "bad offset %llu", (unsigned long long)offset);
-    if (len == 0 || offset + len > src->nbytes) len = src->nbytes - offset;
-    if (len == 0) return LZYB_OK;
+    // a push carries the whole payload: the verdict is the digest of everything that went over the wire against the
+    // digest this slot committed.  (Partial, offset-resumed deliveries between processes take the pull path.)
+    if (offset != 0 || (len != 0 && len != src->nbytes)) return fail(LZYB_E_ARG, "a push carries the whole payload (offset 0, len 0 or nbytes)");
+    uint64_t seq = 0;
+    memcpy(&seq, sink->reserved, sizeof(uint64_t));
+    if (seq == 0) return fail(LZYB_E_PEER, "sink descriptor carries no arrival word (not produced by lzyb_sink_export)");
     DeviceCtx& d = *g.devs[src->dev];
     DeviceGuard dg(d.ordinal);
     void* base = nullptr;
@@ -1552,11 +1479,31 @@ int lzyb_slot_push(lzyb_handle_t src_h, const lzyb_ipc_desc_t* sink, uint64_t of
     if (rc != LZYB_OK) return rc;
     cudaStream_t st = pick_stream(d, stream);
     if (src->last_ev && src->last_stream != st) CU(cudaStreamWaitEvent(st, src->last_ev, 0));
+    // the slot's own accumulator block (zero at rest since its commit) collects this push's partials: pushes of one slot
+    // take turns on the device
+    for (auto& r : src->readers)
+        if (r.first != st) CU(cudaStreamWaitEvent(st, r.second, 0));
     uint8_t* sb = static_cast<uint8_t*>(base);
-    rc = launch_push(d, src->payload() + offset, sb + HEADER_BYTES + offset, len, frame_flags(sb, sink->buffer_bytes), st);
+    CopyParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = src->payload();
+    p.dst = sb + HEADER_BYTES;
+    p.nbytes = src->nbytes;
+    p.ctl = src->ctl;
+    p.total_nbytes = src->nbytes;
+    p.fin = FIN_VERIFY;
+    p.expect[0] = src->digest[0];
+    p.expect[1] = src->digest[1];
+    p.dst_hdr = reinterpret_cast<lzyb_frame_header_t*>(sb);
+    fill_template(*src, &p.hdr_template);
+    p.sys_fence = 1;
+    p.arrive = frame_trailer(sb, sink->buffer_bytes);
+    p.arrive_seq = seq;
+    rc = launch_stream(d, p, true, st, true);
     if (rc != LZYB_OK) return rc;
+    g.st_push++;
     add_reader(*src, st);
-    g.st_bpull_p += len;
+    g.st_bpull_p += src->nbytes;
     if (!stream) CU(cudaStreamSynchronize(st));
     return LZYB_OK;
 }
@@ -1568,48 +1515,37 @@ int64_t lzyb_input_expect_push(lzyb_handle_t dst_h, const lzyb_ipc_desc_t* produ
     if (!dst->is_input || dst->remote) return fail(LZYB_E_STATE, "slot %s is not a local input slot", dst->id.c_str());
     if (dst->state == LZYB_ST_CLOSED || dst->state == LZYB_ST_FAILED) return fail(LZYB_E_LOCAL, "sink %s already closed", dst->id.c_str());
     if (dst->state == LZYB_ST_READY || dst->digest_pending) return LZYB_EOF;
-    if (!has_trailer(dst->cap)) return fail(LZYB_E_ARG, "slot %s is too small to be pushed into", dst->id.c_str());
+    if (dst->push_seq == 0) return fail(LZYB_E_STATE, "slot %s was not exported as a push sink (lzyb_sink_export)", dst->id.c_str());
     if (producer->nbytes != dst->nbytes) return fail(LZYB_E_PEER, "peer holds %llu bytes, sink expects %llu", (unsigned long long)producer->nbytes,
                                                       (unsigned long long)dst->nbytes);
     if (producer->ndim > LZYB_MAX_DIMS) return fail(LZYB_E_PEER, "peer descriptor: ndim %u > %d", producer->ndim, LZYB_MAX_DIMS);
-    if (offset != dst->delivered || (offset & 15)) return fail(LZYB_E_ARG, "offset %llu != delivered %llu", (unsigned long long)offset,
-                                                               (unsigned long long)dst->delivered);
-    if (len == 0 || offset + len > dst->nbytes) len = dst->nbytes - offset;
-    if (len == 0) return LZYB_EOF;
-    const bool last = offset + len == dst->nbytes;
-    if (!last && (len & 15)) return fail(LZYB_E_ARG, "intermediate chunks must be multiples of 16 bytes");
+    if (offset != 0 || (len != 0 && len != dst->nbytes)) return fail(LZYB_E_ARG, "a push carries the whole payload (offset 0, len 0 or nbytes)");
     DeviceCtx& d = *g.devs[dst->dev];
     DeviceGuard dg(d.ordinal);
     cudaStream_t st = pick_stream(d, stream);
-    CopyParams p;
-    memset(&p, 0, sizeof(p));
-    p.src = dst->payload() + offset;
-    p.nbytes = len;
-    p.word_base = offset >> 3;
-    p.ctl = dst->ctl;
-    p.total_nbytes = dst->nbytes;
-    p.fin = FIN_NONE;
-    if (last) {
-        p.fin = FIN_VERIFY;
-        p.expect[0] = producer->digest[0];
-        p.expect[1] = producer->digest[1];
-        p.dst_hdr = reinterpret_cast<lzyb_frame_header_t*>(dst->buf);
-        dst->dtype = producer->dtype;
-        dst->ndim = producer->ndim;
-        memcpy(dst->shape, producer->shape, sizeof(dst->shape));
-        fill_template(*dst, &p.hdr_template);
-        arm_mailbox(*dst, p);
-    }
-    dst->push_dirty = true;
-    int rc = launch_landed_scan(d, p, frame_flags(dst->buf, dst->cap), st);
-    if (rc != LZYB_OK) return rc;
+    dst->dtype = producer->dtype;
+    dst->ndim = producer->ndim;
+    memcpy(dst->shape, producer->shape, sizeof(dst->shape));
+    dst->seq++;
+    dst->mbox->status = 0;
+    dst->mbox->seq = 0;
+    ArrivalWait w;
+    memset(&w, 0, sizeof(w));
+    w.trailer = frame_trailer(dst->buf, dst->cap);
+    w.seq = dst->push_seq;
+    w.mbox = dst->mbox;
+    w.mbox_seq = dst->seq;
+    arrival_wait_kernel<<<1, 32, 0, st>>>(w);
+    g.st_launch++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LZYB_E_LOCAL, "arrival-wait launch failed: %s", cudaGetErrorString(e));
     g.st_pull++;
-    dst->delivered += len;
+    dst->delivered = dst->nbytes;
     dst->state = LZYB_ST_FILLING;
-    dst->ctl_dirty = !last;
-    if (last) dst->digest_pending = true;
+    dst->ctl_dirty = false;
+    dst->digest_pending = true;
     note(*dst, st);
-    return (int64_t)len;
+    return (int64_t)dst->nbytes;
 }
 
 // ---- fan-out: chunk-pipelined pull chain -------------------------------------------------------

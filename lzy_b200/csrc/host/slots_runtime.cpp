@@ -47,7 +47,7 @@ const lzyb_backend_ops_t kHbmBackend = {
     lzyb_slot_create, lzyb_input_open,      lzyb_slot_commit,         lzyb_slot_read,       lzyb_slot_info,
     lzyb_slot_find,   lzyb_slot_close,      lzyb_transfer_chunk,      lzyb_input_finish,    lzyb_input_write_host,
     lzyb_input_finish_expect, lzyb_input_to_output, lzyb_input_reset, lzyb_slot_retain, lzyb_slot_set_meta,
-    lzyb_slot_export, lzyb_peer_import,
+    lzyb_slot_export, lzyb_peer_import, lzyb_slot_set_movable,
 };
 std::atomic<const lzyb_backend_ops_t*> g_ops{&kHbmBackend};
 lzyb_backend_ops_t g_custom_ops;
@@ -494,6 +494,7 @@ struct ExecCtx : std::enable_shared_from_this<ExecCtx> {
     struct Desc {
         std::string name, channel;
         int direction;
+        uint32_t flags = 0;
     };
     std::vector<Desc> descs;
     std::mutex mu;
@@ -516,6 +517,7 @@ struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
     std::mutex mu;
     std::condition_variable cv;
     bool data_done = false, closed = false;
+    bool sole_consumer = false;      // LZYB_SLOTF_SOLE_CONSUMER: the one consumer takes the frame over
     SlotThreads::TicketPtr prepare;  // PrepareThread
     bool is_input() const override { return false; }
     Completion& before() override { return before_; }
@@ -559,6 +561,7 @@ struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
             complete_.fail_with(std::string("Error while binding output slot: ") + lzyb_last_error());
             return;
         }
+        if (sole_consumer && ops().slot_set_movable) ops().slot_set_movable(backend, 1);
         inst->service.reg(shared_from_this());  // enable requests from outside
         lzyb_bind_result_t res;
         int rc = cmc().bind(inst->cm, inst->next_idk("bind").c_str(), channel_id.c_str(), id.c_str(),
@@ -588,6 +591,9 @@ struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
 
     // StorageOutputTransfer.readFrom(backend.readFromOffset(0))
     bool upload_to_storage(const char* uri) {
+        // a frame promised to its one consumer is not parked in a store nobody reads: the reference would hold the
+        // store's second reference and force the copy this hint exists to avoid
+        if (is_hbm_uri(uri) && sole_consumer && ops().slot_set_movable) return true;
         if (is_hbm_uri(uri)) return lzyb_frame_store_put(uri, backend) == LZYB_OK;  // stays in HBM: no copy
         if (is_file_uri(uri)) {  // durable and visible to every process of the box
             const std::string path = file_path_of(uri);
@@ -1076,6 +1082,7 @@ int build_slots(ExecCtx& c) {
             s->id = d.name;
             s->channel_id = d.channel;
             s->ctx = &c;
+            s->sole_consumer = (d.flags & LZYB_SLOTF_SOLE_CONSUMER) != 0;
             c.slots.push_back(s);
             c.outputs[d.name] = s;
             s->start();
@@ -1288,13 +1295,17 @@ int lzyb_ctx_create(lzyb_handle_t slots, const char* execution_id, const char* t
 }
 
 int lzyb_ctx_add_slot(lzyb_handle_t h, const char* slot_name, const char* channel_id, int direction) {
+    return lzyb_ctx_add_slot_flags(h, slot_name, channel_id, direction, 0);
+}
+
+int lzyb_ctx_add_slot_flags(lzyb_handle_t h, const char* slot_name, const char* channel_id, int direction, uint32_t flags) {
     auto c = get_ctx(h);
     if (!c) return fail(LZYB_E_ARG, "unknown context handle");
     if (!slot_name || !channel_id) return fail(LZYB_E_ARG, "null argument");
     if (direction != LZYB_DIR_INPUT && direction != LZYB_DIR_OUTPUT) return fail(LZYB_E_INVALID, "slot direction must be INPUT or OUTPUT");
     std::lock_guard<std::mutex> lk(c->mu);
     if (c->built) return fail(LZYB_E_STATE, "slots are already built");
-    c->descs.push_back({slot_name, channel_id, direction});
+    c->descs.push_back({slot_name, channel_id, direction, flags});
     return LZYB_OK;
 }
 

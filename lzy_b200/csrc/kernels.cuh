@@ -69,7 +69,10 @@ struct CopyParams {
     const unsigned int* wait_flags;   // upstream stage's counters (peer memory); nullptr = the source is final
     unsigned int* signal_flags;       // this stage's counters; nullptr = nobody reads from this stage
     unsigned int chunk_shift;
-    unsigned int pad2;
+    unsigned int sys_fence;           // push into another process's frame: every CTA fences its stores at system scope before its ticket
+    // cross-process push (push_kernels.cuh): the sink frame's trailer; the last CTA writes verdict + digest, then the sequence word
+    unsigned long long* arrive;
+    unsigned long long arrive_seq;
     lzyb_frame_header_t hdr_template;    // magic/version/dtype/shape for FIN_PUBLISH
 };
 
@@ -191,6 +194,15 @@ __device__ __forceinline__ void block_epilogue(const CopyParams& a, unsigned lon
         __threadfence_system();
         a.mbox->status = status;
     }
+    if (a.arrive) {  // the consumer's GPU is spinning on arrive[0] (arrival_wait_kernel): everything else first
+        a.arrive[1] = status;
+        a.arrive[2] = dg[0];
+        a.arrive[3] = dg[1];
+        a.arrive[4] = tsum;
+        a.arrive[5] = txr;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.arrive), "l"(a.arrive_seq) : "memory");
+    }
 }
 
 // Tail of a chunk: the (< 16) bytes after the last full vector, folded as up to two zero-padded
@@ -251,6 +263,7 @@ stream_digest_kernel(const __grid_constant__ CopyParams a) {
         fold_tail(a, a.src + (nvec << 4), STORE ? a.dst + (nvec << 4) : nullptr, a.word_base + 2ull * nvec, tail,
                   sum, xr);
     }
+    if (a.sys_fence) __threadfence_system();  // pushing into another process's frame: stores performed before this CTA's ticket
     block_epilogue(a, sum, xr);
 }
 

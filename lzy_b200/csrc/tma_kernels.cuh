@@ -124,6 +124,9 @@ tma_stream_digest_kernel(const __grid_constant__ CopyParams a) {
                 if (my_tiles > 0) {
                     bulk_wait_read<0>();
                     mbar_arrive(&empty[static_cast<int>((my_tiles - 1) % STAGES)]);
+                    // a consumer in another process learns completion from a flag, not from this stream: this CTA's
+                    // bulk stores must have been performed, not merely read out of shared memory, before its ticket
+                    if (a.sys_fence) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                 }
             }
         }
@@ -173,6 +176,7 @@ tma_stream_digest_kernel(const __grid_constant__ CopyParams a) {
             }
         }
     }
+    if (a.sys_fence) __threadfence_system();  // generic stores of the remainder path and, cumulatively, the storer's bulk stores
     block_epilogue(a, sum, xr);
 }
 

@@ -123,10 +123,10 @@ def test_consumer_process_pulls_over_cuda_ipc_from_producer_process():
 @pytest.mark.parametrize("nbytes", [(96 << 20) + 4096 + 7, (2 << 20) + 1])
 def test_producer_process_pushes_into_the_consumer_process_frame(nbytes):
     """The hand-written carrier between worker PROCESSES: the consumer exports its empty input frame (CUDA IPC), the
-    producer's process runs push_kernel into it over NVLink, the consumer's GPU runs landed_scan_kernel, which digests
-    every chunk as the progress counters in the frame's trailer say it has landed.  No copy engine, no cross-process
-    event; the delivered bytes equal the counter-based pattern of the oracle, twice (the second delivery reuses the
-    pooled frame, so the counters were left at zero)."""
+    producer's process launches the TMA-ring kernel with that frame as destination (digest folded on the way, header,
+    verdict and — last — the arrival word written into the frame), the consumer's GPU runs the one-thread
+    arrival_wait_kernel.  No copy engine, no cross-process event; the delivered bytes equal the counter-based pattern of
+    the oracle, twice (the second delivery reuses the pooled frame under a fresh arrival word)."""
     import numpy as np
 
     import oracle
@@ -147,7 +147,7 @@ def test_producer_process_pushes_into_the_consumer_process_frame(nbytes):
             sink = inp.sink_export()
             stream = torch.cuda.Stream(device=1)
             sp = int(stream.cuda_stream)
-            assert inp.expect_push(producer, 0, 0, sp) == nbytes   # the scan is waiting on the GPU before a byte has moved
+            assert inp.expect_push(producer, 0, 0, sp) == nbytes   # the waiter is spinning on the GPU before a byte has moved
             child.stdin.write(bytes(sink).hex() + "\n")
             child.stdin.flush()
             word, pushes, dma = child.stdout.readline().split()

@@ -61,6 +61,65 @@ def test_ring_control_plane_two_ranks(world):
         assert token == (rank - n_ops) % world  # after 8 hops the chain that started 8 ranks upstream is here
 
 
+def _mailbox_worker(rank: int, world: int, port: int, n_ops: int, steps: int, out):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lzy_b200.ring import DESC_BYTES, ShmMailbox, predecessor, successor
+    box = ShmMailbox.rendezvous(dist, world, rank, lanes=2)
+    SINK, OUT = 0, 1
+    token = rank
+    try:
+        for step in range(steps):
+            token = rank  # every step starts a fresh chain on every rank
+            for h in range(n_ops):
+                # what bench.py's push ring does per hop: publish my sink and my committed output, learn my successor's
+                # sink (my push kernel writes there) and my predecessor's output (what my scan verifies against)
+                box.post(SINK, bytes([rank, step, h, 0xAA]) + bytes(DESC_BYTES - 4))
+                box.post(OUT, bytes([rank, step, h, token]) + bytes(DESC_BYTES - 4))
+                sink = box.read(successor(rank, world), SINK)
+                src = box.read(predecessor(rank, world), OUT)
+                assert tuple(sink[:4]) == (successor(rank, world), step, h, 0xAA)
+                assert tuple(src[:3]) == (predecessor(rank, world), step, h)
+                token = src[3]
+            dist.barrier()
+        out.put((rank, token))
+    finally:
+        box.close()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ring_control_plane_over_the_shared_memory_mailbox(world):
+    """descriptor exchange without a collective: posts and reads pair up one to one per (rank, lane), across steps"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    n_ops, steps = 8, 5
+    procs = [ctx.Process(target=_mailbox_worker, args=(r, world, port, n_ops, steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, token in res:
+        assert token == (rank - n_ops) % world
+
+
+def test_mailbox_refuses_wrong_sizes_and_times_out():
+    from lzy_b200.ring import ShmMailbox
+    import uuid
+    box = ShmMailbox(f"lzyb_t_{uuid.uuid4().hex[:10]}", 2, 0, lanes=1, create=True)
+    try:
+        with pytest.raises(ValueError):
+            box.post(0, b"short")
+        with pytest.raises(TimeoutError):
+            box.read(1, 0, timeout=0.05)
+    finally:
+        box.close()
+
+
 def test_descriptor_size_is_checked():
     from lzy_b200.ring import exchange_descriptors
     with pytest.raises(ValueError):
