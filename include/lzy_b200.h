@@ -299,11 +299,13 @@ int lzyb_stats_reset(void);
  * the sink GPU digests each landed sub-chunk in the shadow of the next copy (same-GPU work as in auto),
  * 4 = GPU→GPU transfers inside this process are PUSHED: the streaming kernel (TMA ring, digest folded from shared
  * memory) runs on the SOURCE GPU and stores into the sink frame through the peer mapping (same-GPU work as in auto).
- * auto = 4 for in-process GPU→GPU transfers of at least lzyb_set_push_min_bytes (default 4 MiB; below that the
- * cross-device hand-shake outweighs the wire); a source mapped from another process is pulled — TMA ring below
- * 256 MiB, 3 from there — unless its owner pushes (lzyb_slot_push); the fused LDG/STG kernel for everything on one GPU.
- * The copy engine is never used by auto inside one process.  1 and 2 are consumer pulls: the digest is then taken
- * from the bytes as they LAND (a push verifies what it hands to the wire, push_kernels.cuh). */
+ * auto, between two GPUs of this process: a PULL (2, or 1 for short / unaligned chunks) while the sink GPU is not itself
+ * serving a transfer — read responses are the cheapest SM traffic, 770–780 GB/s — and a PUSH (4) for transfers of at
+ * least lzyb_set_push_min_bytes (default 4 MiB) into a GPU that is sourcing one right now: in a ring or a bidirectional
+ * exchange a pull's requests share the wire with the payload the same GPU serves (657–671 GB/s per direction), posted
+ * writes keep 684–700.  A source mapped from another process is pulled (2) unless its owner pushes (lzyb_slot_push).
+ * auto never uses the copy engine; 3 stays available by name.  1 and 2 take the digest from the bytes as they LAND,
+ * a push verifies what it hands to the wire (push_kernels.cuh). */
 int lzyb_set_copy_engine(int engine);
 int lzyb_set_push_min_bytes(uint64_t nbytes);
 /* sub-chunk schedule of a copy-engine pull: the last sub-chunk is last_bytes (0 = payload/32 clamped to

@@ -34,7 +34,7 @@ from typing import TYPE_CHECKING, Any, Callable, Dict, List, Optional, Sequence,
 from .... import _host as H
 from .... import _native as N
 from ....devmem import current_stream_ptr
-from ....core.dataflow import plan_dataflow
+from ....core.dataflow import plan_dataflow, sole_consumer_outputs
 from ....env import applied_env
 from ....proxy import proxy
 from ....serialization.types import get_type
@@ -65,6 +65,7 @@ class B200RuntimeConfig:
     fanout_chunk_bytes: int = 0                  # 0 = device-chained kernel; > 0 = host-driven chain with that chunk size
     retain: str = "auto"                         # "auto": a frame is freed once no proxy / queued call can ask for it; "all": keep until clear()
     chunk_bytes: int = 0                         # 0 = one launch per transfer; the reference streams 2 MiB chunks
+    move_sole_consumer: bool = True              # an output with one consumer on the same GPU and no other reader is handed over, not copied
     copy_engine: str = "auto"                    # "auto" | "ldg" | "tma" | "dma" | "push"
     spill_dir: Optional[str] = None              # tier below HBM: evicted frames and cache=True results live here as files
     hbm_budget_bytes: int = 0                    # resident frame-store bytes above which LRU frames are evicted (0 = never)
@@ -95,7 +96,7 @@ class B200RuntimeConfig:
         raw = raw.strip()
         if name == "gpus":
             return None if raw.lower() in ("", "all") else [int(x) for x in raw.split(",") if x.strip()]
-        if name in ("prefetch", "republish_inputs"):
+        if name in ("prefetch", "republish_inputs", "move_sole_consumer"):
             if raw.lower() in ("1", "true", "yes", "on"):
                 return True
             if raw.lower() in ("0", "false", "no", "off"):
@@ -377,6 +378,12 @@ class B200Runtime(Runtime):
                 remote = sorted(g for g in gset if g != src_gpu)
                 if len(remote) >= self.config.fanout_threshold:
                     fanout[eid] = _Fanout(eid, uri, src_gpu, remote)
+        # outputs that travel by ownership hand-over: one consumer on the producer's GPU and nobody else who could ask
+        sole: set = set()
+        if self.config.move_sole_consumer and not self.config.republish_inputs and hasattr(snapshot, "claims"):
+            sole = sole_consumer_outputs(plan, inputs_of, placement, snapshot.claims,
+                                         lambda eid: eid in fanout or snapshot.is_persistent(eid))
+            self.stats["moved_outputs"] = self.stats.get("moved_outputs", 0) + len(sole)
         try:
             # BuildTasks: slot → channel assignments; every input binds right away (prefetch)
             for i, c in enumerate(calls):
@@ -386,7 +393,7 @@ class B200Runtime(Runtime):
                         continue  # delivered by the fan-out chain, not by a unicast transfer
                     ctx.add_slot(f"/{c.id}/{eid}", channel_of[eid], H.DIR_INPUT)
                 for eid in c.entry_ids:
-                    ctx.add_slot(f"/{c.id}/{eid}", channel_of[eid], H.DIR_OUTPUT)
+                    ctx.add_slot(f"/{c.id}/{eid}", channel_of[eid], H.DIR_OUTPUT, sole_consumer=eid in sole)
                 ctxs.append(ctx)
             if self.config.prefetch:
                 for ctx in ctxs:

@@ -117,6 +117,15 @@ class FrameSnapshot(Snapshot):
         with self._lock:
             self._persistent.add(entry_id)
 
+    def claims(self, entry_id: str) -> int:
+        """how many parties can still ask for this entry: queued consumer calls + its lazy proxy while that is alive"""
+        with self._lock:
+            return self._pins.get(entry_id, 0)
+
+    def is_persistent(self, entry_id: str) -> bool:
+        with self._lock:
+            return entry_id in self._persistent
+
     def produced(self, entry_id: str) -> None:
         """an op wrote this entry: take a reference on its frame (or let it go if nobody waits for it)"""
         entry = self._entries.get(entry_id)

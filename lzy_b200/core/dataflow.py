@@ -56,3 +56,50 @@ def plan_dataflow(calls: Sequence["LzyCall"], uri_of: Callable[[str], str], exis
             supplied[u] = index
             plan.supplier[eid] = index
     return plan
+
+
+def sole_consumer_outputs(plan: DataflowPlan, inputs_of: Sequence[Sequence[str]], placement: Sequence[int],
+                          claims_of: Callable[[str], int], excluded: Callable[[str], bool]) -> set:
+    """Result entries of this graph whose frame can be HANDED to their one consumer instead of being copied for it.
+
+    `FileInputBackend.toOutput()` moves a file by ownership (lzy/slots/.../backends/FileInputBackend.java:38-45); an
+    HBM frame may travel the same way along a producer → consumer edge exactly when nobody else can ever ask for it:
+
+    * one op of this graph consumes the entry, on the producer's GPU (`placement`), and no dropped duplicate shares it;
+    * `excluded(eid)` is false — the runtime's veto for cached (`cache=True`) results and fan-out deliveries;
+    * `claims_of(eid)` — the snapshot's pin count: one per queued consumer call and one while the result's lazy proxy
+      is alive — leaves nobody but that consumer: either 1 (the proxy is gone), or 2 with the proxy kept alive by
+      nothing but the consumer call's own argument list (``y = f(y)`` in a loop).  A proxy the caller still holds —
+      in a variable, a list, another object — can be materialized after the graph, so its frame stays in the store and
+      the consumer gets a private copy (snapshot-at-call-time, pylzy/tests/api/v1/test_entries.py:331-384)."""
+    import sys
+
+    from ..api.v1.utils.proxy_adapter import get_proxy_entry_id, is_lzy_proxy
+    consumers: Dict[str, List[int]] = {}
+    for i, ins in enumerate(inputs_of):
+        for eid in ins:
+            consumers.setdefault(eid, []).append(i)
+    shared = {eid for eids in plan.also_supplies.values() for eid in eids}
+    for index, eids in plan.also_supplies.items():
+        if eids:
+            shared.update(plan.calls[index].entry_ids)
+    out = set()
+    for index, call in enumerate(plan.calls):
+        for eid in call.entry_ids:
+            cons = consumers.get(eid, ())
+            if len(cons) != 1 or eid in shared or excluded(eid) or placement[cons[0]] != placement[index]:
+                continue
+            claims = claims_of(eid)
+            if claims == 1:
+                out.add(eid)
+                continue
+            if claims != 2:
+                continue
+            consumer = plan.calls[cons[0]]
+            held = [a for a in (*consumer.args, *consumer.kwargs.values()) if is_lzy_proxy(a) and get_proxy_entry_id(a) == eid]
+            # references to the proxy right now: the consumer's argument tuple (or kwargs dict), `held`, and getrefcount's
+            # own argument.  One more than that is somebody who can still materialize it.
+            if len(held) == 1 and sys.getrefcount(held[0]) == 3:
+                out.add(eid)
+            del held
+    return out

@@ -38,7 +38,6 @@ static_assert(sizeof(lzyb_frame_header_t) == 128, "frame header must be 128 byte
 static_assert(sizeof(lzyb_ipc_desc_t) == 256, "ipc descriptor must be 256 bytes");
 constexpr int CTL_SLAB = 8192;        // slots that can be live per device
 constexpr int MBOX_SLAB = 65536;      // mailboxes (pinned, all devices)
-constexpr uint64_t DMA_MIN_BYTES = 256ull << 20;  // peer pulls at least this long ride the copy engine (auto policy)
 constexpr int GRID_AUTO = -1000;      // lzyb_set_grid: let launch_stream pick the grid shape
 constexpr uint64_t PUSH_MIN_DEFAULT = 4ull << 20;  // in-process GPU→GPU transfers at least this long are pushed from the source GPU (auto policy)
 // TMA ring shapes that can be selected at run time (lzyb_set_tma_config): {stages, stage bytes, CTAs per SM}
@@ -119,6 +118,10 @@ struct DeviceCtx {
     // DMA pull (launch_dma_verify): scans trail the copy engine on their own stream; events are recycled
     cudaStream_t verify_stream = nullptr;
     cudaStream_t push_stream = nullptr;  // this GPU as a SOURCE: push kernels of in-process transfers are issued here
+    // "is this GPU serving a transfer right now?"  sourcing_ev[j] lives on managed device j and is re-recorded on the stream
+    // that carries a transfer OUT of this GPU (its own push stream, or the pulling consumer's stream on device j)
+    std::mutex src_mu;
+    std::vector<cudaEvent_t> sourcing_ev;
     std::mutex dma_mu;  // one copy-engine pull is issued at a time per sink GPU (event ring, verify-stream order)
     std::vector<cudaEvent_t> dma_events;
     size_t dma_ev_next = 0;
@@ -460,6 +463,22 @@ cudaEvent_t add_reader(Slot& s, cudaStream_t st) {
     return ev;
 }
 
+// Bookkeeping for the auto policy: a transfer out of `sd` was just queued on `stream`, a stream of managed device `rec`
+// (current device = that device).
+void mark_sourcing(DeviceCtx& sd, int rec, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lk(sd.src_mu);
+    if (sd.sourcing_ev.size() < g.devs.size()) sd.sourcing_ev.resize(g.devs.size(), nullptr);
+    if (!sd.sourcing_ev[rec]) cudaEventCreateWithFlags(&sd.sourcing_ev[rec], cudaEventDisableTiming);
+    cudaEventRecord(sd.sourcing_ev[rec], stream);
+}
+bool is_sourcing(DeviceCtx& d) {
+    std::lock_guard<std::mutex> lk(d.src_mu);
+    for (cudaEvent_t e : d.sourcing_ev)
+        if (e && cudaEventQuery(e) == cudaErrorNotReady) return true;
+    cudaGetLastError();
+    return false;
+}
+
 // An in-process transfer between two GPUs.  `p` is the chunk as lzyb_transfer_chunk built it (src on the source GPU,
 // dst / header on the sink GPU, ctl on the sink GPU — reached through the peer mapping —, mailbox in pinned host memory);
 // the caller's current device is the sink's.  The kernel runs on the source GPU's push stream; the sink stream `st`
@@ -477,6 +496,7 @@ int launch_push_inproc(DeviceCtx& sd, DeviceCtx& dd, Slot& src, Slot& dst, const
         int rc = launch_stream(sd, p, true, sd.push_stream, true);
         if (rc != LZYB_OK) return rc;
         g.st_push++;
+        mark_sourcing(sd, src.dev, sd.push_stream);
         add_reader(src, sd.push_stream);         // neither frame is recycled under a push that is still running
         done = add_reader(dst, sd.push_stream);
     }
@@ -682,6 +702,8 @@ int lzyb_shutdown(void) {
         for (cudaEvent_t e : d->dma_events) cudaEventDestroy(e);
         cudaStreamDestroy(d->verify_stream);
         cudaStreamDestroy(d->push_stream);
+        for (cudaEvent_t e : d->sourcing_ev)
+            if (e) cudaEventDestroy(e);
         cudaStreamDestroy(d->stream);
     }
     g.devs.clear();
@@ -1114,17 +1136,24 @@ int64_t lzyb_transfer_chunk(lzyb_handle_t dst_h, lzyb_handle_t src_h, uint64_t o
     if (src->last_ev && src->last_stream != st) cudaStreamWaitEvent(st, src->last_ev, 0);
     const bool peer = src->remote || src->dev != dst->dev;
     const int engine = g.engine.load();
-    // auto: an in-process transfer between two GPUs is PUSHED — the streaming kernel runs on the source GPU and stores
-    // through the peer mapping (push_kernels.cuh: posted writes keep 700 GB/s per direction where pulls drop to 671 once
-    // both directions are busy).  A source mapped from another process can only be pulled from here (its owner pushes
-    // through lzyb_slot_push): the TMA ring below 256 MiB, the copy engine + trailing scans above.
-    const bool push = peer && !src->remote && !dst->remote && (engine == 4 || (engine == 0 && len >= g.push_min.load()));
-    const bool dma = !push && peer && (engine == 3 || (engine == 0 && len >= DMA_MIN_BYTES));
+    // Who runs the kernel (measured, push_kernels.cuh): with ONE direction of a GPU pair busy a consumer pull is the
+    // fastest SM carrier (770–780 GB/s: read responses cost 1.125 wire bytes per payload byte), but once the sink GPU is
+    // itself serving a transfer the pull's requests share the wire with that payload (657–671 per direction) and a
+    // producer push — posted writes, 1.19 wire bytes, nothing on the reverse wire — keeps 684–700.  auto therefore pushes
+    // exactly when the sink GPU is sourcing a transfer right now (a ring, a bidirectional exchange) and pulls otherwise;
+    // short transfers always pull (one launch on one GPU, no cross-device hand-shake).  A source mapped from another
+    // process can only be pulled from here (its owner pushes through lzyb_slot_push).  The copy engine (3) is a named
+    // alternative, never auto's choice: it holds 716–737 GB/s with larger packets than an SM can issue.
+    const bool in_process_peer = peer && !src->remote && !dst->remote;
+    const bool push = in_process_peer && (engine == 4 || (engine == 0 && len >= g.push_min.load() && is_sourcing(d)));
+    const bool dma = !push && peer && engine == 3;
     int rc;
-    if (push)
+    if (push) {
         rc = launch_push_inproc(*g.devs[src->dev], d, *src, *dst, p, st);
-    else
+    } else {
         rc = dma ? launch_dma_verify(d, p, st) : launch_stream(d, p, true, st, peer);
+        if (rc == LZYB_OK && in_process_peer) mark_sourcing(*g.devs[src->dev], dst->dev, st);
+    }
     if (rc != LZYB_OK) return rc;
     g.st_pull++;
     if (src->dev == dst->dev && !src->remote)
@@ -1196,11 +1225,18 @@ static int finish_common(Slot& dst, const uint64_t expect[2], const Slot* src, v
     }
     int st = harvest(dst);
     if (st < 0) return st;
-    if (st == 1 && expect && (dst.digest[0] != expect[0] || dst.digest[1] != expect[1])) st = 2;  // verdict of another frame
-    if (st == 2) {
+    if (st == 3) {
         input_reset_locked(dst);
-        return fail(LZYB_E_PEER, "digest mismatch on slot %s: delivered bytes differ from what the producer committed",
-                    dst.id.c_str());
+        return fail(LZYB_E_PEER, "slot %s: the producer's push did not arrive within the sink's timeout", dst.id.c_str());
+    }
+    const bool foreign = st == 1 && expect && (dst.digest[0] != expect[0] || dst.digest[1] != expect[1]);  // the verdict of another frame
+    if (st == 2 || foreign) {
+        const unsigned long long g0 = dst.digest[0], g1 = dst.digest[1];
+        input_reset_locked(dst);
+        return fail(LZYB_E_PEER, "digest mismatch on slot %s: delivered bytes differ from what the producer committed "
+                                 "(%s; delivered %016llx%016llx, expected %016llx%016llx)", dst.id.c_str(),
+                    foreign ? "verified, but against another digest" : "verdict of the digesting kernel", g0, g1,
+                    expect ? (unsigned long long)expect[0] : 0ull, expect ? (unsigned long long)expect[1] : 0ull);
     }
     dst.state = LZYB_ST_READY;
     return LZYB_OK;

@@ -39,7 +39,7 @@ struct Mailbox {
     volatile unsigned long long digest[2];
     volatile unsigned long long sum;
     volatile unsigned long long xr;
-    volatile unsigned int status;    // 0 = pending, 1 = ok, 2 = digest mismatch
+    volatile unsigned int status;    // 0 = pending, 1 = ok, 2 = digest mismatch, 3 = an awaited push never arrived
     volatile unsigned int seq;       // launch sequence number echoed back
     unsigned long long pad[3];
 };

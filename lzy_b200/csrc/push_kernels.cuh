@@ -82,7 +82,7 @@ __global__ void arrival_wait_kernel(const __grid_constant__ ArrivalWait a) {
     a.mbox->xr = xr;
     a.mbox->seq = a.mbox_seq;
     __threadfence_system();
-    a.mbox->status = verdict == 1ull ? 1u : 2u;
+    a.mbox->status = !arrived ? 3u : (verdict == 1ull ? 1u : 2u);  // 3 = the producer's push never arrived
 }
 
 }  // namespace lzyb

@@ -157,13 +157,14 @@ def test_push_catches_a_corrupted_source_and_the_sink_refetches(native_all):
     bad = N.SlotHandle.create_output("pushc/bad", 0, n)
     good = N.SlotHandle.create_output("pushc/good", 0, n)
     inp = N.SlotHandle.open_input("pushc/in", 1, n)
+    N.set_copy_engine(N.ENGINE_PUSH)
     try:
         for s in (bad, good):
             s.pack(t.data_ptr(), n)
             s.commit()
         bad.fault(N.FAULT_CORRUPT_ONCE, (9 << 20) + 3)
         before = N.stats()["push_launches"]
-        assert inp.transfer_chunk(bad, 0, 1 << 40) == n      # auto: ≥ 4 MiB between GPUs of one process = push
+        assert inp.transfer_chunk(bad, 0, 1 << 40) == n
         assert N.stats()["push_launches"] - before == 1
         with pytest.raises(N.ReadException):
             inp.finish(bad)
@@ -173,13 +174,15 @@ def test_push_catches_a_corrupted_source_and_the_sink_refetches(native_all):
         assert tuple(inp.info().digest) == oracle.digest(a)
         assert np.array_equal(to_host(inp), a)
     finally:
+        N.set_copy_engine(N.ENGINE_AUTO)
         for s in (bad, good, inp):
             s.close()
 
 
 def test_both_directions_at_once_are_bit_exact(native_all):
     """the ring's situation: GPU 0 → GPU 1 and GPU 1 → GPU 0 in flight together on their own streams, each GPU pushing
-    and being pushed into at the same time"""
+    and being pushed into at the same time.  Under the auto policy the first transfer finds its sink GPU idle and is
+    pulled; the second finds its sink GPU serving the first and is pushed."""
     n = (192 << 20) + 64
     ts, outs, inps, streams = [], [], [], []
     for g in (0, 1):
@@ -195,6 +198,9 @@ def test_both_directions_at_once_are_bit_exact(native_all):
     try:
         for g in (0, 1):
             inps.append(N.SlotHandle.open_input(f"bidir/in{g}", g, n))
+        for g in (0, 1):
+            torch.cuda.synchronize(g)
+        before = N.stats()
         for g in (0, 1):  # queue both before waiting for either
             assert inps[g].transfer_chunk(outs[1 - g], 0, n, int(streams[g].cuda_stream)) == n
         for g in (0, 1):
@@ -202,6 +208,9 @@ def test_both_directions_at_once_are_bit_exact(native_all):
             assert tuple(inps[g].info().digest) == tuple(outs[1 - g].info().digest) == oracle.digest(oracle.pattern(n, 31 + 1 - g))
             from lzy_b200.devmem import view_bytes
             assert torch.equal(view_bytes(inps[g].device_ptr(), n, g).to(f"cuda:{1 - g}"), ts[1 - g])
+        after = N.stats()
+        assert after["push_launches"] - before["push_launches"] == 1 and after["dma_copies"] == before["dma_copies"]
+        assert after["bytes_pulled_peer"] - before["bytes_pulled_peer"] == 2 * n
     finally:
         for s in outs + inps:
             s.close()
@@ -259,10 +268,10 @@ def test_chain_round_robin_over_gpus(lzy):
     assert len(set(seen)) == min(NGPU, 8) and N.stats()["bytes_pulled_peer"] - before >= 6 * x.numel() * 4
 
 
-def test_long_edges_through_the_runtime_ride_the_push_kernel(lzy):
-    """a 256 MiB edge between ops on different GPUs takes the auto policy's carrier inside the slots runtime's download
-    loop (not only when lzyb_transfer_chunk is called by hand): the push kernel on the producer's GPU with the landed
-    scan on the consumer's — no copy engine — and stays bit-exact"""
+def test_long_edges_through_the_runtime_ride_sm_kernels_only(lzy):
+    """a 256 MiB edge between ops on different GPUs is carried by the hand-written kernels inside the slots runtime's
+    download loop (not only when lzyb_transfer_chunk is called by hand) — pull or push as the auto policy decides, never the
+    copy engine — and stays bit-exact"""
     @op
     def hop(t: torch.Tensor) -> torch.Tensor:
         return t
@@ -274,7 +283,7 @@ def test_long_edges_through_the_runtime_ride_the_push_kernel(lzy):
         y = hop(hop(x))
     assert torch.equal(y.to("cuda:0"), keep)
     after = N.stats()
-    assert after["push_launches"] - before["push_launches"] >= 1  # at least one cross-GPU edge
+    assert after["bytes_pulled_peer"] - before["bytes_pulled_peer"] >= x.numel() * 4  # at least one cross-GPU edge
     assert after["dma_copies"] == before["dma_copies"]
 
 
