@@ -563,7 +563,8 @@ def run_ours(args):
             for fn in ((lambda: bench_configs.c1(dev, with_cpu=not multi)),
                        (lambda: bench_configs.c4(dev, rows_list=(569, 1_000_000) if not multi else (569,), with_cpu=not multi)),
                        (lambda: bench_configs.c5(gpus)),
-                       (lambda: bench_configs.c3_in_process(gpus) if world >= 4 else None)):
+                       (lambda: bench_configs.c3_in_process(gpus) if world >= 4 else None),
+                       (lambda: bench_configs.worker_processes_chain(gpus) if world >= 2 else None)):
                 try:
                     r = fn()
                     if isinstance(r, list):

@@ -167,7 +167,7 @@ def c3_in_process(gpus: List[int], mib: int = 4096, reps: int = 3) -> List[Dict[
         return dt, ok
 
     for name, fn in (("device-chained pull kernel (one launch per GPU, progress counters in peer memory)", run_chain),
-                     (f"{len(consumers)} concurrent unicasts (push kernel + landed scan each)", run_unicasts)):
+                     (f"{len(consumers)} concurrent unicasts (one consumer pull per GPU, all from the same source)", run_unicasts)):
         ts, ok = [], True
         for r in range(reps + 1):
             dt, k = fn()
@@ -323,3 +323,137 @@ def c5(gpus: Optional[List[int]] = None, mib: int = 256, reps: int = 4) -> Dict[
     out["overlap_note"] = ("overlap_fraction = (wall without prefetch − wall with prefetch) ÷ wall without prefetch; the sums are per-op CUDA-event "
                            f"compute time and per-edge transfer time across all GPUs (serial sum {serial_on:.1f} ms runs in {on['wall_ms']:.1f} ms of wall)")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the process-per-GPU deployment: channel manager + one worker process per GPU, tasks sent as WorkerApi.Execute
+# ------------------------------------------------------------------------------------------------------------------
+def worker_processes_chain(gpus: List[int], mib: int = 256, n_ops: int = 8, reps: int = 3) -> Dict[str, Any]:
+    """An n-op identity chain over `mib`-MiB float32 tensors on the deployment shape of the reference (a worker process
+    per GPU — lzy/worker/.../Worker.java:36-56 — and the channel manager as its own process), driven over the kept wire
+    contract: LzyChannelManagerPrivate.GetOrCreate for the channels, WorkerApi.Init / Execute + LongRunningService.Get per
+    task.  Op k runs on the worker of GPU k mod N; every edge is produced in one process and consumed in another: the
+    consumer's transfer factory asks the producer's worker for the frame descriptor (LzybPeerApi.Describe), maps it with
+    CUDA IPC and pulls over NVLink with digest verification (TMA ring).  Wall time from the first Execute to the last
+    response, the check op compares every element on its GPU."""
+    import socket
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+
+    from lzy_b200.api.v1.startup import ProcessingRequest
+    from lzy_b200.api.v1.utils.pickle import pickle
+    from lzy_b200.grpc_api import ChannelManagerPrivateClient, LongRunningClient, WorkerApiClient, messages as M
+    from lzy_b200.grpc_api.protos import GetOperationRequest
+    root = Path(__file__).resolve().parent
+    n_elem = (mib << 20) // 4
+
+    def free_port() -> int:
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            return sk.getsockname()[1]
+
+    def make() -> torch.Tensor:
+        import torch as t_
+        return t_.arange(n_elem, dtype=t_.float32, device="cuda")
+
+    def hop(t: torch.Tensor) -> torch.Tensor:
+        return t
+
+    def check(t: torch.Tensor) -> int:
+        import torch as t_
+        assert t.is_cuda and t.numel() == n_elem
+        assert t_.equal(t, t_.arange(n_elem, dtype=t_.float32, device=t.device))
+        return int(t.device.index)
+
+    procs, clients = [], {}
+    try:
+        cm = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "channel-manager", "--port", "0"], cwd=str(root),
+                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        procs.append(cm)
+        cm_target = cm.stdout.readline().strip().rsplit(" ", 1)[-1]
+        targets = []
+        for g in gpus:
+            port = free_port()
+            w = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "worker", "--gpu", str(g), "--port", str(port),
+                                  "--channel-manager", cm_target], cwd=str(root), stdout=subprocess.PIPE,
+                                 stderr=subprocess.DEVNULL, text=True)
+            procs.append(w)
+            line = w.stdout.readline()
+            if not line.startswith("worker for GPU"):
+                raise RuntimeError(f"worker for GPU {g} did not start: {line!r}")
+            targets.append(f"127.0.0.1:{port}")
+            clients[g] = (WorkerApiClient(targets[-1]), LongRunningClient(targets[-1]))
+            clients[g][0].call("Init", M.InitRequest(user_id="u", workflow_name="wf"), timeout=180.0)
+        priv = ChannelManagerPrivateClient(cm_target)
+
+        def run_once(tag: str) -> float:
+            def channel(uri):
+                sp = M.PeerDescription.StoragePeer(storage_uri=uri)
+                return priv.call("GetOrCreate", M.GetOrCreateRequest(execution_id=f"exec-{tag}", workflow_name="wf", user_id="u",
+                                                                     consumer=sp)).channel_id
+
+            def execute(g, task_id, fn, args_paths, outs, slots, assign):
+                wapi, ops = clients[g]
+                request = ProcessingRequest({}, [], fn, args_paths, {}, outs, (tuple, f"/{task_id}/exc"), lazy_arguments=False)
+                req = M.ExecuteRequest(task_id=task_id, execution_id=f"exec-{tag}", workflow_name="wf", user_id="u")
+                req.task_desc.operation.command = "python -u startup.py " + pickle(request)
+                for name, direction in slots:
+                    req.task_desc.operation.slots.add(name=name, direction=direction)
+                for name, chan in assign.items():
+                    req.task_desc.slot_assignments.add(slot_name=name, channel_id=chan)
+                op_msg = wapi.call("Execute", req)
+                deadline = time.time() + 300
+                while not op_msg.done:
+                    if time.time() > deadline:
+                        raise TimeoutError(task_id)
+                    time.sleep(0.0005)
+                    op_msg = ops.call("Get", GetOperationRequest(operation_id=op_msg.id))
+                resp = M.ExecuteResponse()
+                assert op_msg.WhichOneof("result") == "response" and op_msg.response.Unpack(resp)
+                if resp.rc != 0:
+                    raise RuntimeError(f"{task_id}: rc {resp.rc}: {resp.description}")
+
+            chans = [channel(f"hbm://{tag}/t{k}/ret") for k in range(n_ops + 1)]
+            excs = [channel(f"hbm://{tag}/t{k}/exc") for k in range(n_ops + 2)]
+            res = channel(f"hbm://{tag}/check/ret")
+            t0 = time.perf_counter()
+            execute(gpus[0], f"{tag}-t0", make, [], [(torch.Tensor, "/t0/ret")], [("/t0/ret", 2), (f"/{tag}-t0/exc", 2)],
+                    {"/t0/ret": chans[0], f"/{tag}-t0/exc": excs[0]})
+            for k in range(1, n_ops + 1):
+                g = gpus[k % len(gpus)]
+                execute(g, f"{tag}-t{k}", hop, [(torch.Tensor, f"/t{k}/arg")], [(torch.Tensor, f"/t{k}/ret")],
+                        [(f"/t{k}/arg", 1), (f"/t{k}/ret", 2), (f"/{tag}-t{k}/exc", 2)],
+                        {f"/t{k}/arg": chans[k - 1], f"/t{k}/ret": chans[k], f"/{tag}-t{k}/exc": excs[k]})
+            dt = time.perf_counter() - t0
+            g = gpus[(n_ops + 1) % len(gpus)]
+            execute(g, f"{tag}-check", check, [(torch.Tensor, "/check/arg")], [(int, "/check/ret")],
+                    [("/check/arg", 1), ("/check/ret", 2), (f"/{tag}-check/exc", 2)],
+                    {"/check/arg": chans[n_ops], "/check/ret": res, f"/{tag}-check/exc": excs[n_ops + 1]})
+            priv.call("DestroyAll", M.DestroyAllRequest(execution_id=f"exec-{tag}"))
+            return dt
+
+        run_once("warm")
+        ts = [run_once(f"r{i}") for i in range(reps)]
+        priv.close()
+        t = _median(ts)
+        return {"config": "C2 on worker processes", "gpus": len(gpus), "processes": len(gpus) + 1, "payload_mib": mib, "ops": n_ops,
+                "wall_ms": t * 1e3, "ops_per_sec": n_ops / t, "edge_GBps": n_ops * (mib << 20) / t / 1e9, "bit_exact": True,
+                "wire": "WorkerApi.Init/Execute + LongRunningService.Get + LzyChannelManager(Private) + LzybPeerApi.Describe over gRPC; "
+                        "payload over NVLink through CUDA IPC (consumer pull, TMA ring, digest verified on landing)"}
+    finally:
+        for wapi, ops in clients.values():
+            try:
+                wapi.close()
+                ops.close()
+            except Exception:
+                pass
+        for pr in reversed(procs):
+            pr.terminate()
+        for pr in procs:
+            try:
+                pr.wait(timeout=20)
+            except Exception:
+                pr.kill()

@@ -406,7 +406,29 @@ class B200Runtime(Runtime):
             running: Dict[Any, int] = {}
             failure: Optional[_OpFailed] = None
             while True:
-                for t in graph.next():
+                ready = list(graph.next())
+                while len(ready) == 1 and not running and failure is None:
+                    # a chain: nothing to run next to this op, so it runs right here — no pool hand-off, no future,
+                    # no wake-up (≈ 0.1 ms per op that the data plane does not have to give)
+                    t = ready[0]
+                    try:
+                        self._run_task(t, calls[t], ctxs[t], placement[t], inputs_of[t], fanout)
+                    except _OpFailed as err:
+                        graph.task_done(t, False, repr(err))
+                        failure = err
+                        ready = []
+                        break
+                    graph.task_done(t, True)
+                    for eid in plan.outputs_of(t):
+                        f = fanout.get(eid)
+                        if f is not None and not f.started:
+                            f.started = True
+                            self._pool.submit(self._do_fanout, f)
+                    ready = list(graph.next())
+                if failure is not None:
+                    graph.stop("op failed")
+                    break
+                for t in ready:
                     running[self._pool.submit(self._run_task, t, calls[t], ctxs[t], placement[t], inputs_of[t], fanout)] = t
                 if not running:
                     break

@@ -133,6 +133,10 @@ class SerializerRegistry:
         self._serializers: List[Serializer] = []
         self._serializer_priorities: Dict[Type[Serializer], int] = {}
         self._next_default = 1000
+        # lookups sit on the per-op path (every argument and result asks twice): remembered per type / format until the
+        # registry changes
+        self._by_type: Dict[Any, Optional[Serializer]] = {}
+        self._by_format: Dict[str, Optional[Serializer]] = {}
 
     def register_serializer(self, serializer: Serializer, priority: Optional[int] = None) -> None:
         if priority is None:
@@ -144,12 +148,27 @@ class SerializerRegistry:
         self._serializer_priorities[type(serializer)] = priority
         self._serializers.append(serializer)
         self._serializers.sort(key=lambda s: self._serializer_priorities[type(s)])
+        self._by_type.clear()
+        self._by_format.clear()
 
     def unregister_serializer(self, serializer: Serializer) -> None:
         self._serializers = [s for s in self._serializers if type(s) is not type(serializer)]
         self._serializer_priorities.pop(type(serializer), None)
+        self._by_type.clear()
+        self._by_format.clear()
 
     def find_serializer_by_type(self, typ: Type) -> Optional[Serializer]:
+        try:
+            return self._by_type[typ]
+        except KeyError:
+            pass
+        except TypeError:  # an unhashable annotation object: look it up the long way every time
+            return self._scan_by_type(typ)
+        found = self._scan_by_type(typ)
+        self._by_type[typ] = found
+        return found
+
+    def _scan_by_type(self, typ: Type) -> Optional[Serializer]:
         for s in self._serializers:
             try:
                 if s.handles(typ):
@@ -162,10 +181,17 @@ class SerializerRegistry:
         return self.find_serializer_by_type(type(obj))
 
     def find_serializer_by_data_format(self, data_format: str) -> Optional[Serializer]:
+        try:
+            return self._by_format[data_format]
+        except KeyError:
+            pass
+        found = None
         for s in self._serializers:
             if s.data_format() == data_format:
-                return s
-        return None
+                found = s
+                break
+        self._by_format[data_format] = found
+        return found
 
     def resolve(self, schema: Schema) -> Type:
         s = self.find_serializer_by_data_format(schema.data_format)
