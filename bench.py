@@ -611,7 +611,8 @@ def api_bench(dev0: int, gpus, payload: int, shape, steps: int):
     one chain per GPU (chain j enters on GPU j, op k runs on GPU (j + k) mod N), so every GPU hosts 8 ops per step
     and, for N > 1, every edge crosses NVLink.
     device: the x_j are CUDA tensors already, results stay on the device.
-    e2e:    the x_j sit in pinned host memory; each step does x_j.to(cuda:j) (H2D), the chains, y_j → pinned host (D2H)."""
+    e2e:    the x_j sit in pinned host memory; each step copies them into the caller's device tensors (H2D), runs the
+            chains and copies every y_j into pinned host memory (D2H)."""
     import numpy as np
     import torch
 
@@ -635,10 +636,11 @@ def api_bench(dev0: int, gpus, payload: int, shape, steps: int):
     rt = B200Runtime(gpus=list(gpus), placement="single" if n == 1 else "round_robin")
     lzy = Lzy(runtime=rt)
     streams = [torch.cuda.current_stream(g) if g == dev0 else torch.cuda.Stream(g) for g in gpus]
-    xs, host_in, host_out = [], [], []
+    xs, host_in, host_out, dev_in = [], [], [], []
     for j, g in enumerate(gpus):
         x = torch.empty(shape, dtype=torch.float32, device=f"cuda:{g}").normal_()
         xs.append(x)
+        dev_in.append(torch.empty_like(x))  # the caller's own staging tensor for the H2D copy (no allocation per step)
         host_in.append(torch.empty(shape, dtype=torch.float32, pin_memory=True).copy_(x))
         host_out.append(torch.empty(shape, dtype=torch.float32, pin_memory=True))
     d2h_streams = [torch.cuda.Stream(g) for g in gpus]
@@ -671,7 +673,7 @@ def api_bench(dev0: int, gpus, payload: int, shape, steps: int):
                 inputs = []
                 for j, g in enumerate(gpus):
                     with torch.cuda.stream(streams[j]):
-                        inputs.append(host_in[j].to(f"cuda:{g}", non_blocking=True))
+                        inputs.append(dev_in[j].copy_(host_in[j], non_blocking=True))
                 if collect:
                     sync_all()
                 p1 = time.perf_counter()

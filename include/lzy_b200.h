@@ -319,9 +319,10 @@ int lzyb_dma_schedule(uint64_t nbytes, uint64_t* sizes_out, int cap);
  * -1000 = auto (default) */
 int lzyb_set_grid(int ctas_per_sm);
 /* shape of the TMA shared-memory ring, for measurement: 0 = 6×16 KiB ×2 CTAs/SM, 1 = 3×32 KiB ×2 (default),
- * 2 = 6×32 KiB ×1, 3 = 12×16 KiB ×1, 4 = 8×8 KiB ×3, 5 = 4×16 KiB ×3 */
+ * 2 = 6×32 KiB ×1, 3 = 12×16 KiB ×1, 4 = 8×8 KiB ×3, 5 = 4×16 KiB ×3, 6 = 2×8 KiB ×1 (stress shape: the shallowest ring) */
 int lzyb_set_tma_config(int index);
-/* measurement only.  bit 0: run the TMA ring without the digest arithmetic (digests are then wrong) */
+/* measurement / stress only.  bit 0: run the TMA ring without the digest arithmetic (digests are then wrong);
+ * bit 1: launch the TMA ring with 4 CTAs, so every CTA recycles its stages thousands of times */
 int lzyb_set_debug_flags(int flags);
 
 /* fault injection at the backend seam (the reference's InMemBackend failOpen/failRead/failAfter,

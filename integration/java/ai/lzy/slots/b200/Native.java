@@ -64,6 +64,17 @@ public final class Native {
 
     public static native long peerImport(byte[] descriptor, int ontoGpu);
 
+    // producer-issued push between worker processes (include/lzy_b200.h: lzyb_sink_export / lzyb_slot_push /
+    // lzyb_input_expect_push): the consumer describes its empty input frame, the producer's process pushes into it
+    public static native byte[] sinkExport(long inputHandle);
+
+    public static native int slotPush(long srcHandle, byte[] sinkDescriptor);
+
+    public static native long inputExpectPush(long dst, byte[] producerDescriptor);
+
+    // the channel has exactly one consumer and no other reader: a same-GPU consumer takes the frame over (toOutput-style)
+    public static native int slotSetMovable(long handle, boolean movable);
+
     static long check(long rc) throws java.io.IOException {
         if (rc < 0 && rc != EOF) {
             throw new java.io.IOException("lzy_b200: " + lastError() + " (code " + rc + ")");

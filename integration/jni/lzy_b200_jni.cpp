@@ -188,4 +188,37 @@ JNIEXPORT jlong JNICALL Java_ai_lzy_slots_b200_Native_peerImport(JNIEnv* env, jc
     return handle_or_error(lzyb_peer_import(&desc, ontoGpu, &h), h);
 }
 
+// ---- producer-issued push between worker processes ------------------------------------------------------------------
+JNIEXPORT jbyteArray JNICALL Java_ai_lzy_slots_b200_Native_sinkExport(JNIEnv* env, jclass, jlong inputHandle) {
+    lzyb_ipc_desc_t desc;
+    if (lzyb_sink_export(static_cast<lzyb_handle_t>(inputHandle), &desc) != LZYB_OK) return nullptr;
+    jbyteArray out = env->NewByteArray(static_cast<jsize>(sizeof(desc)));
+    if (out) env->SetByteArrayRegion(out, 0, static_cast<jsize>(sizeof(desc)), reinterpret_cast<const jbyte*>(&desc));
+    return out;
+}
+
+JNIEXPORT jint JNICALL Java_ai_lzy_slots_b200_Native_slotPush(JNIEnv* env, jclass, jlong srcHandle, jbyteArray sinkBytes) {
+    lzyb_ipc_desc_t sink;
+    if (!sinkBytes || env->GetArrayLength(sinkBytes) != static_cast<jsize>(sizeof(sink))) {
+        lzyb_set_last_error("sink descriptor must be 256 bytes");
+        return LZYB_E_ARG;
+    }
+    env->GetByteArrayRegion(sinkBytes, 0, static_cast<jsize>(sizeof(sink)), reinterpret_cast<jbyte*>(&sink));
+    return lzyb_slot_push(static_cast<lzyb_handle_t>(srcHandle), &sink, 0, 0, nullptr);
+}
+
+JNIEXPORT jlong JNICALL Java_ai_lzy_slots_b200_Native_inputExpectPush(JNIEnv* env, jclass, jlong dst, jbyteArray producerBytes) {
+    lzyb_ipc_desc_t producer;
+    if (!producerBytes || env->GetArrayLength(producerBytes) != static_cast<jsize>(sizeof(producer))) {
+        lzyb_set_last_error("producer descriptor must be 256 bytes");
+        return LZYB_E_ARG;
+    }
+    env->GetByteArrayRegion(producerBytes, 0, static_cast<jsize>(sizeof(producer)), reinterpret_cast<jbyte*>(&producer));
+    return static_cast<jlong>(lzyb_input_expect_push(static_cast<lzyb_handle_t>(dst), &producer, 0, 0, nullptr));
+}
+
+JNIEXPORT jint JNICALL Java_ai_lzy_slots_b200_Native_slotSetMovable(JNIEnv*, jclass, jlong handle, jboolean movable) {
+    return lzyb_slot_set_movable(static_cast<lzyb_handle_t>(handle), movable ? 1 : 0);
+}
+
 }  // extern "C"

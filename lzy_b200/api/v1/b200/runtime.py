@@ -136,6 +136,10 @@ class _OpFailed(Exception):
 
 
 class B200Runtime(Runtime):
+    # start / exec / finish / abort never suspend when nobody runs a loop for them: LzyEventLoop drives them on the caller's
+    # thread (exec then runs the graph right there instead of parking it on an executor)
+    inline_coroutines = True
+
     def __init__(self, config: Optional[B200RuntimeConfig] = None, **kwargs):
         self.config = config or B200RuntimeConfig.from_env(**kwargs)
         # started workflows, innermost last: an op body may open a workflow of its own on this very runtime while
@@ -250,9 +254,15 @@ class B200Runtime(Runtime):
             if not self._active:
                 raise ValueError("Runtime is not running")
         progress(ProgressStep.EXECUTING)
-        loop = asyncio.get_running_loop()
         try:
-            await loop.run_in_executor(None, self._exec_graph, list(calls))
+            loop = asyncio.get_running_loop()
+        except RuntimeError:
+            loop = None  # driven inline by LzyEventLoop.run_async on the caller's thread
+        try:
+            if loop is None:
+                self._exec_graph(list(calls))
+            else:
+                await loop.run_in_executor(None, self._exec_graph, list(calls))
         except BaseException:
             progress(ProgressStep.FAILED)
             raise
@@ -380,7 +390,8 @@ class B200Runtime(Runtime):
                     fanout[eid] = _Fanout(eid, uri, src_gpu, remote)
         # outputs that travel by ownership hand-over: one consumer on the producer's GPU and nobody else who could ask
         sole: set = set()
-        if self.config.move_sole_consumer and not self.config.republish_inputs and hasattr(snapshot, "claims"):
+        if self.config.move_sole_consumer and self.config.retain == "auto" and not self.config.republish_inputs and \
+                hasattr(snapshot, "claims"):
             sole = sole_consumer_outputs(plan, inputs_of, placement, snapshot.claims,
                                          lambda eid: eid in fanout or snapshot.is_persistent(eid))
             self.stats["moved_outputs"] = self.stats.get("moved_outputs", 0) + len(sole)

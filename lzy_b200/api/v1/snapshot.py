@@ -84,6 +84,9 @@ class Snapshot(ABC):
 
 
 class FrameSnapshot(Snapshot):
+    # every coroutine below is a synchronous call into the frame store: LzyEventLoop may drive them on the caller's thread
+    inline_coroutines = True
+
     def __init__(self, serializer_registry: SerializerRegistry, storage_uri: str, store: "FrameStore",
                  storage_name: str = "hbm"):
         self._registry = serializer_registry

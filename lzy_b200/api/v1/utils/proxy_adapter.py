@@ -61,7 +61,8 @@ class EntryOrigin:
         raise RuntimeError(f"Cannot materialize data with entry id {self.entry_id} from workflow {self.workflow.name}")
 
     def __call__(self) -> Any:
-        return LzyEventLoop.run_async(self.fetch())
+        inline = getattr(self.workflow, "_inline", None)  # (test doubles stand in for workflows: no such method, no fast path)
+        return LzyEventLoop.run_async(self.fetch(), inline=bool(inline()) if callable(inline) else False)
 
 
 def lzy_proxy(entry_id: str, types: Sequence[Type], wflow: "LzyWorkflow", value: Either = Absence()) -> Any:

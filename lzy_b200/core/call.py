@@ -66,7 +66,7 @@ class LzyCall:
                                            for i, typ in enumerate(func.output_types)]
         self._exception_entry: str = snapshot.create_entry(f"{label}.exception", tuple).id
         if uploads:  # (a call whose arguments are all proxies needs no trip to the workflow thread)
-            LzyEventLoop.gather(*uploads)
+            LzyEventLoop.gather(*uploads, inline=bool(getattr(snapshot, "inline_coroutines", False)))
 
         pin = getattr(snapshot, "pin", None)
         if pin is not None:

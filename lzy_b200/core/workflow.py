@@ -115,8 +115,13 @@ class LzyWorkflow(WithEnvironmentMixin):
         if self.eager:
             self.barrier()
 
+    def _inline(self) -> bool:
+        """may the runtime's and the snapshot's coroutines be driven on the caller's thread? (LzyEventLoop.run_async)"""
+        return bool(getattr(self.owner.runtime, "inline_coroutines", False)) and \
+            (self._snapshot is None or bool(getattr(self._snapshot, "inline_coroutines", False)))
+
     def barrier(self) -> None:
-        LzyEventLoop.run_async(self._barrier())
+        LzyEventLoop.run_async(self._barrier(), inline=self._inline())
 
     async def _barrier(self) -> None:
         if not self._queue:
@@ -136,7 +141,7 @@ class LzyWorkflow(WithEnvironmentMixin):
             if self.get_active() is not None:
                 raise RuntimeError("Simultaneous workflows are not supported")
             self._start_attempted = True
-            self._execution = LzyEventLoop.run_async(self.owner.runtime.start(self))
+            self._execution = LzyEventLoop.run_async(self.owner.runtime.start(self), inline=self._inline())
             self._running = True
             self._mark_active(True)
             where = [self.owner.storage_uri] + ([] if self._user is None else [self._user])
@@ -174,9 +179,9 @@ class LzyWorkflow(WithEnvironmentMixin):
         by_workflow = getattr(runtime, "abort_workflow" if aborting else "finish_workflow", None)
         try:
             if by_workflow is not None:
-                LzyEventLoop.run_async(by_workflow(self))
+                LzyEventLoop.run_async(by_workflow(self), inline=self._inline())
             else:
-                LzyEventLoop.run_async(runtime.abort() if aborting else runtime.finish())
+                LzyEventLoop.run_async(runtime.abort() if aborting else runtime.finish(), inline=self._inline())
         finally:
             if started:
                 self._mark_active(False)

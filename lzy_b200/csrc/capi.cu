@@ -44,7 +44,8 @@ constexpr uint64_t PUSH_MIN_DEFAULT = 4ull << 20;  // in-process GPU→GPU trans
 struct TmaCfg {
     int stages, stage_bytes, ctas_per_sm;
 };
-constexpr TmaCfg kTmaCfgs[] = {{6, 16384, 2}, {3, 32768, 2}, {6, 32768, 1}, {12, 16384, 1}, {8, 8192, 3}, {4, 16384, 3}};
+constexpr TmaCfg kTmaCfgs[] = {{6, 16384, 2}, {3, 32768, 2}, {6, 32768, 1}, {12, 16384, 1}, {8, 8192, 3}, {4, 16384, 3},
+                              {2, 8192, 1}};  // the last one is the stress shape: the shallowest ring, every stage recycled at once
 constexpr int kNumTmaCfgs = sizeof(kTmaCfgs) / sizeof(kTmaCfgs[0]);
 constexpr size_t tma_smem(int stages, int stage_bytes) { return static_cast<size_t>(stages) * stage_bytes + 2 * stages * sizeof(uint64_t); }
 
@@ -334,6 +335,7 @@ int launch_stream(DeviceCtx& d, const CopyParams& p, bool store, cudaStream_t st
         const TmaCfg cfg = kTmaCfgs[ci];
         uint64_t tiles = p.nbytes / cfg.stage_bytes;
         int grid = d.sm_count * cfg.ctas_per_sm;
+        if (g_debug_flags.load() & 2) grid = 4;  // stress: few CTAs, each cycling its ring thousands of times
         if ((uint64_t)grid > tiles) grid = (int)(tiles ? tiles : 1);
         switch (ci) {
             case 0: launch_tma<6, 16384>(p, store, grid, st, d.tma_attr[0]); break;
@@ -341,7 +343,8 @@ int launch_stream(DeviceCtx& d, const CopyParams& p, bool store, cudaStream_t st
             case 2: launch_tma<6, 32768>(p, store, grid, st, d.tma_attr[2]); break;
             case 3: launch_tma<12, 16384>(p, store, grid, st, d.tma_attr[3]); break;
             case 4: launch_tma<8, 8192>(p, store, grid, st, d.tma_attr[4]); break;
-            default: launch_tma<4, 16384>(p, store, grid, st, d.tma_attr[5]); break;
+            case 5: launch_tma<4, 16384>(p, store, grid, st, d.tma_attr[5]); break;
+            default: launch_tma<2, 8192>(p, store, grid, st, d.tma_attr[6]); break;
         }
     } else {
         const uint64_t tile = 256ull * 8;

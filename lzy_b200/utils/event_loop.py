@@ -25,10 +25,14 @@ def _capture_streams() -> Optional[Dict[int, Any]]:
     return {d: torch.cuda.current_stream(d) for d in range(torch.cuda.device_count())}
 
 
+_INLINE = object()  # _CALLER_STREAMS while a coroutine is driven on its caller's own thread: "current" already is the caller's
+
+
 def caller_stream(gpu: int) -> Optional[Any]:
-    """the stream that was current on `gpu` in the thread that called run_async (None outside such a call)"""
+    """the stream that was current on `gpu` in the thread that called run_async (None outside such a call, and None
+    when the coroutine runs on the caller's thread itself: its current stream is the answer)"""
     streams = _CALLER_STREAMS.get()
-    return None if streams is None else streams.get(gpu)
+    return None if streams is None or streams is _INLINE else streams.get(gpu)
 
 
 class LzyEventLoop:
@@ -52,7 +56,24 @@ class LzyEventLoop:
             return cls.instance
 
     @classmethod
-    def run_async(cls, fun: Awaitable[T]) -> T:
+    def run_async(cls, fun: Awaitable[T], inline: bool = False) -> T:
+        """`inline`: the callee has declared that this coroutine (and everything it awaits) never really suspends —
+        ``B200Runtime`` and ``FrameSnapshot`` do (`inline_coroutines`): their bodies are synchronous calls into the C
+        ABI.  It is then driven to completion right here, on the caller's thread: no hand-off to the workflow thread and
+        back (two thread switches and a self-pipe wake-up, ≈ 80 µs a time, five times per two-op workflow), no capture of
+        the caller's streams (the caller's thread is the one running).  Any other runtime / snapshot — the reference's
+        contract is five coroutines on one loop thread — takes the loop as before."""
+        if inline:
+            token = _CALLER_STREAMS.set(_INLINE)
+            try:
+                try:
+                    fun.send(None)  # type: ignore[attr-defined]
+                except StopIteration as done:
+                    return done.value
+                fun.close()  # type: ignore[attr-defined]
+                raise RuntimeError("a coroutine declared inline-safe suspended; it needs the workflow thread")
+            finally:
+                _CALLER_STREAMS.reset(token)
         streams = _capture_streams()
         if streams is None:
             return asyncio.run_coroutine_threadsafe(fun, cls._get()._loop).result()
@@ -64,7 +85,10 @@ class LzyEventLoop:
         return asyncio.run_coroutine_threadsafe(with_caller_streams(), cls._get()._loop).result()
 
     @classmethod
-    def gather(cls, *args: Awaitable[T]) -> Sequence[T]:
+    def gather(cls, *args: Awaitable[T], inline: bool = False) -> Sequence[T]:
+        if inline:
+            return [cls.run_async(a, inline=True) for a in args]
+
         async def _g():
             return await asyncio.gather(*args)
         return cls.run_async(_g())

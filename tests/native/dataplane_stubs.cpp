@@ -40,4 +40,5 @@ int lzyb_slot_retain(lzyb_handle_t) { unreachable("slot_retain"); }
 int lzyb_slot_set_meta(lzyb_handle_t, uint32_t, uint32_t, const uint64_t*) { unreachable("slot_set_meta"); }
 int lzyb_slot_export(lzyb_handle_t, lzyb_ipc_desc_t*) { unreachable("slot_export"); }
 int lzyb_peer_import(const lzyb_ipc_desc_t*, int, lzyb_handle_t*) { unreachable("peer_import"); }
+int lzyb_slot_set_movable(lzyb_handle_t, int) { unreachable("slot_set_movable"); }
 }

@@ -432,3 +432,40 @@ def test_slot_slab_exhaustion_is_an_error_not_a_hang(native):
         N.lib.lzyb_fault_inject(0, N.FAULT_SLAB_RESERVE, 0)
     s = N.SlotHandle.create_output("slab/ok", 0, 4 << 20)  # and the frame it had taken went back to the pool
     s.close()
+
+
+@pytest.mark.parametrize("store", [True, False], ids=["copy", "scan"])
+def test_tma_ring_recycling_under_stress(native, store):
+    """compute-sanitizer's racecheck flags write-after-read hazards on the TMA ring's shared-memory
+    stages that the full/empty mbarrier pair is there to order (profiles/r01_sanitizer_racecheck_hazards.txt).  The
+    argument is checked here the hard way: the shallowest ring the kernel supports (2 stages of 8 KiB) on 4 CTAs, so every
+    CTA recycles each stage thousands of times per transfer, hundreds of transfers of awkward sizes — a stage released one
+    phase early or loaded one phase late would deliver a wrong byte or a wrong digest."""
+    N = native
+    N.set_copy_engine(N.ENGINE_TMA)
+    N.set_tma_config(6)
+    N.lib.lzyb_set_debug_flags(2)
+    try:
+        for i, n in enumerate([(1 << 20), (1 << 20) + 8192 * 3 + 48, (3 << 20) + 16, (5 << 20) + 8192 + 1, 16 << 20]):
+            a = rnd(n, seed=100 + i)
+            t, v = dev_bytes(a)
+            want = oracle.digest(a)
+            for rep in range(20):
+                if store:
+                    out = N.SlotHandle.create_output(f"stress/out{i}/{rep}", 0, n)
+                    out.pack(v.data_ptr(), n)
+                    out.commit()
+                    inp = N.SlotHandle.open_input(f"stress/in{i}/{rep}", 0, n)
+                    assert inp.transfer_chunk(out, 0, 1 << 40) == n  # the TMA ring, copying
+                    inp.finish(out)
+                    assert tuple(inp.info().digest) == want
+                    if rep % 5 == 0:
+                        assert np.array_equal(slot_bytes(n, inp), a)
+                    inp.close()
+                    out.close()
+                else:
+                    assert N.digest_device(0, v.data_ptr(), n) == want  # the TMA ring, scanning
+    finally:
+        N.lib.lzyb_set_debug_flags(0)
+        N.set_tma_config(1)
+        N.set_copy_engine(N.ENGINE_AUTO)
