@@ -270,11 +270,12 @@ class Ring:
             self.box.post(self.OUT, bytes(prev.export()))
             sink = N.IpcDesc.from_buffer_copy(self.box.read(succ, self.SINK))
             src = N.IpcDesc.from_buffer_copy(self.box.read(pred, self.OUT))
-            # my GPU as a sink: the landed scan starts waiting for my predecessor's push ...
+            # my GPU as a source first: my committed output goes into my successor's frame.  (The first push into a frame
+            # maps it — cudaIpcOpenMemHandle synchronises this device — so it must not find my own waiter spinning.)
+            prev.push(sink, 0, 0, self.sp_push)
+            # ... and as a sink: one thread waits for my predecessor's arrival word, then hands over verdict and digest
             got = self.timed("deliver", lambda: inp.expect_push(src, 0, 0, self.sp), record)
             assert got == self.payload
-            # ... and as a source: my committed output goes into my successor's frame
-            prev.push(sink, 0, 0, self.sp_push)
             inp.finish_expect(src.digest, self.sp)
             return inp
         self.box.post(self.OUT, bytes(prev.export()))

@@ -12,8 +12,6 @@ record each, so that `bench.py` can attach them to its JSON line (`extra.configs
 
 The CPU figures come from `oracle/` (test infrastructure: only the timed baseline legs may call it).
 """
-from __future__ import annotations
-
 import time
 from typing import Any, Dict, List, Optional
 
@@ -30,7 +28,6 @@ def c1(dev: int = 0, reps: int = 20, cpu_reps: int = 3, with_cpu: bool = True) -
     import numpy as np
 
     from lzy_b200.api.v1 import B200Runtime, Lzy, materialize, op
-    globals().update(np=np)
 
     @op
     def ident(a: np.ndarray) -> np.ndarray:
@@ -190,7 +187,6 @@ def c4(dev: int = 0, rows_list=(569, 1_000_000), reps: int = 5, with_cpu: bool =
 
     from lzy_b200 import _native as N
     from lzy_b200.api.v1 import B200Runtime, Lzy, materialize, op
-    globals().update(np=np, Bunch=Bunch)
 
     @op
     def train(b: Bunch) -> np.ndarray:  # stand-in for CatBoost fit (catboost is not in the image): a column reduction
@@ -251,7 +247,6 @@ def c5(gpus: Optional[List[int]] = None, mib: int = 256, reps: int = 4) -> Dict[
     import torch
 
     from lzy_b200.api.v1 import B200Runtime, Lzy, materialize, op
-    globals().update(torch=torch, TDict=TDict)
     meta = {f"k{i}": ("v" * 40, i, float(i)) for i in range(700)}  # ≈ 64 KiB pickled
     compute_ms: List[float] = []
 

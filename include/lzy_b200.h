@@ -257,7 +257,10 @@ int lzyb_peer_import(const lzyb_ipc_desc_t* desc, int onto_gpu, lzyb_handle_t* o
  *              lzyb_input_expect_push(dst, producer's slot descriptor, 0, 0, stream) → lzyb_input_finish_expect
  *   producer:  lzyb_slot_push(src, sink desc, 0, 0, stream)
  * A push carries the whole payload (offset 0, len 0 or nbytes); offset-resumed partial deliveries take the pull path
- * (lzyb_peer_import + lzyb_transfer_chunk).  A push that never comes is LZYB_E_PEER after ≈ 4 s, not a hang. */
+ * (lzyb_peer_import + lzyb_transfer_chunk).  A push that never comes is LZYB_E_PEER after ≈ 4 s, not a hang.
+ * Ordering inside ONE process that both pushes and receives on the same GPU (a ring): issue lzyb_slot_push before
+ * lzyb_input_expect_push — the first push into a frame maps it (cudaIpcOpenMemHandle), which synchronises the device
+ * and would wait for a spinning waiter's timeout. */
 int lzyb_sink_export(lzyb_handle_t input, lzyb_ipc_desc_t* out);
 int lzyb_slot_push(lzyb_handle_t src, const lzyb_ipc_desc_t* sink, uint64_t offset, uint64_t len, void* stream);
 int64_t lzyb_input_expect_push(lzyb_handle_t dst, const lzyb_ipc_desc_t* producer, uint64_t offset, uint64_t len, void* stream);
