@@ -20,6 +20,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mib", type=int, nargs="+", default=[1, 8, 32, 128, 1024])
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--only", nargs="*", default=None, help="carriers to run (default: all): push tma ldg dma")
+    ap.add_argument("--dirs", type=int, nargs="*", default=[1, 2])
     args = ap.parse_args()
     if torch.cuda.device_count() < 2:
         print(json.dumps({"skip": "needs 2 GPUs"}))
@@ -40,8 +42,10 @@ def main():
             outs.append(o)
             del t
         for name, eng in ENGINES.items():
+            if args.only and name not in args.only:
+                continue
             N.set_copy_engine(eng)
-            for dirs in (1, 2):
+            for dirs in args.dirs:
                 sinks = [1] if dirs == 1 else [1, 0]  # sink GPU g pulls from out[1 - g]
 
                 def once():
