@@ -39,6 +39,7 @@ static_assert(sizeof(lzyb_ipc_desc_t) == 256, "ipc descriptor must be 256 bytes"
 constexpr int CTL_SLAB = 8192;        // slots that can be live per device
 constexpr int MBOX_SLAB = 65536;      // mailboxes (pinned, all devices)
 constexpr int GRID_AUTO = -1000;      // lzyb_set_grid: let launch_stream pick the grid shape
+constexpr uint64_t BOUNCE_BYTES = 4ull << 20;      // D2H reads of at most this into pageable memory go through a pinned bounce buffer
 constexpr uint64_t PUSH_MIN_DEFAULT = 4ull << 20;  // in-process GPU→GPU transfers at least this long are pushed from the source GPU (auto policy)
 // TMA ring shapes that can be selected at run time (lzyb_set_tma_config): {stages, stage bytes, CTAs per SM}
 struct TmaCfg {
@@ -123,6 +124,11 @@ struct DeviceCtx {
     // that carries a transfer OUT of this GPU (its own push stream, or the pulling consumer's stream on device j)
     std::mutex src_mu;
     std::vector<cudaEvent_t> sourcing_ev;
+    // small device→host reads into PAGEABLE memory (an ndarray argument of a host-side op, a pickle): cudaMemcpy into
+    // pageable memory costs ≈ 0.19 ms per MiB-sized call on these hosts (driver-side staging); a pinned bounce buffer and
+    // a memcpy cost a third of that (profiles/r02_profile_api_c1.txt)
+    std::mutex bounce_mu;
+    uint8_t* bounce = nullptr;
     std::mutex dma_mu;  // one copy-engine pull is issued at a time per sink GPU (event ring, verify-stream order)
     std::vector<cudaEvent_t> dma_events;
     size_t dma_ev_next = 0;
@@ -707,6 +713,7 @@ int lzyb_shutdown(void) {
         cudaStreamDestroy(d->push_stream);
         for (cudaEvent_t e : d->sourcing_ev)
             if (e) cudaEventDestroy(e);
+        if (d->bounce) cudaFreeHost(d->bounce);
         cudaStreamDestroy(d->stream);
     }
     g.devs.clear();
@@ -955,8 +962,26 @@ int lzyb_copy_to_host(lzyb_handle_t h, uint64_t offset, void* dst_host, uint64_t
     DeviceCtx& d = *g.devs[s->dev];
     DeviceGuard dg(d.ordinal);
     cudaStream_t st = pick_stream(d, stream);
-    if (len) CU(cudaMemcpyAsync(dst_host, s->payload() + offset, len, cudaMemcpyDeviceToHost, st));
-    if (!stream) CU(cudaStreamSynchronize(st));
+    bool bounced = false;
+    if (len && len <= BOUNCE_BYTES) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, dst_host) != cudaSuccess) cudaGetLastError();
+        else if (attr.type == cudaMemoryTypeUnregistered) {
+            std::lock_guard<std::mutex> bl(d.bounce_mu);
+            if (!d.bounce && cudaHostAlloc((void**)&d.bounce, BOUNCE_BYTES, cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                d.bounce = nullptr;
+            }
+            if (d.bounce) {
+                CU(cudaMemcpyAsync(d.bounce, s->payload() + offset, len, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                memcpy(dst_host, d.bounce, len);
+                bounced = true;
+            }
+        }
+    }
+    if (len && !bounced) CU(cudaMemcpyAsync(dst_host, s->payload() + offset, len, cudaMemcpyDeviceToHost, st));
+    if (!stream && !bounced) CU(cudaStreamSynchronize(st));
     g.st_d2h += len;
     return LZYB_OK;
 }
