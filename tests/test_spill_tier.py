@@ -238,3 +238,47 @@ def test_pre_existing_plain_file_is_a_storage_producer(env, tmp_path):
     with pytest.raises(N.LzybError):
         lost.before_execution(10000)
     lost.close()
+
+
+@pytest.mark.parametrize("damage", ["truncated", "nbytes lies", "impossible rank"])
+def test_a_frame_file_that_contradicts_itself_is_rotten_not_foreign(env, damage):
+    """a file that carries the frame magic but whose header does not fit the file (truncated payload, wrong
+    nbytes, ndim > 8) used to be served as a *foreign* object — header + partial payload as DT_BYTES under a freshly
+    computed digest.  It is a read error, like any other rotten file."""
+    cm, slots, lib, d = env
+    data = os.urandom(200_000)
+    ctx, chan = produce_to_store(cm, slots, lib, "hbm://t/selfcontra", data, dtype=N.DT_U8, shape=(200_000,))
+    H.frame_store_spill("hbm://t/selfcontra")
+    ctx.close()
+    H.frame_store_drop("hbm://t/selfcontra")
+    (f,) = list(d.iterdir())
+    raw = bytearray(f.read_bytes())
+    if damage == "truncated":
+        raw = raw[: 128 + 150_000]
+    elif damage == "nbytes lies":
+        struct.pack_into("<Q", raw, 16, len(data) - 16)
+    else:
+        struct.pack_into("<I", raw, 24, 9)
+    f.write_bytes(bytes(raw))
+    with pytest.raises(N.LzybError, match="corrupt frame file"):
+        H.frame_store_get("hbm://t/selfcontra")
+    assert lib.hostmem_live_slots() == 0
+
+
+def test_a_truncated_file_storage_peer_fails_the_consumer(env, tmp_path):
+    """the same rule on the file:// storage-peer path: the consumer's transfer factory refuses the peer (a read fault of
+    that producer), it is never handed header + partial payload as bytes"""
+    cm, slots, lib, d = env
+    data = os.urandom(100_000)
+    p = tmp_path / "trunc.lzyb"
+    hdr = bytearray(128)
+    hdr[:8] = b"LZYB200\0"
+    struct.pack_into("<IIQII", hdr, 8, N.lib.lzyb_abi_version(), N.DT_U8, len(data), 1, 1)
+    struct.pack_into("<Q", hdr, 32, len(data))
+    p.write_bytes(bytes(hdr) + data[:60_000])
+    chan = cm.get_or_create("u", "wf", "exec-trunc", producer_uri=f"file://{p}")
+    cons = slots.context("exec-trunc", "c")
+    cons.add_slot("/t/in", chan, DIR_INPUT)
+    with pytest.raises(N.LzybError, match="No more producers|Cannot get data|corrupt frame file"):
+        cons.before_execution(10000)
+    cons.close()

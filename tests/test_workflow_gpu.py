@@ -378,6 +378,35 @@ def test_same_local_data_is_stored_once(lzy, workflow_name):
         assert len(u1.rsplit("/", 1)[1]) == 32  # prefix + 128-bit digest hex, the md5 position
 
 
+def test_equal_bytes_of_another_dtype_or_shape_are_another_value(lzy, workflow_name):
+    """the payload digest does not see dtype / shape / serializer flags (they live in the frame header),
+    so zeros(4, f32) and zeros(4, i32), or one buffer viewed as (2, 8) and (4, 4), used to share a URI: the second was
+    dropped as a duplicate and came back with the first one's dtype and shape, and cache=True calls on them shared a result.
+    The reference's md5 runs over the serialized stream, which carries both (snapshot.py:147-155).  URIs are built from the
+    content key now."""
+    seen = {"n": 0}
+
+    @op(cache=True, version="1")
+    def describe(t: torch.Tensor) -> str:
+        seen["n"] += 1
+        return f"{t.dtype} {tuple(t.shape)}"
+
+    cases = [torch.zeros(16, dtype=torch.float32, device="cuda"), torch.zeros(16, dtype=torch.int32, device="cuda"),
+             torch.zeros(2, 8, dtype=torch.float32, device="cuda"), torch.zeros(4, 4, dtype=torch.float32, device="cuda"),
+             torch.zeros(64, dtype=torch.uint8, device="cuda")]
+    with lzy.workflow(workflow_name) as wf:
+        before = len(lzy.runtime.store)
+        results = [describe(c) for c in cases]
+        uris = [wf.snapshot.get(call.arg_entry_ids[0]).storage_uri for call in wf.call_queue]
+        assert len(set(uris)) == len(cases) and len(lzy.runtime.store) == before + len(cases)
+        assert [str(r) for r in results] == [f"{c.dtype} {tuple(c.shape)}" for c in cases]
+    assert seen["n"] == len(cases)  # five different values: five executions, five cache entries
+    with lzy.workflow(workflow_name) as wf:
+        again = describe(torch.zeros(16, dtype=torch.int32, device="cuda"))  # an equal VALUE still hits the cache
+        assert str(again) == "torch.int32 (16,)"
+    assert seen["n"] == len(cases)
+
+
 def test_cached_op_runs_once(lzy, workflow_name):
     counter = {"n": 0}
 
