@@ -518,9 +518,16 @@ def test_arguments_and_results_follow_the_callers_stream(lzy, workflow_name):
 
 
 def test_without_stream_propagation_the_hazard_is_real(lzy, workflow_name, monkeypatch):
-    """negative control for the test above: with the caller's streams not carried over, the pack runs on the
-    workflow thread's default stream and snapshots the argument before it was filled"""
+    """negative control for the test above, on the path a runtime without `inline_coroutines` takes (the workflow
+    thread): with the caller's streams not carried over, the pack runs on that thread's default stream and snapshots the
+    argument before it was filled.  (B200Runtime's own coroutines run on the caller's thread since round 2, where the
+    caller's stream simply is the current one — the test above.)"""
+    from lzy_b200.api.v1.b200.runtime import B200Runtime
+    from lzy_b200.api.v1.snapshot import FrameSnapshot
     from lzy_b200.utils import event_loop
+    monkeypatch.setattr(B200Runtime, "inline_coroutines", False)
+    monkeypatch.setattr(FrameSnapshot, "inline_coroutines", False)
+    assert _late_filled_tensor_through_an_op(lzy, workflow_name) == (7.0, 7.0)  # the loop thread, streams carried over
     monkeypatch.setattr(event_loop, "_capture_streams", lambda: None)
     assert _late_filled_tensor_through_an_op(lzy, workflow_name) != (7.0, 7.0)
 
