@@ -185,6 +185,12 @@ int lzyb_slot_commit(lzyb_handle_t h, uint64_t digest_out[2], void* stream);
  * at/after the end (OutputSlot.ReadThread, OutputSlot.java:238-265). */
 int64_t lzyb_slot_read(lzyb_handle_t h, uint64_t offset, void* dst_host, uint64_t len);
 int lzyb_slot_info(lzyb_handle_t h, lzyb_slot_info_t* out);
+/* the same without waiting for anything: sizes, state, dtype, shape; the digest fields are filled only if the digest is
+ * already known (see lzyb_set_lazy_commit) */
+int lzyb_slot_meta(lzyb_handle_t h, lzyb_slot_info_t* out);
+/* order `stream` (NULL: the calling thread) after the last launch that wrote this slot's frame — what a reader on another
+ * stream needs before it touches lzyb_slot_device_ptr() */
+int lzyb_slot_wait(lzyb_handle_t h, void* stream);
 int lzyb_slot_header(lzyb_handle_t h, lzyb_frame_header_t* out);   /* D2H copy of the frame header */
 /* = backend.close(): idempotent, returns HBM to the pool, cancels in-flight work.  Frames are
  * reference counted: every lzyb_slot_retain() needs one more close before the HBM is released. */
@@ -311,6 +317,15 @@ int lzyb_stats_reset(void);
  * a push verifies what it hands to the wire (push_kernels.cuh). */
 int lzyb_set_copy_engine(int engine);
 int lzyb_set_push_min_bytes(uint64_t nbytes);
+/* Commit in stream order.  Off (default): lzyb_slot_commit blocks until the pack / scan has finished and the digest is known
+ * — OutputSlotBackend.waitCompleted() as the reference means it.  On: lzyb_slot_commit(h, NULL, …) only QUEUES the
+ * completion — the slot is READY for everything that is ordered behind the pack on the device (a same-GPU hand-over, an op
+ * body on the worker's stream, lzyb_copy_to_host / lzyb_slot_read / transfers, which wait for the frame's last writer on
+ * their own stream) — and the digest is harvested by the first call that needs it (lzyb_slot_info, _export, a copying
+ * transfer, lzyb_slot_commit with digest_out).  lzyb_input_finish on a slot that received its frame by hand-over returns
+ * without waiting.  A runtime that keeps every reader stream-ordered (B200Runtime) turns it on so that an op's successor is
+ * not held up by the op's pack kernel; Java-style blocking callers leave it off. */
+int lzyb_set_lazy_commit(int on);
 /* sub-chunk schedule of a copy-engine pull: the last sub-chunk is last_bytes (0 = payload/32 clamped to
  * 4..32 MiB; else a multiple of 16, at least 1 MiB), each earlier one `growth` times larger (default 6; 1 =
  * uniform), the first takes the remainder */

@@ -151,6 +151,9 @@ typedef struct lzyb_backend_ops {
     /* optional (may be NULL): declare that a committed output frame has exactly one consumer, which may then take the
      * frame over instead of copying it (HBM backend: lzyb_slot_set_movable) */
     int (*slot_set_movable)(lzyb_handle_t h, int movable);
+    /* optional (may be NULL → slot_info): sizes / state / dtype / shape without waiting for a digest that is still being
+     * computed (HBM backend: lzyb_slot_meta) */
+    int (*slot_meta)(lzyb_handle_t h, lzyb_slot_info_t* out);
 } lzyb_backend_ops_t;
 int lzyb_slots_set_backend(const lzyb_backend_ops_t* ops); /* NULL = the HBM backend */
 

@@ -142,6 +142,9 @@ _SIGNATURES = {
     "lzyb_slot_commit": (C.c_int, [_H, C.POINTER(C.c_uint64 * 2), _P]),
     "lzyb_slot_read": (C.c_int64, [_H, C.c_uint64, _P, C.c_uint64]),
     "lzyb_slot_info": (C.c_int, [_H, C.POINTER(SlotInfo)]),
+    "lzyb_slot_meta": (C.c_int, [_H, C.POINTER(SlotInfo)]),
+    "lzyb_slot_wait": (C.c_int, [_H, _P]),
+    "lzyb_set_lazy_commit": (C.c_int, [C.c_int]),
     "lzyb_slot_header": (C.c_int, [_H, C.POINTER(FrameHeader)]),
     "lzyb_slot_close": (C.c_int, [_H]),
     "lzyb_slot_retain": (C.c_int, [_H]),
@@ -348,6 +351,16 @@ class SlotHandle:
         check(lib.lzyb_slot_info(self.h, C.byref(i)))
         return i
 
+    def meta(self) -> SlotInfo:
+        """sizes, state, dtype, shape — never waits; the digest fields are zero while the digest is still being computed"""
+        i = SlotInfo()
+        check(lib.lzyb_slot_meta(self.h, C.byref(i)))
+        return i
+
+    def wait(self, stream: int = 0) -> None:
+        """order `stream` (0: this thread) after the last launch that wrote the frame"""
+        check(lib.lzyb_slot_wait(self.h, stream or None))
+
     def header(self) -> FrameHeader:
         hd = FrameHeader()
         check(lib.lzyb_slot_header(self.h, C.byref(hd)))
@@ -373,7 +386,7 @@ class SlotHandle:
     def adopt(cls, h: int, owned: bool = True) -> "SlotHandle":
         """wrap a handle produced by the slots runtime (retained when `owned`, so closing is safe)"""
         i = SlotInfo()
-        check(lib.lzyb_slot_info(h, C.byref(i)))
+        check(lib.lzyb_slot_meta(h, C.byref(i)))
         if owned:
             check(lib.lzyb_slot_retain(h))
         s = cls(h, f"adopted:{h}", int(i.gpu), int(i.nbytes))
@@ -432,6 +445,10 @@ def fill_pattern(gpu: int, dptr: int, nbytes: int, seed: int, stream: int = 0) -
 
 def set_copy_engine(engine: int) -> None:
     check(lib.lzyb_set_copy_engine(engine))
+
+
+def set_lazy_commit(on: bool) -> None:
+    check(lib.lzyb_set_lazy_commit(int(bool(on))))
 
 
 def set_push_min_bytes(nbytes: int) -> None:

@@ -66,6 +66,7 @@ class B200RuntimeConfig:
     retain: str = "auto"                         # "auto": a frame is freed once no proxy / queued call can ask for it; "all": keep until clear()
     chunk_bytes: int = 0                         # 0 = one launch per transfer; the reference streams 2 MiB chunks
     move_sole_consumer: bool = True              # an output with one consumer on the same GPU and no other reader is handed over, not copied
+    lazy_commit: bool = True                     # an op's result is READY in stream order: its successor is not held up by the pack kernel
     copy_engine: str = "auto"                    # "auto" | "ldg" | "tma" | "dma" | "push"
     spill_dir: Optional[str] = None              # tier below HBM: evicted frames and cache=True results live here as files
     hbm_budget_bytes: int = 0                    # resident frame-store bytes above which LRU frames are evicted (0 = never)
@@ -96,7 +97,7 @@ class B200RuntimeConfig:
         raw = raw.strip()
         if name == "gpus":
             return None if raw.lower() in ("", "all") else [int(x) for x in raw.split(",") if x.strip()]
-        if name in ("prefetch", "republish_inputs", "move_sole_consumer"):
+        if name in ("prefetch", "republish_inputs", "move_sole_consumer", "lazy_commit"):
             if raw.lower() in ("1", "true", "yes", "on"):
                 return True
             if raw.lower() in ("0", "false", "no", "off"):
@@ -139,6 +140,8 @@ class B200Runtime(Runtime):
     # start / exec / finish / abort never suspend when nobody runs a loop for them: LzyEventLoop drives them on the caller's
     # thread (exec then runs the graph right there instead of parking it on an executor)
     inline_coroutines = True
+    _lazy_lock = threading.Lock()
+    _lazy_users = 0
 
     def __init__(self, config: Optional[B200RuntimeConfig] = None, **kwargs):
         self.config = config or B200RuntimeConfig.from_env(**kwargs)
@@ -175,6 +178,10 @@ class B200Runtime(Runtime):
                 self.gpus = list(self.config.gpus)
             N.set_copy_engine({"auto": N.ENGINE_AUTO, "ldg": N.ENGINE_LDG, "tma": N.ENGINE_TMA,
                                "dma": N.ENGINE_DMA, "push": N.ENGINE_PUSH}[self.config.copy_engine])
+            if self.config.lazy_commit:  # a process-wide switch of the library: on while any runtime that wants it is up
+                with B200Runtime._lazy_lock:
+                    B200Runtime._lazy_users += 1
+                    N.set_lazy_commit(True)
             self.store = FrameStore(default_gpu=self.gpus[0])
             if self.config.spill_dir or self.config.hbm_budget_bytes:
                 self.store.configure_tier(self.config.spill_dir, self.config.hbm_budget_bytes)
@@ -295,6 +302,12 @@ class B200Runtime(Runtime):
             if self._pool:
                 self._pool.shutdown(wait=False)
             self.workers.clear()
+            if self.config.lazy_commit:
+                with B200Runtime._lazy_lock:
+                    B200Runtime._lazy_users -= 1
+                    if B200Runtime._lazy_users <= 0:
+                        B200Runtime._lazy_users = 0
+                        N.set_lazy_commit(False)
             self._ready = False
 
     # ---- graph execution ----------------------------------------------------------------------------------
@@ -540,7 +553,9 @@ class B200Runtime(Runtime):
                         slot.finish(base)
                     else:
                         slot = N.SlotHandle.adopt(ctx.input_handle(f"/{call.id}/{eid}"), owned=True)
-                    values[eid] = self.store.unpack_slot(slot, snapshot.get(eid).typ, registry, private=True)
+                    # the op body runs on this worker's stream: that is where the view must be ordered behind its producer
+                    values[eid] = self.store.unpack_slot(slot, snapshot.get(eid).typ, registry, private=True,
+                                                         stream=int(self._streams[gpu].cuda_stream))
                 return values[eid]
 
             def arg(eid: str) -> Any:

@@ -258,8 +258,11 @@ class FrameStore:
         # resident in the C++ store (an op produced it) or waiting in the spill tier; asking does not load it
         return H.frame_store_resident(uri) or (self.spill_dir is not None and H.frame_store_spilled(uri))
 
-    def unpack_slot(self, slot: N.SlotHandle, typ: Type, registry: SerializerRegistry, private: bool) -> Any:
-        info = _InfoView(slot.info())
+    def unpack_slot(self, slot: N.SlotHandle, typ: Type, registry: SerializerRegistry, private: bool, stream: int = 0) -> Any:
+        """`stream`: the CUDA stream the value will be used on (0 = the calling thread's current stream on the slot's
+        GPU).  A zero-copy view is only as good as its ordering: that stream is made to wait for the frame's last writer
+        (a pack that may still be running when the slot was committed in stream order, lzyb_set_lazy_commit)."""
+        info = _InfoView(slot.meta())
         if info.dtype == N.DT_PICKLE and info.flags & FLAG_OOB:
             return self._unpack_composite(slot, info.nbytes)
         if info.dtype == N.DT_PICKLE:
@@ -272,6 +275,8 @@ class FrameStore:
             return ser.deserialize(BytesIO(raw.raw[:info.nbytes]), typ if isinstance(typ, type) else None)
         fmt = "lzyb_ndarray_frame" if info.flags & FLAG_NDARRAY else "lzyb_tensor_frame"
         ser = registry.find_serializer_by_data_format(fmt)
+        if not info.flags & (FLAG_NDARRAY | FLAG_HOST_ORIGIN):  # a device view: the host copies order themselves inside the C ABI
+            slot.wait(stream or current_stream_ptr(slot.gpu))
         value = ser.unpack(slot, info, private)
         if not private and hasattr(value, "is_cuda") and value.is_cuda:
             value = value.clone()  # a client read gets its own copy, like a fresh deserialization

@@ -159,6 +159,7 @@ struct Slot {
     bool remote = false;         // imported over CUDA IPC: we do not own buf
     void* ipc_base = nullptr;
     bool digest_pending = false; // a finalizing launch is in flight (or done) for the payload
+    bool digest_ready = false;   // the verdict of that launch has been harvested: digest / sum / xr below are valid
     bool ctl_dirty = false;      // partial sums sit in ctl (mid-transfer)
     uint64_t delivered = 0;
     uint64_t digest[2] = {0, 0};
@@ -215,6 +216,7 @@ struct Global {
     std::atomic<uint64_t> dma_last_bytes{0};  // last sub-chunk of a copy-engine pull (0 = total/32 in 4..32 MiB)
     std::atomic<int> dma_growth{6};            // each earlier sub-chunk is this many times larger
     std::atomic<uint64_t> push_min{PUSH_MIN_DEFAULT};
+    std::atomic<int> lazy_commit{0};  // lzyb_set_lazy_commit
     std::atomic<uint64_t> st_push{0}, st_moves{0};
     std::atomic<uint64_t> next_push_seq{1};  // arrival words never repeat within this process
     // stats
@@ -535,7 +537,19 @@ int harvest(Slot& s) {
     s.sum = s.mbox->sum;
     s.xr = s.mbox->xr;
     s.ctl_dirty = false;
+    s.digest_ready = s.mbox->status == 1u;
     return static_cast<int>(s.mbox->status);
+}
+
+// A slot that was made READY in stream order (lzyb_set_lazy_commit) learns its digest here, the first time somebody
+// needs it: the host then waits for the pack / scan that has been running since.
+int ensure_digest(Slot& s) {
+    if (s.digest_ready || !s.digest_pending || s.state != LZYB_ST_READY) return LZYB_OK;
+    DeviceGuard dg(g.devs[s.dev]->ordinal);
+    int st = harvest(s);
+    if (st < 0) return st;
+    if (st != 1) return fail(LZYB_E_LOCAL, "slot %s: unexpected finalize status %d", s.id.c_str(), st);
+    return LZYB_OK;
 }
 
 int new_slot(const char* slot_id, int gpu, uint64_t nbytes, bool is_input, lzyb_handle_t* out) {
@@ -923,6 +937,14 @@ int lzyb_slot_commit(lzyb_handle_t h, uint64_t digest_out[2], void* stream) {
             int rc = scan_publish(*s, d, pick_stream(d, stream));
             if (rc != LZYB_OK) return rc;
         }
+        if (!digest_out && g.lazy_commit.load()) {
+            // complete in stream order: everything that reads the frame is queued behind the pack (same-GPU hand-overs,
+            // op bodies on the worker's stream, stream-waits of copies and transfers); the digest is harvested by whoever
+            // asks for it first (ensure_digest).  A pack cannot fail its own digest, so READY is not a guess.
+            s->state = LZYB_ST_READY;
+            s->delivered = s->nbytes;
+            return LZYB_OK;
+        }
         int st = harvest(*s);
         if (st < 0) return st;
         if (st != 1) return fail(LZYB_E_LOCAL, "slot %s: unexpected finalize status %d", s->id.c_str(), st);
@@ -930,6 +952,8 @@ int lzyb_slot_commit(lzyb_handle_t h, uint64_t digest_out[2], void* stream) {
         s->delivered = s->nbytes;
     }
     if (digest_out) {
+        int rc = ensure_digest(*s);
+        if (rc != LZYB_OK) return rc;
         digest_out[0] = s->digest[0];
         digest_out[1] = s->digest[1];
     }
@@ -947,6 +971,7 @@ int64_t lzyb_slot_read(lzyb_handle_t h, uint64_t offset, void* dst_host, uint64_
     if (n > len) n = len;
     DeviceCtx& d = *g.devs[s->dev];
     DeviceGuard dg(d.ordinal);
+    if (s->last_ev && s->last_stream != d.stream) CU(cudaStreamWaitEvent(d.stream, s->last_ev, 0));  // the frame's last writer
     CU(cudaMemcpyAsync(dst_host, s->payload() + offset, n, cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));
     g.st_d2h += n;
@@ -962,6 +987,7 @@ int lzyb_copy_to_host(lzyb_handle_t h, uint64_t offset, void* dst_host, uint64_t
     DeviceCtx& d = *g.devs[s->dev];
     DeviceGuard dg(d.ordinal);
     cudaStream_t st = pick_stream(d, stream);
+    if (s->last_ev && s->last_stream != st) CU(cudaStreamWaitEvent(st, s->last_ev, 0));  // the frame's last writer
     bool bounced = false;
     if (len && len <= BOUNCE_BYTES) {
         cudaPointerAttributes attr;
@@ -990,6 +1016,7 @@ int lzyb_slot_info(lzyb_handle_t h, lzyb_slot_info_t* out) {
     auto s = find(h);
     if (!s || !out) return fail(LZYB_E_ARG, "unknown slot handle");
     std::lock_guard<std::mutex> lk(s->mu);
+    if (int rc = ensure_digest(*s); rc != LZYB_OK) return rc;
     memset(out, 0, sizeof(*out));
     out->nbytes = s->nbytes;
     out->gpu = g.devs[s->dev]->ordinal;
@@ -1002,6 +1029,46 @@ int lzyb_slot_info(lzyb_handle_t h, lzyb_slot_info_t* out) {
     out->dtype = s->dtype;
     out->ndim = s->ndim;
     memcpy(out->shape, s->shape, sizeof(out->shape));
+    return LZYB_OK;
+}
+
+int lzyb_slot_meta(lzyb_handle_t h, lzyb_slot_info_t* out) {
+    auto s = find(h);
+    if (!s || !out) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    memset(out, 0, sizeof(*out));
+    out->nbytes = s->nbytes;
+    out->gpu = g.devs[s->dev]->ordinal;
+    out->state = s->state;
+    out->is_input = s->is_input;
+    out->is_remote = s->remote;
+    out->delivered = s->delivered;
+    if (s->digest_ready) {
+        out->digest[0] = s->digest[0];
+        out->digest[1] = s->digest[1];
+    }
+    out->dtype = s->dtype;
+    out->ndim = s->ndim;
+    memcpy(out->shape, s->shape, sizeof(out->shape));
+    return LZYB_OK;
+}
+
+int lzyb_slot_wait(lzyb_handle_t h, void* stream) {
+    auto s = find(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slot handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (!s->last_ev) return LZYB_OK;
+    DeviceGuard dg(g.devs[s->dev]->ordinal);
+    if (!stream) {
+        CU(cudaEventSynchronize(s->last_ev));
+    } else if (s->last_stream != static_cast<cudaStream_t>(stream)) {
+        CU(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), s->last_ev, 0));
+    }
+    return LZYB_OK;
+}
+
+int lzyb_set_lazy_commit(int on) {
+    g.lazy_commit = on ? 1 : 0;
     return LZYB_OK;
 }
 
@@ -1126,20 +1193,35 @@ int64_t lzyb_transfer_chunk(lzyb_handle_t dst_h, lzyb_handle_t src_h, uint64_t o
         dst->dtype = src->dtype;
         dst->ndim = src->ndim;
         memcpy(dst->shape, src->shape, sizeof(dst->shape));
-        dst->digest[0] = src->digest[0];
-        dst->digest[1] = src->digest[1];
-        dst->sum = src->sum;
-        dst->xr = src->xr;
+        if (src->digest_ready) {
+            dst->digest[0] = src->digest[0];
+            dst->digest[1] = src->digest[1];
+            dst->sum = src->sum;
+            dst->xr = src->xr;
+            dst->digest_pending = false;
+            dst->digest_ready = true;
+        } else {
+            // the producer was committed in stream order (lzyb_set_lazy_commit) and its pack may still be running: the
+            // pending finalize — mailbox, sequence number, the event of the launch — travels with the frame
+            std::swap(src->mbox, dst->mbox);
+            std::swap(src->mbox_idx, dst->mbox_idx);
+            std::swap(src->seq, dst->seq);
+            std::swap(src->last_ev, dst->last_ev);
+            std::swap(src->last_stream, dst->last_stream);
+            dst->digest_pending = true;
+            dst->digest_ready = false;
+            src->digest_pending = false;
+        }
         dst->delivered = dst->nbytes;
         dst->state = LZYB_ST_READY;
-        dst->digest_pending = false;
         src->state = LZYB_ST_MOVED;
         src->movable = false;
-        note(*dst, st);
+        if (dst->digest_ready) note(*dst, st);  // (a pending finalize keeps the event of its own launch: harvest waits for that)
         g.st_moves++;
         g.st_bpull_l += len;
         return (int64_t)len;
     }
+    if (int rc = ensure_digest(*src); rc != LZYB_OK) return rc;  // the copy verifies against the producer's digest
     CopyParams p;
     memset(&p, 0, sizeof(p));
     p.src = src->payload() + offset;
@@ -1219,7 +1301,7 @@ static int input_reset_locked(Slot& s) {
 
 static int finish_common(Slot& dst, const uint64_t expect[2], const Slot* src, void* stream) {
     if (!dst.is_input) return fail(LZYB_E_STATE, "slot %s is not an input slot", dst.id.c_str());
-    if (dst.state == LZYB_ST_READY) return LZYB_OK;
+    if (dst.state == LZYB_ST_READY) return g.lazy_commit.load() ? LZYB_OK : ensure_digest(dst);
     if (dst.state == LZYB_ST_CLOSED || dst.state == LZYB_ST_FAILED) return fail(LZYB_E_LOCAL, "sink %s already closed", dst.id.c_str());
     if (dst.delivered != dst.nbytes) return fail(LZYB_E_STATE, "slot %s: %llu of %llu bytes delivered", dst.id.c_str(),
                                                  (unsigned long long)dst.delivered, (unsigned long long)dst.nbytes);
@@ -1275,6 +1357,8 @@ int lzyb_input_finish(lzyb_handle_t dst_h, lzyb_handle_t src_h, void* stream) {
     auto src = find(src_h);
     if (!dst || !src) return fail(LZYB_E_ARG, "unknown slot handle");
     std::scoped_lock lk(dst->mu, src->mu);
+    if (dst->state != LZYB_ST_READY)
+        if (int rc = ensure_digest(*src); rc != LZYB_OK) return rc;
     return finish_common(*dst, src->digest, src.get(), stream);
 }
 
@@ -1393,6 +1477,7 @@ int lzyb_slot_export(lzyb_handle_t h, lzyb_ipc_desc_t* out) {
     std::lock_guard<std::mutex> lk(s->mu);
     if (s->state != LZYB_ST_READY) return fail(LZYB_E_STATE, "slot %s is not committed", s->id.c_str());
     if (s->remote) return fail(LZYB_E_STATE, "slot %s is itself an import", s->id.c_str());
+    if (int rc = ensure_digest(*s); rc != LZYB_OK) return rc;
     DeviceCtx& d = *g.devs[s->dev];
     DeviceGuard dg(d.ordinal);
     memset(out, 0, sizeof(*out));
@@ -1456,6 +1541,7 @@ int lzyb_peer_import(const lzyb_ipc_desc_t* desc, int onto_gpu, lzyb_handle_t* o
     s->ipc_base = base;
     s->remote = true;
     s->state = LZYB_ST_READY;
+    s->digest_ready = true;
     s->delivered = desc->nbytes;
     s->digest[0] = desc->digest[0];
     s->digest[1] = desc->digest[1];
@@ -1524,6 +1610,7 @@ int lzyb_slot_push(lzyb_handle_t src_h, const lzyb_ipc_desc_t* sink, uint64_t of
     if (!src || !sink) return fail(LZYB_E_ARG, "unknown slot handle");
     std::lock_guard<std::mutex> lk(src->mu);
     if (src->state != LZYB_ST_READY || src->remote) return fail(LZYB_E_STATE, "slot %s is not a committed local slot", src->id.c_str());
+    if (int rc = ensure_digest(*src); rc != LZYB_OK) return rc;
     if (sink->pid == (int32_t)getpid()) return fail(LZYB_E_ARG, "sink belongs to this process; use lzyb_transfer_chunk");
     if (sink->nbytes != src->nbytes) return fail(LZYB_E_PEER, "sink expects %llu bytes, slot %s holds %llu", (unsigned long long)sink->nbytes,
                                                   src->id.c_str(), (unsigned long long)src->nbytes);
@@ -1620,6 +1707,10 @@ static int broadcast_host_driven(lzyb_handle_t src_h, const lzyb_handle_t* dsts,
     chunk_bytes = round_up(chunk_bytes, 4096);
     auto src = find(src_h);
     if (!src) return fail(LZYB_E_ARG, "unknown source handle");
+    {
+        std::lock_guard<std::mutex> lk(src->mu);
+        if (int rc = ensure_digest(*src); rc != LZYB_OK) return rc;
+    }
     const uint64_t total = src->nbytes;
     std::vector<SlotPtr> chain;
     for (int k = 0; k < n; ++k) {
@@ -1715,6 +1806,10 @@ static int broadcast_device_chained(lzyb_handle_t src_h, const lzyb_handle_t* ds
     }
     const uint64_t total = src->nbytes;
     if (src->state != LZYB_ST_READY) return fail(LZYB_E_PEER, "peer %s has no complete data", src->id.c_str());
+    {
+        std::lock_guard<std::mutex> lk(src->mu);
+        if (int rc = ensure_digest(*src); rc != LZYB_OK) return rc;
+    }
     for (auto& s : chain) {
         if (!s->is_input || s->state != LZYB_ST_EMPTY || s->delivered != 0 || s->nbytes != total)
             return fail(LZYB_E_STATE, "consumer %s is not an empty input slot of %llu bytes", s->id.c_str(), (unsigned long long)total);

@@ -47,11 +47,13 @@ const lzyb_backend_ops_t kHbmBackend = {
     lzyb_slot_create, lzyb_input_open,      lzyb_slot_commit,         lzyb_slot_read,       lzyb_slot_info,
     lzyb_slot_find,   lzyb_slot_close,      lzyb_transfer_chunk,      lzyb_input_finish,    lzyb_input_write_host,
     lzyb_input_finish_expect, lzyb_input_to_output, lzyb_input_reset, lzyb_slot_retain, lzyb_slot_set_meta,
-    lzyb_slot_export, lzyb_peer_import, lzyb_slot_set_movable,
+    lzyb_slot_export, lzyb_peer_import, lzyb_slot_set_movable, lzyb_slot_meta,
 };
 std::atomic<const lzyb_backend_ops_t*> g_ops{&kHbmBackend};
 lzyb_backend_ops_t g_custom_ops;
 const lzyb_backend_ops_t& ops() { return *g_ops.load(); }
+// sizes, state, dtype, shape of a slot — never waits for a digest that is still being computed
+int slot_sizes(lzyb_handle_t h, lzyb_slot_info_t* out) { return ops().slot_meta ? ops().slot_meta(h, out) : ops().slot_info(h, out); }
 
 // ---- the matcher as the slots see it: in-process calls by default, a client of a remote channel manager otherwise ----
 const lzyb_cm_client_ops_t kLocalMatcher = {lzyb_cm_bind, lzyb_cm_unbind, lzyb_cm_transfer_completed, lzyb_cm_transfer_failed};
@@ -556,8 +558,8 @@ struct OutputSlotImpl : SlotBase, std::enable_shared_from_this<OutputSlotImpl> {
                 return;
             }
         }
-        uint64_t dg[2];
-        if (ops().slot_commit(backend, dg, nullptr) != LZYB_OK) {
+        // (no digest asked for: under lzyb_set_lazy_commit the backend may then complete the slot in stream order)
+        if (ops().slot_commit(backend, nullptr, nullptr) != LZYB_OK) {
             complete_.fail_with(std::string("Error while binding output slot: ") + lzyb_last_error());
             return;
         }
@@ -786,7 +788,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
             auto t = std::make_unique<SlotPullTransfer>();
             t->peer = h;
             t->retained = true;
-            if (ops().slot_info(h, &info) != LZYB_OK) {
+            if (slot_sizes(h, &info) != LZYB_OK) {
                 err = std::string("Error while reading from storage: ") + lzyb_last_error();
                 return nullptr;
             }
@@ -836,7 +838,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
             imported = true;
         }
         lzyb_slot_info_t info;
-        if (ops().slot_info(h, &info) != LZYB_OK) {
+        if (slot_sizes(h, &info) != LZYB_OK) {
             err = std::string("Cannot read from slot peer ") + p.peer_id + ": " + lzyb_last_error();
             if (imported) ops().slot_close(h);
             return nullptr;
@@ -922,7 +924,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
         if (!rec.ok) rec.error = err;
         if (backend) {
             lzyb_slot_info_t info;
-            if (ops().slot_info(backend, &info) == LZYB_OK) rec.bytes = rec.ok ? info.nbytes : info.delivered;
+            if (slot_sizes(backend, &info) == LZYB_OK) rec.bytes = rec.ok ? info.nbytes : info.delivered;
         }
         inst->record(std::move(rec));
         return ok;
@@ -971,7 +973,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
                 }
             }
             lzyb_slot_info_t info;
-            if (ops().slot_info(backend, &info) == LZYB_OK) offset = info.delivered;  // reopening the channel: resume here
+            if (slot_sizes(backend, &info) == LZYB_OK) offset = info.delivered;  // reopening the channel: resume here
             const uint64_t chunk = inst->chunk_bytes.load();
             int64_t moved = transfer->transfer_chunk_to(backend, offset, chunk ? chunk : ~0ull);
             if (moved == LZYB_E_PEER) {  // ReadException: mark the peer bad, ask for another one
@@ -1590,7 +1592,7 @@ int64_t lzyb_frame_store_bytes(void) {
     int64_t total = 0;
     for (auto h : hs) {
         lzyb_slot_info_t info;
-        if (ops().slot_info(h, &info) == LZYB_OK) total += (int64_t)info.nbytes;
+        if (slot_sizes(h, &info) == LZYB_OK) total += (int64_t)info.nbytes;
     }
     return total;
 }

@@ -41,4 +41,5 @@ int lzyb_slot_set_meta(lzyb_handle_t, uint32_t, uint32_t, const uint64_t*) { unr
 int lzyb_slot_export(lzyb_handle_t, lzyb_ipc_desc_t*) { unreachable("slot_export"); }
 int lzyb_peer_import(const lzyb_ipc_desc_t*, int, lzyb_handle_t*) { unreachable("peer_import"); }
 int lzyb_slot_set_movable(lzyb_handle_t, int) { unreachable("slot_set_movable"); }
+int lzyb_slot_meta(lzyb_handle_t, lzyb_slot_info_t*) { unreachable("slot_meta"); }
 }
