@@ -173,6 +173,7 @@ struct Slot {
     uint64_t fault_arg = 0;
     bool movable = false;        // the owner declared a sole consumer: a whole-payload same-GPU pull moves the frame
     uint64_t push_seq = 0;       // input slot exported as a push sink: the sequence word the producer must write on completion
+    bool quarantined = false;    // a push into this frame was declared lost: it may still land, so the frame is never reused
     std::atomic<int> refs{1};    // lzyb_slot_retain / lzyb_slot_close
     // asynchronous readers of this frame inside this process (consumer stream → event recorded after its last
     // pull launch): close waits for them before the frame goes back to the pool
@@ -1127,6 +1128,8 @@ int lzyb_slot_close(lzyb_handle_t h) {
     s->readers.clear();
     if (s->remote) {
         // the mapping stays in g.ipc_cache (closed at shutdown)
+    } else if (s->buf && s->quarantined) {
+        g.st_hbm_live -= s->cap;  // deliberately not pooled and not freed: a lost push may still write here
     } else if (s->buf) {
         free_frame(d, s->buf, s->cap);
         g.st_hbm_live -= s->cap;
@@ -1336,7 +1339,12 @@ static int finish_common(Slot& dst, const uint64_t expect[2], const Slot* src, v
     int st = harvest(dst);
     if (st < 0) return st;
     if (st == 3) {
-        input_reset_locked(dst);
+        // the producer may still be alive and push late — into this very frame.  It is therefore neither reset for another
+        // attempt nor returned to the pool: the slot fails, its frame is retired with it (a consumer that wants to retry
+        // opens a fresh input slot).
+        dst.state = LZYB_ST_FAILED;
+        dst.quarantined = true;
+        dst.digest_pending = false;
         return fail(LZYB_E_PEER, "slot %s: the producer's push did not arrive within the sink's timeout", dst.id.c_str());
     }
     const bool foreign = st == 1 && expect && (dst.digest[0] != expect[0] || dst.digest[1] != expect[1]);  // the verdict of another frame
