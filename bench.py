@@ -217,9 +217,10 @@ class Ring:
         self.sp, self.sp_push = int(self.stream.cuda_stream), int(self.push_stream.cuda_stream)
         assert self.sp != 0 and self.sp_push != 0
         self.x = self.source_tensor(self.rank)
-        self.host_in = torch.empty(self.shape, dtype=torch.float32, pin_memory=True)
+        from lzy_b200.utils import numa
+        self.host_in = numa.pinned_empty(self.shape, torch.float32, self.dev)  # pinned, on the socket this GPU hangs off
         self.host_in.copy_(self.x)
-        self.host_out = torch.empty(self.shape, dtype=torch.float32, pin_memory=True)
+        self.host_out = numa.pinned_empty(self.shape, torch.float32, self.dev)
         torch.cuda.synchronize()
         self.kern_events = []  # (start, end, kind) for every data-moving launch of ours inside the timed region
         self.step_seq = 0
@@ -619,6 +620,7 @@ def api_bench(dev0: int, gpus, payload: int, shape, steps: int):
 
     from lzy_b200 import _native as N
     from lzy_b200.api.v1 import B200Runtime, Lzy, materialize, op
+    from lzy_b200.utils import numa
     globals().update(torch=torch, np=np)  # annotations are strings here (PEP 563) and are evaluated in module globals
     n = len(gpus)
 
@@ -642,8 +644,8 @@ def api_bench(dev0: int, gpus, payload: int, shape, steps: int):
         x = torch.empty(shape, dtype=torch.float32, device=f"cuda:{g}").normal_()
         xs.append(x)
         dev_in.append(torch.empty_like(x))  # the caller's own staging tensor for the H2D copy (no allocation per step)
-        host_in.append(torch.empty(shape, dtype=torch.float32, pin_memory=True).copy_(x))
-        host_out.append(torch.empty(shape, dtype=torch.float32, pin_memory=True))
+        host_in.append(numa.pinned_empty(shape, torch.float32, g).copy_(x))  # each GPU's host buffers on its own socket
+        host_out.append(numa.pinned_empty(shape, torch.float32, g))
     d2h_streams = [torch.cuda.Stream(g) for g in gpus]
 
     def step(inputs):

@@ -39,4 +39,16 @@ print("full e2e                              %.2f ms" % t(full))
 def full_sync():
     dev_in.copy_(host_in, non_blocking=True); sync(); y=step(dev_in); sync(); host_out.copy_(y, non_blocking=True)
 print("full e2e with syncs between legs      %.2f ms" % t(full_sync))
+# the unsynchronised loop again, with events between its legs: where on the GPU timeline the step's time goes
+def timeline(n=4):
+    evs=[]
+    for _ in range(n):
+        e=[torch.cuda.Event(enable_timing=True) for _ in range(4)]; h=[]
+        e[0].record(); h.append(time.perf_counter()); dev_in.copy_(host_in, non_blocking=True); e[1].record(); h.append(time.perf_counter())
+        y=step(dev_in); e[2].record(); h.append(time.perf_counter()); host_out.copy_(y, non_blocking=True); e[3].record(); h.append(time.perf_counter()); evs.append((e,h))
+    sync()
+    for i,(e,h) in enumerate(evs):
+        gap = evs[i-1][0][3].elapsed_time(e[0]) if i else 0.0
+        print("  iter %d gpu: gap %.2f h2d %.2f chain %.2f d2h %.2f | host: h2d %.2f step %.2f d2h %.2f ms" % (i, gap, e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3]), (h[1]-h[0])*1e3, (h[2]-h[1])*1e3, (h[3]-h[2])*1e3))
+full(); sync(); timeline()
 rt.close()
