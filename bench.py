@@ -552,7 +552,7 @@ def run_ours(args):
             e2e = {"value": world * N_OPS * payload / (rec["ms_e2e"] * 1e-3) / 1e9, "unit": UNIT,
                    "h2d_bytes_per_step": world * payload, "d2h_bytes_per_step": world * payload, "ms_per_step": rec["ms_e2e"],
                    "steps": api_steps, "ops_per_sec": world * N_OPS / (rec["ms_e2e"] * 1e-3), "bit_exact": True,
-                   "phases_ms": rec["phases"],
+                   "phases_ms": rec["phases"], "gpu_timeline_ms": rec["timeline"],
                    "api": ("Lzy(runtime=B200Runtime(gpus=[0..N-1])).workflow(): x_j.to(cuda:j) from pinned host → 8 @op chain, op k of chain j on GPU "
                            "(j + k) mod N → y_j.cpu() into pinned host; ONE runtime in one process spans all N GPUs"),
                    "c_abi_only": e2e_cabi}
@@ -665,8 +665,9 @@ def api_bench(dev0: int, gpus, payload: int, shape, steps: int):
             torch.cuda.synchronize(g)
 
     phases = {"h2d": 0.0, "chain": 0.0, "d2h": 0.0}
+    marks = []  # chain 0 of every serial e2e step: CUDA events around its three legs, on the stream that carries them
 
-    def timed(k, from_host, duplex=False, collect=False):
+    def timed(k, from_host, duplex=False, collect=False, timeline=False):
         sync_all()
         t0 = time.perf_counter()
         outs = None
@@ -674,9 +675,14 @@ def api_bench(dev0: int, gpus, payload: int, shape, steps: int):
             if from_host:
                 p0 = time.perf_counter()
                 inputs = []
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timeline else None
                 for j, g in enumerate(gpus):
                     with torch.cuda.stream(streams[j]):
+                        if ev and j == 0:
+                            ev[0].record()
                         inputs.append(dev_in[j].copy_(host_in[j], non_blocking=True))
+                        if ev and j == 0:
+                            ev[1].record()
                 if collect:
                     sync_all()
                 p1 = time.perf_counter()
@@ -692,8 +698,17 @@ def api_bench(dev0: int, gpus, payload: int, shape, steps: int):
                             host_out[j].copy_(y, non_blocking=True)
                         y.record_stream(d2h_streams[gpus.index(ydev)])
                     else:
-                        with torch.cuda.stream(torch.cuda.current_stream(ydev)):
+                        # the D2H rides the stream the H2D of this GPU rides (never the legacy default stream, which would
+                        # fence every blocking stream of the device), ordered behind the stream the result was handed over on
+                        streams[gpus.index(ydev)].wait_stream(torch.cuda.current_stream(ydev))
+                        with torch.cuda.stream(streams[gpus.index(ydev)]):
+                            if ev and j == 0:
+                                ev[2].record()
                             host_out[j].copy_(y, non_blocking=True)
+                            if ev and j == 0:
+                                ev[3].record()
+                if ev:
+                    marks.append(ev)
                 if collect:
                     sync_all()
                     p3 = time.perf_counter()
@@ -713,7 +728,25 @@ def api_bench(dev0: int, gpus, payload: int, shape, steps: int):
     st = N.stats()
     stats = {k: st[k] // steps for k in ("kernel_launches", "push_launches", "frames_moved", "dma_copies", "pack_launches", "pull_launches")}
     timed(1, True)
-    ms_e2e, _ = timed(steps, True)
+    import gc
+    gc_log = []  # (generation, ms) of every collection inside the serial e2e leg
+
+    def gc_cb(phase, info, _t=[0.0]):
+        if phase == "start":
+            _t[0] = time.perf_counter()
+        else:
+            gc_log.append((info["generation"], round(1e3 * (time.perf_counter() - _t[0]), 2)))
+    gc.callbacks.append(gc_cb)
+    ms_e2e, _ = timed(steps, True, timeline=True)
+    gc.callbacks.remove(gc_cb)
+    tl = {"h2d": 0.0, "h2d_end_to_d2h_start": 0.0, "d2h": 0.0, "d2h_end_to_next_h2d": 0.0}
+    for i, ev in enumerate(marks):
+        tl["h2d"] += ev[0].elapsed_time(ev[1]) / len(marks)
+        tl["h2d_end_to_d2h_start"] += ev[1].elapsed_time(ev[2]) / len(marks)
+        tl["d2h"] += ev[2].elapsed_time(ev[3]) / len(marks)
+        if i:
+            tl["d2h_end_to_next_h2d"] += marks[i - 1][3].elapsed_time(ev[0]) / (len(marks) - 1)
+    mids = [round(ev[1].elapsed_time(ev[2]), 2) for ev in marks]
     for j in range(n):
         assert torch.equal(host_out[j], host_in[j]), "API e2e chain delivered different bytes"
     timed(2, True, collect=True)  # the same step with a device sync between its three legs: where the time goes
@@ -729,7 +762,8 @@ def api_bench(dev0: int, gpus, payload: int, shape, steps: int):
         print(f"[bench] duplex e2e leg skipped: {type(e).__name__}: {e}", file=sys.stderr, flush=True)
     rt.close()
     return {"ms_dev": ms_dev / steps, "ms_e2e": ms_e2e / steps, "ms_duplex": ms_duplex, "stats": stats,
-            "phases": {k: round(v, 3) for k, v in phases.items()}}
+            "phases": {k: round(v, 3) for k, v in phases.items()}, "timeline": {**{k: round(v, 3) for k, v in tl.items()}, "h2d_end_to_d2h_start_per_step": mids,
+                         "gc_collections_ms": [g for g in gc_log if g[1] >= 0.5]}}
 
 
 def run_single_config(args, ring):

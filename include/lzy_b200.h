@@ -326,6 +326,15 @@ int lzyb_set_push_min_bytes(uint64_t nbytes);
  * without waiting.  A runtime that keeps every reader stream-ordered (B200Runtime) turns it on so that an op's successor is
  * not held up by the op's pack kernel; Java-style blocking callers leave it off. */
 int lzyb_set_lazy_commit(int on);
+/* Pinned host blocks for the host side of small reads and writes (the consumer of a host-origin payload — an ndarray, a
+ * pickled object — reads it back out of HBM; into pageable memory that costs a staging copy and a page fault per 4 KiB).
+ * Blocks are pooled by power-of-two size (64 KiB … 16 MiB) and never shrink below what is handed out; lzyb_host_alloc
+ * returns LZYB_E_LOCAL once `limit` bytes (default 512 MiB, lzyb_set_host_pool_limit) are outstanding + pooled, or for a
+ * size outside the classes — the caller then uses ordinary memory.  lzyb_host_free of a pointer that is not an outstanding
+ * block is LZYB_E_ARG.  Blocks still outstanding at lzyb_shutdown stay valid (they are released when freed). */
+int lzyb_host_alloc(uint64_t nbytes, void** out);
+int lzyb_host_free(void* block);
+int lzyb_set_host_pool_limit(uint64_t bytes);
 /* sub-chunk schedule of a copy-engine pull: the last sub-chunk is last_bytes (0 = payload/32 clamped to
  * 4..32 MiB; else a multiple of 16, at least 1 MiB), each earlier one `growth` times larger (default 6; 1 =
  * uniform), the first takes the remainder */

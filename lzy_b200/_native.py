@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from pathlib import Path
 from typing import Optional, Sequence, Tuple
 
@@ -145,6 +146,9 @@ _SIGNATURES = {
     "lzyb_slot_meta": (C.c_int, [_H, C.POINTER(SlotInfo)]),
     "lzyb_slot_wait": (C.c_int, [_H, _P]),
     "lzyb_set_lazy_commit": (C.c_int, [C.c_int]),
+    "lzyb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "lzyb_host_free": (C.c_int, [C.c_void_p]),
+    "lzyb_set_host_pool_limit": (C.c_int, [C.c_uint64]),
     "lzyb_slot_header": (C.c_int, [_H, C.POINTER(FrameHeader)]),
     "lzyb_slot_close": (C.c_int, [_H]),
     "lzyb_slot_retain": (C.c_int, [_H]),
@@ -449,6 +453,27 @@ def set_copy_engine(engine: int) -> None:
 
 def set_lazy_commit(on: bool) -> None:
     check(lib.lzyb_set_lazy_commit(int(bool(on))))
+
+
+HOST_BLOCK_MIN, HOST_BLOCK_MAX = 64 << 10, 16 << 20
+
+
+def pinned_buffer(nbytes: int):
+    """A writable ctypes byte array over a pooled pinned host block (lzyb_host_alloc), returned to the pool when the last
+    reference to it — or to anything built on it, e.g. a numpy view — goes away; None when the pool declines (size outside
+    its classes, limit reached): the caller then uses ordinary memory."""
+    if not HOST_BLOCK_MIN <= nbytes <= HOST_BLOCK_MAX:
+        return None
+    p = C.c_void_p()
+    if lib.lzyb_host_alloc(nbytes, C.byref(p)) != OK:
+        return None
+    buf = (C.c_ubyte * nbytes).from_address(p.value)
+    weakref.finalize(buf, lib.lzyb_host_free, p.value)
+    return buf
+
+
+def set_host_pool_limit(nbytes: int) -> None:
+    check(lib.lzyb_set_host_pool_limit(nbytes))
 
 
 def set_push_min_bytes(nbytes: int) -> None:

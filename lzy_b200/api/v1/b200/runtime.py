@@ -158,7 +158,7 @@ class B200Runtime(Runtime):
         self._pool: Optional[ThreadPoolExecutor] = None
         self._rr = 0
         self.stats = {"ops": 0, "graphs": 0, "cached_ops": 0}
-        self.trace: Optional[list] = [] if os.environ.get("LZYB_TRACE") else None  # (task, phase, ms) records
+        self.trace: Optional[list] = [] if os.environ.get("LZYB_TRACE") else None  # (task, phase, ms, t) records
         tbpickle.install()
 
     # ---- bring-up ------------------------------------------------------------------------------------
@@ -517,14 +517,15 @@ class B200Runtime(Runtime):
 
     # ---- one op (WorkerApiImpl.executeOp + startup.process_execution) -------------------------------------
     def _phase_marker(self, task: int) -> Callable[[str], None]:
-        """LZYB_TRACE=1: (task, phase, ms since the previous mark) records in `self.trace`; otherwise a no-op"""
+        """LZYB_TRACE=1: (task, phase, ms since the previous mark, perf_counter at the mark) records in `self.trace`;
+        otherwise a no-op"""
         if self.trace is None:
             return lambda phase: None
         last = [time.perf_counter()]
 
         def mark(phase: str) -> None:
             now = time.perf_counter()
-            self.trace.append((task, phase, 1e3 * (now - last[0])))
+            self.trace.append((task, phase, 1e3 * (now - last[0]), now))
             last[0] = now
 
         return mark

@@ -39,6 +39,7 @@ static_assert(sizeof(lzyb_ipc_desc_t) == 256, "ipc descriptor must be 256 bytes"
 constexpr int CTL_SLAB = 8192;        // slots that can be live per device
 constexpr int MBOX_SLAB = 65536;      // mailboxes (pinned, all devices)
 constexpr int GRID_AUTO = -1000;      // lzyb_set_grid: let launch_stream pick the grid shape
+constexpr int HOST_CLASS_MIN_LOG2 = 16, HOST_CLASSES = 9;  // pinned host blocks: 64 KiB … 16 MiB
 constexpr uint64_t BOUNCE_BYTES = 4ull << 20;      // D2H reads of at most this into pageable memory go through a pinned bounce buffer
 constexpr uint64_t PUSH_MIN_DEFAULT = 4ull << 20;  // in-process GPU→GPU transfers at least this long are pushed from the source GPU (auto policy)
 // TMA ring shapes that can be selected at run time (lzyb_set_tma_config): {stages, stage bytes, CTAs per SM}
@@ -218,6 +219,12 @@ struct Global {
     std::atomic<int> dma_growth{6};            // each earlier sub-chunk is this many times larger
     std::atomic<uint64_t> push_min{PUSH_MIN_DEFAULT};
     std::atomic<int> lazy_commit{0};  // lzyb_set_lazy_commit
+    // pinned host blocks (lzyb_host_alloc): free lists by class, outstanding blocks by address
+    std::mutex host_mu;
+    std::vector<void*> host_free[HOST_CLASSES];
+    std::unordered_map<void*, int> host_out;
+    uint64_t host_bytes = 0;  // outstanding + pooled
+    uint64_t host_limit = 512ull << 20;
     std::atomic<uint64_t> st_push{0}, st_moves{0};
     std::atomic<uint64_t> next_push_seq{1};  // arrival words never repeat within this process
     // stats
@@ -732,6 +739,16 @@ int lzyb_shutdown(void) {
         cudaStreamDestroy(d->stream);
     }
     g.devs.clear();
+    {
+        std::lock_guard<std::mutex> lk(g.host_mu);
+        for (int c = 0; c < HOST_CLASSES; c++) {
+            for (void* p : g.host_free[c]) {
+                cudaFreeHost(p);
+                g.host_bytes -= 1ull << (HOST_CLASS_MIN_LOG2 + c);
+            }
+            g.host_free[c].clear();
+        }
+    }
     cudaFreeHost((void*)g.mbox_slab);
     cudaFreeHost(g.ring);
     g.mbox_slab = nullptr;
@@ -1065,6 +1082,53 @@ int lzyb_slot_wait(lzyb_handle_t h, void* stream) {
     } else if (s->last_stream != static_cast<cudaStream_t>(stream)) {
         CU(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), s->last_ev, 0));
     }
+    return LZYB_OK;
+}
+
+int lzyb_host_alloc(uint64_t nbytes, void** out) {
+    if (!out || !nbytes) return fail(LZYB_E_ARG, "null argument");
+    if (!g.inited) return fail(LZYB_E_STATE, "lzyb_init has not been called (or found no GPU)");
+    int c = 0;
+    while (c < HOST_CLASSES && (1ull << (HOST_CLASS_MIN_LOG2 + c)) < nbytes) c++;
+    if (c == HOST_CLASSES) return fail(LZYB_E_LOCAL, "no pinned block class for %llu bytes", (unsigned long long)nbytes);
+    uint64_t size = 1ull << (HOST_CLASS_MIN_LOG2 + c);
+    std::lock_guard<std::mutex> lk(g.host_mu);
+    void* p = nullptr;
+    if (!g.host_free[c].empty()) {
+        p = g.host_free[c].back();
+        g.host_free[c].pop_back();
+    } else {
+        if (g.host_bytes + size > g.host_limit)
+            return fail(LZYB_E_LOCAL, "pinned host pool limit reached (%llu bytes in use)", (unsigned long long)g.host_bytes);
+        if (cudaHostAlloc(&p, size, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(LZYB_E_LOCAL, "cudaHostAlloc of %llu bytes failed", (unsigned long long)size);
+        }
+        g.host_bytes += size;
+    }
+    g.host_out[p] = c;
+    *out = p;
+    return LZYB_OK;
+}
+
+int lzyb_host_free(void* block) {
+    std::lock_guard<std::mutex> lk(g.host_mu);
+    auto it = g.host_out.find(block);
+    if (it == g.host_out.end()) return fail(LZYB_E_ARG, "not an outstanding pinned block");
+    int c = it->second;
+    g.host_out.erase(it);
+    if (g.inited) {
+        g.host_free[c].push_back(block);
+    } else {  // the library was shut down while the caller still held the block
+        cudaFreeHost(block);
+        g.host_bytes -= 1ull << (HOST_CLASS_MIN_LOG2 + c);
+    }
+    return LZYB_OK;
+}
+
+int lzyb_set_host_pool_limit(uint64_t bytes) {
+    std::lock_guard<std::mutex> lk(g.host_mu);
+    g.host_limit = bytes;
     return LZYB_OK;
 }
 

@@ -149,8 +149,16 @@ def proxy(constructor: Callable[[], Any], proto_types: Sequence[Type], cls_attrs
             return object.__setattr__(self, item, value)
         return setattr(_resolve(type(self)), item, value)
 
+    def __del__(self):
+        # A class is cyclic garbage by construction (class ↔ __dict__ ↔ mro), so the state hanging off it — the value, the
+        # constructor's closure and whatever those pin: an HBM frame behind a tensor view, a pinned host block — would
+        # wait for the cycle collector.  The proxy instance is not part of a cycle and dies with its last reference:
+        # that is the moment to let go.  (Who asked for the value holds a reference of their own.)
+        type.__getattribute__(type(self), "_lzy_state").clear()
+
     ns["__getattribute__"] = __getattribute__
     ns["__setattr__"] = __setattr__
+    ns["__del__"] = __del__
     ns.update(cls_attrs)
     ns["_lzy_state"] = {"constructor": constructor}
     cls = _LazyMeta("LazyProxy", (object,), ns)

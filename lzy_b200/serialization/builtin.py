@@ -44,6 +44,15 @@ def _np_to_code():
             "uint16": N.DT_U16, "uint32": N.DT_U32, "uint64": N.DT_U64}
 
 
+_CODE_TO_NP: dict = {}
+
+
+def _code_to_np():
+    if not _CODE_TO_NP:
+        _CODE_TO_NP.update({v: k for k, v in _np_to_code().items()})
+    return _CODE_TO_NP
+
+
 _LOG = logging.getLogger(__name__)
 
 
@@ -224,11 +233,15 @@ class NdarrayFrameSerializer(DeviceFrameSerializer):
         slot._keepalive = a  # the H2D copy is asynchronous until commit()
 
     def unpack(self, slot, info, private: bool):
-        names = {v: k for k, v in _np_to_code().items()}
+        from .. import _native as N
         shape = tuple(int(info.shape[i]) for i in range(info.ndim))
-        out = np.empty(shape, dtype=names[int(info.dtype)])
-        if out.nbytes:
-            slot.copy_to_host(out.ctypes.data, out.nbytes)
+        dtype = np.dtype(_code_to_np()[int(info.dtype)])
+        nbytes = int(info.nbytes)
+        # a pooled pinned block as the array's memory: the D2H lands in it directly (no staging copy, no first-touch faults)
+        buf = N.pinned_buffer(nbytes) if nbytes else None
+        out = np.frombuffer(buf, dtype=dtype).reshape(shape) if buf is not None else np.empty(shape, dtype=dtype)
+        if nbytes:
+            slot.copy_to_host(out.ctypes.data, nbytes)
         return out
 
     def _serialize(self, obj, dest: BinaryIO) -> None:

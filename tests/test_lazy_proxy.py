@@ -238,3 +238,32 @@ def test_entry_proxies_obtain_their_value_as_the_reference_adapter_does():
                             is_lzy_proxy=adapter.is_lzy_proxy, get_proxy_entry_id=adapter.get_proxy_entry_id,
                             Result=Result, Absence=Absence))
     assert json.loads(json.dumps(ours)) == json.loads((golden / "reference_materialize_vectors.json").read_text())
+
+
+def test_a_dead_proxy_lets_go_of_its_value_without_the_cycle_collector():
+    """the proxy's class is cyclic garbage by construction; what it caches (a tensor view pinning an HBM frame, a pinned
+    host block) must not wait for the collector to find it"""
+    import gc
+    import weakref
+
+    class Payload:
+        pass
+
+    gc.disable()
+    try:
+        made = []
+
+        def build():
+            made.append(Payload())
+            return made[-1]
+
+        p = proxy(build, (Payload,))
+        value = p.__lzy_origin__
+        ref = weakref.ref(value)
+        made.clear()
+        del value
+        assert ref() is not None       # cached on the proxy while the proxy lives
+        del p
+        assert ref() is None           # gone with it — no gc.collect() in between
+    finally:
+        gc.enable()

@@ -40,7 +40,7 @@ def main():
     for _ in range(50):
         once()
     prof.disable()
-    pstats.Stats(prof).sort_stats("cumulative").print_stats(35)
+    pstats.Stats(prof).sort_stats(sys.argv[1] if len(sys.argv) > 1 else "cumulative").print_stats(45)
 
 
 if __name__ == "__main__":

@@ -17,20 +17,31 @@ def ident(t: torch.Tensor) -> torch.Tensor:
 
 
 def main():
-    rt = B200Runtime(gpus=[0], placement="single")
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1  # GPUs: n chains, op k of chain j on GPU (j + k) mod n
+    gpus = list(range(n))
+    rt = B200Runtime(gpus=gpus, placement="single" if n == 1 else "round_robin")
     lzy = Lzy(runtime=rt)
-    x = torch.empty(16384, 16384, device="cuda:0").normal_()
+    xs = [torch.empty(16384, 16384, device=f"cuda:{g}").normal_() for g in gpus]
+    chains = [[ident.with_provisioning(gpu_index=gpus[(j + k) % n]) if n > 1 else ident for k in range(8)] for j in range(n)]
+
+    def sync():
+        for g in gpus:
+            torch.cuda.synchronize(g)
+
     for it in range(6):
-        torch.cuda.synchronize()
+        sync()
         t0 = time.perf_counter()
         with lzy.workflow("p"):
             t1 = time.perf_counter()
-            y = x
-            for _ in range(8):
-                y = ident(y)
+            ys = []
+            for j in range(n):
+                y = xs[j]
+                for f in chains[j]:
+                    y = f(y)
+                ys.append(y)
             t2 = time.perf_counter()
-            out = materialize(y)
-            torch.cuda.synchronize()
+            out = [materialize(y) for y in ys]
+            sync()
             t3 = time.perf_counter()
         t4 = time.perf_counter()
         rt.clear()
@@ -38,9 +49,16 @@ def main():
         st = N.stats()
         if rt.trace is not None:
             agg = {}
-            for _t, ph, ms in rt.trace:
+            for _t, ph, ms, _at in rt.trace:
                 agg[ph] = agg.get(ph, 0.0) + ms
             print("   ", {k: round(v, 2) for k, v in agg.items()})
+            if it == 5 and n > 1:  # the last step as a timeline: when each op's phases ended, ms after the first mark
+                base = min(at - ms * 1e-3 for _t, _ph, ms, at in rt.trace)
+                per = {}
+                for t, ph, ms, at in rt.trace:
+                    per.setdefault(t, []).append(f"{ph[:6]} {ms:.2f}@{1e3 * (at - base):.2f}")
+                for t in sorted(per):
+                    print(f"      task {t:2d}: " + "  ".join(per[t]))
             rt.trace.clear()
         print(f"iter {it}: enter {1e3*(t1-t0):.2f} calls {1e3*(t2-t1):.2f} exec+materialize {1e3*(t3-t2):.2f} exit {1e3*(t4-t3):.2f} "
               f"clear {1e3*(t5-t4):.2f} ms | pooled {st['hbm_bytes_pooled']>>20} MiB live {st['hbm_bytes_live']>>20} MiB launches {st['kernel_launches']}")
