@@ -740,13 +740,17 @@ def api_bench(dev0: int, gpus, payload: int, shape, steps: int):
     ms_e2e, _ = timed(steps, True, timeline=True)
     gc.callbacks.remove(gc_cb)
     tl = {"h2d": 0.0, "h2d_end_to_d2h_start": 0.0, "d2h": 0.0, "d2h_end_to_next_h2d": 0.0}
+    one_gpu = (N_OPS - 1) % n == 0  # chain 0 ends on the GPU it entered on: its four events share a device
     for i, ev in enumerate(marks):
         tl["h2d"] += ev[0].elapsed_time(ev[1]) / len(marks)
-        tl["h2d_end_to_d2h_start"] += ev[1].elapsed_time(ev[2]) / len(marks)
         tl["d2h"] += ev[2].elapsed_time(ev[3]) / len(marks)
-        if i:
-            tl["d2h_end_to_next_h2d"] += marks[i - 1][3].elapsed_time(ev[0]) / (len(marks) - 1)
-    mids = [round(ev[1].elapsed_time(ev[2]), 2) for ev in marks]
+        if one_gpu:
+            tl["h2d_end_to_d2h_start"] += ev[1].elapsed_time(ev[2]) / len(marks)
+            if i:
+                tl["d2h_end_to_next_h2d"] += marks[i - 1][3].elapsed_time(ev[0]) / (len(marks) - 1)
+    mids = [round(ev[1].elapsed_time(ev[2]), 2) for ev in marks] if one_gpu else None
+    if not one_gpu:  # events of different devices cannot be subtracted
+        tl["h2d_end_to_d2h_start"] = tl["d2h_end_to_next_h2d"] = float("nan")
     for j in range(n):
         assert torch.equal(host_out[j], host_in[j]), "API e2e chain delivered different bytes"
     timed(2, True, collect=True)  # the same step with a device sync between its three legs: where the time goes
@@ -762,7 +766,7 @@ def api_bench(dev0: int, gpus, payload: int, shape, steps: int):
         print(f"[bench] duplex e2e leg skipped: {type(e).__name__}: {e}", file=sys.stderr, flush=True)
     rt.close()
     return {"ms_dev": ms_dev / steps, "ms_e2e": ms_e2e / steps, "ms_duplex": ms_duplex, "stats": stats,
-            "phases": {k: round(v, 3) for k, v in phases.items()}, "timeline": {**{k: round(v, 3) for k, v in tl.items()}, "h2d_end_to_d2h_start_per_step": mids,
+            "phases": {k: round(v, 3) for k, v in phases.items()}, "timeline": {**{k: round(v, 3) for k, v in tl.items() if v == v}, "h2d_end_to_d2h_start_per_step": mids,
                          "gc_collections_ms": [g for g in gc_log if g[1] >= 0.5]}}
 
 

@@ -191,6 +191,11 @@ int lzyb_slots_free(lzyb_handle_t slots);
 /* bytes per transferChunkTo call (0 = the whole remaining payload in one launch; the reference's
  * gRPC chunk is 2 MiB, OutputSlot.java:241) */
 int lzyb_slots_set_chunk_bytes(lzyb_handle_t slots, uint64_t chunk_bytes);
+/* the same for a transfer whose source frame is on ANOTHER GPU (or in another process), when chunk_bytes is 0.  A transfer
+ * kernel is a persistent grid: a kernel launched next to it on either GPU — an op's pack — waits for it to drain (measured,
+ * tools/overlap_probe.py: a 0.35 ms pack launched into a 1 GiB pull ends 1.2 ms later).  In slices the other kernel gets the
+ * GPU at the next slice boundary (0.5 ms with 128 MiB slices) for ≈ 8 % on the transfer itself.  0 (default) = one launch. */
+int lzyb_slots_set_peer_chunk_bytes(lzyb_handle_t slots, uint64_t chunk_bytes);
 /* Slots.context(requestId, executionId, taskId, slots, slotToChannelMapping) */
 int lzyb_ctx_create(lzyb_handle_t slots, const char* execution_id, const char* task_id, lzyb_handle_t* out);
 /* one LMS.Slot + its channel assignment (model/.../slot.proto:10-30, operation.proto:31-37) */

@@ -61,6 +61,7 @@ _SIGS = {
     "lzyb_slots_create": (_i, [_H, _i, _s, C.POINTER(_H)]),
     "lzyb_slots_free": (_i, [_H]),
     "lzyb_slots_set_chunk_bytes": (_i, [_H, C.c_uint64]),
+    "lzyb_slots_set_peer_chunk_bytes": (_i, [_H, C.c_uint64]),
     "lzyb_ctx_create": (_i, [_H, _s, _s, C.POINTER(_H)]),
     "lzyb_ctx_add_slot": (_i, [_H, _s, _s, _i]),
     "lzyb_ctx_add_slot_flags": (_i, [_H, _s, _s, _i, C.c_uint32]),
@@ -439,6 +440,10 @@ class Slots:
 
     def set_chunk_bytes(self, n: int) -> None:
         _check(lib.lzyb_slots_set_chunk_bytes(self.h, n))
+
+    def set_peer_chunk_bytes(self, n: int) -> None:
+        """slice size of transfers whose source is on another GPU (0 = one launch)"""
+        _check(lib.lzyb_slots_set_peer_chunk_bytes(self.h, n))
 
     def transfer_log(self, clear: bool = False) -> List[dict]:
         """one record per finished input transfer: bytes, ns, final peer, failovers, outcome"""

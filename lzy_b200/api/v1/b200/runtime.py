@@ -65,6 +65,8 @@ class B200RuntimeConfig:
     fanout_chunk_bytes: int = 0                  # 0 = device-chained kernel; > 0 = host-driven chain with that chunk size
     retain: str = "auto"                         # "auto": a frame is freed once no proxy / queued call can ask for it; "all": keep until clear()
     chunk_bytes: int = 0                         # 0 = one launch per transfer; the reference streams 2 MiB chunks
+    peer_chunk_bytes: int = 128 << 20            # slices of a cross-GPU transfer (more than one GPU only): an op's pack launched next to a
+                                                 # transfer gets the GPU at the next slice boundary instead of after the whole payload; 0 = off
     move_sole_consumer: bool = True              # an output with one consumer on the same GPU and no other reader is handed over, not copied
     lazy_commit: bool = True                     # an op's result is READY in stream order: its successor is not held up by the pack kernel
     copy_engine: str = "auto"                    # "auto" | "ldg" | "tma" | "dma" | "push"
@@ -103,7 +105,7 @@ class B200RuntimeConfig:
             if raw.lower() in ("0", "false", "no", "off"):
                 return False
             raise ValueError("expected a boolean")
-        if name in ("host_ring_bytes", "fanout_chunk_bytes", "chunk_bytes", "hbm_budget_bytes"):
+        if name in ("host_ring_bytes", "fanout_chunk_bytes", "chunk_bytes", "peer_chunk_bytes", "hbm_budget_bytes"):
             mult = {"k": 1 << 10, "m": 1 << 20, "g": 1 << 30}.get(raw[-1:].lower())
             return int(float(raw[:-1]) * mult) if mult else int(raw)
         if name in ("max_parallel_ops", "fanout_threshold"):
@@ -192,6 +194,8 @@ class B200Runtime(Runtime):
                 w.set_republish(self.config.republish_inputs)
                 if self.config.chunk_bytes:
                     w.set_chunk_bytes(self.config.chunk_bytes)
+                if self.config.peer_chunk_bytes and len(self.gpus) > 1:
+                    w.set_peer_chunk_bytes(self.config.peer_chunk_bytes)
                 self.workers[g] = w
                 self._streams[g] = torch.cuda.Stream(device=g)
             workers = self.config.max_parallel_ops or 2 * len(self.gpus)

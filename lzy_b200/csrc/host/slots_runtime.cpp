@@ -461,6 +461,7 @@ struct TransferRecord {
     std::string slot_id, channel_id, peer_id, error;
     int peer_kind = 0;
     uint64_t bytes = 0, ns = 0;
+    uint64_t ns_setup = 0, ns_issue = 0, ns_wait = 0, ns_complete = 0;  // of the last attempt: open, launch, verdict, TransferCompleted
     int failovers = 0;
     bool ok = false;
 };
@@ -478,6 +479,7 @@ struct SlotsInstance {
     int gpu = 0;
     std::string api_url;
     std::atomic<uint64_t> chunk_bytes{0};
+    std::atomic<uint64_t> peer_chunk_bytes{0};
     std::atomic<bool> republish{true};
     SlotsServiceImpl service;
     std::mutex mu;
@@ -647,6 +649,7 @@ struct InputTransfer {
     virtual int64_t transfer_chunk_to(lzyb_handle_t sink, uint64_t offset, uint64_t max_len) = 0;
     virtual int finish(lzyb_handle_t sink) = 0;
     virtual uint64_t nbytes() const = 0;
+    virtual bool crosses_gpus(int /*sink_gpu*/) const { return false; }  // the source frame is on another GPU / in another process
 };
 
 // SlotInputTransfer: consumer-pull from the peer's frame (same GPU: HBM; other GPU: NVLink)
@@ -654,6 +657,9 @@ struct SlotPullTransfer : InputTransfer {
     lzyb_handle_t peer = 0;
     uint64_t size = 0;
     bool retained = false;  // a frame-store frame may be evicted to the spill tier while we read it: hold it
+    int peer_gpu = -1;
+    bool peer_remote = false;
+    bool crosses_gpus(int sink_gpu) const override { return peer_remote || (peer_gpu >= 0 && peer_gpu != sink_gpu); }
     ~SlotPullTransfer() override {
         if (retained) ops().slot_close(peer);
     }
@@ -847,6 +853,8 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
         t->peer = h;
         t->retained = imported;  // the mapping belongs to this transfer: closed with it
         t->size = info.nbytes;
+        t->peer_gpu = info.gpu;
+        t->peer_remote = info.is_remote != 0;
         return t;
     }
 
@@ -936,6 +944,9 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
         std::string terr;
         rec.peer_id = cur.peer_id;
         rec.peer_kind = cur.kind;
+        using clk = std::chrono::steady_clock;
+        auto since = [](clk::time_point t) { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(clk::now() - t).count(); };
+        auto t_mark = clk::now();
         auto transfer = make_transfer(cur, terr);
         std::string peer_fail_reason = transfer ? "" : terr;
         bool need_new_peer = !transfer;
@@ -974,7 +985,12 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
             }
             lzyb_slot_info_t info;
             if (slot_sizes(backend, &info) == LZYB_OK) offset = info.delivered;  // reopening the channel: resume here
-            const uint64_t chunk = inst->chunk_bytes.load();
+            if (offset == 0) {
+                rec.ns_setup = since(t_mark);
+                t_mark = clk::now();
+            }
+            uint64_t chunk = inst->chunk_bytes.load();
+            if (!chunk && transfer->crosses_gpus(inst->gpu)) chunk = inst->peer_chunk_bytes.load();
             int64_t moved = transfer->transfer_chunk_to(backend, offset, chunk ? chunk : ~0ull);
             if (moved == LZYB_E_PEER) {  // ReadException: mark the peer bad, ask for another one
                 peer_fail_reason = lzyb_last_error();
@@ -986,7 +1002,11 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
                 return false;
             }
             if (moved == LZYB_EOF) {
+                rec.ns_issue = since(t_mark);
+                t_mark = clk::now();
                 int frc = transfer->finish(backend);
+                rec.ns_wait = since(t_mark);
+                t_mark = clk::now();
                 if (frc == LZYB_E_PEER) {  // delivered bytes are not what the producer committed
                     peer_fail_reason = lzyb_last_error();
                     need_new_peer = true;
@@ -1000,6 +1020,7 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
                     err = std::string("TransferCompleted failed: ") + lzyb_last_error();
                     return false;
                 }
+                rec.ns_complete = since(t_mark);
                 return true;
             }
             offset += (uint64_t)moved;
@@ -1278,6 +1299,14 @@ int lzyb_slots_set_chunk_bytes(lzyb_handle_t h, uint64_t chunk) {
     if (!s) return fail(LZYB_E_ARG, "unknown slots handle");
     if (chunk & 15) return fail(LZYB_E_ARG, "chunk size must be a multiple of 16");
     s->chunk_bytes = chunk;
+    return LZYB_OK;
+}
+
+int lzyb_slots_set_peer_chunk_bytes(lzyb_handle_t h, uint64_t chunk) {
+    auto s = get_inst(h);
+    if (!s) return fail(LZYB_E_ARG, "unknown slots handle");
+    if (chunk & 15) return fail(LZYB_E_ARG, "chunk size must be a multiple of 16");
+    s->peer_chunk_bytes = chunk;
     return LZYB_OK;
 }
 
@@ -1627,7 +1656,8 @@ int64_t lzyb_slots_transfer_log(lzyb_handle_t h, char* json_out, uint64_t cap, i
             os << ",\"peer_id\":";
             quote(r.peer_id);
             os << ",\"peer_kind\":\"" << (r.peer_kind == LZYB_PEER_STORAGE ? "storage" : "slot") << "\",\"bytes\":" << r.bytes
-               << ",\"ns\":" << r.ns << ",\"failovers\":" << r.failovers << ",\"ok\":" << (r.ok ? "true" : "false") << ",\"error\":";
+               << ",\"ns\":" << r.ns << ",\"ns_setup\":" << r.ns_setup << ",\"ns_issue\":" << r.ns_issue << ",\"ns_wait\":" << r.ns_wait
+               << ",\"ns_complete\":" << r.ns_complete << ",\"failovers\":" << r.failovers << ",\"ok\":" << (r.ok ? "true" : "false") << ",\"error\":";
             quote(r.error);
             os << '}';
         }

@@ -25,6 +25,7 @@ def load():
     lib.hostmem_write.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
     lib.hostmem_peek.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
     lib.hostmem_peek.restype = C.c_int64
+    lib.hostmem_moving_calls.restype = C.c_longlong
     lib.hostmem_size.argtypes = [C.c_uint64]
     lib.hostmem_size.restype = C.c_int64
     lib.hostmem_set_fail_after.argtypes = [C.c_uint64, C.c_longlong]

@@ -224,6 +224,7 @@ static int m_slot_retain(lzyb_handle_t h) {
     return s ? LZYB_OK : err(LZYB_E_ARG, "unknown slot handle");
 }
 
+static long long g_moving_calls = 0; /* transfer_chunk calls that moved bytes (tests count slices with it) */
 static int64_t m_transfer_chunk(lzyb_handle_t dh, lzyb_handle_t sh, uint64_t off, uint64_t max_len, void* stream) {
     (void)stream;
     pthread_mutex_lock(&g_mu);
@@ -250,6 +251,7 @@ static int64_t m_transfer_chunk(lzyb_handle_t dh, lzyb_handle_t sh, uint64_t off
             if ((long long)(off + len) > s->fail_after) len = (uint64_t)(s->fail_after - (long long)off);
         }
         memcpy(d->data + off, s->data + off, len);
+        g_moving_calls++;
         d->delivered += len;
         d->state = LZYB_ST_FILLING;
         rc = (int64_t)len;
@@ -494,6 +496,12 @@ int hostmem_corrupt(lzyb_handle_t h, uint64_t off) {
     }
     pthread_mutex_unlock(&g_mu);
     return rc;
+}
+long long hostmem_moving_calls(void) {
+    pthread_mutex_lock(&g_mu);
+    long long n = g_moving_calls;
+    pthread_mutex_unlock(&g_mu);
+    return n;
 }
 int hostmem_live_slots(void) {
     int n = 0;

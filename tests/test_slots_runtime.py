@@ -479,3 +479,42 @@ def test_slot_threads_are_recycled(env):
     H.frame_store_clear("hbm://recycle/")
     assert max(seen[50:]) <= max(seen[:50]) + 2, f"thread count keeps growing: {seen[:5]} … {seen[-5:]}"
     assert H.lib.lzyb_slots_threads_spawned() - spawned_before <= 8, "300 slots ran on a handful of threads"
+
+
+def test_cross_gpu_transfers_go_in_slices_same_gpu_ones_do_not():
+    """lzyb_slots_set_peer_chunk_bytes: a transfer whose source frame is on another GPU is issued in slices (so that a
+    kernel launched next to it gets the GPU at a slice boundary); a same-GPU transfer stays one call — it may be a
+    hand-over of the whole frame, which only a whole-payload call can be"""
+    lib = hostmem.install()
+    cm = ChannelManager(seed=5)
+    H.pump_start(cm)
+    w0, w1 = Slots(cm, 0, "lzyb://worker-0"), Slots(cm, 1, "lzyb://worker-1")
+    try:
+        for w in (w0, w1):
+            w.set_peer_chunk_bytes(256 << 10)
+        data = os.urandom(1 << 20)
+        for tag, consumer, want_calls in (("far", w1, 4), ("near", w0, 1)):
+            chan = cm.get_or_create("u", "wf", f"exec-{tag}", consumer_uri=f"mem://slices-{tag}")
+            out = w0.context(f"exec-{tag}", "a")
+            out.add_slot("o", chan, DIR_OUTPUT)
+            out.before_execution()
+            produce(out, "o", data)
+            out.after_execution(5000)
+            before = lib.hostmem_moving_calls()
+            inp = consumer.context(f"exec-{tag}", "b")
+            inp.add_slot("i", chan, DIR_INPUT)
+            inp.before_execution(5000)
+            assert hostmem.peek(inp.input_handle("i"), len(data)) == data
+            assert lib.hostmem_moving_calls() - before == want_calls, tag
+            rec = [r for r in consumer.transfer_log(clear=True) if r["slot_id"] == "i"][-1]
+            assert rec["ok"] and rec["bytes"] == len(data) and rec["ns_issue"] > 0
+            inp.close()
+            out.close()
+            H.blob_delete(f"mem://slices-{tag}")
+    finally:
+        w0.close()
+        w1.close()
+        H.pump_stop(cm)
+        cm.close()
+        hostmem.uninstall()
+    assert lib.hostmem_live_slots() == 0
