@@ -487,6 +487,7 @@ class B200Runtime(Runtime):
             if graph.status != H.G_COMPLETED:
                 raise LzyExecutionException("graph did not complete")
         finally:
+            mark = self._phase_marker(-1)
             for f in fanout.values():
                 if not f.future.done():
                     f.future.set_exception(LzyExecutionException("graph stopped before the fan-out ran"))
@@ -494,6 +495,7 @@ class B200Runtime(Runtime):
                     sl.close()
             for ctx in ctxs:
                 ctx.close()
+            mark("contexts closed")
             graph.close()
             if hasattr(snapshot, "unpin"):
                 for i in range(len(calls)):
@@ -502,6 +504,7 @@ class B200Runtime(Runtime):
                 for c in calls:
                     for eid in list(c.arg_entry_ids) + list(c.kwarg_entry_ids.values()):
                         snapshot.unpin(eid)
+            mark("entries released")
 
     def _do_fanout(self, f: _Fanout) -> None:
         try:
