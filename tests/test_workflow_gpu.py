@@ -549,7 +549,7 @@ def test_ndarray_and_cpu_tensor_round_trip(lzy, workflow_name):
         y = ident(ident(x))
         u = cpu_ident(t)
     assert isinstance(materialize(y), np.ndarray) and y.dtype == np.float32 and np.array_equal(y, x)
-    assert torch.equal(u, t)
+    assert torch.equal(u.to(t.device), t)  # on a multi-GPU box the op may sit on another GPU
 
 
 def test_non_contiguous_tensor_and_mixed_payload(lzy, workflow_name):
@@ -561,7 +561,7 @@ def test_non_contiguous_tensor_and_mixed_payload(lzy, workflow_name):
     view = m[:, 32:160]  # row-pitched view → the 2-D gather pack kernel
     with lzy.workflow(workflow_name):
         s, txt = column_sum(view, {"k": 7})
-    assert torch.equal(s, view.sum(dim=0)) and "rows=64 k=7" == txt
+    assert torch.equal(s.to(view.device), view.sum(dim=0)) and "rows=64 k=7" == txt
 
 
 def test_diamond_graph_runs_and_failure_stops_it(lzy, workflow_name):

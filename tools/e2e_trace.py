@@ -48,60 +48,91 @@ def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     if len(sys.argv) > 2 and sys.argv[2] == "nogc":
         gc.disable()
+    n = int(sys.argv[3]) if len(sys.argv) > 3 else 1  # GPUs: n chains, op k of chain j on GPU (j + k) mod n
+    gpus = list(range(n))
     shape = (16384, 16384)
-    rt = B200Runtime(gpus=[0], placement="single")
+    rt = B200Runtime(gpus=gpus, placement="single" if n == 1 else "round_robin")
     lzy = Lzy(runtime=rt)
-    stream = torch.cuda.Stream(0)
-    torch.cuda.set_stream(stream)
-    x = torch.empty(shape, device="cuda:0").normal_()
-    host_in = numa.pinned_empty(shape, torch.float32, 0).copy_(x)
-    host_out = numa.pinned_empty(shape, torch.float32, 0)
-    dev_in = torch.empty_like(x)
+    streams = [torch.cuda.Stream(g) for g in gpus]
+    torch.cuda.set_stream(streams[0])
+    xs = [torch.empty(shape, device=f"cuda:{g}").normal_() for g in gpus]
+    host_in = [numa.pinned_empty(shape, torch.float32, g).copy_(xs[g]) for g in gpus]
+    host_out = [numa.pinned_empty(shape, torch.float32, g) for g in gpus]
+    dev_in = [torch.empty_like(x) for x in xs]
+    chains = [[ident.with_provisioning(gpu_index=gpus[(j + k) % n]) if n > 1 else ident for k in range(8)] for j in range(n)]
 
-    def step(inp):
+    def step(inputs):
         t0 = time.perf_counter()
         with lzy.workflow("p"):
-            y = inp
-            for _ in range(8):
-                y = ident(y)
+            ys = []
+            for j, inp in enumerate(inputs):
+                y = inp
+                for f in chains[j]:
+                    y = f(y)
+                ys.append(y)
             t1 = time.perf_counter()
-            out = materialize(y)
+            outs = [materialize(y) for y in ys]
             t2 = time.perf_counter()
         t3 = time.perf_counter()
         rt.clear()
         acc["calls"] += t1 - t0
         acc["materialize"] += t2 - t1
         acc["wf exit"] += t3 - t2
-        return out
+        return outs
+
+    def sync():
+        for g in gpus:
+            torch.cuda.synchronize(g)
+
+    def one(ev=None):
+        inputs = []
+        for j, g in enumerate(gpus):
+            with torch.cuda.stream(streams[j]):
+                if ev:
+                    ev[j][0].record()
+                inputs.append(dev_in[j].copy_(host_in[j], non_blocking=True))
+                if ev:
+                    ev[j][1].record()
+        outs = step(inputs)
+        for j, y in enumerate(outs):
+            d = y.device.index
+            streams[d].wait_stream(torch.cuda.current_stream(d))
+            with torch.cuda.stream(streams[d]):
+                if ev:
+                    ev[d][2].record()
+                host_out[j].copy_(y, non_blocking=True)
+                if ev:
+                    ev[d][3].record()
 
     for _ in range(2):
-        dev_in.copy_(host_in, non_blocking=True)
-        host_out.copy_(step(dev_in), non_blocking=True)
-    torch.cuda.synchronize()
+        one()
+    sync()
+    # one reference event per GPU, recorded back to back: the time axes of the devices agree to within the issue jitter
+    refs = []
+    for j, g in enumerate(gpus):
+        with torch.cuda.stream(streams[j]):
+            r = torch.cuda.Event(enable_timing=True)
+            r.record()
+            refs.append(r)
     rows = []
     t_begin = time.perf_counter()
     for _ in range(iters):
         acc.clear()
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        g0 = gc.get_count()
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in gpus]
         h0 = time.perf_counter()
-        e[0].record()
-        dev_in.copy_(host_in, non_blocking=True)
-        e[1].record()
-        y = step(dev_in)
-        e[2].record()
-        host_out.copy_(y, non_blocking=True)
-        e[3].record()
-        rows.append((e, time.perf_counter() - h0, dict(acc), g0))
-    torch.cuda.synchronize()
+        one(ev)
+        rows.append((ev, time.perf_counter() - h0, dict(acc), 1e3 * (h0 - t_begin)))
+    sync()
     total = time.perf_counter() - t_begin
-    print(f"{1e3 * total / iters:.2f} ms per step over {iters} steps, gc {'on' if gc.isenabled() else 'off'}")
-    for i, (e, host, a, g0) in enumerate(rows):
-        gap = rows[i - 1][0][3].elapsed_time(e[0]) if i else 0.0
+    print(f"{1e3 * total / iters:.2f} ms per step over {iters} steps on {n} GPU(s), gc {'on' if gc.isenabled() else 'off'}")
+    for i, (ev, host, a, h_at) in enumerate(rows):
         parts = "  ".join(f"{k} {1e3 * v:.2f}" for k, v in a.items())
-        print(f"  {i}: gpu gap {gap:.2f} h2d {e[0].elapsed_time(e[1]):.2f} mid {e[1].elapsed_time(e[2]):.2f} d2h {e[2].elapsed_time(e[3]):.2f}"
-              f" | host {1e3 * host:.2f}: {parts} | gc counts {g0}")
-    assert torch.equal(host_out, host_in)
+        print(f"  step {i} issued @{h_at:.2f} | host {1e3 * host:.2f}: {parts}")
+        for j in range(n):
+            t = [refs[j].elapsed_time(e) for e in ev[j]]
+            print(f"      gpu{j}: h2d {t[0]:.2f} → {t[1]:.2f}   d2h {t[2]:.2f} → {t[3]:.2f}")
+    for j in range(n):
+        assert torch.equal(host_out[j], host_in[j])
     rt.close()
 
 
