@@ -537,11 +537,21 @@ def run_ours(args):
     # ---- from here on rank 0 works alone (one runtime over all GPUs); the others wait on the host ----------------------
     torch.cuda.synchronize()
     ring.host_barrier()
+    if rank != 0:
+        # Leave: the rest is one process driving every GPU.  A second process with a CUDA context on a GPU — even an idle one —
+        # makes the launches of the first one there slower (time-slicing between contexts): the API step measured
+        # 60 ms with rank 0 alone on the box and 74 ms with rank 1 parked on GPU 1.
+        if ring.box is not None:
+            ring.box.close()
+        N.shutdown()
+        ring.dist.destroy_process_group()
+        return
     api, e2e, cpu = None, e2e_cabi, None
     if rank == 0:
         gpus = list(range(world))
         if multi:
             N.shutdown()  # this process managed GPU 0 only; the runtime below manages all N
+            wait_until_alone(gpus)
         if not args.no_e2e:
             api_steps = max(3, min(args.steps, 10))
             rec = api_bench(dev, gpus, payload, ring.shape, api_steps)
@@ -581,7 +591,6 @@ def run_ours(args):
             cpu = {"value": n_ops * payload / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": cpu_sample_text(payload, n_ops) + f"; one pass, {dt:.1f} s", "sample_ops_per_step": n_ops,
                    "host_cores": os.cpu_count()}
-    ring.host_barrier()
 
     if rank == 0:
         print(json.dumps({
@@ -602,6 +611,22 @@ def run_ours(args):
         ring.box.close()
     if multi:
         ring.dist.destroy_process_group()
+
+
+def wait_until_alone(gpus, timeout_s: float = 15.0) -> None:
+    """the other ranks are exiting: give their CUDA contexts time to disappear from the GPUs (NVML's process list), at most
+    `timeout_s`; without NVML just a short pause"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handles = [pynvml.nvmlDeviceGetHandleByIndex(g) for g in gpus]
+        deadline = time.time() + timeout_s
+        while time.time() < deadline:
+            if all(len(pynvml.nvmlDeviceGetComputeRunningProcesses(h)) <= 1 for h in handles):
+                return
+            time.sleep(0.1)
+    except Exception:
+        time.sleep(3.0)
 
 
 def api_bench(dev0: int, gpus, payload: int, shape, steps: int):

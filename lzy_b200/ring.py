@@ -72,6 +72,14 @@ class ShmMailbox:
         self._shm = shared_memory.SharedMemory(name=name, create=create, size=size if create else 0)
         if create:
             self._shm.buf[:size] = bytes(size)
+        else:
+            # attaching registers the segment with this process's resource tracker as if it were ours (bpo-39959): it would
+            # unlink the creator's segment — or complain that it is gone — when this process exits
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
         self._buf = self._shm.buf
         self._posted = [0] * lanes                            # sequence of my last post per lane
         self._seen = [[0] * lanes for _ in range(world)]      # last sequence consumed per (rank, lane)
