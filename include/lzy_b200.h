@@ -326,6 +326,11 @@ int lzyb_set_push_min_bytes(uint64_t nbytes);
  * without waiting.  A runtime that keeps every reader stream-ordered (B200Runtime) turns it on so that an op's successor is
  * not held up by the op's pack kernel; Java-style blocking callers leave it off. */
 int lzyb_set_lazy_commit(int on);
+/* Grid of a cross-GPU TMA-ring transfer (pull or push): `waves` × the resident CTA count, each CTA carrying 1/waves of the
+ * tiles.  1 (default): a persistent grid — nothing else runs on that GPU until the transfer has drained (a 0.35 ms pack
+ * launched into a 1 GiB pull ends 1.2 ms later, tools/overlap_probe.py).  > 1: CTAs retire all along the transfer and a kernel
+ * on a higher-priority stream gets their SMs. */
+int lzyb_set_transfer_waves(int waves);
 /* Pinned host blocks for the host side of small reads and writes (the consumer of a host-origin payload — an ndarray, a
  * pickled object — reads it back out of HBM; into pageable memory that costs a staging copy and a page fault per 4 KiB).
  * Blocks are pooled by power-of-two size (64 KiB … 16 MiB) and never shrink below what is handed out; lzyb_host_alloc

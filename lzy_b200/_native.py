@@ -146,6 +146,7 @@ _SIGNATURES = {
     "lzyb_slot_meta": (C.c_int, [_H, C.POINTER(SlotInfo)]),
     "lzyb_slot_wait": (C.c_int, [_H, _P]),
     "lzyb_set_lazy_commit": (C.c_int, [C.c_int]),
+    "lzyb_set_transfer_waves": (C.c_int, [C.c_int]),
     "lzyb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
     "lzyb_host_free": (C.c_int, [C.c_void_p]),
     "lzyb_set_host_pool_limit": (C.c_int, [C.c_uint64]),
@@ -449,6 +450,10 @@ def fill_pattern(gpu: int, dptr: int, nbytes: int, seed: int, stream: int = 0) -
 
 def set_copy_engine(engine: int) -> None:
     check(lib.lzyb_set_copy_engine(engine))
+
+
+def set_transfer_waves(waves: int) -> None:
+    check(lib.lzyb_set_transfer_waves(int(waves)))
 
 
 def set_lazy_commit(on: bool) -> None:

@@ -219,6 +219,7 @@ struct Global {
     std::atomic<int> dma_growth{6};            // each earlier sub-chunk is this many times larger
     std::atomic<uint64_t> push_min{PUSH_MIN_DEFAULT};
     std::atomic<int> lazy_commit{0};  // lzyb_set_lazy_commit
+    std::atomic<int> tma_waves{1};    // lzyb_set_transfer_waves
     // pinned host blocks (lzyb_host_alloc): free lists by class, outstanding blocks by address
     std::mutex host_mu;
     std::vector<void*> host_free[HOST_CLASSES];
@@ -350,7 +351,9 @@ int launch_stream(DeviceCtx& d, const CopyParams& p, bool store, cudaStream_t st
         const int ci = g.tma_cfg.load();
         const TmaCfg cfg = kTmaCfgs[ci];
         uint64_t tiles = p.nbytes / cfg.stage_bytes;
-        int grid = d.sm_count * cfg.ctas_per_sm;
+        // waves > 1: more CTAs than are resident at once, each with 1/waves of the tiles — CTAs retire all along the transfer,
+        // so a kernel on a higher-priority stream (an op's pack) gets SMs within a CTA's lifetime instead of the transfer's
+        int grid = d.sm_count * cfg.ctas_per_sm * (peer ? g.tma_waves.load() : 1);
         if (g_debug_flags.load() & 2) grid = 4;  // stress: few CTAs, each cycling its ring thousands of times
         if ((uint64_t)grid > tiles) grid = (int)(tiles ? tiles : 1);
         switch (ci) {
@@ -1129,6 +1132,12 @@ int lzyb_host_free(void* block) {
 int lzyb_set_host_pool_limit(uint64_t bytes) {
     std::lock_guard<std::mutex> lk(g.host_mu);
     g.host_limit = bytes;
+    return LZYB_OK;
+}
+
+int lzyb_set_transfer_waves(int waves) {
+    if (waves < 1 || waves > 64) return fail(LZYB_E_ARG, "waves must be in [1, 64]");
+    g.tma_waves = waves;
     return LZYB_OK;
 }
 

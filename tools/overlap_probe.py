@@ -80,6 +80,15 @@ def main():
                 pull, pack, span = run(engine, k, st, 0.4)
                 print(json.dumps({"case": "pack launched 0.4 ms into the pull", "engine": engine, "pull_sublaunches": k, "pack_stream": name,
                                   "pull_ms": pull, "pack_wait_plus_run_ms": pack, "pull_start_to_pack_end_ms": span}), flush=True)
+    # the TMA ring as a grid of several waves (CTAs retire all along the transfer) with the pack on a high-priority stream
+    for waves in (2, 4, 8, 16):
+        N.set_transfer_waves(waves)
+        alone = run("tma", 1, None, 0)[0]
+        for name, st in (("same priority", s_lo), ("high priority", s_hi)):
+            pull, pack, span = run("tma", 1, st, 0.4)
+            print(json.dumps({"case": "pack launched 0.4 ms into the pull", "engine": "tma", "waves": waves, "pack_stream": name,
+                              "pull_alone_ms": alone, "pull_ms": pull, "pack_wait_plus_run_ms": pack, "pull_start_to_pack_end_ms": span}), flush=True)
+    N.set_transfer_waves(1)
     N.set_copy_engine(N.ENGINE_AUTO)
     src.close()
 
