@@ -341,7 +341,6 @@ def worker_processes_chain(gpus: List[int], mib: int = 256, n_ops: int = 8, reps
     from lzy_b200.api.v1.startup import ProcessingRequest
     from lzy_b200.api.v1.utils.pickle import pickle
     from lzy_b200.grpc_api import ChannelManagerPrivateClient, LongRunningClient, WorkerApiClient, messages as M
-    from lzy_b200.grpc_api.protos import GetOperationRequest
     root = Path(__file__).resolve().parent
     n_elem = (mib << 20) // 4
 
@@ -400,12 +399,10 @@ def worker_processes_chain(gpus: List[int], mib: int = 256, n_ops: int = 8, reps
                 for name, chan in assign.items():
                     req.task_desc.slot_assignments.add(slot_name=name, channel_id=chan)
                 op_msg = wapi.call("Execute", req)
-                deadline = time.time() + 300
-                while not op_msg.done:
-                    if time.time() > deadline:
-                        raise TimeoutError(task_id)
-                    time.sleep(0.0005)
-                    op_msg = ops.call("Get", GetOperationRequest(operation_id=op_msg.id))
+                if not op_msg.done:
+                    # one Get, answered by the worker when the task completes (`lzyb-wait-ms`, grpc_api/server.py): polling
+                    # every 0.5 ms took the task's own interpreter ≈ 0.3 ms per poll (tools/worker_chain_cpu.py)
+                    op_msg = ops.wait(op_msg.id, timeout=300.0)
                 resp = M.ExecuteResponse()
                 assert op_msg.WhichOneof("result") == "response" and op_msg.response.Unpack(resp)
                 if resp.rc != 0:
@@ -436,7 +433,7 @@ def worker_processes_chain(gpus: List[int], mib: int = 256, n_ops: int = 8, reps
         t = _median(ts)
         return {"config": "C2 on worker processes", "gpus": len(gpus), "processes": len(gpus) + 1, "payload_mib": mib, "ops": n_ops,
                 "wall_ms": t * 1e3, "ops_per_sec": n_ops / t, "edge_GBps": n_ops * (mib << 20) / t / 1e9, "bit_exact": True,
-                "wire": "WorkerApi.Init/Execute + LongRunningService.Get + LzyChannelManager(Private) + LzybPeerApi.Describe over gRPC; "
+                "wire": "WorkerApi.Init/Execute + LongRunningService.Get (answered on completion: lzyb-wait-ms) + LzyChannelManager(Private) + LzybPeerApi.Describe over gRPC; "
                         "payload over NVLink through CUDA IPC (consumer pull, TMA ring, digest verified on landing)"}
     finally:
         for wapi, ops in clients.values():

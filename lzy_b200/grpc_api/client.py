@@ -1,11 +1,16 @@
 """Thin blocking clients for the kept gRPC surface (what the reference's generated stubs do)."""
 from __future__ import annotations
 
+import os
+import sys
+import time
 from typing import Optional
 
 import grpc
 
 from .protos import SERVICES, method_types
+
+_TRACE = bool(os.environ.get("LZYB_TRACE"))
 
 
 class _Client:
@@ -20,9 +25,18 @@ class _Client:
             setattr(self, "_" + method, mk(f"/{self.SERVICE}/{method}", request_serializer=req_cls.SerializeToString,
                                            response_deserializer=resp_cls.FromString))
 
-    def call(self, method: str, request, idempotency_key: Optional[str] = None, timeout: float = 30.0):
+    def call(self, method: str, request, idempotency_key: Optional[str] = None, timeout: float = 30.0,
+             metadata: Optional[tuple] = None):
         md = (("idempotency-key", idempotency_key),) if idempotency_key else None
-        return getattr(self, "_" + method)(request, metadata=md, timeout=timeout)
+        if metadata:
+            md = (md or ()) + tuple(metadata)
+        if not _TRACE:
+            return getattr(self, "_" + method)(request, metadata=md, timeout=timeout)
+        t0 = time.perf_counter()  # LZYB_TRACE=1: one stderr line per outgoing call (next to the worker's phase lines)
+        try:
+            return getattr(self, "_" + method)(request, metadata=md, timeout=timeout)
+        finally:
+            print(f"LZYB_TRACE rpc={method} ms={1e3 * (time.perf_counter() - t0):.3f} t={t0:.6f}", file=sys.stderr, flush=True)
 
     def close(self):
         self.channel.close()
@@ -60,6 +74,23 @@ class WorkerApiClient(_Client):
 
 class LongRunningClient(_Client):
     SERVICE = "ai.lzy.v1.longrunning.LongRunningService"
+
+    def wait(self, operation_id: str, timeout: float = 300.0, slice_ms: int = 1000):
+        """the operation once it is done: ``Get`` with the ``lzyb-wait-ms`` header, which this repository's workers answer
+        when the operation completes (a server that ignores the header answers at once: then this is a poll with a
+        short sleep, as against the reference's operation service)"""
+        from .protos import GetOperationRequest
+        deadline = time.monotonic() + timeout
+        req = GetOperationRequest(operation_id=operation_id)
+        while True:
+            t0 = time.monotonic()
+            op = self.call("Get", req, timeout=slice_ms * 1e-3 + 10.0, metadata=(("lzyb-wait-ms", str(slice_ms)),))
+            if op.done:
+                return op
+            if time.monotonic() > deadline:
+                raise TimeoutError(f"operation {operation_id} still running after {timeout} s")
+            if time.monotonic() - t0 < 1e-3:  # the header was not honoured
+                time.sleep(5e-4)
 
 
 class PeerApiClient(_Client):

@@ -14,6 +14,7 @@ from .. import _native as N
 from .protos import SERVICES, DescribeResponse, LongRunningOperation, messages, method_types
 
 READ_CHUNK = 2 << 20  # OutputSlot.java:241
+WAIT_HEADER = "lzyb-wait-ms"  # LongRunningService.Get: hold the answer until the operation is done (at most that long)
 _STATUS = {N.E_NOT_FOUND: grpc.StatusCode.NOT_FOUND, N.E_PRECONDITION: grpc.StatusCode.FAILED_PRECONDITION,
            N.E_UNAVAILABLE: grpc.StatusCode.UNAVAILABLE, N.E_INTERNAL: grpc.StatusCode.INTERNAL,
            N.E_UNIMPLEMENTED: grpc.StatusCode.UNIMPLEMENTED, N.E_INVALID: grpc.StatusCode.INVALID_ARGUMENT,
@@ -255,8 +256,23 @@ class LongRunningService:
         self.worker = worker
 
     def Get(self, request, context):
+        """Answers at once, as the reference's operation service does — unless the caller sent ``lzyb-wait-ms: <n>``: then an
+        operation that is still running is answered when it completes, or as it stands after n ms (never past the call's own
+        deadline).  A driver on the same box gets the completion the moment it happens without polling the worker's
+        interpreter every fraction of a millisecond (tools/worker_chain_cpu.py: each poll costs the running task ≈ 0.3 ms)."""
         from ..worker import WorkerStatusError
+        wait_ms = 0.0
+        for k, v in context.invocation_metadata() or ():
+            if k.lower() == WAIT_HEADER:
+                try:
+                    wait_ms = max(0.0, min(float(v), 60_000.0))
+                except ValueError:
+                    context.abort(grpc.StatusCode.INVALID_ARGUMENT, f"{WAIT_HEADER}: not a number: {v!r}")
         try:
+            if wait_ms > 0:
+                left = context.time_remaining()
+                budget = wait_ms * 1e-3 if left is None else max(0.0, min(wait_ms * 1e-3, left - 0.05))
+                return _operation_to_proto(self.worker.wait_operation(request.operation_id, budget))
             return _operation_to_proto(self.worker.get_operation(request.operation_id))
         except WorkerStatusError as e:
             _worker_abort(context, e)

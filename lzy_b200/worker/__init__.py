@@ -25,6 +25,7 @@ from __future__ import annotations
 import contextlib
 import dataclasses
 import logging
+import os
 import sys
 import threading
 import time
@@ -114,6 +115,21 @@ def _env_vars(spec: Any) -> Dict[str, str]:
     return dict(inner) if inner is not None and not callable(inner) else dict(spec) if isinstance(spec, Mapping) else {}
 
 
+def _phase_marker(task_id: str) -> Callable[[str], None]:
+    """LZYB_TRACE=1: one stderr line per staging phase of a task (milliseconds since the previous mark) — where a task's
+    wall time goes between Execute and its response; otherwise a no-op"""
+    if not os.environ.get("LZYB_TRACE"):
+        return lambda phase: None
+    last = [time.perf_counter()]
+
+    def mark(phase: str) -> None:
+        now = time.perf_counter()
+        print(f"LZYB_TRACE task={task_id} phase={phase!r} ms={1e3 * (now - last[0]):.3f}", file=sys.stderr, flush=True)
+        last[0] = now
+
+    return mark
+
+
 def run_startup_in_process(command: str, ctx: H.ExecutionContext, worker: "Worker") -> int:
     """The command a pylzy client builds is ``python -u <startup.py> <pickled request>``
     (remote/runtime.py:375-381); the request is its last token.  Exit code as a Python process would report
@@ -144,6 +160,7 @@ class Worker:
                  command_runner: Optional[CommandRunner] = None, vm_id: str = ""):
         self.cm, self.gpu, self.api_url, self.vm_id = cm, gpu, api_url, vm_id or f"vm-{uuid.uuid4().hex[:8]}"
         self._lock = threading.RLock()
+        self._done = threading.Condition(self._lock)  # notified whenever an operation completes
         self._owner: Optional[Tuple[str, str]] = None
         self.slots: Optional[H.Slots] = None  # exists only after Init (WorkerApiImpl.java:255-264)
         self._active = threading.Event()      # hasActiveExecution
@@ -227,9 +244,13 @@ class Worker:
             result = self.execute_op(task)
             with self._lock:
                 op.response, op.done, op.modified_at = result, True, time.time()
+                self._active.clear()
+                self._done.notify_all()
         except BaseException as e:  # LocalOperationService turns an escaped error into the operation's error
             with self._lock:
                 op.error, op.done, op.modified_at = (13, f"{type(e).__name__}: {e}"), True, time.time()
+                self._active.clear()
+                self._done.notify_all()
         finally:
             self._active.clear()
 
@@ -250,19 +271,24 @@ class Worker:
             return ExecuteResult(ReturnCodes.INTERNAL_ERROR, "Internal error")
         _LOG.info("Executing task...")
         assert self.slots is not None
+        mark = _phase_marker(task.task_id)
         try:
             ctx = self.slots.context(task.execution_id, task.task_id)
             with self._lock:
                 self._contexts.setdefault(task.execution_id, []).append(ctx)
             for slot in task.slots:
                 ctx.add_slot(slot.name, task.slot_assignments[slot.name], slot.direction)
+            mark("slots added")
             _LOG.info("Waiting for slots...")
             ctx.before_execution(-1)
+            mark("before_execution")
             with applied_env(_env_vars(task.env)):  # Operation.env.env: the variables the op asked for
                 rc = self.command_runner(task.command, ctx, self)
+            mark("command")
             if rc == 0:
                 message = "Success"
                 ctx.after_execution(-1)
+                mark("after_execution")
             else:
                 message = "Error while executing command on worker. See your stdout/stderr to see more info."
             return ExecuteResult(rc, message)
@@ -279,12 +305,16 @@ class Worker:
             return op.snapshot()
 
     def wait_operation(self, operation_id: str, timeout: float = 60.0) -> Operation:
-        deadline = time.time() + timeout
-        while True:
-            op = self.get_operation(operation_id)
-            if op.done or time.time() > deadline:
-                return op
-            time.sleep(0.002)
+        """the operation as soon as it is done, or as it stands after `timeout` seconds — woken by the completing task, no
+        polling (what a ``Get`` that carries a ``lzyb-wait-ms`` header is answered with, grpc_api/server.py)"""
+        deadline = time.monotonic() + timeout
+        with self._done:
+            while True:
+                op = self.get_operation(operation_id)
+                left = deadline - time.monotonic()
+                if op.done or left <= 0:
+                    return op
+                self._done.wait(left)
 
     # ---- lifecycle --------------------------------------------------------------------------------------
     def release_execution(self, execution_id: str) -> None:

@@ -235,6 +235,51 @@ def test_worker_api_over_grpc(env):
         server.stop(0)
 
 
+def _slow(a: str) -> str:
+    time.sleep(0.4)
+    return a + "!"
+
+
+def test_get_with_the_wait_header_is_answered_when_the_task_completes(env):
+    """`lzyb-wait-ms` on LongRunningService.Get (grpc_api/server.py): without it the answer comes at once, done or not, as from
+    the reference's operation service; with it a running operation is answered when it completes — one call, no polling —
+    and an expired wait returns the operation as it stands; nonsense in the header is INVALID_ARGUMENT."""
+    cm, worker = env
+    server, port = serve("127.0.0.1:0", worker=worker)
+    wapi, ops = WorkerApiClient(f"127.0.0.1:{port}"), LongRunningClient(f"127.0.0.1:{port}")
+    try:
+        wapi.call("Init", M.InitRequest(user_id="uid", workflow_name="wf"))
+        task = make_task(cm, _slow, [(str, "x")])
+        req = M.ExecuteRequest(task_id=task.task_id, execution_id=task.execution_id, workflow_name="wf", user_id="uid")
+        req.task_desc.operation.command = task.command
+        for s in task.slots:
+            req.task_desc.operation.slots.add(name=s.name, direction=s.direction)
+        for name, chan in task.slot_assignments.items():
+            req.task_desc.slot_assignments.add(slot_name=name, channel_id=chan)
+        t0 = time.monotonic()
+        op = wapi.call("Execute", req)
+        get = GetOperationRequest(operation_id=op.id)
+        assert not ops.call("Get", get).done and time.monotonic() - t0 < 0.3          # a stock Get never waits
+        assert not ops.call("Get", get, metadata=(("lzyb-wait-ms", "50"),)).done       # a wait that expires: as it stands
+        with pytest.raises(grpc.RpcError) as e:
+            ops.call("Get", get, metadata=(("lzyb-wait-ms", "soon"),))
+        assert e.value.code() == grpc.StatusCode.INVALID_ARGUMENT
+        done = ops.wait(op.id, timeout=30.0)                                            # one call, answered on completion
+        took = time.monotonic() - t0
+        assert done.done and 0.35 < took < 5.0
+        resp = M.ExecuteResponse()
+        assert done.response.Unpack(resp) and (resp.rc, resp.description) == (0, "Success")
+        assert dec(str, H.blob_get("mem://exec-1/t1/ret0")) == "x!"
+        assert ops.wait(op.id).done                                                     # already done: at once
+        with pytest.raises(grpc.RpcError) as e:
+            ops.call("Get", GetOperationRequest(operation_id="nope"), metadata=(("lzyb-wait-ms", "50"),))
+        assert e.value.code() == grpc.StatusCode.NOT_FOUND
+    finally:
+        wapi.close()
+        ops.close()
+        server.stop(0)
+
+
 def test_diamond_graph_driven_through_two_workers_over_grpc(env):
     """What the reference's graph executor does with its workers, end to end on this repository's pieces: channels
     from CreateChannels' rule (storage consumer per result, storage producer per existing input), tasks released by
