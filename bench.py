@@ -61,6 +61,8 @@ def parse():
                     help="how a frame crosses GPUs (N > 1): push = producer-issued push kernel + landed scan (auto); "
                          "ldg / tma / dma = consumer pull through a CUDA-IPC import.  N = 1: ldg / tma force a copying pull")
     ap.add_argument("--no-move", action="store_true", help="N = 1: copy on delivery even for a sole consumer (round-1 behaviour)")
+    ap.add_argument("--blocking-commit", action="store_true",
+                    help="N = 1: every op waits for its pack and digest before the next delivery (lzyb_slot_commit as round 1 used it)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -190,6 +192,7 @@ class Ring:
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         self.multi = self.world > 1
+        self.stream_order = False  # N = 1: commits complete in stream order (set in run_ours)
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device; the data plane has no CPU path")
         self.dev = self.local
@@ -304,7 +307,10 @@ class Ring:
             ingest.pack_host(self.host_in.data_ptr(), self.payload, self.sp)
         else:
             self.timed("pack", lambda: ingest.pack(self.x.data_ptr(), self.payload, self.sp), record)
-        ingest.commit(self.sp)
+        if self.stream_order and corrupt_at is None:
+            ingest.commit_async(self.sp)
+        else:
+            ingest.commit(self.sp)
         if corrupt_at is not None:
             ingest.fault(N.FAULT_CORRUPT_ONCE, corrupt_at)
         prev = ingest
@@ -325,10 +331,15 @@ class Ring:
             out.set_meta(N.DT_F32, self.shape)
             live.append(out)
             self.timed("pack", lambda: out.pack(res.data_ptr(), self.payload, self.sp), record)
-            out.commit(self.sp)
+            if self.stream_order:
+                out.commit_async(self.sp)  # READY in stream order: the next op's launches queue behind this pack
+            else:
+                out.commit(self.sp)
             prev = out
         if from_host:
             prev.copy_to_host(self.host_out.data_ptr(), self.payload, 0, self.sp)
+        if self.stream_order:
+            prev.commit(self.sp)  # the step's one wait: the chain's last pack has finished and its digest is published
         return prev, live
 
     def close_all(self, live):
@@ -440,6 +451,11 @@ def run_ours(args):
         carrier = "move" if (args.engine == "auto" and not args.no_move) else ("ldg" if args.engine in ("auto", "push", "dma") else args.engine)
         parity_carriers = ["move", "ldg", "tma"]
         move = carrier == "move"
+    # N = 1: commits complete in stream order (lzyb_set_lazy_commit — B200Runtime's default): an op's hand-over and pack are queued
+    # behind its predecessor's pack instead of waiting for it on the host; the step waits once, for the last digest.  The ring
+    # (N > 1) exports every committed frame to another process, which needs the digest: it commits as before.
+    ring.stream_order = (not multi) and not args.blocking_commit
+    N.set_lazy_commit(ring.stream_order)
     parity = ring.parity(parity_carriers, True)
     N.set_copy_engine({"ldg": N.ENGINE_LDG, "tma": N.ENGINE_TMA, "dma": N.ENGINE_DMA}.get(carrier, N.ENGINE_AUTO))
 
@@ -599,6 +615,8 @@ def run_ours(args):
             "dtype": "u8", "data": "synthetic",
             "config": workload_config(payload, world),
             "carrier_detail": {"carrier": carrier, "engine_flag": args.engine,
+                               "commit": ("stream order (lzyb_set_lazy_commit): launches of op k+1 queue behind the pack of op k; one host wait per "
+                                          "step, on the last digest" if ring.stream_order else "blocking: the host waits for every pack's digest"),
                                "what": ("ownership hand-over of the frame to its sole same-GPU consumer + pack of the op result" if carrier == "move" else
                                         "TMA-ring push kernel on the producer's GPU (digest folded, header + arrival word written into the consumer's frame)" if carrier == "push" else
                                         f"consumer pull ({carrier})")},

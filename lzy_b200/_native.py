@@ -293,6 +293,12 @@ class SlotHandle:
         check(lib.lzyb_slot_commit(self.h, C.byref(d), stream or None))
         return int(d[0]), int(d[1])
 
+    def commit_async(self, stream: int = 0) -> None:
+        """commit in stream order (needs ``set_lazy_commit(True)``, else it blocks like ``commit``): the slot is READY for every
+        reader that is ordered behind the pack on the device; the digest is harvested by whoever asks first (``commit`` /
+        ``info`` / ``export`` / a copying transfer) — include/lzy_b200.h: lzyb_set_lazy_commit"""
+        check(lib.lzyb_slot_commit(self.h, None, stream or None))
+
     def read(self, offset: int, length: int) -> Optional[bytes]:
         """``readFromOffset`` for legacy consumers; None at EOF."""
         buf = C.create_string_buffer(length)

@@ -40,6 +40,8 @@ def main():
     for _ in range(50):
         once()
     prof.disable()
+    if len(sys.argv) > 2:
+        prof.dump_stats(sys.argv[2])  # raw stats for pstats on another box
     pstats.Stats(prof).sort_stats(sys.argv[1] if len(sys.argv) > 1 else "cumulative").print_stats(45)
 
 
