@@ -207,6 +207,8 @@ class Ring:
             self.host_group = dist.new_group(backend="gloo")
             from lzy_b200.ring import ShmMailbox
             self.box = ShmMailbox.rendezvous(_GlooFacade(dist, self.host_group), self.world, self.rank, lanes=2)
+            self.pids = [None] * self.world  # rank 0 later waits for the other ranks' processes to be gone (wait_until_alone)
+            dist.all_gather_object(self.pids, os.getpid(), group=self.host_group)
         N.init(self.dev, 1, 64 << 20)
         if args.ctas_per_sm:
             N.set_grid(args.ctas_per_sm)
@@ -560,14 +562,21 @@ def run_ours(args):
         if ring.box is not None:
             ring.box.close()
         N.shutdown()
-        ring.dist.destroy_process_group()
+        # ... and leave for good: a teardown that waits for rank 0 (which is about to measure for a while) would keep this
+        # process and its CUDA context on the GPU — then it is cut short
+        t = threading.Thread(target=ring.dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(5.0)
+        if t.is_alive():
+            sys.stdout.flush()
+            os._exit(0)
         return
     api, e2e, cpu = None, e2e_cabi, None
     if rank == 0:
         gpus = list(range(world))
         if multi:
             N.shutdown()  # this process managed GPU 0 only; the runtime below manages all N
-            wait_until_alone(gpus)
+            waited_s = wait_until_alone([p for r, p in enumerate(ring.pids) if r != rank])
         if not args.no_e2e:
             api_steps = max(3, min(args.steps, 10))
             rec = api_bench(dev, gpus, payload, ring.shape, api_steps)
@@ -575,6 +584,8 @@ def run_ours(args):
                                        "ms_per_step": rec["ms_dev"], "ops_per_sec": world * N_OPS / (rec["ms_dev"] * 1e-3)},
                    "steps": api_steps, "chains_per_step": world, "gpus": world, "stats": rec["stats"],
                    "call": "with Lzy(runtime=B200Runtime(gpus=all)).workflow(): ys = [f8(...f1(x_j)) for j in range(N)]; materialize each"}
+            if multi:
+                api["other_ranks_gone_after_s"] = round(waited_s, 2)  # rank 0 measures alone on the box (wait_until_alone)
             e2e = {"value": world * N_OPS * payload / (rec["ms_e2e"] * 1e-3) / 1e9, "unit": UNIT,
                    "h2d_bytes_per_step": world * payload, "d2h_bytes_per_step": world * payload, "ms_per_step": rec["ms_e2e"],
                    "steps": api_steps, "ops_per_sec": world * N_OPS / (rec["ms_e2e"] * 1e-3), "bit_exact": True,
@@ -631,20 +642,23 @@ def run_ours(args):
         ring.dist.destroy_process_group()
 
 
-def wait_until_alone(gpus, timeout_s: float = 15.0) -> None:
-    """the other ranks are exiting: give their CUDA contexts time to disappear from the GPUs (NVML's process list), at most
-    `timeout_s`; without NVML just a short pause"""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        handles = [pynvml.nvmlDeviceGetHandleByIndex(g) for g in gpus]
-        deadline = time.time() + timeout_s
-        while time.time() < deadline:
-            if all(len(pynvml.nvmlDeviceGetComputeRunningProcesses(h)) <= 1 for h in handles):
-                return
-            time.sleep(0.1)
-    except Exception:
-        time.sleep(3.0)
+def wait_until_alone(pids, timeout_s: float = 20.0) -> float:
+    """the other ranks are exiting: wait until their processes are gone (no /proc entry, or a zombie waiting for torchrun to
+    reap it — its CUDA contexts are released either way), at most `timeout_s`.  Returns the seconds waited.  The process ids
+    come from the ranks themselves, so they are in this process's pid namespace (NVML's process list need not be)."""
+    def gone(pid: int) -> bool:
+        try:
+            with open(f"/proc/{pid}/stat") as f:
+                return f.read().rsplit(")", 1)[1].split()[0] in ("Z", "X")
+        except OSError:
+            return True
+
+    t0 = time.time()
+    while time.time() - t0 < timeout_s and not all(gone(p) for p in pids):
+        time.sleep(0.05)
+    if all(gone(p) for p in pids):
+        time.sleep(0.2)  # the driver's teardown of a context that died with its process
+    return time.time() - t0
 
 
 def api_bench(dev0: int, gpus, payload: int, shape, steps: int):

@@ -69,3 +69,26 @@ def test_product_arm_refuses_to_run_without_a_gpu(bench, monkeypatch):
     monkeypatch.delenv("WORLD_SIZE", raising=False)
     with pytest.raises(SystemExit, match="needs a CUDA device"):
         bench.run_ours(args(impl="ours"))
+
+
+def test_rank_0_waits_for_the_other_ranks_processes_not_for_a_process_count(bench):
+    """N > 1: before the one-process legs rank 0 waits until the other ranks are gone — a zombie (exited, not yet reaped by
+    torchrun) counts as gone, a live process does not, and the wait is bounded"""
+    import subprocess
+    import time
+    quick = subprocess.Popen([sys.executable, "-c", "pass"])
+    slow = subprocess.Popen([sys.executable, "-c", "import time; time.sleep(30)"])
+    try:
+        deadline = time.time() + 10
+        while quick.poll() is None and time.time() < deadline:  # reaped here; an unreaped child is covered below
+            time.sleep(0.02)
+        assert bench.wait_until_alone([quick.pid], timeout_s=5.0) < 1.0
+        t0 = time.time()
+        waited = bench.wait_until_alone([quick.pid, slow.pid], timeout_s=0.5)
+        assert 0.5 <= waited < 2.0 and time.time() - t0 < 2.0
+        zombie = subprocess.Popen([sys.executable, "-c", "pass"])  # never polled: stays a zombie until wait()
+        assert bench.wait_until_alone([zombie.pid], timeout_s=10.0) < 5.0
+        zombie.wait()
+    finally:
+        slow.kill()
+        slow.wait()
