@@ -89,8 +89,8 @@ class LongRunningClient(_Client):
                 return op
             if time.monotonic() > deadline:
                 raise TimeoutError(f"operation {operation_id} still running after {timeout} s")
-            if time.monotonic() - t0 < 1e-3:  # the header was not honoured
-                time.sleep(5e-4)
+            if time.monotonic() - t0 < slice_ms * 5e-4:  # back long before the slice was over: the header was not honoured
+                time.sleep(2e-3)
 
 
 class PeerApiClient(_Client):
