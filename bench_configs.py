@@ -324,6 +324,24 @@ def c5(gpus: Optional[List[int]] = None, mib: int = 256, reps: int = 4) -> Dict[
 # the process-per-GPU deployment: channel manager + one worker process per GPU, tasks sent as WorkerApi.Execute
 # ------------------------------------------------------------------------------------------------------------------
 def worker_processes_chain(gpus: List[int], mib: int = 256, n_ops: int = 8, reps: int = 3) -> Dict[str, Any]:
+    """The chain of `_worker_processes_chain` twice: with the control calls of the workers (Bind / TransferCompleted towards the
+    channel manager, Describe towards the producer's worker) on the library's unix sockets (csrc/host/local_rpc.cpp) — the
+    record — and over gRPC as between stock processes — the A/B, and the fallback should the sockets fail on this box."""
+    try:
+        rec = _worker_processes_chain(gpus, mib, n_ops, reps, local=True)
+    except Exception as e:  # noqa: BLE001
+        rec = _worker_processes_chain(gpus, mib, n_ops, reps, local=False)
+        rec["local_sockets_error"] = f"{type(e).__name__}: {e}"
+        return rec
+    try:
+        grpc_rec = _worker_processes_chain(gpus, mib, n_ops, reps, local=False)
+        rec["control_calls_over_grpc"] = {k: grpc_rec[k] for k in ("wall_ms", "ops_per_sec", "edge_GBps", "bit_exact")}
+    except Exception as e:  # noqa: BLE001
+        rec["control_calls_over_grpc"] = {"error": f"{type(e).__name__}: {e}"}
+    return rec
+
+
+def _worker_processes_chain(gpus: List[int], mib: int, n_ops: int, reps: int, local: bool) -> Dict[str, Any]:
     """An n-op identity chain over `mib`-MiB float32 tensors on the deployment shape of the reference (a worker process
     per GPU — lzy/worker/.../Worker.java:36-56 — and the channel manager as its own process), driven over the kept wire
     contract: LzyChannelManagerPrivate.GetOrCreate for the channels, WorkerApi.Init / Execute + LongRunningService.Get per
@@ -363,8 +381,12 @@ def worker_processes_chain(gpus: List[int], mib: int = 256, n_ops: int = 8, reps
         return int(t.device.index)
 
     procs, clients = [], {}
+    import shutil
+    import tempfile
+    sockdir = tempfile.mkdtemp(prefix="lzyb-", dir="/tmp")  # unix socket paths are short
     try:
-        cm = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "channel-manager", "--port", "0"], cwd=str(root),
+        cm = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "channel-manager", "--port", "0"] +
+                              (["--local-socket", f"{sockdir}/cm.sock"] if local else []), cwd=str(root),
                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         procs.append(cm)
         cm_target = cm.stdout.readline().strip().rsplit(" ", 1)[-1]
@@ -372,8 +394,9 @@ def worker_processes_chain(gpus: List[int], mib: int = 256, n_ops: int = 8, reps
         for g in gpus:
             port = free_port()
             w = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "worker", "--gpu", str(g), "--port", str(port),
-                                  "--channel-manager", cm_target], cwd=str(root), stdout=subprocess.PIPE,
-                                 stderr=subprocess.DEVNULL, text=True)
+                                  "--channel-manager", cm_target] +
+                                 (["--channel-manager-local", f"{sockdir}/cm.sock", "--local-socket", f"{sockdir}/w{g}.sock"] if local else []),
+                                 cwd=str(root), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             procs.append(w)
             line = w.stdout.readline()
             if not line.startswith("worker for GPU"):
@@ -402,7 +425,7 @@ def worker_processes_chain(gpus: List[int], mib: int = 256, n_ops: int = 8, reps
                 if not op_msg.done:
                     # one Get, answered by the worker when the task completes (`lzyb-wait-ms`, grpc_api/server.py): polling
                     # every 0.5 ms took the task's own interpreter ≈ 0.3 ms per poll (tools/worker_chain_cpu.py)
-                    op_msg = ops.wait(op_msg.id, timeout=300.0)
+                    op_msg = ops.wait(op_msg.id, timeout=90.0)
                 resp = M.ExecuteResponse()
                 assert op_msg.WhichOneof("result") == "response" and op_msg.response.Unpack(resp)
                 if resp.rc != 0:
@@ -433,7 +456,9 @@ def worker_processes_chain(gpus: List[int], mib: int = 256, n_ops: int = 8, reps
         t = _median(ts)
         return {"config": "C2 on worker processes", "gpus": len(gpus), "processes": len(gpus) + 1, "payload_mib": mib, "ops": n_ops,
                 "wall_ms": t * 1e3, "ops_per_sec": n_ops / t, "edge_GBps": n_ops * (mib << 20) / t / 1e9, "bit_exact": True,
-                "wire": "WorkerApi.Init/Execute + LongRunningService.Get (answered on completion: lzyb-wait-ms) + LzyChannelManager(Private) + LzybPeerApi.Describe over gRPC; "
+                "control_calls": ("unix sockets served by the library's threads (local_rpc.cpp): Bind / TransferCompleted to the channel "
+                                  "manager, Describe to the producer's worker" if local else "gRPC, as between stock processes"),
+                "wire": "WorkerApi.Init/Execute + LongRunningService.Get (answered on completion: lzyb-wait-ms) + LzyChannelManagerPrivate over gRPC; "
                         "payload over NVLink through CUDA IPC (consumer pull, TMA ring, digest verified on landing)"}
     finally:
         for wapi, ops in clients.values():
@@ -449,3 +474,4 @@ def worker_processes_chain(gpus: List[int], mib: int = 256, n_ops: int = 8, reps
                 pr.wait(timeout=20)
             except Exception:
                 pr.kill()
+        shutil.rmtree(sockdir, ignore_errors=True)

@@ -182,6 +182,27 @@ typedef int (*lzyb_peer_resolver_t)(const char* peer_url, const char* peer_id, l
 int lzyb_slots_set_peer_resolver(lzyb_peer_resolver_t resolver); /* NULL = peers must be local (default) */
 int lzyb_slots_describe(lzyb_handle_t slots, const char* peer_id, lzyb_ipc_desc_t* out);
 
+/* The same two seams over a unix socket, for this repository's own processes on ONE box (csrc/host/local_rpc.cpp).  gRPC stays
+ * the wire contract towards stock peers; between a worker process per GPU and the channel manager of one box a task's six
+ * control calls (Bind, Describe, TransferCompleted for an input; Bind, upload, TransferCompleted for an output) cost
+ * 0.5–0.9 ms each through two interpreters — here they are length-prefixed frames served by threads of this library, with the
+ * same arguments, result codes and lzyb_last_error texts.
+ *   lzyb_cm_serve_local(cm, path)          serve Bind / Unbind / TransferCompleted / TransferFailed of matcher `cm` on `path`
+ *   lzyb_slots_connect_cm_local(path, &c)  route this process's slot state machines to that socket (installs the client
+ *                                          table of lzyb_slots_set_cm_client); `c` goes where a matcher handle would
+ *                                          (lzyb_slots_create).  LZYB_E_UNAVAILABLE if nobody listens there
+ *   lzyb_slots_serve_local(slots, path)    serve Describe(peer_id) of worker `slots`; a worker that does puts
+ *                                          "uds=<path>" into its URL's query ("cuda+ipc://host:port?gpu=3&uds=/run/w3.sock")
+ *                                          and consumers of this box resolve its peers over the socket instead of
+ *                                          through the resolver callback
+ * The matcher's deferred StartTransfer keeps travelling as LzySlotsApi.StartTransfer. */
+int lzyb_cm_serve_local(lzyb_handle_t cm, const char* socket_path);
+int lzyb_cm_stop_local(lzyb_handle_t cm);
+int lzyb_slots_connect_cm_local(const char* socket_path, lzyb_handle_t* cm_cookie);
+int lzyb_slots_disconnect_cm_local(void);
+int lzyb_slots_serve_local(lzyb_handle_t slots, const char* socket_path);
+int lzyb_slots_stop_local(lzyb_handle_t slots);
+
 #define LZYB_DIR_INPUT 1
 #define LZYB_DIR_OUTPUT 2
 

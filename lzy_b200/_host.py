@@ -85,6 +85,12 @@ _SIGS = {
     "lzyb_slots_set_cm_client": (_i, [C.c_void_p]),
     "lzyb_slots_set_peer_resolver": (_i, [C.c_void_p]),
     "lzyb_slots_describe": (_i, [_H, _s, C.c_void_p]),
+    "lzyb_cm_serve_local": (_i, [_H, _s]),
+    "lzyb_cm_stop_local": (_i, [_H]),
+    "lzyb_slots_connect_cm_local": (_i, [_s, C.POINTER(_H)]),
+    "lzyb_slots_disconnect_cm_local": (_i, []),
+    "lzyb_slots_serve_local": (_i, [_H, _s]),
+    "lzyb_slots_stop_local": (_i, [_H]),
     "lzyb_slots_transfer_log": (C.c_int64, [_H, C.c_char_p, C.c_uint64, C.c_int]),
     "lzyb_frame_store_put": (_i, [_s, _H]),
     "lzyb_frame_store_get": (_i, [_s, C.POINTER(_H)]),
@@ -167,8 +173,18 @@ class ChannelManager:
 
     def close(self):
         if self.h:
+            lib.lzyb_cm_stop_local(self.h)
             lib.lzyb_cm_free(self.h)
             self.h = 0
+
+    # -- box-local transport (csrc/host/local_rpc.cpp) -----------------------------------------------
+    def serve_local(self, socket_path: str) -> None:
+        """Bind / Unbind / TransferCompleted / TransferFailed of this matcher on a unix socket, served by library threads:
+        what the worker processes of this box dial instead of the gRPC port (`connect_cm_local`)"""
+        _check(lib.lzyb_cm_serve_local(self.h, _b(socket_path)))
+
+    def stop_local(self) -> None:
+        _check(lib.lzyb_cm_stop_local(self.h))
 
     # -- private API ---------------------------------------------------------------------------
     def get_or_create(self, user_id: str, workflow_name: str, execution_id: str, *, producer_uri: Optional[str] = None,
@@ -482,9 +498,31 @@ class Slots:
         _check(n)
         return buf.raw[:n]
 
+    def serve_local(self, socket_path: str) -> None:
+        """LzybPeerApi.Describe of this worker on a unix socket (library threads); announce it as "uds=<path>" in the
+        query of `api_url` and consumers of this box resolve this worker's peers there"""
+        _check(lib.lzyb_slots_serve_local(self.h, _b(socket_path)))
+
     def close(self) -> None:
         if self.h:
+            lib.lzyb_slots_stop_local(self.h)
             lib.lzyb_slots_free(self.h)
+            self.h = 0
+
+
+class LocalChannelManager:
+    """stands where a `ChannelManager` would in `Slots(cm, …)`: the channel manager of this box behind its unix socket
+    (`ChannelManager.serve_local` in that process).  One transport per process: connecting installs the client table of the
+    slots runtime's seam, like `grpc_api.remote_cm.connect` does for the gRPC transport."""
+
+    def __init__(self, socket_path: str):
+        h = _H()
+        _check(lib.lzyb_slots_connect_cm_local(_b(socket_path), C.byref(h)))
+        self.h, self.socket_path = h.value, socket_path
+
+    def close(self) -> None:
+        if self.h:
+            lib.lzyb_slots_disconnect_cm_local()
             self.h = 0
 
 

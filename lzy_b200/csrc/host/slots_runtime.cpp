@@ -36,6 +36,7 @@
 
 #include "../../../include/lzy_b200_host.h"
 #include "host_common.h"
+#include "local_rpc.h"
 
 namespace {
 
@@ -832,12 +833,15 @@ struct InputSlotImpl : SlotBase, std::enable_shared_from_this<InputSlotImpl> {
             const std::string local_err = lzyb_last_error();
             lzyb_peer_resolver_t resolve = g_peer_resolver.load();
             lzyb_ipc_desc_t desc;
-            if (!resolve || !ops().peer_import || p.url[0] == 0 || inst->api_url == p.url) {
+            std::string peer_socket;  // a worker of this box that serves Describe on a unix socket says so in its URL
+            const bool by_socket = lzyb_host::local_peer_socket(p.url, &peer_socket);
+            if ((!resolve && !by_socket) || !ops().peer_import || p.url[0] == 0 || inst->api_url == p.url) {
                 err = std::string("Cannot read from slot peer ") + p.peer_id + ": " + local_err;
                 return nullptr;
             }
             memset(&desc, 0, sizeof(desc));
-            if (resolve(p.url, p.peer_id, &desc) != LZYB_OK || ops().peer_import(&desc, inst->gpu, &h) != LZYB_OK) {
+            const int found = by_socket ? lzyb_host::local_describe(peer_socket, p.peer_id, &desc) : resolve(p.url, p.peer_id, &desc);
+            if (found != LZYB_OK || ops().peer_import(&desc, inst->gpu, &h) != LZYB_OK) {
                 err = std::string("Cannot read from slot peer ") + p.peer_id + " at " + p.url + ": " + lzyb_last_error();
                 return nullptr;
             }
@@ -1179,7 +1183,7 @@ void pump_loop(lzyb_handle_t cm, std::shared_ptr<Pump> p) {
             {
                 std::shared_lock<std::shared_mutex> lk(g_mu);
                 for (auto& kv : g_instances)
-                    if (kv.second->cm == cm) insts.push_back(kv.second);
+                    if (kv.second->cm == cm || lzyb_host::local_matcher_behind(kv.second->cm) == cm) insts.push_back(kv.second);
             }
             // The reference issues StartTransfer first and marks the transfer ACTIVE afterwards
             // (ActionScheduler.java:74-91); a consumer that finishes its download in between would
@@ -1200,7 +1204,9 @@ void pump_loop(lzyb_handle_t cm, std::shared_ptr<Pump> p) {
             {
                 std::shared_lock<std::shared_mutex> lk(g_mu);
                 for (auto& kv : g_ctxs)
-                    if (kv.second->inst->cm == cm && kv.second->execution_id == a.execution_id) ctxs.push_back(kv.second);
+                    if ((kv.second->inst->cm == cm || lzyb_host::local_matcher_behind(kv.second->inst->cm) == cm) &&
+                        kv.second->execution_id == a.execution_id)
+                        ctxs.push_back(kv.second);
             }
             for (auto& c : ctxs) {
                 std::vector<std::shared_ptr<SlotBase>> slots;

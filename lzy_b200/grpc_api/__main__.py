@@ -22,20 +22,40 @@ from .pump import RemoteActionPump
 from .server import serve
 
 
-def _worker(args) -> int:
-    from .. import _native as N
+def make_worker(gpu: int, host: str, port: int, channel_manager: str, channel_manager_local=None, local_socket=None,
+                mount_factory=None):
+    """(matcher connection, Worker, the worker's URL) as the `worker` service wires them — one place, so that the CPU twin of
+    the tests (tests/support/remote_worker_api.py, in-memory backend) runs the very wiring the GPU worker runs.
+    The matcher: over gRPC, or — same box, this repository's channel manager — over its unix socket (no interpreter on the
+    path of Bind / TransferCompleted; the matcher's deferred StartTransfer still arrives on the gRPC port)."""
     from ..worker import Worker
     from . import peers, remote_cm
+    cm = H.LocalChannelManager(channel_manager_local) if channel_manager_local else remote_cm.connect(channel_manager)
+    peers.install()
+    url = f"cuda+ipc://{host}:{port}?gpu={gpu}"
+    if local_socket:
+        url += f"&uds={local_socket}"  # consumers of this box fetch this worker's frame descriptors there
+    return cm, Worker(cm, gpu, url, local_socket=local_socket, mount_factory=mount_factory), url
+
+
+def close_worker(cm, worker) -> None:
+    from . import peers, remote_cm
+    worker.close()
+    peers.uninstall()
+    if isinstance(cm, H.LocalChannelManager):
+        cm.close()
+    remote_cm.disconnect_all()
+
+
+def _worker(args) -> int:
+    from .. import _native as N
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(name)s %(levelname)s %(message)s")
     try:
         N.init(args.gpu, 1, args.host_ring_mib << 20)
     except N.LzybError as e:
         print(f"worker needs a CUDA device: {e}", flush=True)
         return 3
-    cm = remote_cm.connect(args.channel_manager)
-    peers.install()
-    url = f"cuda+ipc://{args.host}:{args.port}?gpu={args.gpu}"
-    worker = Worker(cm, args.gpu, url)
+    cm, worker, url = make_worker(args.gpu, args.host, args.port, args.channel_manager, args.channel_manager_local, args.local_socket)
     server, port = serve(f"{args.host}:{args.port}", worker=worker)
     print(f"worker for GPU {args.gpu} listening on {args.host}:{port} as {url}", flush=True)
     done = threading.Event()
@@ -43,9 +63,7 @@ def _worker(args) -> int:
         signal.signal(sig, lambda *_: done.set())
     done.wait()
     server.stop(1)
-    worker.close()
-    peers.uninstall()
-    remote_cm.disconnect_all()
+    close_worker(cm, worker)
     return 0
 
 
@@ -56,12 +74,18 @@ def main(argv=None) -> int:
     cm_args.add_argument("--host", default="127.0.0.1")
     cm_args.add_argument("--port", type=int, default=0)
     cm_args.add_argument("--seed", type=int, default=None, help="deterministic producer tie-break (tests)")
+    cm_args.add_argument("--local-socket", default=None, metavar="PATH",
+                         help="also serve Bind / Unbind / TransferCompleted / TransferFailed on this unix socket (workers of this box)")
     w_args = sub.add_parser("worker", help="serve WorkerApi + LzySlotsApi + LzybPeerApi for one GPU")
     w_args.add_argument("--gpu", type=int, default=0)
     w_args.add_argument("--host", default="127.0.0.1")
     w_args.add_argument("--port", type=int, required=True, help="also part of the URL other workers dial: must be fixed")
     w_args.add_argument("--channel-manager", required=True, metavar="HOST:PORT")
     w_args.add_argument("--host-ring-mib", type=int, default=64)
+    w_args.add_argument("--channel-manager-local", default=None, metavar="PATH",
+                        help="the channel manager's --local-socket: the slot state machines dial it instead of the gRPC port")
+    w_args.add_argument("--local-socket", default=None, metavar="PATH",
+                        help="answer LzybPeerApi.Describe on this unix socket too and say so in the worker's URL (uds=PATH)")
     args = ap.parse_args(argv)
     if args.service == "worker":
         return _worker(args)
@@ -69,6 +93,8 @@ def main(argv=None) -> int:
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(name)s %(levelname)s %(message)s")
     cm = H.ChannelManager(seed=args.seed) if args.seed is not None else H.ChannelManager()
     server, port = serve(f"{args.host}:{args.port}", cm=cm)
+    if args.local_socket:
+        cm.serve_local(args.local_socket)
     pump = RemoteActionPump(cm, on_abort=lambda a: logging.getLogger("lzy_b200.cm").error(
         "workflow %s of execution %s must be aborted: %s", a["workflow_name"], a["execution_id"], a["reason"])).start()
     print(f"channel-manager listening on {args.host}:{port}", flush=True)

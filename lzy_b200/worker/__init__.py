@@ -157,8 +157,11 @@ class Worker:
 
     def __init__(self, cm: H.ChannelManager, gpu: int = 0, api_url: str = "lzyb://worker-0", *,
                  mount_factory: Optional[MountFactory] = None, env_factory: Optional[EnvFactory] = None,
-                 command_runner: Optional[CommandRunner] = None, vm_id: str = ""):
+                 command_runner: Optional[CommandRunner] = None, vm_id: str = "", local_socket: Optional[str] = None):
         self.cm, self.gpu, self.api_url, self.vm_id = cm, gpu, api_url, vm_id or f"vm-{uuid.uuid4().hex[:8]}"
+        # a unix socket on which this worker answers LzybPeerApi.Describe for consumers of the same box (csrc/host/
+        # local_rpc.cpp); `api_url` must then carry "uds=<that path>" in its query
+        self.local_socket = local_socket
         self._lock = threading.RLock()
         self._done = threading.Condition(self._lock)  # notified whenever an operation completes
         self._owner: Optional[Tuple[str, str]] = None
@@ -204,6 +207,8 @@ class Worker:
                 self._owner = requester
                 try:
                     self.slots = H.Slots(self.cm, self.gpu, self.api_url)
+                    if self.local_socket:
+                        self.slots.serve_local(self.local_socket)
                 except Exception as e:
                     self._owner = None
                     raise WorkerStatusError("INTERNAL", f"Cannot start slots server: {e}")

@@ -147,17 +147,29 @@ int main(int argc, char** argv) {
     const char* spill_dir = argc > 3 ? argv[3] : "/tmp/lzyb_host_stress_spill";
     lzyb_slots_set_backend(&hostmem_backend_ops);
     if (lzyb_frame_store_set_spill(spill_dir, 0) != LZYB_OK) return 2;
+    // argv[4]: a unix socket path — the slot state machines then reach the matcher through the box-local transport
+    // (csrc/host/local_rpc.cpp: serving threads, per-thread client connections) instead of calling it in process
+    const char* socket_path = argc > 4 ? argv[4] : nullptr;
     lzyb_handle_t cm = 0;
     if (lzyb_cm_create(&cm) != LZYB_OK || lzyb_cm_seed(cm, 7) != LZYB_OK || lzyb_cm_pump_start(cm) != LZYB_OK) return 2;
+    lzyb_handle_t via = cm;  // what the slots instances are created with: the matcher, or the connection to its socket
+    if (socket_path && (lzyb_cm_serve_local(cm, socket_path) != LZYB_OK || lzyb_slots_connect_cm_local(socket_path, &via) != LZYB_OK)) {
+        fprintf(stderr, "local socket: %s\n", lzyb_last_error());
+        return 2;
+    }
     std::vector<lzyb_handle_t> slots(4);
     for (size_t i = 0; i < slots.size(); ++i)
-        if (lzyb_slots_create(cm, 0, ("lzyb://worker-" + std::to_string(i)).c_str(), &slots[i]) != LZYB_OK) return 2;
+        if (lzyb_slots_create(via, 0, ("lzyb://worker-" + std::to_string(i)).c_str(), &slots[i]) != LZYB_OK) return 2;
 
     std::vector<std::thread> ts;
     for (int t = 0; t < threads; ++t) ts.emplace_back(worker, t, cm, std::cref(slots), jobs);
     for (auto& t : ts) t.join();
 
     for (auto s : slots) lzyb_slots_free(s);
+    if (socket_path) {
+        lzyb_slots_disconnect_cm_local();
+        lzyb_cm_stop_local(cm);
+    }
     lzyb_cm_pump_stop(cm);
     lzyb_cm_free(cm);
     lzyb_frame_store_clear("");

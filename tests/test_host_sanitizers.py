@@ -30,15 +30,25 @@ def build(name: str, flags):
     return exe
 
 
-@pytest.mark.parametrize("name, flags, threads, jobs", [
-    ("tsan", ["-fsanitize=thread"], 6, 30),
-    ("asan", ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"], 8, 40),
-])
-def test_host_logic_under_sanitizers(name, flags, threads, jobs, tmp_path):
+@pytest.mark.parametrize("name, flags, threads, jobs, over_socket", [
+    ("tsan", ["-fsanitize=thread"], 6, 30, False),
+    ("asan", ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"], 8, 40, False),
+    # the same workout with every matcher call of the slot threads crossing the box-local transport (local_rpc.cpp)
+    ("tsan", ["-fsanitize=thread"], 6, 20, True),
+    ("asan", ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"], 8, 30, True),
+], ids=["tsan", "asan", "tsan-socket", "asan-socket"])
+def test_host_logic_under_sanitizers(name, flags, threads, jobs, over_socket, tmp_path):
     if shutil.which("g++") is None:
         pytest.skip("no g++")
     exe = build(name, flags)
-    r = subprocess.run([str(exe), str(threads), str(jobs), str(tmp_path / "spill")], capture_output=True, text=True, timeout=600)
+    import tempfile
+    sockdir = tempfile.mkdtemp(prefix="lzyb-", dir="/tmp") if over_socket else None  # short path: sun_path is 108 bytes
+    try:
+        r = subprocess.run([str(exe), str(threads), str(jobs), str(tmp_path / "spill")] + ([f"{sockdir}/cm.sock"] if over_socket else []),
+                           capture_output=True, text=True, timeout=600)
+    finally:
+        if sockdir:
+            shutil.rmtree(sockdir, ignore_errors=True)
     report = r.stdout + r.stderr
     if "FATAL: ThreadSanitizer" in report or "FATAL: AddressSanitizer" in report or "Shadow memory range interleaves" in report:
         pytest.skip("the sanitizer runtime cannot map its shadow memory in this sandbox: " + report.strip().splitlines()[0])

@@ -23,6 +23,7 @@ from lzy_b200.grpc_api.protos import GetOperationRequest  # noqa: E402
 
 N_BYTES = 64 << 10
 POLL_S = float(os.environ["POLL_S"]) if os.environ.get("POLL_S") else None  # POLL_S=0.0005: poll Get like a stock client
+LOCAL = os.environ.get("LOCAL", "1") != "0"  # LOCAL=0: matcher calls and Describe over gRPC, as between stock processes
 
 
 def make() -> bytes:
@@ -48,13 +49,16 @@ def main(n_ops: int = 8, reps: int = 5, n_workers: int = 2) -> None:
     procs, clients = [], []
     tmp = tempfile.mkdtemp(prefix="lzyb-wc-", dir="/dev/shm")
     try:
-        cm = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "channel-manager", "--port", "0"], cwd=str(ROOT),
+        cm_sock = f"{tmp}/cm.sock"
+        cm = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "channel-manager", "--port", "0"] +
+                              (["--local-socket", cm_sock] if LOCAL else []), cwd=str(ROOT),
                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         procs.append(cm)
         cm_target = cm.stdout.readline().strip().rsplit(" ", 1)[-1]
         for _ in range(n_workers):
             port = free_port()
-            w = subprocess.Popen([sys.executable, str(ROOT / "tests/support/remote_worker_api.py"), cm_target, str(port)],
+            w = subprocess.Popen([sys.executable, str(ROOT / "tests/support/remote_worker_api.py"), cm_target, str(port)] +
+                                 ([cm_sock, f"{tmp}/w{len(clients)}.sock"] if LOCAL else []),
                                  cwd=str(ROOT), stdin=subprocess.PIPE, stdout=subprocess.PIPE,
                                  stderr=open(f"/tmp/lzyb_worker_{len(clients)}.err", "w"), text=True)
             procs.append(w)
@@ -127,7 +131,8 @@ def main(n_ops: int = 8, reps: int = 5, n_workers: int = 2) -> None:
         runs.sort(key=lambda r: r["chain_ms"])
         med = runs[len(runs) // 2]
         print(json.dumps({"what": "worker-process chain on CPU (in-memory backend)", "ops": n_ops, "workers": n_workers,
-                          "payload_bytes": N_BYTES, "median": med, "ms_per_op": med["chain_ms"] / n_ops}))
+                          "payload_bytes": N_BYTES,
+                          "control_calls": "unix sockets of the library (local_rpc.cpp)" if LOCAL else "gRPC", "median": med, "ms_per_op": med["chain_ms"] / n_ops}))
         priv.close()
     finally:
         for wapi, ops in clients:
