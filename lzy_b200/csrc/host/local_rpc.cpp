@@ -31,6 +31,7 @@
 #include <vector>
 
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <sys/un.h>
 #include <unistd.h>
 
@@ -45,6 +46,7 @@ using lzyb_host::fail;
 
 enum Op : uint32_t { OP_BIND = 1, OP_UNBIND = 2, OP_COMPLETED = 3, OP_FAILED = 4, OP_DESCRIBE = 5 };
 constexpr uint32_t MAX_FRAME = 1u << 20;
+constexpr long CALL_TIMEOUT_S = 30;
 
 // ---- plumbing --------------------------------------------------------------------------------------------------------
 bool read_all(int fd, void* buf, size_t n) {
@@ -302,6 +304,10 @@ int dial(const std::string& path) {
         ::close(fd);
         return -1;
     }
+    // the matcher answers in microseconds; a peer that has not answered for this long is gone (the gRPC clients give a call 30 s too)
+    timeval tv{CALL_TIMEOUT_S, 0};
+    ::setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+    ::setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof(tv));
     return fd;
 }
 
