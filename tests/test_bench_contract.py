@@ -92,3 +92,35 @@ def test_rank_0_waits_for_the_other_ranks_processes_not_for_a_process_count(benc
     finally:
         slow.kill()
         slow.wait()
+
+
+def test_worker_process_leg_records_both_transports_and_falls_back(monkeypatch):
+    """bench_configs.worker_processes_chain: the record is the run with the control calls on the library's unix sockets, the
+    gRPC run rides along as the A/B; sockets that fail on a box leave the gRPC record with the reason next to it"""
+    sys.path.insert(0, str(ROOT))
+    import bench_configs
+    calls = []
+
+    def fake(gpus, mib, n_ops, reps, local):
+        calls.append(local)
+        return {"config": "C2 on worker processes", "wall_ms": 20.0 if local else 36.0, "ops_per_sec": 1.0, "edge_GBps": 1.0,
+                "bit_exact": True, "control_calls": "unix" if local else "gRPC"}
+    monkeypatch.setattr(bench_configs, "_worker_processes_chain", fake)
+    rec = bench_configs.worker_processes_chain([0, 1])
+    assert calls == [True, False] and rec["wall_ms"] == 20.0 and rec["control_calls_over_grpc"]["wall_ms"] == 36.0
+
+    def broken(gpus, mib, n_ops, reps, local):
+        if local:
+            raise RuntimeError("worker for GPU 0 did not start")
+        return fake(gpus, mib, n_ops, reps, local)
+    monkeypatch.setattr(bench_configs, "_worker_processes_chain", broken)
+    rec = bench_configs.worker_processes_chain([0, 1])
+    assert rec["control_calls"] == "gRPC" and "did not start" in rec["local_sockets_error"]
+
+    def grpc_broken(gpus, mib, n_ops, reps, local):
+        if not local:
+            raise TimeoutError("t3")
+        return fake(gpus, mib, n_ops, reps, local)
+    monkeypatch.setattr(bench_configs, "_worker_processes_chain", grpc_broken)
+    rec = bench_configs.worker_processes_chain([0, 1])
+    assert rec["wall_ms"] == 20.0 and "TimeoutError" in rec["control_calls_over_grpc"]["error"]
