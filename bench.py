@@ -633,13 +633,27 @@ def run_ours(args):
                                         f"consumer pull ({carrier})")},
             "ops_per_sec": world * N_OPS * args.steps / (ms_total * 1e-3),
             "roofline": roof, "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "api": api, "clocks": clocks, "gpu_launches": launches,
-            "launch_breakdown": {k: {"n": len(v), "avg_ms": sum(v) / len(v)} for k, v in per_kind.items()},
+            "launch_breakdown": {k: {"n": len(v), "avg_ms": sum(v) / len(v), "min_ms": min(v), "median_ms": sorted(v)[len(v) // 2], "max_ms": max(v)}
+                                 for k, v in per_kind.items()},
+            "per_edge_GBps": per_edge_gbps(per_kind.get("deliver" if multi else "pack"), payload, multi),
             "extra": {"configs": extras},
         }), flush=True)
     if ring.box is not None:
         ring.box.close()
     if multi:
         ring.dist.destroy_process_group()
+
+
+def per_edge_gbps(ms, payload: int, multi: bool):
+    """per-edge GB/s, min / median / max over the deliveries of the timed region.  N > 1: the NVLink
+    delivery of S bytes.  N = 1: an edge is a hand-over (no bytes move) + the pack of the consumer's result, so the edge
+    costs that pack (S bytes of payload; 2·S of HBM traffic)."""
+    if not ms:
+        return None
+    v = sorted(ms)
+    gbps = lambda t: payload / (t * 1e-3) / 1e9  # noqa: E731
+    return {"min": gbps(v[-1]), "median": gbps(v[len(v) // 2]), "max": gbps(v[0]), "edges": len(v),
+            "what": "NVLink delivery, S bytes per edge" if multi else "the pack that follows the hand-over, S payload bytes per edge"}
 
 
 def wait_until_alone(pids, timeout_s: float = 20.0) -> float:
