@@ -144,6 +144,45 @@ def test_refusals_arrive_with_the_matchers_own_code_and_text(env):
     ctx.close()
 
 
+def test_garbage_on_the_socket_does_not_take_the_server_down(env, sockdir):
+    """a connection that sends nonsense is answered UNIMPLEMENTED (unknown call), E_ARG (fields missing) or dropped (a frame
+    longer than the limit, a truncated one) — and the next well-formed client is served as if nothing had happened"""
+    import struct
+    cm, _lcm, slots = env
+    path = f"{sockdir}/cm.sock"
+
+    def raw(payload: bytes, expect_answer=True):
+        with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as sk:
+            sk.settimeout(5)
+            sk.connect(path)
+            sk.sendall(payload)
+            if not expect_answer:
+                sk.shutdown(socket.SHUT_WR)
+                return sk.recv(4)
+            (n,) = struct.unpack("<I", sk.recv(4, socket.MSG_WAITALL))
+            body = sk.recv(n, socket.MSG_WAITALL)
+            rc, elen = struct.unpack_from("<iI", body, 0)
+            return rc, body[8:8 + elen].decode()
+
+    rc, text = raw(struct.pack("<II", 4, 99))                      # a call this socket does not serve
+    assert rc == H.N.E_UNIMPLEMENTED and "99" in text
+    rc, text = raw(struct.pack("<II", 4, 1))                       # Bind without its fields
+    assert rc < 0 and "malformed Bind" in text
+    rc, text = raw(struct.pack("<III", 8, 5, 0))                   # Describe asked of the matcher's socket
+    assert rc == H.N.E_UNIMPLEMENTED
+    assert raw(struct.pack("<I", 1 << 30), expect_answer=False) == b""   # a frame beyond the limit: dropped
+    assert raw(struct.pack("<II", 400, 1) + b"x" * 10, expect_answer=False) == b""  # truncated: dropped when the peer gives up
+    chan = cm.get_or_create("u", "wf", "exec", consumer_uri="mem://after-garbage")
+    out = slots.context("exec", "fine")
+    out.add_slot("o", chan, DIR_OUTPUT)
+    out.before_execution()
+    produce(out, "o", b"still here")
+    out.after_execution(5000)
+    assert H.blob_get("mem://after-garbage") == b"still here"
+    out.close()
+    H.blob_delete("mem://after-garbage")
+
+
 def test_nobody_listening_is_unavailable_at_connect_time(sockdir):
     with pytest.raises(GrpcStatusError) as e:
         LocalChannelManager(f"{sockdir}/nobody.sock")
