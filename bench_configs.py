@@ -421,7 +421,7 @@ def _worker_processes_chain(gpus: List[int], mib: int, n_ops: int, reps: int, lo
                     req.task_desc.operation.slots.add(name=name, direction=direction)
                 for name, chan in assign.items():
                     req.task_desc.slot_assignments.add(slot_name=name, channel_id=chan)
-                op_msg = wapi.call("Execute", req)
+                op_msg = wapi.execute_and_wait(req, timeout=90.0)  # answered with the completed operation (lzyb-wait-ms)
                 if not op_msg.done:
                     # one Get, answered by the worker when the task completes (`lzyb-wait-ms`, grpc_api/server.py): polling
                     # every 0.5 ms took the task's own interpreter ≈ 0.3 ms per poll (tools/worker_chain_cpu.py)
@@ -458,7 +458,7 @@ def _worker_processes_chain(gpus: List[int], mib: int, n_ops: int, reps: int, lo
                 "wall_ms": t * 1e3, "ops_per_sec": n_ops / t, "edge_GBps": n_ops * (mib << 20) / t / 1e9, "bit_exact": True,
                 "control_calls": ("unix sockets served by the library's threads (local_rpc.cpp): Bind / TransferCompleted to the channel "
                                   "manager, Describe to the producer's worker" if local else "gRPC, as between stock processes"),
-                "wire": "WorkerApi.Init/Execute + LongRunningService.Get (answered on completion: lzyb-wait-ms) + LzyChannelManagerPrivate over gRPC; "
+                "wire": "WorkerApi.Init/Execute (answered on completion: lzyb-wait-ms; LongRunningService.Get honours the same header) + LzyChannelManagerPrivate over gRPC; "
                         "payload over NVLink through CUDA IPC (consumer pull, TMA ring, digest verified on landing)"}
     finally:
         for wapi, ops in clients.values():

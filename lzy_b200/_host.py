@@ -228,10 +228,13 @@ class ChannelManager:
 
     def channels_status(self, execution_id: str = "", channel_ids: Sequence[str] = ()) -> List[dict]:
         arr = (C.c_char_p * max(1, len(channel_ids)))(*[c.encode() for c in channel_ids])
-        need = _check(lib.lzyb_cm_channels_status(self.h, _b(execution_id), arr, len(channel_ids), None, 0))
-        buf = C.create_string_buffer(int(need))
-        _check(lib.lzyb_cm_channels_status(self.h, _b(execution_id), arr, len(channel_ids), buf, need))
-        return json.loads(buf.value.decode())["channels"]
+        cap = 4096
+        while True:  # the document may grow between a sizing call and the real one (peers bind concurrently): ask until it fits
+            buf = C.create_string_buffer(cap)
+            need = int(_check(lib.lzyb_cm_channels_status(self.h, _b(execution_id), arr, len(channel_ids), buf, cap)))
+            if need <= cap:
+                return json.loads(buf.value.decode())["channels"]
+            cap = need + 1024
 
     # -- deferred actions ------------------------------------------------------------------------
     def poll_action(self, timeout_ms: int = 0) -> Optional[dict]:

@@ -71,6 +71,13 @@ class ChannelManagerPrivateClient(_Client):
 class WorkerApiClient(_Client):
     SERVICE = "ai.lzy.v1.worker.WorkerApi"
 
+    def execute_and_wait(self, request, timeout: float = 300.0, idempotency_key: Optional[str] = None):
+        """``Execute`` with the ``lzyb-wait-ms`` header: this repository's workers answer with the COMPLETED operation (one
+        round trip per task); a worker that ignores the header answers at once with a running one — then ask
+        ``LongRunningClient.wait``"""
+        return self.call("Execute", request, idempotency_key=idempotency_key, timeout=timeout + 10.0,
+                         metadata=(("lzyb-wait-ms", str(int(timeout * 1e3))),))
+
 
 class LongRunningClient(_Client):
     SERVICE = "ai.lzy.v1.longrunning.LongRunningService"

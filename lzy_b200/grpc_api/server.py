@@ -203,6 +203,22 @@ class PeerApiService:
             _abort(context, e)
 
 
+def _wait_budget(context) -> float:
+    """seconds the caller allows this call to wait for the operation (`lzyb-wait-ms`, never past the call's own deadline);
+    0 without the header — then the answer comes at once, as from the reference's services"""
+    wait_ms = 0.0
+    for k, v in context.invocation_metadata() or ():
+        if k.lower() == WAIT_HEADER:
+            try:
+                wait_ms = max(0.0, min(float(v), 600_000.0))
+            except ValueError:
+                context.abort(grpc.StatusCode.INVALID_ARGUMENT, f"{WAIT_HEADER}: not a number: {v!r}")
+    if wait_ms <= 0:
+        return 0.0
+    left = context.time_remaining()
+    return wait_ms * 1e-3 if left is None else max(0.0, min(wait_ms * 1e-3, left - 0.05))
+
+
 def _operation_to_proto(op):
     """worker.Operation → ai.lzy.v1.longrunning.Operation; the result is ``response = Any(ExecuteResponse)``
     as declared by the ``(ai.lzy.v1.operation)`` option of WorkerApi.Execute (worker-service.proto:17-22)"""
@@ -243,7 +259,14 @@ class WorkerApiService:
                         slots=[SlotSpec(s.name, int(s.direction)) for s in op.slots],
                         slot_assignments={a.slot_name: a.channel_id for a in request.task_desc.slot_assignments})
         try:
-            return _operation_to_proto(self.worker.execute(task, _idk(context)))
+            op_state = self.worker.execute(task, _idk(context))
+            wait_s = _wait_budget(context)
+            if wait_s > 0 and not op_state.done:
+                # the caller asked (`lzyb-wait-ms`) to be answered when the task is done: the long-running operation comes back
+                # completed — `done` with its response, which every client of the operation pattern must accept anyway — and
+                # the driver saves the Get round trip (LongRunningService.Get honours the same header)
+                op_state = self.worker.wait_operation(op_state.id, wait_s)
+            return _operation_to_proto(op_state)
         except WorkerStatusError as e:
             _worker_abort(context, e)
 
@@ -261,18 +284,10 @@ class LongRunningService:
         deadline).  A driver on the same box gets the completion the moment it happens without polling the worker's
         interpreter every fraction of a millisecond (tools/worker_chain_cpu.py: each poll costs the running task ≈ 0.3 ms)."""
         from ..worker import WorkerStatusError
-        wait_ms = 0.0
-        for k, v in context.invocation_metadata() or ():
-            if k.lower() == WAIT_HEADER:
-                try:
-                    wait_ms = max(0.0, min(float(v), 60_000.0))
-                except ValueError:
-                    context.abort(grpc.StatusCode.INVALID_ARGUMENT, f"{WAIT_HEADER}: not a number: {v!r}")
+        wait_s = _wait_budget(context)
         try:
-            if wait_ms > 0:
-                left = context.time_remaining()
-                budget = wait_ms * 1e-3 if left is None else max(0.0, min(wait_ms * 1e-3, left - 0.05))
-                return _operation_to_proto(self.worker.wait_operation(request.operation_id, budget))
+            if wait_s > 0:
+                return _operation_to_proto(self.worker.wait_operation(request.operation_id, wait_s))
             return _operation_to_proto(self.worker.get_operation(request.operation_id))
         except WorkerStatusError as e:
             _worker_abort(context, e)

@@ -271,6 +271,19 @@ def test_get_with_the_wait_header_is_answered_when_the_task_completes(env):
         assert done.response.Unpack(resp) and (resp.rc, resp.description) == (0, "Success")
         assert dec(str, H.blob_get("mem://exec-1/t1/ret0")) == "x!"
         assert ops.wait(op.id).done                                                     # already done: at once
+        # Execute itself honours the header: the operation comes back completed, no Get at all
+        task2 = make_task(cm, _slow, [(str, "y")], task_id="t2")
+        req2 = M.ExecuteRequest(task_id=task2.task_id, execution_id=task2.execution_id, workflow_name="wf", user_id="uid")
+        req2.task_desc.operation.command = task2.command
+        for s in task2.slots:
+            req2.task_desc.operation.slots.add(name=s.name, direction=s.direction)
+        for name, chan in task2.slot_assignments.items():
+            req2.task_desc.slot_assignments.add(slot_name=name, channel_id=chan)
+        t1 = time.monotonic()
+        done2 = wapi.execute_and_wait(req2, timeout=30.0)
+        assert done2.done and time.monotonic() - t1 > 0.35 and done2.created_by == "t2"
+        resp2 = M.ExecuteResponse()
+        assert done2.response.Unpack(resp2) and resp2.rc == 0 and dec(str, H.blob_get("mem://exec-1/t2/ret0")) == "y!"
         with pytest.raises(grpc.RpcError) as e:
             ops.call("Get", GetOperationRequest(operation_id="nope"), metadata=(("lzyb-wait-ms", "50"),))
         assert e.value.code() == grpc.StatusCode.NOT_FOUND

@@ -85,11 +85,13 @@ def main(n_ops: int = 8, reps: int = 5, n_workers: int = 2) -> None:
                     req.task_desc.operation.slots.add(name=name, direction=direction)
                 for name, chan in assign.items():
                     req.task_desc.slot_assignments.add(slot_name=name, channel_id=chan)
-                op_msg = wapi.call("Execute", req)
-                if POLL_S is None:  # the product's way: one Get that is answered when the task completes
+                if POLL_S is None:  # the product's way: Execute answered with the completed operation (else one waiting Get)
+                    op_msg = wapi.execute_and_wait(req, timeout=120.0)
                     if not op_msg.done:
                         polls[0] += 1
                         op_msg = ops.wait(op_msg.id)
+                else:
+                    op_msg = wapi.call("Execute", req)
                 while not op_msg.done:  # a stock client's way
                     time.sleep(POLL_S)
                     polls[0] += 1
