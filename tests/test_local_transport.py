@@ -318,3 +318,64 @@ def test_two_worker_processes_and_a_channel_manager_process(sockdir, second_work
                 p.kill()
         procs[0].terminate()
         procs[0].wait(timeout=15)
+
+
+@pytest.mark.parametrize("local", [True, False], ids=["local-sockets", "grpc-only"])
+def test_the_worker_service_itself_starts_serves_a_task_and_leaves_on_sigterm(sockdir, local):
+    """`python -m lzy_b200.grpc_api worker` (through tests/support/worker_main_twin.py: the same main, in-memory backend) next
+    to `python -m lzy_b200.grpc_api channel-manager`: the line it announces itself with, one task through WorkerApi.Execute
+    answered on completion, SIGTERM → exit code 0 and no socket left behind"""
+    import signal
+
+    from lzy_b200.api.v1.startup import ProcessingRequest
+    from lzy_b200.api.v1.utils.pickle import pickle
+    from lzy_b200.grpc_api import ChannelManagerPrivateClient, WorkerApiClient, messages as M
+
+    def forty_two() -> int:
+        return 42
+
+    cm = subprocess.Popen([sys.executable, "-m", "lzy_b200.grpc_api", "channel-manager", "--port", "0"] +
+                          (["--local-socket", f"{sockdir}/cm.sock"] if local else []), cwd=str(ROOT), stdout=subprocess.PIPE,
+                          stderr=subprocess.DEVNULL, text=True)
+    w = None
+    try:
+        cm_target = cm.stdout.readline().strip().rsplit(" ", 1)[-1]
+        port = free_port()
+        w = subprocess.Popen([sys.executable, str(ROOT / "tests/support/worker_main_twin.py"), "worker", "--gpu", "0", "--port", str(port),
+                              "--channel-manager", cm_target] +
+                             (["--channel-manager-local", f"{sockdir}/cm.sock", "--local-socket", f"{sockdir}/w0.sock"] if local else []),
+                             cwd=str(ROOT), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        line = w.stdout.readline()
+        assert line.startswith("worker for GPU 0 listening on 127.0.0.1:"), line + w.stderr.read()
+        assert line.strip().endswith(f"?gpu=0&uds={sockdir}/w0.sock" if local else "?gpu=0")
+        wapi, priv = WorkerApiClient(f"127.0.0.1:{port}"), ChannelManagerPrivateClient(cm_target)
+        wapi.call("Init", M.InitRequest(user_id="u", workflow_name="wf"))
+        assert os.path.exists(f"{sockdir}/w0.sock") == local  # the Describe socket exists once the slots server does
+
+        def channel(name):
+            sp = M.PeerDescription.StoragePeer(storage_uri=f"file://{sockdir}/{name}")
+            return priv.call("GetOrCreate", M.GetOrCreateRequest(execution_id="exec-m", workflow_name="wf", user_id="u", consumer=sp)).channel_id
+
+        request = ProcessingRequest({}, [], forty_two, [], {}, [(int, "/t/ret")], (tuple, "/t/exc"), lazy_arguments=False)
+        req = M.ExecuteRequest(task_id="t", execution_id="exec-m", workflow_name="wf", user_id="u")
+        req.task_desc.operation.command = "python -u startup.py " + pickle(request)
+        for name in ("/t/ret", "/t/exc"):
+            req.task_desc.operation.slots.add(name=name, direction=2)
+        req.task_desc.slot_assignments.add(slot_name="/t/ret", channel_id=channel("t.ret"))
+        req.task_desc.slot_assignments.add(slot_name="/t/exc", channel_id=channel("t.exc"))
+        op = wapi.execute_and_wait(req, timeout=60.0)
+        resp = M.ExecuteResponse()
+        assert op.done and op.response.Unpack(resp) and (resp.rc, resp.description) == (0, "Success")
+        assert os.path.getsize(f"{sockdir}/t.ret") > 0
+        wapi.close()
+        priv.close()
+        w.send_signal(signal.SIGTERM)
+        assert w.wait(timeout=30) == 0, w.stderr.read()[-2000:]
+        assert not os.path.exists(f"{sockdir}/w0.sock")
+        cm.send_signal(signal.SIGTERM)
+        assert cm.wait(timeout=30) == 0
+        assert not os.path.exists(f"{sockdir}/cm.sock")
+    finally:
+        for p in (w, cm):
+            if p is not None and p.poll() is None:
+                p.kill()
