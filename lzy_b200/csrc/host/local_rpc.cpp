@@ -215,6 +215,16 @@ struct Server {
                 ::close(fd);
                 break;
             }
+            // connections whose thread has finished (a client thread that went away) are reaped here: their last locked act was
+            // to mark the descriptor closed, so the join returns at once
+            for (size_t i = 0; i < conns.size();) {
+                if (conns[i]->fd < 0) {
+                    if (conns[i]->th.joinable()) conns[i]->th.join();
+                    conns.erase(conns.begin() + static_cast<long>(i));
+                } else {
+                    ++i;
+                }
+            }
             auto conn = std::make_shared<Conn>();
             conn->fd = fd;
             conns.push_back(conn);
