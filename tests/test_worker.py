@@ -236,7 +236,7 @@ def test_worker_api_over_grpc(env):
 
 
 def _slow(a: str) -> str:
-    time.sleep(0.4)
+    time.sleep(1.0)
     return a + "!"
 
 
@@ -259,14 +259,14 @@ def test_get_with_the_wait_header_is_answered_when_the_task_completes(env):
         t0 = time.monotonic()
         op = wapi.call("Execute", req)
         get = GetOperationRequest(operation_id=op.id)
-        assert not ops.call("Get", get).done and time.monotonic() - t0 < 0.3          # a stock Get never waits
+        assert not ops.call("Get", get).done and time.monotonic() - t0 < 0.8          # a stock Get never waits
         assert not ops.call("Get", get, metadata=(("lzyb-wait-ms", "50"),)).done       # a wait that expires: as it stands
         with pytest.raises(grpc.RpcError) as e:
             ops.call("Get", get, metadata=(("lzyb-wait-ms", "soon"),))
         assert e.value.code() == grpc.StatusCode.INVALID_ARGUMENT
         done = ops.wait(op.id, timeout=30.0)                                            # one call, answered on completion
         took = time.monotonic() - t0
-        assert done.done and 0.35 < took < 5.0
+        assert done.done and 0.9 < took < 10.0
         resp = M.ExecuteResponse()
         assert done.response.Unpack(resp) and (resp.rc, resp.description) == (0, "Success")
         assert dec(str, H.blob_get("mem://exec-1/t1/ret0")) == "x!"
@@ -281,7 +281,7 @@ def test_get_with_the_wait_header_is_answered_when_the_task_completes(env):
             req2.task_desc.slot_assignments.add(slot_name=name, channel_id=chan)
         t1 = time.monotonic()
         done2 = wapi.execute_and_wait(req2, timeout=30.0)
-        assert done2.done and time.monotonic() - t1 > 0.35 and done2.created_by == "t2"
+        assert done2.done and time.monotonic() - t1 > 0.9 and done2.created_by == "t2"
         resp2 = M.ExecuteResponse()
         assert done2.response.Unpack(resp2) and resp2.rc == 0 and dec(str, H.blob_get("mem://exec-1/t2/ret0")) == "y!"
         with pytest.raises(grpc.RpcError) as e:
