@@ -47,7 +47,15 @@ int main(int argc, char** argv) {
     CHECK(lzyb_cm_create(&cm));
     CHECK(lzyb_cm_seed(cm, 7));
     CHECK(lzyb_cm_pump_start(cm));
-    CHECK(lzyb_slots_create(cm, 0, "lzyb://worker-0", &slots));
+    // argv[5]: a unix socket path — Bind / TransferCompleted / Unbind of every slot then cross the box-local transport
+    // (csrc/host/local_rpc.cpp) instead of being function calls: the transport's cost per op, without Python
+    const char* socket_path = argc > 5 ? argv[5] : nullptr;
+    lzyb_handle_t via = cm;
+    if (socket_path) {
+        CHECK(lzyb_cm_serve_local(cm, socket_path));
+        CHECK(lzyb_slots_connect_cm_local(socket_path, &via));
+    }
+    CHECK(lzyb_slots_create(via, 0, "lzyb://worker-0", &slots));
     CHECK(lzyb_slots_set_republish(slots, republish ? 1 : 0));
     const char payload[256] = "x";
     using clk = std::chrono::steady_clock;
@@ -119,9 +127,14 @@ int main(int argc, char** argv) {
     }
     const double us = std::chrono::duration<double, std::micro>(clk::now() - t0).count();
     lzyb_slots_free(slots);
+    if (socket_path) {
+        lzyb_slots_disconnect_cm_local();
+        lzyb_cm_stop_local(cm);
+    }
     lzyb_cm_pump_stop(cm);
     lzyb_cm_free(cm);
-    printf("{\"steps\": %d, \"ops_per_step\": %d, \"prefetch\": %s, \"republish\": %s, \"us_per_op\": %.1f, \"live_slots\": %d}\n", steps,
+    printf("{\"matcher_calls\": \"%s\", \"steps\": %d, \"ops_per_step\": %d, \"prefetch\": %s, \"republish\": %s, \"us_per_op\": %.1f, \"live_slots\": %d}\n",
+           socket_path ? "unix socket (local_rpc.cpp)" : "in process", steps,
            n_ops, prefetch ? "true" : "false", republish ? "true" : "false", us / steps / n_ops, hostmem_live_slots());
     return 0;
 }
