@@ -124,3 +124,50 @@ def test_descriptor_size_is_checked():
     from lzy_b200.ring import exchange_descriptors
     with pytest.raises(ValueError):
         exchange_descriptors(None, b"short")
+
+
+def _leaver(rank: int, world: int, port: int, out):
+    """bench.py's sequence around the one-process legs (run_ours): the ranks learn each other's pids over a gloo HOST group,
+    meet at a host barrier, then every rank but 0 tears its process group down (bounded) and leaves while rank 0 waits for
+    their processes to be gone and goes on alone — and can still destroy its own group afterwards"""
+    import threading
+    import time
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    host_group = dist.new_group(backend="gloo")
+    pids = [None] * world
+    dist.all_gather_object(pids, os.getpid(), group=host_group)
+    dist.barrier(group=host_group)
+    if rank != 0:
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(5.0)
+        out.put((rank, pids, None))
+        if t.is_alive():
+            os._exit(0)
+        return
+    import bench
+    t0 = time.time()
+    waited = bench.wait_until_alone([p for r, p in enumerate(pids) if r != rank], timeout_s=30.0)
+    alone = all(not os.path.exists(f"/proc/{p}") or open(f"/proc/{p}/stat").read().rsplit(")", 1)[1].split()[0] in "ZX"
+                for r, p in enumerate(pids) if r != rank)
+    dist.destroy_process_group()  # the peers are gone: must not hang
+    out.put((rank, pids, (waited, alone, time.time() - t0)))
+
+
+def test_other_ranks_leave_and_rank_0_goes_on_alone():
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_leaver, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {r: (pids, extra) for r, pids, extra in (q.get(timeout=120) for _ in range(world))}
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(res[r][0] == [p.pid for p in procs] for r in range(world))  # everybody learnt everybody's pid, in rank order
+    waited, alone, total = res[0][1]
+    assert alone and waited < 25.0 and total < 40.0
